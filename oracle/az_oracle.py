@@ -1,0 +1,540 @@
+"""oracle/az_oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement (numpy + the plain-C helpers in oracle/caffe_layers.c) of the
+reference's adaptive-search hot path, written from the reference's behaviour and
+cited function by function.  All citations are relative to /root/reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's `cpu_baseline` /
+`--impl reference` legs may import this module.  The product package
+(aznet_b200/) must never import it: a product path that routes through the
+oracle voids every parity claim.
+
+Pinning: the reference has NO tests for this path, so
+the pin is the reference's own code executed in the authoring container:
+  * divide_region/_sift_dup and nms are checked against lib/utils/div.pyx and
+    lib/utils/nms.pyx compiled unmodified from /root/reference (oracle/build_ref.py
+    -> oracle/_ref/*.so) and against tests/golden/{div,nms}_*.npz made by them;
+  * _bbox_pred/_clip_boxes/_unwrap_adj_pred/_az_forward/im_propose/test_net
+    selection are checked against lib/detect/test.py (mechanically converted
+    py2->py3 into oracle/_ref/, never committed) through tests/golden/search_*.npz;
+  * the Caffe layers (ROIPooling, InnerProduct) cannot be built here (no
+    glog/gflags/boost/BLAS headers): PARITY UNPINNED for those two, the restatement
+    of Forward_cpu is the oracle (cross-checked bitwise with torchvision's CPU
+    roi_pool, which implements the same algorithm).
+"""
+from __future__ import annotations
+
+import ctypes
+import heapq
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/caffe_layers.c -> oracle/liboracle.so (gcc, no deps)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "caffe_layers.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-o", so, src, "-lm"])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        c = ctypes
+        L.azo_roi_pool_fwd.restype = c.c_int
+        L.azo_roi_pool_fwd.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int,
+                                       c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_float,
+                                       c.c_void_p, c.c_void_p]
+        L.azo_sigmoid.restype = None
+        L.azo_sigmoid.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t]
+        L.azo_softmax.restype = None
+        L.azo_softmax.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_int]
+        L.azo_nms.restype = c.c_int64
+        L.azo_nms.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_double, c.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+# --------------------------------------------------------------------------------------
+# configuration: the cfg keys the hot path reads (lib/detect/config.py:100-216)
+# --------------------------------------------------------------------------------------
+@dataclass
+class OracleCfg:
+    TEST_SCALES: tuple = (600,)          # config.py:109
+    TEST_MAX_SIZE: int = 1000            # config.py:112  (voc.yml/coco.yml: 800)
+    TEST_NMS: float = 0.5                # config.py:116
+    NUM_PROPOSALS: int = 300             # config.py:129 via cfg_set_mode('Test') :272-280
+    Tz: float = 0.5                      # injected by cfg_set_mode; no default in the reference
+    Tc: float = 0.05                     # config.py:166
+    FIXED_PROPOSAL_NUM: bool = True      # config.py:167
+    MIN_SIDE: object = 10                # config.py:183 (an int: Python-2 `/` is floor division)
+    BATCH_SIZE: int = 10000              # config.py:186 (voc.yml: 1000)
+    DEDUP_BOXES: float = 1. / 16.        # config.py:203
+    EPS: float = 1e-14                   # config.py:213
+    SPATIAL_SCALE: float = 0.0625        # models/Pascal/VGG16/az-net/test_fc.prototxt:23
+    POOLED: int = 7                      # test_fc.prototxt:21-22
+    extra: dict = field(default_factory=dict)
+
+
+# --------------------------------------------------------------------------------------
+# Caffe layers
+# --------------------------------------------------------------------------------------
+def roi_pool_fwd(feat, rois, pooled=7, spatial_scale=0.0625, want_argmax=False):
+    """caffe-fast-rcnn/src/caffe/layers/roi_pooling_layer.cpp:46-125 (see caffe_layers.c)."""
+    feat = np.ascontiguousarray(feat, dtype=np.float32)
+    rois = np.ascontiguousarray(rois, dtype=np.float32).reshape(-1, 5)
+    n, C, H, W = feat.shape
+    R = rois.shape[0]
+    out = np.empty((R, C, pooled, pooled), dtype=np.float32)
+    amax = np.empty((R, C, pooled, pooled), dtype=np.int32) if want_argmax else None
+    rc = _lib().azo_roi_pool_fwd(feat.ctypes.data, n, C, H, W, rois.ctypes.data, R, pooled, pooled,
+                                 ctypes.c_float(spatial_scale), out.ctypes.data,
+                                 amax.ctypes.data if want_argmax else None)
+    if rc != 0:
+        raise RuntimeError("roi batch index out of range (Caffe CHECK would abort)")
+    return (out, amax) if want_argmax else out
+
+
+def sigmoid(x):
+    """caffe-fast-rcnn/src/caffe/layers/sigmoid_layer.cpp:11-13."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    _lib().azo_sigmoid(x.ctypes.data, y.ctypes.data, x.size)
+    return y
+
+
+def softmax(x):
+    """caffe-fast-rcnn/src/caffe/layers/softmax_layer.cpp:28-60, rows of [R, C]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    _lib().azo_softmax(x.ctypes.data, y.ctypes.data, x.shape[0], x.shape[1])
+    return y
+
+
+def inner_product(x, w, b, threads=None):
+    """caffe-fast-rcnn/src/caffe/layers/inner_product_layer.cpp:80-93:
+    top = bottom . W^T (cblas_sgemm, util/math_functions.cpp:13-21) + 1 . b^T, fp32.
+    The BLAS is un-vendored in the reference (ATLAS|MKL|OpenBLAS, no pinned version);
+    torch-CPU sgemm (MKL) is the same class of library."""
+    import torch
+    if threads:
+        torch.set_num_threads(threads)
+    xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    wt = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+    bt = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32))
+    return torch.addmm(bt, xt, wt.t()).numpy()
+
+
+def relu(x):
+    """caffe-fast-rcnn/src/caffe/layers/relu_layer.cpp:16-19."""
+    return np.maximum(x, np.float32(0))
+
+
+class _Blob:
+    def __init__(self):
+        self.shape = ()
+
+    def reshape(self, *shape):
+        self.shape = tuple(shape)
+
+    @property
+    def num(self):
+        return self.shape[0] if self.shape else 0
+
+
+class OracleNet:
+    """Duck-typed caffe.Net (caffe-fast-rcnn/python/caffe/pycaffe.py:52-95) running the
+    fc part of AZ-Net (models/Pascal/VGG16/az-net/test_fc.prototxt:14-232) or of the
+    Fast R-CNN detector (models/*/VGG16/frcnn/test_fc.prototxt:14-145) on the CPU.
+
+    weights: dict name -> (W [N,K] f32, b [N] f32) with the prototxt layer names.
+    kind:    'az' | 'frcnn'.  A `backbone` callable (data blob -> conv5_3) turns it into the
+             'full' net; without one it is the 'fc' net whose inputs are (conv5_3, rois).
+    """
+
+    def __init__(self, weights, kind="az", backbone=None, name="oracle", cfg=None, threads=None):
+        self.w = weights
+        self.kind = kind
+        self.backbone = backbone
+        self.name = name
+        self.cfg = cfg or OracleCfg()
+        self.threads = threads
+        self.inputs = ["data", "rois"] if backbone is not None else ["conv5_3", "rois"]
+        self.outputs = ["zoom_prob", "adj_prob", "adj_bbox"] if kind == "az" else ["cls_prob", "bbox_pred"]
+        self.blobs = {k: _Blob() for k in self.inputs + ["conv5_3"]}
+        self.stats = {"pool_s": 0.0, "fc_s": 0.0}
+
+    def forward(self, blobs=None, **kwargs):
+        import time
+        if set(kwargs.keys()) != set(self.inputs):                       # pycaffe.py:83-84
+            raise Exception("Input blob arguments do not match net inputs.")
+        for k, v in kwargs.items():                                      # pycaffe.py:88-89
+            if v.shape[0] != self.blobs[k].num:
+                raise Exception("Input is not batch sized")
+        rois = kwargs["rois"]
+        conv = self.backbone(kwargs["data"]) if self.backbone is not None else kwargs["conv5_3"]
+        t0 = time.perf_counter()
+        pool5 = roi_pool_fwd(conv, rois, self.cfg.POOLED, self.cfg.SPATIAL_SCALE)
+        t1 = time.perf_counter()
+        x = pool5.reshape(pool5.shape[0], -1)            # K index = c*49 + ph*7 + pw (Q12)
+        ip = lambda name, v: inner_product(v, self.w[name][0], self.w[name][1], self.threads)
+        out = {}
+        if self.kind == "az":
+            h6 = relu(ip("int6", x))                      # dropout in TEST phase = identity
+            h71 = relu(ip("int7_1", h6))
+            h72 = relu(ip("int7_2", h6))
+            out["adj_prob"] = sigmoid(ip("adj_score", h71))
+            out["adj_bbox"] = ip("adj_bbox", h71)
+            out["zoom_prob"] = sigmoid(ip("zoom_score", h72))
+        else:
+            h6 = relu(ip("fc6", x))
+            h7 = relu(ip("fc7", h6))
+            out["cls_prob"] = softmax(ip("cls_score", h7))
+            out["bbox_pred"] = ip("bbox_pred", h7)
+        self.stats["pool_s"] += t1 - t0
+        self.stats["fc_s"] += time.perf_counter() - t1
+        for b in (blobs or []):
+            if b == "conv5_3":
+                out[b] = conv
+            elif b == "pool5":
+                out[b] = pool5
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# lib/utils/div.pyx
+# --------------------------------------------------------------------------------------
+def sift_dup(regions, min_height):
+    """lib/utils/div.pyx:78-88."""
+    regions = np.asarray(regions, dtype=np.float64).reshape(-1, 4)
+    v = np.array([1, 1e3, 1e6, 1e9], dtype=np.float64)
+    hashes = np.round(regions / min_height).dot(v)
+    _, index = np.unique(hashes, return_index=True)
+    return regions[index, :]
+
+
+def divide_region(regions, min_height=10.0):
+    """lib/utils/div.pyx:15-76: split every region into a 2 x num_long grid of
+    near-square cells plus the 1 x (num_long-1) cells offset by half a cell, then
+    _sift_dup.  Arithmetic is float64, in the operation order of :47-72."""
+    regions = np.asarray(regions, dtype=np.float64).reshape(-1, 4)
+    out = []
+    for x1, y1, x2, y2 in regions:
+        lengths = (x2 - x1 + 1.0, y2 - y1 + 1.0)                      # :32-33
+        min_ind = 0 if lengths[0] <= lengths[1] else 1                # :35 argmin, tie -> 0
+        max_ind = 1 - min_ind
+        l_short = lengths[min_ind] / 2                                # :41
+        num_long = int(lengths[max_ind] / l_short)                    # :43 (truncation)
+        l_long = lengths[max_ind] / num_long                          # :44
+        sub = np.zeros((2 * num_long + (num_long - 1), 4))            # :46-47
+        for k in range(2):
+            for j in range(num_long):
+                if min_ind == 0:                                      # width is the short side
+                    sub[k * num_long + j] = (k * l_short, j * l_long, (k + 1) * l_short, (j + 1) * l_long)
+                else:
+                    sub[k * num_long + j] = (j * l_long, k * l_short, (j + 1) * l_long, (k + 1) * l_short)
+        offset = 2 * num_long
+        h_short = l_short / 2
+        h_long = l_long / 2
+        for j in range(num_long - 1):                                 # k == 0 only (num_short-1 == 1)
+            if min_ind == 0:
+                sub[j + offset] = (h_short, j * l_long + h_long, l_short + h_short, (j + 1) * l_long + h_long)
+            else:
+                sub[j + offset] = (j * l_long + h_long, h_short, (j + 1) * l_long + h_long, l_short + h_short)
+        # the reference forms k*l_short + h_short with k == 0, i.e. 0*l_short + h_short == h_short
+        # and (k+1)*l_short + h_short == 1*l_short + h_short == l_short + h_short exactly.
+        sub[:, [0, 2]] += x1                                          # :71-72
+        sub[:, [1, 3]] += y1
+        out.append(sub)
+    regions_out = np.vstack(out) if out else np.zeros((0, 4))
+    return sift_dup(regions_out, min_height)
+
+
+# --------------------------------------------------------------------------------------
+# lib/utils/nms.pyx
+# --------------------------------------------------------------------------------------
+def nms(dets, thresh, stable_ties=True):
+    """lib/utils/nms.pyx:17-68.  `order = scores.argsort()[::-1]` (:25); with
+    stable_ties the ascending sort is the stable one, which is what the reference's
+    default introsort yields whenever scores are unique (benchmarks and goldens use
+    tie-free scores)."""
+    if not (isinstance(dets, np.ndarray) and dets.dtype == np.float32 and dets.ndim == 2):
+        raise ValueError("Buffer dtype mismatch, expected 'float32_t'")   # Cython typed buffer, :17
+    if not isinstance(thresh, float):
+        raise TypeError("Argument 'thresh' has incorrect type (expected float)")
+    n = dets.shape[0]
+    d = np.ascontiguousarray(dets)
+    scores = d[:, 4]
+    order = scores.argsort(kind="stable" if stable_ties else None)[::-1].astype(np.int64)
+    order = np.ascontiguousarray(order)
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    nk = _lib().azo_nms(d.ctypes.data, d.shape[1], n, order.ctypes.data, float(thresh), keep.ctypes.data)
+    return [int(i) for i in keep[:nk]]
+
+
+def apply_nms(all_boxes, thresh):
+    """lib/detect/test.py:467-484."""
+    num_classes = len(all_boxes)
+    num_images = len(all_boxes[0])
+    nms_boxes = [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    for c in range(num_classes):
+        for i in range(num_images):
+            dets = all_boxes[c][i]
+            if isinstance(dets, list) and dets == []:
+                continue
+            keep = nms(dets, thresh)
+            if len(keep) == 0:
+                continue
+            nms_boxes[c][i] = dets[keep, :].copy()
+    return nms_boxes
+
+
+# --------------------------------------------------------------------------------------
+# lib/detect/test.py
+# --------------------------------------------------------------------------------------
+def im_scale_for(im_shape, cfg):
+    """Scale logic of _get_image_blob, lib/detect/test.py:40-52 (one scale per TEST.SCALES)."""
+    size_min = min(im_shape[0], im_shape[1])
+    size_max = max(im_shape[0], im_shape[1])
+    scales = []
+    for target in cfg.TEST_SCALES:
+        s = float(target) / float(size_min)
+        if np.round(s * size_max) > cfg.TEST_MAX_SIZE:
+            s = float(cfg.TEST_MAX_SIZE) / float(size_max)
+        scales.append(s)
+    return np.array(scales)
+
+
+def get_rois_blob(im_rois, scales):
+    """_get_rois_blob + _project_im_rois, lib/detect/test.py:61-97 (single-scale branch :92-95;
+    the multi-scale branch :83-91 is restated too)."""
+    im_rois = np.asarray(im_rois).astype(np.float64, copy=False)
+    if len(scales) > 1:
+        widths = im_rois[:, 2] - im_rois[:, 0] + 1
+        heights = im_rois[:, 3] - im_rois[:, 1] + 1
+        areas = widths * heights
+        scaled = areas[:, None] * (scales[None, :] ** 2)
+        levels = np.abs(scaled - 224 * 224).argmin(axis=1)[:, None]
+    else:
+        levels = np.zeros((im_rois.shape[0], 1), dtype=np.int64)
+    rois = im_rois * scales[levels]
+    return np.hstack((levels, rois)).astype(np.float32, copy=False)
+
+
+def bbox_pred(boxes, box_deltas, eps=1e-14):
+    """_bbox_pred, lib/detect/test.py:106-139.  float64 except np.exp on the float32 deltas."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, box_deltas.shape[1]))
+    boxes = boxes.astype(np.float64, copy=False)
+    widths = boxes[:, 2] - boxes[:, 0] + eps
+    heights = boxes[:, 3] - boxes[:, 1] + eps
+    ctr_x = boxes[:, 0] + 0.5 * widths
+    ctr_y = boxes[:, 1] + 0.5 * heights
+    dx, dy, dw, dh = (box_deltas[:, i::4] for i in range(4))
+    pcx = dx * widths[:, None] + ctr_x[:, None]
+    pcy = dy * heights[:, None] + ctr_y[:, None]
+    pw = np.exp(dw) * widths[:, None]
+    ph = np.exp(dh) * heights[:, None]
+    pred = np.zeros(box_deltas.shape)
+    pred[:, 0::4] = pcx - 0.5 * pw
+    pred[:, 1::4] = pcy - 0.5 * ph
+    pred[:, 2::4] = pcx + 0.5 * pw
+    pred[:, 3::4] = pcy + 0.5 * ph
+    return pred
+
+
+def clip_boxes(boxes, im_shape):
+    """_clip_boxes, lib/detect/test.py:141-151 (in place)."""
+    boxes[:, 0::4] = np.maximum(boxes[:, 0::4], 0)
+    boxes[:, 1::4] = np.maximum(boxes[:, 1::4], 0)
+    boxes[:, 2::4] = np.minimum(boxes[:, 2::4], im_shape[1] - 1)
+    boxes[:, 3::4] = np.minimum(boxes[:, 3::4], im_shape[0] - 1)
+    return boxes
+
+
+def unwrap_adj_pred(boxes, scores, min_side):
+    """_unwrap_adj_pred, lib/detect/test.py:171-187."""
+    scores = scores.ravel()
+    b = np.vstack((boxes[:, 0::4].ravel(), boxes[:, 1::4].ravel(),
+                   boxes[:, 2::4].ravel(), boxes[:, 3::4].ravel())).transpose()
+    heights = b[:, 3] - b[:, 1] + 1
+    widths = b[:, 2] - b[:, 0] + 1
+    keep = np.where(np.minimum(heights, widths) >= min_side)[0]
+    return b[keep, :], scores[keep]
+
+
+def _dedup(rois_blob, dedup):
+    """lib/detect/test.py:212-218."""
+    v = np.array([1, 1e3, 1e6, 1e9, 1e12])
+    hashes = np.round(rois_blob * dedup).dot(v)
+    _, index, inv = np.unique(hashes, return_index=True, return_inverse=True)
+    return index, inv
+
+
+def az_forward(net, im_shape, all_boxes, conv, cfg, data_blob=None):
+    """_az_forward, lib/detect/test.py:189-257.  `im_shape` replaces `im` (only im.shape and
+    the image blob are used); `data_blob` is what _get_image_blob would produce for the 'full'
+    net, and is not needed once `conv` is cached."""
+    bs = cfg.BATCH_SIZE
+    nb = int(np.ceil(all_boxes.shape[0] / float(bs)))
+    z_all, a_all, c_all = np.zeros((0,)), np.zeros((0, 4)), np.zeros((0,))
+    scales = im_scale_for(im_shape, cfg)
+    for bid in range(nb):
+        boxes = all_boxes[bs * bid:min(all_boxes.shape[0], bs * (bid + 1)), 0:4]
+        rois = get_rois_blob(boxes, scales)
+        inv = None
+        if cfg.DEDUP_BOXES > 0:
+            index, inv = _dedup(rois, cfg.DEDUP_BOXES)
+            rois = rois[index, :]
+            boxes = boxes[index, :]
+        if conv is None or "fc" not in net.keys():
+            net["full"].blobs["data"].reshape(*data_blob.shape)
+            net["full"].blobs["rois"].reshape(*rois.shape)
+            out = net["full"].forward(data=data_blob.astype(np.float32, copy=False),
+                                      rois=rois.astype(np.float32, copy=False), blobs=["conv5_3"])
+            conv = {"conv5_3": out["conv5_3"]}
+        else:
+            net["fc"].blobs["conv5_3"].reshape(*conv["conv5_3"].shape)
+            net["fc"].blobs["rois"].reshape(*rois.shape)
+            out = net["fc"].forward(rois=rois.astype(np.float32, copy=False), conv5_3=conv["conv5_3"])
+        z = out["zoom_prob"]
+        scores = out["adj_prob"]
+        pred = clip_boxes(bbox_pred(boxes, out["adj_bbox"], cfg.EPS), im_shape)
+        if cfg.DEDUP_BOXES > 0:
+            scores = scores[inv, :]
+            pred = pred[inv, :]
+            z = z[inv].ravel()
+        else:
+            z = z.ravel()
+        a, c = unwrap_adj_pred(pred, scores, cfg.MIN_SIDE)
+        z_all = np.hstack((z_all, z))
+        a_all = np.vstack((a_all, a))
+        c_all = np.hstack((c_all, c))
+    return z_all, a_all, c_all, conv
+
+
+def search_depth(im_shape, cfg):
+    """K of lib/detect/test.py:363-368.  `side/cfg.SEAR.MIN_SIDE` is Python-2 division:
+    floor division when MIN_SIDE is an int."""
+    side = int(min(im_shape[0], im_shape[1]))
+    q = side // cfg.MIN_SIDE if isinstance(cfg.MIN_SIDE, (int, np.integer)) else side / cfg.MIN_SIDE
+    return int(np.log2(q) + 1.0)
+
+
+def im_propose(net, im_shape, cfg, conv=None, data_blob=None, num_proposals=None, return_scores=False,
+               trace=None):
+    """im_propose, lib/detect/test.py:346-414 (APPEND_BOXES branch :404-406 omitted: off by
+    default, config.py:170).  Returns Y [n,4] float64 (and the matching scores / a per-level
+    trace for the parity tests)."""
+    B = np.array([[0, 0, im_shape[1] - 1.0, im_shape[0] - 1.0]])
+    Y = np.zeros((0, 4))
+    a_scores = np.zeros((0,))
+    num_eval = 0
+    K = search_depth(im_shape, cfg)
+    k = 0
+    for k in range(1, K):
+        zoom, boxes, c, conv = az_forward(net, im_shape, B, conv, cfg, data_blob)
+        num_eval += B.shape[0]
+        Y = np.vstack((Y, boxes))
+        a_scores = np.hstack((a_scores, c))
+        if k == 1:
+            zoom[0] = 1.0
+        ind_z = np.where(zoom >= cfg.Tz)[0]
+        if trace is not None:
+            trace.append({"B": B.copy(), "zoom": zoom.copy(), "n_boxes": boxes.shape[0]})
+        Z = B[ind_z, :]
+        if Z.shape[0] == 0:
+            break
+        B = divide_region(Z, float(cfg.MIN_SIDE))
+    if (not cfg.FIXED_PROPOSAL_NUM) and num_proposals is None:
+        ind_a = np.where(a_scores >= cfg.Tc)[0]
+    else:
+        if num_proposals is None:
+            num_proposals = cfg.NUM_PROPOSALS
+        ind_a = np.argsort(-a_scores, kind="stable")[:min(num_proposals, Y.shape[0])]
+    info = {"num_eval": num_eval, "depth": k, "Y_all": Y, "scores_all": a_scores}
+    Y = Y[ind_a, :]
+    if return_scores:
+        return Y, a_scores[ind_a], info
+    return Y
+
+
+def frcnn_forward(net, im_shape, all_boxes, num_classes, conv, cfg, data_blob=None):
+    """_frcnn_forward, lib/detect/test.py:259-318."""
+    bs = cfg.BATCH_SIZE
+    nb = int(np.ceil(all_boxes.shape[0] / float(bs)))
+    all_pred = np.zeros((0, 4 * num_classes))
+    all_scores = np.zeros((0, num_classes))
+    scales = im_scale_for(im_shape, cfg)
+    for bid in range(nb):
+        boxes = all_boxes[bs * bid:min(all_boxes.shape[0], bs * (bid + 1)), 0:4]
+        rois = get_rois_blob(boxes, scales)
+        inv = None
+        if cfg.DEDUP_BOXES > 0:
+            index, inv = _dedup(rois, cfg.DEDUP_BOXES)
+            rois = rois[index, :]
+            boxes = boxes[index, :]
+        if conv is None or "fc" not in net.keys():
+            net["full"].blobs["data"].reshape(*data_blob.shape)
+            net["full"].blobs["rois"].reshape(*rois.shape)
+            out = net["full"].forward(data=data_blob.astype(np.float32, copy=False),
+                                      rois=rois.astype(np.float32, copy=False), blobs=["conv5_3"])
+            conv = {"conv5_3": out["conv5_3"]}
+        else:
+            net["fc"].blobs["conv5_3"].reshape(*conv["conv5_3"].shape)
+            net["fc"].blobs["rois"].reshape(*rois.shape)
+            out = net["fc"].forward(rois=rois.astype(np.float32, copy=False), conv5_3=conv["conv5_3"])
+        scores = out["cls_prob"]
+        pred = clip_boxes(bbox_pred(boxes, out["bbox_pred"], cfg.EPS), im_shape)
+        if cfg.DEDUP_BOXES > 0:
+            scores = scores[inv, :]
+            pred = pred[inv, :]
+        all_scores = np.vstack((all_scores, scores))
+        all_pred = np.vstack((all_pred, pred))
+    return all_scores, all_pred, conv
+
+
+def test_net_select(per_image, num_classes, max_per_image=100):
+    """Per-class selection of test_net, lib/detect/test.py:549-651.
+    per_image: list of (scores [R,C], boxes [R,4C]) or None for images without proposals.
+    Returns (all_boxes[cls][img] float32 [n,5] | [], thresh [C])."""
+    num_images = len(per_image)
+    max_per_set = 800 // (num_classes - 1) * num_images               # :551 Python-2 int division
+    thresh = -np.inf * np.ones(num_classes)
+    top_scores = [[] for _ in range(num_classes)]
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    for i, item in enumerate(per_image):
+        if item is None:
+            continue
+        scores, boxes = item
+        for j in range(1, num_classes):
+            inds = np.where(scores[:, j] > thresh[j])[0]
+            cls_scores = scores[inds, j]
+            cls_boxes = boxes[inds, j * 4:(j + 1) * 4]
+            top = np.argsort(-cls_scores, kind="stable")[:max_per_image]
+            cls_scores = cls_scores[top]
+            cls_boxes = cls_boxes[top, :]
+            for val in cls_scores:
+                heapq.heappush(top_scores[j], val)
+            if len(top_scores[j]) > max_per_set:
+                while len(top_scores[j]) > max_per_set:
+                    heapq.heappop(top_scores[j])
+                thresh[j] = top_scores[j][0]
+            all_boxes[j][i] = np.hstack((cls_boxes, cls_scores[:, None])).astype(np.float32, copy=False)
+    for j in range(1, num_classes):
+        for i, item in enumerate(per_image):
+            if item is None:
+                continue
+            inds = np.where(all_boxes[j][i][:, -1] > thresh[j])[0]
+            all_boxes[j][i] = all_boxes[j][i][inds, :]
+    return all_boxes, thresh

@@ -1,0 +1,178 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE.  Run in the authoring container only.
+
+Generates tests/golden/*.npz by executing the REFERENCE'S OWN CODE on seeded inputs:
+  * lib/utils/div.pyx / nms.pyx compiled unmodified (oracle/build_ref.py),
+  * lib/detect/test.py converted py2->py3 in oracle/_ref/pyref (never committed), driven with
+    aznet_b200.synth.HashNet (integer-hash net outputs, bit-reproducible on any machine).
+The fixtures store inputs' seeds + the reference's outputs; tests/ compare the oracle
+restatement (CPU suite) and the CUDA path (gpu suite) against them.
+
+    python oracle/gen_golden.py        # rewrites tests/golden/
+"""
+from __future__ import annotations
+
+import io
+import os
+import sys
+import types
+import contextlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import build_ref  # noqa: E402
+from aznet_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    """Import the converted lib/detect/test.py with the compiled Cython modules behind it."""
+    assert build_ref.build(), "/root/reference is required to generate goldens"
+    div, nms, bbox = build_ref.import_ref_cython()
+    pyref = os.path.join(build_ref.OUT, "pyref")
+    # py3/NumPy-2 compatibility edits that keep Python-2 semantics:
+    p = os.path.join(pyref, "detect", "test.py")
+    s = open(p).read()
+    s = s.replace("max_per_set = 800 / (imdb.num_classes - 1)", "max_per_set = 800 // (imdb.num_classes - 1)")
+    s = s.replace("if dets == []:", "if isinstance(dets, list) and dets == []:")
+    open(p, "w").write(s)
+
+    class EasyDict(dict):                      # 20-line stand-in for the absent `easydict`
+        def __init__(self, d=None, **kw):
+            super().__init__()
+            for k, v in dict(d or {}, **kw).items():
+                self[k] = v
+
+        def __setitem__(self, k, v):
+            if isinstance(v, dict) and not isinstance(v, EasyDict):
+                v = EasyDict(v)
+            super().__setitem__(k, v)
+
+        __setattr__ = __setitem__
+
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    ed = types.ModuleType("easydict")
+    ed.EasyDict = EasyDict
+    sys.modules["easydict"] = ed
+    sys.modules["caffe"] = types.ModuleType("caffe")
+    sys.path.insert(0, pyref)
+    import utils  # noqa  (pyref/utils)
+    sys.modules["utils.cython_nms"] = nms
+    sys.modules["utils.cython_bbox"] = bbox
+    sys.modules["utils.cython_div"] = div
+    utils.cython_nms, utils.cython_bbox, utils.cython_div = nms, bbox, div
+    import detect.test as rtest
+    import detect.config as rconfig
+    return rtest, rconfig, div, nms
+
+
+def gen_div(div):
+    rng = np.random.default_rng(21)
+    cases = {}
+    cases["root_600x1000"] = np.array([[0, 0, 999, 599.]])
+    cases["root_375x500"] = np.array([[0, 0, 499, 374.]])
+    cases["square"] = np.array([[10, 20, 109, 119.]])
+    cases["tall"] = np.array([[5, 5, 24, 204.]])
+    b = synth.make_boxes(200, 600, 1000, seed=5, lo=12, hi=500)
+    cases["random200"] = b
+    cases["dups"] = np.vstack([b[:20], b[:20] + 0.4, b[:20]])
+    # full-zoom cascade from the 600x1000 root: levels 1..5 (sizes 1, 8, 32, 134, 564)
+    lv = cases["root_600x1000"]
+    out = {}
+    for name, r in cases.items():
+        out["in_" + name] = r
+        out["out_" + name] = div.divide_region(np.ascontiguousarray(r, dtype=np.float64), 10.0)
+    sizes = [1]
+    for k in range(4):
+        lv = div.divide_region(lv, 10.0)
+        sizes.append(lv.shape[0])
+        out["cascade_%d" % (k + 2)] = lv
+    out["cascade_sizes"] = np.array(sizes)
+    out["sift_in"] = np.round(rng.uniform(0, 300, (500, 4)), 1)
+    out["sift_out"] = div._sift_dup(out["sift_in"], 10.0)
+    np.savez_compressed(os.path.join(GOLD, "div.npz"), **out)
+    print("div: cascade sizes", sizes)
+
+
+def gen_nms(nms):
+    out = {}
+    for n in (1, 2, 17, 300, 2000):
+        dets = synth.make_dets(n, seed=3)
+        for th in (0.3, 0.5, 0.7):
+            keep = nms.nms(dets, th)
+            out["keep_n%d_t%d" % (n, int(th * 10))] = np.array(keep, dtype=np.int64)
+    # boxes engineered so that some IoUs land exactly on the threshold (suppress iff ovr >= thresh)
+    d = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 4, 0.8], [0, 5, 9, 9, 0.7], [20, 20, 29, 29, 0.6],
+                  [20, 20, 29, 24, 0.5]], dtype=np.float32)
+    out["edge_dets"] = d
+    out["edge_keep_t5"] = np.array(nms.nms(d, 0.5), dtype=np.int64)
+    out["edge_keep_t51"] = np.array(nms.nms(d, 0.51), dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "nms.npz"), **out)
+    print("nms: n2000 keeps", [len(out["keep_n2000_t%d" % t]) for t in (3, 5, 7)])
+
+
+def gen_search(rtest, rconfig):
+    """Reference im_propose (lib/detect/test.py:346-414) + HashNet on several image shapes/configs."""
+    cfg = rconfig.cfg
+    out = {}
+    cases = [
+        # name, (H, W), MAX_SIZE, BATCH_SIZE, Tz, zoom_rate, num_proposals, fixed
+        ("d0_600x1000", (600, 1000), 1000, 10000, 0.5, 0.5, 300, True),
+        ("voc_600x1000", (600, 1000), 800, 1000, 0.5, 0.4, 300, True),
+        ("fullzoom_600x1000", (600, 1000), 1000, 10000, 0.0, 0.5, 2000, True),
+        ("small_375x500", (375, 500), 1000, 10000, 0.5, 0.6, 300, True),
+        ("chunked_480x640", (480, 640), 800, 50, 0.0, 0.5, 300, True),
+        ("tc_thresh_333x500", (333, 500), 1000, 10000, 0.5, 0.5, None, False),
+        ("nozoom_600x1000", (600, 1000), 1000, 10000, 0.999, 0.0, 300, True),
+    ]
+    for name, shape, max_size, bs, tz, rate, nprop, fixed in cases:
+        cfg.TEST.MAX_SIZE = max_size
+        cfg.SEAR.BATCH_SIZE = bs
+        cfg.SEAR.FIXED_PROPOSAL_NUM = fixed
+        rconfig.cfg_set_mode("Test", tz)
+        if nprop is not None:
+            cfg.SEAR.NUM_PROPOSALS = nprop
+        net = synth.HashNet(seed=11, zoom_rate=rate)
+        im = np.zeros(shape + (3,), dtype=np.uint8)
+        conv = {"conv5_3": np.zeros((1, 1, 2, 2), np.float32)}
+        # the reference computes `conv` at level 1 through net['full']; HashNet ignores the image, so
+        # 'full' and 'fc' are the same object and the image blob path (cv2.resize) still runs.
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            Y = rtest.im_propose({"full": net, "fc": net}, im)
+        line = buf.getvalue().strip()
+        out[name + "_Y"] = Y
+        out[name + "_log"] = np.array(line)
+        out[name + "_cfg"] = np.array([shape[0], shape[1], max_size, bs, tz, rate, -1 if nprop is None else nprop,
+                                       int(fixed)], dtype=np.float64)
+        print("search:", name, line)
+    # component vectors
+    rng = np.random.default_rng(9)
+    boxes = synth.make_boxes(64, 600, 1000, seed=8)
+    deltas = (rng.standard_normal((64, 44)) * 0.3).astype(np.float32)
+    pred = rtest._bbox_pred(boxes, deltas)
+    out["bbox_boxes"], out["bbox_deltas"], out["bbox_pred"] = boxes, deltas, pred.copy()
+    out["bbox_clip"] = rtest._clip_boxes(pred.copy(), (600, 1000, 3))
+    scores = rng.uniform(0, 1, (64, 11)).astype(np.float32)
+    a, c = rtest._unwrap_adj_pred(out["bbox_clip"], scores)
+    out["unwrap_scores_in"], out["unwrap_boxes"], out["unwrap_scores"] = scores, a, c
+    np.savez_compressed(os.path.join(GOLD, "search.npz"), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    rtest, rconfig, div, nms = load_reference()
+    gen_div(div)
+    gen_nms(nms)
+    gen_search(rtest, rconfig)
+
+
+if __name__ == "__main__":
+    main()
