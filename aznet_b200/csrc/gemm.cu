@@ -1,0 +1,506 @@
+// Fully connected layers of the AZ-Net / Fast R-CNN heads on the 5th-generation tensor cores.
+//
+//   out[M, N] = act(A[M, K] . W[N, K]^T + bias[N])        A, W bf16 (K-major), fp32 accumulate
+//
+// replaces InnerProductLayer::Forward (caffe-fast-rcnn/src/caffe/layers/inner_product_layer.cpp:80-93:
+// one cblas/cublas sgemm for the product, a second rank-1 sgemm for the bias) and the ReLU / Sigmoid
+// layers that follow it in models/Pascal/VGG16/az-net/test_fc.prototxt:26-232.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of a 128x64 A box and a BLOCK_Nx64 W box
+//               (128-byte swizzle) into a STAGES-deep shared-memory ring, completion on mbarriers.
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1
+//               .kind::f16 (UMMA 128 x BLOCK_N x 16, bf16 in, fp32 accumulate) straight from the
+//               swizzled shared tiles through UMMA smem descriptors; tcgen05.commit releases the
+//               ring slot / publishes the accumulator.
+//   warps 2-5   epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row per thread),
+//               bias + ReLU / sigmoid, 16-byte stores.  Two accumulator buffers in TMEM
+//               (2 x BLOCK_N columns) let the epilogue of tile i overlap the main loop of tile i+1.
+// Scheduling is decided ON THE DEVICE from the live row count (the search keeps its region counts
+// in HBM): tiles = ceil(m_live/128) x ceil(N/BLOCK_N); when that is smaller than the grid the K
+// loop is split across CTAs (weight-streaming regime of the shallow search levels), partial sums
+// go to a fixed 148-slot fp32 workspace and fc_splitk_finish_kernel reduces them in split order
+// (deterministic, no atomics) and applies the epilogue.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_SPLIT = 32;
+
+template <int BLOCK_N> struct Cfg {
+    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c_inner, int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 bytes, 8-row groups
+// 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// UMMA instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Sched {
+    int m_live, m_tiles, n_tiles, tiles, split, units, kblocks;
+};
+__device__ __forceinline__ Sched make_sched(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int grid) {
+    Sched s;
+    s.m_live = m_live_ptr ? min(max(*m_live_ptr, 0), M_cap) : M_cap;
+    s.m_tiles = (s.m_live + BLOCK_M - 1) / BLOCK_M;
+    s.n_tiles = (N + block_n - 1) / block_n;
+    s.tiles = s.m_tiles * s.n_tiles;
+    s.kblocks = K / BLOCK_K;
+    s.split = 1;
+    if (s.tiles > 0 && s.tiles * 2 <= grid) {
+        s.split = grid / s.tiles;
+        if (s.split > s.kblocks) s.split = s.kblocks;
+        if (s.split > MAX_SPLIT) s.split = MAX_SPLIT;
+        if (s.split < 1) s.split = 1;
+    }
+    s.units = s.tiles * s.split;
+    return s;
+}
+
+__device__ __forceinline__ float sigmoid_caffe(float x) {
+    // sigmoid_layer.cpp:11-13: exp in float, `1. / (1. + e)` in double, rounded to float
+    return (float)(1.0 / (1.0 + (double)expf(-x)));
+}
+// AZN_ACT_AZ_HEAD: columns are [adj_score (nsub) | adj_bbox (4*nsub) | zoom_score (1)]; the two score
+// groups go through the Sigmoid layers adj_prob / zoom_prob (test_fc.prototxt:221-232).
+__device__ __forceinline__ float apply_act(float v, int act, int col, int nsub) {
+    if (act == AZN_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == AZN_ACT_AZ_HEAD) return (col < nsub || col == 5 * nsub) ? sigmoid_caffe(v) : v;
+    return v;
+}
+
+struct EpiParams {
+    const float *bias;
+    void *out;
+    int out_dtype, ldo, N, act, act_aux;
+    float *ws;           // split-K partials: [unit][BLOCK_M][BLOCK_N] fp32
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, EpiParams ep) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + C::STAGES * C::A_BYTES;
+    uint64_t *bars = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *tmem_full = bars + 2 * C::STAGES, *tmem_empty = bars + 2 * C::STAGES + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Sched sc = make_sched(m_live_ptr, M_cap, N, K, BLOCK_N, gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < sc.units; u += gridDim.x) {
+                const int tile = u % sc.tiles, ks = u / sc.tiles;
+                const int m_tile = tile / sc.n_tiles, n_tile = tile % sc.n_tiles;
+                const int kb0 = (int)((long)sc.kblocks * ks / sc.split), kb1 = (int)((long)sc.kblocks * (ks + 1) / sc.split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                    tma_load_2d(smem_a + s * C::A_BYTES, &tmap_a, &full[s], kb * BLOCK_K, m_tile * BLOCK_M);
+                    tma_load_2d(smem_b + s * C::B_BYTES, &tmap_w, &full[s], kb * BLOCK_K, n_tile * BLOCK_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N);
+            uint32_t it = 0, ut = 0;
+            for (int u = blockIdx.x; u < sc.units; u += gridDim.x, ++ut) {
+                const int ks = u / sc.tiles;
+                const int kb0 = (int)((long)sc.kblocks * ks / sc.split), kb1 = (int)((long)sc.kblocks * (ks + 1) / sc.split);
+                const int a = ut & 1;
+                const uint32_t aph = (ut >> 1) & 1;
+                mbar_wait(&tmem_empty[a], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(a * BLOCK_N);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_smem_desc(smem_u32(smem_a + s * C::A_BYTES));
+                    const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + s * C::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
+                }
+                umma_commit(&tmem_full[a]);          // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+        uint32_t ut = 0;
+        for (int u = blockIdx.x; u < sc.units; u += gridDim.x, ++ut) {
+            const int tile = u % sc.tiles;
+            const int m_tile = tile / sc.n_tiles, n_tile = tile % sc.n_tiles;
+            const int a = ut & 1;
+            const uint32_t aph = (ut >> 1) & 1;
+            mbar_wait(&tmem_full[a], aph);
+            tc_fence_after();
+            const int row = m_tile * BLOCK_M + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BLOCK_N);
+            const bool row_ok = row < sc.m_live;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = n_tile * BLOCK_N + c * 32;
+                if (sc.split > 1) {
+                    float *dst = ep.ws + ((size_t)u * BLOCK_M + (q * 32 + lane)) * BLOCK_N + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *(uint4 *)(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                } else if (row_ok && col0 < ep.N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        const float b = col < ep.N ? __ldg(ep.bias + col) : 0.f;
+                        v[j] = apply_act(__uint_as_float(r[j]) + b, ep.act, col, ep.act_aux);
+                    }
+                    if (ep.out_dtype == AZN_DTYPE_BF16) {
+                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0;
+                        if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint32_t p[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                                    p[t] = *(uint32_t *)&h;
+                                }
+                                *(uint4 *)(dst + j) = make_uint4(p[0], p[1], p[2], p[3]);
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < ep.N) dst[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    } else {
+                        float *dst = (float *)ep.out + (size_t)row * ep.ldo + col0;
+                        if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < ep.N) dst[j] = v[j];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// Reduces the split-K partials in split order and applies bias + activation.
+__global__ void __launch_bounds__(256)
+fc_splitk_finish_kernel(const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, int block_n, int grid_gemm,
+                        EpiParams ep) {
+    const Sched sc = make_sched(m_live_ptr, M_cap, N, K, block_n, grid_gemm);
+    if (sc.split <= 1) return;
+    const long total = (long)sc.m_live * N;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int row = (int)(e / N), col = (int)(e - (long)row * N);
+        const int m_tile = row / BLOCK_M, n_tile = col / block_n;
+        const int tile = m_tile * sc.n_tiles + n_tile;
+        const size_t inner = (size_t)(row - m_tile * BLOCK_M) * block_n + (col - n_tile * block_n);
+        float acc = 0.f;
+        for (int ks = 0; ks < sc.split; ++ks) {
+            const int u = ks * sc.tiles + tile;
+            acc += ep.ws[(size_t)u * BLOCK_M * block_n + inner];
+        }
+        const float v = apply_act(acc + ep.bias[col], ep.act, col, ep.act_aux);
+        if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(v);
+        else ((float *)ep.out)[(size_t)row * ep.ldo + col] = v;
+    }
+}
+
+// Row softmax over the first `ncls` columns of a f32 [M, ld] matrix, in place
+// (softmax_layer.cpp:28-60: max-subtract, exp, sum, divide).  One warp per row.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float *__restrict__ x, const int32_t *__restrict__ m_live_ptr, int M_cap, int ld, int ncls) {
+    const int m = m_live_ptr ? min(max(*m_live_ptr, 0), M_cap) : M_cap;
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < m; row += gridDim.x * (blockDim.x >> 5)) {
+        float *r = x + (size_t)row * ld;
+        float mx = -INFINITY;
+        for (int j = lane; j < ncls; j += 32) mx = fmaxf(mx, r[j]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        float s = 0.f;
+        for (int j = lane; j < ncls; j += 32) { float e = expf(r[j] - mx); r[j] = e; s += e; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        for (int j = lane; j < ncls; j += 32) r[j] = __fdiv_rn(r[j], s);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+struct MapKey {
+    const void *ptr;
+    int rows, cols, box_rows;
+    bool operator==(const MapKey &o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const {
+        return std::hash<const void *>()(k.ptr) ^ ((size_t)k.rows * 1315423911u) ^ ((size_t)k.cols << 20) ^ (size_t)k.box_rows;
+    }
+};
+
+// bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle, zero OOB fill.
+int make_tmap(const void *ptr, int rows, int cols, int box_rows, CUtensorMap *out) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key{ptr, rows, cols, box_rows};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return AZN_OK; }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { azn_set_error("cuTensorMapEncodeTiled entry point not found"); return AZN_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { azn_set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box_rows=%d", (int)r, rows, cols, box_rows); return AZN_ERR_CUDA; }
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return AZN_OK;
+}
+
+int pick_block_n(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+
+template <int BLOCK_N>
+int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_live, int M_cap, int N, int K,
+                const EpiParams &ep, int grid, cudaStream_t s) {
+    using C = Cfg<BLOCK_N>;
+    static bool attr = false;
+    if (!attr) {
+        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr = true;
+    }
+    fc_gemm_kernel<BLOCK_N><<<grid, GEMM_THREADS, C::SMEM_BYTES, s>>>(ta, tw, m_live, M_cap, N, K, ep);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+}  // namespace
+
+extern "C" size_t azn_fc_workspace_bytes(int M_cap, int N, int K) {
+    (void)M_cap; (void)K;
+    // split-K only engages when tiles*split <= grid, so `grid` slots of one 128 x BLOCK_N fp32 tile suffice
+    return (size_t)azn_num_sms() * BLOCK_M * pick_block_n(N) * sizeof(float);
+}
+
+extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype, int ldo,
+                              int M_cap, const int32_t *m_live, int N, int K, int act, int act_aux, void *workspace,
+                              size_t workspace_bytes, azn_stream_t stream) {
+    AZN_REQUIRE(A && W && bias && out, "azn_fc_forward: null pointer");
+    AZN_REQUIRE(M_cap > 0 && N > 0 && K > 0, "azn_fc_forward: bad shape M=%d N=%d K=%d", M_cap, N, K);
+    AZN_REQUIRE(K % BLOCK_K == 0, "azn_fc_forward: K=%d must be a multiple of %d", K, BLOCK_K);
+    AZN_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "azn_fc_forward: A and W must be 16-byte aligned");
+    AZN_REQUIRE(out_dtype == AZN_DTYPE_F32 || out_dtype == AZN_DTYPE_BF16, "azn_fc_forward: bad out dtype");
+    AZN_REQUIRE(ldo >= N, "azn_fc_forward: ldo=%d < N=%d", ldo, N);
+    AZN_REQUIRE(act >= AZN_ACT_NONE && act <= AZN_ACT_SOFTMAX_BBOX, "azn_fc_forward: bad activation %d", act);
+    AZN_REQUIRE(act != AZN_ACT_AZ_HEAD || (act_aux > 0 && 5 * act_aux + 1 <= N), "azn_fc_forward: AZ head needs act_aux = nsub with 5*nsub+1 <= N");
+    AZN_REQUIRE(act != AZN_ACT_SOFTMAX_BBOX || (out_dtype == AZN_DTYPE_F32 && act_aux > 0 && act_aux <= N),
+                "azn_fc_forward: softmax needs f32 output and 0 < classes <= N");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int bn = pick_block_n(N);
+    const int grid = azn_num_sms();
+    const size_t need = (size_t)grid * BLOCK_M * bn * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+        azn_set_error("azn_fc_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+        return AZN_ERR_CAPACITY;
+    }
+    CUtensorMap ta, tw;
+    int rc = make_tmap(A, M_cap, K, BLOCK_M, &ta);
+    if (rc) return rc;
+    rc = make_tmap(W, N, K, bn, &tw);
+    if (rc) return rc;
+    EpiParams ep;
+    ep.bias = bias; ep.out = out; ep.out_dtype = out_dtype; ep.ldo = ldo; ep.N = N;
+    ep.act = act == AZN_ACT_SOFTMAX_BBOX ? AZN_ACT_NONE : act;
+    ep.act_aux = act_aux;
+    ep.ws = (float *)workspace;
+    if (bn == 256) rc = launch_gemm<256>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    else if (bn == 128) rc = launch_gemm<128>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    else rc = launch_gemm<64>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    if (rc) return rc;
+    // split-K is decided on the device; the finish kernel returns immediately when split == 1
+    if ((long)((M_cap + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn) * 2 <= grid || m_live != nullptr) {
+        fc_splitk_finish_kernel<<<grid * 2, 256, 0, s>>>(m_live, M_cap, N, K, bn, grid, ep);
+        AZN_LAUNCH_CHECK();
+    }
+    if (act == AZN_ACT_SOFTMAX_BBOX) {
+        softmax_rows_kernel<<<grid, 256, 0, s>>>((float *)out, m_live, M_cap, ldo, act_aux);
+        AZN_LAUNCH_CHECK();
+    }
+    return AZN_OK;
+}

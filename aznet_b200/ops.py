@@ -1,0 +1,142 @@
+"""Torch-tensor front end of the C ABI (include/aznet_b200.h).
+
+PyTorch is used for device memory and streams only; every function here ends in exactly one
+call into libaznet_b200.so on torch's current stream.  Nothing falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("aznet_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_scale: float = 0.0625,
+             layout: str = "NCHW", n_rois: torch.Tensor | None = None, want_argmax: bool = False,
+             out: torch.Tensor | None = None):
+    """ROI max pooling (roi_pooling_layer.cpp:46-125).  feat [n,C,H,W] (NCHW) or [n,H,W,C] (NHWC),
+    f32 or bf16; rois f32 [R,5].  Returns pooled [R,C,P,P] (NCHW) or [R,P,P,C] (NHWC)."""
+    _need_cuda(feat, rois, n_rois)
+    assert feat.is_contiguous() and rois.is_contiguous() and rois.dtype == torch.float32
+    if layout == "NCHW":
+        n, Cc, H, W = feat.shape
+    else:
+        n, H, W, Cc = feat.shape
+    R = rois.shape[0]
+    dt = {torch.float32: L.DTYPE_F32, torch.bfloat16: L.DTYPE_BF16}[feat.dtype]
+    shape = (R, Cc, pooled, pooled) if layout == "NCHW" else (R, pooled, pooled, Cc)
+    if out is None:
+        out = torch.empty(shape, dtype=feat.dtype, device=feat.device)
+    amax = torch.empty(shape, dtype=torch.int32, device=feat.device) if want_argmax else None
+    L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, L.LAYOUT_NCHW if layout == "NCHW" else L.LAYOUT_NHWC,
+                                     dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled, spatial_scale, _ptr(out),
+                                     _ptr(amax), _stream()), "azn_roi_pool_fwd")
+    return (out, amax) if want_argmax else out
+
+
+def nchw_to_nhwc_bf16(src: torch.Tensor, out: torch.Tensor | None = None):
+    _need_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    n, Cc, H, W = src.shape
+    if out is None:
+        out = torch.empty((n, H, W, Cc), dtype=torch.bfloat16, device=src.device)
+    L.check(L.lib().azn_nchw_f32_to_nhwc_bf16(_ptr(src), n, Cc, H, W, _ptr(out), _stream()), "azn_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+_WS = {}
+
+
+def fc_workspace(device, N):
+    """The fixed split-K workspace (one 128 x BLOCK_N fp32 tile per SM), cached per device."""
+    nbytes = L.lib().azn_fc_workspace_bytes(1, int(N), 64)
+    key = (device, nbytes)
+    if key not in _WS:
+        _WS[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return _WS[key]
+
+
+def fc_forward(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, act: int = L.ACT_NONE, act_aux: int = 0,
+               out_dtype=torch.bfloat16, m_live: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    """out = act(A . W^T + bias) on the tensor cores (inner_product_layer.cpp:80-93).  A bf16 [M,K],
+    W bf16 [N,K], bias f32 [N]."""
+    _need_cuda(A, W, bias, m_live)
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert A.is_contiguous() and W.is_contiguous() and A.shape[1] == W.shape[1]
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    ws = fc_workspace(A.device, N)
+    od = {torch.float32: L.DTYPE_F32, torch.bfloat16: L.DTYPE_BF16}[out.dtype]
+    L.check(L.lib().azn_fc_forward(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), od, out.stride(0), M, _ptr(m_live), N, K,
+                                   act, act_aux, _ptr(ws), ws.numel(), _stream()), "azn_fc_forward")
+    return out
+
+
+def nms(dets: torch.Tensor, thresh: float):
+    """Greedy NMS (lib/utils/nms.pyx:17-68) on a CUDA f32 [n,5] tensor.  Returns (keep int64 [n],
+    count int32 [1]) on the device; keep[:count] are the kept indices in descending score order."""
+    _need_cuda(dets)
+    assert dets.dtype == torch.float32 and dets.dim() == 2 and dets.shape[1] == 5 and dets.is_contiguous()
+    n = dets.shape[0]
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=dets.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dets.device)
+    nbytes = L.lib().azn_nms_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dets.device)
+    L.check(L.lib().azn_nms(_ptr(dets), n, float(thresh), _ptr(keep), _ptr(cnt), _ptr(ws), nbytes, _stream()), "azn_nms")
+    return keep, cnt
+
+
+def nms_batched(dets: torch.Tensor, seg_off: torch.Tensor, thresh: float):
+    """Independent NMS problems in one launch.  dets f32 [T,5], seg_off int32 [S+1] (device).
+    Returns (keep int64 [T] segment-local indices at seg_off[s], counts int32 [S])."""
+    _need_cuda(dets, seg_off)
+    assert dets.dtype == torch.float32 and seg_off.dtype == torch.int32 and dets.is_contiguous()
+    S = seg_off.numel() - 1
+    keep = torch.empty(max(dets.shape[0], 1), dtype=torch.int64, device=dets.device)
+    cnt = torch.zeros(max(S, 1), dtype=torch.int32, device=dets.device)
+    L.check(L.lib().azn_nms_batched(_ptr(dets), _ptr(seg_off), S, float(thresh), _ptr(keep), _ptr(cnt), _stream()),
+            "azn_nms_batched")
+    return keep, cnt[:S]
+
+
+def divide_region(regions: torch.Tensor, min_side: float, sift_only: bool = False):
+    """divide_region + _sift_dup (lib/utils/div.pyx:15-88) for one region set, f64 [n,4] on the device.
+    Returns (out f64 [cap,4], count int32 [1])."""
+    _need_cuda(regions)
+    assert regions.dtype == torch.float64 and regions.is_contiguous()
+    n = regions.shape[0]
+    cap = max(n * 16 + 64, 1)
+    out = torch.empty((cap, 4), dtype=torch.float64, device=regions.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=regions.device)
+    nbytes = L.lib().azn_divide_region_scratch_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=regions.device)
+    L.check(L.lib().azn_divide_region(_ptr(regions), n, float(min_side), _ptr(out), _ptr(cnt), cap, int(sift_only),
+                                      _ptr(ws), nbytes, _stream()), "azn_divide_region")
+    return out, cnt
+
+
+def decode_boxes(boxes: torch.Tensor, deltas: torch.Tensor, im_h: int, im_w: int, eps: float = 1e-14):
+    """_bbox_pred + _clip_boxes (lib/detect/test.py:106-151).  boxes f64 [n,4], deltas f32 [n,4k]."""
+    _need_cuda(boxes, deltas)
+    assert boxes.dtype == torch.float64 and deltas.dtype == torch.float32
+    boxes, deltas = boxes.contiguous(), deltas.contiguous()
+    n, ncol = boxes.shape[0], deltas.shape[1] // 4
+    out = torch.empty((n, 4 * ncol), dtype=torch.float64, device=boxes.device)
+    L.check(L.lib().azn_decode_boxes(_ptr(boxes), _ptr(deltas), n, ncol, float(eps), int(im_h), int(im_w), _ptr(out),
+                                     _stream()), "azn_decode_boxes")
+    return out

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- AZ-Net proposal throughput (images/sec) on B200, the metric of BASELINE.json.
+
+A step = one pass of the adaptive search (all levels: ROI max-pool over the cached conv5_3 map,
+fc heads, decode/clip, zoom-subdivide, dedup, top-N) over one batch of 64 synthetic 600x1000 images
+per GPU, AZ-Net VGG16 head widths, PASCAL config (experiments/cfgs/voc.yml: MAX_SIZE 800 -> conv5_3
+512x30x50, BATCH_SIZE 1000, 300 proposals).  The conv5_3 maps are the input of the path (the backbone
+runs once per image before the search and is out of scope).
+
+  value   whole-job images/sec with the maps resident in HBM (NHWC bf16)
+  e2e     the same through the host-facing call: f32 NCHW maps in pinned host memory -> H2D -> layout
+          conversion -> search -> D2H of the proposal lists, every step
+  roofline  the int6 GEMM (25088 -> 4096) launch of the deepest level vs the measured bf16 peak
+  cpu_baseline / --impl reference  the oracle port of the reference's CPU path on the host cores
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IM_H, IM_W, BATCH = 600, 1000, 64
+CFG = dict(scales=(600,), max_size=800, min_side=10, tz=0.5, num_proposals=300, batch_size=1000,
+           dedup=1. / 16., eps=1e-14)
+ZOOM_BIAS = 0.1          # ~40 % of regions zoom at Tz = 0.5 with the seed-3 He-init heads
+WORKLOAD = ("AZ-Net VGG16 PASCAL config (voc.yml: MAX_SIZE 800 -> conv5_3 512x30x50), batch of 64 synthetic "
+            "600x1000 images per GPU, search from cached conv5_3, Tz=0.5, 300 proposals")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+class OracleRunner:
+    """The reference's CPU path (oracle port: lib/detect/test.py control flow, Caffe ROIPooling loop on one
+    core, fp32 sgemm heads on `threads` cores) on images of the bench workload."""
+
+    def __init__(self, weights, threads, n_maps=8, seed=7):
+        from aznet_b200 import synth
+        from oracle import az_oracle as O
+        self.O = O
+        self.cfg = O.OracleCfg(TEST_MAX_SIZE=CFG["max_size"], Tz=CFG["tz"], NUM_PROPOSALS=CFG["num_proposals"],
+                               BATCH_SIZE=CFG["batch_size"])
+        s = O.im_scale_for((IM_H, IM_W), self.cfg)[0]
+        fh, fw = synth.conv_shape(IM_H, IM_W, s)
+        self.conv = synth.make_conv_maps(n_maps, 512, fh, fw, seed=seed)
+        self.net = O.OracleNet(weights, "az", cfg=self.cfg, threads=threads)
+        self.regions = 0
+        self.images = 0
+
+    def run(self, n_images, start=0):
+        nets = {"full": self.net, "fc": self.net}
+        for i in range(n_images):
+            j = (start + i) % self.conv.shape[0]
+            _, _, info = self.O.im_propose(nets, (IM_H, IM_W, 3), self.cfg, conv={"conv5_3": self.conv[j:j + 1]},
+                                           return_scores=True)
+            self.regions += info["num_eval"]
+            self.images += 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; Caffe cannot be
+    built here) on the host cores, same config / metric / unit.  One step = a bounded sample of
+    4 images of the 64-image batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from aznet_b200 import synth
+    threads = os.cpu_count() or 1
+    w = synth.make_az_weights(seed=3, zoom_bias=ZOOM_BIAS)
+    per_step = 4
+    runner = OracleRunner(w, threads)
+    for k in range(max(args.warmup, 1)):
+        runner.run(1, k)
+    runner.regions = runner.images = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        runner.run(per_step, k * per_step)
+    dt = time.perf_counter() - t0
+    n = per_step * args.steps
+    ips = n / dt
+    line = {
+        "impl": "reference", "metric": "AZ proposal images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "regions_per_image": runner.regions / max(runner.images, 1),
+                   "step": "bounded sample: %d images of the 64-image batch per step" % per_step},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": "%d images of the bench workload in %.1f s (oracle port of lib/detect/test.py + Caffe layers; "
+                                   "ROI-pool and control flow single-threaded like the reference, sgemm heads on %d threads)"
+                                   % (n, dt, threads)},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from aznet_b200 import _lib, engine, ops, synth
+    from aznet_b200.dist import gather_proposals
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.build()
+    _lib.require_device()
+
+    weights = synth.make_az_weights(seed=3, zoom_bias=ZOOM_BIAS)
+    head = engine.AZHeadWeights(weights, dev)
+    eng = engine.SearchEngine(head, BATCH, IM_H, IM_W, **CFG)
+    fh, fw = synth.conv_shape(IM_H, IM_W, eng.scale)
+    # two distinct synthetic batches per rank (rotated, so consecutive steps never see the same maps)
+    n_sets = 2
+    host_sets, dev_sets = [], []
+    for sidx in range(n_sets):
+        maps = synth.make_conv_maps(BATCH, 512, fh, fw, seed=7 + 1000 * rank + 100 * sidx)
+        hp = torch.from_numpy(maps).pin_memory()
+        host_sets.append(hp)
+        dev_sets.append(ops.nchw_to_nhwc_bf16(hp.to(dev)))
+    stage_f32 = torch.empty_like(host_sets[0], device=dev)
+    stage_nhwc = torch.empty_like(dev_sets[0])
+    out_host = (torch.empty(eng.out_boxes.shape, dtype=torch.float64).pin_memory(),
+                torch.empty(eng.out_scores.shape, dtype=torch.float32).pin_memory(),
+                torch.empty(eng.out_count.shape, dtype=torch.int32).pin_memory())
+    h2d_bytes = host_sets[0].numel() * 4
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        eng.propose(dev_sets[i % n_sets])
+        if world > 1:
+            gather_proposals(eng.out_boxes, eng.out_scores, eng.out_count)
+
+    def step_e2e(i):
+        stage_f32.copy_(host_sets[i % n_sets], non_blocking=True)
+        ops.nchw_to_nhwc_bf16(stage_f32, out=stage_nhwc)
+        eng.propose(stage_nhwc)
+        for dst, src in zip(out_host, (eng.out_boxes, eng.out_scores, eng.out_count)):
+            dst.copy_(src, non_blocking=True)
+        if world > 1:
+            gather_proposals(eng.out_boxes, eng.out_scores, eng.out_count)
+        torch.cuda.current_stream().synchronize()      # the caller owns its proposals when the call returns
+
+    def timed(step_fn, steps, profile=False):
+        barrier()
+        eng.launches = 0
+        eng.profile = profile
+        eng.prof_events = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    for i in range(max(args.warmup - 1, 1)):
+        step_e2e(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps, profile=True)
+    launches = eng.launches
+    prof = eng.prof_summary()
+    regions = float(eng.n_eval.float().mean().item())
+    if int(eng.status.item()) != 0:
+        raise RuntimeError("search capacity overflow during the bench")
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        hbm_peak, tf_peak, which = peaks()
+        value = world * BATCH * args.steps / (ms_total / 1e3)
+        e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
+        top = prof["int6_deepest"]
+        line = {
+            "metric": "AZ proposal images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "regions_per_image": regions,
+                       "l2": "working set per step (216 MB bf16 weights + pooled rows) exceeds the 126 MB L2; inputs rotate over 2 distinct batches",
+                       "parallelism": "image-sharded x%d, no collective on the hot path; NCCL all_gather of proposal lists per step" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "fc_gemm_kernel<256> int6 25088->4096, deepest level", "bound": "tensor",
+                         "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
+                         "traffic": None, "peak_source": which + " (sustained bf16)", "m_rows": top["m"], "ms": top["ms"],
+                         "per_level": prof["levels"], "hbm_peak_gbs": hbm_peak},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            runner = OracleRunner(weights, threads)
+            runner.run(1)
+            runner.regions = runner.images = 0
+            t0 = time.perf_counter()
+            runner.run(16)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 16 / dt, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": "16 images of the same workload in %.1f s (oracle port; ROI-pool/control flow 1 core, "
+                                              "sgemm heads %d threads); %.0f regions/image" % (dt, threads, runner.regions / 16)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

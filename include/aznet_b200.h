@@ -1,0 +1,180 @@
+/*
+ * aznet_b200.h -- C ABI of libaznet_b200.so: the B200 (sm_100a) implementation of AZ-Net's
+ * adaptive-search hot path.  One entry point per reference function on the path
+ * (SURVEY.md section 8a); the "replaces" lines cite /root/reference.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all
+ *     buffers (PyTorch tensors in the Python host layer) and sizes outputs for the worst case;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates, keeps no global state;
+ *   - return value 0 = ok, nonzero = AZN_ERR_*; azn_last_error() gives the thread-local text;
+ *   - region / ROI counts that are produced on the device stay on the device (int32 in HBM):
+ *     kernels are launched for the capacity and read the live count themselves, so the level
+ *     loop of the search never round-trips to the host (the reference does, once per level:
+ *     caffe-fast-rcnn/python/caffe/pycaffe.py:90,95).
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef AZNET_B200_H_
+#define AZNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZN_OK 0
+#define AZN_ERR_INVALID 1   /* bad argument (shape, alignment, enum) */
+#define AZN_ERR_CUDA 2      /* a CUDA runtime/driver call failed */
+#define AZN_ERR_CAPACITY 3  /* a caller-provided buffer is too small for the request */
+
+#define AZN_LAYOUT_NCHW 0   /* Caffe blob order: [n][c][h][w]; pooled output [r][c][ph][pw] */
+#define AZN_LAYOUT_NHWC 1   /* channels-last:    [n][h][w][c]; pooled output [r][ph][pw][c] */
+#define AZN_DTYPE_F32 0
+#define AZN_DTYPE_BF16 1
+
+#define AZN_ACT_NONE 0
+#define AZN_ACT_RELU 1
+#define AZN_ACT_AZ_HEAD 2   /* act_aux = nsub: sigmoid on columns [0,nsub) and column 5*nsub, identity elsewhere */
+#define AZN_ACT_SOFTMAX_BBOX 3 /* act_aux = classes: softmax over columns [0,classes), identity on the rest */
+
+typedef void *azn_stream_t;
+
+const char *azn_version(void);
+const char *azn_last_error(void);
+/* 0 when the current device is sm_100 (B200); AZN_ERR_CUDA otherwise. */
+int azn_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * ROI max pooling, forward.
+ * replaces: ROIPoolingLayer<Dtype>::Forward_cpu / Forward_gpu
+ *           caffe-fast-rcnn/src/caffe/layers/roi_pooling_layer.cpp:46-125, .cu:18-92
+ *   feat      [n_img, C, H, W] (NCHW) or [n_img, H, W, C] (NHWC), f32 or bf16
+ *   rois      f32 [R, 5] = (batch_index, x1, y1, x2, y2)
+ *   n_rois    int32 device scalar with the live ROI count (<= R_cap), or NULL for R_cap
+ *   out       same dtype as feat; [R, C, PH, PW] for NCHW, [R, PH, PW, C] for NHWC
+ *   argmax    int32, out's shape, or NULL (NCHW only; h*W + w of the winner, -1 for empty bins)
+ * Bit-exact with the reference for f32; bf16 in -> bf16 out is bit-exact with bf16(f32 result)
+ * because max commutes with the monotone rounding.  NHWC needs C*sizeof(dtype) % 16 == 0.
+ * A batch index outside [0, n_img) yields an all-zero row (the reference CPU path aborts,
+ * roi_pooling_layer.cpp:66-67; its GPU path reads out of bounds). */
+int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
+                     const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
+                     float spatial_scale, void *out, int32_t *argmax, azn_stream_t stream);
+
+/* f32 NCHW -> bf16 NHWC feature-map conversion (layout the search engine keeps resident). */
+int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, void *dst,
+                              azn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fully connected layer on the tensor cores: out = act(A . W^T + bias).
+ * replaces: InnerProductLayer<Dtype>::Forward_{cpu,gpu} (+ ReLU / Sigmoid / Softmax layers)
+ *           caffe-fast-rcnn/src/caffe/layers/inner_product_layer.cpp:80-93, .cu:13-25,
+ *           relu_layer.cu:10, sigmoid_layer.cu:11-15, softmax_layer.cu:14-70
+ *   A     bf16 [M_cap, K] row-major (lda = K), W bf16 [N, K] row-major (Caffe's blob order),
+ *   bias  f32 [N]; out bf16 or f32 [M_cap, ldo]
+ *   m_live  int32 device scalar with the live row count, or NULL for M_cap
+ * bf16 operands, fp32 accumulation in TMEM (tcgen05.mma kind::f16), TMA-fed.
+ * K % 64 == 0, N % 16 == 0, pointers 16-byte aligned.  `workspace` (azn_fc_workspace_bytes)
+ * is used for split-K partial sums when M is small. */
+size_t azn_fc_workspace_bytes(int M_cap, int N, int K);
+int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype,
+                   int ldo, int M_cap, const int32_t *m_live, int N, int K, int act, int act_aux,
+                   void *workspace, size_t workspace_bytes, azn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One level of the adaptive search for a batch of images, after the heads have run.
+ * replaces: _bbox_pred, _clip_boxes, un-dedup, _unwrap_adj_pred (lib/detect/test.py:106-151,
+ *           :171-187, :243-251), the zoom selection of im_propose (:380-389), divide_region +
+ *           _sift_dup (lib/utils/div.pyx:15-88) and the feature-space dedup of the NEXT level's
+ *           ROIs (lib/detect/test.py:61-97, :212-218).
+ * The per-image state lives in an azn_search_state that the caller fills with device pointers. */
+typedef struct azn_search_state {
+    int32_t n_img;
+    int32_t cap_regions;     /* per image, per level                                        */
+    int32_t cap_children;    /* per image: children generated before _sift_dup              */
+    int32_t cap_props;       /* per image: accumulated adjacent predictions (Y)             */
+    int32_t nsub;            /* 11 sub-region priors (lib/detect/config.py:149-155)          */
+    int32_t chunk;           /* cfg.SEAR.BATCH_SIZE: dedup is per chunk of this many regions */
+    const int32_t *im_h;     /* [n_img] original image height / width (clip + root region)  */
+    const int32_t *im_w;
+    const double *im_scale;  /* [n_img] image -> network-input scale (_get_image_blob)       */
+    double tz;               /* cfg.SEAR.Tz                                                  */
+    double min_side;         /* cfg.SEAR.MIN_SIDE                                            */
+    double eps;              /* cfg.EPS                                                      */
+    double dedup;            /* cfg.DEDUP_BOXES (<= 0 disables the feature-space dedup)      */
+    /* current level */
+    double *regions;         /* [n_img, cap_regions, 4] B of this level, reference order     */
+    int32_t *n_regions;      /* [n_img]                                                      */
+    int32_t *inv;            /* [n_img, cap_regions] region -> unique ROI slot (inv_index)   */
+    int32_t *rep;            /* [n_img, cap_regions] unique slot -> representative region    */
+    int32_t *n_uniq;         /* [n_img]                                                      */
+    int32_t *img_off;        /* [n_img + 1] exclusive scan of n_uniq = row offset in heads   */
+    float *rois;             /* [n_img * cap_regions, 5] packed unique ROIs (pool input)     */
+    int32_t *m_total;        /* [1] total unique ROIs of the level                           */
+    /* next level (double buffer; the caller swaps the pointers between levels) */
+    double *next_regions;
+    int32_t *next_n_regions;
+    /* scratch */
+    double *children;        /* [n_img, cap_children, 4]                                     */
+    int64_t *hashes;         /* [n_img, cap_children]                                        */
+    int32_t *flags;          /* [n_img, cap_children]                                        */
+    /* accumulated adjacent predictions */
+    double *props;           /* [n_img, cap_props, 4]                                        */
+    float *prop_scores;      /* [n_img, cap_props]                                           */
+    int32_t *n_props;        /* [n_img]                                                      */
+    int32_t *n_eval;         /* [n_img] regions evaluated so far (num_eval)                  */
+    int32_t *depth;          /* [n_img] last level that ran (the k printed by im_propose)    */
+    int32_t *status;         /* [1] sticky device-side error flag (capacity overflow)        */
+} azn_search_state;
+
+/* Level-1 setup: B = [[0, 0, W-1, H-1]] per image (lib/detect/test.py:355), its ROI, counters. */
+int azn_search_init(const azn_search_state *st, azn_stream_t stream);
+/* heads: zoom_prob f32 (row stride ld_zoom floats), adj_prob f32 [.,nsub] (ld_prob),
+ * adj_bbox f32 [.,4*nsub] (ld_bbox), rows indexed by img_off[i] + unique slot.
+ * level: 1-based k of the reference loop; last_level != 0 skips the (discarded) subdivision. */
+int azn_search_level(const azn_search_state *st, const float *zoom_prob, int ld_zoom,
+                     const float *adj_prob, int ld_prob, const float *adj_bbox, int ld_bbox,
+                     int level, int last_level, azn_stream_t stream);
+
+/* Final selection.  replaces: lib/detect/test.py:393-401.
+ *   mode 0: top-`num_proposals` by score (ties: lower index first), mode 1: score >= tc in order.
+ *   out_boxes f64 [n_img, cap_out, 4], out_scores f32 [n_img, cap_out], out_count i32 [n_img]. */
+int azn_select_proposals(const azn_search_state *st, int mode, int num_proposals, double tc,
+                         double *out_boxes, float *out_scores, int32_t *out_count, int cap_out,
+                         azn_stream_t stream);
+
+/* Stand-alone pieces of the level kernel, exposed with the reference's own signatures.
+ * azn_divide_region replaces utils.cython_div.divide_region / _sift_dup for ONE region set
+ * (lib/utils/div.pyx:15-88): regions f64 [n,4] -> out f64 [cap_out,4], out_count[1]. */
+int azn_divide_region(const double *regions, int n, double min_side, double *out, int32_t *out_count,
+                      int cap_out, int sift_only, void *scratch, size_t scratch_bytes, azn_stream_t stream);
+size_t azn_divide_region_scratch_bytes(int n);
+/* azn_decode_boxes replaces _bbox_pred + _clip_boxes (lib/detect/test.py:106-151):
+ * boxes f64 [n,4], deltas f32 [n, 4*ncol] -> out f64 [n, 4*ncol] clipped to (im_h, im_w). */
+int azn_decode_boxes(const double *boxes, const float *deltas, int n, int ncol, double eps,
+                     int im_h, int im_w, double *out, azn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Greedy NMS.  replaces: utils.cython_nms.nms (lib/utils/nms.pyx:17-68), called by apply_nms
+ * (lib/detect/test.py:467-484).
+ *   dets f32 [n,5] (x1,y1,x2,y2,score); thresh is a double, compared as (double)ovr >= thresh;
+ *   keep int64 [n] kept indices in descending score order (ties: higher index first, i.e. the
+ *   order of a stable ascending argsort reversed); keep_count int32 [1].
+ * f32 arithmetic with one rounding per operation (no FMA contraction) => bit-exact keep lists. */
+size_t azn_nms_workspace_bytes(int64_t n);
+int azn_nms(const float *dets, int64_t n, double thresh, int64_t *keep, int32_t *keep_count,
+            void *workspace, size_t workspace_bytes, azn_stream_t stream);
+/* Many small independent problems in one launch (one per class per image in apply_nms).
+ *   seg_off int32 [n_seg + 1] row offsets into dets; every segment <= AZN_NMS_SEG_MAX rows;
+ *   keep int64 [total rows] segment-local indices written at seg_off[s]; keep_count int32 [n_seg]. */
+#define AZN_NMS_SEG_MAX 1024
+int azn_nms_batched(const float *dets, const int32_t *seg_off, int n_seg, double thresh,
+                    int64_t *keep, int32_t *keep_count, azn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZNET_B200_H_ */

@@ -1,0 +1,254 @@
+"""GPU suite (run on the B200 box: pytest -m gpu): kernel-level parity of every C-ABI entry point
+against the oracle on the same seeded inputs.  Bit-exact for ROI pooling, NMS and region
+arithmetic; stated tolerances for the bf16 tensor-core layers and the f32-exp box decode."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from aznet_b200 import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from aznet_b200 import _lib
+    _lib.build()
+    _lib.require_device()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import az_oracle
+    az_oracle.build()
+    return az_oracle
+
+
+def _natural_regions(O, n_levels=5):
+    lv = np.array([[0, 0, 999, 599.]])
+    out = [lv]
+    for _ in range(n_levels - 1):
+        lv = O.divide_region(lv, 10.0)
+        out.append(lv)
+    return np.vstack(out)
+
+
+def _edge_rois(n_img):
+    r = synth.make_rois(400, 600, 1000, seed=5, n_img=n_img)
+    r[:20, 1:] = np.round(r[:20, 1:] / 8) * 8        # x*1/16 lands on .5: round half away from zero
+    r[20:26, 1:] += 2000                             # outside the map -> empty bins -> 0
+    r[26] = [0, 300, 300, 100, 100]                  # malformed -> 1x1
+    r[27] = [0, 0, 0, 999, 599]                      # whole image
+    r[28] = [0, 0, 0, 0, 0]
+    r[29] = [0, -50, -50, 30, 30]                    # negative start: clamped
+    return r
+
+
+# ------------------------------------------------------------------------------- ROI pooling
+@pytest.mark.parametrize("hw", [(38, 63), (30, 50)])
+def test_roi_pool_nchw_f32_bit_exact(dev, O, hw):
+    from aznet_b200 import ops
+    feat = synth.make_conv_maps(2, 64, hw[0], hw[1], seed=7)
+    feat[1] -= 0.3                                   # negative values too: the layer itself is sign-agnostic
+    rois = _edge_rois(2)
+    ref, ref_am = O.roi_pool_fwd(feat, rois, want_argmax=True)
+    got, am = ops.roi_pool(torch.from_numpy(feat).to(dev), torch.from_numpy(rois).to(dev), layout="NCHW", want_argmax=True)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(am.cpu().numpy(), ref_am)
+
+
+@pytest.mark.parametrize("C", [64, 512])
+def test_roi_pool_nhwc_bit_exact_f32_and_bf16(dev, O, C):
+    from aznet_b200 import ops
+    n_img = 2 if C == 512 else 3
+    feat = synth.make_conv_maps(n_img, C, 38, 63, seed=9)
+    rois = _edge_rois(n_img)
+    if C == 512:
+        nat = _natural_regions(O)                    # the 739 natural full-zoom regions of a 600x1000 image
+        rois = np.vstack([rois, np.hstack([np.zeros((len(nat), 1)), nat]).astype(np.float32)])
+    ref = O.roi_pool_fwd(feat, rois).transpose(0, 2, 3, 1)          # -> [R, ph, pw, C]
+    f = torch.from_numpy(feat).to(dev)
+    r = torch.from_numpy(rois).to(dev)
+    got = ops.roi_pool(f.permute(0, 2, 3, 1).contiguous(), r, layout="NHWC")
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+    # bf16: pool(bf16(x)) == bf16(pool(x)) bit for bit
+    fb = f.to(torch.bfloat16)
+    ref_b = O.roi_pool_fwd(fb.float().cpu().numpy(), rois).transpose(0, 2, 3, 1)
+    got_b = ops.roi_pool(fb.permute(0, 2, 3, 1).contiguous(), r, layout="NHWC")
+    assert np.array_equal(got_b.float().cpu().numpy(), ref_b)
+    # the conversion kernel produces the same NHWC bf16 map
+    conv = ops.nchw_to_nhwc_bf16(f)
+    assert torch.equal(conv, fb.permute(0, 2, 3, 1).contiguous())
+    # bf16 NCHW variant
+    got_c = ops.roi_pool(fb.contiguous(), r, layout="NCHW")
+    assert np.array_equal(got_c.float().cpu().numpy(), ref_b.transpose(0, 3, 1, 2))
+
+
+def test_roi_pool_device_count_bad_index_and_empty(dev, O):
+    from aznet_b200 import ops
+    feat = synth.make_conv_maps(1, 64, 20, 20, seed=1)
+    rois = synth.make_rois(50, 300, 300, seed=2)
+    rois[3, 0] = 7                                   # batch index out of range -> zero row (documented)
+    f = torch.from_numpy(feat).to(dev).permute(0, 2, 3, 1).contiguous()
+    r = torch.from_numpy(rois).to(dev)
+    out = torch.full((50, 7, 7, 64), -1.0, device=dev)
+    ops.roi_pool(f, r, layout="NHWC", n_rois=torch.tensor([10], dtype=torch.int32, device=dev), out=out)
+    got = out.cpu().numpy()
+    ok = rois[:10].copy()
+    ok[3, 0] = 0
+    ref = O.roi_pool_fwd(feat, ok).transpose(0, 2, 3, 1)
+    ref[3] = 0
+    assert np.array_equal(got[:10], ref) and np.all(got[10:] == -1.0)   # rows past the live count untouched
+    z = ops.roi_pool(f, r[:0].contiguous(), layout="NHWC")
+    assert z.shape[0] == 0
+    with pytest.raises(ValueError):
+        ops.roi_pool(torch.zeros((1, 4, 4, 3), device=dev), r, layout="NHWC")     # C*4 % 16 != 0
+
+
+# ------------------------------------------------------------------------------- NMS
+def test_nms_golden_and_oracle(dev, O, golden):
+    from aznet_b200 import ops
+    g = golden["nms"]
+    for n in (1, 2, 17, 300, 2000):
+        d = synth.make_dets(n, seed=3)
+        for th in (0.3, 0.5, 0.7):
+            keep, cnt = ops.nms(torch.from_numpy(d).to(dev), th)
+            got = keep[:int(cnt.item())].cpu().tolist()
+            assert got == list(g["keep_n%d_t%d" % (n, int(th * 10))]), (n, th)
+    for th, key in ((0.5, "edge_keep_t5"), (0.51, "edge_keep_t51")):
+        keep, cnt = ops.nms(torch.from_numpy(g["edge_dets"]).to(dev), th)
+        assert keep[:int(cnt.item())].cpu().tolist() == list(g[key])
+    keep, cnt = ops.nms(torch.zeros((0, 5), device=dev), 0.5)
+    assert int(cnt.item()) == 0
+
+
+@pytest.mark.parametrize("n,th", [(8000, 0.3), (8000, 0.7), (20000, 0.3)])
+def test_nms_large_matches_oracle(dev, O, n, th):
+    from aznet_b200 import ops
+    d = synth.make_dets(n, seed=3)
+    keep, cnt = ops.nms(torch.from_numpy(d).to(dev), th)
+    assert keep[:int(cnt.item())].cpu().tolist() == O.nms(d, th)
+
+
+def test_nms_ties_and_idempotence(dev, O):
+    from aznet_b200 import ops
+    d = synth.make_dets(600, seed=11)
+    d[:, 4] = np.round(d[:, 4] * 20) / 20            # many exact score ties: order = stable argsort reversed
+    keep, cnt = ops.nms(torch.from_numpy(d).to(dev), 0.5)
+    k1 = keep[:int(cnt.item())].cpu().tolist()
+    assert k1 == O.nms(d, 0.5)
+    kept = np.ascontiguousarray(d[k1])
+    keep2, cnt2 = ops.nms(torch.from_numpy(kept).to(dev), 0.5)     # survivors never suppress each other
+    assert int(cnt2.item()) == len(k1)
+
+
+def test_nms_batched_matches_per_segment(dev, O):
+    from aznet_b200 import ops
+    rng = np.random.default_rng(0)
+    sizes = [0, 1, 100, 37, 64, 65, 100, 250, 3, 1000] + [int(x) for x in rng.integers(0, 101, 150)]
+    segs = [synth.make_dets(max(s, 1), seed=50 + i)[:s] for i, s in enumerate(sizes)]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    d = np.ascontiguousarray(np.vstack(segs).astype(np.float32))
+    keep, cnt = ops.nms_batched(torch.from_numpy(d).to(dev), torch.from_numpy(off).to(dev), 0.5)
+    keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+    for i, s in enumerate(sizes):
+        ref = O.nms(np.ascontiguousarray(segs[i]), 0.5) if s else []
+        assert list(keep[off[i]:off[i] + cnt[i]]) == ref, i
+
+
+# ------------------------------------------------------------------------------- regions / decode
+def test_divide_region_bit_exact(dev, O, golden):
+    from aznet_b200 import ops
+    g = golden["div"]
+    for k in g.files:
+        if not k.startswith("in_"):
+            continue
+        out, cnt = ops.divide_region(torch.from_numpy(np.ascontiguousarray(g[k], dtype=np.float64)).to(dev), 10.0)
+        got = out[:int(cnt.item())].cpu().numpy()
+        assert np.array_equal(got.view(np.uint64), g["out_" + k[3:]].view(np.uint64)), k
+    lv = torch.from_numpy(g["in_root_600x1000"]).to(dev)
+    for lvl in range(2, 6):
+        out, cnt = ops.divide_region(lv, 10.0)
+        lv = out[:int(cnt.item())].contiguous()
+        assert np.array_equal(lv.cpu().numpy(), g["cascade_%d" % lvl])
+    out, cnt = ops.divide_region(torch.from_numpy(g["sift_in"]).to(dev), 10.0, sift_only=True)
+    assert np.array_equal(out[:int(cnt.item())].cpu().numpy(), g["sift_out"])
+    out, cnt = ops.divide_region(torch.zeros((0, 4), dtype=torch.float64, device=dev), 10.0)
+    assert int(cnt.item()) == 0
+
+
+def test_decode_boxes_within_1e5(dev, O, golden):
+    from aznet_b200 import ops
+    g = golden["search"]
+    got = ops.decode_boxes(torch.from_numpy(g["bbox_boxes"]).to(dev), torch.from_numpy(g["bbox_deltas"]).to(dev), 600, 1000)
+    ref = g["bbox_clip"]
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)      # north_star: 1e-5 relative
+
+
+# ------------------------------------------------------------------------------- fc layers (tcgen05)
+def _fc_case(dev, M, N, K, act, seed, m_live=None, out_dtype=torch.bfloat16, act_aux=0):
+    from aznet_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    A = (torch.randn((M, K), generator=g) * 0.5).to(torch.bfloat16)
+    W = (torch.randn((N, K), generator=g) * (1.0 / np.sqrt(K))).to(torch.bfloat16)
+    b = torch.randn((N,), generator=g) * 0.1
+    ml = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=dev)
+    out = torch.full((M, (N + 7) // 8 * 8), -7.0, dtype=out_dtype, device=dev)[:, :N] if out_dtype == torch.float32 else None
+    if out is not None:
+        got = ops.fc_forward(A.to(dev), W.to(dev), b.to(dev), act, act_aux, out_dtype=out_dtype, m_live=ml, out=out)
+    else:
+        got = ops.fc_forward(A.to(dev), W.to(dev), b.to(dev), act, act_aux, out_dtype=out_dtype, m_live=ml)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + b                       # plain fp32 reference of the same op
+    return got.float().cpu(), ref
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 128), (64, 256, 3136), (300, 512, 1024),
+                                   (1000, 4096, 3136), (2500, 1280, 4096), (700, 56, 1280), (129, 105, 256)])
+def test_fc_forward_matches_fp32_reference(dev, M, N, K):
+    from aznet_b200 import _lib as L
+    got, ref = _fc_case(dev, M, N, K, L.ACT_RELU, seed=M + N + K)
+    ref = torch.relu(ref)
+    err = (got - ref).abs().max().item()
+    # bf16 output rounding (2^-9 relative) on |values| <~ 4, fp32 accumulation: stated tolerance 3e-2 abs
+    assert err < 3e-2, "max abs err %.4g" % err
+    assert (got - ref).abs().mean().item() < 3e-3
+
+
+def test_fc_forward_live_count_and_f32_heads(dev):
+    from aznet_b200 import _lib as L
+    nsub = 11
+    got, ref = _fc_case(dev, 900, 56, 1280, L.ACT_AZ_HEAD, seed=5, m_live=333, out_dtype=torch.float32, act_aux=nsub)
+    sig = torch.sigmoid(ref)
+    want = ref.clone()
+    want[:, :nsub] = sig[:, :nsub]
+    want[:, 5 * nsub] = sig[:, 5 * nsub]
+    assert (got[:333] - want[:333]).abs().max().item() < 2e-3          # f32 out of bf16 operands
+    assert torch.all(got[333:] == -7.0)                                # rows past the live count untouched
+
+
+def test_fc_forward_splitk_small_m(dev):
+    from aznet_b200 import _lib as L
+    for M in (1, 8, 64, 200):
+        got, ref = _fc_case(dev, M, 4096, 25088, L.ACT_RELU, seed=M)
+        assert (got - torch.relu(ref)).abs().max().item() < 4e-2, M
+
+
+def test_fc_forward_softmax_rows(dev):
+    from aznet_b200 import _lib as L
+    C = 21
+    got, ref = _fc_case(dev, 300, 5 * C, 4096, L.ACT_SOFTMAX_BBOX, seed=9, out_dtype=torch.float32, act_aux=C)
+    want = ref.clone()
+    want[:, :C] = torch.softmax(ref[:, :C], dim=1)
+    assert (got - want).abs().max().item() < 5e-3
+    np.testing.assert_allclose(got[:, :C].sum(1).numpy(), 1.0, atol=1e-5)
+
+
+def test_fc_forward_argument_errors(dev):
+    from aznet_b200 import ops
+    A = torch.zeros((128, 100), dtype=torch.bfloat16, device=dev)
+    W = torch.zeros((64, 100), dtype=torch.bfloat16, device=dev)
+    with pytest.raises(ValueError):
+        ops.fc_forward(A, W, torch.zeros(64, device=dev))              # K % 64 != 0
