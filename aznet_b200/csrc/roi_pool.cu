@@ -267,11 +267,11 @@ nchw_to_nhwc_bf16_kernel(const float *__restrict__ src, int C, int HW, __nv_bflo
 extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                                 const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
                                 float spatial_scale, void *out, int32_t *argmax, azn_stream_t stream) {
+    if (R_cap == 0) return AZN_OK;
     AZN_REQUIRE(feat && rois && out, "azn_roi_pool_fwd: null pointer");
     AZN_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R_cap >= 0,
                 "azn_roi_pool_fwd: bad shape n_img=%d C=%d H=%d W=%d PH=%d PW=%d R=%d", n_img, C, H, W, PH, PW, R_cap);
     AZN_REQUIRE(dtype == AZN_DTYPE_F32 || dtype == AZN_DTYPE_BF16, "azn_roi_pool_fwd: bad dtype %d", dtype);
-    if (R_cap == 0) return AZN_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int sms = azn_num_sms();
     if (layout == AZN_LAYOUT_NHWC) {

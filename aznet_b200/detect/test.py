@@ -1,0 +1,448 @@
+"""Drop-in for lib/detect/test.py: the Python entry points that tools/prop_az.py and
+tools/test_det_net.py call -- test_proposals, test_net, im_propose, im_detect, im_detect_shared,
+apply_nms, divide_region -- with the reference's signatures, argument meaning, printed lines and
+pickle formats, computed on the B200 through libaznet_b200.so.
+
+Two execution routes for the adaptive search:
+  * nets built from aznet_b200.net.Net: the whole level loop runs device-resident in
+    aznet_b200.engine.SearchEngine (no host round trip between levels);
+  * any other duck-typed net (e.g. a caffe.Net-like object): the reference's level loop is kept on the
+    host, one net.forward per level, while decode/clip, divide_region/_sift_dup and NMS still run in the
+    CUDA kernels.
+Neither route has a CPU fallback.
+"""
+from __future__ import annotations
+
+import heapq
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .config import cfg, get_output_dir
+from .. import ops
+from ..engine import SearchEngine, im_scale_for, search_depth
+from ..net import Net
+from ..utils import cython_div as div
+from ..utils.blob import im_list_to_blob
+from ..utils.cython_nms import nms
+from ..utils.timer import Timer
+
+
+# --------------------------------------------------------------------------- blob preparation
+def _get_image_blob(im):
+    """Mean-subtracted, rescaled image pyramid blob + scale factors (lib/detect/test.py:27-59)."""
+    import cv2
+    im_orig = im.astype(np.float32, copy=True)
+    im_orig -= cfg.PIXEL_MEANS
+    size_min, size_max = np.min(im_orig.shape[0:2]), np.max(im_orig.shape[0:2])
+    ims, factors = [], []
+    for target in cfg.TEST.SCALES:
+        s = float(target) / float(size_min)
+        if np.round(s * size_max) > cfg.TEST.MAX_SIZE:
+            s = float(cfg.TEST.MAX_SIZE) / float(size_max)
+        ims.append(cv2.resize(im_orig, None, None, fx=s, fy=s, interpolation=cv2.INTER_LINEAR))
+        factors.append(s)
+    return im_list_to_blob(ims), np.array(factors)
+
+
+def _project_im_rois(im_rois, scales):
+    """lib/detect/test.py:73-97."""
+    im_rois = im_rois.astype(np.float64, copy=False)
+    if len(scales) > 1:
+        w = im_rois[:, 2] - im_rois[:, 0] + 1
+        h = im_rois[:, 3] - im_rois[:, 1] + 1
+        scaled = (w * h)[:, np.newaxis] * (scales[np.newaxis, :] ** 2)
+        levels = np.abs(scaled - 224 * 224).argmin(axis=1)[:, np.newaxis]
+    else:
+        levels = np.zeros((im_rois.shape[0], 1), dtype=np.int64)
+    return im_rois * scales[levels], levels
+
+
+def _get_rois_blob(im_rois, im_scale_factors):
+    """lib/detect/test.py:61-71: [level, x1, y1, x2, y2] float32."""
+    rois, levels = _project_im_rois(im_rois, im_scale_factors)
+    return np.hstack((levels, rois)).astype(np.float32, copy=False)
+
+
+def _get_blobs(im, rois):
+    blobs = {'data': None, 'rois': None}
+    blobs['data'], factors = _get_image_blob(im)
+    blobs['rois'] = _get_rois_blob(rois, factors)
+    return blobs, factors
+
+
+# --------------------------------------------------------------------------- box arithmetic (CUDA)
+def _bbox_pred_clip(boxes, box_deltas, im_shape):
+    """_bbox_pred followed by _clip_boxes (lib/detect/test.py:106-151) in one kernel launch."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, box_deltas.shape[1]))
+    b = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float64)).cuda()
+    d = torch.from_numpy(np.ascontiguousarray(box_deltas, dtype=np.float32)).cuda()
+    return ops.decode_boxes(b, d, int(im_shape[0]), int(im_shape[1]), float(cfg.EPS)).cpu().numpy()
+
+
+def _bbox_pred(boxes, box_deltas):
+    """Unclipped decode (lib/detect/test.py:106-139): the clip bounds are pushed out of reach."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, box_deltas.shape[1]))
+    b = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float64)).cuda()
+    d = torch.from_numpy(np.ascontiguousarray(box_deltas, dtype=np.float32)).cuda()
+    out = ops.decode_boxes(b, d, 2 ** 30, 2 ** 30, float(cfg.EPS)).cpu().numpy()
+    return out
+
+
+def _clip_boxes(boxes, im_shape):
+    """lib/detect/test.py:141-151 (in place, host: four vector min/max)."""
+    boxes[:, 0::4] = np.maximum(boxes[:, 0::4], 0)
+    boxes[:, 1::4] = np.maximum(boxes[:, 1::4], 0)
+    boxes[:, 2::4] = np.minimum(boxes[:, 2::4], im_shape[1] - 1)
+    boxes[:, 3::4] = np.minimum(boxes[:, 3::4], im_shape[0] - 1)
+    return boxes
+
+
+def divide_region(regions):
+    """lib/detect/test.py:153-161 -> utils.cython_div.divide_region(regions, MIN_SIDE)."""
+    return div.divide_region(np.ascontiguousarray(regions, dtype=np.float64), float(cfg.SEAR.MIN_SIDE))
+
+
+def _unwrap_adj_pred(boxes, scores):
+    """[R, 44] -> [11R, 4] roi-major, drop boxes whose shorter side (+1) is below MIN_SIDE (test.py:171-187)."""
+    scores = scores.ravel()
+    b = np.stack((boxes[:, 0::4].ravel(), boxes[:, 1::4].ravel(), boxes[:, 2::4].ravel(), boxes[:, 3::4].ravel()), axis=1)
+    sides = np.minimum(b[:, 3] - b[:, 1] + 1, b[:, 2] - b[:, 0] + 1)
+    keep = np.where(sides >= cfg.SEAR.MIN_SIDE)[0]
+    return b[keep, :], scores[keep]
+
+
+def _dedup(rois_blob):
+    v = np.array([1, 1e3, 1e6, 1e9, 1e12])
+    hashes = np.round(rois_blob * cfg.DEDUP_BOXES).dot(v)
+    _, index, inv = np.unique(hashes, return_index=True, return_inverse=True)
+    return index, inv
+
+
+def _net_forward(net, blobs, conv, conv_names):
+    """Shared by _az_forward/_frcnn_forward: 'full' net on the first call, 'fc' net on the cached map."""
+    if conv is None or 'fc' not in net.keys():
+        net['full'].blobs['data'].reshape(*(blobs['data'].shape))
+        net['full'].blobs['rois'].reshape(*(blobs['rois'].shape))
+        out = net['full'].forward(data=blobs['data'].astype(np.float32, copy=False),
+                                  rois=blobs['rois'].astype(np.float32, copy=False), blobs=conv_names)
+        conv = {name: out[name] for name in conv_names}
+        if 'fc' in net.keys() and isinstance(net['fc'], Net) and isinstance(net['full'], Net):
+            net['fc'].adopt_conv(net['full'])
+    else:
+        for name in conv_names:
+            net['fc'].blobs[name].reshape(*(conv[name].shape))
+        net['fc'].blobs['rois'].reshape(*(blobs['rois'].shape))
+        out = net['fc'].forward(rois=blobs['rois'].astype(np.float32, copy=False), **{n: conv[n] for n in conv_names})
+    return out, conv
+
+
+def _az_forward(net, im, all_boxes, conv=None):
+    """Host-loop route of lib/detect/test.py:189-257 (one forward per BATCH_SIZE chunk)."""
+    bs = cfg.SEAR.BATCH_SIZE
+    z_all, a_all, c_all = np.zeros((0,)), np.zeros((0, 4)), np.zeros((0,))
+    for start in range(0, all_boxes.shape[0], bs):
+        boxes = all_boxes[start:start + bs, 0:4]
+        blobs, _ = _get_blobs(im, boxes)
+        inv = None
+        if cfg.DEDUP_BOXES > 0:
+            index, inv = _dedup(blobs['rois'])
+            blobs['rois'] = blobs['rois'][index, :]
+            boxes = boxes[index, :]
+        out, conv = _net_forward(net, blobs, conv, cfg.SEAR.AZ_CONV)
+        z = out['zoom_prob']
+        scores = out['adj_prob']
+        pred = _bbox_pred_clip(boxes, out['adj_bbox'], im.shape)
+        if inv is not None:
+            scores, pred, z = scores[inv, :], pred[inv, :], z[inv]
+        a, c = _unwrap_adj_pred(pred, scores)
+        z_all = np.hstack((z_all, z.ravel()))
+        a_all = np.vstack((a_all, a))
+        c_all = np.hstack((c_all, c))
+    return z_all, a_all, c_all, conv
+
+
+def _frcnn_forward(net, im, all_boxes, num_classes, conv=None):
+    """lib/detect/test.py:259-318."""
+    bs = cfg.SEAR.BATCH_SIZE
+    all_pred, all_scores = np.zeros((0, 4 * num_classes)), np.zeros((0, num_classes))
+    for start in range(0, all_boxes.shape[0], bs):
+        boxes = all_boxes[start:start + bs, 0:4]
+        blobs, _ = _get_blobs(im, boxes)
+        inv = None
+        if cfg.DEDUP_BOXES > 0:
+            index, inv = _dedup(blobs['rois'])
+            blobs['rois'] = blobs['rois'][index, :]
+            boxes = boxes[index, :]
+        out, conv = _net_forward(net, blobs, conv, cfg.SEAR.FRCNN_CONV)
+        scores = out['cls_prob']
+        pred = _bbox_pred_clip(boxes, out['bbox_pred'], im.shape)
+        if inv is not None:
+            scores, pred = scores[inv, :], pred[inv, :]
+        all_scores = np.vstack((all_scores, scores))
+        all_pred = np.vstack((all_pred, pred))
+    return all_scores, all_pred, conv
+
+
+# --------------------------------------------------------------------------- the adaptive search
+_ENGINES = {}
+
+
+def _engine_for(az_net: Net, im_shape, num_proposals):
+    key = (id(az_net.head), int(im_shape[0]), int(im_shape[1]), tuple(cfg.TEST.SCALES), cfg.TEST.MAX_SIZE, cfg.SEAR.MIN_SIDE,
+           float(cfg.SEAR.Tz), float(cfg.SEAR.Tc), bool(cfg.SEAR.FIXED_PROPOSAL_NUM), num_proposals, cfg.SEAR.BATCH_SIZE,
+           float(cfg.DEDUP_BOXES), float(cfg.EPS))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        if len(_ENGINES) > 16:
+            _ENGINES.clear()
+        fixed = bool(cfg.SEAR.FIXED_PROPOSAL_NUM) or num_proposals is not None
+        eng = SearchEngine(az_net.head, 1, im_shape[0], im_shape[1], scales=tuple(cfg.TEST.SCALES), max_size=cfg.TEST.MAX_SIZE,
+                           min_side=cfg.SEAR.MIN_SIDE, tz=float(cfg.SEAR.Tz), tc=float(cfg.SEAR.Tc), fixed_num=fixed,
+                           num_proposals=num_proposals if num_proposals is not None else cfg.SEAR.NUM_PROPOSALS,
+                           batch_size=cfg.SEAR.BATCH_SIZE, dedup=float(cfg.DEDUP_BOXES), eps=float(cfg.EPS),
+                           spatial_scale=az_net.spatial_scale)
+        _ENGINES[key] = eng
+    return eng
+
+
+def _fast_route(net):
+    full = net.get('full') if hasattr(net, 'get') else None
+    return isinstance(full, Net) and full.kind == "az" and full.backbone is not None and len(cfg.TEST.SCALES) == 1
+
+
+def im_propose(net, im, return_conv=False, num_proposals=None):
+    """Generate object proposals with AZ-Net (lib/detect/test.py:346-414).
+    net: {'full': Net[, 'fc': Net]}; im: HxWx3 uint8 BGR.  Returns Y [n,4] float64 (and conv dict)."""
+    if cfg.SEAR.APPEND_BOXES:
+        raise NotImplementedError("SEAR.APPEND_BOXES (off by default, config.py:170) is outside the hot path")
+    if _fast_route(net):
+        full = net['full']
+        eng = _engine_for(full, im.shape, num_proposals)
+        data, _ = _get_image_blob(im)
+        conv_dev, nhwc = full.conv_from_data(data)
+        eng.propose(nhwc)
+        boxes, _, n_eval, depth = eng.results()
+        Y, num_eval, k = boxes[0], int(n_eval[0]), int(depth[0])
+        conv = None
+        if return_conv:
+            host = conv_dev.cpu().numpy()
+            full._last_conv = (host, conv_dev, nhwc)
+            conv = {name: host for name in cfg.SEAR.FRCNN_CONV}
+    else:
+        B = np.array([[0, 0, im.shape[1] - 1.0, im.shape[0] - 1.0]])
+        Y, a_scores = np.zeros((0, 4)), np.zeros((0,))
+        num_eval, conv, k = 0, None, 0
+        for k in range(1, search_depth(im.shape[0], im.shape[1], cfg.SEAR.MIN_SIDE)):
+            zoom, boxes, c, conv = _az_forward(net, im, B, conv)
+            num_eval += B.shape[0]
+            Y = np.vstack((Y, boxes))
+            a_scores = np.hstack((a_scores, c))
+            if k == 1:
+                zoom[0] = 1.0                         # the root region is always divided
+            Z = B[np.where(zoom >= cfg.SEAR.Tz)[0], :]
+            if Z.shape[0] == 0:
+                break
+            B = divide_region(Z)
+        if (not cfg.SEAR.FIXED_PROPOSAL_NUM) and (num_proposals is None):
+            Y = Y[np.where(a_scores >= cfg.SEAR.Tc)[0], :]
+        else:
+            n = cfg.SEAR.NUM_PROPOSALS if num_proposals is None else num_proposals
+            Y = Y[np.argsort(-a_scores, kind='stable')[:min(n, Y.shape[0])], :]
+    print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(Y.shape[0], num_eval, k))
+    return (Y, conv) if return_conv else Y
+
+
+def im_propose_batch(net, conv_maps, im_shape, num_proposals=None, engine=None):
+    """Batched search over same-sized images whose conv5_3 maps are already computed.
+    conv_maps: f32 NCHW host/device tensor or ndarray [n, C, h, w].  Returns (list of Y, list of scores)."""
+    az = net['fc'] if 'fc' in net.keys() else net['full']
+    maps = conv_maps if torch.is_tensor(conv_maps) else torch.from_numpy(np.ascontiguousarray(conv_maps, dtype=np.float32))
+    n = maps.shape[0]
+    if engine is None:
+        fixed = bool(cfg.SEAR.FIXED_PROPOSAL_NUM) or num_proposals is not None
+        engine = SearchEngine(az.head, n, im_shape[0], im_shape[1], scales=tuple(cfg.TEST.SCALES), max_size=cfg.TEST.MAX_SIZE,
+                              min_side=cfg.SEAR.MIN_SIDE, tz=float(cfg.SEAR.Tz), tc=float(cfg.SEAR.Tc), fixed_num=fixed,
+                              num_proposals=num_proposals if num_proposals is not None else cfg.SEAR.NUM_PROPOSALS,
+                              batch_size=cfg.SEAR.BATCH_SIZE, dedup=float(cfg.DEDUP_BOXES), eps=float(cfg.EPS))
+    engine.propose(ops.nchw_to_nhwc_bf16(maps.to(engine.dev, non_blocking=True)))
+    boxes, scores, _, _ = engine.results()
+    return boxes, scores
+
+
+def im_detect(net, im, boxes, num_classes):
+    """Fast R-CNN scores [R,C] and class-specific boxes [R,4C] for the proposals (test.py:416-430)."""
+    scores, pred_boxes, _ = _frcnn_forward(net, im, boxes, num_classes)
+    return scores, pred_boxes
+
+
+def im_detect_shared(az_net, frcnn_net, im, num_classes):
+    """AZ-Net proposals + Fast R-CNN on the shared conv map (test.py:432-445)."""
+    boxes, conv = im_propose(az_net, im, return_conv=True)
+    if isinstance(frcnn_net.get('fc'), Net) and isinstance(az_net.get('full'), Net):
+        frcnn_net['fc'].adopt_conv(az_net['full'])
+    scores, pred_boxes, _ = _frcnn_forward(frcnn_net, im, boxes, num_classes, conv)
+    return scores, pred_boxes
+
+
+def apply_nms(all_boxes, thresh):
+    """NMS over all_boxes[cls][img] (test.py:467-484): every (class, image) problem of the whole set goes
+    into ONE batched kernel launch (segments above AZN_NMS_SEG_MAX rows use the large-N path)."""
+    from .. import _lib as L
+    num_classes, num_images = len(all_boxes), len(all_boxes[0])
+    out = [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    small, big = [], []
+    for c in range(num_classes):
+        for i in range(num_images):
+            d = all_boxes[c][i]
+            if isinstance(d, list) and d == []:
+                continue
+            if not isinstance(d, np.ndarray) or d.dtype != np.float32 or d.ndim != 2:
+                raise ValueError("Buffer dtype mismatch, expected 'float32_t'")
+            if d.shape[0] == 0:
+                continue
+            (small if d.shape[0] <= L.NMS_SEG_MAX else big).append((c, i, d))
+    if small:
+        sizes = np.array([d.shape[0] for _, _, d in small], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        dets = torch.from_numpy(np.ascontiguousarray(np.vstack([d[:, :5] for _, _, d in small]))).cuda()
+        keep, cnt = ops.nms_batched(dets, torch.from_numpy(off).cuda(), float(thresh))
+        keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+        for s, (c, i, d) in enumerate(small):
+            k = keep[off[s]:off[s] + cnt[s]]
+            if len(k):
+                out[c][i] = d[k, :].copy()
+    for c, i, d in big:
+        k = nms(d, float(thresh))
+        if len(k):
+            out[c][i] = d[k, :].copy()
+    return out
+
+
+# --------------------------------------------------------------------------- dataset drivers
+def test_proposals(net, imdb):
+    """Generate proposals on an image database and pickle them (test.py:486-539)."""
+    import cv2
+    num_images = len(imdb.image_index)
+    prop_boxes = [[] for _ in range(num_images)]
+    output_dir = get_output_dir(imdb, net['full'])
+    if not os.path.exists(output_dir):
+        os.makedirs(output_dir)
+    t = Timer()
+    num_boxes = 0.0
+    for i in range(num_images):
+        im = cv2.imread(imdb.image_path_at(i))
+        t.tic()
+        prop_boxes[i] = im_propose(net, im)
+        t.toc()
+        print('im_prop: {:d}/{:d} {:.3f}s'.format(i + 1, num_images, t.average_time))
+    recall = 0
+    prop = {'boxes': prop_boxes, 'time': t.average_time, 'recall': recall}
+    with open(os.path.join(output_dir, 'proposals.pkl'), 'wb') as f:
+        pickle.dump(prop, f, pickle.HIGHEST_PROTOCOL)
+    print('The recall is {:.3f}'.format(recall))
+    print('On average, {0} boxes per image are generated'.format(num_boxes / num_images))
+    print('The average proposal generation time is {:.3f}s'.format(t.average_time))
+
+
+def _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, num_classes):
+    """Per-class selection for one image (test.py:608-636): score > thresh[j], top-100, heap cap."""
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] > thresh[j])[0]
+        cls_scores = scores[inds, j]
+        cls_boxes = boxes[inds, j * 4:(j + 1) * 4]
+        top = np.argsort(-cls_scores, kind='stable')[:max_per_image]
+        cls_scores, cls_boxes = cls_scores[top], cls_boxes[top, :]
+        for val in cls_scores:
+            heapq.heappush(top_scores[j], val)
+        if len(top_scores[j]) > max_per_set:
+            while len(top_scores[j]) > max_per_set:
+                heapq.heappop(top_scores[j])
+            thresh[j] = top_scores[j][0]
+        all_boxes[j][i] = np.hstack((cls_boxes, cls_scores[:, np.newaxis])).astype(np.float32, copy=False)
+
+
+def _finish_detections(all_boxes, thresh, skip, imdb, output_dir):
+    for j in range(1, imdb.num_classes):
+        for i in range(len(imdb.image_index)):
+            if i in skip:
+                continue
+            inds = np.where(all_boxes[j][i][:, -1] > thresh[j])[0]
+            all_boxes[j][i] = all_boxes[j][i][inds, :]
+    with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
+        pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
+    print('Applying NMS to all detections')
+    nms_dets = apply_nms(all_boxes, cfg.TEST.NMS)
+    print('Evaluating detections')
+    imdb.evaluate_detections(nms_dets, output_dir)
+
+
+def test_net(net, prop_file, imdb):
+    """Fast R-CNN over pre-computed proposals (test.py:541-668)."""
+    import cv2
+    with open(prop_file, 'rb') as f:
+        prop = pickle.load(f)
+    prop_boxes = prop['boxes']
+    num_images = len(imdb.image_index)
+    max_per_set = 800 // (imdb.num_classes - 1) * num_images       # Python-2 integer division
+    max_per_image = 100
+    thresh = -np.inf * np.ones(imdb.num_classes)
+    top_scores = [[] for _ in range(imdb.num_classes)]
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
+    num_boxes = 0.0
+    output_dir = get_output_dir(imdb, net['full'])
+    if not os.path.exists(output_dir):
+        os.makedirs(output_dir)
+    _t = {'im_detect': Timer(), 'misc': Timer()}
+    skip = set()
+    for i in range(num_images):
+        if prop_boxes[i].shape[0] == 0:
+            skip.add(i)
+            continue
+        im = cv2.imread(imdb.image_path_at(i))
+        _t['im_detect'].tic()
+        scores, boxes = im_detect(net, im, prop_boxes[i], imdb.num_classes)
+        num_boxes += scores.shape[0]
+        _t['im_detect'].toc()
+        _t['misc'].tic()
+        _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, imdb.num_classes)
+        _t['misc'].toc()
+        print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
+                                                            _t['misc'].average_time))
+    _finish_detections(all_boxes, thresh, skip, imdb, output_dir)
+    print('The average time is proposal {:.3f}s, detection {:.3f}s'.format(prop['time'], _t['im_detect'].average_time))
+    print('On average, {0} boxes per image are generated'.format(num_boxes / num_images))
+
+
+def test_net_shared(sc_net, frcnn_net, imdb):
+    """Shared-conv detection (test.py:670-780): proposals and detection in one pass per image."""
+    import cv2
+    num_images = len(imdb.image_index)
+    max_per_set = 800 // (imdb.num_classes - 1) * num_images
+    max_per_image = 100
+    thresh = -np.inf * np.ones(imdb.num_classes)
+    top_scores = [[] for _ in range(imdb.num_classes)]
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
+    num_boxes = 0.0
+    output_dir = get_output_dir(imdb, sc_net['full'])
+    if not os.path.exists(output_dir):
+        os.makedirs(output_dir)
+    _t = {'im_detect': Timer(), 'misc': Timer()}
+    for i in range(num_images):
+        im = cv2.imread(imdb.image_path_at(i))
+        _t['im_detect'].tic()
+        scores, boxes = im_detect_shared(sc_net, frcnn_net, im, imdb.num_classes)
+        num_boxes += scores.shape[0]
+        _t['im_detect'].toc()
+        _t['misc'].tic()
+        _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, imdb.num_classes)
+        _t['misc'].toc()
+        print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
+                                                            _t['misc'].average_time))
+    _finish_detections(all_boxes, thresh, set(), imdb, output_dir)
+    print('The average detection time is {:.3f}s'.format(_t['im_detect'].average_time))
+    print('On average, {0} boxes per image are proposed'.format(num_boxes / num_images))

@@ -1,0 +1,18 @@
+"""Wall-clock timer with the interface of lib/utils/timer.py:10-32 (tic / toc / average_time)."""
+import time
+
+
+class Timer(object):
+    def __init__(self):
+        self.total_time = self.start_time = self.diff = self.average_time = 0.
+        self.calls = 0
+
+    def tic(self):
+        self.start_time = time.time()
+
+    def toc(self, average=True):
+        self.diff = time.time() - self.start_time
+        self.total_time += self.diff
+        self.calls += 1
+        self.average_time = self.total_time / self.calls
+        return self.average_time if average else self.diff
