@@ -23,7 +23,7 @@ def gather_proposals(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Te
     world = dist.get_world_size()
     outs = []
     for t in (boxes, scores, counts):
-        buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(buf, t.contiguous())
-        outs.append(buf.view((-1,) + tuple(t.shape[1:])))
+        outs.append(buf)
     return tuple(outs)

@@ -1,0 +1,131 @@
+"""CPU suite: host-side logic of the drop-in layer (config system, shard/gather plumbing with gloo at
+world_size 2, blob helpers, capacity/depth planning) -- nothing here needs a GPU."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from aznet_b200.detect import config as C
+from aznet_b200 import dist as azdist
+from aznet_b200 import synth
+
+
+def test_cfg_defaults_and_mode():
+    cfg = C.cfg
+    assert cfg.TEST.SCALES == (600,) and cfg.TEST.MAX_SIZE in (800, 1000) and cfg.TEST.NMS == 0.5
+    assert cfg.SEAR.MIN_SIDE == 10 and cfg.SEAR.NUM_SUBREG == 11 and abs(cfg.DEDUP_BOXES - 1 / 16.) < 1e-12
+    assert cfg.EPS == 1e-14 and cfg.SEAR.AZ_CONV == ['conv5_3']
+    C.cfg_set_mode('Train')
+    assert cfg.SEAR.Tz == 0.0 and cfg.SEAR.NUM_PROPOSALS == 2000
+    with pytest.raises(AssertionError):
+        C.cfg_set_mode('Test')                      # "testing Tz is not set!"
+    C.cfg_set_mode('Test', 0.37)
+    assert cfg.SEAR.Tz == 0.37 and cfg.SEAR.NUM_PROPOSALS == 300
+
+
+def test_cfg_from_file_voc_like(tmp_path):
+    yml = tmp_path / "voc.yml"                      # the values of experiments/cfgs/voc.yml
+    yml.write_text("TRAIN:\n  IMS_PER_BATCH: 1\n  MAX_SIZE: 800\nTEST:\n  MAX_SIZE: 800\n  NUM_PROPOSALS: 300\n"
+                   "SEAR:\n  FIXED_PROPOSAL_NUM: True\n  BATCH_SIZE: 1000\n  AZ_CONV: [conv5_3]\n  FRCNN_CONV: [conv5_3]\n")
+    old = (C.cfg.TEST.MAX_SIZE, C.cfg.SEAR.BATCH_SIZE)
+    try:
+        C.cfg_from_file(str(yml))
+        assert C.cfg.TEST.MAX_SIZE == 800 and C.cfg.SEAR.BATCH_SIZE == 1000
+        bad = tmp_path / "bad.yml"
+        bad.write_text("TEST:\n  NOT_A_KEY: 1\n")
+        with pytest.raises(KeyError):
+            C.cfg_from_file(str(bad))
+        bad.write_text("TEST:\n  MAX_SIZE: big\n")
+        with pytest.raises(ValueError):
+            C.cfg_from_file(str(bad))
+    finally:
+        C.cfg.TEST.MAX_SIZE, C.cfg.SEAR.BATCH_SIZE = old
+
+
+def test_cfg_paths_and_thresh(tmp_path):
+    C.cfg_set_path(None)
+    assert C.cfg.EXP_DIR == 'default'
+    C.cfg_set_path('exp1')
+
+    class I:
+        name = 'voc_2007_test'
+
+    class N:
+        name = 'vgg16_az'
+    assert C.get_output_dir(I, N).endswith(os.path.join('output', 'exp1', 'voc_2007_test', 'vgg16_az'))
+    assert C.get_output_dir(I, None).endswith(os.path.join('output', 'exp1', 'voc_2007_test'))
+    p = tmp_path / "thresh.pkl"
+    pickle.dump(0.42, open(p, "wb"))
+    assert C.cfg_load_thresh(str(p)) == 0.42
+
+
+def test_blob_helpers():
+    from aznet_b200.utils.blob import im_list_to_blob, prep_im_for_blob
+    a, b = np.ones((4, 6, 3), np.float32), 2 * np.ones((5, 3, 3), np.float32)
+    blob = im_list_to_blob([a, b])
+    assert blob.shape == (2, 3, 5, 6) and blob.dtype == np.float32
+    assert blob[0, :, :4, :6].min() == 1 and blob[0, :, 4:, :].max() == 0 and blob[1, :, :, 3:].max() == 0
+    im, s = prep_im_for_blob(np.zeros((600, 1000, 3), np.uint8), np.zeros((1, 1, 3)), 600, 800)
+    assert s == 0.8 and im.shape[:2] == (480, 800)
+
+
+def test_depth_scale_planning():
+    from aznet_b200.engine import im_scale_for, search_depth
+    assert search_depth(600, 1000, 10) == 6 and search_depth(375, 500, 10) == 6 and search_depth(100, 100, 10) == 4
+    assert im_scale_for(600, 1000, (600,), 1000) == 1.0 and im_scale_for(600, 1000, (600,), 800) == 0.8
+    assert synth.conv_shape(600, 1000, 1.0) == (38, 63) and synth.conv_shape(600, 1000, 0.8) == (30, 50)
+
+
+def test_shard_images_partition():
+    for n, w in ((1024, 8), (10, 4), (3, 8), (0, 2)):
+        parts = [azdist.shard_images(n, r, w) for r in range(w)]
+        covered = [i for lo, hi in parts for i in range(lo, hi)]
+        assert covered == list(range(n))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_img = 16
+    lo, hi = azdist.shard_images(n_img, rank, world)
+    P = 5
+    boxes = torch.zeros((hi - lo, P, 4), dtype=torch.float64)
+    scores = torch.zeros((hi - lo, P), dtype=torch.float32)
+    counts = torch.zeros((hi - lo,), dtype=torch.int32)
+    for j, img in enumerate(range(lo, hi)):                     # each image's "proposals" encode its index
+        counts[j] = 1 + img % P
+        boxes[j, :counts[j]] = img
+        scores[j, :counts[j]] = img / 100.0
+    b, s, c = azdist.gather_proposals(boxes, scores, counts)
+    ok = b.shape == (n_img, P, 4) and all(int(c[i]) == 1 + i % P and float(b[i, 0, 0]) == i for i in range(n_img))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gather_proposals_gloo_world2():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(30) for p in procs]
+    assert res == [(0, True), (1, True)]
+
+
+def test_hashnet_is_deterministic():
+    net = synth.HashNet(seed=11)
+    r = synth.make_rois(50, seed=1)
+    z1, p1, d1 = net.heads(r)
+    z2, p2, d2 = net.heads(r.copy())
+    assert np.array_equal(z1, z2) and np.array_equal(p1, p2) and np.array_equal(d1, d2)
+    assert z1.shape == (50, 1) and p1.shape == (50, 11) and d1.shape == (50, 44)
+    assert 0 <= p1.min() and p1.max() < 1

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Condense `ncu --set full` reports (gpurun_out/*.ncu-rep) into small CSV summaries for profiles/:
+one row per captured launch with the metrics B200_PROFILING.md asks for.
+    python tools/ncu_summary.py gpurun_out/prof_gemm.ncu-rep profiles/r1_gemm.csv"""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max"]
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = [hdr.index(w) for w in WANT if w in hdr]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] + (" [%s]" % units[i] if units[i] else "") for i in idx])
+        for r in rows[2:]:
+            w.writerow([r[i] for i in idx])
+    print("wrote", out, len(rows) - 2, "launches")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
