@@ -26,7 +26,7 @@ ACT_NONE, ACT_RELU, ACT_AZ_HEAD, ACT_SOFTMAX_BBOX = 0, 1, 2, 3
 NMS_SEG_MAX = 1024
 
 EXPORTS = [
-    "azn_version", "azn_last_error", "azn_check_device", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
+    "azn_version", "azn_last_error", "azn_check_device", "azn_roi_pool_workspace_bytes", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
     "azn_fc_workspace_bytes", "azn_fc_forward", "azn_search_init", "azn_search_level", "azn_select_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched",
@@ -91,7 +91,9 @@ def _bind(L):
     L.azn_last_error.restype = C.c_char_p
     L.azn_check_device.restype = i32
     L.azn_roi_pool_fwd.restype = i32
-    L.azn_roi_pool_fwd.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp, vp]
+    L.azn_roi_pool_fwd.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp, vp, sz, vp]
+    L.azn_roi_pool_workspace_bytes.restype = sz
+    L.azn_roi_pool_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
     L.azn_nchw_f32_to_nhwc_bf16.restype = i32
     L.azn_nchw_f32_to_nhwc_bf16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.azn_fc_workspace_bytes.restype = sz

@@ -17,10 +17,15 @@
 //               bias + ReLU / sigmoid, 16-byte stores.  Two accumulator buffers in TMEM
 //               (2 x BLOCK_N columns) let the epilogue of tile i overlap the main loop of tile i+1.
 // Scheduling is decided ON THE DEVICE from the live row count (the search keeps its region counts
-// in HBM): tiles = ceil(m_live/128) x ceil(N/BLOCK_N); when that is smaller than the grid the K
-// loop is split across CTAs (weight-streaming regime of the shallow search levels), partial sums
-// go to a fixed 148-slot fp32 workspace and fc_splitk_finish_kernel reduces them in split order
-// (deterministic, no atomics) and applies the epilogue.
+// in HBM) as a data-parallel + stream-K hybrid: tiles = ceil(m_live/128) x ceil(N/BLOCK_N); whole
+// waves of tiles go one per CTA, and the k-blocks of the remaining tiles (plus one full wave, so
+// that no tile is cut into more than ~3 pieces) are dealt out evenly over all CTAs as contiguous
+// (tile, k-block) ranges.  A CTA that computes the middle or the tail of a tile dumps its raw fp32
+// accumulator into its own slot of a fixed 148-slot workspace and raises a flag (release); the CTA
+// that computes the head of the tile waits for those flags (acquire), adds the partials in CTA
+// order (deterministic, no atomics on data) and runs the epilogue.  With few tiles (the shallow
+// search levels: M = 64 .. 2048) this turns into an even split of the K loop across the whole
+// chip, i.e. every SM streams its share of the 205 MB int6 weight matrix.
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -32,7 +37,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
-constexpr int MAX_SPLIT = 32;
+
 
 template <int BLOCK_N> struct Cfg {
     static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
@@ -148,26 +153,78 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct Sched {
-    int m_live, m_tiles, n_tiles, tiles, split, units, kblocks;
+constexpr int MIN_KB_PER_CTA = 4;      // do not cut the K loop finer than this many 64-wide k-blocks
+
+// Work decomposition, identical on every CTA and every warp role (pure function of m_live and the grid).
+struct Plan {
+    int m_live, m_tiles, n_tiles, tiles, kblocks;
+    int dp_tiles, sk_tiles, g_eff;         // data-parallel tiles (first), stream-K tiles (last), CTAs sharing them
+    long units;                            // sk_tiles * kblocks
+    int n_major;                           // raster order of tile ids
 };
-__device__ __forceinline__ Sched make_sched(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int grid) {
-    Sched s;
-    s.m_live = m_live_ptr ? min(max(*m_live_ptr, 0), M_cap) : M_cap;
-    s.m_tiles = (s.m_live + BLOCK_M - 1) / BLOCK_M;
-    s.n_tiles = (N + block_n - 1) / block_n;
-    s.tiles = s.m_tiles * s.n_tiles;
-    s.kblocks = K / BLOCK_K;
-    s.split = 1;
-    if (s.tiles > 0 && s.tiles * 2 <= grid) {
-        s.split = grid / s.tiles;
-        if (s.split > s.kblocks) s.split = s.kblocks;
-        if (s.split > MAX_SPLIT) s.split = MAX_SPLIT;
-        if (s.split < 1) s.split = 1;
-    }
-    s.units = s.tiles * s.split;
-    return s;
+struct Work {
+    int tile, kb0, kb1, kind;              // kind 0: whole tile, 1: partial producer, 2: owner (head of a split tile)
+};
+enum { WORK_FULL = 0, WORK_PARTIAL = 1, WORK_OWNER = 2 };
+
+__device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int grid) {
+    Plan p;
+    p.m_live = m_live_ptr ? min(max(*m_live_ptr, 0), M_cap) : M_cap;
+    p.m_tiles = (p.m_live + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = (N + block_n - 1) / block_n;
+    p.tiles = p.m_tiles * p.n_tiles;
+    p.kblocks = K / BLOCK_K;
+    const int full = p.tiles / grid, rem = p.tiles - full * grid;
+    if (rem == 0) p.sk_tiles = 0;
+    else p.sk_tiles = full >= 1 ? rem + grid : rem;
+    p.dp_tiles = p.tiles - p.sk_tiles;
+    p.units = (long)p.sk_tiles * p.kblocks;
+    long g = p.units / MIN_KB_PER_CTA;
+    p.g_eff = (int)(g < 1 ? 1 : (g > grid ? grid : g));
+    // operands are re-read from HBM once per wave of tiles that does not share them: keep the bigger one
+    // (W: N*K, A: m_live*K) shared inside a wave
+    p.n_major = p.m_live < N ? 1 : 0;
+    return p;
 }
+__device__ __forceinline__ long sk_begin(const Plan &p, int g) { return p.units * g / p.g_eff; }
+
+// idx-th piece of work of CTA `cta`: stream-K segments first (range order), then data-parallel tiles.
+__device__ __forceinline__ bool get_work(const Plan &p, int cta, int grid, int idx, Work &w) {
+    if (p.sk_tiles > 0 && cta < p.g_eff) {
+        const long u0 = sk_begin(p, cta), u1 = sk_begin(p, cta + 1);
+        if (u1 > u0) {
+            const int first = (int)(u0 / p.kblocks), last = (int)((u1 - 1) / p.kblocks);
+            if (idx <= last - first) {
+                const int sidx = first + idx;
+                const long t0 = (long)sidx * p.kblocks;
+                w.kb0 = (int)((u0 > t0 ? u0 : t0) - t0);
+                w.kb1 = (int)((u1 < t0 + p.kblocks ? u1 : t0 + p.kblocks) - t0);
+                w.tile = p.dp_tiles + sidx;
+                w.kind = (w.kb0 == 0 && w.kb1 == p.kblocks) ? WORK_FULL : (w.kb0 == 0 ? WORK_OWNER : WORK_PARTIAL);
+                return true;
+            }
+            idx -= last - first + 1;
+        }
+    }
+    const long t = (long)cta + (long)idx * grid;
+    if (t >= p.dp_tiles) return false;
+    w.tile = (int)t; w.kb0 = 0; w.kb1 = p.kblocks; w.kind = WORK_FULL;
+    return true;
+}
+__device__ __forceinline__ void tile_coords(const Plan &p, int tile, int &m_tile, int &n_tile) {
+    if (p.n_major) { n_tile = tile / p.m_tiles; m_tile = tile - n_tile * p.m_tiles; }
+    else           { m_tile = tile / p.n_tiles; n_tile = tile - m_tile * p.n_tiles; }
+}
+
+__device__ __forceinline__ void flag_release(int *flag) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+__device__ __forceinline__ int flag_acquire(const int *flag) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ float sigmoid_caffe(float x) {
     // sigmoid_layer.cpp:11-13: exp in float, `1. / (1. + e)` in double, rounded to float
@@ -185,7 +242,8 @@ struct EpiParams {
     const float *bias;
     void *out;
     int out_dtype, ldo, N, act, act_aux;
-    float *ws;           // split-K partials: [unit][BLOCK_M][BLOCK_N] fp32
+    float *ws;           // stream-K partials: [cta][BLOCK_M][BLOCK_N] fp32
+    int *flags;          // [grid] "partial of CTA g is in its slot" (zero between launches)
 };
 
 template <int BLOCK_N>
@@ -202,7 +260,8 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Sched sc = make_sched(m_live_ptr, M_cap, N, K, BLOCK_N, gridDim.x);
+    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, BLOCK_N, gridDim.x);
+    const int cta = blockIdx.x, grid = gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -221,11 +280,11 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int u = blockIdx.x; u < sc.units; u += gridDim.x) {
-                const int tile = u % sc.tiles, ks = u / sc.tiles;
-                const int m_tile = tile / sc.n_tiles, n_tile = tile % sc.n_tiles;
-                const int kb0 = (int)((long)sc.kblocks * ks / sc.split), kb1 = (int)((long)sc.kblocks * (ks + 1) / sc.split);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            Work w;
+            for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx) {
+                int m_tile, n_tile;
+                tile_coords(pl, w.tile, m_tile, n_tile);
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
@@ -239,16 +298,15 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N);
-            uint32_t it = 0, ut = 0;
-            for (int u = blockIdx.x; u < sc.units; u += gridDim.x, ++ut) {
-                const int ks = u / sc.tiles;
-                const int kb0 = (int)((long)sc.kblocks * ks / sc.split), kb1 = (int)((long)sc.kblocks * (ks + 1) / sc.split);
-                const int a = ut & 1;
-                const uint32_t aph = (ut >> 1) & 1;
+            uint32_t it = 0;
+            Work w;
+            for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx) {
+                const int a = idx & 1;
+                const uint32_t aph = ((uint32_t)idx >> 1) & 1;
                 mbar_wait(&tmem_empty[a], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(a * BLOCK_N);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&full[s], ph);
@@ -258,78 +316,110 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
                 }
-                umma_commit(&tmem_full[a]);          // accumulator complete
+                umma_commit(&tmem_full[a]);          // accumulator (or partial accumulator) complete
             }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-        uint32_t ut = 0;
-        for (int u = blockIdx.x; u < sc.units; u += gridDim.x, ++ut) {
-            const int tile = u % sc.tiles;
-            const int m_tile = tile / sc.n_tiles, n_tile = tile % sc.n_tiles;
-            const int a = ut & 1;
-            const uint32_t aph = (ut >> 1) & 1;
+        const int trow = q * 32 + lane;              // row of the tile owned by this thread
+        Work w;
+        for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx) {
+            int m_tile, n_tile;
+            tile_coords(pl, w.tile, m_tile, n_tile);
+            const int a = idx & 1;
+            const uint32_t aph = ((uint32_t)idx >> 1) & 1;
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
-            const int row = m_tile * BLOCK_M + q * 32 + lane;
+            const int row = m_tile * BLOCK_M + trow;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BLOCK_N);
-            const bool row_ok = row < sc.m_live;
+            const bool row_ok = row < pl.m_live;
+            // peers of a split tile: the CTAs after this one whose stream-K range still lies inside the tile
+            int peers = 0;
+            if (w.kind == WORK_OWNER) {
+                const long tile_end = (long)(w.tile - pl.dp_tiles + 1) * pl.kblocks;
+                while (cta + 1 + peers < pl.g_eff && sk_begin(pl, cta + 1 + peers) < tile_end) ++peers;
+                if (threadIdx.x == 64) {
+                    for (int j = 1; j <= peers; ++j)
+                        while (flag_acquire(ep.flags + cta + j) == 0) { }
+                }
+                epi_bar_sync();
+            }
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();
                 const int col0 = n_tile * BLOCK_N + c * 32;
-                if (sc.split > 1) {
-                    float *dst = ep.ws + ((size_t)u * BLOCK_M + (q * 32 + lane)) * BLOCK_N + c * 32;
+                if (w.kind == WORK_PARTIAL) {
+                    float *dst = ep.ws + ((size_t)cta * BLOCK_M + trow) * BLOCK_N + c * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *(uint4 *)(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                } else if (row_ok && col0 < ep.N) {
-                    float v[32];
+                        __stcg((uint4 *)(dst + j), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+                    continue;
+                }
+                if (!(row_ok && col0 < ep.N)) continue;
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        const float b = col < ep.N ? __ldg(ep.bias + col) : 0.f;
-                        v[j] = apply_act(__uint_as_float(r[j]) + b, ep.act, col, ep.act_aux);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int pj = 1; pj <= peers; ++pj) {           // fixed CTA order => deterministic sum
+                    const float *src = ep.ws + ((size_t)(cta + pj) * BLOCK_M + trow) * BLOCK_N + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 t = __ldcg((const float4 *)(src + j));
+                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
-                    if (ep.out_dtype == AZN_DTYPE_BF16) {
-                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0;
-                        if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
+                }
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint32_t p[4];
+                for (int j = 0; j < 32; ++j) {
+                    const int col = col0 + j;
+                    const float b = col < ep.N ? __ldg(ep.bias + col) : 0.f;
+                    v[j] = apply_act(v[j] + b, ep.act, col, ep.act_aux);
+                }
+                if (ep.out_dtype == AZN_DTYPE_BF16) {
+                    __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0;
+                    if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                                    p[t] = *(uint32_t *)&h;
-                                }
-                                *(uint4 *)(dst + j) = make_uint4(p[0], p[1], p[2], p[3]);
+                        for (int j = 0; j < 32; j += 8) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                                pk[t] = *(uint32_t *)&h;
                             }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < ep.N) dst[j] = __float2bfloat16_rn(v[j]);
+                            *(uint4 *)(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     } else {
-                        float *dst = (float *)ep.out + (size_t)row * ep.ldo + col0;
-                        if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) dst[j] = __float2bfloat16_rn(v[j]);
+                    }
+                } else {
+                    float *dst = (float *)ep.out + (size_t)row * ep.ldo + col0;
+                    if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < ep.N) dst[j] = v[j];
-                        }
+                        for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) dst[j] = v[j];
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
+            if (w.kind == WORK_PARTIAL) {
+                __threadfence();                      // partial visible device-wide before the flag
+                epi_bar_sync();
+                if (threadIdx.x == 64) flag_release(ep.flags + cta);
+            } else if (w.kind == WORK_OWNER) {
+                epi_bar_sync();                       // every epilogue thread is done reading the peers' slots
+                if (threadIdx.x == 64)
+                    for (int j = 1; j <= peers; ++j) ep.flags[cta + j] = 0;     // leave the flags clean for the next launch
+            }
         }
     }
     tc_fence_before();
@@ -337,29 +427,6 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
-    }
-}
-
-// Reduces the split-K partials in split order and applies bias + activation.
-__global__ void __launch_bounds__(256)
-fc_splitk_finish_kernel(const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, int block_n, int grid_gemm,
-                        EpiParams ep) {
-    const Sched sc = make_sched(m_live_ptr, M_cap, N, K, block_n, grid_gemm);
-    if (sc.split <= 1) return;
-    const long total = (long)sc.m_live * N;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int row = (int)(e / N), col = (int)(e - (long)row * N);
-        const int m_tile = row / BLOCK_M, n_tile = col / block_n;
-        const int tile = m_tile * sc.n_tiles + n_tile;
-        const size_t inner = (size_t)(row - m_tile * BLOCK_M) * block_n + (col - n_tile * block_n);
-        float acc = 0.f;
-        for (int ks = 0; ks < sc.split; ++ks) {
-            const int u = ks * sc.tiles + tile;
-            acc += ep.ws[(size_t)u * BLOCK_M * block_n + inner];
-        }
-        const float v = apply_act(acc + ep.bias[col], ep.act, col, ep.act_aux);
-        if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(v);
-        else ((float *)ep.out)[(size_t)row * ep.ldo + col] = v;
     }
 }
 
@@ -454,8 +521,8 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_l
 
 extern "C" size_t azn_fc_workspace_bytes(int M_cap, int N, int K) {
     (void)M_cap; (void)K;
-    // split-K only engages when tiles*split <= grid, so `grid` slots of one 128 x BLOCK_N fp32 tile suffice
-    return (size_t)azn_num_sms() * BLOCK_M * pick_block_n(N) * sizeof(float);
+    // one 128 x BLOCK_N fp32 slot per CTA (a CTA produces at most one partial per launch) + the flag words
+    return (size_t)azn_num_sms() * BLOCK_M * pick_block_n(N) * sizeof(float) + 4096;
 }
 
 extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype, int ldo,
@@ -474,7 +541,9 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     cudaStream_t s = (cudaStream_t)stream;
     const int bn = pick_block_n(N);
     const int grid = azn_num_sms();
-    const size_t need = (size_t)grid * BLOCK_M * bn * sizeof(float);
+    const size_t slots = (size_t)grid * BLOCK_M * bn * sizeof(float);
+    const size_t need = slots + 4096;
+    AZN_REQUIRE(grid * sizeof(int) <= 4096, "azn_fc_forward: grid too large for the flag block");
     if (!workspace || workspace_bytes < need) {
         azn_set_error("azn_fc_forward: workspace %zu < %zu bytes", workspace_bytes, need);
         return AZN_ERR_CAPACITY;
@@ -489,15 +558,11 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     ep.act = act == AZN_ACT_SOFTMAX_BBOX ? AZN_ACT_NONE : act;
     ep.act_aux = act_aux;
     ep.ws = (float *)workspace;
+    ep.flags = (int *)((char *)workspace + slots);
     if (bn == 256) rc = launch_gemm<256>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 128) rc = launch_gemm<128>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else rc = launch_gemm<64>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     if (rc) return rc;
-    // split-K is decided on the device; the finish kernel returns immediately when split == 1
-    if ((long)((M_cap + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn) * 2 <= grid || m_live != nullptr) {
-        fc_splitk_finish_kernel<<<grid * 2, 256, 0, s>>>(m_live, M_cap, N, K, bn, grid, ep);
-        AZN_LAUNCH_CHECK();
-    }
     if (act == AZN_ACT_SOFTMAX_BBOX) {
         softmax_rows_kernel<<<grid, 256, 0, s>>>((float *)out, m_live, M_cap, ldo, act_aux);
         AZN_LAUNCH_CHECK();

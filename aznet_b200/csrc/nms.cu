@@ -12,17 +12,17 @@
 // a multiply-add into an FMA (x86-64 gcc, which built the reference, has no FMA by default).
 //
 // Large single problem (azn_nms), four launches on one stream:
-//   1. nms_rank_kernel   -- rank sort by (score desc, index desc): every thread counts the
-//                           detections that precede its own, tile by tile out of shared memory,
-//                           and scatters its box to the sorted position.
+//   1. nms_rank_kernel   -- rank sort by (score desc, index desc) on a 2-D grid: every thread counts
+//      nms_scatter_kernel   the detections of one score tile that precede its own (shared memory),
+//                           partial counts are added atomically, then boxes move to sorted position.
 //   2. nms_mask_kernel   -- 64x64 IoU tiles of the upper triangle -> one 64-bit suppression word
-//                           per (row, column tile).
-//   3. nms_scan_kernel   -- one CTA walks the column tiles in order: warp 0 resolves the 64x64
-//                           diagonal block with register-resident words exchanged by shuffles,
-//                           the whole CTA then ORs the rows of the boxes that were kept into the
-//                           running `removed` bitmap in shared memory, and the kept original
-//                           indices are appended to `keep` (on-device compaction; the count
-//                           never visits the host).
+//                           per (row, column tile); exact intersection pre-test, division only
+//                           for intersecting pairs.
+//   3. nms_scan_kernel   -- one CTA walks the column tiles in order: it gathers (pull) the column
+//                           word of every row kept so far and OR-reduces it with warp shuffles,
+//                           warp 0 resolves the 64x64 diagonal block over the surviving rows with
+//                           register-resident words, and the kept original indices are appended to
+//                           `keep` (on-device compaction; the count never visits the host).
 // Many small problems (azn_nms_batched, one per class per image in apply_nms,
 // lib/detect/test.py:467-484): one warp per problem, boxes in shared memory, the suppression
 // state in per-lane registers exchanged with ballots.
@@ -62,33 +62,51 @@ __device__ __forceinline__ bool precedes(float sj, int j, float si, int i) {
 constexpr int RANK_THREADS = 256;
 constexpr int RANK_TILE = 2048;
 
+// grid = (ceil(n/256), ceil(n/RANK_TILE)): block (bx, by) counts, for its 256 detections, how many of the
+// by-th tile of detections precede each of them, and adds the partial count to rank[i].
 __global__ void __launch_bounds__(RANK_THREADS)
-nms_rank_kernel(const float *__restrict__ dets, int n, float4 *__restrict__ boxes, float *__restrict__ areas,
-                int *__restrict__ order) {
+nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank) {
     __shared__ float s_tile[RANK_TILE];
     const int i = blockIdx.x * RANK_THREADS + threadIdx.x;
-    const float si = i < n ? dets[(size_t)i * 5 + 4] : 0.f;
-    int rank = 0;
-    for (int t0 = 0; t0 < n; t0 += RANK_TILE) {
-        const int tn = min(RANK_TILE, n - t0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < tn; k += RANK_THREADS) s_tile[k] = dets[(size_t)(t0 + k) * 5 + 4];
-        __syncthreads();
-        if (i < n) {
+    const int t0 = blockIdx.y * RANK_TILE, tn = min(RANK_TILE, n - t0);
+    for (int k = threadIdx.x; k < tn; k += RANK_THREADS) s_tile[k] = dets[(size_t)(t0 + k) * 5 + 4];
+    __syncthreads();
+    if (i >= n) return;
+    const float si = dets[(size_t)i * 5 + 4];
+    int cnt = 0;
 #pragma unroll 8
-            for (int k = 0; k < tn; ++k) rank += precedes(s_tile[k], t0 + k, si, i) ? 1 : 0;
-        }
-    }
-    if (i < n) {
-        const float *d = dets + (size_t)i * 5;
-        float4 b = make_float4(d[0], d[1], d[2], d[3]);
-        boxes[rank] = b;
-        areas[rank] = box_area(b.x, b.y, b.z, b.w);
-        order[rank] = i;
-    }
+    for (int k = 0; k < tn; ++k) cnt += precedes(s_tile[k], t0 + k, si, i) ? 1 : 0;
+    if (cnt) atomicAdd(rank + i, cnt);
 }
 
-// grid = (col_tiles, row_tiles), 64 threads; only tiles with col >= row do work.
+__global__ void __launch_bounds__(256)
+nms_scatter_kernel(const float *__restrict__ dets, int n, const int *__restrict__ rank, float4 *__restrict__ boxes,
+                   float *__restrict__ areas, int *__restrict__ order) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float *d = dets + (size_t)i * 5;
+    const float4 b = make_float4(d[0], d[1], d[2], d[3]);
+    const int r = rank[i];
+    boxes[r] = b;
+    areas[r] = box_area(b.x, b.y, b.z, b.w);
+    order[r] = i;
+}
+
+// true iff the clamped intersection of a and b is non-empty (w > 0 and h > 0 with the reference's f32 ops)
+__device__ __forceinline__ bool intersects(const float4 &a, const float4 &b) {
+    float xx1 = a.x >= b.x ? a.x : b.x;
+    float yy1 = a.y >= b.y ? a.y : b.y;
+    float xx2 = a.z <= b.z ? a.z : b.z;
+    float yy2 = a.w <= b.w ? a.w : b.w;
+    float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.f);
+    float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
+    return w > 0.f && h > 0.f;
+}
+
+// grid = (col_tiles, row_tiles), 64 threads; only tiles with col >= row do work.  Two phases per thread:
+// a cheap exact intersection test over the 64 columns, then the full IoU (IEEE division + double compare)
+// only for the columns that intersect -- with an empty intersection the reference computes ovr = +-0 or
+// NaN, which is >= thresh for no positive threshold, so those pairs can never be suppressed.
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
                 u64 *__restrict__ mask, int col_tiles) {
@@ -106,64 +124,87 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
     if (row >= n) return;
     const float4 rb = boxes[row];
     const float ra = areas[row];
-    u64 bits = 0;
     const int start = (rt == ct) ? threadIdx.x + 1 : 0;
-    for (int k = start; k < cn; ++k)
+    u64 cand = 0;
+    if (thresh > 0.0) {
+        for (int k = start; k < cn; ++k) cand |= (u64)(intersects(rb, cb[k]) ? 1 : 0) << k;
+    } else {
+        cand = (cn == 64 ? ~0ull : ((1ull << cn) - 1ull)) & (start >= 64 ? 0ull : (~0ull << start));
+    }
+    u64 bits = 0;
+    while (cand) {
+        const int k = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
         if (suppresses(rb, ra, cb[k], ca[k], thresh)) bits |= 1ull << k;
+    }
     mask[(size_t)row * col_tiles + ct] = bits;
 }
 
 constexpr int SCAN_THREADS = 1024;
 
+// One CTA walks the column tiles in score order.  For tile b it PULLS the suppression word of column tile b
+// from every row kept so far (parallel gather + OR-reduction), warp 0 resolves the 64x64 diagonal block by
+// iterating over the surviving rows only, and the kept rows are appended to `keep` / `kept_rows`.
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_scan_kernel(const u64 *__restrict__ mask, const int *__restrict__ order, int n, int col_tiles,
-                int64_t *__restrict__ keep, int32_t *__restrict__ keep_count) {
-    extern __shared__ u64 removed[];   // [col_tiles]
-    __shared__ u64 s_kept;
+                int *__restrict__ kept_rows, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count) {
+    __shared__ u64 s_or[SCAN_THREADS / 32];
     __shared__ int s_nkept;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int w = tid; w < col_tiles; w += SCAN_THREADS) removed[w] = 0;
     if (tid == 0) s_nkept = 0;
     __syncthreads();
     for (int b = 0; b < col_tiles; ++b) {
         const int row0 = b * 64;
+        const int nkept = s_nkept;
+        // diagonal words first (independent of the gather below)
+        u64 d_lo = 0, d_hi = 0;
         if (warp == 0) {
             const int r_lo = row0 + lane, r_hi = row0 + 32 + lane;
-            const u64 d_lo = r_lo < n ? mask[(size_t)r_lo * col_tiles + b] : 0ull;
-            const u64 d_hi = r_hi < n ? mask[(size_t)r_hi * col_tiles + b] : 0ull;
-            u64 cur = removed[b];
-            u64 kept = 0;
+            d_lo = r_lo < n ? mask[(size_t)r_lo * col_tiles + b] : 0ull;
+            d_hi = r_hi < n ? mask[(size_t)r_hi * col_tiles + b] : 0ull;
+        }
+        u64 acc = 0;
+        int j = tid;
+        for (; j + 3 * SCAN_THREADS < nkept; j += 4 * SCAN_THREADS) {
+            const int r0 = __ldcg(kept_rows + j), r1 = __ldcg(kept_rows + j + SCAN_THREADS), r2 = __ldcg(kept_rows + j + 2 * SCAN_THREADS),
+                      r3 = __ldcg(kept_rows + j + 3 * SCAN_THREADS);
+            const u64 m0 = mask[(size_t)r0 * col_tiles + b], m1 = mask[(size_t)r1 * col_tiles + b],
+                      m2 = mask[(size_t)r2 * col_tiles + b], m3 = mask[(size_t)r3 * col_tiles + b];
+            acc |= m0 | m1 | m2 | m3;
+        }
+        for (; j < nkept; j += SCAN_THREADS) acc |= mask[(size_t)__ldcg(kept_rows + j) * col_tiles + b];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) s_or[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            u64 cur = s_or[lane];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cur |= __shfl_xor_sync(0xffffffffu, cur, d);
             const int rows = min(64, n - row0);
-            for (int r = 0; r < rows; ++r) {
+            u64 alive = ~cur & (rows == 64 ? ~0ull : ((1ull << rows) - 1ull));
+            u64 kept = 0;
+            while (alive) {                                   // warp-uniform: every lane holds the same `alive`
+                const int r = __ffsll((long long)alive) - 1;
+                kept |= 1ull << r;
                 const u64 d = __shfl_sync(0xffffffffu, r < 32 ? d_lo : d_hi, r & 31);
-                if (!((cur >> r) & 1ull)) {
-                    kept |= 1ull << r;
-                    cur |= d;
-                }
+                alive &= ~d;
+                alive &= ~(1ull << r);
             }
-            const int base = s_nkept;
-            if (r_lo < n && ((kept >> lane) & 1ull))
-                keep[base + __popcll(kept & ((1ull << lane) - 1ull))] = order[r_lo];
-            if (r_hi < n && ((kept >> (lane + 32)) & 1ull))
-                keep[base + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = order[r_hi];
-            __syncwarp();
-            if (lane == 0) {
-                s_kept = kept;
-                s_nkept = base + __popcll(kept);
+            const int r_lo = row0 + lane, r_hi = row0 + 32 + lane;
+            if ((kept >> lane) & 1ull) {
+                const int pos = nkept + __popcll(kept & ((1ull << lane) - 1ull));
+                keep[pos] = order[r_lo];
+                kept_rows[pos] = r_lo;
             }
+            if ((kept >> (lane + 32)) & 1ull) {
+                const int pos = nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull));
+                keep[pos] = order[r_hi];
+                kept_rows[pos] = r_hi;
+            }
+            if (lane == 0) s_nkept = nkept + __popcll(kept);
         }
-        __syncthreads();
-        const u64 kept = s_kept;
-        for (int w = b + 1 + tid; w < col_tiles; w += SCAN_THREADS) {
-            u64 acc = 0, k = kept;
-            while (k) {
-                const int r = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                acc |= mask[(size_t)(row0 + r) * col_tiles + w];
-            }
-            removed[w] |= acc;
-        }
-        __syncthreads();
+        __syncthreads();      // kept_rows / s_nkept visible to the whole CTA (global writes by the same CTA)
     }
     if (tid == 0) *keep_count = s_nkept;
 }
@@ -220,7 +261,7 @@ nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ s
 struct NmsWorkspace {
     float4 *boxes;
     float *areas;
-    int *order;
+    int *order, *rank, *kept_rows;
     u64 *mask;
 };
 
@@ -232,6 +273,8 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
     w.boxes = (float4 *)p;  p += align_up(sizeof(float4) * n, 256);
     w.areas = (float *)p;   p += align_up(sizeof(float) * n, 256);
     w.order = (int *)p;     p += align_up(sizeof(int) * n, 256);
+    w.rank = (int *)p;      p += align_up(sizeof(int) * n, 256);
+    w.kept_rows = (int *)p; p += align_up(sizeof(int) * n, 256);
     w.mask = (u64 *)p;
     (void)col_tiles;
     return w;
@@ -242,7 +285,7 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
 extern "C" size_t azn_nms_workspace_bytes(int64_t n) {
     if (n <= 0) return 256;
     const size_t ct = (size_t)((n + 63) / 64);
-    return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + align_up(sizeof(int) * n, 256) +
+    return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + 3 * align_up(sizeof(int) * n, 256) +
            align_up(sizeof(u64) * (size_t)n * ct, 256);
 }
 
@@ -261,17 +304,16 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         return AZN_ERR_CAPACITY;
     }
     const int col_tiles = (int)((n + 63) / 64);
-    const size_t scan_smem = sizeof(u64) * col_tiles;
-    AZN_REQUIRE(scan_smem <= 200 * 1024, "azn_nms: n=%lld exceeds the scan kernel's shared bitmap", (long long)n);
     NmsWorkspace w = carve(workspace, n, col_tiles);
-    nms_rank_kernel<<<(unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), RANK_THREADS, 0, s>>>(
-        dets, (int)n, w.boxes, w.areas, w.order);
+    AZN_CUDA(cudaMemsetAsync(w.rank, 0, sizeof(int) * n, s));
+    nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
+                      RANK_THREADS, 0, s>>>(dets, (int)n, w.rank);
+    AZN_LAUNCH_CHECK();
+    nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
     AZN_LAUNCH_CHECK();
     nms_mask_kernel<<<dim3(col_tiles, col_tiles), 64, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles);
     AZN_LAUNCH_CHECK();
-    if (scan_smem > 48 * 1024)
-        AZN_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-    nms_scan_kernel<<<1, SCAN_THREADS, scan_smem, s>>>(w.mask, w.order, (int)n, col_tiles, keep, keep_count);
+    nms_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(w.mask, w.order, (int)n, col_tiles, w.kept_rows, keep, keep_count);
     AZN_LAUNCH_CHECK();
     return AZN_OK;
 }

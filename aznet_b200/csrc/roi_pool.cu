@@ -47,52 +47,30 @@ __device__ __forceinline__ void bin_bounds(int p, float bin, int start, int limi
     hi = min(max(hi + start, 0), limit);
 }
 
-// ---- 16-byte channel vectors -----------------------------------------------------------
-struct VecF32 {
-    float v[4];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = -FLT_MAX;
+// ---- 16-byte channel vectors: exact `v > best ? v : best` on 4 f32 / 8 bf16 lanes -------
+struct OpsF32 {
+    static __device__ __forceinline__ uint4 lowest() {
+        const unsigned m = __float_as_uint(-FLT_MAX);
+        return make_uint4(m, m, m, m);
     }
-    __device__ __forceinline__ void zero() {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = 0.f;
+    static __device__ __forceinline__ unsigned pick(unsigned v, unsigned b) {
+        return __uint_as_float(v) > __uint_as_float(b) ? v : b;
     }
-    __device__ __forceinline__ void take(const uint4 &q) {
-        float x[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = x[i] > v[i] ? x[i] : v[i];
-    }
-    __device__ __forceinline__ uint4 pack() const {
-        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    static __device__ __forceinline__ void take(uint4 &acc, const uint4 &q) {
+        acc.x = pick(q.x, acc.x); acc.y = pick(q.y, acc.y); acc.z = pick(q.z, acc.z); acc.w = pick(q.w, acc.w);
     }
 };
 
-struct VecBF16 {   // 8 bf16 lanes, compared as the f32 values they denote
-    float v[8];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = -INFINITY;   // bf16(-FLT_MAX) rounds to -inf
+struct OpsBF16 {   // packed: HSET2.BF16.GT (mask) + LOP3 (select) per pair; gt is false on NaN and on +0 vs -0
+    static __device__ __forceinline__ uint4 lowest() {
+        return make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16(-FLT_MAX) rounds to -inf
     }
-    __device__ __forceinline__ void zero() {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    static __device__ __forceinline__ unsigned pick(unsigned v, unsigned b) {
+        const unsigned m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&v), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+        return (v & m) | (b & ~m);
     }
-    __device__ __forceinline__ void take(const uint4 &q) {
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
-            v[2 * i] = lo > v[2 * i] ? lo : v[2 * i];
-            v[2 * i + 1] = hi > v[2 * i + 1] ? hi : v[2 * i + 1];
-        }
-    }
-    __device__ __forceinline__ uint4 pack() const {
-        unsigned w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            w[i] = (__float_as_uint(v[2 * i]) >> 16) | (__float_as_uint(v[2 * i + 1]) & 0xffff0000u);
-        return make_uint4(w[0], w[1], w[2], w[3]);
+    static __device__ __forceinline__ void take(uint4 &acc, const uint4 &q) {
+        acc.x = pick(q.x, acc.x); acc.y = pick(q.y, acc.y); acc.z = pick(q.z, acc.z); acc.w = pick(q.w, acc.w);
     }
 };
 
@@ -104,109 +82,137 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
                  : "memory");
 }
 
-// blockDim = (LX lanes, SY bin slots).  L = 16-byte vectors per map cell (C * sizeof(T) / 16).
-template <typename Vec>
+// One CTA owns one (roi, ph) row of bins, one warp per bin of the row: lanes 0..PW-1 of the CTA derive the ROI
+// geometry once per row (shared through shared memory), then every warp max-reduces its bin with its lanes
+// spanning the channel vectors (NV 16-byte vectors per lane, 32*NV per pass), so every global access of a
+// warp is a run of consecutive 16-byte vectors and large ROIs still spread over PW warps per row.
+// L = vectors per map cell (C * sizeof(T) / 16).
+constexpr int POOL_MAX_PW = 32;
+
+template <typename Ops, int NV>
 __global__ void __launch_bounds__(256)
 roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
                      int PH, int PW, float scale, uint4 *__restrict__ out) {
+    __shared__ int s_ws[2][POOL_MAX_PW], s_we[2][POOL_MAX_PW], s_row[2][3];
     const int R = n_rois ? min(*n_rois, R_cap) : R_cap;
-    const unsigned bins = (unsigned)(PH * PW);
-    const unsigned total_bins = (unsigned)R * bins;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned items = (unsigned)R * (unsigned)PH;
     const size_t row_stride = (size_t)W * L;      // vectors per map row
-    for (unsigned g = blockIdx.x * blockDim.y + threadIdx.y; g < total_bins; g += gridDim.x * blockDim.y) {
-        const unsigned r = g / bins, bin = g - r * bins;
-        const int ph = (int)(bin / (unsigned)PW), pw = (int)(bin - (unsigned)ph * PW);
-        const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, PH, PW);
-        int hs, he, ws, we;
-        bin_bounds(ph, q.bin_h, q.start_h, H, hs, he);
-        bin_bounds(pw, q.bin_w, q.start_w, W, ws, we);
-        const bool bad_img = q.b < 0 || q.b >= n_img;
-        const bool empty = bad_img || he <= hs || we <= ws;
-        const uint4 *base = feat + (size_t)(bad_img ? 0 : q.b) * H * row_stride;
-        for (int lane = threadIdx.x; lane < L; lane += blockDim.x) {
-            Vec acc;
-            if (empty) {
-                acc.zero();
-            } else {
-                acc.init();
-                for (int h = hs; h < he; ++h) {
-                    const uint4 *p = base + (size_t)h * row_stride + (size_t)ws * L + lane;
-#pragma unroll 4
-                    for (int w = ws; w < we; ++w, p += L) acc.take(ld_map(p));
-                }
+    int buf = 0;
+    for (unsigned it = blockIdx.x; it < items; it += gridDim.x, buf ^= 1) {
+        const unsigned r = it / (unsigned)PH;
+        const int ph = (int)(it - r * (unsigned)PH);
+        if ((int)threadIdx.x < PW) {
+            const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, PH, PW);
+            int ws, we;
+            bin_bounds(threadIdx.x, q.bin_w, q.start_w, W, ws, we);
+            s_ws[buf][threadIdx.x] = ws;
+            s_we[buf][threadIdx.x] = we;
+            if (threadIdx.x == 0) {
+                int hs, he;
+                bin_bounds(ph, q.bin_h, q.start_h, H, hs, he);
+                s_row[buf][0] = hs;
+                s_row[buf][1] = he;
+                s_row[buf][2] = (q.b < 0 || q.b >= n_img) ? -1 : q.b;
             }
-            st_stream(out + (size_t)g * L + lane, acc.pack());
+        }
+        __syncthreads();                          // double-buffered geometry: one barrier per item
+        const int hs = s_row[buf][0], he = s_row[buf][1], b = s_row[buf][2];
+        const uint4 *base = feat + (size_t)(b < 0 ? 0 : b) * H * row_stride;
+        uint4 *orow = out + (size_t)it * PW * L;
+        for (int pw = warp; pw < PW; pw += nwarps) {
+            const int ws = s_ws[buf][pw], we = s_we[buf][pw];
+            const bool empty = b < 0 || he <= hs || we <= ws;
+            for (int v0 = lane; v0 < L; v0 += 32 * NV) {
+                uint4 acc[NV];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) acc[j] = empty ? make_uint4(0u, 0u, 0u, 0u) : Ops::lowest();
+                if (!empty) {
+                    for (int h = hs; h < he; ++h) {
+                        const uint4 *p = base + (size_t)h * row_stride + (size_t)ws * L + v0;
+#pragma unroll 4
+                        for (int w = ws; w < we; ++w, p += L) {
+#pragma unroll
+                            for (int j = 0; j < NV; ++j)
+                                if (v0 + 32 * j < L) Ops::take(acc[j], ld_map(p + 32 * j));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    if (v0 + 32 * j < L) st_stream(orow + (size_t)pw * L + v0 + 32 * j, acc[j]);
+            }
         }
     }
 }
 
-// Caffe layout: f32 NCHW in, [R, C, PH, PW] out (+ argmax).  CTA = (roi, group of CG channels).
-constexpr int CG = 8;
-constexpr int NCHW_THREADS = 128;
-constexpr int NCHW_SMEM_FLOATS = 10240;   // 40 KB window budget
+// Caffe blob layout out: [R, C, PH, PW] f32 (+ argmax).  The map is read channels-last (the f32 NHWC copy
+// that azn_roi_pool_fwd makes in its workspace), one CTA pools one ROI (x one channel chunk) into a
+// [bins][CC+1] shared tile -- coalesced 16-byte map loads, lanes along channels -- and then streams the tile
+// out transposed, so the CTA's global writes are one contiguous run of CC*PH*PW floats (the +1 padding
+// makes the transposed shared reads conflict-free).
+constexpr int CAFFE_THREADS = 256;
 
-__global__ void __launch_bounds__(NCHW_THREADS)
-roi_pool_nchw_kernel(const float *__restrict__ feat, int n_img, int C, int H, int W,
-                     const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
-                     int PH, int PW, float scale, float *__restrict__ out, int32_t *__restrict__ argmax) {
-    extern __shared__ float win[];
+template <bool ARGMAX, int VEC>
+__global__ void __launch_bounds__(CAFFE_THREADS)
+roi_pool_caffe_kernel(const float *__restrict__ nhwc, int n_img, int C, int H, int W,
+                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
+                      int PH, int PW, float scale, float *__restrict__ out, int32_t *__restrict__ argmax, int CC) {
+    extern __shared__ float tile[];
     const int R = n_rois ? min(*n_rois, R_cap) : R_cap;
-    const int groups = (C + CG - 1) / CG;
-    const int bins = PH * PW;
-    for (long item = blockIdx.x; item < (long)R * groups; item += gridDim.x) {
-        const int r = (int)(item / groups), c0 = (int)(item - (long)r * groups) * CG;
-        const int nc = min(CG, C - c0);
+    const int bins = PH * PW, ld = CC + 1;
+    int *atile = reinterpret_cast<int *>(tile + (size_t)bins * ld);
+    const int nchunks = (C + CC - 1) / CC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long item = blockIdx.x; item < (long)R * nchunks; item += gridDim.x) {
+        const int r = (int)(item / nchunks), c0 = (int)(item - (long)r * nchunks) * CC;
+        const int cc = min(CC, C - c0);
         const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, PH, PW);
         const bool bad_img = q.b < 0 || q.b >= n_img;
-        int h0, h1, w0, w1, t0, t1;
-        bin_bounds(0, q.bin_h, q.start_h, H, h0, t0);
-        bin_bounds(PH - 1, q.bin_h, q.start_h, H, t1, h1);
-        bin_bounds(0, q.bin_w, q.start_w, W, w0, t0);
-        bin_bounds(PW - 1, q.bin_w, q.start_w, W, t1, w1);
-        const int wh = max(h1 - h0, 0), ww = max(w1 - w0, 0);
-        const bool staged = !bad_img && (long)wh * ww * nc <= NCHW_SMEM_FLOATS && wh * ww > 0;
-        const float *img = feat + ((size_t)(bad_img ? 0 : q.b) * C + c0) * H * W;
-        __syncthreads();   // previous item's readers are done with `win`
-        if (staged) {
-            const int rows = nc * wh;
-            for (int row = threadIdx.x / 32; row < rows; row += NCHW_THREADS / 32) {
-                const int c = row / wh, h = row - c * wh;
-                const float *src = img + ((size_t)c * H + (h0 + h)) * W + w0;
-                float *dst = win + (size_t)row * ww;
-                for (int w = threadIdx.x % 32; w < ww; w += 32) dst[w] = __ldg(src + w);
-            }
-        }
-        __syncthreads();
-        for (int o = threadIdx.x; o < nc * bins; o += NCHW_THREADS) {
-            const int c = o / bins, bin = o - c * bins;
+        const float *img = nhwc + (size_t)(bad_img ? 0 : q.b) * H * W * C + c0;
+        for (int bin = warp; bin < bins; bin += CAFFE_THREADS / 32) {
             const int ph = bin / PW, pw = bin - ph * PW;
             int hs, he, ws, we;
             bin_bounds(ph, q.bin_h, q.start_h, H, hs, he);
             bin_bounds(pw, q.bin_w, q.start_w, W, ws, we);
-            float best = -FLT_MAX;
-            int best_i = -1;
-            if (bad_img || he <= hs || we <= ws) {
-                best = 0.f;
-            } else if (staged) {
-                const float *wc = win + (size_t)c * wh * ww;
-                for (int h = hs; h < he; ++h)
-                    for (int w = ws; w < we; ++w) {
-                        float v = wc[(h - h0) * ww + (w - w0)];
-                        if (v > best) { best = v; best_i = h * W + w; }
-                    }
-            } else {
-                const float *gc = img + (size_t)c * H * W;
-                for (int h = hs; h < he; ++h)
-                    for (int w = ws; w < we; ++w) {
-                        float v = __ldg(gc + (size_t)h * W + w);
-                        if (v > best) { best = v; best_i = h * W + w; }
-                    }
+            const bool empty = bad_img || he <= hs || we <= ws;
+            for (int c = lane * VEC; c < cc; c += 32 * VEC) {
+                float best[VEC];
+                int bi[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) { best[k] = empty ? 0.f : -FLT_MAX; bi[k] = -1; }
+                if (!empty) {
+                    for (int h = hs; h < he; ++h)
+                        for (int w = ws; w < we; ++w) {
+                            const float *p = img + ((size_t)h * W + w) * C + c;
+                            float v[VEC];
+                            if (VEC == 4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+                                v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+                            } else {
+                                v[0] = __ldg(p);
+                            }
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k)
+                                if (v[k] > best[k]) { best[k] = v[k]; if (ARGMAX) bi[k] = h * W + w; }
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    tile[(size_t)bin * ld + c + k] = best[k];
+                    if (ARGMAX) atile[(size_t)bin * ld + c + k] = bi[k];
+                }
             }
-            const size_t oi = ((size_t)r * C + c0) * bins + o;
-            out[oi] = best;
-            if (argmax) argmax[oi] = best_i;
         }
+        __syncthreads();
+        const size_t obase = ((size_t)r * C + c0) * bins;
+        for (int o = threadIdx.x; o < cc * bins; o += CAFFE_THREADS) {
+            const int c = o / bins, bin = o - c * bins;
+            out[obase + o] = tile[(size_t)bin * ld + c];
+            if (ARGMAX) argmax[obase + o] = atile[(size_t)bin * ld + c];
+        }
+        __syncthreads();
     }
 }
 
@@ -243,14 +249,18 @@ roi_pool_nchw_bf16_kernel(const __nv_bfloat16 *__restrict__ feat, int n_img, int
     }
 }
 
-// f32 NCHW -> bf16 NHWC through a 32x33 shared tile (both sides coalesced).
+// f32 NCHW -> bf16 / f32 NHWC through a 32x33 shared tile (both sides coalesced).
+__device__ __forceinline__ void cvt_store(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void cvt_store(float *p, float v) { *p = v; }
+
+template <typename TOut>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_bf16_kernel(const float *__restrict__ src, int C, int HW, __nv_bfloat16 *__restrict__ dst) {
+nchw_to_nhwc_kernel(const float *__restrict__ src, int C, int HW, TOut *__restrict__ dst) {
     __shared__ float tile[32][33];
     const int img = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float *s = src + (size_t)img * C * HW;
-    __nv_bfloat16 *d = dst + (size_t)img * C * HW;
+    TOut *d = dst + (size_t)img * C * HW;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         int c = c0 + j, p = p0 + threadIdx.x;
         tile[j][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
@@ -258,15 +268,21 @@ nchw_to_nhwc_bf16_kernel(const float *__restrict__ src, int C, int HW, __nv_bflo
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         int p = p0 + j, c = c0 + threadIdx.x;
-        if (p < HW && c < C) d[(size_t)p * C + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+        if (p < HW && c < C) cvt_store(d + (size_t)p * C + c, tile[threadIdx.x][j]);
     }
 }
 
 }  // namespace
 
+extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype) {
+    if (layout == AZN_LAYOUT_NCHW && dtype == AZN_DTYPE_F32) return (size_t)n_img * C * H * W * sizeof(float);
+    return 0;
+}
+
 extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                                 const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
-                                float spatial_scale, void *out, int32_t *argmax, azn_stream_t stream) {
+                                float spatial_scale, void *out, int32_t *argmax, void *workspace,
+                                size_t workspace_bytes, azn_stream_t stream) {
     if (R_cap == 0) return AZN_OK;
     AZN_REQUIRE(feat && rois && out, "azn_roi_pool_fwd: null pointer");
     AZN_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R_cap >= 0,
@@ -280,29 +296,57 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         AZN_REQUIRE((C * esize) % 16 == 0, "azn_roi_pool_fwd: NHWC needs C*sizeof(dtype) %% 16 == 0 (C=%d)", C);
         AZN_REQUIRE(((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0), "azn_roi_pool_fwd: 16-byte alignment");
         const int L = C * esize / 16;
-        AZN_REQUIRE((double)R_cap * PH * PW < 2.0e9, "azn_roi_pool_fwd: too many bins for one launch");
-        const int LX = L < 128 ? L : 128;
-        const int SY = 256 / LX > 0 ? 256 / LX : 1;
-        dim3 block(LX, SY);
-        const long total_bins = (long)R_cap * PH * PW;
-        long blocks = (total_bins + SY - 1) / SY;
+        AZN_REQUIRE((double)R_cap * PH < 2.0e9, "azn_roi_pool_fwd: too many ROI rows for one launch");
+        AZN_REQUIRE(PW <= POOL_MAX_PW, "azn_roi_pool_fwd: pooled width %d > %d", PW, POOL_MAX_PW);
+        const long items = (long)R_cap * PH;
+        const int nwarps = PW < 8 ? PW : 8;
+        long blocks = items;
         const long max_blocks = (long)sms * 16;
         if (blocks > max_blocks) blocks = max_blocks;
-        if (dtype == AZN_DTYPE_F32)
-            roi_pool_nhwc_kernel<VecF32><<<(unsigned)blocks, block, 0, s>>>(
-                (const uint4 *)feat, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, (uint4 *)out);
-        else
-            roi_pool_nhwc_kernel<VecBF16><<<(unsigned)blocks, block, 0, s>>>(
-                (const uint4 *)feat, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, (uint4 *)out);
+        const int nv = L >= 128 ? 4 : (L >= 64 ? 2 : 1);
+        const uint4 *f = (const uint4 *)feat;
+        uint4 *o = (uint4 *)out;
+#define AZN_POOL_LAUNCH(OPS, NVV) \
+        roi_pool_nhwc_kernel<OPS, NVV><<<(unsigned)blocks, nwarps * 32, 0, s>>>(f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o)
+        if (dtype == AZN_DTYPE_F32) {
+            if (nv == 4) AZN_POOL_LAUNCH(OpsF32, 4); else if (nv == 2) AZN_POOL_LAUNCH(OpsF32, 2); else AZN_POOL_LAUNCH(OpsF32, 1);
+        } else {
+            if (nv == 4) AZN_POOL_LAUNCH(OpsBF16, 4); else if (nv == 2) AZN_POOL_LAUNCH(OpsBF16, 2); else AZN_POOL_LAUNCH(OpsBF16, 1);
+        }
+#undef AZN_POOL_LAUNCH
         AZN_LAUNCH_CHECK();
         return AZN_OK;
     }
     AZN_REQUIRE(layout == AZN_LAYOUT_NCHW, "azn_roi_pool_fwd: bad layout %d", layout);
     if (dtype == AZN_DTYPE_F32) {
-        const long items = (long)R_cap * ((C + CG - 1) / CG);
-        long blocks = items < (long)sms * 32 ? items : (long)sms * 32;
-        roi_pool_nchw_kernel<<<(unsigned)blocks, NCHW_THREADS, NCHW_SMEM_FLOATS * sizeof(float), s>>>(
-            (const float *)feat, n_img, C, H, W, rois, n_rois, R_cap, PH, PW, spatial_scale, (float *)out, argmax);
+        const size_t need = azn_roi_pool_workspace_bytes(n_img, C, H, W, layout, dtype);
+        if (!workspace || workspace_bytes < need) {
+            azn_set_error("azn_roi_pool_fwd: the NCHW f32 path needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
+            return AZN_ERR_CAPACITY;
+        }
+        float *nhwc = (float *)workspace;
+        const int HW = H * W;
+        nchw_to_nhwc_kernel<float><<<dim3((HW + 31) / 32, (C + 31) / 32, n_img), dim3(32, 8), 0, s>>>((const float *)feat, C, HW, nhwc);
+        AZN_LAUNCH_CHECK();
+        const int bins = PH * PW;
+        const int per = argmax ? 8 : 4;                        // bytes of shared tile per (bin, channel)
+        int CC = (int)((200 * 1024) / ((size_t)bins * per)) - 1;
+        AZN_REQUIRE(CC >= 32, "azn_roi_pool_fwd: pooled size %dx%d too large for the shared tile", PH, PW);
+        CC = CC / 32 * 32;
+        if (CC > C) CC = C;
+        const size_t smem = (size_t)bins * (CC + 1) * per;
+        const long items = (long)R_cap * ((C + CC - 1) / CC);
+        long blocks = items < (long)sms * 4 ? items : (long)sms * 4;
+        const bool vec = (C % 4 == 0) && (CC % 4 == 0);
+#define AZN_CAFFE_LAUNCH(AM, V)                                                                                          \
+        do {                                                                                                             \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_caffe_kernel<AM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            roi_pool_caffe_kernel<AM, V><<<(unsigned)blocks, CAFFE_THREADS, smem, s>>>(                                  \
+                nhwc, n_img, C, H, W, rois, n_rois, R_cap, PH, PW, spatial_scale, (float *)out, argmax, CC);            \
+        } while (0)
+        if (argmax) { if (vec) AZN_CAFFE_LAUNCH(true, 4); else AZN_CAFFE_LAUNCH(true, 1); }
+        else        { if (vec) AZN_CAFFE_LAUNCH(false, 4); else AZN_CAFFE_LAUNCH(false, 1); }
+#undef AZN_CAFFE_LAUNCH
     } else {
         AZN_REQUIRE(argmax == nullptr, "azn_roi_pool_fwd: argmax needs f32");
         const long total = (long)R_cap * C * PH * PW;
@@ -321,7 +365,7 @@ extern "C" int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int
     AZN_REQUIRE(src && dst && n_img > 0 && C > 0 && H > 0 && W > 0, "azn_nchw_f32_to_nhwc_bf16: bad argument");
     const int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img), block(32, 8);
-    nchw_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, C, HW, (__nv_bfloat16 *)dst);
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, HW, (__nv_bfloat16 *)dst);
     AZN_LAUNCH_CHECK();
     return AZN_OK;
 }

@@ -40,6 +40,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int &total, int *s_warp /*
 }
 
 // ---- _bbox_pred + _clip_boxes for one (box, 4 deltas) ------------------------------------
+template <bool CLIP = true>
 __device__ __forceinline__ void decode_clip(const double bx1, const double by1, const double bx2, const double by2,
                                             const float dx, const float dy, const float dw, const float dh,
                                             const double eps, const double wmax, const double hmax, double out[4]) {
@@ -55,6 +56,7 @@ __device__ __forceinline__ void decode_clip(const double bx1, const double by1, 
     double y1 = __dsub_rn(pcy, __dmul_rn(0.5, ph));
     double x2 = __dadd_rn(pcx, __dmul_rn(0.5, pw));
     double y2 = __dadd_rn(pcy, __dmul_rn(0.5, ph));
+    if (!CLIP) { out[0] = x1; out[1] = y1; out[2] = x2; out[3] = y2; return; }
     out[0] = x1 > 0.0 ? x1 : 0.0;                            // np.maximum(., 0)
     out[1] = y1 > 0.0 ? y1 : 0.0;
     out[2] = x2 < wmax ? x2 : wmax;                          // np.minimum(., W-1)
@@ -510,14 +512,15 @@ divide_kernel(const double *__restrict__ regions, int n, double min_side, double
 }
 
 __global__ void decode_kernel(const double *__restrict__ boxes, const float *__restrict__ deltas, int n, int ncol,
-                              double eps, double wmax, double hmax, double *__restrict__ out) {
+                              double eps, double wmax, double hmax, int clip, double *__restrict__ out) {
     const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (t >= (long)n * ncol) return;
     const int r = (int)(t / ncol), s = (int)(t - (long)r * ncol);
     const double *b = boxes + (size_t)r * 4;
     const float *d = deltas + ((size_t)r * ncol + s) * 4;
     double o[4];
-    decode_clip(b[0], b[1], b[2], b[3], d[0], d[1], d[2], d[3], eps, wmax, hmax, o);
+    if (clip) decode_clip<true>(b[0], b[1], b[2], b[3], d[0], d[1], d[2], d[3], eps, wmax, hmax, o);
+    else decode_clip<false>(b[0], b[1], b[2], b[3], d[0], d[1], d[2], d[3], eps, wmax, hmax, o);
     double *dst = out + ((size_t)r * ncol + s) * 4;
     dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
 }
@@ -622,7 +625,8 @@ extern "C" int azn_decode_boxes(const double *boxes, const float *deltas, int n,
     AZN_REQUIRE(boxes && deltas && out, "azn_decode_boxes: null pointer");
     const long total = (long)n * ncol;
     decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boxes, deltas, n, ncol, eps,
-                                                                                   (double)im_w - 1.0, (double)im_h - 1.0, out);
+                                                                                   (double)im_w - 1.0, (double)im_h - 1.0,
+                                                                                   (im_h > 0 && im_w > 0) ? 1 : 0, out);
     AZN_LAUNCH_CHECK();
     return AZN_OK;
 }

@@ -84,12 +84,12 @@ def _bbox_pred_clip(boxes, box_deltas, im_shape):
 
 
 def _bbox_pred(boxes, box_deltas):
-    """Unclipped decode (lib/detect/test.py:106-139): the clip bounds are pushed out of reach."""
+    """Unclipped decode (lib/detect/test.py:106-139)."""
     if boxes.shape[0] == 0:
         return np.zeros((0, box_deltas.shape[1]))
     b = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float64)).cuda()
     d = torch.from_numpy(np.ascontiguousarray(box_deltas, dtype=np.float32)).cuda()
-    out = ops.decode_boxes(b, d, 2 ** 30, 2 ** 30, float(cfg.EPS)).cpu().numpy()
+    out = ops.decode_boxes(b, d, 0, 0, float(cfg.EPS)).cpu().numpy()
     return out
 
 

@@ -41,9 +41,11 @@ def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_sc
     if out is None:
         out = torch.empty(shape, dtype=feat.dtype, device=feat.device)
     amax = torch.empty(shape, dtype=torch.int32, device=feat.device) if want_argmax else None
-    L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, L.LAYOUT_NCHW if layout == "NCHW" else L.LAYOUT_NHWC,
-                                     dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled, spatial_scale, _ptr(out),
-                                     _ptr(amax), _stream()), "azn_roi_pool_fwd")
+    lay = L.LAYOUT_NCHW if layout == "NCHW" else L.LAYOUT_NHWC
+    nbytes = L.lib().azn_roi_pool_workspace_bytes(n, Cc, H, W, lay, dt)
+    ws = _scratch(feat.device, nbytes) if nbytes else None
+    L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
+                                     spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, _stream()), "azn_roi_pool_fwd")
     return (out, amax) if want_argmax else out
 
 
@@ -58,14 +60,25 @@ def nchw_to_nhwc_bf16(src: torch.Tensor, out: torch.Tensor | None = None):
 
 
 _WS = {}
+_SCRATCH = {}
+
+
+def _scratch(device, nbytes):
+    """Grow-only per-device scratch buffer (stream-ordered reuse on torch's current stream)."""
+    t = _SCRATCH.get(device)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _SCRATCH[device] = t
+    return t
 
 
 def fc_workspace(device, N):
-    """The fixed split-K workspace (one 128 x BLOCK_N fp32 tile per SM), cached per device."""
+    """The fixed stream-K workspace (one 128 x BLOCK_N fp32 slot per SM + flags), zeroed once, cached per
+    (device, stream)."""
     nbytes = L.lib().azn_fc_workspace_bytes(1, int(N), 64)
-    key = (device, nbytes)
+    key = (device, nbytes, torch.cuda.current_stream().cuda_stream)
     if key not in _WS:
-        _WS[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WS[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
     return _WS[key]
 
 

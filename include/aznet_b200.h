@@ -59,10 +59,14 @@ int azn_check_device(void);
  * Bit-exact with the reference for f32; bf16 in -> bf16 out is bit-exact with bf16(f32 result)
  * because max commutes with the monotone rounding.  NHWC needs C*sizeof(dtype) % 16 == 0.
  * A batch index outside [0, n_img) yields an all-zero row (the reference CPU path aborts,
- * roi_pooling_layer.cpp:66-67; its GPU path reads out of bounds). */
+ * roi_pooling_layer.cpp:66-67; its GPU path reads out of bounds).
+ * The NCHW f32 path (Caffe's own blob layout) transposes the map into `workspace`
+ * (azn_roi_pool_workspace_bytes; 0 for every other layout/dtype, workspace may then be NULL). */
+size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype);
 int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                      const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
-                     float spatial_scale, void *out, int32_t *argmax, azn_stream_t stream);
+                     float spatial_scale, void *out, int32_t *argmax, void *workspace,
+                     size_t workspace_bytes, azn_stream_t stream);
 
 /* f32 NCHW -> bf16 NHWC feature-map conversion (layout the search engine keeps resident). */
 int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, void *dst,
@@ -77,8 +81,10 @@ int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, 
  *   bias  f32 [N]; out bf16 or f32 [M_cap, ldo]
  *   m_live  int32 device scalar with the live row count, or NULL for M_cap
  * bf16 operands, fp32 accumulation in TMEM (tcgen05.mma kind::f16), TMA-fed.
- * K % 64 == 0, N % 16 == 0, pointers 16-byte aligned.  `workspace` (azn_fc_workspace_bytes)
- * is used for split-K partial sums when M is small. */
+ * K % 64 == 0, A and W 16-byte aligned.  `workspace` (azn_fc_workspace_bytes) holds the stream-K
+ * partial accumulators and their flags; it must be ZEROED ONCE before its first use (every launch
+ * leaves the flags clean) and must not be shared by launches on different streams.  The kernel is
+ * persistent with one CTA per SM and its CTAs wait on each other: it needs the whole GPU. */
 size_t azn_fc_workspace_bytes(int M_cap, int N, int K);
 int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype,
                    int ldo, int M_cap, const int32_t *m_live, int N, int K, int act, int act_aux,
@@ -153,7 +159,8 @@ int azn_divide_region(const double *regions, int n, double min_side, double *out
                       int cap_out, int sift_only, void *scratch, size_t scratch_bytes, azn_stream_t stream);
 size_t azn_divide_region_scratch_bytes(int n);
 /* azn_decode_boxes replaces _bbox_pred + _clip_boxes (lib/detect/test.py:106-151):
- * boxes f64 [n,4], deltas f32 [n, 4*ncol] -> out f64 [n, 4*ncol] clipped to (im_h, im_w). */
+ * boxes f64 [n,4], deltas f32 [n, 4*ncol] -> out f64 [n, 4*ncol] clipped to (im_h, im_w);
+ * im_h <= 0 or im_w <= 0 skips the clip (_bbox_pred alone). */
 int azn_decode_boxes(const double *boxes, const float *deltas, int n, int ncol, double eps,
                      int im_h, int im_w, double *out, azn_stream_t stream);
 
