@@ -17,15 +17,17 @@
 //               bias + ReLU / sigmoid, 16-byte stores.  Two accumulator buffers in TMEM
 //               (2 x BLOCK_N columns) let the epilogue of tile i overlap the main loop of tile i+1.
 // Scheduling is decided ON THE DEVICE from the live row count (the search keeps its region counts
-// in HBM) as a data-parallel + stream-K hybrid: tiles = ceil(m_live/128) x ceil(N/BLOCK_N); whole
-// waves of tiles go one per CTA, and the k-blocks of the remaining tiles (plus one full wave, so
-// that no tile is cut into more than ~3 pieces) are dealt out evenly over all CTAs as contiguous
-// (tile, k-block) ranges.  A CTA that computes the middle or the tail of a tile dumps its raw fp32
-// accumulator into its own slot of a fixed 148-slot workspace and raises a flag (release); the CTA
-// that computes the head of the tile waits for those flags (acquire), adds the partials in CTA
-// order (deterministic, no atomics on data) and runs the epilogue.  With few tiles (the shallow
-// search levels: M = 64 .. 2048) this turns into an even split of the K loop across the whole
-// chip, i.e. every SM streams its share of the 205 MB int6 weight matrix.
+// in HBM): tiles = ceil(m_live/128) x ceil(N/BLOCK_N).  Whole waves of tiles go one per CTA
+// (data-parallel); the K loop of the remaining tiles is cut into P equal parts, P chosen on the
+// device to minimise waves(P)/P plus a fix-up charge, and the (tile, part) units are dealt out
+// part-major so that CTAs running side by side sweep the SAME k-range and share A / W panels
+// through L2 (a k-staggered stream-K schedule was measured 1.3x slower: every CTA streamed its own
+// panels from HBM).  A CTA that computes a non-final part dumps its raw fp32 accumulator into a
+// workspace slot (coalesced layout) and raises the slot's flag (release); the CTA that computes the
+// final part waits for the flags (acquire), adds the partials in part order -- deterministic, no
+// atomics on data -- and runs the epilogue.  With few tiles (the shallow search levels:
+// M = 64 .. 2048) this is an even split of the K loop across the whole chip: every SM streams its
+// share of the 205 MB int6 weight matrix.
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -153,17 +155,19 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int MIN_KB_PER_CTA = 4;      // do not cut the K loop finer than this many 64-wide k-blocks
+constexpr int MIN_KB_PER_PART = 8;      // do not cut the K loop finer than this many 64-wide k-blocks
+constexpr int MAX_PARTS = 16;
+constexpr int WS_SLOTS = 512;          // partial-accumulator slots in the workspace (one flag each)
+constexpr int FIXUP_KB = 4;            // cost of dumping + re-reading one partial, in k-block times
 
 // Work decomposition, identical on every CTA and every warp role (pure function of m_live and the grid).
 struct Plan {
     int m_live, m_tiles, n_tiles, tiles, kblocks;
-    int dp_tiles, sk_tiles, g_eff;         // data-parallel tiles (first), stream-K tiles (last), CTAs sharing them
-    long units;                            // sk_tiles * kblocks
+    int dp_tiles, rem_tiles, parts;        // data-parallel tiles (first), split tiles (last), parts per split tile
     int n_major;                           // raster order of tile ids
 };
 struct Work {
-    int tile, kb0, kb1, kind;              // kind 0: whole tile, 1: partial producer, 2: owner (head of a split tile)
+    int tile, kb0, kb1, kind, part, rem;   // rem = index of the tile among the split tiles
 };
 enum { WORK_FULL = 0, WORK_PARTIAL = 1, WORK_OWNER = 2 };
 
@@ -174,47 +178,48 @@ __device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, 
     p.n_tiles = (N + block_n - 1) / block_n;
     p.tiles = p.m_tiles * p.n_tiles;
     p.kblocks = K / BLOCK_K;
-    const int full = p.tiles / grid, rem = p.tiles - full * grid;
-    if (rem == 0) p.sk_tiles = 0;
-    else p.sk_tiles = full >= 1 ? rem + grid : rem;
-    p.dp_tiles = p.tiles - p.sk_tiles;
-    p.units = (long)p.sk_tiles * p.kblocks;
-    long g = p.units / MIN_KB_PER_CTA;
-    p.g_eff = (int)(g < 1 ? 1 : (g > grid ? grid : g));
+    p.rem_tiles = p.tiles % grid;
+    p.dp_tiles = p.tiles - p.rem_tiles;
+    p.parts = 1;
+    if (p.rem_tiles > 0) {
+        int best = p.kblocks;              // P = 1: one wave of whole tiles
+        for (int P = 2; P <= MAX_PARTS; ++P) {
+            if (p.kblocks / P < MIN_KB_PER_PART || p.rem_tiles * (P - 1) > WS_SLOTS) break;
+            const int waves = (p.rem_tiles * P + grid - 1) / grid;
+            const int cost = waves * ((p.kblocks + P - 1) / P) + FIXUP_KB * (P - 1);
+            if (cost < best) { best = cost; p.parts = P; }
+        }
+    }
     // operands are re-read from HBM once per wave of tiles that does not share them: keep the bigger one
     // (W: N*K, A: m_live*K) shared inside a wave
     p.n_major = p.m_live < N ? 1 : 0;
     return p;
 }
-__device__ __forceinline__ long sk_begin(const Plan &p, int g) { return p.units * g / p.g_eff; }
 
-// idx-th piece of work of CTA `cta`: stream-K segments first (range order), then data-parallel tiles.
+// idx-th piece of work of CTA `cta`: data-parallel tiles first, then (tile, part) units, part-major.
 __device__ __forceinline__ bool get_work(const Plan &p, int cta, int grid, int idx, Work &w) {
-    if (p.sk_tiles > 0 && cta < p.g_eff) {
-        const long u0 = sk_begin(p, cta), u1 = sk_begin(p, cta + 1);
-        if (u1 > u0) {
-            const int first = (int)(u0 / p.kblocks), last = (int)((u1 - 1) / p.kblocks);
-            if (idx <= last - first) {
-                const int sidx = first + idx;
-                const long t0 = (long)sidx * p.kblocks;
-                w.kb0 = (int)((u0 > t0 ? u0 : t0) - t0);
-                w.kb1 = (int)((u1 < t0 + p.kblocks ? u1 : t0 + p.kblocks) - t0);
-                w.tile = p.dp_tiles + sidx;
-                w.kind = (w.kb0 == 0 && w.kb1 == p.kblocks) ? WORK_FULL : (w.kb0 == 0 ? WORK_OWNER : WORK_PARTIAL);
-                return true;
-            }
-            idx -= last - first + 1;
-        }
+    const int n_dp = p.dp_tiles / grid;
+    if (idx < n_dp) {
+        w.tile = cta + idx * grid; w.kb0 = 0; w.kb1 = p.kblocks; w.kind = WORK_FULL; w.part = 0; w.rem = 0;
+        return true;
     }
-    const long t = (long)cta + (long)idx * grid;
-    if (t >= p.dp_tiles) return false;
-    w.tile = (int)t; w.kb0 = 0; w.kb1 = p.kblocks; w.kind = WORK_FULL;
+    const int u = cta + (idx - n_dp) * grid;
+    if (u >= p.rem_tiles * p.parts) return false;
+    w.part = u / p.rem_tiles;
+    w.rem = u - w.part * p.rem_tiles;
+    w.tile = p.dp_tiles + w.rem;
+    w.kb0 = (int)((long)p.kblocks * w.part / p.parts);
+    w.kb1 = (int)((long)p.kblocks * (w.part + 1) / p.parts);
+    w.kind = p.parts == 1 ? WORK_FULL : (w.part == p.parts - 1 ? WORK_OWNER : WORK_PARTIAL);
     return true;
 }
 __device__ __forceinline__ void tile_coords(const Plan &p, int tile, int &m_tile, int &n_tile) {
     if (p.n_major) { n_tile = tile / p.m_tiles; m_tile = tile - n_tile * p.m_tiles; }
     else           { m_tile = tile / p.n_tiles; n_tile = tile - m_tile * p.n_tiles; }
 }
+// Partial accumulators are stored so that the 32 lanes of a warp (32 consecutive tile rows) touch 32
+// consecutive 16-byte words: float4 index ((chunk*8 + j4) * 128 + row).
+__device__ __forceinline__ size_t partial_f4(int chunk, int j4, int row) { return ((size_t)(chunk * 8 + j4) * BLOCK_M + row); }
 
 __device__ __forceinline__ void flag_release(int *flag) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
@@ -242,8 +247,8 @@ struct EpiParams {
     const float *bias;
     void *out;
     int out_dtype, ldo, N, act, act_aux;
-    float *ws;           // stream-K partials: [cta][BLOCK_M][BLOCK_N] fp32
-    int *flags;          // [grid] "partial of CTA g is in its slot" (zero between launches)
+    float *ws;           // split partials: [slot][BLOCK_N/4][BLOCK_M] float4, slot = part * rem_tiles + rem
+    int *flags;          // [WS_SLOTS] "the partial of this slot is complete" (zero between launches)
 };
 
 template <int BLOCK_N>
@@ -338,17 +343,16 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int row = m_tile * BLOCK_M + trow;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BLOCK_N);
             const bool row_ok = row < pl.m_live;
-            // peers of a split tile: the CTAs after this one whose stream-K range still lies inside the tile
-            int peers = 0;
+            // the final part of a split tile waits for the earlier parts (always scheduled on lower unit ids)
+            const int peers = w.kind == WORK_OWNER ? pl.parts - 1 : 0;
             if (w.kind == WORK_OWNER) {
-                const long tile_end = (long)(w.tile - pl.dp_tiles + 1) * pl.kblocks;
-                while (cta + 1 + peers < pl.g_eff && sk_begin(pl, cta + 1 + peers) < tile_end) ++peers;
                 if (threadIdx.x == 64) {
-                    for (int j = 1; j <= peers; ++j)
-                        while (flag_acquire(ep.flags + cta + j) == 0) { }
+                    for (int j = 0; j < peers; ++j)
+                        while (flag_acquire(ep.flags + j * pl.rem_tiles + w.rem) == 0) { }
                 }
                 epi_bar_sync();
             }
+            constexpr size_t SLOT_F4 = (size_t)BLOCK_M * BLOCK_N / 4;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t r[32];
@@ -356,21 +360,21 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tmem_ld_wait();
                 const int col0 = n_tile * BLOCK_N + c * 32;
                 if (w.kind == WORK_PARTIAL) {
-                    float *dst = ep.ws + ((size_t)cta * BLOCK_M + trow) * BLOCK_N + c * 32;
+                    uint4 *dst = (uint4 *)ep.ws + (size_t)(w.part * pl.rem_tiles + w.rem) * SLOT_F4;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        __stcg((uint4 *)(dst + j), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+                        __stcg(dst + partial_f4(c, j >> 2, trow), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
                     continue;
                 }
                 if (!(row_ok && col0 < ep.N)) continue;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                for (int pj = 1; pj <= peers; ++pj) {           // fixed CTA order => deterministic sum
-                    const float *src = ep.ws + ((size_t)(cta + pj) * BLOCK_M + trow) * BLOCK_N + c * 32;
+                for (int pj = 0; pj < peers; ++pj) {            // fixed part order => deterministic sum
+                    const float4 *src = (const float4 *)ep.ws + (size_t)(pj * pl.rem_tiles + w.rem) * SLOT_F4;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 t = __ldcg((const float4 *)(src + j));
+                        const float4 t = __ldcg(src + partial_f4(c, j >> 2, trow));
                         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
                 }
@@ -414,11 +418,11 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (w.kind == WORK_PARTIAL) {
                 __threadfence();                      // partial visible device-wide before the flag
                 epi_bar_sync();
-                if (threadIdx.x == 64) flag_release(ep.flags + cta);
+                if (threadIdx.x == 64) flag_release(ep.flags + w.part * pl.rem_tiles + w.rem);
             } else if (w.kind == WORK_OWNER) {
                 epi_bar_sync();                       // every epilogue thread is done reading the peers' slots
                 if (threadIdx.x == 64)
-                    for (int j = 1; j <= peers; ++j) ep.flags[cta + j] = 0;     // leave the flags clean for the next launch
+                    for (int j = 0; j < peers; ++j) ep.flags[j * pl.rem_tiles + w.rem] = 0;   // clean for the next launch
             }
         }
     }
@@ -521,8 +525,8 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_l
 
 extern "C" size_t azn_fc_workspace_bytes(int M_cap, int N, int K) {
     (void)M_cap; (void)K;
-    // one 128 x BLOCK_N fp32 slot per CTA (a CTA produces at most one partial per launch) + the flag words
-    return (size_t)azn_num_sms() * BLOCK_M * pick_block_n(N) * sizeof(float) + 4096;
+    // WS_SLOTS partial accumulators of 128 x BLOCK_N fp32 + one flag word per slot
+    return (size_t)WS_SLOTS * BLOCK_M * pick_block_n(N) * sizeof(float) + 4096;
 }
 
 extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype, int ldo,
@@ -541,9 +545,9 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     cudaStream_t s = (cudaStream_t)stream;
     const int bn = pick_block_n(N);
     const int grid = azn_num_sms();
-    const size_t slots = (size_t)grid * BLOCK_M * bn * sizeof(float);
+    const size_t slots = (size_t)WS_SLOTS * BLOCK_M * bn * sizeof(float);
     const size_t need = slots + 4096;
-    AZN_REQUIRE(grid * sizeof(int) <= 4096, "azn_fc_forward: grid too large for the flag block");
+    static_assert(WS_SLOTS * sizeof(int) <= 4096, "flag block");
     if (!workspace || workspace_bytes < need) {
         azn_set_error("azn_fc_forward: workspace %zu < %zu bytes", workspace_bytes, need);
         return AZN_ERR_CAPACITY;
