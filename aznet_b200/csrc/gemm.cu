@@ -155,15 +155,19 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int MIN_KB_PER_PART = 8;      // do not cut the K loop finer than this many 64-wide k-blocks
+constexpr int MIN_KB_PER_PART = 4;      // do not cut the K loop finer than this many 64-wide k-blocks
 constexpr int MAX_PARTS = 16;
-constexpr int WS_SLOTS = 512;          // partial-accumulator slots in the workspace (one flag each)
-constexpr int FIXUP_KB = 4;            // cost of dumping + re-reading one partial, in k-block times
+constexpr int WS_SLOTS = 1024;         // partial-accumulator slots in the workspace (one flag each)
+// measured fix-up charges, in SM cycles: an owner CTA adds one peer's partial in ~4 us (latency-bound L2
+// reads by 128 threads); the stand-alone finish kernel costs ~12 us but reduces all parts in parallel
+constexpr int PEER_CYCLES = 8000;
+constexpr int FINISH_CYCLES = 24000;
 
 // Work decomposition, identical on every CTA and every warp role (pure function of m_live and the grid).
 struct Plan {
     int m_live, m_tiles, n_tiles, tiles, kblocks;
     int dp_tiles, rem_tiles, parts;        // data-parallel tiles (first), split tiles (last), parts per split tile
+    int finish;                            // 1: every part dumps a partial and fc_finish_kernel reduces them
     int n_major;                           // raster order of tile ids
 };
 struct Work {
@@ -181,13 +185,17 @@ __device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, 
     p.rem_tiles = p.tiles % grid;
     p.dp_tiles = p.tiles - p.rem_tiles;
     p.parts = 1;
+    p.finish = 0;
     if (p.rem_tiles > 0) {
-        int best = p.kblocks;              // P = 1: one wave of whole tiles
+        const int kb_cycles = 2 * block_n;                 // 4 UMMAs of 128 x block_n x 16
+        int best = p.kblocks * kb_cycles;                  // P = 1: one wave of whole tiles
         for (int P = 2; P <= MAX_PARTS; ++P) {
-            if (p.kblocks / P < MIN_KB_PER_PART || p.rem_tiles * (P - 1) > WS_SLOTS) break;
+            if (p.kblocks / P < MIN_KB_PER_PART || p.rem_tiles * P > WS_SLOTS) break;
             const int waves = (p.rem_tiles * P + grid - 1) / grid;
-            const int cost = waves * ((p.kblocks + P - 1) / P) + FIXUP_KB * (P - 1);
-            if (cost < best) { best = cost; p.parts = P; }
+            const int mma = waves * ((p.kblocks + P - 1) / P) * kb_cycles;
+            const int c_in = mma + PEER_CYCLES * (P - 1), c_fin = mma + FINISH_CYCLES;
+            if (c_in < best) { best = c_in; p.parts = P; p.finish = 0; }
+            if (c_fin < best) { best = c_fin; p.parts = P; p.finish = 1; }
         }
     }
     // operands are re-read from HBM once per wave of tiles that does not share them: keep the bigger one
@@ -210,7 +218,7 @@ __device__ __forceinline__ bool get_work(const Plan &p, int cta, int grid, int i
     w.tile = p.dp_tiles + w.rem;
     w.kb0 = (int)((long)p.kblocks * w.part / p.parts);
     w.kb1 = (int)((long)p.kblocks * (w.part + 1) / p.parts);
-    w.kind = p.parts == 1 ? WORK_FULL : (w.part == p.parts - 1 ? WORK_OWNER : WORK_PARTIAL);
+    w.kind = p.parts == 1 ? WORK_FULL : ((w.part == p.parts - 1 && !p.finish) ? WORK_OWNER : WORK_PARTIAL);
     return true;
 }
 __device__ __forceinline__ void tile_coords(const Plan &p, int tile, int &m_tile, int &n_tile) {
@@ -415,7 +423,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
-            if (w.kind == WORK_PARTIAL) {
+            if (w.kind == WORK_PARTIAL && !pl.finish) {
                 __threadfence();                      // partial visible device-wide before the flag
                 epi_bar_sync();
                 if (threadIdx.x == 64) flag_release(ep.flags + w.part * pl.rem_tiles + w.rem);
@@ -431,6 +439,40 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// Finish-kernel mode of the split schedule (many parts): sums the P partials of every split tile in part
+// order and applies bias + activation.  One thread per (row, 4 columns); exits at once in the other modes.
+__global__ void __launch_bounds__(256)
+fc_finish_kernel(const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, int block_n, int grid_gemm, EpiParams ep) {
+    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, block_n, grid_gemm);
+    if (!pl.finish || pl.parts <= 1) return;
+    const int q4 = block_n / 4;                              // float4 columns per tile row
+    const size_t slot_f4 = (size_t)BLOCK_M * q4;
+    const long total = (long)pl.rem_tiles * BLOCK_M * q4;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int trow = (int)(e % BLOCK_M);                 // consecutive threads -> consecutive rows: coalesced partial reads
+        const int c4 = (int)((e / BLOCK_M) % q4);
+        const int rem = (int)(e / ((long)BLOCK_M * q4));
+        int m_tile, n_tile;
+        tile_coords(pl, pl.dp_tiles + rem, m_tile, n_tile);
+        const int row = m_tile * BLOCK_M + trow, col0 = n_tile * block_n + c4 * 4;
+        if (row >= pl.m_live || col0 >= N) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int part = 0; part < pl.parts; ++part) {
+            const float4 t = __ldcg((const float4 *)ep.ws + (size_t)(part * pl.rem_tiles + rem) * slot_f4 +
+                                    partial_f4(c4 >> 3, c4 & 7, trow));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        for (int j = 0; j < 4; ++j) {
+            const int col = col0 + j;
+            if (col >= N) break;
+            const float o = apply_act(v[j] + ep.bias[col], ep.act, col, ep.act_aux);
+            if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(o);
+            else ((float *)ep.out)[(size_t)row * ep.ldo + col] = o;
+        }
     }
 }
 
@@ -567,6 +609,16 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     else if (bn == 128) rc = launch_gemm<128>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else rc = launch_gemm<64>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     if (rc) return rc;
+    // the split mode is decided on the device; the finish kernel returns at once unless it is needed, and is
+    // not even launched when the capacity rules a split out (tile count of M_cap a multiple of the grid is
+    // not knowable for a live count, so only the static case is skipped)
+    {
+        const long tiles_cap = (long)((M_cap + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
+        if (m_live != nullptr || tiles_cap % grid != 0) {
+            fc_finish_kernel<<<grid * 4, 256, 0, s>>>(m_live, M_cap, N, K, bn, grid, ep);
+            AZN_LAUNCH_CHECK();
+        }
+    }
     if (act == AZN_ACT_SOFTMAX_BBOX) {
         softmax_rows_kernel<<<grid, 256, 0, s>>>((float *)out, m_live, M_cap, ldo, act_aux);
         AZN_LAUNCH_CHECK();

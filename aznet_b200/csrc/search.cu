@@ -401,6 +401,10 @@ select_kernel(azn_search_state st, int mode, int num_proposals, double tc, doubl
     // mode 0: the num_proposals highest scores, ties by lower index (stable argsort of -score)
     int k = num_proposals < n ? num_proposals : n;
     if (k > cap_out) { k = cap_out; if (tid == 0) *st.status = AZN_ERR_CAPACITY; }
+    if (k <= 0) {
+        if (tid == 0) out_count[i] = 0;
+        return;
+    }
     unsigned prefix = 0, need = (unsigned)k;    // find the k-th largest key by 8-bit radix select
     int *cand = scratch + (size_t)i * cap_out;   // candidate indices (index order)
     if (k < n) {
@@ -413,15 +417,24 @@ select_kernel(azn_search_state st, int mode, int num_proposals, double tc, doubl
                 if ((key & himask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned acc = 0;
-                int b = 255;
-                for (; b > 0; --b) {
-                    if (acc + s_hist[b] >= need) break;
-                    acc += s_hist[b];
+            if (tid < 32) {
+                // warp-parallel top-down scan of the 256 bins: lane l owns bins 255-8l .. 248-8l
+                unsigned c[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = s_hist[255 - (8 * tid + j)]; sum += c[j]; }
+                const unsigned incl = (unsigned)warp_incl_scan((int)sum, tid), excl = incl - sum;
+                if (excl < need && need <= incl) {            // exactly one lane: the bin holding the need-th largest
+                    unsigned acc = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (acc + c[j] >= need) {
+                            s_prefix = prefix | ((unsigned)(255 - (8 * tid + j)) << shift);
+                            s_need = need - acc;
+                            break;
+                        }
+                        acc += c[j];
+                    }
                 }
-                s_prefix = prefix | ((unsigned)b << shift);
-                s_need = need - acc;
             }
             __syncthreads();
             prefix = s_prefix;

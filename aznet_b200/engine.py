@@ -202,7 +202,7 @@ class SearchEngine:
         t = ev(level, "int7", t, midx)
         ops.fc_forward(self.h7[:mc], hd.wh, hd.bh, L.ACT_AZ_HEAD, hd.nsub, m_live=self.m_total, out=self.heads[:mc])
         ev(level, "heads", t, midx)
-        self.launches += 1 + 3
+        self.launches += 1 + 3 * 2
 
     def _ev(self, level=None, name=None, prev=None, midx=None):
         if not self.profile:

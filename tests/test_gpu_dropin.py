@@ -101,6 +101,7 @@ def _small_nets(dev, num_classes=6):
     azw = synth.make_az_weights(seed=3, C=64, h6=256, h71=96, h72=32, zoom_bias=0.0)
     frw = synth.make_frcnn_weights(seed=4, num_classes=num_classes, C=64, h6=256, h7=128)
     frw["cls_score"] = (frw["cls_score"][0] * np.float32(0.02), frw["cls_score"][1])      # O(1) logits: unsaturated softmax
+    frw["bbox_pred"] = (frw["bbox_pred"][0] * np.float32(0.05), frw["bbox_pred"][1])      # |deltas| << 1: boxes stay box-sized
     az = {"full": net.Net(azw, "az", backbone=bb, name="az_small"), "fc": net.Net(azw, "az", name="az_small")}
     fr = {"full": net.Net(frw, "frcnn", backbone=bb, name="frcnn_small"), "fc": net.Net(frw, "frcnn", name="frcnn_small")}
     return az, fr, azw, frw
