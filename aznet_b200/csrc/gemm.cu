@@ -175,7 +175,8 @@ struct Work {
 };
 enum { WORK_FULL = 0, WORK_PARTIAL = 1, WORK_OWNER = 2 };
 
-__device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int grid) {
+__device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int grid,
+                                          int force_parts = 0, int force_finish = -1) {
     Plan p;
     p.m_live = m_live_ptr ? min(max(*m_live_ptr, 0), M_cap) : M_cap;
     p.m_tiles = (p.m_live + BLOCK_M - 1) / BLOCK_M;
@@ -197,6 +198,13 @@ __device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, 
             if (c_in < best) { best = c_in; p.parts = P; p.finish = 0; }
             if (c_fin < best) { best = c_fin; p.parts = P; p.finish = 1; }
         }
+    }
+    if (force_parts > 0 && p.rem_tiles > 0) {
+        p.parts = force_parts;
+        while (p.parts > 1 && (p.kblocks / p.parts < 1 || p.rem_tiles * p.parts > WS_SLOTS)) --p.parts;
+        p.finish = force_finish > 0 ? 1 : 0;
+    } else if (force_finish >= 0 && p.parts > 1) {
+        p.finish = force_finish;
     }
     // operands are re-read from HBM once per wave of tiles that does not share them: keep the bigger one
     // (W: N*K, A: m_live*K) shared inside a wave
@@ -255,6 +263,7 @@ struct EpiParams {
     const float *bias;
     void *out;
     int out_dtype, ldo, N, act, act_aux;
+    int force_parts, force_finish;   // tuning hook (azn_fc_tune): 0 / -1 = automatic
     float *ws;           // split partials: [slot][BLOCK_N/4][BLOCK_M] float4, slot = part * rem_tiles + rem
     int *flags;          // [WS_SLOTS] "the partial of this slot is complete" (zero between launches)
 };
@@ -273,7 +282,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, BLOCK_N, gridDim.x);
+    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, BLOCK_N, gridDim.x, ep.force_parts, ep.force_finish);
     const int cta = blockIdx.x, grid = gridDim.x;
 
     if (warp == 0 && lane == 0) {
@@ -378,12 +387,25 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                for (int pj = 0; pj < peers; ++pj) {            // fixed part order => deterministic sum
-                    const float4 *src = (const float4 *)ep.ws + (size_t)(pj * pl.rem_tiles + w.rem) * SLOT_F4;
+                for (int pj = 0; pj < peers; pj += 2) {         // fixed part order => deterministic sum
+                    const float4 *s0 = (const float4 *)ep.ws + (size_t)(pj * pl.rem_tiles + w.rem) * SLOT_F4;
+                    const bool two = pj + 1 < peers;
+                    const float4 *s1 = two ? s0 + (size_t)pl.rem_tiles * SLOT_F4 : s0;
+                    float4 t0[8], t1[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 t = __ldcg(src + partial_f4(c, j >> 2, trow));
-                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    for (int j = 0; j < 8; ++j) {               // 16 independent L2 reads in flight per thread
+                        t0[j] = __ldcg(s0 + partial_f4(c, j, trow));
+                        t1[j] = __ldcg(s1 + partial_f4(c, j, trow));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[4 * j] += t0[j].x; v[4 * j + 1] += t0[j].y; v[4 * j + 2] += t0[j].z; v[4 * j + 3] += t0[j].w;
+                    }
+                    if (two) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[4 * j] += t1[j].x; v[4 * j + 1] += t1[j].y; v[4 * j + 2] += t1[j].z; v[4 * j + 3] += t1[j].w;
+                        }
                     }
                 }
 #pragma unroll
@@ -446,7 +468,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // order and applies bias + activation.  One thread per (row, 4 columns); exits at once in the other modes.
 __global__ void __launch_bounds__(256)
 fc_finish_kernel(const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, int block_n, int grid_gemm, EpiParams ep) {
-    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, block_n, grid_gemm);
+    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, block_n, grid_gemm, ep.force_parts, ep.force_finish);
     if (!pl.finish || pl.parts <= 1) return;
     const int q4 = block_n / 4;                              // float4 columns per tile row
     const size_t slot_f4 = (size_t)BLOCK_M * q4;
@@ -547,7 +569,13 @@ int make_tmap(const void *ptr, int rows, int cols, int box_rows, CUtensorMap *ou
     return AZN_OK;
 }
 
-int pick_block_n(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+// 128 x 256 tiles (87 FLOP per L2 byte) for the wide layers that carry the FLOPs (int6 / fc6 / fc7);
+// narrower tiles for the small layers, where more tiles beat splitting the K loop.
+int g_force_parts = 0, g_force_finish = -1, g_force_bn = 0;
+int pick_block_n(int N) {
+    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) return g_force_bn;
+    return N >= 2048 ? 256 : (N > 64 ? 128 : 64);
+}
 
 template <int BLOCK_N>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_live, int M_cap, int N, int K,
@@ -565,10 +593,17 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_l
 
 }  // namespace
 
+extern "C" void azn_fc_tune(int parts, int finish_mode, int block_n) {
+    g_force_parts = parts;
+    g_force_finish = finish_mode;
+    g_force_bn = block_n;
+}
+
 extern "C" size_t azn_fc_workspace_bytes(int M_cap, int N, int K) {
     (void)M_cap; (void)K;
     // WS_SLOTS partial accumulators of 128 x BLOCK_N fp32 + one flag word per slot
-    return (size_t)WS_SLOTS * BLOCK_M * pick_block_n(N) * sizeof(float) + 4096;
+    (void)N;
+    return (size_t)WS_SLOTS * BLOCK_M * 256 * sizeof(float) + 4096;    // sized for the widest tile
 }
 
 extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype, int ldo,
@@ -587,7 +622,7 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     cudaStream_t s = (cudaStream_t)stream;
     const int bn = pick_block_n(N);
     const int grid = azn_num_sms();
-    const size_t slots = (size_t)WS_SLOTS * BLOCK_M * bn * sizeof(float);
+    const size_t slots = (size_t)WS_SLOTS * BLOCK_M * 256 * sizeof(float);
     const size_t need = slots + 4096;
     static_assert(WS_SLOTS * sizeof(int) <= 4096, "flag block");
     if (!workspace || workspace_bytes < need) {
@@ -603,6 +638,8 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     ep.bias = bias; ep.out = out; ep.out_dtype = out_dtype; ep.ldo = ldo; ep.N = N;
     ep.act = act == AZN_ACT_SOFTMAX_BBOX ? AZN_ACT_NONE : act;
     ep.act_aux = act_aux;
+    ep.force_parts = g_force_parts;
+    ep.force_finish = g_force_finish;
     ep.ws = (float *)workspace;
     ep.flags = (int *)((char *)workspace + slots);
     if (bn == 256) rc = launch_gemm<256>(ta, tw, m_live, M_cap, N, K, ep, grid, s);

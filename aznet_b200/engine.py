@@ -269,6 +269,27 @@ class SearchEngine:
             self.search_level(k)
         self.select()
 
+    def capture(self, conv_nhwc: torch.Tensor, pre=None):
+        """Capture `pre(); propose(conv_nhwc)` into a CUDA graph.  The launch sequence of the search is static
+        (every count lives on the device, every kernel is launched for the capacity), so one graph replays the
+        whole level loop with no per-launch host cost.  Returns (graph, launches per replay)."""
+        assert not self.profile, "event profiling and graph capture are exclusive"
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):                      # warm-up on the capture stream: workspaces, attributes
+            if pre is not None:
+                pre()
+            self.propose(conv_nhwc)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        before = self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            if pre is not None:
+                pre()
+            self.propose(conv_nhwc)
+        return g, self.launches - before
+
     def results(self):
         """Synchronise and fetch (boxes list of f64 [n_i,4], scores list, n_eval, depth) to the host."""
         torch.cuda.current_stream().synchronize()

@@ -26,17 +26,21 @@ class _Slot:
         self.consumed = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.busy = False
+        self.graph = None
 
 
 class ProposalPipeline:
-    def __init__(self, eng: SearchEngine, map_shape, depth: int = 2, after_search=None):
+    def __init__(self, eng: SearchEngine, map_shape, depth: int = 2, after_search=None, use_graph: bool = True):
         """map_shape = (n_img, C, H, W) of the f32 NCHW batches; after_search: optional callable run on the
-        compute stream right after the search (e.g. the NCCL gather of a multi-GPU run)."""
+        compute stream right after the search (e.g. the NCCL gather of a multi-GPU run); use_graph: replay the
+        layout conversion + level loop of every slot from a CUDA graph."""
         self.eng, self.dev = eng, eng.dev
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.slots = [_Slot(eng, map_shape, self.dev) for _ in range(depth)]
         self.nhwc = torch.empty((map_shape[0], map_shape[2], map_shape[3], map_shape[1]), dtype=torch.bfloat16, device=self.dev)
         self.after_search = after_search
+        self.use_graph = use_graph
+        self.launches_per_submit = 0
         self._i = 0
         self.h2d_bytes = int(map_shape[0] * map_shape[1] * map_shape[2] * map_shape[3] * 4)
         s = self.slots[0]
@@ -55,10 +59,19 @@ class ProposalPipeline:
             slot.stage.copy_(host_maps, non_blocking=True)
             slot.h2d_done.record(self.copy_stream)
         compute.wait_event(slot.h2d_done)
-        ops.nchw_to_nhwc_bf16(slot.stage, out=self.nhwc)
+        if self.use_graph:
+            if slot.graph is None:
+                def pre(stage=slot.stage):
+                    ops.nchw_to_nhwc_bf16(stage, out=self.nhwc)
+                    self.eng.launches += 1
+                slot.graph, self.launches_per_submit = self.eng.capture(self.nhwc, pre=pre)
+            slot.graph.replay()
+            self.eng.launches += self.launches_per_submit
+        else:
+            ops.nchw_to_nhwc_bf16(slot.stage, out=self.nhwc)
+            self.eng.launches += 1
+            self.eng.propose(self.nhwc)
         slot.consumed.record(compute)
-        self.eng.launches += 1
-        self.eng.propose(self.nhwc)
         if self.after_search is not None:
             self.after_search()
         e = self.eng

@@ -86,6 +86,9 @@ int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, 
  * leaves the flags clean) and must not be shared by launches on different streams.  The kernel is
  * persistent with one CTA per SM and its CTAs wait on each other: it needs the whole GPU. */
 size_t azn_fc_workspace_bytes(int M_cap, int N, int K);
+/* Tuning hook for benchmarks: force the split factor (0 = automatic), the fix-up mode (-1 automatic, 0 in-kernel,
+ * 1 finish kernel) and the tile width (0 automatic, 64 / 128 / 256) of subsequent azn_fc_forward calls. */
+void azn_fc_tune(int parts, int finish_mode, int block_n);
 int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype,
                    int ldo, int M_cap, const int32_t *m_live, int N, int K, int act, int act_aux,
                    void *workspace, size_t workspace_bytes, azn_stream_t stream);

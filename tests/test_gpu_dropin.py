@@ -67,9 +67,10 @@ def test_cython_div_dropin(dev, O):
 def test_bbox_pred_clip_dropin(dev, golden, cfg):
     from aznet_b200.detect import test as T
     g = golden["search"]
-    np.testing.assert_allclose(T._bbox_pred(g["bbox_boxes"], g["bbox_deltas"]), g["bbox_pred"], rtol=1e-5, atol=1e-5)
+    # 1e-5 relative to the box scale: x1 = ctr - w/2 cancels, so the absolute floor is 1e-5 * O(100 px)
+    np.testing.assert_allclose(T._bbox_pred(g["bbox_boxes"], g["bbox_deltas"]), g["bbox_pred"], rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(T._bbox_pred_clip(g["bbox_boxes"], g["bbox_deltas"], (600, 1000, 3)), g["bbox_clip"],
-                               rtol=1e-5, atol=1e-5)
+                               rtol=1e-5, atol=1e-3)
     a, c = T._unwrap_adj_pred(g["bbox_clip"].copy(), g["unwrap_scores_in"])
     assert np.array_equal(a, g["unwrap_boxes"]) and np.array_equal(c, g["unwrap_scores"])
     assert T._bbox_pred(np.zeros((0, 4)), np.zeros((0, 44), np.float32)).shape == (0, 44)

@@ -7,6 +7,7 @@ timeout -k 10 240 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k fc_
 if ! grep -q "passed" gpurun_out/t_fc.log || grep -q "failed" gpurun_out/t_fc.log; then echo "fc tests did not pass; stopping"; exit 1; fi
 echo "== gpu tests"; timeout -k 10 900 python -m pytest tests -m gpu -q 2>&1 > gpurun_out/t_gpu.log; tail -5 gpurun_out/t_gpu.log; grep -E "^E  |Error" gpurun_out/t_gpu.log | head -40
 echo "== smoke"; timeout -k 10 300 python __graft_entry__.py smoke 2>&1 | tail -15 | tee gpurun_out/smoke.log
-echo "== bench"; timeout -k 10 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log | cut -c1-1200
-echo "== microbench"; timeout -k 10 600 python tools/microbench.py 2>&1 | tee gpurun_out/microbench.jsonl | cut -c1-250
-echo "== ncu pool"; timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"roi_pool_nhwc|roi_pool_caffe" -s 12 -c 6 -o gpurun_out/prof_pool2 -f python tools/microbench.py --sizes 20000 > gpurun_out/prof_pool2.log 2>&1
+echo "== bench"; timeout -k 10 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log | cut -c1-600
+echo "== bench eager"; timeout -k 10 900 python bench.py --steps 10 --warmup 3 --no-graph --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_eager.log | cut -c1-300
+if [ "$1" == "micro" ]; then echo "== microbench"; timeout -k 10 600 python tools/microbench.py 2>&1 | tee gpurun_out/microbench.jsonl | cut -c1-250; fi
+if [ "$1" == "prof" ] || [ "$2" == "prof" ]; then bash tools/gpu_profile.sh; fi
