@@ -26,7 +26,7 @@ ACT_NONE, ACT_RELU, ACT_AZ_HEAD, ACT_SOFTMAX_BBOX = 0, 1, 2, 3
 NMS_SEG_MAX = 1024
 
 EXPORTS = [
-    "azn_version", "azn_last_error", "azn_check_device", "azn_roi_pool_workspace_bytes", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
+    "azn_version", "azn_last_error", "azn_check_device", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_forward", "azn_search_init", "azn_search_level", "azn_select_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched",
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in srcs:
         o = os.path.join(build_dir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", s, "-o", o]
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("AZN_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -93,7 +93,9 @@ def _bind(L):
     L.azn_roi_pool_fwd.restype = i32
     L.azn_roi_pool_fwd.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp, vp, sz, vp]
     L.azn_roi_pool_workspace_bytes.restype = sz
-    L.azn_roi_pool_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+    L.azn_roi_pool_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32]
+    L.azn_roi_pool_tune.restype = None
+    L.azn_roi_pool_tune.argtypes = [i32]
     L.azn_nchw_f32_to_nhwc_bf16.restype = i32
     L.azn_nchw_f32_to_nhwc_bf16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.azn_fc_workspace_bytes.restype = sz

@@ -49,6 +49,7 @@ __device__ __forceinline__ void bin_bounds(int p, float bin, int start, int limi
 
 // ---- 16-byte channel vectors: exact `v > best ? v : best` on 4 f32 / 8 bf16 lanes -------
 struct OpsF32 {
+    typedef float tag;
     static __device__ __forceinline__ uint4 lowest() {
         const unsigned m = __float_as_uint(-FLT_MAX);
         return make_uint4(m, m, m, m);
@@ -61,7 +62,9 @@ struct OpsF32 {
     }
 };
 
-struct OpsBF16 {   // packed: HSET2.BF16.GT (mask) + LOP3 (select) per pair; gt is false on NaN and on +0 vs -0
+struct OpsBF16 {
+    typedef __nv_bfloat16 tag;
+    // packed: HSET2.BF16.GT (mask) + LOP3 (select) per pair; gt is false on NaN and on +0 vs -0
     static __device__ __forceinline__ uint4 lowest() {
         return make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16(-FLT_MAX) rounds to -inf
     }
@@ -144,6 +147,403 @@ roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                     if (v0 + 32 * j < L) st_stream(orow + (size_t)pw * L + v0 + 32 * j, acc[j]);
             }
         }
+    }
+}
+
+// ---- (1b) staged kernel: the map slice lives in shared memory ---------------------------------
+// With many ROIs per image the L2 -> SM traffic of kernel (1) (every bin re-reads its window, ~4 map
+// cells per output vector) is what bounds it, not HBM.  Here one CTA stages a channel slice of ONE
+// image -- all H*W cells x SV 16-byte vectors, <= 200 KB -- in shared memory with cp.async, then pools a
+// whole chunk of that image's ROIs out of it: HBM/L2 see the slice once per CTA and the pooled rows
+// once.  Work item = (image bucket, ROI chunk, slice); slices of one chunk are adjacent items so the 16-
+// or 32-byte pieces of a pooled row are written at about the same time and merge in L2.
+// ROI geometry is computed once per ROI per CTA (PH + PW threads per ROI, packed lo|hi<<16 bounds in
+// shared memory, double-buffered so that one barrier per batch of ROIs suffices).
+// MODE 0: out [R, P, P, C] (NHWC).  MODE 1: out [R, C, P, P] f32 (Caffe blob order), MODE 2: + argmax;
+// both go through a shared [roi][c][bin] tile so that the global writes are contiguous runs of CC*P*P.
+constexpr int ST_THREADS = 1024;
+constexpr int ST_P = 7;                      // pooled size this kernel is specialised for
+constexpr int ST_BINS = ST_P * ST_P;
+constexpr int ST_RB_MAX = 64;                // ROIs per geometry batch (MODE 0)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <typename Ops, int SV, int MODE>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+roi_pool_staged_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
+                       const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
+                       const int32_t *__restrict__ bucket_off, const int32_t *__restrict__ perm,
+                       float scale, void *__restrict__ out_v, int32_t *__restrict__ argmax,
+                       int n_buckets, int nchunk, int nslices, int RB) {
+    extern __shared__ uint4 s_dyn[];
+    uint4 *s_map = s_dyn;                                   // [H*W][SV]
+    __shared__ uint32_t s_hb[2][ST_RB_MAX][8], s_wb[2][ST_RB_MAX][8];
+    __shared__ int s_r[2][ST_RB_MAX];
+    constexpr int CC = SV * 4;                              // f32 channels per slice (MODE 1/2 are f32 only)
+    float *s_tile = reinterpret_cast<float *>(s_map + (size_t)H * W * SV);       // MODE >= 1: [RB][CC][49]
+    int *s_atile = reinterpret_cast<int *>(s_tile + (size_t)RB * CC * ST_BINS);  // MODE 2
+    const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
+    const int cells = H * W;
+    const long n_items = (long)n_buckets * nchunk * nslices;
+    int buf = 0;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int slice = (int)(item % nslices);
+        const int chunk = (int)((item / nslices) % nchunk);
+        const int bucket = (int)(item / ((long)nslices * nchunk));
+        const int base = bucket_off ? bucket_off[bucket] : 0;
+        const int cnt = bucket_off ? bucket_off[bucket + 1] - base : R;
+        const int lo = base + (int)((long)cnt * chunk / nchunk), hi = base + (int)((long)cnt * (chunk + 1) / nchunk);
+        if (hi <= lo) continue;
+        const bool real = bucket < n_img;                   // the last bucket collects ROIs with a bad batch index
+        const int c0v = slice * SV;
+        if (real) {
+            const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
+            const int n_vec = cells * SV;
+            const int rot = (int)(((long)blockIdx.x * cells) / gridDim.x) * SV;     // see roi_pool_keys_kernel
+            for (int i0 = threadIdx.x; i0 < n_vec; i0 += ST_THREADS) {
+                const int i = i0 + rot < n_vec ? i0 + rot : i0 + rot - n_vec;
+                const int cell = i / SV, j = i - cell * SV;
+                if (c0v + j < L) cp_async16(s_map + i, src + (size_t)cell * L + j);
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        for (int r0 = lo; r0 < hi; r0 += RB, buf ^= 1) {
+            const int nb = min(RB, hi - r0);
+            if ((int)threadIdx.x < nb * 2 * ST_P) {
+                const int rl = threadIdx.x / (2 * ST_P), k = threadIdx.x - rl * 2 * ST_P;
+                const int r = perm ? perm[r0 + rl] : r0 + rl;
+                const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
+                const bool ok = real && q.b == bucket;      // single-image call without buckets: b != 0 -> zeros
+                int a = 0, b = 0;
+                if (k < ST_P) {
+                    if (ok) bin_bounds(k, q.bin_h, q.start_h, H, a, b);
+                    s_hb[buf][rl][k] = (uint32_t)a | ((uint32_t)b << 16);
+                } else {
+                    if (ok) bin_bounds(k - ST_P, q.bin_w, q.start_w, W, a, b);
+                    s_wb[buf][rl][k - ST_P] = (uint32_t)a | ((uint32_t)b << 16);
+                }
+                if (k == 0) s_r[buf][rl] = r;
+            }
+            __syncthreads();
+            const int total = nb * ST_BINS * SV;
+            for (int qi = threadIdx.x; qi < total; qi += ST_THREADS) {
+                const int rl = qi / (ST_BINS * SV), rem = qi - rl * (ST_BINS * SV);
+                const int bin = rem / SV, j = rem - bin * SV;
+                const int ph = bin / ST_P, pw = bin - ph * ST_P;
+                const uint32_t hb = s_hb[buf][rl][ph], wb = s_wb[buf][rl][pw];
+                const int hs = hb & 0xffff, he = hb >> 16, ws = wb & 0xffff, we = wb >> 16;
+                const bool empty = he <= hs || we <= ws;
+                uint4 acc = empty ? make_uint4(0u, 0u, 0u, 0u) : Ops::lowest();
+                int4 am = make_int4(-1, -1, -1, -1);
+                if (!empty && c0v + j < L) {
+                    for (int h = hs; h < he; ++h) {
+                        const uint4 *p = s_map + ((size_t)h * W + ws) * SV + j;
+#pragma unroll 2
+                        for (int w = ws; w < we; ++w, p += SV) {
+                            const uint4 v = *p;
+                            if (MODE == 2) {
+                                const int idx = h * W + w;
+                                if (__uint_as_float(v.x) > __uint_as_float(acc.x)) { acc.x = v.x; am.x = idx; }
+                                if (__uint_as_float(v.y) > __uint_as_float(acc.y)) { acc.y = v.y; am.y = idx; }
+                                if (__uint_as_float(v.z) > __uint_as_float(acc.z)) { acc.z = v.z; am.z = idx; }
+                                if (__uint_as_float(v.w) > __uint_as_float(acc.w)) { acc.w = v.w; am.w = idx; }
+                            } else {
+                                Ops::take(acc, v);
+                            }
+                        }
+                    }
+                }
+                if (MODE == 0) {
+                    if (c0v + j < L)
+                        st_stream(reinterpret_cast<uint4 *>(out_v) + ((size_t)s_r[buf][rl] * ST_BINS + bin) * L + c0v + j, acc);
+                } else {
+                    float *t = s_tile + ((size_t)rl * CC + 4 * j) * ST_BINS + bin;
+                    t[0] = __uint_as_float(acc.x); t[ST_BINS] = __uint_as_float(acc.y);
+                    t[2 * ST_BINS] = __uint_as_float(acc.z); t[3 * ST_BINS] = __uint_as_float(acc.w);
+                    if (MODE == 2) {
+                        int *u = s_atile + ((size_t)rl * CC + 4 * j) * ST_BINS + bin;
+                        u[0] = am.x; u[ST_BINS] = am.y; u[2 * ST_BINS] = am.z; u[3 * ST_BINS] = am.w;
+                    }
+                }
+            }
+            if (MODE != 0) {
+                __syncthreads();
+                const int C = L * 4;                         // f32 channels of the map
+                const int cc = min(CC, C - slice * CC);
+                const int run = cc * ST_BINS;                // contiguous floats per ROI of this slice
+                for (int o = threadIdx.x; o < nb * run; o += ST_THREADS) {
+                    const int rl = o / run, e = o - rl * run;
+                    const size_t g = ((size_t)s_r[buf][rl] * C + (size_t)slice * CC) * ST_BINS + e;
+                    reinterpret_cast<float *>(out_v)[g] = s_tile[(size_t)rl * CC * ST_BINS + e];
+                    if (MODE == 2) argmax[g] = s_atile[(size_t)rl * CC * ST_BINS + e];
+                }
+                __syncthreads();                             // tile free for the next batch
+            }
+        }
+        __syncthreads();                                     // every thread is done with the slice before it is replaced
+    }
+}
+
+// ---- (1c) staged kernel, NHWC out, order-preserving integer keys --------------------------------
+// Kernel (1b) is bound by instruction issue (compare + select per 16-bit pair, per-output index math), not
+// by memory.  This variant maps every staged value ONCE to a signed integer key whose integer order is the
+// float order (negative values: magnitude bits flipped), so that the pooling loop is VIMNMX3 -- a 3-input
+// packed max, two map cells per instruction -- and maps the winner back.  NaN never wins in the reference
+// (`v > best` is false): NaNs get the key of the initial value (-FLT_MAX / bf16 -inf).  The one thing a pure
+// max cannot reproduce is the reference's first-wins rule between +0 and -0 when the maximum is zero, so a
+// CTA whose slice contains a -0 anywhere pools that slice with the exact compare-select of (1b) instead.
+// One warp owns one ROI at a time (geometry in registers, handed out by shuffles: no block barriers while
+// pooling); its lanes span 32/SV bins x SV channel vectors per pass.
+template <bool BF16> struct KeyOps;
+template <> struct KeyOps<true> {
+    typedef OpsBF16 Exact;
+    static __device__ __forceinline__ unsigned flipmask(unsigned x) {     // 0x7fff in every negative half
+        unsigned m;
+        asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(x));           // sign-replicate bytes 1 and 3
+        return m & 0x7fff7fffu;
+    }
+    static __device__ __forceinline__ bool neg_zero(unsigned x) { return __vcmpeq2(x, 0x80008000u) != 0u; }
+    static __device__ __forceinline__ unsigned to_key(unsigned x) {
+        const unsigned k = x ^ flipmask(x);
+        const unsigned nan = __vcmpgtu2(x & 0x7fff7fffu, 0x7f807f80u);    // 0xffff in every NaN half
+        return (k & ~nan) | (0x807f807fu & nan);                          // NaN -> key(-inf)
+    }
+    static __device__ __forceinline__ unsigned from_key(unsigned k) { return k ^ flipmask(k); }
+    static __device__ __forceinline__ unsigned lowest() { return 0x807f807fu; }
+    static __device__ __forceinline__ unsigned max3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
+};
+template <> struct KeyOps<false> {
+    typedef OpsF32 Exact;
+    static __device__ __forceinline__ bool neg_zero(unsigned x) { return x == 0x80000000u; }
+    static __device__ __forceinline__ unsigned to_key(unsigned x) {
+        if ((x & 0x7fffffffu) > 0x7f800000u) return 0x80800000u;         // NaN -> key(-FLT_MAX)
+        return x ^ (((unsigned)((int)x >> 31)) & 0x7fffffffu);
+    }
+    static __device__ __forceinline__ unsigned from_key(unsigned k) { return k ^ (((unsigned)((int)k >> 31)) & 0x7fffffffu); }
+    static __device__ __forceinline__ unsigned lowest() { return 0x80800000u; }
+    static __device__ __forceinline__ unsigned max3(unsigned a, unsigned b, unsigned c) { return (unsigned)__vimax3_s32((int)a, (int)b, (int)c); }
+};
+
+template <bool BF16, int SV>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
+                     const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
+                     const int32_t *__restrict__ bucket_off, const int32_t *__restrict__ perm,
+                     float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices) {
+    typedef KeyOps<BF16> K;
+    typedef typename K::Exact Exact;
+    extern __shared__ uint4 s_dyn[];
+    uint4 *s_map = s_dyn;                                   // [H*W][SV]
+    __shared__ int s_negzero;
+    __shared__ int s_next;
+    constexpr int PHG = 32 / SV;                            // bin rows a warp covers at once
+    constexpr int NG = (ST_P + PHG - 1) / PHG;              // groups of bin rows per ROI
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane % SV, bsub = lane / SV;
+    const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
+    const int cells = H * W;
+    const long n_items = (long)n_buckets * nchunk * nslices;
+    const int row_step = W * SV;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int slice = (int)(item % nslices);
+        const int chunk = (int)((item / nslices) % nchunk);
+        const int bucket = (int)(item / ((long)nslices * nchunk));
+        const int base = bucket_off ? bucket_off[bucket] : 0;
+        const int cnt = bucket_off ? bucket_off[bucket + 1] - base : R;
+        const int lo = base + (int)((long)cnt * chunk / nchunk), hi = base + (int)((long)cnt * (chunk + 1) / nchunk);
+        if (hi <= lo) continue;
+        const bool real = bucket < n_img;
+        const int c0v = slice * SV;
+        if (threadIdx.x == 0) { s_negzero = 0; s_next = lo + ST_THREADS / 32; }
+        const bool jv = c0v + j < L;
+#ifdef AZN_POOL_TRACE
+        const long long t0 = clock64();
+#endif
+        if (real) {
+            // every CTA starts its sweep over the map at a different cell: CTAs that all walk the same cells in
+            // the same order queue up on the same few L2 slices (measured: ~35 us per staging instead of ~3)
+            const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
+            const int n_vec = cells * SV;
+            const int rot = (int)(((long)blockIdx.x * cells) / gridDim.x) * SV;
+            for (int i0 = threadIdx.x; i0 < n_vec; i0 += ST_THREADS) {
+                const int i = i0 + rot < n_vec ? i0 + rot : i0 + rot - n_vec;
+                const int cell = i / SV, jj = i - cell * SV;
+                if (c0v + jj < L) cp_async16(s_map + i, src + (size_t)cell * L + jj);
+                else s_map[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+#ifdef AZN_POOL_TRACE
+        const long long t2 = clock64();
+#endif
+        if (real) {                                          // raw bits -> keys in place, looking for a -0 on the way
+            bool nz = false;
+            for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
+                uint4 v = s_map[i];
+                nz |= K::neg_zero(v.x) | K::neg_zero(v.y) | K::neg_zero(v.z) | K::neg_zero(v.w);
+                v.x = K::to_key(v.x); v.y = K::to_key(v.y); v.z = K::to_key(v.z); v.w = K::to_key(v.w);
+                s_map[i] = v;
+            }
+            if (nz) s_negzero = 1;
+        }
+        __syncthreads();
+        const bool exact = s_negzero != 0;
+        if (exact) {                                         // rare: bring the raw slice back for the exact path
+            const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
+            for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
+                const int cell = i / SV, jj = i - cell * SV;
+                if (c0v + jj < L) cp_async16(s_map + i, src + (size_t)cell * L + jj);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
+#ifdef AZN_POOL_TRACE
+        const long long t3 = clock64();
+#endif
+        // ROIs are handed out dynamically (shared cursor): their cost varies by an order of magnitude with
+        // their size, and a static deal leaves a tail of one big ROI per item.
+        int ri = lo + warp;
+        while (ri < hi) {
+            const int r = perm ? perm[ri] : ri;
+            const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
+            const bool ok = real && q.b == bucket;
+            unsigned gb = 0;                                 // lanes 0..6: packed h bounds of bin row `lane`; 7..13: w bounds
+            if (ok && lane < 2 * ST_P) {
+                int a, b;
+                if (lane < ST_P) bin_bounds(lane, q.bin_h, q.start_h, H, a, b);
+                else bin_bounds(lane - ST_P, q.bin_w, q.start_w, W, a, b);
+                gb = (unsigned)a | ((unsigned)b << 16);
+            }
+            // A pass pools one COLUMN of bins (fixed pw): every lane of the warp then has the same [ws, we), so the
+            // inner loops are warp-uniform; lanes differ only in their bin row (ph = lane / SV) and channel vector.
+#pragma unroll 1
+            for (int rg = 0; rg < NG; ++rg) {
+                const int ph = rg * PHG + bsub;
+                const bool phv = ph < ST_P && jv;
+                const unsigned hb = __shfl_sync(0xffffffffu, gb, min(ph, ST_P - 1));
+                const int hs = hb & 0xffff, nh = phv ? (int)(hb >> 16) - hs : 0;
+                uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
+                const uint4 *rowbase = s_map + (size_t)hs * row_step + j;
+#pragma unroll 1
+                for (int pw = 0; pw < ST_P; ++pw, optr += L) {
+                    const unsigned wb = __shfl_sync(0xffffffffu, gb, ST_P + pw);
+                    const int ws = wb & 0xffff, nw = (int)(wb >> 16) - ws;          // warp-uniform
+                    uint4 res = make_uint4(0u, 0u, 0u, 0u);
+                    if (nh > 0 && nw > 0) {
+                        const uint4 *p = rowbase + ws * SV;
+                        if (!exact) {
+                            uint4 acc = make_uint4(K::lowest(), K::lowest(), K::lowest(), K::lowest());
+#define AZN_MAX3(A, B)                                                                           \
+    acc.x = K::max3(acc.x, (A).x, (B).x); acc.y = K::max3(acc.y, (A).y, (B).y);                  \
+    acc.z = K::max3(acc.z, (A).z, (B).z); acc.w = K::max3(acc.w, (A).w, (B).w)
+                            if (nw == 1) {                   // two rows per VIMNMX3
+                                int t = 0;
+#pragma unroll 1
+                                for (; t + 1 < nh; t += 2, p += 2 * row_step) { const uint4 a = p[0], b = p[row_step]; AZN_MAX3(a, b); }
+                                if (t < nh) { const uint4 a = p[0]; AZN_MAX3(a, a); }
+                            } else if (nw == 2) {            // all loads of two rows in flight before the first max
+                                int t = 0;
+#pragma unroll 1
+                                for (; t + 1 < nh; t += 2, p += 2 * row_step) {
+                                    const uint4 a = p[0], b = p[SV], c = p[row_step], d = p[row_step + SV];
+                                    AZN_MAX3(a, b); AZN_MAX3(c, d);
+                                }
+                                if (t < nh) { const uint4 a = p[0], b = p[SV]; AZN_MAX3(a, b); }
+                            } else if (nw == 3) {
+#pragma unroll 1
+                                for (int t = 0; t < nh; ++t, p += row_step) {
+                                    const uint4 a = p[0], b = p[SV], c = p[2 * SV];
+                                    AZN_MAX3(a, b); AZN_MAX3(c, c);
+                                }
+                            } else if (nw == 4) {
+#pragma unroll 1
+                                for (int t = 0; t < nh; ++t, p += row_step) {
+                                    const uint4 a = p[0], b = p[SV], c = p[2 * SV], d = p[3 * SV];
+                                    AZN_MAX3(a, b); AZN_MAX3(c, d);
+                                }
+                            } else {
+#pragma unroll 1
+                                for (int t = 0; t < nh; ++t, p += row_step) {
+                                    int w = 0;
+#pragma unroll 1
+                                    for (; w + 1 < nw; w += 2) { const uint4 a = p[w * SV], b = p[(w + 1) * SV]; AZN_MAX3(a, b); }
+                                    if (w < nw) { const uint4 a = p[w * SV]; AZN_MAX3(a, a); }
+                                }
+                            }
+#undef AZN_MAX3
+                            res = make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
+                        } else {
+                            res = Exact::lowest();
+#pragma unroll 1
+                            for (int t = 0; t < nh; ++t, p += row_step)
+#pragma unroll 1
+                                for (int w = 0; w < nw; ++w) Exact::take(res, p[w * SV]);
+                        }
+                    }
+                    if (phv) st_stream(optr, res);
+                }
+            }
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&s_next, 1);
+            ri = __shfl_sync(0xffffffffu, nxt, 0);
+        }
+#ifdef AZN_POOL_TRACE
+        const long long t4 = clock64();
+#endif
+        __syncthreads();                                     // every warp is done with the slice before it is replaced
+#ifdef AZN_POOL_TRACE
+        if ((blockIdx.x == 0 || blockIdx.x == 77) && (threadIdx.x == 0 || threadIdx.x == 1023))
+            printf("pool trace cta %d t %d item %ld rois %d: stage+detect %lld transform %lld pool(own) %lld tail %lld cycles\n", blockIdx.x, threadIdx.x, item,
+                   hi - lo, t2 - t0, t3 - t2, t4 - t3, clock64() - t4);
+#endif
+    }
+}
+
+// ROIs grouped by image for the staged kernel: bucket b in [0, n_img) = batch index b, bucket n_img = bad
+// index.  One CTA: shared-memory histogram, scan, scatter (order inside a bucket is irrelevant: every ROI's
+// output row depends on that ROI alone).  off[n_img + 2], perm[R].
+constexpr int BUCKET_MAX_IMG = 8190;
+__global__ void __launch_bounds__(1024)
+roi_bucket_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap, int n_img,
+                  int32_t *__restrict__ off, int32_t *__restrict__ perm) {
+    extern __shared__ int s_cnt[];                           // [n_img + 2] counts -> offsets, then cursors
+    __shared__ int s_part[1024];
+    const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
+    const int nb = n_img + 1;
+    for (int i = threadIdx.x; i < nb + 1; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int b = (int)rois[(size_t)r * 5];
+        atomicAdd(&s_cnt[(b < 0 || b >= n_img) ? n_img : b], 1);
+    }
+    __syncthreads();
+    // exclusive scan of s_cnt[0..nb): each thread owns a run of `per` consecutive buckets
+    const int per = (nb + blockDim.x - 1) / blockDim.x;
+    const int b0 = min((int)threadIdx.x * per, nb), b1 = min(b0 + per, nb);
+    int sum = 0;
+    for (int b = b0; b < b1; ++b) sum += s_cnt[b];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {                                  // warp 0 scans the 1024 partial sums, 32 per lane
+        int run = 0;
+        for (int k = 0; k < 32; ++k) run += s_part[threadIdx.x * 32 + k];
+        const int incl = warp_incl_scan(run, threadIdx.x);
+        int pre = incl - run;
+        for (int k = 0; k < 32; ++k) { const int t = s_part[threadIdx.x * 32 + k]; s_part[threadIdx.x * 32 + k] = pre; pre += t; }
+    }
+    __syncthreads();
+    int pre = s_part[threadIdx.x];
+    for (int b = b0; b < b1; ++b) { const int t = s_cnt[b]; s_cnt[b] = pre; off[b] = pre; pre += t; }
+    if (threadIdx.x == 0) off[nb] = R;
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int b = (int)rois[(size_t)r * 5];
+        perm[atomicAdd(&s_cnt[(b < 0 || b >= n_img) ? n_img : b], 1)] = r;
     }
 }
 
@@ -274,10 +674,123 @@ nchw_to_nhwc_kernel(const float *__restrict__ src, int C, int HW, TOut *__restri
 
 }  // namespace
 
-extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype) {
-    if (layout == AZN_LAYOUT_NCHW && dtype == AZN_DTYPE_F32) return (size_t)n_img * C * H * W * sizeof(float);
+// workspace = [transposed f32 map (NCHW f32 only)] [bucket offsets n_img + 2] [bucket permutation R_cap]
+static size_t map_ws_bytes(int n_img, int C, int H, int W, int layout, int dtype) {
+    if (layout == AZN_LAYOUT_NCHW && dtype == AZN_DTYPE_F32) return ((size_t)n_img * C * H * W * sizeof(float) + 255) / 256 * 256;
     return 0;
 }
+static size_t bucket_ws_bytes(int n_img, int R_cap) {
+    if (n_img <= 1 || n_img > BUCKET_MAX_IMG) return 0;
+    return ((size_t)(n_img + 2) + (size_t)(R_cap > 0 ? R_cap : 0)) * sizeof(int32_t);
+}
+
+extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype, int R_cap) {
+    if (layout == AZN_LAYOUT_NCHW && dtype != AZN_DTYPE_F32) return 0;
+    return map_ws_bytes(n_img, C, H, W, layout, dtype) + bucket_ws_bytes(n_img, R_cap);
+}
+
+namespace {
+int g_pool_mode = 0;           // azn_roi_pool_tune: 0 automatic, 1 direct kernels only, 2 staged whenever possible
+
+constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the staged kernel may ask for
+
+// Staged-kernel launch (see roi_pool_staged_kernel).  `nhwc` is the channels-last map; returns AZN_OK after a
+// launch, or 1 when the configuration is outside the staged kernel's domain (caller takes the direct kernel).
+template <typename Ops, int MODE>
+int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float *rois, const int32_t *n_rois, int R_cap,
+                  float scale, void *out, int32_t *argmax, int32_t *bucket_ws, cudaStream_t s) {
+    const size_t cells = (size_t)H * W;
+    int sv = 0, rb = ST_RB_MAX;
+    for (int cand = (MODE == 0 ? 8 : 4); cand >= 2; cand >>= 1) {
+        const size_t map_bytes = cells * cand * 16;
+        if (map_bytes > ST_SMEM_BUDGET) continue;
+        if (MODE != 0) {
+            const size_t per = (size_t)cand * 4 * ST_BINS * 4 * (MODE == 2 ? 2 : 1);
+            const size_t fit = (ST_SMEM_BUDGET - map_bytes) / per;
+            if (fit < 4) continue;
+            rb = (int)(fit < (size_t)ST_RB_MAX ? fit : ST_RB_MAX);
+        }
+        sv = cand;
+        break;
+    }
+    if (sv == 0) return 1;
+    const int sms = azn_num_sms();
+    const int nslices = (L + sv - 1) / sv;
+    const int n_buckets = n_img > 1 ? n_img + 1 : 1;
+    int32_t *off = nullptr, *perm = nullptr;
+    if (n_img > 1) {
+        off = bucket_ws;
+        perm = bucket_ws + n_img + 2;
+        roi_bucket_kernel<<<1, 1024, (size_t)(n_img + 2) * sizeof(int), s>>>(rois, n_rois, R_cap, n_img, off, perm);
+        AZN_LAUNCH_CHECK();
+    }
+    // (bucket, chunk, slice) items are dealt round-robin to one CTA per SM.  Cost model in units of one ROI-slice
+    // of pooling (measured ~300 cycles): an item costs its staging (~27 units: load + key transform of the slice)
+    // plus its ROIs; the launch costs rounds(items) x the item.  Pick the chunk count that minimises it.
+    const long pairs = (long)n_buckets * nslices;
+    const double rois_per_bucket = (double)R_cap / (double)n_img;
+    long nchunk = 1;
+    double best_cost = 0.0;
+    for (int rounds = 1; rounds <= 4; ++rounds) {
+        long c = (long)rounds * sms / pairs;
+        if (c < 1) c = 1;
+        const long it = c * pairs;
+        const double cost = (double)((it + sms - 1) / sms) * (27.0 + rois_per_bucket / (double)c);
+        if (rounds == 1 || cost < best_cost * 0.97) { best_cost = cost; nchunk = c; }
+    }
+    const long items = (long)n_buckets * nchunk * nslices;
+    const unsigned grid = (unsigned)(items < sms ? items : sms);
+    size_t smem = cells * sv * 16;
+    if (MODE != 0) smem += (size_t)rb * sv * 4 * ST_BINS * 4 * (MODE == 2 ? 2 : 1);
+#define AZN_ST_LAUNCH(SVV)                                                                                               \
+    do {                                                                                                                 \
+        static bool attr_set = false;            /* once per instantiation: the call costs tens of microseconds */     \
+        if (!attr_set) {                                                                                                 \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_staged_kernel<Ops, SVV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)ST_SMEM_BUDGET));                                                         \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        roi_pool_staged_kernel<Ops, SVV, MODE><<<grid, ST_THREADS, smem, s>>>(                                           \
+            (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, out, argmax, n_buckets,          \
+            (int)nchunk, nslices, rb);                                                                                   \
+    } while (0)
+#define AZN_KEY_LAUNCH(SVV)                                                                                              \
+    do {                                                                                                                 \
+        constexpr bool kBf16 = sizeof(typename Ops::tag) == 2;                                                           \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)ST_SMEM_BUDGET));                                                         \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                                 \
+            (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,         \
+            (int)nchunk, nslices);                                                                                       \
+    } while (0)
+    if (MODE == 0) {
+        if (sv == 8) AZN_KEY_LAUNCH(8); else if (sv == 4) AZN_KEY_LAUNCH(4); else AZN_KEY_LAUNCH(2);
+    } else {
+        if (sv == 8) return 1;
+        else if (sv == 4) AZN_ST_LAUNCH(4);
+        else AZN_ST_LAUNCH(2);
+    }
+#undef AZN_KEY_LAUNCH
+#undef AZN_ST_LAUNCH
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+// The staged kernel pays one slice load per (image, chunk): worth it when an image has many ROIs.
+bool want_staged(int n_img, int H, int W, int PH, int PW, const int32_t *n_rois, int R_cap, bool have_bucket_ws) {
+    if (g_pool_mode == 1) return false;
+    if (PH != ST_P || PW != ST_P || H > 65535 || W > 65535) return false;
+    if (n_img > 1 && !have_bucket_ws) return false;
+    if (g_pool_mode == 2) return true;
+    return n_rois == nullptr && (long)R_cap >= 64L * n_img;
+}
+}  // namespace
+
+extern "C" void azn_roi_pool_tune(int mode) { g_pool_mode = mode; }
 
 extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                                 const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
@@ -296,6 +809,13 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         AZN_REQUIRE((C * esize) % 16 == 0, "azn_roi_pool_fwd: NHWC needs C*sizeof(dtype) %% 16 == 0 (C=%d)", C);
         AZN_REQUIRE(((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0), "azn_roi_pool_fwd: 16-byte alignment");
         const int L = C * esize / 16;
+        const bool bucket_ok = n_img <= 1 || (workspace && bucket_ws_bytes(n_img, R_cap) > 0 && workspace_bytes >= bucket_ws_bytes(n_img, R_cap));
+        if (want_staged(n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
+            const int rc = dtype == AZN_DTYPE_F32
+                ? launch_staged<OpsF32, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s)
+                : launch_staged<OpsBF16, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s);
+            if (rc != 1) return rc;
+        }
         AZN_REQUIRE((double)R_cap * PH < 2.0e9, "azn_roi_pool_fwd: too many ROI rows for one launch");
         AZN_REQUIRE(PW <= POOL_MAX_PW, "azn_roi_pool_fwd: pooled width %d > %d", PW, POOL_MAX_PW);
         const long items = (long)R_cap * PH;
@@ -319,7 +839,7 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
     }
     AZN_REQUIRE(layout == AZN_LAYOUT_NCHW, "azn_roi_pool_fwd: bad layout %d", layout);
     if (dtype == AZN_DTYPE_F32) {
-        const size_t need = azn_roi_pool_workspace_bytes(n_img, C, H, W, layout, dtype);
+        const size_t need = map_ws_bytes(n_img, C, H, W, layout, dtype);
         if (!workspace || workspace_bytes < need) {
             azn_set_error("azn_roi_pool_fwd: the NCHW f32 path needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
             return AZN_ERR_CAPACITY;
@@ -328,6 +848,16 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         const int HW = H * W;
         nchw_to_nhwc_kernel<float><<<dim3((HW + 31) / 32, (C + 31) / 32, n_img), dim3(32, 8), 0, s>>>((const float *)feat, C, HW, nhwc);
         AZN_LAUNCH_CHECK();
+        {
+            int32_t *bws = (int32_t *)((char *)workspace + need);
+            const bool bucket_ok = n_img <= 1 || (bucket_ws_bytes(n_img, R_cap) > 0 && workspace_bytes >= need + bucket_ws_bytes(n_img, R_cap));
+            if (C % 4 == 0 && want_staged(n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
+                const int rc = argmax
+                    ? launch_staged<OpsF32, 2>(nhwc, n_img, H, W, C / 4, rois, n_rois, R_cap, spatial_scale, out, argmax, bws, s)
+                    : launch_staged<OpsF32, 1>(nhwc, n_img, H, W, C / 4, rois, n_rois, R_cap, spatial_scale, out, nullptr, bws, s);
+                if (rc != 1) return rc;
+            }
+        }
         const int bins = PH * PW;
         const int per = argmax ? 8 : 4;                        // bytes of shared tile per (bin, channel)
         int CC = (int)((200 * 1024) / ((size_t)bins * per)) - 1;
@@ -340,7 +870,11 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         const bool vec = (C % 4 == 0) && (CC % 4 == 0);
 #define AZN_CAFFE_LAUNCH(AM, V)                                                                                          \
         do {                                                                                                             \
-            AZN_CUDA(cudaFuncSetAttribute(roi_pool_caffe_kernel<AM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            static size_t attr_smem = 0;         /* raise the limit only when it grows: the call is slow */              \
+            if (smem > attr_smem) {                                                                                      \
+                AZN_CUDA(cudaFuncSetAttribute(roi_pool_caffe_kernel<AM, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                attr_smem = smem;                                                                                        \
+            }                                                                                                            \
             roi_pool_caffe_kernel<AM, V><<<(unsigned)blocks, CAFFE_THREADS, smem, s>>>(                                  \
                 nhwc, n_img, C, H, W, rois, n_rois, R_cap, PH, PW, spatial_scale, (float *)out, argmax, CC);            \
         } while (0)

@@ -42,7 +42,7 @@ def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_sc
         out = torch.empty(shape, dtype=feat.dtype, device=feat.device)
     amax = torch.empty(shape, dtype=torch.int32, device=feat.device) if want_argmax else None
     lay = L.LAYOUT_NCHW if layout == "NCHW" else L.LAYOUT_NHWC
-    nbytes = L.lib().azn_roi_pool_workspace_bytes(n, Cc, H, W, lay, dt)
+    nbytes = L.lib().azn_roi_pool_workspace_bytes(n, Cc, H, W, lay, dt, R)
     ws = _scratch(feat.device, nbytes) if nbytes else None
     L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
                                      spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, _stream()), "azn_roi_pool_fwd")

@@ -61,8 +61,13 @@ int azn_check_device(void);
  * A batch index outside [0, n_img) yields an all-zero row (the reference CPU path aborts,
  * roi_pooling_layer.cpp:66-67; its GPU path reads out of bounds).
  * The NCHW f32 path (Caffe's own blob layout) transposes the map into `workspace`
- * (azn_roi_pool_workspace_bytes; 0 for every other layout/dtype, workspace may then be NULL). */
-size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype);
+ * (azn_roi_pool_workspace_bytes).  For the other layouts the workspace is optional: with n_img > 1 it
+ * holds the per-image ROI buckets of the shared-memory-staged kernel (taken for 7x7 pooling with a static
+ * ROI count of >= 64 ROIs per image: one CTA stages a channel slice of one image's map in shared memory
+ * and pools all of that image's ROIs out of it); without it the direct (L2-fed) kernel runs. */
+size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype, int R_cap);
+/* Benchmark hook: 0 automatic kernel choice, 1 direct kernels only, 2 staged kernel whenever it applies. */
+void azn_roi_pool_tune(int mode);
 int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                      const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
                      float spatial_scale, void *out, int32_t *argmax, void *workspace,

@@ -47,8 +47,17 @@ def _edge_rois(n_img):
 
 
 # ------------------------------------------------------------------------------- ROI pooling
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "direct", "staged"])
+def pool_mode(request):
+    """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, shared-memory-staged kernel."""
+    from aznet_b200 import _lib
+    _lib.lib().azn_roi_pool_tune(request.param)
+    yield request.param
+    _lib.lib().azn_roi_pool_tune(0)
+
+
 @pytest.mark.parametrize("hw", [(38, 63), (30, 50)])
-def test_roi_pool_nchw_f32_bit_exact(dev, O, hw):
+def test_roi_pool_nchw_f32_bit_exact(dev, O, hw, pool_mode):
     from aznet_b200 import ops
     feat = synth.make_conv_maps(2, 64, hw[0], hw[1], seed=7)
     feat[1] -= 0.3                                   # negative values too: the layer itself is sign-agnostic
@@ -57,10 +66,12 @@ def test_roi_pool_nchw_f32_bit_exact(dev, O, hw):
     got, am = ops.roi_pool(torch.from_numpy(feat).to(dev), torch.from_numpy(rois).to(dev), layout="NCHW", want_argmax=True)
     assert np.array_equal(got.cpu().numpy().view(np.uint32), ref.view(np.uint32))
     assert np.array_equal(am.cpu().numpy(), ref_am)
+    got2 = ops.roi_pool(torch.from_numpy(feat).to(dev), torch.from_numpy(rois).to(dev), layout="NCHW")     # no argmax
+    assert np.array_equal(got2.cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 
 @pytest.mark.parametrize("C", [64, 512])
-def test_roi_pool_nhwc_bit_exact_f32_and_bf16(dev, O, C):
+def test_roi_pool_nhwc_bit_exact_f32_and_bf16(dev, O, C, pool_mode):
     from aznet_b200 import ops
     n_img = 2 if C == 512 else 3
     feat = synth.make_conv_maps(n_img, C, 38, 63, seed=9)
@@ -86,7 +97,7 @@ def test_roi_pool_nhwc_bit_exact_f32_and_bf16(dev, O, C):
     assert np.array_equal(got_c.float().cpu().numpy(), ref_b.transpose(0, 3, 1, 2))
 
 
-def test_roi_pool_device_count_bad_index_and_empty(dev, O):
+def test_roi_pool_device_count_bad_index_and_empty(dev, O, pool_mode):
     from aznet_b200 import ops
     feat = synth.make_conv_maps(1, 64, 20, 20, seed=1)
     rois = synth.make_rois(50, 300, 300, seed=2)
@@ -105,6 +116,38 @@ def test_roi_pool_device_count_bad_index_and_empty(dev, O):
     assert z.shape[0] == 0
     with pytest.raises(ValueError):
         ops.roi_pool(torch.zeros((1, 4, 4, 3), device=dev), r, layout="NHWC")     # C*4 % 16 != 0
+
+
+def test_roi_pool_signed_zero_nan_and_many_images(dev, O, pool_mode):
+    """`v > best ? v : best` semantics: the first of +-0 ties wins, NaN never wins; ROIs of 5 images interleaved,
+    bad batch indices in the middle of the list (they go to their own bucket of the staged kernel)."""
+    from aznet_b200 import ops
+    n_img = 5
+    feat = synth.make_conv_maps(n_img, 32, 30, 50, seed=21)
+    feat[feat < 0.4] = 0.0
+    rs = np.random.RandomState(5)
+    feat[rs.rand(*feat.shape) < 0.2] *= -1.0                      # -0.0 and negative values
+    feat[rs.rand(*feat.shape) < 0.01] = np.nan
+    rois = synth.make_rois(700, 480, 800, seed=8, n_img=n_img)
+    rois[::97, 0] = n_img + 3
+    rois[5, 0] = -1
+    ok = rois.copy()
+    bad = (ok[:, 0] < 0) | (ok[:, 0] >= n_img)
+    ok[bad, 0] = 0
+    ref = O.roi_pool_fwd(feat, ok)
+    ref[bad] = 0
+    f = torch.from_numpy(feat).to(dev)
+    r = torch.from_numpy(rois).to(dev)
+    got = ops.roi_pool(f, r, layout="NCHW").cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    got = ops.roi_pool(f.permute(0, 2, 3, 1).contiguous(), r, layout="NHWC").cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(ref.transpose(0, 2, 3, 1)).view(np.uint32))
+    fb = f.to(torch.bfloat16)
+    ref_b = O.roi_pool_fwd(fb.float().cpu().numpy(), ok)
+    ref_b[bad] = 0
+    ref_b = torch.from_numpy(ref_b).to(torch.bfloat16).float().numpy()       # an all-NaN window leaves -FLT_MAX -> bf16 -inf
+    got = ops.roi_pool(fb.permute(0, 2, 3, 1).contiguous(), r, layout="NHWC").float().cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(ref_b.transpose(0, 2, 3, 1)).view(np.uint32))
 
 
 # ------------------------------------------------------------------------------- NMS

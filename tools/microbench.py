@@ -36,6 +36,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--sizes", default="2000,8000,20000")
+    ap.add_argument("--hw", default="38,63", help="conv5_3 map size: 38,63 (default cfg, scale 1.0) or 30,50 (voc.yml, scale 0.8)")
+    ap.add_argument("--only", default="", help="roi_pool | nms")
+    ap.add_argument("--pool-mode", type=int, default=0, help="azn_roi_pool_tune: 0 auto, 1 direct, 2 staged")
     args = ap.parse_args()
     _lib.build()
     _lib.require_device()
@@ -43,27 +46,29 @@ def main():
     peak = json.load(open(os.path.join(os.path.dirname(_lib.HEADER), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
         if os.path.exists(os.path.join(os.path.dirname(_lib.HEADER), "..", "MEASURED_PEAKS.json")) else 6650.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    C, H, W = 512, 38, 63
+    C = 512
+    H, W = [int(x) for x in args.hw.split(",")]
     feat = torch.from_numpy(synth.make_conv_maps(1, C, H, W, seed=7)).to(dev)
     nhwc32 = feat.permute(0, 2, 3, 1).contiguous()
     nhwc16 = nhwc32.to(torch.bfloat16)
     if args.cpu:
         from oracle import az_oracle as O
-    for R in [int(x) for x in args.sizes.split(",")]:
+    _lib.lib().azn_roi_pool_tune(args.pool_mode)
+    for R in [int(x) for x in args.sizes.split(",")] if args.only in ("", "roi_pool") else []:
         rois = torch.from_numpy(synth.make_rois(R, 600, 1000, seed=3)).to(dev)
         for name, f, layout, esz in (("nhwc_bf16", nhwc16, "NHWC", 2), ("nhwc_f32", nhwc32, "NHWC", 4), ("nchw_f32", feat, "NCHW", 4)):
             shape = (R, 7, 7, C) if layout == "NHWC" else (R, C, 7, 7)
             out = torch.empty(shape, dtype=f.dtype, device=dev)
             best, mean = timeit(lambda: ops.roi_pool(f, rois, layout=layout, out=out), flush)
             nbytes = C * H * W * esz + R * (20 + C * 49 * esz)
-            line = {"bench": "roi_pool", "variant": name, "R": R, "ms_best": best, "ms_mean": mean, "bytes": nbytes,
+            line = {"bench": "roi_pool", "variant": name, "pool_mode": args.pool_mode, "map": [H, W], "R": R, "ms_best": best, "ms_mean": mean, "bytes": nbytes,
                     "gbs": nbytes / (best * 1e-3) / 1e9, "frac_of_measured_hbm": nbytes / (best * 1e-3) / 1e9 / peak}
             if args.cpu and name == "nchw_f32" and R <= 2000:
                 t0 = time.perf_counter()
                 O.roi_pool_fwd(feat.cpu().numpy(), rois.cpu().numpy())
                 line["cpu_oracle_s"] = time.perf_counter() - t0
             print(json.dumps(line), flush=True)
-    for N in [int(x) for x in args.sizes.split(",")]:
+    for N in [int(x) for x in args.sizes.split(",")] if args.only in ("", "nms") else []:
         d_host = synth.make_dets(N, seed=3)
         d = torch.from_numpy(d_host).to(dev)
         for th in (0.3, 0.7):
