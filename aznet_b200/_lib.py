@@ -26,8 +26,8 @@ ACT_NONE, ACT_RELU, ACT_AZ_HEAD, ACT_SOFTMAX_BBOX = 0, 1, 2, 3
 NMS_SEG_MAX = 1024
 
 EXPORTS = [
-    "azn_version", "azn_last_error", "azn_check_device", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
-    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_forward", "azn_search_init", "azn_search_level", "azn_select_proposals",
+    "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
+    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_level", "azn_select_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched",
 ]
@@ -102,6 +102,10 @@ def _bind(L):
     L.azn_fc_workspace_bytes.argtypes = [i32, i32, i32]
     L.azn_fc_tune.restype = None
     L.azn_fc_tune.argtypes = [i32, i32, i32]
+    L.azn_set_pdl.restype = None
+    L.azn_set_pdl.argtypes = [i32]
+    L.azn_fc_trace.restype = None
+    L.azn_fc_trace.argtypes = [vp]
     L.azn_fc_forward.restype = i32
     L.azn_fc_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, sz, vp]
     L.azn_search_init.restype = i32

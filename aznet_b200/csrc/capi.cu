@@ -11,6 +11,9 @@ void azn_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int g_azn_pdl = 1;
+extern "C" void azn_set_pdl(int on) { g_azn_pdl = on ? 1 : 0; }
+
 extern "C" const char *azn_version(void) { return "aznet_b200 0.1 (sm_100a)"; }
 extern "C" const char *azn_last_error(void) { return g_err; }
 

@@ -46,3 +46,33 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     }
     return v;
 }
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The level loop is a chain of ~26 short kernels per step.  Launched with the programmatic-stream-
+// serialization attribute, kernel K+1 may be scheduled while kernel K drains: its prologue (barrier
+// init, TMEM allocation, descriptor prefetch, smem carve-out) and the launch latency overlap K's tail.
+// Contract of every kernel launched through azn_launch_pdl: it touches NO global memory (reads or
+// writes) before pdl_grid_wait(), which returns when the preceding grid has completed and flushed;
+// right after it the kernel lets its own successor start (pdl_launch_dependents), so at most one
+// successor is ever waiting.  azn_set_pdl(0) launches the same kernels fully serialised.
+__device__ __forceinline__ void pdl_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_grid_wait(); pdl_launch_dependents(); }
+
+extern int g_azn_pdl;
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t azn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_azn_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

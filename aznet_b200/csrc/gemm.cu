@@ -6,18 +6,23 @@
 // one cblas/cublas sgemm for the product, a second rank-1 sgemm for the bias) and the ReLU / Sigmoid
 // layers that follow it in models/Pascal/VGG16/az-net/test_fc.prototxt:26-232.
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d of a 128x64 A box and a BLOCK_Nx64 W box
+// Kernel anatomy (one persistent CTA per SM, 64 + 128*MH threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of MH 128x64 A boxes and a BLOCK_Nx64 W box
 //               (128-byte swizzle) into a STAGES-deep shared-memory ring, completion on mbarriers.
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1
 //               .kind::f16 (UMMA 128 x BLOCK_N x 16, bf16 in, fp32 accumulate) straight from the
 //               swizzled shared tiles through UMMA smem descriptors; tcgen05.commit releases the
 //               ring slot / publishes the accumulator.
-//   warps 2-5   epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row per thread),
-//               bias + ReLU / sigmoid, 16-byte stores.  Two accumulator buffers in TMEM
-//               (2 x BLOCK_N columns) let the epilogue of tile i overlap the main loop of tile i+1.
+//   warps 2..   epilogue, 4 warps per 128-row half: tcgen05.ld the accumulator (one TMEM lane = one
+//               output row per thread), bias + ReLU / sigmoid, 16-byte stores.
+// Tile = (128*MH) x BLOCK_N.  The wide layers (int6 / fc6 / fc7) run MH = 2, BLOCK_N = 256: two
+// 128 x 256 accumulators fill the 512 TMEM columns and every W box is used for two UMMAs, which
+// halves the L2 -> SM bytes per FLOP of a 128 x 256 tile (measured: the 128-row kernel was bound by
+// L2 bandwidth at 72 % tensor-pipe activity).  A half whose rows are all past the live count is
+// neither loaded nor multiplied.  Narrow tiles (MH = 1) keep two accumulator buffers in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 // Scheduling is decided ON THE DEVICE from the live row count (the search keeps its region counts
-// in HBM): tiles = ceil(m_live/128) x ceil(N/BLOCK_N).  Whole waves of tiles go one per CTA
+// in HBM): tiles = ceil(m_live/TILE_M) x ceil(N/BLOCK_N).  Whole waves of tiles go one per CTA
 // (data-parallel); the K loop of the remaining tiles is cut into P equal parts, P chosen on the
 // device to minimise waves(P)/P plus a fix-up charge, and the (tile, part) units are dealt out
 // part-major so that CTAs running side by side sweep the SAME k-range and share A / W panels
@@ -35,19 +40,31 @@
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int HALF_M = 128;            // rows of one UMMA / one accumulator
 constexpr int BLOCK_K = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_RING_BYTES = 192 * 1024;
+constexpr size_t WS_DATA_BYTES = (size_t)128 << 20;    // partial-accumulator area of the workspace
+constexpr int WS_MAX_SLOTS = 1024;                     // flag words (one per slot)
 
 
-template <int BLOCK_N> struct Cfg {
-    static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+template <int BLOCK_N, int MH> struct Cfg {
+    static constexpr int TILE_M = HALF_M * MH;
+    static constexpr int A_HALF_BYTES = HALF_M * BLOCK_K * 2;
+    static constexpr int A_BYTES = MH * A_HALF_BYTES;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    static constexpr int STAGES = SMEM_RING_BYTES / STAGE_BYTES < 8 ? SMEM_RING_BYTES / STAGE_BYTES : 8;
+    static constexpr int ACC_COLS = MH * BLOCK_N;                       // TMEM columns of one accumulator set
+    static constexpr int NUM_ACC = 2 * ACC_COLS <= 512 ? 2 : 1;        // double-buffered when it fits
+    static constexpr int TMEM_COLS = NUM_ACC * ACC_COLS < 32 ? 32 : NUM_ACC * ACC_COLS;
+    static constexpr int THREADS = 64 + 128 * MH;
+    static constexpr int EPI_THREADS = 128 * MH;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr size_t SLOT_BYTES = (size_t)TILE_M * BLOCK_N * sizeof(float);
+    static constexpr int WS_SLOTS = (int)(WS_DATA_BYTES / SLOT_BYTES) < WS_MAX_SLOTS ? (int)(WS_DATA_BYTES / SLOT_BYTES) : WS_MAX_SLOTS;
+    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+    static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -157,17 +174,16 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
 
 constexpr int MIN_KB_PER_PART = 4;      // do not cut the K loop finer than this many 64-wide k-blocks
 constexpr int MAX_PARTS = 16;
-constexpr int WS_SLOTS = 1024;         // partial-accumulator slots in the workspace (one flag each)
-// measured fix-up charges, in SM cycles: an owner CTA adds one peer's partial in ~4 us (latency-bound L2
-// reads by 128 threads); the stand-alone finish kernel costs ~12 us but reduces all parts in parallel
-constexpr int PEER_CYCLES = 8000;
-constexpr int FINISH_CYCLES = 24000;
+// measured fix-up charges, in SM cycles: an owner CTA adds one peer's 256 x 256 partial in ~9 us (latency-bound
+// L2 reads by its epilogue threads); the grid-wide finish phase costs a barrier plus one pass over all partials
+constexpr int PEER_CYCLES = 18000;      // per 256 x 256 fp32 partial added by an owner CTA (measured ~9 us)
+constexpr int FINISH_CYCLES = 4000;     // grid barrier + start of the finish phase
 
 // Work decomposition, identical on every CTA and every warp role (pure function of m_live and the grid).
 struct Plan {
     int m_live, m_tiles, n_tiles, tiles, kblocks;
     int dp_tiles, rem_tiles, parts;        // data-parallel tiles (first), split tiles (last), parts per split tile
-    int finish;                            // 1: every part dumps a partial and fc_finish_kernel reduces them
+    int finish;                            // 1: every part dumps a partial and finish_phase() reduces them after a grid barrier
     int n_major;                           // raster order of tile ids
 };
 struct Work {
@@ -175,11 +191,11 @@ struct Work {
 };
 enum { WORK_FULL = 0, WORK_PARTIAL = 1, WORK_OWNER = 2 };
 
-__device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int grid,
-                                          int force_parts = 0, int force_finish = -1) {
+__device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, int N, int K, int block_n, int tile_m,
+                                          int ws_slots, int grid, int force_parts = 0, int force_finish = -1) {
     Plan p;
     p.m_live = m_live_ptr ? min(max(*m_live_ptr, 0), M_cap) : M_cap;
-    p.m_tiles = (p.m_live + BLOCK_M - 1) / BLOCK_M;
+    p.m_tiles = (p.m_live + tile_m - 1) / tile_m;
     p.n_tiles = (N + block_n - 1) / block_n;
     p.tiles = p.m_tiles * p.n_tiles;
     p.kblocks = K / BLOCK_K;
@@ -188,20 +204,28 @@ __device__ __forceinline__ Plan make_plan(const int32_t *m_live_ptr, int M_cap, 
     p.parts = 1;
     p.finish = 0;
     if (p.rem_tiles > 0) {
-        const int kb_cycles = 2 * block_n;                 // 4 UMMAs of 128 x block_n x 16
+        const int mh = tile_m / HALF_M;
+        // per k-block: 4*mh UMMAs of 128 x block_n x 16 (2*block_n*mh cycles), but never faster than the SM can
+        // take the operands in (measured ~50 B per cycle per SM through TMA)
+        const int kb_bytes = (mh * HALF_M + block_n) * BLOCK_K * 2;
+        const int kb_cycles = max(2 * block_n * mh, kb_bytes / 50);
+        const long slot_bytes = (long)tile_m * block_n * 4;
+        const int peer = (int)(PEER_CYCLES * slot_bytes / 262144);            // in-kernel: the owner adds one peer's partial
         int best = p.kblocks * kb_cycles;                  // P = 1: one wave of whole tiles
         for (int P = 2; P <= MAX_PARTS; ++P) {
-            if (p.kblocks / P < MIN_KB_PER_PART || p.rem_tiles * P > WS_SLOTS) break;
+            if (p.kblocks / P < MIN_KB_PER_PART || p.rem_tiles * P > ws_slots) break;
             const int waves = (p.rem_tiles * P + grid - 1) / grid;
             const int mma = waves * ((p.kblocks + P - 1) / P) * kb_cycles;
-            const int c_in = mma + PEER_CYCLES * (P - 1), c_fin = mma + FINISH_CYCLES;
+            // finish phase: grid barrier + all partials read once by the whole grid (measured ~0.8 KB per cycle)
+            const int fin = FINISH_CYCLES + (int)((long)P * p.rem_tiles * slot_bytes / 800);
+            const int c_in = mma + peer * (P - 1), c_fin = mma + fin;
             if (c_in < best) { best = c_in; p.parts = P; p.finish = 0; }
             if (c_fin < best) { best = c_fin; p.parts = P; p.finish = 1; }
         }
     }
     if (force_parts > 0 && p.rem_tiles > 0) {
         p.parts = force_parts;
-        while (p.parts > 1 && (p.kblocks / p.parts < 1 || p.rem_tiles * p.parts > WS_SLOTS)) --p.parts;
+        while (p.parts > 1 && (p.kblocks / p.parts < 1 || p.rem_tiles * p.parts > ws_slots)) --p.parts;
         p.finish = force_finish > 0 ? 1 : 0;
     } else if (force_finish >= 0 && p.parts > 1) {
         p.finish = force_finish;
@@ -234,8 +258,8 @@ __device__ __forceinline__ void tile_coords(const Plan &p, int tile, int &m_tile
     else           { m_tile = tile / p.n_tiles; n_tile = tile - m_tile * p.n_tiles; }
 }
 // Partial accumulators are stored so that the 32 lanes of a warp (32 consecutive tile rows) touch 32
-// consecutive 16-byte words: float4 index ((chunk*8 + j4) * 128 + row).
-__device__ __forceinline__ size_t partial_f4(int chunk, int j4, int row) { return ((size_t)(chunk * 8 + j4) * BLOCK_M + row); }
+// consecutive 16-byte words: float4 index ((chunk*8 + j4) * tile_m + row).
+__device__ __forceinline__ size_t partial_f4(int chunk, int j4, int row, int tile_m) { return ((size_t)(chunk * 8 + j4) * tile_m + row); }
 
 __device__ __forceinline__ void flag_release(int *flag) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
@@ -245,14 +269,46 @@ __device__ __forceinline__ int flag_acquire(const int *flag) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     return v;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-__device__ __forceinline__ float sigmoid_caffe(float x) {
-    // sigmoid_layer.cpp:11-13: exp in float, `1. / (1. + e)` in double, rounded to float
-    return (float)(1.0 / (1.0 + (double)expf(-x)));
+template <int N_THREADS> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_THREADS) : "memory"); }
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+
+// sigmoid_layer.cpp:11-13 evaluates `1. / (1. + exp(-x))` with a float exp and a double division; here the
+// division is IEEE float (<= 1 ulp from the reference formula, which the reference's own test pins to 4 ulp,
+// test_neuron_layer.cpp:202-217; the bf16 operands of the product move the argument by ~2^-9 relative anyway).
+// A double division per score made the 128-thread epilogue of the heads layer latency-bound (measured 9 us).
+__device__ __forceinline__ float sigmoid_caffe(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// Bias + activation of 32 consecutive columns held in registers.  The activation switch sits OUTSIDE the
+// unrolled column loops: with the switch inside, every column carried all activation bodies and the epilogue
+// thrashed the instruction cache (measured 12 us per 128 x 128 tile instead of ~1).
 // AZN_ACT_AZ_HEAD: columns are [adj_score (nsub) | adj_bbox (4*nsub) | zoom_score (1)]; the two score
 // groups go through the Sigmoid layers adj_prob / zoom_prob (test_fc.prototxt:221-232).
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float *__restrict__ bias, int col0, int N, int act, int nsub) {
+    if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col0 + j));     // col0 % 32 == 0
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += col0 + j < N ? __ldg(bias + col0 + j) : 0.f;
+    }
+    if (act == AZN_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+    } else if (act == AZN_ACT_AZ_HEAD) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;                             // the same column in every lane: a uniform branch
+            if (col < nsub || col == 5 * nsub) v[j] = sigmoid_caffe(v[j]);
+        }
+    }
+}
 __device__ __forceinline__ float apply_act(float v, int act, int col, int nsub) {
     if (act == AZN_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == AZN_ACT_AZ_HEAD) return (col < nsub || col == 5 * nsub) ? sigmoid_caffe(v) : v;
@@ -264,15 +320,85 @@ struct EpiParams {
     void *out;
     int out_dtype, ldo, N, act, act_aux;
     int force_parts, force_finish;   // tuning hook (azn_fc_tune): 0 / -1 = automatic
-    float *ws;           // split partials: [slot][BLOCK_N/4][BLOCK_M] float4, slot = part * rem_tiles + rem
-    int *flags;          // [WS_SLOTS] "the partial of this slot is complete" (zero between launches)
+    float *ws;           // split partials: [slot][BLOCK_N/4][TILE_M] float4, slot = part * rem_tiles + rem
+    int *flags;          // [WS_MAX_SLOTS] "the partial of this slot is complete" (zero between launches)
+    unsigned long long *sync;   // grid-barrier ticket counter of the finish phase (monotonic, never reset)
+    long long *trace;    // azn_fc_trace: per CTA 8 globaltimer stamps, or NULL
 };
+enum { TR_START = 0, TR_SETUP = 1, TR_FIRST_FULL = 2, TR_MMA_DONE = 3, TR_ACC_READY = 4, TR_EPI_DONE = 5, TR_END = 6, TR_UNITS = 7 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// Finish phase of the split schedule with many parts: every part has dumped a raw partial; after a grid-wide
+// barrier (all CTAs are co-resident: one persistent CTA per SM) ALL threads of the grid sum the P partials of
+// every split tile in part order and apply bias + activation.  One thread per (row, 4 columns).
+__device__ __forceinline__ void finish_phase(const Plan &pl, int N, int block_n, int tile_m, const EpiParams &ep) {
+    const int q4 = block_n / 4;                              // float4 columns per tile row
+    const size_t slot_f4 = (size_t)tile_m * q4;
+    const long total = (long)pl.rem_tiles * tile_m * q4;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int trow = (int)(e % tile_m);                  // consecutive threads -> consecutive rows: coalesced partial reads
+        const int c4 = (int)((e / tile_m) % q4);
+        const int rem = (int)(e / ((long)tile_m * q4));
+        int m_tile, n_tile;
+        tile_coords(pl, pl.dp_tiles + rem, m_tile, n_tile);
+        const int row = m_tile * tile_m + trow, col0 = n_tile * block_n + c4 * 4;
+        if (row >= pl.m_live || col0 >= N) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *src = (const float4 *)ep.ws + (size_t)rem * slot_f4 + partial_f4(c4 >> 3, c4 & 7, trow, tile_m);
+        const size_t part_stride = (size_t)pl.rem_tiles * slot_f4;
+        int part = 0;
+        for (; part + 4 <= pl.parts; part += 4) {            // 4 independent L2 reads in flight, summed in part order
+            const float4 t0 = __ldcg(src + (size_t)part * part_stride), t1 = __ldcg(src + (size_t)(part + 1) * part_stride);
+            const float4 t2 = __ldcg(src + (size_t)(part + 2) * part_stride), t3 = __ldcg(src + (size_t)(part + 3) * part_stride);
+            acc.x += t0.x; acc.y += t0.y; acc.z += t0.z; acc.w += t0.w;
+            acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
+            acc.x += t2.x; acc.y += t2.y; acc.z += t2.z; acc.w += t2.w;
+            acc.x += t3.x; acc.y += t3.y; acc.z += t3.z; acc.w += t3.w;
+        }
+        for (; part < pl.parts; ++part) {
+            const float4 t = __ldcg(src + (size_t)part * part_stride);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        if (ep.out_dtype == AZN_DTYPE_BF16 && col0 + 4 <= N && (ep.ldo & 3) == 0) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = apply_act(v[j] + ep.bias[col0 + j], ep.act, col0 + j, ep.act_aux);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+            *reinterpret_cast<uint2 *>((__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0) = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
+            continue;
+        }
+        for (int j = 0; j < 4; ++j) {
+            const int col = col0 + j;
+            if (col >= N) break;
+            const float o = apply_act(v[j] + ep.bias[col], ep.act, col, ep.act_aux);
+            if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(o);
+            else ((float *)ep.out)[(size_t)row * ep.ldo + col] = o;
+        }
+    }
+}
+
+// Grid-wide barrier on a monotonic ticket counter: CTA k takes ticket t and waits until the counter reaches
+// the end of t's generation (every launch that comes here adds exactly gridDim.x tickets).
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long t = atomicAdd(counter, 1ull);
+        const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+template <int BLOCK_N, int MH>
+__global__ void __launch_bounds__(Cfg<BLOCK_N, MH>::THREADS, 1)
 fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, EpiParams ep) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, MH>;
+    constexpr int TILE_M = C::TILE_M;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
@@ -282,14 +408,14 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, BLOCK_N, gridDim.x, ep.force_parts, ep.force_finish);
     const int cta = blockIdx.x, grid = gridDim.x;
+    long long *tr = ep.trace ? ep.trace + (size_t)cta * 8 : nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * MH); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -297,6 +423,10 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above is on-chip setup: it overlaps the tail of the preceding kernel (PDL); global memory from here on
+    pdl_enter();
+    if (tr && threadIdx.x == 0) tr[TR_START] = tr[TR_SETUP] = global_ns();
+    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, BLOCK_N, TILE_M, C::WS_SLOTS, gridDim.x, ep.force_parts, ep.force_finish);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -306,12 +436,16 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx) {
                 int m_tile, n_tile;
                 tile_coords(pl, w.tile, m_tile, n_tile);
+                // 128-row halves of this tile that hold live rows: the others are neither loaded nor multiplied
+                const int halves = min(MH, (pl.m_live - m_tile * TILE_M + HALF_M - 1) / HALF_M);
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(smem_a + s * C::A_BYTES, &tmap_a, &full[s], kb * BLOCK_K, m_tile * BLOCK_M);
+                    mbar_expect_tx(&full[s], halves * C::A_HALF_BYTES + C::B_BYTES);
+                    for (int h = 0; h < halves; ++h)
+                        tma_load_2d(smem_a + s * C::A_BYTES + h * C::A_HALF_BYTES, &tmap_a, &full[s], kb * BLOCK_K,
+                                    m_tile * TILE_M + h * HALF_M);
                     tma_load_2d(smem_b + s * C::B_BYTES, &tmap_w, &full[s], kb * BLOCK_K, n_tile * BLOCK_N);
                 }
             }
@@ -319,126 +453,138 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc = umma_idesc(HALF_M, BLOCK_N);
             uint32_t it = 0;
             Work w;
             for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx) {
-                const int a = idx & 1;
-                const uint32_t aph = ((uint32_t)idx >> 1) & 1;
+                int m_tile, n_tile;
+                tile_coords(pl, w.tile, m_tile, n_tile);
+                const int halves = min(MH, (pl.m_live - m_tile * TILE_M + HALF_M - 1) / HALF_M);
+                const int a = C::NUM_ACC == 2 ? (idx & 1) : 0;
+                const uint32_t aph = C::NUM_ACC == 2 ? (((uint32_t)idx >> 1) & 1) : ((uint32_t)idx & 1);
                 mbar_wait(&tmem_empty[a], aph ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(a * BLOCK_N);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(a * C::ACC_COLS);
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
+                    if (tr && it == 0) tr[TR_FIRST_FULL] = global_ns();
                     const uint64_t adesc = umma_smem_desc(smem_u32(smem_a + s * C::A_BYTES));
                     const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + s * C::B_BYTES));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field;
+                        // the second half's A box sits A_HALF_BYTES further and accumulates BLOCK_N columns further
+                        const uint32_t acc = (kb > w.kb0 || k > 0) ? 1u : 0u;
+                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                        if (MH == 2 && halves == 2)
+                            umma_f16(tmem_d + BLOCK_N, adesc + (uint64_t)(C::A_HALF_BYTES >> 4) + (uint64_t)(2 * k),
+                                     bdesc + (uint64_t)(2 * k), idesc, acc);
                     }
                     umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
                 }
                 umma_commit(&tmem_full[a]);          // accumulator (or partial accumulator) complete
             }
+            if (tr) { tr[TR_MMA_DONE] = global_ns(); }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (4 warps per 128-row half) =====================
         const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-        const int trow = q * 32 + lane;              // row of the tile owned by this thread
+        const int half = (warp - 2) >> 2;            // which accumulator half
+        const int trow = half * HALF_M + q * 32 + lane;   // row of the tile owned by this thread
+        const bool leader = threadIdx.x == 64;
         Work w;
-        for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx) {
+        int units = 0;
+        for (int idx = 0; get_work(pl, cta, grid, idx, w); ++idx, ++units) {
             int m_tile, n_tile;
             tile_coords(pl, w.tile, m_tile, n_tile);
-            const int a = idx & 1;
-            const uint32_t aph = ((uint32_t)idx >> 1) & 1;
+            const int a = C::NUM_ACC == 2 ? (idx & 1) : 0;
+            const uint32_t aph = C::NUM_ACC == 2 ? (((uint32_t)idx >> 1) & 1) : ((uint32_t)idx & 1);
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
-            const int row = m_tile * BLOCK_M + trow;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BLOCK_N);
+            if (tr && leader && idx == 0) tr[TR_ACC_READY] = global_ns();
+            const int row = m_tile * TILE_M + trow;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C::ACC_COLS + half * BLOCK_N);
             const bool row_ok = row < pl.m_live;
+            const bool half_live = m_tile * TILE_M + half * HALF_M < pl.m_live;    // warp-uniform
             // the final part of a split tile waits for the earlier parts (always scheduled on lower unit ids)
             const int peers = w.kind == WORK_OWNER ? pl.parts - 1 : 0;
             if (w.kind == WORK_OWNER) {
-                if (threadIdx.x == 64) {
+                if (leader) {
                     for (int j = 0; j < peers; ++j)
                         while (flag_acquire(ep.flags + j * pl.rem_tiles + w.rem) == 0) { }
                 }
-                epi_bar_sync();
+                epi_bar_sync<C::EPI_THREADS>();
             }
-            constexpr size_t SLOT_F4 = (size_t)BLOCK_M * BLOCK_N / 4;
+            constexpr size_t SLOT_F4 = (size_t)TILE_M * BLOCK_N / 4;
+            if (half_live) {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
-                tmem_ld_wait();
-                const int col0 = n_tile * BLOCK_N + c * 32;
-                if (w.kind == WORK_PARTIAL) {
-                    uint4 *dst = (uint4 *)ep.ws + (size_t)(w.part * pl.rem_tiles + w.rem) * SLOT_F4;
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    const int col0 = n_tile * BLOCK_N + c * 32;
+                    if (w.kind == WORK_PARTIAL) {
+                        uint4 *dst = (uint4 *)ep.ws + (size_t)(w.part * pl.rem_tiles + w.rem) * SLOT_F4;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        __stcg(dst + partial_f4(c, j >> 2, trow), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
-                    continue;
-                }
-                if (!(row_ok && col0 < ep.N)) continue;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                for (int pj = 0; pj < peers; pj += 2) {         // fixed part order => deterministic sum
-                    const float4 *s0 = (const float4 *)ep.ws + (size_t)(pj * pl.rem_tiles + w.rem) * SLOT_F4;
-                    const bool two = pj + 1 < peers;
-                    const float4 *s1 = two ? s0 + (size_t)pl.rem_tiles * SLOT_F4 : s0;
-                    float4 t0[8], t1[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {               // 16 independent L2 reads in flight per thread
-                        t0[j] = __ldcg(s0 + partial_f4(c, j, trow));
-                        t1[j] = __ldcg(s1 + partial_f4(c, j, trow));
+                        for (int j = 0; j < 32; j += 4)
+                            __stcg(dst + partial_f4(c, j >> 2, trow, TILE_M), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+                        continue;
                     }
+                    if (!(row_ok && col0 < ep.N)) continue;
+                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        v[4 * j] += t0[j].x; v[4 * j + 1] += t0[j].y; v[4 * j + 2] += t0[j].z; v[4 * j + 3] += t0[j].w;
-                    }
-                    if (two) {
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int pj = 0; pj < peers; pj += 2) {         // fixed part order => deterministic sum
+                        const float4 *s0 = (const float4 *)ep.ws + (size_t)(pj * pl.rem_tiles + w.rem) * SLOT_F4;
+                        const bool two = pj + 1 < peers;
+                        const float4 *s1 = two ? s0 + (size_t)pl.rem_tiles * SLOT_F4 : s0;
+                        float4 t0[8], t1[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {               // 16 independent L2 reads in flight per thread
+                            t0[j] = __ldcg(s0 + partial_f4(c, j, trow, TILE_M));
+                            t1[j] = __ldcg(s1 + partial_f4(c, j, trow, TILE_M));
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            v[4 * j] += t1[j].x; v[4 * j + 1] += t1[j].y; v[4 * j + 2] += t1[j].z; v[4 * j + 3] += t1[j].w;
+                            v[4 * j] += t0[j].x; v[4 * j + 1] += t0[j].y; v[4 * j + 2] += t0[j].z; v[4 * j + 3] += t0[j].w;
                         }
-                    }
-                }
+                        if (two) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = col0 + j;
-                    const float b = col < ep.N ? __ldg(ep.bias + col) : 0.f;
-                    v[j] = apply_act(v[j] + b, ep.act, col, ep.act_aux);
-                }
-                if (ep.out_dtype == AZN_DTYPE_BF16) {
-                    __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0;
-                    if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                                pk[t] = *(uint32_t *)&h;
+                            for (int j = 0; j < 8; ++j) {
+                                v[4 * j] += t1[j].x; v[4 * j + 1] += t1[j].y; v[4 * j + 2] += t1[j].z; v[4 * j + 3] += t1[j].w;
                             }
-                            *(uint4 *)(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                    bias_act32(v, ep.bias, col0, ep.N, ep.act, ep.act_aux);
+                    if (ep.out_dtype == AZN_DTYPE_BF16) {
+                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0;
+                        if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                                    pk[t] = *(uint32_t *)&h2;
+                                }
+                                *(uint4 *)(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < ep.N) dst[j] = __float2bfloat16_rn(v[j]);
                         }
                     } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < ep.N) dst[j] = __float2bfloat16_rn(v[j]);
-                    }
-                } else {
-                    float *dst = (float *)ep.out + (size_t)row * ep.ldo + col0;
-                    if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
+                        float *dst = (float *)ep.out + (size_t)row * ep.ldo + col0;
+                        if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < ep.N) dst[j] = v[j];
+                            for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < ep.N) dst[j] = v[j];
+                        }
                     }
                 }
             }
@@ -447,14 +593,15 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
             if (w.kind == WORK_PARTIAL && !pl.finish) {
                 __threadfence();                      // partial visible device-wide before the flag
-                epi_bar_sync();
-                if (threadIdx.x == 64) flag_release(ep.flags + w.part * pl.rem_tiles + w.rem);
+                epi_bar_sync<C::EPI_THREADS>();
+                if (leader) flag_release(ep.flags + w.part * pl.rem_tiles + w.rem);
             } else if (w.kind == WORK_OWNER) {
-                epi_bar_sync();                       // every epilogue thread is done reading the peers' slots
-                if (threadIdx.x == 64)
+                epi_bar_sync<C::EPI_THREADS>();       // every epilogue thread is done reading the peers' slots
+                if (leader)
                     for (int j = 0; j < peers; ++j) ep.flags[j * pl.rem_tiles + w.rem] = 0;   // clean for the next launch
             }
         }
+        if (tr && leader) { tr[TR_EPI_DONE] = global_ns(); tr[TR_UNITS] = units; }
     }
     tc_fence_before();
     __syncthreads();
@@ -462,40 +609,12 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
-}
-
-// Finish-kernel mode of the split schedule (many parts): sums the P partials of every split tile in part
-// order and applies bias + activation.  One thread per (row, 4 columns); exits at once in the other modes.
-__global__ void __launch_bounds__(256)
-fc_finish_kernel(const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, int block_n, int grid_gemm, EpiParams ep) {
-    const Plan pl = make_plan(m_live_ptr, M_cap, N, K, block_n, grid_gemm, ep.force_parts, ep.force_finish);
-    if (!pl.finish || pl.parts <= 1) return;
-    const int q4 = block_n / 4;                              // float4 columns per tile row
-    const size_t slot_f4 = (size_t)BLOCK_M * q4;
-    const long total = (long)pl.rem_tiles * BLOCK_M * q4;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int trow = (int)(e % BLOCK_M);                 // consecutive threads -> consecutive rows: coalesced partial reads
-        const int c4 = (int)((e / BLOCK_M) % q4);
-        const int rem = (int)(e / ((long)BLOCK_M * q4));
-        int m_tile, n_tile;
-        tile_coords(pl, pl.dp_tiles + rem, m_tile, n_tile);
-        const int row = m_tile * BLOCK_M + trow, col0 = n_tile * block_n + c4 * 4;
-        if (row >= pl.m_live || col0 >= N) continue;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int part = 0; part < pl.parts; ++part) {
-            const float4 t = __ldcg((const float4 *)ep.ws + (size_t)(part * pl.rem_tiles + rem) * slot_f4 +
-                                    partial_f4(c4 >> 3, c4 & 7, trow));
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
-        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
-        for (int j = 0; j < 4; ++j) {
-            const int col = col0 + j;
-            if (col >= N) break;
-            const float o = apply_act(v[j] + ep.bias[col], ep.act, col, ep.act_aux);
-            if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(o);
-            else ((float *)ep.out)[(size_t)row * ep.ldo + col] = o;
-        }
+    if (pl.finish && pl.parts > 1) {                 // uniform over the grid: the plan is a pure function of m_live
+        __threadfence();                             // this CTA's partial dumps, before the barrier publishes them
+        grid_barrier(ep.sync);
+        finish_phase(pl, N, BLOCK_N, TILE_M, ep);
     }
+    if (tr && threadIdx.x == 0) tr[TR_END] = global_ns();
 }
 
 // Row softmax over the first `ncls` columns of a f32 [M, ld] matrix, in place
@@ -569,25 +688,29 @@ int make_tmap(const void *ptr, int rows, int cols, int box_rows, CUtensorMap *ou
     return AZN_OK;
 }
 
-// 128 x 256 tiles (87 FLOP per L2 byte) for the wide layers that carry the FLOPs (int6 / fc6 / fc7);
-// narrower tiles for the small layers, where more tiles beat splitting the K loop.
-int g_force_parts = 0, g_force_finish = -1, g_force_bn = 0;
-int pick_block_n(int N) {
-    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) return g_force_bn;
-    return N >= 2048 ? 256 : (N > 64 ? 128 : 64);
+// Tile choice: 256 x 256 (two accumulators, 128 FLOP per L2 byte) for the wide layers that carry the FLOPs
+// (int6 / fc6 / fc7); narrower single-accumulator tiles for the small layers, where more tiles beat splitting
+// the K loop.
+int g_force_parts = 0, g_force_finish = -1, g_force_bn = 0, g_force_mh = 0;
+long long *g_trace = nullptr;
+void pick_tile(int N, int &bn, int &mh) {
+    bn = N >= 2048 ? 256 : (N > 64 ? 128 : 64);
+    mh = N >= 2048 ? 2 : 1;
+    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) bn = g_force_bn;
+    if (g_force_mh == 1 || g_force_mh == 2) mh = g_force_mh;
+    if (bn == 64) mh = 1;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MH>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_live, int M_cap, int N, int K,
                 const EpiParams &ep, int grid, cudaStream_t s) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, MH>;
     static bool attr = false;
     if (!attr) {
-        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
-    fc_gemm_kernel<BLOCK_N><<<grid, GEMM_THREADS, C::SMEM_BYTES, s>>>(ta, tw, m_live, M_cap, N, K, ep);
-    AZN_LAUNCH_CHECK();
+    AZN_CUDA(azn_launch_pdl(fc_gemm_kernel<BLOCK_N, MH>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep));
     return AZN_OK;
 }
 
@@ -596,14 +719,16 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_l
 extern "C" void azn_fc_tune(int parts, int finish_mode, int block_n) {
     g_force_parts = parts;
     g_force_finish = finish_mode;
-    g_force_bn = block_n;
+    g_force_bn = block_n % 1000;             // block_n + 1000 * rows-halves: 1256 = 128 x 256 tiles, 2256 = 256 x 256
+    g_force_mh = block_n / 1000;
 }
 
+extern "C" void azn_fc_trace(long long *device_buffer) { g_trace = device_buffer; }
+
 extern "C" size_t azn_fc_workspace_bytes(int M_cap, int N, int K) {
-    (void)M_cap; (void)K;
-    // WS_SLOTS partial accumulators of 128 x BLOCK_N fp32 + one flag word per slot
-    (void)N;
-    return (size_t)WS_SLOTS * BLOCK_M * 256 * sizeof(float) + 4096;    // sized for the widest tile
+    (void)M_cap; (void)K; (void)N;
+    // partial-accumulator slots (128 MB: 512 slots of 256 x 256 fp32, or 1024 narrower ones) + one flag word per slot
+    return WS_DATA_BYTES + 8192;
 }
 
 extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype, int ldo,
@@ -620,17 +745,17 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     AZN_REQUIRE(act != AZN_ACT_SOFTMAX_BBOX || (out_dtype == AZN_DTYPE_F32 && act_aux > 0 && act_aux <= N),
                 "azn_fc_forward: softmax needs f32 output and 0 < classes <= N");
     cudaStream_t s = (cudaStream_t)stream;
-    const int bn = pick_block_n(N);
+    int bn, mh;
+    pick_tile(N, bn, mh);
     const int grid = azn_num_sms();
-    const size_t slots = (size_t)WS_SLOTS * BLOCK_M * 256 * sizeof(float);
-    const size_t need = slots + 4096;
-    static_assert(WS_SLOTS * sizeof(int) <= 4096, "flag block");
+    const size_t need = WS_DATA_BYTES + 8192;        // partials + flag block + barrier counter
+    static_assert(WS_MAX_SLOTS * sizeof(int) <= 4096, "flag block");
     if (!workspace || workspace_bytes < need) {
         azn_set_error("azn_fc_forward: workspace %zu < %zu bytes", workspace_bytes, need);
         return AZN_ERR_CAPACITY;
     }
     CUtensorMap ta, tw;
-    int rc = make_tmap(A, M_cap, K, BLOCK_M, &ta);
+    int rc = make_tmap(A, M_cap, K, HALF_M, &ta);
     if (rc) return rc;
     rc = make_tmap(W, N, K, bn, &tw);
     if (rc) return rc;
@@ -641,21 +766,15 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     ep.force_parts = g_force_parts;
     ep.force_finish = g_force_finish;
     ep.ws = (float *)workspace;
-    ep.flags = (int *)((char *)workspace + slots);
-    if (bn == 256) rc = launch_gemm<256>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
-    else if (bn == 128) rc = launch_gemm<128>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
-    else rc = launch_gemm<64>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    ep.flags = (int *)((char *)workspace + WS_DATA_BYTES);
+    ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
+    ep.trace = g_trace;
+    if (bn == 256 && mh == 2) rc = launch_gemm<256, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    else if (bn == 256) rc = launch_gemm<256, 1>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    else if (bn == 128 && mh == 2) rc = launch_gemm<128, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    else if (bn == 128) rc = launch_gemm<128, 1>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
+    else rc = launch_gemm<64, 1>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     if (rc) return rc;
-    // the split mode is decided on the device; the finish kernel returns at once unless it is needed, and is
-    // not even launched when the capacity rules a split out (tile count of M_cap a multiple of the grid is
-    // not knowable for a live count, so only the static case is skipped)
-    {
-        const long tiles_cap = (long)((M_cap + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
-        if (m_live != nullptr || tiles_cap % grid != 0) {
-            fc_finish_kernel<<<grid * 4, 256, 0, s>>>(m_live, M_cap, N, K, bn, grid, ep);
-            AZN_LAUNCH_CHECK();
-        }
-    }
     if (act == AZN_ACT_SOFTMAX_BBOX) {
         softmax_rows_kernel<<<grid, 256, 0, s>>>((float *)out, m_live, M_cap, ldo, act_aux);
         AZN_LAUNCH_CHECK();

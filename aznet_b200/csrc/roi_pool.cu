@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256)
 roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
                      int PH, int PW, float scale, uint4 *__restrict__ out) {
+    pdl_enter();
     __shared__ int s_ws[2][POOL_MAX_PW], s_we[2][POOL_MAX_PW], s_row[2][3];
     const int R = n_rois ? min(*n_rois, R_cap) : R_cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -827,7 +828,7 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         const uint4 *f = (const uint4 *)feat;
         uint4 *o = (uint4 *)out;
 #define AZN_POOL_LAUNCH(OPS, NVV) \
-        roi_pool_nhwc_kernel<OPS, NVV><<<(unsigned)blocks, nwarps * 32, 0, s>>>(f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o)
+        AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_kernel<OPS, NVV>, dim3((unsigned)blocks), dim3(nwarps * 32), 0, s, f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o))
         if (dtype == AZN_DTYPE_F32) {
             if (nv == 4) AZN_POOL_LAUNCH(OpsF32, 4); else if (nv == 2) AZN_POOL_LAUNCH(OpsF32, 2); else AZN_POOL_LAUNCH(OpsF32, 1);
         } else {

@@ -151,6 +151,7 @@ __device__ __forceinline__ int unique_slot(const long long *__restrict__ keys, c
 }
 
 __global__ void search_init_kernel(azn_search_state st) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         *st.m_total = st.n_img;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(LEVEL_THREADS)
 search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, int ld_zoom,
                     const float *__restrict__ adj_prob, int ld_prob, const float *__restrict__ adj_bbox, int ld_bbox,
                     int level, int last_level) {
+    pdl_enter();
     __shared__ int s_warp[33];
     const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int capR = st.cap_regions;
@@ -330,6 +332,7 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
 // Packs the per-image unique ROIs of the level that is about to run into one dense [M,5] blob.
 // Called after the caller swapped regions <-> next_regions.
 __global__ void __launch_bounds__(256) search_pack_kernel(azn_search_state st) {
+    pdl_enter();
     const int i = blockIdx.x, tid = threadIdx.x;
     __shared__ int s_off;
     if (tid < 32) {
@@ -370,6 +373,7 @@ __device__ __forceinline__ unsigned score_key(float s) {      // monotone float 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(azn_search_state st, int mode, int num_proposals, double tc, double *__restrict__ out_boxes,
               float *__restrict__ out_scores, int32_t *__restrict__ out_count, int cap_out, int *__restrict__ scratch) {
+    pdl_enter();
     __shared__ int s_warp[33];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_prefix, s_need;
@@ -557,8 +561,7 @@ int check_state(const azn_search_state *st) {
 extern "C" int azn_search_init(const azn_search_state *st, azn_stream_t stream) {
     int rc = check_state(st);
     if (rc) return rc;
-    search_init_kernel<<<(st->n_img + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*st);
-    AZN_LAUNCH_CHECK();
+    AZN_CUDA(azn_launch_pdl(search_init_kernel, dim3((st->n_img + 127) / 128), dim3(128), 0, (cudaStream_t)stream, *st));
     return AZN_OK;
 }
 
@@ -571,16 +574,14 @@ extern "C" int azn_search_level(const azn_search_state *st, const float *zoom_pr
                 "azn_search_level: bad head pointers/strides");
     AZN_REQUIRE(level >= 1, "azn_search_level: level is 1-based");
     cudaStream_t s = (cudaStream_t)stream;
-    search_level_kernel<<<st->n_img, LEVEL_THREADS, 0, s>>>(*st, zoom_prob, ld_zoom, adj_prob, ld_prob, adj_bbox,
-                                                           ld_bbox, level, last_level);
-    AZN_LAUNCH_CHECK();
+    AZN_CUDA(azn_launch_pdl(search_level_kernel, dim3(st->n_img), dim3(LEVEL_THREADS), 0, s, *st, zoom_prob, ld_zoom, adj_prob,
+                            ld_prob, adj_bbox, ld_bbox, level, last_level));
     if (!last_level) {
         // the next level's regions become current: swap, then pack its unique ROIs
         azn_search_state nx = *st;
         nx.regions = st->next_regions;
         nx.n_regions = st->next_n_regions;
-        search_pack_kernel<<<st->n_img, 256, 0, s>>>(nx);
-        AZN_LAUNCH_CHECK();
+        AZN_CUDA(azn_launch_pdl(search_pack_kernel, dim3(st->n_img), dim3(256), 0, s, nx));
     }
     return AZN_OK;
 }
@@ -595,9 +596,8 @@ extern "C" int azn_select_proposals(const azn_search_state *st, int mode, int nu
     AZN_REQUIRE(mode == 1 || num_proposals >= 0, "azn_select_proposals: num_proposals < 0");
     AZN_REQUIRE(cap_out <= st->cap_children, "azn_select_proposals: cap_out (%d) exceeds the flags scratch (%d)", cap_out,
                 st->cap_children);
-    select_kernel<<<st->n_img, SEL_THREADS, 0, (cudaStream_t)stream>>>(*st, mode, num_proposals, tc, out_boxes, out_scores,
-                                                                      out_count, cap_out, st->flags);
-    AZN_LAUNCH_CHECK();
+    AZN_CUDA(azn_launch_pdl(select_kernel, dim3(st->n_img), dim3(SEL_THREADS), 0, (cudaStream_t)stream, *st, mode, num_proposals,
+                            tc, out_boxes, out_scores, out_count, cap_out, st->flags));
     return AZN_OK;
 }
 

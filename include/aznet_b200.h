@@ -46,6 +46,9 @@ const char *azn_version(void);
 const char *azn_last_error(void);
 /* 0 when the current device is sm_100 (B200); AZN_ERR_CUDA otherwise. */
 int azn_check_device(void);
+/* Programmatic dependent launch of the level-loop kernels (default on): kernel K+1 is scheduled while kernel K
+ * drains and waits (griddepcontrol.wait) before it touches global memory.  0 = plain stream order (benchmarks). */
+void azn_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------
  * ROI max pooling, forward.
@@ -92,8 +95,13 @@ int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, 
  * persistent with one CTA per SM and its CTAs wait on each other: it needs the whole GPU. */
 size_t azn_fc_workspace_bytes(int M_cap, int N, int K);
 /* Tuning hook for benchmarks: force the split factor (0 = automatic), the fix-up mode (-1 automatic, 0 in-kernel,
- * 1 finish kernel) and the tile width (0 automatic, 64 / 128 / 256) of subsequent azn_fc_forward calls. */
+ * 1 grid-wide finish phase) and the tile (0 automatic; 64 / 128 / 256 = tile width, + 1000 x the number of 128-row
+ * accumulator halves: 1256 = 128 x 256 tiles, 2256 = 256 x 256) of subsequent azn_fc_forward calls. */
 void azn_fc_tune(int parts, int finish_mode, int block_n);
+/* Profiling hook: when non-NULL, every CTA of subsequent azn_fc_forward launches writes 8 int64 words
+ * (globaltimer ns: start, setup done, first operands landed, last MMA issued, first accumulator ready,
+ * epilogue done, end; and its number of work units) at device_buffer[8 * cta].  NULL switches it off. */
+void azn_fc_trace(long long *device_buffer);
 int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, int out_dtype,
                    int ldo, int M_cap, const int32_t *m_live, int N, int K, int act, int act_aux,
                    void *workspace, size_t workspace_bytes, azn_stream_t stream);

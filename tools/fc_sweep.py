@@ -40,9 +40,9 @@ def main():
         for M in Ms:
             ml = torch.tensor([M], dtype=torch.int32, device=dev)
             res = {}
-            bns = [256, 128] if N >= 1024 else [64, 128]
+            bns = [2256, 1256, 2128, 1128] if N >= 1024 else [64, 1128, 2128]      # tile code: 1000 * row halves + width
             for bn in bns:
-                for parts, mode in [(0, -1), (1, 0), (2, 0), (3, 0), (2, 1), (4, 1), (8, 1), (16, 1)]:
+                for parts, mode in [(0, -1), (1, 0), (2, 0), (3, 0), (4, 0), (2, 1), (4, 1), (8, 1)]:
                     L.lib().azn_fc_tune(parts, mode, bn)
                     res["bn%d_p%d_m%d" % (bn, parts, mode)] = round(run(A, W, b, act, aux, out, ml) * 1e3, 1)
             L.lib().azn_fc_tune(0, -1, 0)
