@@ -18,11 +18,16 @@
 //   2. nms_mask_kernel   -- 64x64 IoU tiles of the upper triangle -> one 64-bit suppression word
 //                           per (row, column tile); exact intersection pre-test, division only
 //                           for intersecting pairs.
-//   3. nms_scan_kernel   -- one CTA walks the column tiles in order: it gathers (pull) the column
-//                           word of every row kept so far and OR-reduces it with warp shuffles,
-//                           warp 0 resolves the 64x64 diagonal block over the surviving rows with
-//                           register-resident words, and the kept original indices are appended to
-//                           `keep` (on-device compaction; the count never visits the host).
+//   3. nms_super_kernel  -- the greedy pass, blocked like a triangular solve: super-tiles of 16 column tiles
+//                           (1024 boxes) are resolved one launch each.  CTA 0 stages the 1024 x 1024-bit
+//                           diagonal block (128 KB) in shared memory, folds in the suppression words of the
+//                           previous super-tile's kept rows ("urgent" update), then walks its 16 tiles: warp 0
+//                           resolves the 64 x 64 diagonal block of tile b with register-resident words while
+//                           the other 31 warps OR together column b+1's words of the rows kept so far; kept
+//                           original indices are appended to `keep` (on-device compaction; the count never
+//                           visits the host).  The other CTAs of the same launch push the PREVIOUS super-tile's
+//                           kept rows into the `removed` words of all later columns (bulk update, atomicOr).
+//                           No CTA ever waits for another inside a launch.
 // Many small problems (azn_nms_batched, one per class per image in apply_nms,
 // lib/detect/test.py:467-484): one warp per problem, boxes in shared memory, the suppression
 // state in per-lane registers exchanged with ballots.
@@ -103,15 +108,25 @@ __device__ __forceinline__ bool intersects(const float4 &a, const float4 &b) {
     return w > 0.f && h > 0.f;
 }
 
-// grid = (col_tiles, row_tiles), 64 threads; only tiles with col >= row do work.  Two phases per thread:
-// a cheap exact intersection test over the 64 columns, then the full IoU (IEEE division + double compare)
-// only for the columns that intersect -- with an empty intersection the reference computes ovr = +-0 or
-// NaN, which is >= thresh for no positive threshold, so those pairs can never be suppressed.
-__global__ void __launch_bounds__(64)
+// One 64-thread CTA per 64 x 64 tile of the upper triangle (linear block id -> (row tile, col tile)); thread =
+// row.  Two phases per thread: a cheap exact intersection test over the 64 columns (boxes broadcast from shared
+// memory), then the full IoU (IEEE division + double compare) only for the columns that intersect -- with an
+// empty intersection the reference computes ovr = +-0 or NaN, which is >= thresh for no positive threshold,
+// so those pairs can never be suppressed.  (A lanes-own-columns / ballot variant was measured 1.5x slower: it
+// runs the division path for every row, because some lane of 32 random columns always intersects.)
+constexpr int MASK_THREADS = 64;
+
+__global__ void __launch_bounds__(MASK_THREADS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
                 u64 *__restrict__ mask, int col_tiles) {
-    const int rt = blockIdx.y, ct = blockIdx.x;
-    if (ct < rt) return;
+    // block id -> (rt, ct), ct >= rt: row rt of the triangle starts at id0(rt) = rt * T - rt * (rt - 1) / 2
+    const long id = blockIdx.x;
+    const double Tp = 2.0 * col_tiles + 1.0;
+    int rt = (int)((Tp - sqrt(Tp * Tp - 8.0 * (double)id)) * 0.5);
+    rt = max(0, min(rt, col_tiles - 1));
+    while (rt > 0 && (long)rt * col_tiles - (long)rt * (rt - 1) / 2 > id) --rt;
+    while ((long)(rt + 1) * col_tiles - (long)(rt + 1) * rt / 2 <= id) ++rt;
+    const int ct = rt + (int)(id - ((long)rt * col_tiles - (long)rt * (rt - 1) / 2));
     __shared__ float4 cb[64];
     __shared__ float ca[64];
     const int cn = min(64, n - ct * 64);
@@ -120,93 +135,220 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
         ca[threadIdx.x] = areas[ct * 64 + threadIdx.x];
     }
     __syncthreads();
+    u64 *dst = mask + ((size_t)rt * col_tiles + ct) * 64 + threadIdx.x;      // blocked: [row tile][col tile][64 rows]
     const int row = rt * 64 + threadIdx.x;
-    if (row >= n) return;
+    if (row >= n) {                                                          // rows past the end: no suppression bits
+        *dst = 0ull;
+        return;
+    }
     const float4 rb = boxes[row];
     const float ra = areas[row];
     const int start = (rt == ct) ? threadIdx.x + 1 : 0;
-    u64 cand = 0;
+    unsigned cand_lo = 0, cand_hi = 0;
     if (thresh > 0.0) {
-        for (int k = start; k < cn; ++k) cand |= (u64)(intersects(rb, cb[k]) ? 1 : 0) << k;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if (k >= start && k < cn && intersects(rb, cb[k])) cand_lo |= 1u << k;
+            if (k + 32 >= start && k + 32 < cn && intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+        }
     } else {
-        cand = (cn == 64 ? ~0ull : ((1ull << cn) - 1ull)) & (start >= 64 ? 0ull : (~0ull << start));
+        const u64 all = (cn == 64 ? ~0ull : ((1ull << cn) - 1ull)) & (start >= 64 ? 0ull : (~0ull << start));
+        cand_lo = (unsigned)all;
+        cand_hi = (unsigned)(all >> 32);
     }
+    u64 cand = (u64)cand_lo | ((u64)cand_hi << 32);
     u64 bits = 0;
     while (cand) {
         const int k = __ffsll((long long)cand) - 1;
         cand &= cand - 1;
         if (suppresses(rb, ra, cb[k], ca[k], thresh)) bits |= 1ull << k;
     }
-    mask[(size_t)row * col_tiles + ct] = bits;
+    *dst = bits;
+}
+
+// Transposed diagonal blocks: diag_t[t][j] bit i <=> row i of tile t suppresses row j of tile t (i < j).  The
+// greedy pass resolves a tile from these columns (which kept rows suppress me?) in a few ballot rounds.
+__global__ void __launch_bounds__(64)
+nms_diag_transpose_kernel(const u64 *__restrict__ mask, int col_tiles, u64 *__restrict__ diag_t) {
+    __shared__ u64 s_d[64];
+    const int t = blockIdx.x;
+    s_d[threadIdx.x] = mask[((size_t)t * col_tiles + t) * 64 + threadIdx.x];
+    __syncthreads();
+    u64 col = 0;
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> threadIdx.x) & 1ull) << i;
+    diag_t[(size_t)t * 64 + threadIdx.x] = col;
 }
 
 constexpr int SCAN_THREADS = 1024;
+constexpr int SUPER = 16;                      // column tiles per super-tile
+constexpr int SUPER_UPDATERS = 48;             // CTAs of a launch that push the previous super-tile's kept rows
 
-// One CTA walks the column tiles in score order.  For tile b it PULLS the suppression word of column tile b
-// from every row kept so far (parallel gather + OR-reduction), warp 0 resolves the 64x64 diagonal block by
-// iterating over the surviving rows only, and the kept rows are appended to `keep` / `kept_rows`.
+__device__ __forceinline__ u64 warp_or(u64 v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+// OR of the words of one 64-row block whose row bit is set in `kb`; lane l holds rows 2l and 2l+1 (one 16-byte load)
+__device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
+    return (((kb >> (2 * lane)) & 1ull) ? w.x : 0ull) | (((kb >> (2 * lane + 1)) & 1ull) ? w.y : 0ull);
+}
+
+// Launch s of the greedy pass (see the header).  mask is blocked [row tile][col tile][64]; `removed[c]` collects
+// the suppression bits of column tile c from all kept rows of super-tiles that are at least two behind c's;
+// `kept_bits[t]` is the kept mask of row tile t; `nkept` the running number of kept boxes.
 __global__ void __launch_bounds__(SCAN_THREADS)
-nms_scan_kernel(const u64 *__restrict__ mask, const int *__restrict__ order, int n, int col_tiles,
-                int *__restrict__ kept_rows, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count) {
-    __shared__ u64 s_or[SCAN_THREADS / 32];
-    __shared__ int s_nkept;
+nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, const int *__restrict__ order, int n, int col_tiles, int s_idx,
+                 u64 *__restrict__ removed, u64 *__restrict__ kept_bits, int *__restrict__ nkept_ptr,
+                 int64_t *__restrict__ keep, int32_t *__restrict__ keep_count, int last) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_nkept = 0;
-    __syncthreads();
-    for (int b = 0; b < col_tiles; ++b) {
-        const int row0 = b * 64;
-        const int nkept = s_nkept;
-        // diagonal words first (independent of the gather below)
-        u64 d_lo = 0, d_hi = 0;
-        if (warp == 0) {
-            const int r_lo = row0 + lane, r_hi = row0 + 32 + lane;
-            d_lo = r_lo < n ? mask[(size_t)r_lo * col_tiles + b] : 0ull;
-            d_hi = r_hi < n ? mask[(size_t)r_hi * col_tiles + b] : 0ull;
-        }
-        u64 acc = 0;
-        int j = tid;
-        for (; j + 3 * SCAN_THREADS < nkept; j += 4 * SCAN_THREADS) {
-            const int r0 = __ldcg(kept_rows + j), r1 = __ldcg(kept_rows + j + SCAN_THREADS), r2 = __ldcg(kept_rows + j + 2 * SCAN_THREADS),
-                      r3 = __ldcg(kept_rows + j + 3 * SCAN_THREADS);
-            const u64 m0 = mask[(size_t)r0 * col_tiles + b], m1 = mask[(size_t)r1 * col_tiles + b],
-                      m2 = mask[(size_t)r2 * col_tiles + b], m3 = mask[(size_t)r3 * col_tiles + b];
-            acc |= m0 | m1 | m2 | m3;
-        }
-        for (; j < nkept; j += SCAN_THREADS) acc |= mask[(size_t)__ldcg(kept_rows + j) * col_tiles + b];
+    const int T0 = s_idx * SUPER;
+    if (blockIdx.x > 0) {
+        // ---------------- bulk update: kept rows of super-tile s-1 -> removed[] of the columns after super-tile s
+        pdl_enter();
+        if (s_idx == 0) return;
+        const int pt0 = T0 - SUPER, c0 = T0 + SUPER;
+        const int ncols = col_tiles - c0;
+        if (ncols <= 0) return;
+        const long nblk = (long)SUPER * ncols;
+        const long wid = (long)(blockIdx.x - 1) * (SCAN_THREADS / 32) + warp, nw = (long)(gridDim.x - 1) * (SCAN_THREADS / 32);
+        for (long k0 = wid; k0 < nblk; k0 += 4 * nw) {
+            ulonglong2 w[4];
+            u64 kb[4];
+            int col[4];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) s_or[warp] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            u64 cur = s_or[lane];
+            for (int u = 0; u < 4; ++u) {                       // four independent 512-byte blocks in flight per warp
+                const long k = k0 + u * nw;
+                col[u] = -1;
+                kb[u] = 0ull;
+                w[u] = make_ulonglong2(0ull, 0ull);
+                if (k < nblk) {
+                    const int tp = (int)(k / ncols), c = c0 + (int)(k - (long)tp * ncols);
+                    kb[u] = kept_bits[pt0 + tp];
+                    col[u] = c;
+                    if (kb[u]) w[u] = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(pt0 + tp) * col_tiles + c) * 64) + lane);
+                }
+            }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) cur |= __shfl_xor_sync(0xffffffffu, cur, d);
-            const int rows = min(64, n - row0);
-            u64 alive = ~cur & (rows == 64 ? ~0ull : ((1ull << rows) - 1ull));
-            u64 kept = 0;
-            while (alive) {                                   // warp-uniform: every lane holds the same `alive`
-                const int r = __ffsll((long long)alive) - 1;
-                kept |= 1ull << r;
-                const u64 d = __shfl_sync(0xffffffffu, r < 32 ? d_lo : d_hi, r & 31);
-                alive &= ~d;
-                alive &= ~(1ull << r);
+            for (int u = 0; u < 4; ++u) {
+                if (col[u] < 0 || kb[u] == 0ull) continue;      // warp-uniform
+                const u64 v = warp_or(select2(w[u], kb[u], lane));
+                if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + col[u]), (unsigned long long)v);
             }
-            const int r_lo = row0 + lane, r_hi = row0 + 32 + lane;
-            if ((kept >> lane) & 1ull) {
-                const int pos = nkept + __popcll(kept & ((1ull << lane) - 1ull));
-                keep[pos] = order[r_lo];
-                kept_rows[pos] = r_lo;
-            }
-            if ((kept >> (lane + 32)) & 1ull) {
-                const int pos = nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull));
-                keep[pos] = order[r_hi];
-                kept_rows[pos] = r_hi;
-            }
-            if (lane == 0) s_nkept = nkept + __popcll(kept);
         }
-        __syncthreads();      // kept_rows / s_nkept visible to the whole CTA (global writes by the same CTA)
+        return;
     }
-    if (tid == 0) *keep_count = s_nkept;
+    // ---------------- CTA 0: resolve super-tile s
+#ifdef AZN_NMS_TRACE
+    const long long tt0 = clock64();
+#endif
+    extern __shared__ u64 s_blk[];                               // [SUPER][SUPER][64] diagonal super-block
+    __shared__ u64 s_col[SUPER], s_kept[SUPER], s_prev[SUPER];
+    __shared__ int s_order[SUPER * 64];
+    const int nt = min(SUPER, col_tiles - T0);
+    // The mask, its transposed diagonal blocks and the sort order were written before the FIRST launch of the
+    // greedy pass: this launch may stage them while the previous one is still resolving (PDL), and only then
+    // waits for the previous super-tile's results.
+    if (T0 * 64 + tid < n) s_order[tid] = order[T0 * 64 + tid];
+    // A: stage the upper triangle of the diagonal super-block (16-byte cp.async chunks, 32 per 64-row block)
+    for (int ch = tid; ch < SUPER * SUPER * 32; ch += SCAN_THREADS) {
+        const int blk = ch >> 5, tp = blk / SUPER, b = blk - tp * SUPER;
+        if (tp <= b && b < nt) {                                 // slot (b, b) holds the TRANSPOSED diagonal block of tile b
+            const u64 *src = (tp == b ? diag_t + (size_t)(T0 + b) * 64 : mask + ((size_t)(T0 + tp) * col_tiles + (T0 + b)) * 64) + (ch & 31) * 2;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_blk + (size_t)blk * 64 + (ch & 31) * 2)), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pdl_enter();
+    if (tid < SUPER) {
+        s_col[tid] = tid < nt ? removed[T0 + tid] : 0ull;
+        s_kept[tid] = 0ull;
+        s_prev[tid] = s_idx > 0 ? kept_bits[T0 - SUPER + tid] : 0ull;
+    }
+    __syncthreads();
+    // B: urgent update -- kept rows of super-tile s-1 against this super-tile's columns (SUPER x nt blocks)
+    if (s_idx > 0) {
+        const int pt0 = T0 - SUPER;
+        const int nblk = SUPER * nt;                                       // <= 256 blocks: 8 per warp, all in flight
+        ulonglong2 w[8];
+        u64 kb[8];
+        int bcol[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = warp + u * (SCAN_THREADS / 32);
+            bcol[u] = -1;
+            kb[u] = 0ull;
+            w[u] = make_ulonglong2(0ull, 0ull);
+            if (k < nblk) {
+                const int tp = k / nt, b = k - tp * nt;
+                kb[u] = s_prev[tp];
+                bcol[u] = b;
+                if (kb[u]) w[u] = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(pt0 + tp) * col_tiles + (T0 + b)) * 64) + lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (bcol[u] < 0 || kb[u] == 0ull) continue;                   // warp-uniform
+            const u64 v = warp_or(select2(w[u], kb[u], lane));
+            if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(&s_col[bcol[u]]), (unsigned long long)v);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+#ifdef AZN_NMS_TRACE
+    const long long tt1 = clock64();
+#endif
+    // C: the 16 tiles in order.  Iteration b: warp 0 resolves tile b; warps 1..31 gather, for column b+1, the words of
+    // the rows kept in tiles 0..b-1 of this super-tile; warp 0 adds tile b's own rows once it knows them.
+    int nkept = *nkept_ptr;
+    for (int b = 0; b < nt; ++b) {
+        if (warp == 0) {
+            const int row0 = (T0 + b) * 64;
+            // Lane l owns rows l and l+32 and holds their columns of the diagonal block: t_lo / t_hi bit i <=> row i
+            // (i < own row) suppresses it.  Rounds over the undecided set U: a row with a KEPT suppressor is removed,
+            // a row with no undecided suppressor left is kept; the lowest undecided row always decides, and
+            // independent rows decide together (typically 2-4 rounds per tile instead of one step per kept row).
+            const u64 *diag = s_blk + (size_t)(b * SUPER + b) * 64;
+            const u64 t_lo = diag[lane], t_hi = diag[lane + 32];
+            const int rows = min(64, n - row0);
+            u64 und = ~s_col[b] & (rows == 64 ? ~0ull : ((1ull << rows) - 1ull));       // warp-uniform
+            u64 kept = 0;
+            while (und) {
+                const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+                const bool rem0 = u0 && (t_lo & kept) != 0ull, rem1 = u1 && (t_hi & kept) != 0ull;
+                const bool ok0 = u0 && !rem0 && (t_lo & und) == 0ull, ok1 = u1 && !rem1 && (t_hi & und) == 0ull;
+                const u64 new_kept = (u64)__ballot_sync(0xffffffffu, ok0) | ((u64)__ballot_sync(0xffffffffu, ok1) << 32);
+                const u64 new_rem = (u64)__ballot_sync(0xffffffffu, rem0) | ((u64)__ballot_sync(0xffffffffu, rem1) << 32);
+                kept |= new_kept;
+                und &= ~(new_kept | new_rem);
+            }
+            if (b + 1 < nt) {                                 // tile b's rows against column b+1
+                const u64 *nb = s_blk + (size_t)(b * SUPER + b + 1) * 64;
+                const u64 v = warp_or((((kept >> lane) & 1ull) ? nb[lane] : 0ull) | (((kept >> (lane + 32)) & 1ull) ? nb[lane + 32] : 0ull));
+                if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(&s_col[b + 1]), (unsigned long long)v);
+            }
+            if ((kept >> lane) & 1ull) keep[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = s_order[b * 64 + lane];
+            if ((kept >> (lane + 32)) & 1ull) keep[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = s_order[b * 64 + 32 + lane];
+            if (lane == 0) { s_kept[b] = kept; kept_bits[T0 + b] = kept; }
+            nkept += __popcll(kept);
+        } else if (b + 1 < nt && b >= 1) {
+            u64 acc = 0;
+            for (int p = tid - 32; p < b * 64; p += SCAN_THREADS - 32) {
+                const int tp = p >> 6, i = p & 63;
+                if ((s_kept[tp] >> i) & 1ull) acc |= s_blk[(size_t)(tp * SUPER + b + 1) * 64 + i];
+            }
+            acc = warp_or(acc);
+            if (lane == 0 && acc) atomicOr(reinterpret_cast<unsigned long long *>(&s_col[b + 1]), (unsigned long long)acc);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *nkept_ptr = nkept;
+        if (last) *keep_count = nkept;
+#ifdef AZN_NMS_TRACE
+        printf("nms super %d: stage+urgent %lld cycles, 16 tiles %lld cycles\n", s_idx, tt1 - tt0, clock64() - tt1);
+#endif
+    }
 }
 
 // One warp per segment.  Shared memory per warp: 6 * max_seg floats/ints.
@@ -261,8 +403,8 @@ nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ s
 struct NmsWorkspace {
     float4 *boxes;
     float *areas;
-    int *order, *rank, *kept_rows;
-    u64 *mask;
+    int *order, *rank, *nkept;
+    u64 *removed, *kept_bits, *diag_t, *mask;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -274,9 +416,12 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
     w.areas = (float *)p;   p += align_up(sizeof(float) * n, 256);
     w.order = (int *)p;     p += align_up(sizeof(int) * n, 256);
     w.rank = (int *)p;      p += align_up(sizeof(int) * n, 256);
-    w.kept_rows = (int *)p; p += align_up(sizeof(int) * n, 256);
+    // zeroed per call in one memset: rank | removed | kept_bits | nkept
+    w.removed = (u64 *)p;   p += align_up(sizeof(u64) * col_tiles, 256);
+    w.kept_bits = (u64 *)p; p += align_up(sizeof(u64) * col_tiles, 256);
+    w.nkept = (int *)p;     p += 256;
+    w.diag_t = (u64 *)p;    p += align_up(sizeof(u64) * col_tiles * 64, 256);
     w.mask = (u64 *)p;
-    (void)col_tiles;
     return w;
 }
 
@@ -285,8 +430,8 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
 extern "C" size_t azn_nms_workspace_bytes(int64_t n) {
     if (n <= 0) return 256;
     const size_t ct = (size_t)((n + 63) / 64);
-    return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + 3 * align_up(sizeof(int) * n, 256) +
-           align_up(sizeof(u64) * (size_t)n * ct, 256);
+    return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + 2 * align_up(sizeof(int) * n, 256) +
+           2 * align_up(sizeof(u64) * ct, 256) + 256 + align_up(sizeof(u64) * ct * 64, 256) + align_up(sizeof(u64) * ct * ct * 64, 256);
 }
 
 extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *keep, int32_t *keep_count,
@@ -305,16 +450,34 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
     }
     const int col_tiles = (int)((n + 63) / 64);
     NmsWorkspace w = carve(workspace, n, col_tiles);
-    AZN_CUDA(cudaMemsetAsync(w.rank, 0, sizeof(int) * n, s));
+    AZN_CUDA(cudaMemsetAsync(w.rank, 0, (size_t)((char *)w.diag_t - (char *)w.rank), s));   // rank, removed, kept_bits, nkept
     nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
                       RANK_THREADS, 0, s>>>(dets, (int)n, w.rank);
     AZN_LAUNCH_CHECK();
     nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
     AZN_LAUNCH_CHECK();
-    nms_mask_kernel<<<dim3(col_tiles, col_tiles), 64, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles);
+    nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles);
     AZN_LAUNCH_CHECK();
-    nms_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(w.mask, w.order, (int)n, col_tiles, w.kept_rows, keep, keep_count);
+    nms_diag_transpose_kernel<<<col_tiles, 64, 0, s>>>(w.mask, col_tiles, w.diag_t);
     AZN_LAUNCH_CHECK();
+    {
+        const size_t smem = (size_t)SUPER * SUPER * 64 * sizeof(u64);      // 128 KB diagonal super-block
+        static bool attr_set = false;
+        if (!attr_set) {
+            AZN_CUDA(cudaFuncSetAttribute(nms_super_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int n_super = (col_tiles + SUPER - 1) / SUPER;
+        for (int si = 0; si < n_super; ++si) {
+            // the updaters of launch si push super-tile si-1 into the columns after super-tile si
+            const int upd_cols = col_tiles - (si + 1) * SUPER;
+            int updaters = (si == 0 || upd_cols <= 0) ? 0 : (SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
+            if (updaters > SUPER_UPDATERS) updaters = SUPER_UPDATERS;
+            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, s, (const u64 *)w.mask, (const u64 *)w.diag_t,
+                                    (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
+                                    si == n_super - 1 ? 1 : 0));
+        }
+    }
     return AZN_OK;
 }
 
