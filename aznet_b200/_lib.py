@@ -24,10 +24,11 @@ LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_AZ_HEAD, ACT_SOFTMAX_BBOX = 0, 1, 2, 3
 NMS_SEG_MAX = 1024
+LEVEL_LAST, LEVEL_ROOT_PROPS = 1, 2
 
 EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
-    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_level", "azn_select_proposals",
+    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched",
 ]
@@ -110,6 +111,8 @@ def _bind(L):
     L.azn_fc_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, sz, vp]
     L.azn_search_init.restype = i32
     L.azn_search_init.argtypes = [C.POINTER(SearchState), vp]
+    L.azn_search_root.restype = i32
+    L.azn_search_root.argtypes = [C.POINTER(SearchState), vp]
     L.azn_search_level.restype = i32
     L.azn_search_level.argtypes = [C.POINTER(SearchState), vp, i32, vp, i32, vp, i32, i32, i32, vp]
     L.azn_select_proposals.restype = i32

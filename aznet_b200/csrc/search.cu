@@ -20,6 +20,7 @@
 namespace {
 
 constexpr int LEVEL_THREADS = 512;
+constexpr int AZN_LEVEL_ROOT_DIVIDE = 4;     // internal: phases 2-4 for the root only (azn_search_root)
 
 // exclusive block scan of one int per thread; returns the exclusive prefix, `total` = block sum.
 __device__ __forceinline__ int block_excl_scan(int v, int &total, int *s_warp /* [33] */) {
@@ -178,27 +179,31 @@ __global__ void search_init_kernel(azn_search_state st) {
 __global__ void __launch_bounds__(LEVEL_THREADS)
 search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, int ld_zoom,
                     const float *__restrict__ adj_prob, int ld_prob, const float *__restrict__ adj_bbox, int ld_bbox,
-                    int level, int last_level) {
+                    int level, int mode) {
     pdl_enter();
     __shared__ int s_warp[33];
     const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int capR = st.cap_regions;
+    const bool last_level = mode & AZN_LEVEL_LAST, root_props = mode & AZN_LEVEL_ROOT_PROPS,
+               root_divide = mode & AZN_LEVEL_ROOT_DIVIDE;
+    // merged levels 1+2: the root's rows are [0, n_img) of the head outputs and its inv/rep are the identity
+    // (the per-image index arrays already describe level 2 when the root's predictions are appended)
     const int nR = st.n_regions[i];
-    const int row0 = st.img_off[i];
+    const int row0 = root_props ? i : st.img_off[i];
     const double *regions = st.regions + (size_t)i * capR * 4;
     const int *inv = st.inv + (size_t)i * capR;
     const int *rep = st.rep + (size_t)i * capR;
     if (nR <= 0) {                                   // search already ended for this image (test.py:388-389)
-        if (tid == 0) st.next_n_regions[i] = 0, st.n_uniq[i] = 0;
+        if (tid == 0 && !root_props) st.next_n_regions[i] = 0, st.n_uniq[i] = 0;
         return;
     }
-    if (tid == 0) {
+    if (tid == 0 && !root_divide) {
         st.depth[i] = level;
         st.n_eval[i] += nR;
     }
 
     // ---------------- phase 1: adjacent predictions -> Y ------------------------------------
-    {
+    if (!root_divide) {
         const int nsub = st.nsub, ncand = nR * nsub;
         const double wmax = (double)st.im_w[i] - 1.0, hmax = (double)st.im_h[i] - 1.0;
         double *props = st.props + (size_t)i * st.cap_props * 4;
@@ -211,8 +216,8 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
             int keep = 0;
             if (c < ncand) {
                 const int r = c / nsub, s = c - r * nsub;
-                const int u = inv[r];                              // un-dedup: pred[inv_index] (:246-249)
-                const double *box = regions + (size_t)rep[u] * 4;  // boxes = boxes[index] (:218): the representative's box
+                const int u = root_props ? 0 : inv[r];             // un-dedup: pred[inv_index] (:246-249)
+                const double *box = regions + (size_t)(root_props ? 0 : rep[u]) * 4;  // boxes = boxes[index] (:218): the representative's box
                 const float *d = adj_bbox + (size_t)(row0 + u) * ld_bbox + 4 * s;
                 decode_clip(box[0], box[1], box[2], box[3], d[0], d[1], d[2], d[3], st.eps, wmax, hmax, b);
                 const double hh = __dadd_rn(__dsub_rn(b[3], b[1]), 1.0), ww = __dadd_rn(__dsub_rn(b[2], b[0]), 1.0);
@@ -234,6 +239,7 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
         }
         if (tid == 0) st.n_props[i] = base < st.cap_props ? base : st.cap_props;
     }
+    if (root_props) return;
     if (last_level) {
         if (tid == 0) st.next_n_regions[i] = 0, st.n_uniq[i] = 0;
         return;
@@ -250,8 +256,10 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
         DivGeom g;
         const double *box = regions + (size_t)(r < nR ? r : 0) * 4;
         if (r < nR) {
-            double z = (double)zoom_prob[(size_t)(row0 + inv[r]) * ld_zoom];
-            if (level == 1 && r == 0) z = 1.0;                     // the root region is always divided (:383-384)
+            // the root region is always divided (:383-384), whatever the net says: level 2 does not depend on
+            // level 1's outputs, which is what lets the two levels share one pass of the heads
+            double z = 1.0;
+            if (!(level == 1 && r == 0)) z = (double)zoom_prob[(size_t)(row0 + inv[r]) * ld_zoom];
             if (z >= st.tz) {                                      // indZ = where(zoom >= Tz) (:386)
                 g = div_geom(box[0], box[1], box[2], box[3]);
                 cnt = div_count(g);
@@ -331,7 +339,7 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
 
 // Packs the per-image unique ROIs of the level that is about to run into one dense [M,5] blob.
 // Called after the caller swapped regions <-> next_regions.
-__global__ void __launch_bounds__(256) search_pack_kernel(azn_search_state st) {
+__global__ void __launch_bounds__(256) search_pack_kernel(azn_search_state st, int row_base) {
     pdl_enter();
     const int i = blockIdx.x, tid = threadIdx.x;
     __shared__ int s_off;
@@ -341,6 +349,7 @@ __global__ void __launch_bounds__(256) search_pack_kernel(azn_search_state st) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         if (tid == 0) {
+            acc += row_base;                         // merged levels 1+2: rows [0, n_img) belong to the roots
             s_off = acc;
             st.img_off[i] = acc;
             if (i == st.n_img - 1) {
@@ -567,22 +576,38 @@ extern "C" int azn_search_init(const azn_search_state *st, azn_stream_t stream) 
 
 extern "C" int azn_search_level(const azn_search_state *st, const float *zoom_prob, int ld_zoom,
                                 const float *adj_prob, int ld_prob, const float *adj_bbox, int ld_bbox,
-                                int level, int last_level, azn_stream_t stream) {
+                                int level, int flags, azn_stream_t stream) {
     int rc = check_state(st);
     if (rc) return rc;
     AZN_REQUIRE(zoom_prob && adj_prob && adj_bbox && ld_zoom >= 1 && ld_prob >= st->nsub && ld_bbox >= 4 * st->nsub,
                 "azn_search_level: bad head pointers/strides");
     AZN_REQUIRE(level >= 1, "azn_search_level: level is 1-based");
+    AZN_REQUIRE((flags & ~(AZN_LEVEL_LAST | AZN_LEVEL_ROOT_PROPS)) == 0, "azn_search_level: unknown flags %d", flags);
+    AZN_REQUIRE(!(flags & AZN_LEVEL_ROOT_PROPS) || level == 1, "azn_search_level: AZN_LEVEL_ROOT_PROPS is for level 1");
     cudaStream_t s = (cudaStream_t)stream;
     AZN_CUDA(azn_launch_pdl(search_level_kernel, dim3(st->n_img), dim3(LEVEL_THREADS), 0, s, *st, zoom_prob, ld_zoom, adj_prob,
-                            ld_prob, adj_bbox, ld_bbox, level, last_level));
-    if (!last_level) {
+                            ld_prob, adj_bbox, ld_bbox, level, flags));
+    if (!flags) {
         // the next level's regions become current: swap, then pack its unique ROIs
         azn_search_state nx = *st;
         nx.regions = st->next_regions;
         nx.n_regions = st->next_n_regions;
-        AZN_CUDA(azn_launch_pdl(search_pack_kernel, dim3(st->n_img), dim3(256), 0, s, nx));
+        AZN_CUDA(azn_launch_pdl(search_pack_kernel, dim3(st->n_img), dim3(256), 0, s, nx, 0));
     }
+    return AZN_OK;
+}
+
+extern "C" int azn_search_root(const azn_search_state *st, azn_stream_t stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    AZN_CUDA(azn_launch_pdl(search_init_kernel, dim3((st->n_img + 127) / 128), dim3(128), 0, s, *st));
+    AZN_CUDA(azn_launch_pdl(search_level_kernel, dim3(st->n_img), dim3(LEVEL_THREADS), 0, s, *st, (const float *)nullptr, 0,
+                            (const float *)nullptr, 0, (const float *)nullptr, 0, 1, (int)AZN_LEVEL_ROOT_DIVIDE));
+    azn_search_state nx = *st;
+    nx.regions = st->next_regions;
+    nx.n_regions = st->next_n_regions;
+    AZN_CUDA(azn_launch_pdl(search_pack_kernel, dim3(st->n_img), dim3(256), 0, s, nx, st->n_img));
     return AZN_OK;
 }
 

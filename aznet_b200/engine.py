@@ -83,7 +83,7 @@ class SearchEngine:
 
     def __init__(self, head: AZHeadWeights, n_img, im_h, im_w, *, scales=(600,), max_size=1000, min_side=10, tz=0.5,
                  tc=0.05, fixed_num=True, num_proposals=300, batch_size=10000, dedup=1. / 16., eps=1e-14,
-                 spatial_scale=0.0625, device=None):
+                 spatial_scale=0.0625, device=None, merge_root=True):
         L.require_device()
         self.head = head
         self.dev = device or head.w6.device
@@ -94,6 +94,9 @@ class SearchEngine:
         self.scale = im_scale_for(im_h, im_w, scales, max_size)
         self.K = search_depth(im_h, im_w, min_side)
         self.n_levels = max(self.K - 1, 0)
+        # the root is always zoomed (test.py:383-384), so level 2 does not depend on level 1's head outputs:
+        # both levels go through ONE pass of the heads (one stream of the 216 MB of weights less per step)
+        self.merge_root = bool(merge_root) and self.n_levels >= 2
         dev, i32, f64 = self.dev, torch.int32, torch.float64
         # capacity plan: full-zoom cascade of divide_region run with the product kernel itself
         self.level_sizes = self._plan_levels()
@@ -112,7 +115,7 @@ class SearchEngine:
         self.regions = [z(n, capR, 4, dt=f64), z(n, capR, 4, dt=f64)]
         self.n_regions = [z(n), z(n)]
         self.inv, self.rep, self.n_uniq, self.img_off = z(n, capR), z(n, capR), z(n), z(n + 1)
-        self.rois = z(n * capR, 5, dt=torch.float32)
+        self.rois = z(n * capR + n, 5, dt=torch.float32)
         self.m_total = z(1)
         self.children, self.hashes, self.flags = z(n, capC, 4, dt=f64), z(n, capC, dt=torch.int64), z(n, capC)
         self.props, self.prop_scores = z(n, capP, 4, dt=f64), z(n, capP, dt=torch.float32)
@@ -122,6 +125,9 @@ class SearchEngine:
         self.out_count = z(n)
         m_cap = n * capR
         self.m_cap_level = [n * s for s in self.level_sizes]
+        if self.merge_root:
+            self.m_cap_level[1] += n                       # the merged pass: root rows + level-2 rows
+        m_cap = max([m_cap] + self.m_cap_level)
         k6 = head.w6.shape[1]
         self.pool5 = torch.empty((m_cap, k6), dtype=torch.bfloat16, device=dev)
         self.h6 = torch.empty((m_cap, head.h6), dtype=torch.bfloat16, device=dev)
@@ -241,15 +247,21 @@ class SearchEngine:
         self._m_idx = 0
         return {"levels": levels, "int6_deepest": top}
 
-    def search_level(self, level: int):
+    def begin_merged(self):
+        """Levels 1+2 share one pass of the heads: root ROIs in rows [0, n_img), level-2 ROIs behind them."""
+        self._point(0)
+        L.check(L.lib().azn_search_root(C.byref(self._st), ops._stream()), "azn_search_root")
+        self.launches += 3
+
+    def search_level(self, level: int, root_props: bool = False):
         hd, ld = self.head, self.head.ld_head
-        last = 1 if level == self.n_levels else 0
+        flags = L.LEVEL_ROOT_PROPS if root_props else (L.LEVEL_LAST if level == self.n_levels else 0)
         base = self.heads.data_ptr()
         L.check(L.lib().azn_search_level(C.byref(self._st), base + 4 * 5 * hd.nsub, ld, base, ld, base + 4 * hd.nsub, ld,
-                                         level, last, ops._stream()), "azn_search_level")
-        self.launches += 1 if last else 2
-        if not last:
-            self._point(1 - self._cur)
+                                         level, flags, ops._stream()), "azn_search_level")
+        self.launches += 1 if flags else 2
+        if not flags or root_props:
+            self._point(1 - self._cur)                 # after the root's predictions, level 2 becomes current
 
 
     def select(self):
@@ -263,8 +275,16 @@ class SearchEngine:
         """Run the whole search on resident NHWC bf16 maps [n_img, H, W, C].  Asynchronous; results are
         in out_boxes / out_scores / out_count / n_eval / depth (device tensors)."""
         assert conv_nhwc.dtype == torch.bfloat16 and conv_nhwc.shape[0] == self.n_img and conv_nhwc.is_contiguous()
-        self.begin()
-        for k in range(1, self.n_levels + 1):
+        first = 1
+        if self.merge_root:
+            self.begin_merged()
+            self.run_heads(conv_nhwc, 2)
+            self.search_level(1, root_props=True)
+            self.search_level(2)
+            first = 3
+        else:
+            self.begin()
+        for k in range(first, self.n_levels + 1):
             self.run_heads(conv_nhwc, k)
             self.search_level(k)
         self.select()

@@ -156,10 +156,24 @@ typedef struct azn_search_state {
 int azn_search_init(const azn_search_state *st, azn_stream_t stream);
 /* heads: zoom_prob f32 (row stride ld_zoom floats), adj_prob f32 [.,nsub] (ld_prob),
  * adj_bbox f32 [.,4*nsub] (ld_bbox), rows indexed by img_off[i] + unique slot.
- * level: 1-based k of the reference loop; last_level != 0 skips the (discarded) subdivision. */
+ * level: 1-based k of the reference loop; flags:
+ *   AZN_LEVEL_LAST        the subdivision of this level would be discarded (k == K-1): skip it;
+ *   AZN_LEVEL_ROOT_PROPS  level 1 after azn_search_root: append the root's adjacent predictions (head rows
+ *                         [0, n_img), one per image) and nothing else -- the subdivision already happened. */
+#define AZN_LEVEL_LAST 1
+#define AZN_LEVEL_ROOT_PROPS 2
 int azn_search_level(const azn_search_state *st, const float *zoom_prob, int ld_zoom,
                      const float *adj_prob, int ld_prob, const float *adj_bbox, int ld_bbox,
-                     int level, int last_level, azn_stream_t stream);
+                     int level, int flags, azn_stream_t stream);
+/* Levels 1 and 2 in one pass of the heads.  The reference forces zoom[0] = 1.0 at k == 1
+ * (lib/detect/test.py:383-384), so the regions of level 2 = _sift_dup(divide_region(root)) do not depend on
+ * the net's output for the root.  azn_search_root = azn_search_init + that subdivision + the level-2 dedup:
+ * afterwards `rois` holds the n_img root ROIs in rows [0, n_img) followed by the packed unique level-2 ROIs
+ * (img_off[i] >= n_img, m_total = n_img + sum n_uniq), and next_regions / next_n_regions hold level 2.
+ * The caller runs the heads once over m_total rows, then azn_search_level(level 1, AZN_LEVEL_ROOT_PROPS) on
+ * the unswapped state and azn_search_level(level 2, ...) on the swapped one: same Y, same order, one weight
+ * pass less. */
+int azn_search_root(const azn_search_state *st, azn_stream_t stream);
 
 /* Final selection.  replaces: lib/detect/test.py:393-401.
  *   mode 0: top-`num_proposals` by score (ties: lower index first), mode 1: score >= tc in order.

@@ -34,17 +34,30 @@ class _FakeHead:
         self.w6 = torch.zeros((64, 7 * 7 * 8), dtype=torch.bfloat16, device=dev)
 
 
+def _host_heads(eng, net):
+    m = int(eng.m_total.item())
+    rois = eng.rois[:m].cpu().numpy().copy()
+    rois[:, 0] = 0                                      # HashNet hashes the reference's per-image blob (level column 0)
+    z, p, d = net.heads(rois)
+    h = np.zeros((m, 56), np.float32)
+    h[:, :11], h[:, 11:55], h[:, 55] = p, d, z[:, 0]
+    eng.heads[:m] = torch.from_numpy(h).to(eng.heads.device)
+
+
 def _drive_with_hashnet(eng, net, n_img):
-    """Level loop with the heads computed on the host by HashNet from the ROIs the GPU produced."""
-    eng.begin()
-    for k in range(1, eng.n_levels + 1):
-        m = int(eng.m_total.item())
-        rois = eng.rois[:m].cpu().numpy().copy()
-        rois[:, 0] = 0                                  # HashNet hashes the reference's per-image blob (level column 0)
-        z, p, d = net.heads(rois)
-        h = np.zeros((m, 56), np.float32)
-        h[:, :11], h[:, 11:55], h[:, 55] = p, d, z[:, 0]
-        eng.heads[:m] = torch.from_numpy(h).to(eng.heads.device)
+    """Level loop with the heads computed on the host by HashNet from the ROIs the GPU produced; the same
+    launch sequence as SearchEngine.propose (levels 1+2 in one pass of the heads when eng.merge_root)."""
+    first = 1
+    if eng.merge_root:
+        eng.begin_merged()
+        _host_heads(eng, net)
+        eng.search_level(1, root_props=True)
+        eng.search_level(2)
+        first = 3
+    else:
+        eng.begin()
+    for k in range(first, eng.n_levels + 1):
+        _host_heads(eng, net)
         eng.search_level(k)
     eng.select()
     return eng.results()
@@ -54,14 +67,15 @@ CASES = ["d0_600x1000", "voc_600x1000", "fullzoom_600x1000", "small_375x500", "c
          "tc_thresh_333x500", "nozoom_600x1000"]
 
 
+@pytest.mark.parametrize("merge_root", [True, False], ids=["merged12", "level_by_level"])
 @pytest.mark.parametrize("name", CASES)
-def test_search_matches_reference_golden(dev, golden, name):
+def test_search_matches_reference_golden(dev, golden, name, merge_root):
     from aznet_b200 import engine
     g = golden["search"]
     H, W, max_size, bs, tz, rate, nprop, fixed = g[name + "_cfg"]
     n_img = 3
     eng = engine.SearchEngine(_FakeHead(dev), n_img, int(H), int(W), max_size=int(max_size), batch_size=int(bs), tz=float(tz),
-                              fixed_num=bool(fixed), num_proposals=300 if nprop < 0 else int(nprop))
+                              fixed_num=bool(fixed), num_proposals=300 if nprop < 0 else int(nprop), merge_root=merge_root)
     boxes, scores, n_eval, depth = _drive_with_hashnet(eng, synth.HashNet(seed=11, zoom_rate=float(rate)), n_img)
     ref = g[name + "_Y"]
     log = str(g[name + "_log"])
@@ -86,7 +100,7 @@ def test_search_levels_match_oracle_trace(dev, O):
     cfg = O.OracleCfg(Tz=0.5)
     trace = []
     O.im_propose({"full": net, "fc": net}, (H, W, 3), cfg, conv={"conv5_3": np.zeros((1, 1, 2, 2), np.float32)}, trace=trace)
-    eng = engine.SearchEngine(_FakeHead(dev), 1, H, W, tz=0.5)
+    eng = engine.SearchEngine(_FakeHead(dev), 1, H, W, tz=0.5, merge_root=False)
     eng.begin()
     for k in range(1, eng.n_levels + 1):
         n = int(eng.n_regions[eng._cur][0].item())
@@ -126,7 +140,7 @@ def test_engine_real_heads_vs_oracle(dev, O):
     head = engine.AZHeadWeights(w, dev)
     eng = engine.SearchEngine(head, n_img, H, W, num_proposals=300, tz=0.5)
     nhwc = ops.nchw_to_nhwc_bf16(torch.from_numpy(conv).to(dev))
-    # level-1 head outputs
+    # level-1 head outputs (the root rows of the merged pass are the same rows 0 .. n_img-1)
     eng.begin()
     eng.run_heads(nhwc, 1)
     torch.cuda.synchronize()
