@@ -30,7 +30,8 @@ EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
-    "azn_nms", "azn_nms_batched",
+    "azn_nms", "azn_nms_batched", "azn_nms_segments",
+    "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter",
 ]
 
 
@@ -83,6 +84,21 @@ class SearchState(C.Structure):
     ]
 
 
+class DetectState(C.Structure):
+    """Mirror of `struct azn_detect_state`."""
+    _fields_ = [
+        ("n_img", C.c_int32), ("cap_boxes", C.c_int32), ("num_classes", C.c_int32), ("max_per_image", C.c_int32),
+        ("chunk", C.c_int32), ("ld_head", C.c_int32),
+        ("im_h", C.c_void_p), ("im_w", C.c_void_p), ("im_scale", C.c_void_p),
+        ("eps", C.c_double), ("dedup", C.c_double),
+        ("boxes", C.c_void_p), ("n_boxes", C.c_void_p), ("inv", C.c_void_p), ("rep", C.c_void_p),
+        ("n_uniq", C.c_void_p), ("img_off", C.c_void_p), ("rois", C.c_void_p), ("m_total", C.c_void_p),
+        ("hashes", C.c_void_p), ("flags", C.c_void_p),
+        ("head_out", C.c_void_p), ("thresh", C.c_void_p), ("dets", C.c_void_p), ("top_scores", C.c_void_p),
+        ("det_count", C.c_void_p),
+    ]
+
+
 _LIB = None
 
 
@@ -129,6 +145,16 @@ def _bind(L):
     L.azn_nms.argtypes = [vp, i64, f64, vp, vp, vp, sz, vp]
     L.azn_nms_batched.restype = i32
     L.azn_nms_batched.argtypes = [vp, vp, i32, f64, vp, vp, vp]
+    L.azn_nms_segments.restype = i32
+    L.azn_nms_segments.argtypes = [vp, vp, vp, i32, i32, f64, vp, vp, vp]
+    L.azn_detect_rois.restype = i32
+    L.azn_detect_rois.argtypes = [C.POINTER(DetectState), vp]
+    L.azn_detect_select.restype = i32
+    L.azn_detect_select.argtypes = [C.POINTER(DetectState), vp]
+    L.azn_detect_thresholds.restype = i32
+    L.azn_detect_thresholds.argtypes = [vp, vp, i32, i32, i32, C.c_longlong, vp, vp]
+    L.azn_detect_filter.restype = i32
+    L.azn_detect_filter.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     return L
 
 

@@ -355,15 +355,15 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
 constexpr int BATCH_WARPS = 4;
 
 __global__ void __launch_bounds__(BATCH_WARPS * 32)
-nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ seg_off, int n_seg, double thresh,
-                   int max_seg, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count) {
+nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ seg_off, const int32_t *__restrict__ seg_len,
+                   int n_seg, double thresh, int max_seg, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *sx1 = smem + (size_t)warp * 6 * max_seg;
     float *sy1 = sx1 + max_seg, *sx2 = sy1 + max_seg, *sy2 = sx2 + max_seg, *sar = sy2 + max_seg;
     int *sid = (int *)(sar + max_seg);
     for (int seg = blockIdx.x * BATCH_WARPS + warp; seg < n_seg; seg += gridDim.x * BATCH_WARPS) {
-        const int o = seg_off[seg], n = seg_off[seg + 1] - o;
+        const int o = seg_off[seg], n = seg_len ? seg_len[seg] : seg_off[seg + 1] - o;
         if (n > max_seg || n < 0) {
             if (lane == 0) keep_count[seg] = -1;
             continue;
@@ -481,23 +481,40 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
     return AZN_OK;
 }
 
+static int launch_batched(const float *dets, const int32_t *seg_off, const int32_t *seg_len, int n_seg, int max_seg,
+                          double thresh, int64_t *keep, int32_t *keep_count, cudaStream_t stream) {
+    const size_t smem = (size_t)BATCH_WARPS * 6 * max_seg * sizeof(float);   // 96 KB at AZN_NMS_SEG_MAX
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        AZN_CUDA(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    int blocks = (n_seg + BATCH_WARPS - 1) / BATCH_WARPS;
+    size_t per_sm = (200 * 1024) / (smem > 0 ? smem : 1);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int cap = azn_num_sms() * (int)per_sm;
+    if (blocks > cap) blocks = cap;
+    nms_batched_kernel<<<blocks, BATCH_WARPS * 32, smem, stream>>>(dets, seg_off, seg_len, n_seg, thresh, max_seg, keep,
+                                                                keep_count);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
 extern "C" int azn_nms_batched(const float *dets, const int32_t *seg_off, int n_seg, double thresh,
                                int64_t *keep, int32_t *keep_count, azn_stream_t stream) {
     AZN_REQUIRE(n_seg >= 0, "azn_nms_batched: n_seg < 0");
     if (n_seg == 0) return AZN_OK;
     AZN_REQUIRE(dets && seg_off && keep && keep_count, "azn_nms_batched: null pointer");
-    const int max_seg = AZN_NMS_SEG_MAX;
-    const size_t smem = (size_t)BATCH_WARPS * 6 * max_seg * sizeof(float);   // 96 KB
-    static bool attr_set = false;
-    if (!attr_set) {
-        AZN_CUDA(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    int blocks = (n_seg + BATCH_WARPS - 1) / BATCH_WARPS;
-    const int cap = azn_num_sms() * 2;
-    if (blocks > cap) blocks = cap;
-    nms_batched_kernel<<<blocks, BATCH_WARPS * 32, smem, (cudaStream_t)stream>>>(dets, seg_off, n_seg, thresh, max_seg,
-                                                                              keep, keep_count);
-    AZN_LAUNCH_CHECK();
-    return AZN_OK;
+    return launch_batched(dets, seg_off, nullptr, n_seg, AZN_NMS_SEG_MAX, thresh, keep, keep_count, (cudaStream_t)stream);
+}
+
+extern "C" int azn_nms_segments(const float *dets, const int32_t *seg_off, const int32_t *seg_len, int n_seg, int max_len,
+                                double thresh, int64_t *keep, int32_t *keep_count, azn_stream_t stream) {
+    AZN_REQUIRE(n_seg >= 0, "azn_nms_segments: n_seg < 0");
+    if (n_seg == 0) return AZN_OK;
+    AZN_REQUIRE(dets && seg_off && seg_len && keep && keep_count, "azn_nms_segments: null pointer");
+    AZN_REQUIRE(max_len > 0 && max_len <= AZN_NMS_SEG_MAX, "azn_nms_segments: max_len must be in [1, %d]", AZN_NMS_SEG_MAX);
+    return launch_batched(dets, seg_off, seg_len, n_seg, (max_len + 31) / 32 * 32, thresh, keep, keep_count,
+                          (cudaStream_t)stream);
 }

@@ -26,7 +26,7 @@ def _need_cuda(*ts):
 
 def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_scale: float = 0.0625,
              layout: str = "NCHW", n_rois: torch.Tensor | None = None, want_argmax: bool = False,
-             out: torch.Tensor | None = None):
+             out: torch.Tensor | None = None, staged: bool | None = None):
     """ROI max pooling (roi_pooling_layer.cpp:46-125).  feat [n,C,H,W] (NCHW) or [n,H,W,C] (NHWC),
     f32 or bf16; rois f32 [R,5].  Returns pooled [R,C,P,P] (NCHW) or [R,P,P,C] (NHWC)."""
     _need_cuda(feat, rois, n_rois)
@@ -44,8 +44,14 @@ def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_sc
     lay = L.LAYOUT_NCHW if layout == "NCHW" else L.LAYOUT_NHWC
     nbytes = L.lib().azn_roi_pool_workspace_bytes(n, Cc, H, W, lay, dt, R)
     ws = _scratch(feat.device, nbytes) if nbytes else None
-    L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
-                                     spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, _stream()), "azn_roi_pool_fwd")
+    if staged is not None:                     # many ROIs per image with a device-side count: ask for the staged kernel
+        L.lib().azn_roi_pool_tune(2 if staged else 1)
+    try:
+        L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
+                                         spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, _stream()), "azn_roi_pool_fwd")
+    finally:
+        if staged is not None:
+            L.lib().azn_roi_pool_tune(0)
     return (out, amax) if want_argmax else out
 
 
@@ -125,6 +131,44 @@ def nms_batched(dets: torch.Tensor, seg_off: torch.Tensor, thresh: float):
     L.check(L.lib().azn_nms_batched(_ptr(dets), _ptr(seg_off), S, float(thresh), _ptr(keep), _ptr(cnt), _stream()),
             "azn_nms_batched")
     return keep, cnt[:S]
+
+
+def nms_segments(dets: torch.Tensor, seg_off: torch.Tensor, seg_len: torch.Tensor, max_len: int, thresh: float):
+    """NMS over padded storage: segment s = rows [seg_off[s], seg_off[s] + seg_len[s]) of dets f32 [T,5].
+    Returns (keep int64 [T] segment-local indices at seg_off[s], counts int32 [S])."""
+    _need_cuda(dets, seg_off, seg_len)
+    assert dets.dtype == torch.float32 and seg_off.dtype == torch.int32 and seg_len.dtype == torch.int32
+    assert dets.is_contiguous() and seg_off.is_contiguous() and seg_len.is_contiguous()
+    S = seg_off.numel()
+    keep = torch.empty(max(dets.shape[0], 1), dtype=torch.int64, device=dets.device)
+    cnt = torch.zeros(max(S, 1), dtype=torch.int32, device=dets.device)
+    L.check(L.lib().azn_nms_segments(_ptr(dets), _ptr(seg_off), _ptr(seg_len), S, int(max_len), float(thresh), _ptr(keep),
+                                     _ptr(cnt), _stream()), "azn_nms_segments")
+    return keep, cnt[:S]
+
+
+def detect_thresholds(top_scores: torch.Tensor, det_count: torch.Tensor, max_per_set: int, out: torch.Tensor | None = None):
+    """test_net's per-class thresholds after the whole image set (lib/detect/test.py:624-631).
+    top_scores f32 [n, C, mpi] score-descending rows, det_count int32 [n, C].  Returns f32 [C]."""
+    _need_cuda(top_scores, det_count)
+    assert top_scores.dtype == torch.float32 and det_count.dtype == torch.int32
+    assert top_scores.is_contiguous() and det_count.is_contiguous()
+    n, Cc, mpi = top_scores.shape
+    if out is None:
+        out = torch.empty(Cc, dtype=torch.float32, device=top_scores.device)
+    L.check(L.lib().azn_detect_thresholds(_ptr(top_scores), _ptr(det_count), n, Cc, mpi, int(max_per_set), _ptr(out),
+                                          _stream()), "azn_detect_thresholds")
+    return out
+
+
+def detect_filter(top_scores: torch.Tensor, det_count: torch.Tensor, thresh: torch.Tensor):
+    """Final `score > thresh[class]` filter of test_net (:646-651): shrinks det_count in place."""
+    _need_cuda(top_scores, det_count, thresh)
+    assert thresh.dtype == torch.float32 and det_count.dtype == torch.int32 and det_count.is_contiguous()
+    n, Cc, mpi = top_scores.shape
+    L.check(L.lib().azn_detect_filter(_ptr(top_scores), _ptr(det_count), _ptr(thresh), n, Cc, mpi, _stream()),
+            "azn_detect_filter")
+    return det_count
 
 
 def divide_region(regions: torch.Tensor, min_side: float, sift_only: bool = False):

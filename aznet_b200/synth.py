@@ -160,6 +160,38 @@ class HashNet:
         return out
 
 
+class HashDetNet(HashNet):
+    """The Fast R-CNN flavour of HashNet: cls_prob [R,C] (24-bit uniforms, not normalised -- the selection only
+    compares them) and bbox_pred [R,4C] as an integer hash of the ROI bits.  Pins the detection step's control
+    flow (dedup, un-dedup, per-class selection, thresholds, NMS) bit for bit."""
+
+    def __init__(self, seed=13, num_classes=21, name="hashdetnet"):
+        HashNet.__init__(self, seed=seed, name=name)
+        self.num_classes = num_classes
+        self.outputs = ["cls_prob", "bbox_pred"]
+
+    def heads(self, rois):
+        rois = np.ascontiguousarray(rois, dtype=np.float32)
+        bits = rois.view(np.uint32).astype(np.uint64)
+        with np.errstate(over="ignore"):
+            key = np.full(rois.shape[0], np.uint64(self.seed) * np.uint64(0x9e3779b97f4a7c15), dtype=np.uint64)
+            for c in range(5):
+                key = self._mix(key ^ (bits[:, c] + np.uint64(0x9e3779b97f4a7c15) * np.uint64(c + 1)))
+            cols = np.arange(5 * self.num_classes, dtype=np.uint64)[None, :]
+            h = self._mix(key[:, None] ^ (cols * np.uint64(0xd6e8feb86659fd93)))
+        u = ((h >> np.uint64(40)).astype(np.float64) / float(1 << 24)).astype(np.float32)
+        cls_prob = u[:, :self.num_classes].copy()
+        bbox_pred = ((u[:, self.num_classes:] - np.float32(0.5)) * np.float32(0.5)).astype(np.float32)
+        return cls_prob, bbox_pred
+
+    def forward(self, blobs=None, **kw):
+        p, d = self.heads(kw["rois"])
+        out = {"cls_prob": p, "bbox_pred": d}
+        for b in (blobs or []):
+            out[b] = kw.get(b, np.zeros((1, 1, 1, 1), np.float32))
+        return out
+
+
 class SyntheticImdb:
     """The slice of lib/datasets/imdb.py:16-201 that detect.test touches: image_index,
     image_path_at, name, num_classes, classes, evaluate_detections, competition_mode."""

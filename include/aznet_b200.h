@@ -211,6 +211,64 @@ int azn_nms(const float *dets, int64_t n, double thresh, int64_t *keep, int32_t 
 int azn_nms_batched(const float *dets, const int32_t *seg_off, int n_seg, double thresh,
                     int64_t *keep, int32_t *keep_count, azn_stream_t stream);
 
+/* The same kernel over padded storage: segment s = rows [seg_off[s], seg_off[s] + seg_len[s]) of dets, both int32
+ * [n_seg] on the device, every length <= max_len <= AZN_NMS_SEG_MAX (a longer segment reports keep_count -1).
+ * This is how the batched detection step runs apply_nms over its [image, class, 100, 5] detections. */
+int azn_nms_segments(const float *dets, const int32_t *seg_off, const int32_t *seg_len, int n_seg, int max_len,
+                     double thresh, int64_t *keep, int32_t *keep_count, azn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The Fast R-CNN detection step, batched over images and classes (BASELINE config #3).
+ * replaces: the host code of _frcnn_forward around the net call (lib/detect/test.py:259-318) and the
+ *           per-class selection of test_net (:549-553, :608-651); the net itself is azn_roi_pool_fwd +
+ *           3 x azn_fc_forward (fc6, fc7, cls_score|bbox_pred with AZN_ACT_SOFTMAX_BBOX), the NMS is
+ *           azn_nms_segments.  All counts stay on the device. */
+typedef struct azn_detect_state {
+    int32_t n_img;
+    int32_t cap_boxes;       /* proposals per image (capacity of boxes / inv / rep / hashes / flags) */
+    int32_t num_classes;     /* C, background class 0 included                                  */
+    int32_t max_per_image;   /* 100 (lib/detect/test.py:553)                                    */
+    int32_t chunk;           /* cfg.SEAR.BATCH_SIZE: the dedup runs per chunk of this many boxes */
+    int32_t ld_head;         /* floats per row of head_out                                      */
+    const int32_t *im_h;     /* [n_img] original image sizes (clip)                             */
+    const int32_t *im_w;
+    const double *im_scale;  /* [n_img]                                                         */
+    double eps;              /* cfg.EPS                                                         */
+    double dedup;            /* cfg.DEDUP_BOXES (<= 0: no dedup)                                */
+    const double *boxes;     /* [n_img, cap_boxes, 4] proposals in image coordinates            */
+    const int32_t *n_boxes;  /* [n_img]                                                         */
+    int32_t *inv;            /* [n_img, cap_boxes] proposal -> unique ROI slot                  */
+    int32_t *rep;            /* [n_img, cap_boxes] unique slot -> representative proposal       */
+    int32_t *n_uniq;         /* [n_img]                                                         */
+    int32_t *img_off;        /* [n_img + 1] row offset of the image in the ROI blob / head_out  */
+    float *rois;             /* [n_img * cap_boxes, 5] packed unique ROIs                       */
+    int32_t *m_total;        /* [1]                                                             */
+    int64_t *hashes;         /* scratch [n_img, cap_boxes]                                      */
+    int32_t *flags;          /* scratch [n_img, cap_boxes]                                      */
+    const float *head_out;   /* [M, ld_head]: cls_prob in columns [0, C), bbox_pred in [C, 5C)  */
+    const float *thresh;     /* [C] running per-class thresholds (strict >), or NULL = -inf     */
+    float *dets;             /* [n_img, C, max_per_image, 5] f32 (x1, y1, x2, y2, score), score-descending */
+    float *top_scores;       /* [n_img, C, max_per_image] the same scores, padded with -inf     */
+    int32_t *det_count;      /* [n_img, C]                                                      */
+} azn_detect_state;
+
+/* proposals -> [batch index, box * im_scale] float32 ROIs, deduplicated per image and per chunk in feature
+ * space exactly like _frcnn_forward (np.round(rois * DEDUP_BOXES) hash, np.unique order), packed densely. */
+int azn_detect_rois(const azn_detect_state *st, azn_stream_t stream);
+/* After the head: for every (image, class j >= 1) the rows with cls_prob > thresh[j], the max_per_image
+ * highest of them in descending score order (ties: lower row first), each decoded with _bbox_pred +
+ * _clip_boxes from its representative's box and rounded to float32 like all_boxes[j][i] (:636). */
+int azn_detect_select(const azn_detect_state *st, azn_stream_t stream);
+/* thresh[j] of test_net after the whole image set: the max_per_set-th highest score among
+ * top_scores[:, j, :det_count] if more than max_per_set were pushed, else -inf (thresh[0] = -inf).
+ * top_scores / det_count may span more images than one azn_detect_select call (concatenate batches; on
+ * several GPUs all-gather them first: every rank then computes identical thresholds). */
+int azn_detect_thresholds(const float *top_scores, const int32_t *det_count, int n_images, int num_classes,
+                          int max_per_image, long long max_per_set, float *thresh, azn_stream_t stream);
+/* Final `score > thresh[j]` filter (:646-651): shrinks det_count in place (rows are score-descending). */
+int azn_detect_filter(const float *top_scores, int32_t *det_count, const float *thresh, int n_images,
+                      int num_classes, int max_per_image, azn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
