@@ -10,6 +10,12 @@ Two execution routes for the adaptive search:
     host, one net.forward per level, while decode/clip, divide_region/_sift_dup and NMS still run in the
     CUDA kernels.
 Neither route has a CPU fallback.
+
+The detection drivers (test_net, test_net_shared) likewise: with aznet_b200.net.Net detectors every image's
+Fast R-CNN step (ROI dedup, pool, fc head, per-class top-100, decode) runs in aznet_b200.detector.DetectEngine
+and stays in HBM; the set-wide thresholds, the final filter and ALL (class, image) NMS problems run once at the
+end on the device (the heap cap of the reference is order-independent, see csrc/detect.cu).  Other nets take the
+reference's host loop.
 """
 from __future__ import annotations
 
@@ -22,6 +28,7 @@ import torch
 
 from .config import cfg, get_output_dir
 from .. import ops
+from ..detector import DetectEngine, DetectionSet
 from ..engine import SearchEngine, im_scale_for, search_depth
 from ..net import Net
 from ..utils import cython_div as div
@@ -323,6 +330,58 @@ def apply_nms(all_boxes, thresh):
     return out
 
 
+# --------------------------------------------------------------------------- device-resident detection
+_DET_ENGINES = {}
+
+
+def _fast_detect_route(net, key='full'):
+    n = net.get(key) if hasattr(net, 'get') else None
+    return isinstance(n, Net) and n.kind == "frcnn" and len(cfg.TEST.SCALES) == 1 and (key == 'fc' or n.backbone is not None)
+
+
+def _det_engine_for(fr_net: Net, im_shape, cap):
+    key = (id(fr_net.head), int(im_shape[0]), int(im_shape[1]), int(cap), tuple(cfg.TEST.SCALES), cfg.TEST.MAX_SIZE,
+           cfg.SEAR.BATCH_SIZE, float(cfg.DEDUP_BOXES), float(cfg.EPS))
+    eng = _DET_ENGINES.get(key)
+    if eng is None:
+        if len(_DET_ENGINES) > 8:
+            _DET_ENGINES.clear()
+        eng = DetectEngine(fr_net.head, 1, im_shape[0], im_shape[1], cap, scales=tuple(cfg.TEST.SCALES),
+                           max_size=cfg.TEST.MAX_SIZE, batch_size=cfg.SEAR.BATCH_SIZE, dedup=float(cfg.DEDUP_BOXES),
+                           eps=float(cfg.EPS), spatial_scale=fr_net.spatial_scale)
+        _DET_ENGINES[key] = eng
+    return eng
+
+
+def _detect_on_device(fr_net: Net, nhwc, im_shape, boxes, dset: DetectionSet, i):
+    """One image's detection step into slot i of the set.  boxes: f64 ndarray [R,4] or (device [1,cap,4], count [1])."""
+    if isinstance(boxes, tuple):
+        boxes_d, count_d = boxes
+    else:
+        R = boxes.shape[0]
+        cap = max(int(cfg.SEAR.NUM_PROPOSALS), (R + 127) // 128 * 128)
+        boxes_d = torch.zeros((1, cap, 4), dtype=torch.float64, device=fr_net.dev)
+        boxes_d[0, :R] = torch.from_numpy(np.ascontiguousarray(boxes[:, :4], dtype=np.float64)).to(fr_net.dev)
+        count_d = torch.tensor([R], dtype=torch.int32, device=fr_net.dev)
+    eng = _det_engine_for(fr_net, im_shape, boxes_d.shape[1])
+    eng.detect(nhwc, boxes_d, count_d, **dset.slot(i, i + 1))
+
+
+def _finish_on_device(dset: DetectionSet, skip, imdb, output_dir):
+    """thresholds + final filter + NMS for the whole set on the device; same files and calls as _finish_detections."""
+    dset.finish(cfg.TEST.NMS)
+    all_boxes = dset.to_host()
+    for j in range(imdb.num_classes):
+        for i in skip:
+            all_boxes[j][i] = []
+    with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
+        pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
+    print('Applying NMS to all detections')
+    nms_dets = dset.to_host(nms=True)
+    print('Evaluating detections')
+    imdb.evaluate_detections(nms_dets, output_dir)
+
+
 # --------------------------------------------------------------------------- dataset drivers
 def test_proposals(net, imdb):
     """Generate proposals on an image database and pickle them (test.py:486-539)."""
@@ -399,12 +458,24 @@ def test_net(net, prop_file, imdb):
         os.makedirs(output_dir)
     _t = {'im_detect': Timer(), 'misc': Timer()}
     skip = set()
+    fast = _fast_detect_route(net)
+    dset = DetectionSet(num_images, imdb.num_classes, max_per_image, net['full'].dev) if fast else None
     for i in range(num_images):
         if prop_boxes[i].shape[0] == 0:
             skip.add(i)
             continue
         im = cv2.imread(imdb.image_path_at(i))
         _t['im_detect'].tic()
+        if fast:
+            data, _ = _get_image_blob(im)
+            _, nhwc = net['full'].conv_from_data(data)
+            _detect_on_device(net['full'], nhwc, im.shape, prop_boxes[i], dset, i)
+            torch.cuda.current_stream().synchronize()
+            num_boxes += prop_boxes[i].shape[0]
+            _t['im_detect'].toc()
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
+                                                                _t['misc'].average_time))
+            continue
         scores, boxes = im_detect(net, im, prop_boxes[i], imdb.num_classes)
         num_boxes += scores.shape[0]
         _t['im_detect'].toc()
@@ -413,7 +484,10 @@ def test_net(net, prop_file, imdb):
         _t['misc'].toc()
         print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
                                                             _t['misc'].average_time))
-    _finish_detections(all_boxes, thresh, skip, imdb, output_dir)
+    if fast:
+        _finish_on_device(dset, skip, imdb, output_dir)
+    else:
+        _finish_detections(all_boxes, thresh, skip, imdb, output_dir)
     print('The average time is proposal {:.3f}s, detection {:.3f}s'.format(prop['time'], _t['im_detect'].average_time))
     print('On average, {0} boxes per image are generated'.format(num_boxes / num_images))
 
@@ -432,9 +506,26 @@ def test_net_shared(sc_net, frcnn_net, imdb):
     if not os.path.exists(output_dir):
         os.makedirs(output_dir)
     _t = {'im_detect': Timer(), 'misc': Timer()}
+    fast = _fast_route(sc_net) and _fast_detect_route(frcnn_net, 'fc')
+    dset = DetectionSet(num_images, imdb.num_classes, max_per_image, sc_net['full'].dev) if fast else None
     for i in range(num_images):
         im = cv2.imread(imdb.image_path_at(i))
         _t['im_detect'].tic()
+        if fast:
+            # proposals never leave the device: the search engine's output buffers are the detector's input
+            full = sc_net['full']
+            eng = _engine_for(full, im.shape, None)
+            data, _ = _get_image_blob(im)
+            _, nhwc = full.conv_from_data(data)
+            eng.propose(nhwc)
+            _detect_on_device(frcnn_net['fc'], nhwc, im.shape, (eng.out_boxes, eng.out_count), dset, i)
+            n_prop, n_eval, depth = int(eng.out_count[0].item()), int(eng.n_eval[0].item()), int(eng.depth[0].item())
+            print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(n_prop, n_eval, depth))
+            num_boxes += n_prop
+            _t['im_detect'].toc()
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
+                                                                _t['misc'].average_time))
+            continue
         scores, boxes = im_detect_shared(sc_net, frcnn_net, im, imdb.num_classes)
         num_boxes += scores.shape[0]
         _t['im_detect'].toc()
@@ -443,6 +534,9 @@ def test_net_shared(sc_net, frcnn_net, imdb):
         _t['misc'].toc()
         print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
                                                             _t['misc'].average_time))
-    _finish_detections(all_boxes, thresh, set(), imdb, output_dir)
+    if fast:
+        _finish_on_device(dset, set(), imdb, output_dir)
+    else:
+        _finish_detections(all_boxes, thresh, set(), imdb, output_dir)
     print('The average detection time is {:.3f}s'.format(_t['im_detect'].average_time))
     print('On average, {0} boxes per image are proposed'.format(num_boxes / num_images))

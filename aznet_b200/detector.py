@@ -118,6 +118,40 @@ class DetectEngine:
         return self.select(**out)
 
 
+class DetectionSet:
+    """Set-wide device buffers of a detection run: every batch's azn_detect_select writes into its slice, the
+    thresholds / filter / NMS run once at the end (`finish`).  On several GPUs every rank holds its shard of the
+    images; `finish` all-gathers the [images, C, 100] score tensor so that every rank computes the same
+    thresholds (the one exchange step of the detection path), then filters and suppresses locally."""
+
+    def __init__(self, num_images, num_classes, max_per_image=100, device=None, total_images=None):
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.N, self.C, self.mpi = int(num_images), int(num_classes), int(max_per_image)
+        self.total_images = int(total_images) if total_images is not None else self.N
+        self.dets = torch.zeros((self.N, self.C, self.mpi, 5), dtype=torch.float32, device=dev)
+        self.top_scores = torch.full((self.N, self.C, self.mpi), float("-inf"), dtype=torch.float32, device=dev)
+        self.det_count = torch.zeros((self.N, self.C), dtype=torch.int32, device=dev)
+        self.thresh = self.keep = self.keep_count = None
+
+    def slot(self, lo, hi):
+        return dict(dets=self.dets[lo:hi], top_scores=self.top_scores[lo:hi], det_count=self.det_count[lo:hi])
+
+    @property
+    def max_per_set(self):
+        return 800 // (self.C - 1) * self.total_images          # Python-2 integer division (test.py:551, SURVEY Q13)
+
+    def finish(self, nms_thresh):
+        from .dist import gather_detection_scores
+        top, cnt = gather_detection_scores(self.top_scores, self.det_count)
+        self.thresh = ops.detect_thresholds(top, cnt, self.max_per_set)
+        _, self.keep, self.keep_count = finish_detections(self.dets, self.top_scores, self.det_count, self.max_per_set,
+                                                          nms_thresh, thresh=self.thresh)
+        return self.thresh, self.keep, self.keep_count
+
+    def to_host(self, nms=False):
+        return detections_to_host(self.dets, self.det_count, self.keep if nms else None, self.keep_count if nms else None)
+
+
 def finish_detections(dets: torch.Tensor, top_scores: torch.Tensor, det_count: torch.Tensor, max_per_set: int,
                       nms_thresh: float, thresh: torch.Tensor | None = None):
     """The end of test_net for a whole image set (lib/detect/test.py:624-651 + apply_nms :467-484), on the device:

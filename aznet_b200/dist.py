@@ -27,3 +27,18 @@ def gather_proposals(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Te
         dist.all_gather_into_tensor(buf, t.contiguous())
         outs.append(buf)
     return tuple(outs)
+
+
+def gather_detection_scores(top_scores: torch.Tensor, det_count: torch.Tensor):
+    """The exchange step of the detection path: test_net's thresh[j] is global over the image set
+    (lib/detect/test.py:624-631) but order-independent, so every rank all-gathers the [imgs, C, 100] f32 score
+    tensor and the [imgs, C] counts of its shard (equal shard sizes) and computes identical thresholds."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return top_scores, det_count
+    world = dist.get_world_size()
+    outs = []
+    for t in (top_scores, det_count):
+        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t.contiguous())
+        outs.append(buf)
+    return tuple(outs)

@@ -203,3 +203,45 @@ def test_drivers_and_pickle_formats(dev, O, cfg, tmp_path, capsys):
             assert (isinstance(a, list) and isinstance(b, list)) or np.array_equal(a, b), (c, i)
     T.test_net_shared(az, fr, imdb)
     assert "The average detection time is" in capsys.readouterr().out
+
+
+def test_test_net_device_route_equals_host_route(dev, cfg, tmp_path, capsys):
+    """test_net / test_net_shared with Net detectors (DetectEngine + set-wide finish on the device) against the
+    reference's host loop over the same Net objects (numpy selection, heap thresholds, per-class NMS calls)."""
+    import cv2
+    from aznet_b200.detect import config as C
+    from aznet_b200.detect import test as T
+    az, fr, _, _ = _small_nets(dev)
+    paths = []
+    for i, im in enumerate(synth.make_images(4, 200, 300, seed=60)):
+        p = str(tmp_path / ("im%d.png" % i))
+        cv2.imwrite(p, im)
+        paths.append(p)
+    C.cfg.ROOT_DIR = str(tmp_path)
+    imdb = synth.SyntheticImdb(paths, num_classes=6)
+    T.test_proposals(az, imdb)
+    prop_file = os.path.join(C.get_output_dir(imdb, az["full"]), "proposals.pkl")
+    det_file = os.path.join(C.get_output_dir(imdb, fr["full"]), "detections.pkl")
+
+    class Foreign(dict):                      # hides the Net type -> forces the host route
+        pass
+    wrap = lambda n: type("W", (), {"forward": n.forward, "blobs": n.blobs, "name": n.name})()
+
+    def run(nets, shared):
+        if shared:
+            T.test_net_shared(az, nets, imdb)
+        else:
+            T.test_net(nets, prop_file, imdb)
+        capsys.readouterr()
+        return pickle.load(open(det_file, "rb")), imdb.evaluated[0]
+
+    for shared in (False, True):
+        pre_d, nms_d = run(fr, shared)
+        pre_h, nms_h = run(Foreign(full=wrap(fr["full"]), fc=wrap(fr["fc"])), shared)
+        for a_set, b_set in ((pre_d, pre_h), (nms_d, nms_h)):
+            for j in range(1, 6):
+                for i in range(4):
+                    a, b = a_set[j][i], b_set[j][i]
+                    assert len(a) == len(b), (shared, j, i, len(a), len(b))
+                    if len(a):
+                        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-4)

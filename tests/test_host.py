@@ -101,6 +101,16 @@ def _gloo_worker(rank, world, port, q):
         scores[j, :counts[j]] = img / 100.0
     b, s, c = azdist.gather_proposals(boxes, scores, counts)
     ok = b.shape == (n_img, P, 4) and all(int(c[i]) == 1 + i % P and float(b[i, 0, 0]) == i for i in range(n_img))
+    # the detection path's exchange step: every rank ends up with the whole set's [imgs, C, mpi] scores / counts
+    Cc, mpi = 4, 3
+    top = torch.full((hi - lo, Cc, mpi), float("-inf"))
+    cnt = torch.zeros((hi - lo, Cc), dtype=torch.int32)
+    for j, img in enumerate(range(lo, hi)):
+        cnt[j, 1:] = 1 + img % mpi
+        top[j, 1:, :int(cnt[j, 1])] = img + 0.5
+    t, c2 = azdist.gather_detection_scores(top, cnt)
+    ok = ok and t.shape == (n_img, Cc, mpi) and all(float(t[i, 1, 0]) == i + 0.5 and int(c2[i, 2]) == 1 + i % mpi
+                                                    for i in range(n_img))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
