@@ -28,7 +28,7 @@ LEVEL_LAST, LEVEL_ROOT_PROPS = 1, 2
 
 EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
-    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals",
+    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter",
@@ -133,6 +133,8 @@ def _bind(L):
     L.azn_search_level.argtypes = [C.POINTER(SearchState), vp, i32, vp, i32, vp, i32, i32, i32, vp]
     L.azn_select_proposals.restype = i32
     L.azn_select_proposals.argtypes = [C.POINTER(SearchState), i32, i32, f64, vp, vp, vp, i32, vp]
+    L.azn_collect_proposals.restype = i32
+    L.azn_collect_proposals.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]
     L.azn_divide_region.restype = i32
     L.azn_divide_region.argtypes = [vp, i32, f64, vp, vp, i32, i32, vp, sz, vp]
     L.azn_divide_region_scratch_bytes.restype = sz

@@ -324,12 +324,26 @@ struct EpiParams {
     int *flags;          // [WS_MAX_SLOTS] "the partial of this slot is complete" (zero between launches)
     unsigned long long *sync;   // grid-barrier ticket counter of the finish phase (monotonic, never reset)
     long long *trace;    // azn_fc_trace: per CTA 8 globaltimer stamps, or NULL
+    // CONV kernels only -- 3x3 / pad 1 / stride 1 convolution as an implicit GEMM over a zero-bordered NHWC map
+    // (see azn_conv3x3_forward): k-blocks per filter tap (Cin / 64), padded width / height, rows per image,
+    // and whether the output map is written without the border (the last layer of the backbone)
+    int cv_kbt, cv_wp, cv_hp, cv_plane, cv_unpad;
 };
+
+// Row of the padded pixel grid -> is it a border pixel, and which output row does it go to.
+__device__ __forceinline__ bool conv_row(const EpiParams &ep, int row, size_t &orow) {
+    const int n = row / ep.cv_plane, pp = row - n * ep.cv_plane;
+    const int y = pp / ep.cv_wp, x = pp - y * ep.cv_wp;
+    const bool border = y == 0 || y == ep.cv_hp - 1 || x == 0 || x == ep.cv_wp - 1;
+    orow = ep.cv_unpad ? ((size_t)n * (ep.cv_hp - 2) + (y - 1)) * (ep.cv_wp - 2) + (x - 1) : (size_t)row;
+    return border;
+}
 enum { TR_START = 0, TR_SETUP = 1, TR_FIRST_FULL = 2, TR_MMA_DONE = 3, TR_ACC_READY = 4, TR_EPI_DONE = 5, TR_END = 6, TR_UNITS = 7 };
 
 // Finish phase of the split schedule with many parts: every part has dumped a raw partial; after a grid-wide
 // barrier (all CTAs are co-resident: one persistent CTA per SM) ALL threads of the grid sum the P partials of
 // every split tile in part order and apply bias + activation.  One thread per (row, 4 columns).
+template <bool CONV>
 __device__ __forceinline__ void finish_phase(const Plan &pl, int N, int block_n, int tile_m, const EpiParams &ep) {
     const int q4 = block_n / 4;                              // float4 columns per tile row
     const size_t slot_f4 = (size_t)tile_m * q4;
@@ -342,6 +356,12 @@ __device__ __forceinline__ void finish_phase(const Plan &pl, int N, int block_n,
         tile_coords(pl, pl.dp_tiles + rem, m_tile, n_tile);
         const int row = m_tile * tile_m + trow, col0 = n_tile * block_n + c4 * 4;
         if (row >= pl.m_live || col0 >= N) continue;
+        size_t orow = (size_t)row;
+        bool border = false;
+        if (CONV) {
+            border = conv_row(ep, row, orow);
+            if (border && ep.cv_unpad) continue;
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 *src = (const float4 *)ep.ws + (size_t)rem * slot_f4 + partial_f4(c4 >> 3, c4 & 7, trow, tile_m);
         const size_t part_stride = (size_t)pl.rem_tiles * slot_f4;
@@ -362,17 +382,17 @@ __device__ __forceinline__ void finish_phase(const Plan &pl, int N, int block_n,
         if (ep.out_dtype == AZN_DTYPE_BF16 && col0 + 4 <= N && (ep.ldo & 3) == 0) {
             float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = apply_act(v[j] + ep.bias[col0 + j], ep.act, col0 + j, ep.act_aux);
+            for (int j = 0; j < 4; ++j) o[j] = border ? 0.f : apply_act(v[j] + ep.bias[col0 + j], ep.act, col0 + j, ep.act_aux);
             __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
-            *reinterpret_cast<uint2 *>((__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0) = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
+            *reinterpret_cast<uint2 *>((__nv_bfloat16 *)ep.out + orow * ep.ldo + col0) = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
             continue;
         }
         for (int j = 0; j < 4; ++j) {
             const int col = col0 + j;
             if (col >= N) break;
-            const float o = apply_act(v[j] + ep.bias[col], ep.act, col, ep.act_aux);
-            if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(o);
-            else ((float *)ep.out)[(size_t)row * ep.ldo + col] = o;
+            const float o = border ? 0.f : apply_act(v[j] + ep.bias[col], ep.act, col, ep.act_aux);
+            if (ep.out_dtype == AZN_DTYPE_BF16) ((__nv_bfloat16 *)ep.out)[orow * ep.ldo + col] = __float2bfloat16_rn(o);
+            else ((float *)ep.out)[orow * ep.ldo + col] = o;
         }
     }
 }
@@ -393,7 +413,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter) {
     __syncthreads();
 }
 
-template <int BLOCK_N, int MH>
+template <int BLOCK_N, int MH, bool CONV>
 __global__ void __launch_bounds__(Cfg<BLOCK_N, MH>::THREADS, 1)
 fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, EpiParams ep) {
@@ -443,9 +463,16 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], halves * C::A_HALF_BYTES + C::B_BYTES);
+                    int a_col = kb * BLOCK_K, a_row = m_tile * TILE_M;
+                    if (CONV) {
+                        // k-block -> (filter tap, channel block): the A box of tap (dy, dx) is the same 128 pixels
+                        // shifted by dy rows and dx columns of the padded grid; rows outside the tensor read as zero
+                        const int tap = kb / ep.cv_kbt, dy = tap / 3;
+                        a_col = (kb - tap * ep.cv_kbt) * BLOCK_K;
+                        a_row += (dy - 1) * ep.cv_wp + (tap - dy * 3 - 1);
+                    }
                     for (int h = 0; h < halves; ++h)
-                        tma_load_2d(smem_a + s * C::A_BYTES + h * C::A_HALF_BYTES, &tmap_a, &full[s], kb * BLOCK_K,
-                                    m_tile * TILE_M + h * HALF_M);
+                        tma_load_2d(smem_a + s * C::A_BYTES + h * C::A_HALF_BYTES, &tmap_a, &full[s], a_col, a_row + h * HALF_M);
                     tma_load_2d(smem_b + s * C::B_BYTES, &tmap_w, &full[s], kb * BLOCK_K, n_tile * BLOCK_N);
                 }
             }
@@ -507,7 +534,13 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (tr && leader && idx == 0) tr[TR_ACC_READY] = global_ns();
             const int row = m_tile * TILE_M + trow;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * C::ACC_COLS + half * BLOCK_N);
-            const bool row_ok = row < pl.m_live;
+            bool row_ok = row < pl.m_live;
+            size_t orow = (size_t)row;
+            bool border = false;
+            if (CONV && row_ok) {
+                border = conv_row(ep, row, orow);
+                if (border && ep.cv_unpad) row_ok = false;
+            }
             const bool half_live = m_tile * TILE_M + half * HALF_M < pl.m_live;    // warp-uniform
             // the final part of a split tile waits for the earlier parts (always scheduled on lower unit ids)
             const int peers = w.kind == WORK_OWNER ? pl.parts - 1 : 0;
@@ -559,8 +592,12 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                     }
                     bias_act32(v, ep.bias, col0, ep.N, ep.act, ep.act_aux);
+                    if (CONV && border) {                    // the zero border of the next layer's input
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
                     if (ep.out_dtype == AZN_DTYPE_BF16) {
-                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + (size_t)row * ep.ldo + col0;
+                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.out + orow * ep.ldo + col0;
                         if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
@@ -577,7 +614,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 if (col0 + j < ep.N) dst[j] = __float2bfloat16_rn(v[j]);
                         }
                     } else {
-                        float *dst = (float *)ep.out + (size_t)row * ep.ldo + col0;
+                        float *dst = (float *)ep.out + orow * ep.ldo + col0;
                         if (col0 + 32 <= ep.N && ((uintptr_t)dst & 15) == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -612,7 +649,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (pl.finish && pl.parts > 1) {                 // uniform over the grid: the plan is a pure function of m_live
         __threadfence();                             // this CTA's partial dumps, before the barrier publishes them
         grid_barrier(ep.sync);
-        finish_phase(pl, N, BLOCK_N, TILE_M, ep);
+        finish_phase<CONV>(pl, N, BLOCK_N, TILE_M, ep);
     }
     if (tr && threadIdx.x == 0) tr[TR_END] = global_ns();
 }
@@ -701,16 +738,16 @@ void pick_tile(int N, int &bn, int &mh) {
     if (bn == 64) mh = 1;
 }
 
-template <int BLOCK_N, int MH>
+template <int BLOCK_N, int MH, bool CONV = false>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_live, int M_cap, int N, int K,
                 const EpiParams &ep, int grid, cudaStream_t s) {
     using C = Cfg<BLOCK_N, MH>;
     static bool attr = false;
     if (!attr) {
-        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N, MH, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
-    AZN_CUDA(azn_launch_pdl(fc_gemm_kernel<BLOCK_N, MH>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep));
+    AZN_CUDA(azn_launch_pdl(fc_gemm_kernel<BLOCK_N, MH, CONV>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep));
     return AZN_OK;
 }
 
@@ -769,6 +806,7 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     ep.flags = (int *)((char *)workspace + WS_DATA_BYTES);
     ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
     ep.trace = g_trace;
+    ep.cv_kbt = ep.cv_wp = ep.cv_hp = ep.cv_plane = ep.cv_unpad = 0;
     if (bn == 256 && mh == 2) rc = launch_gemm<256, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 256) rc = launch_gemm<256, 1>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 128 && mh == 2) rc = launch_gemm<128, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
@@ -780,4 +818,58 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
         AZN_LAUNCH_CHECK();
     }
     return AZN_OK;
+}
+
+// 3x3 / pad 1 / stride 1 convolution + bias + ReLU on the tensor cores, as an implicit GEMM.
+// replaces: ConvolutionLayer::Forward (caffe-fast-rcnn/src/caffe/layers/conv_layer.cpp: im2col + sgemm per image,
+// base_conv_layer.cpp forward_cpu_gemm / forward_cpu_bias) followed by the in-place ReLU layers of
+// models/Pascal/VGG16/az-net/test.prototxt:16-384.
+//
+// Layout trick: every map lives in HBM as a ZERO-BORDERED channels-last grid [n_img, H+2, W+2, C] bf16.  Seen as a
+// row-major matrix [P = n_img*(H+2)*(W+2), C], the input of filter tap (dy, dx) for output pixel p is simply row
+// p + dy*(W+2) + dx -- the zero border supplies the padding and keeps a shifted row from wrapping into the
+// neighbouring image row.  So the convolution is the fc GEMM  Y[P, Cout] = sum_tap X[P + shift(tap), Cin] . W_tap^T
+// with a K loop over 9 taps x Cin/64 channel blocks, fed by the same TMA boxes (the A box just starts `shift` rows
+// further; rows before 0 / past P are zero-filled by TMA) into the same tcgen05 pipeline.  Border rows of the
+// output are computed like any other and then stored as zeros (they are the next layer's padding): (H+2)(W+2)/(HW)
+// of the minimum work, 1.03x at 240x400, 1.11x at 30x50.
+extern "C" int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
+                                   int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
+                                   azn_stream_t stream) {
+    AZN_REQUIRE(X && Wt && bias && Y, "azn_conv3x3_forward: null pointer");
+    AZN_REQUIRE(n_img > 0 && H > 0 && W > 0, "azn_conv3x3_forward: bad shape n=%d H=%d W=%d", n_img, H, W);
+    AZN_REQUIRE(Cin > 0 && Cin % BLOCK_K == 0, "azn_conv3x3_forward: Cin=%d must be a multiple of %d (pad the channels)", Cin, BLOCK_K);
+    AZN_REQUIRE(Cout > 0 && Cout % 8 == 0, "azn_conv3x3_forward: Cout=%d must be a multiple of 8", Cout);
+    AZN_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Y % 16 == 0), "azn_conv3x3_forward: pointers must be 16-byte aligned");
+    const long long P = (long long)n_img * (H + 2) * (W + 2);
+    AZN_REQUIRE(P < (1ll << 31) - 4096, "azn_conv3x3_forward: %lld padded pixels exceed the 32-bit row index", P);
+    const size_t need = WS_DATA_BYTES + 8192;
+    if (!workspace || workspace_bytes < need) {
+        azn_set_error("azn_conv3x3_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+        return AZN_ERR_CAPACITY;
+    }
+    const int K = 9 * Cin;
+    const int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+    CUtensorMap ta, tw;
+    int rc = make_tmap(X, (int)P, Cin, HALF_M, &ta);
+    if (rc) return rc;
+    rc = make_tmap(Wt, Cout, K, bn, &tw);
+    if (rc) return rc;
+    EpiParams ep;
+    ep.bias = bias; ep.out = Y; ep.out_dtype = AZN_DTYPE_BF16; ep.ldo = Cout; ep.N = Cout;
+    ep.act = relu ? AZN_ACT_RELU : AZN_ACT_NONE;
+    ep.act_aux = 0;
+    ep.force_parts = g_force_parts;
+    ep.force_finish = g_force_finish;
+    ep.ws = (float *)workspace;
+    ep.flags = (int *)((char *)workspace + WS_DATA_BYTES);
+    ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
+    ep.trace = nullptr;
+    ep.cv_kbt = Cin / BLOCK_K; ep.cv_wp = W + 2; ep.cv_hp = H + 2; ep.cv_plane = (H + 2) * (W + 2); ep.cv_unpad = out_unpadded ? 1 : 0;
+    const int grid = azn_num_sms();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (bn == 256) rc = launch_gemm<256, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
+    else if (bn == 128) rc = launch_gemm<128, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
+    else rc = launch_gemm<64, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
+    return rc;
 }

@@ -545,6 +545,48 @@ extern "C" int azn_select_proposals(const azn_search_state *st, int mode, int nu
     return AZN_OK;
 }
 
+// ---- proposal lists of a run of batches, collected on the device ---------------------------------
+// test_proposals appends every image's list and writes proposals.pkl once (lib/detect/test.py:508-539).  Here
+// the final lists of batch `step` are copied into slot step % n_slots of a per-rank collection that is
+// gathered once at the end of the job.  The step counter lives on the device (state[0]) so that the launch is
+// identical every step and replays from a CUDA graph; the CTA that finishes last (ticket in state[1]) bumps it
+// -- every CTA has read it by then.
+__global__ void __launch_bounds__(256)
+collect_kernel(const uint32_t *__restrict__ boxes, const uint32_t *__restrict__ scores, const uint32_t *__restrict__ counts,
+               uint32_t *__restrict__ dst_boxes, uint32_t *__restrict__ dst_scores, uint32_t *__restrict__ dst_counts,
+               long nb, long ns, long nc, int n_slots, unsigned *__restrict__ state) {
+    pdl_enter();
+    const unsigned step = *(volatile unsigned *)state;
+    const size_t slot = step % (unsigned)n_slots;
+    const long total = nb + ns + nc;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        if (i < nb) dst_boxes[slot * nb + i] = boxes[i];
+        else if (i < nb + ns) dst_scores[slot * ns + (i - nb)] = scores[i - nb];
+        else dst_counts[slot * nc + (i - nb - ns)] = counts[i - nb - ns];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&state[1], 1u) == gridDim.x - 1) {
+            state[1] = 0u;
+            state[0] = step + 1u;
+        }
+    }
+}
+
+extern "C" int azn_collect_proposals(const double *boxes, const float *scores, const int32_t *counts, int n_img, int cap_out,
+                                     double *dst_boxes, float *dst_scores, int32_t *dst_counts, int n_slots,
+                                     uint32_t *state, azn_stream_t stream) {
+    AZN_REQUIRE(boxes && scores && counts && dst_boxes && dst_scores && dst_counts && state, "azn_collect_proposals: null pointer");
+    AZN_REQUIRE(n_img > 0 && cap_out > 0 && n_slots > 0, "azn_collect_proposals: bad shape");
+    const long nb = (long)n_img * cap_out * 8, ns = (long)n_img * cap_out, nc = n_img;      // 32-bit words
+    const int grid = (int)((nb + ns + nc + 256 * 8 - 1) / (256 * 8));
+    AZN_CUDA(azn_launch_pdl(collect_kernel, dim3(grid < 1 ? 1 : (grid > 592 ? 592 : grid)), dim3(256), 0, (cudaStream_t)stream,
+                            (const uint32_t *)boxes, (const uint32_t *)scores, (const uint32_t *)counts, (uint32_t *)dst_boxes,
+                            (uint32_t *)dst_scores, (uint32_t *)dst_counts, nb, ns, nc, n_slots, state));
+    return AZN_OK;
+}
+
 extern "C" size_t azn_divide_region_scratch_bytes(int n) {
     // children of n regions: 3*num_long-1 each; num_long is unbounded for degenerate aspect ratios, so the
     // scratch is sized for 16 children per region (num_long <= 5) with a floor, and overflow is reported.

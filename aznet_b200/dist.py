@@ -29,6 +29,63 @@ def gather_proposals(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Te
     return tuple(outs)
 
 
+class ProposalCollector:
+    """Per-rank accumulation of the proposal lists of a run of batches, gathered ONCE at the end -- the way
+    test_proposals appends per image and writes one proposals.pkl after the loop (lib/detect/test.py:508-539).
+    `add(i, ...)` is three small device-to-device copies on the current stream (no collective per batch);
+    `gather()` is the job's only exchange: one all_gather per tensor, image order = (rank, batch, image) for a
+    contiguous block partition of the batches."""
+
+    def __init__(self, n_batches: int, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
+        self.n_batches = nb = int(n_batches)
+        # one byte buffer [all boxes slots | all scores slots | all counts slots]: the gather is ONE collective
+        sizes = [nb * t.numel() * t.element_size() for t in (boxes, scores, counts)]
+        self._buf = torch.zeros(sum(sizes), dtype=torch.uint8, device=boxes.device)
+        views, off = [], 0
+        for t, sz in zip((boxes, scores, counts), sizes):
+            views.append(self._buf[off:off + sz].view(t.dtype).view((nb,) + tuple(t.shape)))
+            off += sz
+        self.boxes, self.scores, self.counts = views
+        self._sizes = sizes
+        self._gathered = None
+        self.state = torch.zeros(2, dtype=torch.int32, device=boxes.device)      # device-side batch counter
+
+    def reset(self):
+        self.state.zero_()
+
+    def device_add(self, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
+        """One kernel launch (azn_collect_proposals) whose slot comes from the device-side counter: the launch is
+        the same every batch, so it is captured into the CUDA graph of the search."""
+        from . import _lib as L
+        n_img, cap = int(boxes.shape[0]), int(boxes.shape[1])
+        L.check(L.lib().azn_collect_proposals(boxes.data_ptr(), scores.data_ptr(), counts.data_ptr(), n_img, cap,
+                                              self.boxes.data_ptr(), self.scores.data_ptr(), self.counts.data_ptr(),
+                                              self.n_batches, self.state.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "azn_collect_proposals")
+
+    def add(self, i: int, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
+        j = i % self.n_batches
+        self.boxes[j].copy_(boxes, non_blocking=True)
+        self.scores[j].copy_(scores, non_blocking=True)
+        self.counts[j].copy_(counts, non_blocking=True)
+
+    def gather(self):
+        """-> (boxes [world*n_batches*imgs, P, 4], scores [.., P], counts [..]) on every rank."""
+        flat = lambda t: t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return flat(self.boxes), flat(self.scores), flat(self.counts)
+        world = dist.get_world_size()
+        if self._gathered is None:
+            self._gathered = torch.empty((world, self._buf.numel()), dtype=torch.uint8, device=self._buf.device)
+        dist.all_gather_into_tensor(self._gathered.view(-1), self._buf)
+        outs, off = [], 0
+        for t, sz in zip((self.boxes, self.scores, self.counts), self._sizes):
+            g = self._gathered[:, off:off + sz].contiguous().view(t.dtype)
+            outs.append(g.view((world * t.shape[0] * t.shape[1],) + tuple(t.shape[2:])))
+            off += sz
+        return tuple(outs)
+
+
 def gather_detection_scores(top_scores: torch.Tensor, det_count: torch.Tensor):
     """The exchange step of the detection path: test_net's thresh[j] is global over the image set
     (lib/detect/test.py:624-631) but order-independent, so every rank all-gathers the [imgs, C, 100] f32 score

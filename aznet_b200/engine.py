@@ -133,6 +133,7 @@ class SearchEngine:
         self.h6 = torch.empty((m_cap, head.h6), dtype=torch.bfloat16, device=dev)
         self.h7 = torch.empty((m_cap, head.h71 + head.h72), dtype=torch.bfloat16, device=dev)
         self.heads = torch.zeros((m_cap, head.ld_head), dtype=torch.float32, device=dev)
+        self.collector = None                # dist.ProposalCollector: the final lists are also copied into its next slot
         self._st = L.SearchState()
         self._cur = 0
         self.launches = 0
@@ -270,6 +271,9 @@ class SearchEngine:
                                              self.out_boxes.data_ptr(), self.out_scores.data_ptr(),
                                              self.out_count.data_ptr(), self.cap_out, ops._stream()), "azn_select_proposals")
         self.launches += 1
+        if self.collector is not None:
+            self.collector.device_add(self.out_boxes, self.out_scores, self.out_count)
+            self.launches += 1
 
     def propose(self, conv_nhwc: torch.Tensor):
         """Run the whole search on resident NHWC bf16 maps [n_img, H, W, C].  Asynchronous; results are

@@ -182,6 +182,16 @@ int azn_select_proposals(const azn_search_state *st, int mode, int num_proposals
                          double *out_boxes, float *out_scores, int32_t *out_count, int cap_out,
                          azn_stream_t stream);
 
+/* Collection of the final proposal lists of a run of batches on the device.
+ * replaces: the `all_boxes[i] = ...` append of test_proposals (lib/detect/test.py:508-513); proposals.pkl is
+ * written once after the loop (:533-539), so a multi-GPU job gathers the collection ONCE at the end.
+ *   copies out_boxes f64 [n_img, cap_out, 4] / out_scores f32 [n_img, cap_out] / out_count i32 [n_img] into
+ *   slot (state[0] % n_slots) of dst_* ([n_slots, ...] each) and increments state[0]; `state` = 2 uint32 words,
+ *   zero-initialised by the caller (word 1 is scratch).  Same launch every step: replays from a CUDA graph. */
+int azn_collect_proposals(const double *out_boxes, const float *out_scores, const int32_t *out_count, int n_img,
+                          int cap_out, double *dst_boxes, float *dst_scores, int32_t *dst_counts, int n_slots,
+                          uint32_t *state, azn_stream_t stream);
+
 /* Stand-alone pieces of the level kernel, exposed with the reference's own signatures.
  * azn_divide_region replaces utils.cython_div.divide_region / _sift_dup for ONE region set
  * (lib/utils/div.pyx:15-88): regions f64 [n,4] -> out f64 [cap_out,4], out_count[1]. */

@@ -176,3 +176,34 @@ def test_engine_real_heads_vs_oracle(dev, O):
         m = iou(Y, boxes[i])
         assert (m.max(1) >= 0.9).mean() >= 0.95, (m.max(1) >= 0.9).mean()
         assert (m.max(0) >= 0.9).mean() >= 0.95
+
+
+def test_collector_slots_follow_the_device_counter(dev):
+    """azn_collect_proposals: the final lists of batch k land in slot k % n_slots of the per-rank collection, the
+    slot index comes from the device-side counter (same launch every step, also under CUDA-graph replay)."""
+    from aznet_b200 import engine, ops
+    from aznet_b200.dist import ProposalCollector
+    C, H, W, n_img = 64, 200, 320, 3
+    w = synth.make_az_weights(seed=3, C=C, h6=256, h71=64, h72=64, zoom_bias=0.2)
+    head = engine.AZHeadWeights(w, dev)
+    eng = engine.SearchEngine(head, n_img, H, W, num_proposals=50, tz=0.5)
+    fh, fw = synth.conv_shape(H, W, eng.scale)
+    maps = [ops.nchw_to_nhwc_bf16(torch.from_numpy(synth.make_conv_maps(n_img, C, fh, fw, seed=7 + k)).to(dev)) for k in range(2)]
+    want = []
+    for k in range(2):
+        eng.propose(maps[k])
+        torch.cuda.synchronize()
+        want.append((eng.out_boxes.clone(), eng.out_scores.clone(), eng.out_count.clone()))
+    col = ProposalCollector(3, eng.out_boxes, eng.out_scores, eng.out_count)
+    eng.collector = col
+    graphs = [eng.capture(m)[0] for m in maps]          # capture runs warm-up passes: the counter has moved
+    col.reset()
+    for k in (0, 1, 1, 0):                               # batches 0..3 -> slots 0, 1, 2, 0
+        graphs[k].replay()
+    torch.cuda.synchronize()
+    assert int(col.state[0].item()) == 4 and int(col.state[1].item()) == 0
+    for slot, k in ((0, 0), (1, 1), (2, 1)):
+        assert torch.equal(col.boxes[slot], want[k][0]) and torch.equal(col.scores[slot], want[k][1])
+        assert torch.equal(col.counts[slot], want[k][2])
+    gb, gs, gc = col.gather()                            # single process: the flattened collection itself
+    assert gb.shape[0] == 3 * n_img and torch.equal(gc[:n_img], want[0][2])

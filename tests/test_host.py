@@ -101,6 +101,17 @@ def _gloo_worker(rank, world, port, q):
         scores[j, :counts[j]] = img / 100.0
     b, s, c = azdist.gather_proposals(boxes, scores, counts)
     ok = b.shape == (n_img, P, 4) and all(int(c[i]) == 1 + i % P and float(b[i, 0, 0]) == i for i in range(n_img))
+    # a run of batches collected per rank and gathered once at the end (bench.py, N > 1)
+    col = azdist.ProposalCollector(2, boxes, scores, counts)
+    col.add(0, boxes, scores, counts)
+    col.add(1, boxes + 1000.0, scores, counts)
+    gb, gs, gc = col.gather()
+    per = hi - lo
+    ok = ok and gb.shape == (world * 2 * per, P, 4)
+    for r in range(world):
+        first = azdist.shard_images(n_img, r, world)[0]
+        ok = ok and float(gb[(r * 2 + 0) * per, 0, 0]) == first and float(gb[(r * 2 + 1) * per, 0, 0]) == first + 1000.0
+        ok = ok and int(gc[(r * 2 + 1) * per]) == 1 + first % P
     # the detection path's exchange step: every rank ends up with the whole set's [imgs, C, mpi] scores / counts
     Cc, mpi = 4, 3
     top = torch.full((hi - lo, Cc, mpi), float("-inf"))
