@@ -32,6 +32,7 @@ EXPORTS = [
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter",
+    "azn_image_blob", "azn_conv3x3_forward", "azn_maxpool2x2_forward", "azn_nhwc_border",
 ]
 
 
@@ -157,6 +158,14 @@ def _bind(L):
     L.azn_detect_thresholds.argtypes = [vp, vp, i32, i32, i32, C.c_longlong, vp, vp]
     L.azn_detect_filter.restype = i32
     L.azn_detect_filter.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.azn_image_blob.restype = i32
+    L.azn_image_blob.argtypes = [vp, i32, i32, i32, f64, vp, vp, i32, i32, i32, vp, vp]
+    L.azn_conv3x3_forward.restype = i32
+    L.azn_conv3x3_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]
+    L.azn_maxpool2x2_forward.restype = i32
+    L.azn_maxpool2x2_forward.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.azn_nhwc_border.restype = i32
+    L.azn_nhwc_border.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp]
     return L
 
 

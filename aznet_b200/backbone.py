@@ -1,14 +1,24 @@
-"""VGG16 conv1_1 .. conv5_3 (models/Pascal/VGG16/az-net/test.prototxt:16-384) producing the shared
-conv5_3 map.  This is NOT part of the hand-written hot path ("next" row): it runs once per
-image before the search and is served by PyTorch/cuDNN as plumbing so that the from-image entry points
-(`im_propose(net, im)`) are usable.  Pooling is ceil-mode like Caffe (pooling_layer.cpp:93-95)."""
+"""VGG16 conv1_1 .. conv5_3 (models/Pascal/VGG16/az-net/test.prototxt:16-384) producing the shared conv5_3
+map -- SURVEY 8f-1, the first "next" row after the search path itself.
+
+`VGG16Native` is the product: image blob (azn_image_blob), thirteen 3x3 convolutions as implicit GEMMs on the
+tcgen05 tensor cores (azn_conv3x3_forward: the fc GEMM kernel fed with row-shifted TMA boxes over zero-bordered
+channels-last maps) and four ceil-mode 2x2 max pools (azn_maxpool2x2_forward), all through the C ABI.  Pooling is
+ceil-mode like Caffe (pooling_layer.cpp:93-95): 600x1000 -> 38x63.
+
+`VGG16Torch` is the same network through PyTorch/cuDNN.  It is a LIBRARY reference for tests and for the
+"vs cuDNN" line of tools/backbone_bench.py only; nothing in the product path constructs it.
+"""
 from __future__ import annotations
 
 import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import ops
+
 VGG16_CFG = [(64, 2), (128, 2), (256, 3), (512, 3), (512, 3)]      # (channels, convs) per stage
+PIXEL_MEANS = (102.9801, 115.9465, 122.7717)                        # lib/detect/config.py:210 (BGR)
 
 
 def make_vgg16_weights(seed=5, in_ch=3, width_div=1):
@@ -26,7 +36,82 @@ def make_vgg16_weights(seed=5, in_ch=3, width_div=1):
     return w
 
 
-class VGG16Backbone:
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+class VGG16Native:
+    """The backbone on hand-written sm_100a kernels.  Channel counts that are not multiples of 64 (reduced test
+    networks, the 3 input channels) are zero-padded in the packed weights: a padded output channel has zero
+    weights and zero bias, so it stays exactly 0 through ReLU and pooling."""
+
+    def __init__(self, weights: dict, device, pixel_means=PIXEL_MEANS):
+        self.dev = torch.device(device)
+        self.pixel_means = tuple(float(m) for m in pixel_means)
+        self.layers, self.dims = [], []
+        c_in = None
+        for s, (_, n) in enumerate(VGG16_CFG, 1):
+            for i in range(1, n + 1):
+                W, b = weights["conv%d_%d" % (s, i)]
+                W = torch.from_numpy(np.ascontiguousarray(W)).to(self.dev)
+                co, ci = W.shape[0], W.shape[1]
+                self.dims.append((ci, co, i == n and s < 5))
+                if c_in is None:
+                    self.in_channels = ci
+                cop, cip = _pad64(co), _pad64(ci)
+                Wp = torch.zeros((cop, ci, 3, 3), dtype=torch.float32, device=self.dev)
+                Wp[:co] = W
+                bp = torch.zeros((cop,), dtype=torch.float32, device=self.dev)
+                bp[:co] = torch.from_numpy(np.ascontiguousarray(b)).to(self.dev)
+                self.layers.append((ops.pack_conv_weight(Wp, cip), bp, i == n and s < 5))
+                c_in = co
+        self.out_channels = c_in
+        self.cpad_in = _pad64(self.in_channels)
+        self.launches_per_call = 1 + len(self.layers) + sum(1 for l in self.layers if l[2])
+
+    def flops(self, hs: int, ws: int) -> float:
+        """Algorithmic FLOPs of conv1_1 .. conv5_3 for one hs x ws network input (real channel counts)."""
+        total, h, w = 0.0, hs, ws
+        for ci, co, pool in self.dims:
+            total += 2.0 * 9 * ci * co * h * w
+            if pool:
+                h, w = (h + 1) // 2, (w + 1) // 2
+        return total
+
+    @torch.no_grad()
+    def run_padded(self, x: torch.Tensor) -> torch.Tensor:
+        """x bf16 [n, Hs+2, Ws+2, cpad_in] zero-bordered -> conv5_3 bf16 NHWC [n, fh, fw, C] (post-ReLU)."""
+        last = len(self.layers) - 1
+        for k, (wt, b, pool) in enumerate(self.layers):
+            x = ops.conv3x3(x, wt, b, relu=True, unpadded=(k == last))
+            if pool:
+                x = ops.maxpool2x2(x)
+        if x.shape[3] != self.out_channels:
+            x = x[..., :self.out_channels].contiguous()
+        return x
+
+    @torch.no_grad()
+    def from_images(self, images: torch.Tensor, im_scale: float) -> torch.Tensor:
+        """uint8 [n, H0, W0, 3] BGR images (device) -> conv5_3 bf16 NHWC, everything on the device."""
+        return self.run_padded(ops.image_blob(images, im_scale, self.pixel_means, self.cpad_in))
+
+    @torch.no_grad()
+    def nhwc_from_data(self, data: torch.Tensor) -> torch.Tensor:
+        """Caffe's 'data' blob f32 NCHW [n, 3, H, W] (device) -> conv5_3 bf16 NHWC."""
+        n, c, h, w = data.shape
+        x = torch.zeros((n, h + 2, w + 2, self.cpad_in), dtype=torch.bfloat16, device=data.device)
+        x[:, 1:h + 1, 1:w + 1, :c] = data.permute(0, 2, 3, 1)
+        return self.run_padded(x)
+
+    @torch.no_grad()
+    def __call__(self, data: torch.Tensor) -> torch.Tensor:
+        """The blob-level protocol of Net: 'data' f32 NCHW -> conv5_3 f32 NCHW (both on the device)."""
+        return self.nhwc_from_data(data).permute(0, 3, 1, 2).float().contiguous()
+
+
+class VGG16Torch:
+    """Library reference (PyTorch/cuDNN, bf16 channels-last) -- tests and the cuDNN comparison only."""
+
     def __init__(self, weights: dict, device, dtype=torch.bfloat16):
         self.dev, self.dtype = device, dtype
         self.layers = []
@@ -46,3 +131,6 @@ class VGG16Backbone:
             if pool:
                 x = F.max_pool2d(x, 2, 2, ceil_mode=True)
         return x.float().contiguous()
+
+
+VGG16Backbone = VGG16Native

@@ -1,0 +1,159 @@
+// The memory-bound pieces of the conv5_3 backbone: image -> network-input blob, and the 2x2 max
+// pooling between the conv stages.  The convolutions themselves are azn_conv3x3_forward (gemm.cu).
+//
+// Every activation map is a ZERO-BORDERED channels-last grid [n_img, H+2, W+2, C] bf16 (see gemm.cu): each
+// kernel here writes the border of its output itself, so buffers can be reused across layers without memsets.
+#include <float.h>
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void st16(void *p, const uint4 &v) { *reinterpret_cast<uint4 *>(p) = v; }
+
+// ---- _get_image_blob + im_list_to_blob (lib/detect/test.py:27-59, lib/utils/blob.py:13-29) -------------------
+//   im_orig = im.astype(float32) - PIXEL_MEANS     (numpy evaluates the in-place subtract in float64, stores f32)
+//   cv2.resize(im_orig, fx = fy = im_scale, INTER_LINEAR)
+// cv::resize, float source, INTER_LINEAR (OpenCV modules/imgproc/src/resize.cpp, 4.x):
+//   scale = 1 / f (double);  for every destination index d:  s = (d + 0.5) * scale - 0.5 (double),
+//   i = floor(s), a = (float)(s - i);  x: i < 0 -> (0, a = 0), i >= W-1 -> (W-1, a = 0);  y: rows i and i+1 clamped;
+//   horizontal pass  t = S[i] * (1 - a) + S[i+1] * a  (float), vertical pass  d = t0 * (1 - b) + t1 * b  (float).
+// One thread group of 8 lanes per destination pixel of the padded grid: lane 0 computes the three channels, all
+// 8 lanes store one 16-byte piece of the pixel's Cpad-channel row (channels >= 3 are zero).
+__global__ void __launch_bounds__(256)
+image_blob_kernel(const uint8_t *__restrict__ im, int n_img, int H0, int W0, int Hs, int Ws, double scale_x, double scale_y,
+                  double m0, double m1, double m2, __nv_bfloat16 *__restrict__ out, int Cpad, float *__restrict__ blob_f32) {
+    const int vec_per_px = Cpad / 8;
+    const long total = (long)n_img * (Hs + 2) * (Ws + 2) * vec_per_px;
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        const int part = (int)(g % vec_per_px);
+        const long px = g / vec_per_px;
+        const int xp = (int)(px % (Ws + 2));
+        const int yp = (int)((px / (Ws + 2)) % (Hs + 2));
+        const int n = (int)(px / ((long)(Ws + 2) * (Hs + 2)));
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        const bool interior = xp >= 1 && xp <= Ws && yp >= 1 && yp <= Hs;
+        if (part == 0 && interior) {
+            const int dx = xp - 1, dy = yp - 1;
+            const double xd = ((double)dx + 0.5) * scale_x - 0.5, yd = ((double)dy + 0.5) * scale_y - 0.5;
+            int sx = (int)floor(xd);
+            float fx = (float)(xd - (double)sx);        // the fraction is taken in double, then rounded (pinned against cv2 4.13)
+            if (sx < 0) { fx = 0.f; sx = 0; }
+            if (sx >= W0 - 1) { fx = 0.f; sx = W0 - 1; }
+            const int sy = (int)floor(yd);
+            const float fy = (float)(yd - (double)sy);
+            const int y0 = min(max(sy, 0), H0 - 1), y1 = min(max(sy + 1, 0), H0 - 1);
+            const int x1 = min(sx + 1, W0 - 1);
+            const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
+            const uint8_t *r0 = im + ((size_t)n * H0 + y0) * W0 * 3, *r1 = im + ((size_t)n * H0 + y1) * W0 * 3;
+            const double mean[3] = {m0, m1, m2};
+            float res[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float p00 = (float)((double)r0[sx * 3 + c] - mean[c]), p01 = (float)((double)r0[x1 * 3 + c] - mean[c]);
+                const float p10 = (float)((double)r1[sx * 3 + c] - mean[c]), p11 = (float)((double)r1[x1 * 3 + c] - mean[c]);
+                const float t0 = __fadd_rn(__fmul_rn(p00, a0), __fmul_rn(p01, a1));
+                const float t1 = __fadd_rn(__fmul_rn(p10, a0), __fmul_rn(p11, a1));
+                res[c] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, b1));
+                if (blob_f32) blob_f32[(((size_t)n * 3 + c) * Hs + dy) * Ws + dx] = res[c];      // Caffe's 'data' blob, NCHW
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(res[0], res[1]);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(res[2], 0.f);
+            v.x = *reinterpret_cast<const uint32_t *>(&lo);
+            v.y = *reinterpret_cast<const uint32_t *>(&hi);
+        }
+        st16(out + (size_t)px * Cpad + part * 8, v);
+    }
+}
+
+// ---- PoolingLayer MAX 2x2 stride 2 (caffe-fast-rcnn/src/caffe/layers/pooling_layer.cpp:81-95,144-168) --------
+// pooled size = ceil((H - 2) / 2) + 1 (ceil mode), windows clipped to the map, strict `>` scan from -FLT_MAX.
+// One thread per output pixel (of the padded grid) and 16-byte channel vector.
+__device__ __forceinline__ unsigned pick_bf16x2(unsigned v, unsigned b) {
+    const unsigned m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&v), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+    return (v & m) | (b & ~m);
+}
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const uint4 *__restrict__ in, int n_img, int H, int W, int L, uint4 *__restrict__ out, int Ho, int Wo) {
+    const long total = (long)n_img * (Ho + 2) * (Wo + 2) * L;
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(g % L);
+        const long px = g / L;
+        const int xp = (int)(px % (Wo + 2));
+        const int yp = (int)((px / (Wo + 2)) % (Ho + 2));
+        const int n = (int)(px / ((long)(Wo + 2) * (Ho + 2)));
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        if (xp >= 1 && xp <= Wo && yp >= 1 && yp <= Ho) {
+            const int hs = (yp - 1) * 2, ws = (xp - 1) * 2;
+            const int he = min(hs + 2, H), we = min(ws + 2, W);
+            acc = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);       // bf16(-FLT_MAX) = -inf
+            for (int h = hs; h < he; ++h)
+                for (int w = ws; w < we; ++w) {
+                    const uint4 q = __ldg(in + (((size_t)n * (H + 2) + h + 1) * (W + 2) + w + 1) * L + v);
+                    acc.x = pick_bf16x2(q.x, acc.x); acc.y = pick_bf16x2(q.y, acc.y);
+                    acc.z = pick_bf16x2(q.z, acc.z); acc.w = pick_bf16x2(q.w, acc.w);
+                }
+        }
+        out[(size_t)px * L + v] = acc;
+    }
+}
+
+// Unpadded NHWC bf16 [n, H, W, C] <-> zero-bordered grid (tests, and maps that arrive from elsewhere).
+__global__ void __launch_bounds__(256)
+pad_border_kernel(const uint4 *__restrict__ in, int n_img, int H, int W, int L, uint4 *__restrict__ out, int to_padded) {
+    const long total = (long)n_img * (H + 2) * (W + 2) * L;
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(g % L);
+        const long px = g / L;
+        const int xp = (int)(px % (W + 2));
+        const int yp = (int)((px / (W + 2)) % (H + 2));
+        const int n = (int)(px / ((long)(W + 2) * (H + 2)));
+        const bool interior = xp >= 1 && xp <= W && yp >= 1 && yp <= H;
+        const size_t flat = (((size_t)n * H + (yp - 1)) * W + (xp - 1)) * L + v;
+        if (to_padded) out[(size_t)px * L + v] = interior ? __ldg(in + flat) : make_uint4(0u, 0u, 0u, 0u);
+        else if (interior) out[flat] = __ldg(in + (size_t)px * L + v);
+    }
+}
+
+int grid_for(long total) {
+    const long blocks = (total + 255) / 256;
+    const long cap = (long)azn_num_sms() * 16;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+extern "C" int azn_image_blob(const uint8_t *images, int n_img, int H0, int W0, double im_scale, const double *pixel_means,
+                              void *out_padded_nhwc, int Cpad, int Hs, int Ws, float *blob_f32, azn_stream_t stream) {
+    AZN_REQUIRE(images && out_padded_nhwc && pixel_means, "azn_image_blob: null pointer");
+    AZN_REQUIRE(n_img > 0 && H0 > 0 && W0 > 0 && Hs > 0 && Ws > 0 && im_scale > 0, "azn_image_blob: bad shape");
+    AZN_REQUIRE(Cpad >= 8 && Cpad % 8 == 0, "azn_image_blob: Cpad=%d must be a multiple of 8 (>= 8)", Cpad);
+    const long total = (long)n_img * (Hs + 2) * (Ws + 2) * (Cpad / 8);
+    const double sc = 1.0 / im_scale;                     // cv::resize: scale_x = 1. / inv_scale_x with inv_scale_x = fx
+    image_blob_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(images, n_img, H0, W0, Hs, Ws, sc, sc, pixel_means[0],
+                                                                        pixel_means[1], pixel_means[2],
+                                                                        (__nv_bfloat16 *)out_padded_nhwc, Cpad, blob_f32);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+extern "C" int azn_maxpool2x2_forward(const void *in_padded, int n_img, int H, int W, int C, void *out_padded,
+                                      azn_stream_t stream) {
+    AZN_REQUIRE(in_padded && out_padded, "azn_maxpool2x2_forward: null pointer");
+    AZN_REQUIRE(n_img > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "azn_maxpool2x2_forward: bad shape (C must be a multiple of 8)");
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;         // ceil((H - 2) / 2) + 1
+    const long total = (long)n_img * (Ho + 2) * (Wo + 2) * (C / 8);
+    maxpool2x2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in_padded, n_img, H, W, C / 8,
+                                                                        (uint4 *)out_padded, Ho, Wo);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+extern "C" int azn_nhwc_border(const void *in, int n_img, int H, int W, int C, void *out, int to_padded, azn_stream_t stream) {
+    AZN_REQUIRE(in && out, "azn_nhwc_border: null pointer");
+    AZN_REQUIRE(n_img > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "azn_nhwc_border: bad shape (C must be a multiple of 8)");
+    const long total = (long)n_img * (H + 2) * (W + 2) * (C / 8);
+    pad_border_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, n_img, H, W, C / 8, (uint4 *)out,
+                                                                        to_padded ? 1 : 0);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}

@@ -197,3 +197,89 @@ def decode_boxes(boxes: torch.Tensor, deltas: torch.Tensor, im_h: int, im_w: int
     L.check(L.lib().azn_decode_boxes(_ptr(boxes), _ptr(deltas), n, ncol, float(eps), int(im_h), int(im_w), _ptr(out),
                                      _stream()), "azn_decode_boxes")
     return out
+
+
+# ---- the conv5_3 backbone: zero-bordered channels-last maps [n, H+2, W+2, C] bf16 -----------------
+def blob_size(h0: int, w0: int, im_scale: float):
+    """Destination size of cv2.resize(im, None, None, fx=s, fy=s): cvRound (half to even) of size * s."""
+    import numpy as np
+    return int(np.rint(h0 * im_scale)), int(np.rint(w0 * im_scale))
+
+
+def image_blob(images: torch.Tensor, im_scale: float, pixel_means, cpad: int = 64, out: torch.Tensor | None = None,
+               want_f32: bool = False):
+    """uint8 [n, H0, W0, 3] BGR images -> mean-subtracted, bilinearly resized network input
+    (_get_image_blob, lib/detect/test.py:27-59) as a zero-bordered NHWC bf16 map [n, Hs+2, Ws+2, cpad]
+    (+ Caffe's f32 NCHW 'data' blob [n, 3, Hs, Ws] when want_f32)."""
+    _need_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+    n, h0, w0, _ = images.shape
+    hs, ws = blob_size(h0, w0, im_scale)
+    if out is None:
+        out = torch.empty((n, hs + 2, ws + 2, cpad), dtype=torch.bfloat16, device=images.device)
+    assert out.shape == (n, hs + 2, ws + 2, cpad) and out.dtype == torch.bfloat16 and out.is_contiguous()
+    blob = torch.empty((n, 3, hs, ws), dtype=torch.float32, device=images.device) if want_f32 else None
+    import ctypes as C
+    means = (C.c_double * 3)(*[float(m) for m in pixel_means])
+    L.check(L.lib().azn_image_blob(_ptr(images), n, h0, w0, float(im_scale), means, _ptr(out), cpad, hs, ws, _ptr(blob),
+                                   _stream()), "azn_image_blob")
+    return (out, blob) if want_f32 else out
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: int | None = None):
+    """Caffe conv weight [Cout, Cin, 3, 3] -> bf16 [Cout, 9 * Cin_pad] with column (ky*3+kx)*Cin_pad + c
+    (the K order of azn_conv3x3_forward); input channels zero-padded to a multiple of 64."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    cp = cin_pad or (ci + 63) // 64 * 64
+    t = torch.zeros((co, 3, 3, cp), dtype=torch.float32, device=w.device)
+    t[..., :ci] = w.permute(0, 2, 3, 1)
+    return t.reshape(co, 9 * cp).to(torch.bfloat16).contiguous()
+
+
+def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, relu: bool = True, out: torch.Tensor | None = None,
+            unpadded: bool = False):
+    """3x3 / pad 1 / stride 1 convolution (+ bias, ReLU) as an implicit GEMM on the tensor cores.
+    x bf16 [n, H+2, W+2, Cin] zero-bordered; wt = pack_conv_weight(W); -> [n, H+2, W+2, Cout] zero-bordered, or
+    [n, H, W, Cout] with unpadded=True."""
+    _need_cuda(x, wt, bias)
+    assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert x.is_contiguous() and wt.is_contiguous() and x.dim() == 4
+    n, hp, wp, cin = x.shape
+    cout = wt.shape[0]
+    assert wt.shape[1] == 9 * cin
+    shape = (n, hp - 2, wp - 2, cout) if unpadded else (n, hp, wp, cout)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.bfloat16
+    ws = fc_workspace(x.device, cout)
+    L.check(L.lib().azn_conv3x3_forward(_ptr(x), _ptr(wt), _ptr(bias), _ptr(out), n, hp - 2, wp - 2, cin, cout, int(relu),
+                                        int(unpadded), _ptr(ws), ws.numel(), _stream()), "azn_conv3x3_forward")
+    return out
+
+
+def maxpool2x2(x: torch.Tensor, out: torch.Tensor | None = None):
+    """MAX 2x2 / stride 2 pooling, ceil mode (pooling_layer.cpp:81-95), zero-bordered NHWC bf16 in and out."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    n, hp, wp, c = x.shape
+    h, w = hp - 2, wp - 2
+    shape = (n, (h + 1) // 2 + 2, (w + 1) // 2 + 2, c)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    assert tuple(out.shape) == shape and out.is_contiguous()
+    L.check(L.lib().azn_maxpool2x2_forward(_ptr(x), n, h, w, c, _ptr(out), _stream()), "azn_maxpool2x2_forward")
+    return out
+
+
+def nhwc_border(x: torch.Tensor, to_padded: bool, out: torch.Tensor | None = None):
+    """[n, H, W, C] bf16 -> zero-bordered [n, H+2, W+2, C] (to_padded) or back."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    n, a, b, c = x.shape
+    h, w = (a, b) if to_padded else (a - 2, b - 2)
+    shape = (n, h + 2, w + 2, c) if to_padded else (n, h, w, c)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().azn_nhwc_border(_ptr(x), n, h, w, c, _ptr(out), int(to_padded), _stream()), "azn_nhwc_border")
+    return out

@@ -279,6 +279,35 @@ int azn_detect_thresholds(const float *top_scores, const int32_t *det_count, int
 int azn_detect_filter(const float *top_scores, int32_t *det_count, const float *thresh, int n_images,
                       int num_classes, int max_per_image, azn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The conv5_3 backbone (the first "next" row): VGG16 conv1_1 .. conv5_3 of
+ * models/Pascal/VGG16/az-net/test.prototxt:16-384 and the image blob of lib/detect/test.py:27-59.
+ * Every activation map is a ZERO-BORDERED channels-last grid [n_img, H+2, W+2, C] bf16: the border is the
+ * convolution's padding and every producer below writes it, so buffers can be reused without memsets.
+ *
+ * azn_image_blob  replaces: _get_image_blob + im_list_to_blob (lib/detect/test.py:27-59, lib/utils/blob.py:13-29)
+ *   images uint8 [n_img, H0, W0, 3] (BGR, cv2.imread order; one size per batch) -> (image - pixel_means) resized
+ *   by im_scale with cv::resize's INTER_LINEAR arithmetic (float source) -> out bf16 [n_img, Hs+2, Ws+2, Cpad]
+ *   (channels 0..2 = B, G, R, the rest zero) and, when blob_f32 != NULL, Caffe's own f32 NCHW 'data' blob
+ *   [n_img, 3, Hs, Ws].  Hs/Ws = the reference's destination size, cvRound(H0 * im_scale), computed by the caller.
+ * azn_conv3x3_forward  replaces: ConvolutionLayer::Forward (3x3, pad 1, stride 1) + in-place ReLU
+ *   (caffe-fast-rcnn/src/caffe/layers/conv_layer.cpp, base_conv_layer.cpp forward_cpu_gemm/forward_cpu_bias)
+ *   X bf16 [n_img, H+2, W+2, Cin] zero-bordered, Cin % 64 == 0; Wt bf16 [Cout, 9*Cin], column (ky*3+kx)*Cin + c
+ *   = Caffe's weight[o][c][ky][kx]; bias f32 [Cout]; Y bf16 [n_img, H+2, W+2, Cout] (border written as zeros) or,
+ *   with out_unpadded, [n_img, H, W, Cout] -- the map layout of azn_roi_pool_fwd.  Implicit GEMM on tcgen05:
+ *   same kernel, workspace and constraints as azn_fc_forward (persistent, needs the whole GPU).
+ * azn_maxpool2x2_forward  replaces: PoolingLayer MAX 2x2 / stride 2, ceil mode (pooling_layer.cpp:81-95,144-168)
+ *   in [n_img, H+2, W+2, C] -> out [n_img, ceil(H/2)+2, ceil(W/2)+2, C], C % 8 == 0.
+ * azn_nhwc_border: [n_img, H, W, C] <-> zero-bordered grid (to_padded = 1 / 0). */
+int azn_image_blob(const uint8_t *images, int n_img, int H0, int W0, double im_scale, const double *pixel_means,
+                   void *out_padded_nhwc, int Cpad, int Hs, int Ws, float *blob_f32, azn_stream_t stream);
+int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
+                        int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
+                        azn_stream_t stream);
+int azn_maxpool2x2_forward(const void *in_padded, int n_img, int H, int W, int C, void *out_padded,
+                           azn_stream_t stream);
+int azn_nhwc_border(const void *in, int n_img, int H, int W, int C, void *out, int to_padded, azn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

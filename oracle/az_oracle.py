@@ -538,3 +538,71 @@ def test_net_select(per_image, num_classes, max_per_image=100):
             inds = np.where(all_boxes[j][i][:, -1] > thresh[j])[0]
             all_boxes[j][i] = all_boxes[j][i][inds, :]
     return all_boxes, thresh
+
+
+# ---- backbone: image blob and VGG16 conv1_1 .. conv5_3 -------------------------------------------
+PIXEL_MEANS = np.array([[[102.9801, 115.9465, 122.7717]]])          # lib/detect/config.py:210
+
+
+def resize_linear_f32(src, fx, fy):
+    """cv2.resize(src f32 HxWxC, None, None, fx, fy, INTER_LINEAR) restated in numpy (OpenCV 4.x
+    modules/imgproc/src/resize.cpp: coordinate tables in float from a double scale, horizontal pass
+    S[x0]*(1-a) + S[x1]*a, vertical pass T0*(1-b) + T1*b, all float32; destination size = cvRound(size * f)).
+    Pinned against cv2 itself by tests/test_oracle.py::test_image_blob_matches_cv2 (<= 1 ulp-level differences:
+    cv2's SIMD path may contract a multiply-add)."""
+    h0, w0 = src.shape[:2]
+    hs, ws = int(np.rint(h0 * fy)), int(np.rint(w0 * fx))
+    sx_scale, sy_scale = 1.0 / fx, 1.0 / fy
+
+    def table(n_dst, n_src, scale, clamp_frac):
+        d = np.arange(n_dst, dtype=np.float64)
+        f = (d + 0.5) * scale - 0.5                      # source coordinate, double
+        i = np.floor(f).astype(np.int64)
+        a = (f - i).astype(np.float32)                   # fraction taken in double, THEN rounded to float
+        if clamp_frac:                                   # x: the fraction is zeroed where the index is clamped
+            a[i < 0] = 0
+            i[i < 0] = 0
+            a[i >= n_src - 1] = 0
+            i[i >= n_src - 1] = n_src - 1
+            return i, np.minimum(i + 1, n_src - 1), a
+        return np.clip(i, 0, n_src - 1), np.clip(i + 1, 0, n_src - 1), a      # y: rows clamped, fraction kept
+
+    x0, x1, ax = table(ws, w0, sx_scale, True)
+    y0, y1, ay = table(hs, h0, sy_scale, False)
+    src = src.astype(np.float32, copy=False)
+    a1 = ax[None, :, None]
+    a0 = (np.float32(1) - ax)[None, :, None]
+    rows = src[:, x0] * a0 + src[:, x1] * a1             # horizontal pass on every source row (float32)
+    b1 = ay[:, None, None]
+    b0 = (np.float32(1) - ay)[:, None, None]
+    return (rows[y0] * b0 + rows[y1] * b1).astype(np.float32)
+
+
+def get_image_blob(im, cfg):
+    """_get_image_blob + im_list_to_blob (lib/detect/test.py:27-59, lib/utils/blob.py:13-29) for one scale:
+    uint8 HxWx3 BGR -> f32 blob [1, 3, Hs, Ws], im_scale."""
+    im_orig = im.astype(np.float32, copy=True)
+    im_orig -= PIXEL_MEANS
+    s = im_scale_for(im.shape, cfg)[0]
+    out = resize_linear_f32(im_orig, s, s)
+    return np.ascontiguousarray(out.transpose(2, 0, 1)[None]), s
+
+
+def vgg16_conv5(weights, data, threads=None):
+    """conv1_1 .. conv5_3 of models/Pascal/VGG16/az-net/test.prototxt:16-384 in fp32 on the CPU:
+    ConvolutionLayer (im2col + sgemm + bias, conv_layer.cpp / base_conv_layer.cpp) = a 3x3 pad-1 correlation,
+    in-place ReLU, MAX pooling 2x2/2 in ceil mode (pooling_layer.cpp:81-95).  data f32 [n,3,H,W] -> f32 [n,C,h,w]."""
+    import torch
+    import torch.nn.functional as F
+    if threads:
+        torch.set_num_threads(threads)
+    x = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+    stages = [2, 2, 3, 3, 3]
+    with torch.no_grad():
+        for s, n in enumerate(stages, 1):
+            for i in range(1, n + 1):
+                W, b = weights["conv%d_%d" % (s, i)]
+                x = F.relu(F.conv2d(x, torch.from_numpy(np.ascontiguousarray(W)), torch.from_numpy(np.ascontiguousarray(b)), padding=1))
+            if s < 5:
+                x = F.max_pool2d(x, 2, 2, ceil_mode=True)
+    return x.numpy()

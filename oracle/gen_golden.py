@@ -7,7 +7,8 @@ Generates tests/golden/*.npz by executing the REFERENCE'S OWN CODE on seeded inp
 The fixtures store inputs' seeds + the reference's outputs; tests/ compare the oracle
 restatement (CPU suite) and the CUDA path (gpu suite) against them.
 
-    python oracle/gen_golden.py        # rewrites tests/golden/
+    python oracle/gen_golden.py                 # rewrites tests/golden/
+    python oracle/gen_golden.py --only blob     # one fixture file (div | nms | search | blob)
 """
 from __future__ import annotations
 
@@ -166,12 +167,43 @@ def gen_search(rtest, rconfig):
     np.savez_compressed(os.path.join(GOLD, "search.npz"), **out)
 
 
+BLOB_CASES = [  # name, image shape, TEST.SCALES, TEST.MAX_SIZE
+    ("up_1p6", (30, 50), (48,), 1000),
+    ("capped_by_max_size", (45, 75), (60,), 80),
+    ("down_portrait", (64, 48), (40,), 1000),
+    ("odd_ratio", (37, 53), (61,), 1000),
+]
+
+
+def gen_blob(rtest, rconfig):
+    """The reference's own _get_image_blob (lib/detect/test.py:27-59: mean subtraction + cv2.resize INTER_LINEAR +
+    im_list_to_blob) on seeded uint8 images -> tests/golden/blob.npz."""
+    cfg = rconfig.cfg
+    out = {}
+    keep = (cfg.TEST.SCALES, cfg.TEST.MAX_SIZE)
+    for k, (name, shape, scales, max_size) in enumerate(BLOB_CASES):
+        cfg.TEST.SCALES, cfg.TEST.MAX_SIZE = scales, max_size
+        im = np.random.RandomState(1000 + k).randint(0, 256, shape + (3,)).astype(np.uint8)
+        blob, factors = rtest._get_image_blob(im)
+        out[name + "_im"], out[name + "_blob"] = im, blob.astype(np.float32)
+        out[name + "_cfg"] = np.array([scales[0], max_size, float(factors[0])], dtype=np.float64)
+        print("blob:", name, im.shape, "->", blob.shape, "scale", float(factors[0]))
+    cfg.TEST.SCALES, cfg.TEST.MAX_SIZE = keep
+    np.savez_compressed(os.path.join(GOLD, "blob.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     rtest, rconfig, div, nms = load_reference()
-    gen_div(div)
-    gen_nms(nms)
-    gen_search(rtest, rconfig)
+    only = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None
+    if only in (None, "div"):
+        gen_div(div)
+    if only in (None, "nms"):
+        gen_nms(nms)
+    if only in (None, "search"):
+        gen_search(rtest, rconfig)
+    if only in (None, "blob"):
+        gen_blob(rtest, rconfig)
 
 
 if __name__ == "__main__":

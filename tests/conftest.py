@@ -17,3 +17,9 @@ def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
     return {n: np.load(os.path.join(d, n + ".npz"), allow_pickle=False) for n in ("div", "nms", "search")}
+
+
+@pytest.fixture(scope="session")
+def golden_blob():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "blob.npz"), allow_pickle=False)

@@ -156,3 +156,39 @@ def test_test_net_select_small():
         tot = sum(len(all_boxes[j][i]) for i in range(6) if not isinstance(all_boxes[j][i], list))
         assert tot <= max_per_set
         assert all_boxes[j][2] == []
+
+
+BLOB_TOL = 6.2e-5      # 4 float32 ulps at |v| < 256: cv2's SIMD path rounds the two multiply-adds differently
+
+
+def test_image_blob_golden(golden_blob):
+    """The numpy restatement of _get_image_blob vs the blobs the reference's own function produced
+    (oracle/gen_golden.py --only blob)."""
+    names = sorted(k[:-3] for k in golden_blob.files if k.endswith("_im"))
+    assert len(names) >= 4
+    for name in names:
+        im, ref, c = golden_blob[name + "_im"], golden_blob[name + "_blob"], golden_blob[name + "_cfg"]
+        cfg = O.OracleCfg(TEST_SCALES=(int(c[0]),), TEST_MAX_SIZE=int(c[1]))
+        blob, s = O.get_image_blob(im, cfg)
+        assert s == c[2] and blob.shape == ref.shape and blob.dtype == np.float32
+        assert np.abs(blob - ref).max() <= BLOB_TOL, name
+
+
+def test_image_blob_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(0)
+    for (h, w, s) in [(60, 100, 0.8), (75, 50, 1.6), (33, 50, 600 / 333.0), (20, 32, 3.0), (97, 131, 0.37)]:
+        f = rng.randint(0, 256, (h, w, 3)).astype(np.float32)
+        f -= O.PIXEL_MEANS
+        ref = cv2.resize(f, None, None, fx=s, fy=s, interpolation=cv2.INTER_LINEAR)
+        got = O.resize_linear_f32(f, s, s)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= BLOB_TOL
+
+
+def test_vgg16_conv5_shapes_ceil_mode():
+    """Caffe pooling is ceil-mode (pooling_layer.cpp:93-95): a 75x125 input -> 5x8 conv5_3 map, post-ReLU."""
+    from aznet_b200 import backbone
+    w = backbone.make_vgg16_weights(seed=5, width_div=8)
+    x = np.random.RandomState(1).standard_normal((1, 3, 75, 125)).astype(np.float32)
+    y = O.vgg16_conv5(w, x)
+    assert y.shape == (1, 64, 5, 8) and y.min() >= 0 and y.max() > 0
