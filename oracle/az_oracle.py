@@ -140,6 +140,14 @@ def relu(x):
     return np.maximum(x, np.float32(0))
 
 
+def round_bf16(x):
+    """float32 -> nearest-even bfloat16 -> float32 (the storage format of the product's activations)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u + np.uint32(0x7fff) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xffff0000)).astype(np.uint32)
+    r = np.where((u & np.uint32(0x7f800000)) == np.uint32(0x7f800000), u, r)        # inf / nan pass through
+    return r.view(np.float32).reshape(np.shape(x))
+
+
 class _Blob:
     def __init__(self):
         self.shape = ()
@@ -162,8 +170,11 @@ class OracleNet:
              'full' net; without one it is the 'fc' net whose inputs are (conv5_3, rois).
     """
 
-    def __init__(self, weights, kind="az", backbone=None, name="oracle", cfg=None, threads=None):
+    def __init__(self, weights, kind="az", backbone=None, name="oracle", cfg=None, threads=None, act_round=None):
         self.w = weights
+        # optional storage rounding of the hidden activations (e.g. round_bf16): lets a test separate the
+        # product's bf16 activation storage from everything else.  None = the reference's fp32 blobs.
+        self.act_round = act_round or (lambda v: v)
         self.kind = kind
         self.backbone = backbone
         self.name = name
@@ -189,16 +200,17 @@ class OracleNet:
         x = pool5.reshape(pool5.shape[0], -1)            # K index = c*49 + ph*7 + pw (Q12)
         ip = lambda name, v: inner_product(v, self.w[name][0], self.w[name][1], self.threads)
         out = {}
+        rnd = self.act_round
         if self.kind == "az":
-            h6 = relu(ip("int6", x))                      # dropout in TEST phase = identity
-            h71 = relu(ip("int7_1", h6))
-            h72 = relu(ip("int7_2", h6))
+            h6 = rnd(relu(ip("int6", x)))                 # dropout in TEST phase = identity
+            h71 = rnd(relu(ip("int7_1", h6)))
+            h72 = rnd(relu(ip("int7_2", h6)))
             out["adj_prob"] = sigmoid(ip("adj_score", h71))
             out["adj_bbox"] = ip("adj_bbox", h71)
             out["zoom_prob"] = sigmoid(ip("zoom_score", h72))
         else:
-            h6 = relu(ip("fc6", x))
-            h7 = relu(ip("fc7", h6))
+            h6 = rnd(relu(ip("fc6", x)))
+            h7 = rnd(relu(ip("fc7", h6)))
             out["cls_prob"] = softmax(ip("cls_score", h7))
             out["bbox_pred"] = ip("bbox_pred", h7)
         self.stats["pool_s"] += t1 - t0

@@ -162,9 +162,18 @@ def test_im_detect_vs_oracle(dev, O, cfg):
     bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
     wq = {k: (bf(v[0]), v[1]) for k, v in frw.items()}
     ocfg = O.OracleCfg()
+    # (1) the oracle with the product's bf16 activation storage emulated: only the fp32 summation order differs
+    onet = O.OracleNet(wq, "frcnn", cfg=ocfg, act_round=O.round_bf16)
+    s_ref, p_ref, _ = O.frcnn_forward({"full": onet, "fc": onet}, im.shape, boxes, 6, {"conv5_3": bf(conv)}, ocfg)
+    np.testing.assert_allclose(scores, s_ref, atol=5e-3)
+    np.testing.assert_allclose(pred, p_ref, rtol=5e-3, atol=0.5)
+    # (2) the reference's fp32 blobs: stated tolerance for bf16 activations.  The logits here are O(10) (the conv
+    # map of a random-init backbone is not normalised), so a 2^-9 relative activation error moves a probability
+    # by up to ~3e-2
     onet = O.OracleNet(wq, "frcnn", cfg=ocfg)
     s_ref, p_ref, _ = O.frcnn_forward({"full": onet, "fc": onet}, im.shape, boxes, 6, {"conv5_3": bf(conv)}, ocfg)
-    np.testing.assert_allclose(scores, s_ref, atol=2e-2)                 # bf16 activations vs fp32: stated tolerance
+    np.testing.assert_allclose(scores, s_ref, atol=4e-2)
+    assert np.mean(np.abs(scores - s_ref)) < 4e-3
     np.testing.assert_allclose(pred, p_ref, rtol=2e-2, atol=2.0)
 
 
