@@ -24,14 +24,14 @@ LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_AZ_HEAD, ACT_SOFTMAX_BBOX = 0, 1, 2, 3
 NMS_SEG_MAX = 1024
-LEVEL_LAST, LEVEL_ROOT_PROPS = 1, 2
+LEVEL_LAST, LEVEL_ROOT_PROPS, LEVEL_TUNE = 1, 2, 4
 
 EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments",
-    "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter",
+    "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter", "azn_tune_threshold",
     "azn_image_blob", "azn_conv3x3_forward", "azn_maxpool2x2_forward", "azn_nhwc_border",
 ]
 
@@ -82,6 +82,7 @@ class SearchState(C.Structure):
         ("children", C.c_void_p), ("hashes", C.c_void_p), ("flags", C.c_void_p),
         ("props", C.c_void_p), ("prop_scores", C.c_void_p), ("n_props", C.c_void_p),
         ("n_eval", C.c_void_p), ("depth", C.c_void_p), ("status", C.c_void_p),
+        ("hist_regions", C.c_void_p), ("hist_zoom", C.c_void_p), ("n_history", C.c_void_p), ("cap_history", C.c_int32),
     ]
 
 
@@ -156,6 +157,8 @@ def _bind(L):
     L.azn_detect_select.argtypes = [C.POINTER(DetectState), vp]
     L.azn_detect_thresholds.restype = i32
     L.azn_detect_thresholds.argtypes = [vp, vp, i32, i32, i32, C.c_longlong, vp, vp]
+    L.azn_tune_threshold.restype = i32
+    L.azn_tune_threshold.argtypes = [vp, vp, i32, i32, C.c_longlong, vp, vp]
     L.azn_detect_filter.restype = i32
     L.azn_detect_filter.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.azn_image_blob.restype = i32

@@ -234,11 +234,11 @@ __global__ void __launch_bounds__(SEL_THREADS_D) detect_select_kernel(azn_detect
 // ---- per class: the max_per_set-th highest pushed score of the whole image set ----------------------
 __global__ void __launch_bounds__(TH_THREADS)
 detect_thresh_kernel(const float *__restrict__ top_scores, const int32_t *__restrict__ det_count, int n_images, int C,
-                     int mpi, long long max_per_set, float *__restrict__ thresh) {
+                     int mpi, long long max_per_set, float *__restrict__ thresh, int has_background) {
     __shared__ unsigned s_hist[256], s_pn[2];
     __shared__ int s_warp[33];
     const int j = blockIdx.x, tid = threadIdx.x;
-    if (j == 0) {
+    if (j == 0 && has_background) {
         if (tid == 0) thresh[0] = -INFINITY;
         return;
     }
@@ -326,7 +326,18 @@ extern "C" int azn_detect_thresholds(const float *top_scores, const int32_t *det
                 "azn_detect_thresholds: bad sizes");
     AZN_REQUIRE((double)n_images * max_per_image < 2.0e9, "azn_detect_thresholds: too many scores for one launch");
     detect_thresh_kernel<<<num_classes, TH_THREADS, 0, (cudaStream_t)stream>>>(top_scores, det_count, n_images, num_classes,
-                                                                             max_per_image, max_per_set, thresh);
+                                                                             max_per_image, max_per_set, thresh, 1);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+// tune_thresh (lib/detect/tune.py:318-366): one "class" without a background column, scores = anchor zoom scores
+extern "C" int azn_tune_threshold(const float *zoom, const int32_t *counts, int n_images, int cap, long long max_per_set,
+                                  float *thresh, azn_stream_t stream) {
+    AZN_REQUIRE(zoom && counts && thresh, "azn_tune_threshold: null pointer");
+    AZN_REQUIRE(n_images > 0 && cap > 0 && max_per_set > 0, "azn_tune_threshold: bad sizes");
+    AZN_REQUIRE((double)n_images * cap < 2.0e9, "azn_tune_threshold: too many scores for one launch");
+    detect_thresh_kernel<<<1, TH_THREADS, 0, (cudaStream_t)stream>>>(zoom, counts, n_images, 1, cap, max_per_set, thresh, 0);
     AZN_LAUNCH_CHECK();
     return AZN_OK;
 }

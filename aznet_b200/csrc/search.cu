@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int LEVEL_THREADS = 512;
-constexpr int AZN_LEVEL_ROOT_DIVIDE = 4;     // internal: phases 2-4 for the root only (azn_search_root)
+constexpr int AZN_LEVEL_ROOT_DIVIDE = 64;    // internal: phases 2-4 for the root only (azn_search_root)
 
 // ---- divide_region for one region: number of children and the children themselves -------
 struct DivGeom {
@@ -98,6 +98,7 @@ __global__ void search_init_kernel(azn_search_state st) {
     st.n_props[i] = 0;
     st.n_eval[i] = 0;
     st.depth[i] = 0;
+    if (st.n_history) st.n_history[i] = 0;
 }
 
 __global__ void __launch_bounds__(LEVEL_THREADS)
@@ -121,9 +122,28 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
         if (tid == 0 && !root_props) st.next_n_regions[i] = 0, st.n_uniq[i] = 0;
         return;
     }
+    const bool tune = mode & AZN_LEVEL_TUNE;
     if (tid == 0 && !root_divide) {
         st.depth[i] = level;
         st.n_eval[i] += nR;
+    }
+    // anchor history: Bhis = vstack((Bhis, hstack((B, zoom)))) (lib/detect/tune.py:298)
+    if (!root_divide && st.hist_regions != nullptr) {
+        const int h0 = st.n_history[i];
+        __syncthreads();
+        double *hr = st.hist_regions + (size_t)i * st.cap_history * 4;
+        float *hz = st.hist_zoom + (size_t)i * st.cap_history;
+        for (int r = tid; r < nR; r += LEVEL_THREADS) {
+            if (h0 + r < st.cap_history) {
+                const double *b = regions + (size_t)r * 4;
+                double *o = hr + (size_t)(h0 + r) * 4;
+                o[0] = b[0]; o[1] = b[1]; o[2] = b[2]; o[3] = b[3];
+                hz[h0 + r] = zoom_prob[(size_t)(row0 + (root_props ? 0 : inv[r])) * ld_zoom];
+            } else {
+                *st.status = AZN_ERR_CAPACITY;
+            }
+        }
+        if (tid == 0) st.n_history[i] = h0 + nR < st.cap_history ? h0 + nR : st.cap_history;
     }
 
     // ---------------- phase 1: adjacent predictions -> Y ------------------------------------
@@ -183,8 +203,9 @@ search_level_kernel(azn_search_state st, const float *__restrict__ zoom_prob, in
             // the root region is always divided (:383-384), whatever the net says: level 2 does not depend on
             // level 1's outputs, which is what lets the two levels share one pass of the heads
             double z = 1.0;
-            if (!(level == 1 && r == 0)) z = (double)zoom_prob[(size_t)(row0 + inv[r]) * ld_zoom];
-            if (z >= st.tz) {                                      // indZ = where(zoom >= Tz) (:386)
+            if (tune || !(level == 1 && r == 0)) z = (double)zoom_prob[(size_t)(row0 + inv[r]) * ld_zoom];
+            const double tz = (tune && level == 1) ? 0.0 : st.tz;   // tune.py:278 starts at Tz = 0, then cfg.SEAR.Tz (:305)
+            if (z >= tz) {                                      // indZ = where(zoom >= Tz) (:386)
                 g = div_geom(box[0], box[1], box[2], box[3]);
                 cnt = div_count(g);
             }
@@ -481,6 +502,8 @@ int check_state(const azn_search_state *st) {
                     st->n_eval && st->depth && st->status,
                 "search: null pointer in state");
     AZN_REQUIRE(st->min_side > 0, "search: min_side must be positive");
+    AZN_REQUIRE(st->hist_regions == nullptr || (st->hist_zoom && st->n_history && st->cap_history > 0),
+                "search: hist_regions needs hist_zoom, n_history and cap_history > 0");
     return AZN_OK;
 }
 
@@ -501,12 +524,13 @@ extern "C" int azn_search_level(const azn_search_state *st, const float *zoom_pr
     AZN_REQUIRE(zoom_prob && adj_prob && adj_bbox && ld_zoom >= 1 && ld_prob >= st->nsub && ld_bbox >= 4 * st->nsub,
                 "azn_search_level: bad head pointers/strides");
     AZN_REQUIRE(level >= 1, "azn_search_level: level is 1-based");
-    AZN_REQUIRE((flags & ~(AZN_LEVEL_LAST | AZN_LEVEL_ROOT_PROPS)) == 0, "azn_search_level: unknown flags %d", flags);
+    AZN_REQUIRE((flags & ~(AZN_LEVEL_LAST | AZN_LEVEL_ROOT_PROPS | AZN_LEVEL_TUNE)) == 0, "azn_search_level: unknown flags %d", flags);
+    AZN_REQUIRE(!(flags & AZN_LEVEL_TUNE) || !(flags & AZN_LEVEL_ROOT_PROPS), "azn_search_level: AZN_LEVEL_TUNE excludes the merged root");
     AZN_REQUIRE(!(flags & AZN_LEVEL_ROOT_PROPS) || level == 1, "azn_search_level: AZN_LEVEL_ROOT_PROPS is for level 1");
     cudaStream_t s = (cudaStream_t)stream;
     AZN_CUDA(azn_launch_pdl(search_level_kernel, dim3(st->n_img), dim3(LEVEL_THREADS), 0, s, *st, zoom_prob, ld_zoom, adj_prob,
                             ld_prob, adj_bbox, ld_bbox, level, flags));
-    if (!flags) {
+    if (!(flags & (AZN_LEVEL_LAST | AZN_LEVEL_ROOT_PROPS))) {
         // the next level's regions become current: swap, then pack its unique ROIs
         azn_search_state nx = *st;
         nx.regions = st->next_regions;

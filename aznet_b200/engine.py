@@ -83,7 +83,7 @@ class SearchEngine:
 
     def __init__(self, head: AZHeadWeights, n_img, im_h, im_w, *, scales=(600,), max_size=1000, min_side=10, tz=0.5,
                  tc=0.05, fixed_num=True, num_proposals=300, batch_size=10000, dedup=1. / 16., eps=1e-14,
-                 spatial_scale=0.0625, device=None, merge_root=True):
+                 spatial_scale=0.0625, device=None, merge_root=True, tune=False):
         L.require_device()
         self.head = head
         self.dev = device or head.w6.device
@@ -93,10 +93,13 @@ class SearchEngine:
         self.spatial_scale = float(spatial_scale)
         self.scale = im_scale_for(im_h, im_w, scales, max_size)
         self.K = search_depth(im_h, im_w, min_side)
-        self.n_levels = max(self.K - 1, 0)
+        # tune=True is the diagnostic search of lib/detect/tune.py:256-316: K levels (`for k in xrange(K)`), the
+        # root's own zoom score against Tz = 0 at the first level, and the anchor history Bhis
+        self.tune = bool(tune)
+        self.n_levels = self.K if self.tune else max(self.K - 1, 0)
         # the root is always zoomed (test.py:383-384), so level 2 does not depend on level 1's head outputs:
         # both levels go through ONE pass of the heads (one stream of the 216 MB of weights less per step)
-        self.merge_root = bool(merge_root) and self.n_levels >= 2
+        self.merge_root = bool(merge_root) and self.n_levels >= 2 and not self.tune
         dev, i32, f64 = self.dev, torch.int32, torch.float64
         # capacity plan: full-zoom cascade of divide_region run with the product kernel itself
         self.level_sizes = self._plan_levels()
@@ -133,6 +136,10 @@ class SearchEngine:
         self.h6 = torch.empty((m_cap, head.h6), dtype=torch.bfloat16, device=dev)
         self.h7 = torch.empty((m_cap, head.h71 + head.h72), dtype=torch.bfloat16, device=dev)
         self.heads = torch.zeros((m_cap, head.ld_head), dtype=torch.float32, device=dev)
+        self.cap_hist = max(sum(self.level_sizes), 1) if self.tune else 0
+        if self.tune:
+            self.hist_regions, self.hist_zoom = z(n, self.cap_hist, 4, dt=f64), z(n, self.cap_hist, dt=torch.float32)
+            self.n_history = z(n)
         self.collector = None                # dist.ProposalCollector: the final lists are also copied into its next slot
         self._st = L.SearchState()
         self._cur = 0
@@ -152,9 +159,9 @@ class SearchEngine:
     def _plan_levels(self):
         sizes = []
         cur = torch.tensor([[0.0, 0.0, self.im_w - 1.0, self.im_h - 1.0]], dtype=torch.float64, device=self.dev)
-        for k in range(1, self.K):
+        for k in range(1, self.n_levels + 1):
             sizes.append(int(cur.shape[0]))
-            if k == self.K - 1:
+            if k == self.n_levels:
                 break
             out, cnt = ops.divide_region(cur, float(self.min_side))
             c = int(cnt.item())
@@ -174,6 +181,9 @@ class SearchEngine:
         st.children, st.hashes, st.flags = p(self.children), p(self.hashes), p(self.flags)
         st.props, st.prop_scores, st.n_props = p(self.props), p(self.prop_scores), p(self.n_props)
         st.n_eval, st.depth, st.status = p(self.n_eval), p(self.depth), p(self.status)
+        if self.tune:
+            st.hist_regions, st.hist_zoom, st.n_history = p(self.hist_regions), p(self.hist_zoom), p(self.n_history)
+            st.cap_history = self.cap_hist
         self._point(0)
 
     def _point(self, cur):
@@ -257,11 +267,14 @@ class SearchEngine:
     def search_level(self, level: int, root_props: bool = False):
         hd, ld = self.head, self.head.ld_head
         flags = L.LEVEL_ROOT_PROPS if root_props else (L.LEVEL_LAST if level == self.n_levels else 0)
+        swap = not flags or root_props
+        if self.tune:
+            flags |= L.LEVEL_TUNE
         base = self.heads.data_ptr()
         L.check(L.lib().azn_search_level(C.byref(self._st), base + 4 * 5 * hd.nsub, ld, base, ld, base + 4 * hd.nsub, ld,
                                          level, flags, ops._stream()), "azn_search_level")
-        self.launches += 1 if flags else 2
-        if not flags or root_props:
+        self.launches += 2 if swap and not root_props else 1
+        if swap:
             self._point(1 - self._cur)                 # after the root's predictions, level 2 becomes current
 
 
@@ -313,6 +326,14 @@ class SearchEngine:
                 pre()
             self.propose(conv_nhwc)
         return g, self.launches - before
+
+    def history(self):
+        """Anchor history per image, f64 [n_i, 5] = (region, zoom score): the `Bhis` of lib/detect/tune.py:298."""
+        assert self.tune, "the anchor history is recorded by SearchEngine(tune=True)"
+        torch.cuda.current_stream().synchronize()
+        cnt = self.n_history.cpu().numpy()
+        reg, zoom = self.hist_regions.cpu().numpy(), self.hist_zoom.cpu().numpy()
+        return [np.hstack((reg[i, :cnt[i]], zoom[i, :cnt[i], None].astype(np.float64))) for i in range(self.n_img)]
 
     def results(self):
         """Synchronise and fetch (boxes list of f64 [n_i,4], scores list, n_eval, depth) to the host."""

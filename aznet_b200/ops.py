@@ -161,6 +161,18 @@ def detect_thresholds(top_scores: torch.Tensor, det_count: torch.Tensor, max_per
     return out
 
 
+def tune_threshold(zoom: torch.Tensor, counts: torch.Tensor, max_per_set: int):
+    """tune_thresh's zoom threshold (lib/detect/tune.py:318-366): the max_per_set-th highest anchor zoom score of the
+    image set, -inf when fewer anchors were seen.  zoom f32 [n, cap], counts int32 [n].  Returns f32 [1]."""
+    _need_cuda(zoom, counts)
+    assert zoom.dtype == torch.float32 and counts.dtype == torch.int32 and zoom.is_contiguous() and counts.is_contiguous()
+    n, cap = zoom.shape
+    out = torch.empty(1, dtype=torch.float32, device=zoom.device)
+    L.check(L.lib().azn_tune_threshold(_ptr(zoom), _ptr(counts), n, cap, int(max_per_set), _ptr(out), _stream()),
+            "azn_tune_threshold")
+    return out
+
+
 def detect_filter(top_scores: torch.Tensor, det_count: torch.Tensor, thresh: torch.Tensor):
     """Final `score > thresh[class]` filter of test_net (:646-651): shrinks det_count in place."""
     _need_cuda(top_scores, det_count, thresh)

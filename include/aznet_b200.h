@@ -150,6 +150,12 @@ typedef struct azn_search_state {
     int32_t *n_eval;         /* [n_img] regions evaluated so far (num_eval)                  */
     int32_t *depth;          /* [n_img] last level that ran (the k printed by im_propose)    */
     int32_t *status;         /* [1] sticky device-side error flag (capacity overflow)        */
+    /* optional anchor-region history (NULL = off): every evaluated region with its zoom score, level by
+     * level in the reference's order -- the `Bhis` of lib/detect/tune.py:270,298 (diagnostic im_propose) */
+    double *hist_regions;    /* [n_img, cap_history, 4]                                      */
+    float *hist_zoom;        /* [n_img, cap_history]                                         */
+    int32_t *n_history;      /* [n_img]                                                      */
+    int32_t cap_history;
 } azn_search_state;
 
 /* Level-1 setup: B = [[0, 0, W-1, H-1]] per image (lib/detect/test.py:355), its ROI, counters. */
@@ -162,6 +168,9 @@ int azn_search_init(const azn_search_state *st, azn_stream_t stream);
  *                         [0, n_img), one per image) and nothing else -- the subdivision already happened. */
 #define AZN_LEVEL_LAST 1
 #define AZN_LEVEL_ROOT_PROPS 2
+/*   AZN_LEVEL_TUNE        the diagnostic search of lib/detect/tune.py:256-316: level 1 compares the root's
+ *                         own zoom score with Tz = 0 (:278) instead of forcing it to 1.0 (test.py:383-384) */
+#define AZN_LEVEL_TUNE 4
 int azn_search_level(const azn_search_state *st, const float *zoom_prob, int ld_zoom,
                      const float *adj_prob, int ld_prob, const float *adj_bbox, int ld_bbox,
                      int level, int flags, azn_stream_t stream);
@@ -275,6 +284,12 @@ int azn_detect_select(const azn_detect_state *st, azn_stream_t stream);
  * several GPUs all-gather them first: every rank then computes identical thresholds). */
 int azn_detect_thresholds(const float *top_scores, const int32_t *det_count, int n_images, int num_classes,
                           int max_per_image, long long max_per_set, float *thresh, azn_stream_t stream);
+/* tune_thresh (lib/detect/tune.py:318-366): the zoom threshold that keeps max_per_set = num_images *
+ * cfg.TRAIN.ANCHORS_PER_IMG anchor regions over the whole image set = the max_per_set-th highest zoom score
+ * of all anchor histories (the reference's min-heap, order-independent), -inf if fewer were seen.
+ * zoom [n_images, cap] f32 (azn_search_state.hist_zoom of one or several batches), counts [n_images]. */
+int azn_tune_threshold(const float *zoom, const int32_t *counts, int n_images, int cap, long long max_per_set,
+                       float *thresh, azn_stream_t stream);
 /* Final `score > thresh[j]` filter (:646-651): shrinks det_count in place (rows are score-descending). */
 int azn_detect_filter(const float *top_scores, int32_t *det_count, const float *thresh, int n_images,
                       int num_classes, int max_per_image, azn_stream_t stream);

@@ -481,6 +481,52 @@ def im_propose(net, im_shape, cfg, conv=None, data_blob=None, num_proposals=None
     return Y
 
 
+def im_propose_tune(net, im_shape, cfg, conv=None, data_blob=None):
+    """The diagnostic im_propose of lib/detect/tune.py:256-316: K levels (`for k in xrange(K)`), Tz = 0 for the
+    first level and cfg.SEAR.Tz afterwards (:278, :305), no forced root, anchor history Bhis (:298).
+    Returns (hstack(Y, scores) [n,5], Bhis [m,5], info)."""
+    B = np.array([[0, 0, im_shape[1] - 1.0, im_shape[0] - 1.0]])
+    Bhis = np.zeros((0, 5))
+    Y = np.zeros((0, 4))
+    a_scores = np.zeros((0,))
+    num_eval = 0
+    K = search_depth(im_shape, cfg)
+    Tz = 0
+    k = 0
+    for k in range(K):
+        zoom, boxes, c, conv = az_forward(net, im_shape, B, conv, cfg, data_blob)
+        num_eval += B.shape[0]
+        Y = np.vstack((Y, boxes))
+        a_scores = np.hstack((a_scores, c))
+        ind_z = np.where(zoom >= Tz)[0]
+        Z = B[ind_z, :]
+        Bhis = np.vstack((Bhis, np.hstack((B, zoom[:, np.newaxis]))))
+        if Z.shape[0] == 0:
+            break
+        B = divide_region(Z, float(cfg.MIN_SIDE))
+        Tz = cfg.Tz
+    ind_a = np.argsort(-a_scores, kind="stable")[:min(cfg.NUM_PROPOSALS, Y.shape[0])]
+    info = {"num_eval": num_eval, "depth": k}
+    return np.hstack((Y[ind_a, :], a_scores[ind_a, np.newaxis])), Bhis, info
+
+
+def tune_thresh(histories, anchors_per_img=20):
+    """tune_thresh's heap loop (lib/detect/tune.py:318-366) over the per-image anchor histories [m_i, 5]:
+    the zoom threshold that keeps num_images * cfg.TRAIN.ANCHORS_PER_IMG anchors."""
+    import heapq
+    max_per_set = len(histories) * anchors_per_img
+    top_scores, thresh = [], -np.inf
+    for h in histories:
+        scores = h[:, -1]
+        for val in scores[np.where(scores > thresh)[0]]:
+            heapq.heappush(top_scores, val)
+        if len(top_scores) > max_per_set:
+            while len(top_scores) > max_per_set:
+                heapq.heappop(top_scores)
+            thresh = top_scores[0]
+    return thresh
+
+
 def frcnn_forward(net, im_shape, all_boxes, num_classes, conv, cfg, data_blob=None):
     """_frcnn_forward, lib/detect/test.py:259-318."""
     bs = cfg.BATCH_SIZE

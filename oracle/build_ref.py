@@ -9,7 +9,7 @@ GPU box with the snapshot like any other built artefact):
                           (np.int_t -> np.intp_t, dtype=np.int -> np.intp; semantics unchanged:
                           argsort returns intp)
   * lib/utils/bbox.pyx -> oracle/_ref/cython_bbox*.so   unmodified (recall parity only)
-  * lib/detect/{test,config}.py, lib/utils/{blob,timer}.py -> oracle/_ref/pyref/  mechanical
+  * lib/detect/{test,tune,config}.py, lib/utils/{blob,timer}.py -> oracle/_ref/pyref/  mechanical
     py2 -> py3 text conversion (print statement, xrange, iteritems, has_key, cPickle, tabs),
     used ONLY by oracle/gen_golden.py in this container.
 
@@ -88,7 +88,7 @@ def _convert_python():
     for sub in ("detect", "utils"):
         os.makedirs(os.path.join(dst, sub), exist_ok=True)
         open(os.path.join(dst, sub, "__init__.py"), "w").close()
-    for rel in ("detect/test.py", "detect/config.py", "utils/blob.py", "utils/timer.py"):
+    for rel in ("detect/test.py", "detect/tune.py", "detect/config.py", "utils/blob.py", "utils/timer.py"):
         src = open(os.path.join(REF, "lib", rel)).read()
         open(os.path.join(dst, rel), "w").write(_py2to3(src))
 

@@ -8,7 +8,7 @@ The fixtures store inputs' seeds + the reference's outputs; tests/ compare the o
 restatement (CPU suite) and the CUDA path (gpu suite) against them.
 
     python oracle/gen_golden.py                 # rewrites tests/golden/
-    python oracle/gen_golden.py --only blob     # one fixture file (div | nms | search | blob)
+    python oracle/gen_golden.py --only blob     # one fixture file (div | nms | search | blob | tune)
 """
 from __future__ import annotations
 
@@ -192,6 +192,72 @@ def gen_blob(rtest, rconfig):
     np.savez_compressed(os.path.join(GOLD, "blob.npz"), **out)
 
 
+TUNE_CASES = [  # name, (H, W), MAX_SIZE, BATCH_SIZE, Tz, zoom_rate, NUM_PROPOSALS
+    ("train_375x500", (375, 500), 1000, 10000, 0.0, 0.5, 2000),      # tools/set_thresh.py: cfg_set_mode('Train') -> Tz = 0
+    ("train_voc_600x1000", (600, 1000), 800, 1000, 0.0, 0.4, 2000),
+    ("tz05_480x640", (480, 640), 1000, 10000, 0.5, 0.5, 300),        # tools/diagnose_prop.py: Test mode
+    ("stop_early_333x500", (333, 500), 1000, 10000, 0.999, 0.0, 300),
+]
+
+
+def gen_tune(rconfig):
+    """The reference's diagnostic im_propose + tune_thresh (lib/detect/tune.py:256-366) with HashNet."""
+    import tempfile
+    import pickle
+    import cv2
+    import detect.tune as rtune
+    cfg = rconfig.cfg
+    out = {}
+    for name, shape, max_size, bs, tz, rate, nprop in TUNE_CASES:
+        cfg.TEST.MAX_SIZE = max_size
+        cfg.SEAR.BATCH_SIZE = bs
+        cfg.SEAR.Tz = tz
+        cfg.SEAR.NUM_PROPOSALS = nprop
+        net = synth.HashNet(seed=11, zoom_rate=rate)
+        im = np.zeros(shape + (3,), dtype=np.uint8)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            Y5, Bhis = rtune.im_propose({"full": net, "fc": net}, im)
+        out[name + "_Y5"], out[name + "_Bhis"] = Y5, Bhis
+        out[name + "_log"] = np.array(buf.getvalue().strip())
+        out[name + "_cfg"] = np.array([shape[0], shape[1], max_size, bs, tz, rate, nprop], dtype=np.float64)
+        print("tune:", name, buf.getvalue().strip(), "history", Bhis.shape)
+    # tune_thresh over a small image set (three sizes, written as PNGs for the reference's cv2.imread)
+    cfg.TEST.MAX_SIZE, cfg.SEAR.BATCH_SIZE = 1000, 10000
+    rconfig.cfg_set_mode("Train")
+    shapes = [(375, 500), (333, 500), (375, 500), (480, 640), (375, 500), (333, 500)]
+    for per_img in (20, 1000000):
+        cfg.TRAIN.ANCHORS_PER_IMG = per_img
+        with tempfile.TemporaryDirectory() as tmp:
+            paths = []
+            for i, sh in enumerate(shapes):
+                paths.append(os.path.join(tmp, "%d.png" % i))
+                cv2.imwrite(paths[-1], np.zeros(sh + (3,), np.uint8))
+
+            class Imdb:
+                name = "synth"
+                image_index = list(range(len(shapes)))
+                roidb = None
+
+                def image_path_at(self, i):
+                    return paths[i]
+
+                def gt_roidb(self):
+                    return None
+            cfg.ROOT_DIR = tmp
+            rconfig.cfg_set_path("golden")
+            net = synth.HashNet(seed=11, zoom_rate=0.5)
+            with contextlib.redirect_stdout(io.StringIO()):
+                rtune.tune_thresh({"full": net, "fc": net}, Imdb())
+            with open(os.path.join(rconfig.get_output_dir(Imdb(), net), "thresh.pkl"), "rb") as f:
+                th = pickle.load(f)
+        out["thresh_per%d" % per_img] = np.array(float(th))
+        print("tune_thresh: ANCHORS_PER_IMG", per_img, "->", th)
+    cfg.TRAIN.ANCHORS_PER_IMG = 20
+    out["thresh_shapes"] = np.array(shapes)
+    np.savez_compressed(os.path.join(GOLD, "tune.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     rtest, rconfig, div, nms = load_reference()
@@ -204,6 +270,8 @@ def main():
         gen_search(rtest, rconfig)
     if only in (None, "blob"):
         gen_blob(rtest, rconfig)
+    if only in (None, "tune"):
+        gen_tune(rconfig)
 
 
 if __name__ == "__main__":

@@ -95,6 +95,66 @@ def test_im_propose_host_route_matches_reference_golden(dev, golden, cfg, name, 
         np.testing.assert_allclose(Y[np.lexsort(Y.T[::-1])], ref[np.lexsort(ref.T[::-1])], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["train_375x500", "tz05_480x640", "stop_early_333x500"])
+def test_tune_im_propose_host_route_matches_reference_golden(dev, golden, cfg, name, capsys):
+    """detect.tune.im_propose with a foreign net = the reference's lib/detect/tune.py run."""
+    from aznet_b200.detect import tune as U
+    g = golden["tune"]
+    H, W, max_size, bs, tz, rate, nprop = g[name + "_cfg"]
+    cfg.TEST.MAX_SIZE, cfg.SEAR.BATCH_SIZE = int(max_size), int(bs)
+    cfg.SEAR.Tz, cfg.SEAR.NUM_PROPOSALS = float(tz), int(nprop)
+    net = synth.HashNet(seed=11, zoom_rate=float(rate))
+    Y5, Bhis = U.im_propose({"full": net, "fc": net}, np.zeros((int(H), int(W), 3), np.uint8))
+    assert capsys.readouterr().out.strip().splitlines()[-1] == str(g[name + "_log"])
+    assert np.array_equal(Bhis.view(np.uint64), g[name + "_Bhis"].view(np.uint64))
+    ref = g[name + "_Y5"]
+    if not np.allclose(Y5, ref, rtol=1e-5, atol=1e-5):
+        np.testing.assert_allclose(Y5[np.lexsort(Y5.T[::-1])], ref[np.lexsort(ref.T[::-1])], rtol=1e-5, atol=1e-5)
+
+
+def test_tune_thresh_dropin(dev, golden, cfg, tmp_path, capsys):
+    """tune_thresh: (a) foreign net over the golden image set -> the reference's thresh.pkl value;
+    (b) device route (Net) = host route over the same nets; thresh.pkl round-trips through cfg_load_thresh."""
+    import cv2
+    from aznet_b200.detect import config as C
+    from aznet_b200.detect import tune as U
+    g = golden["tune"]
+    paths = []
+    for i, (h, w) in enumerate(g["thresh_shapes"]):
+        paths.append(str(tmp_path / ("%d.png" % i)))
+        cv2.imwrite(paths[-1], synth.make_images(1, int(h), int(w), seed=40 + i)[0])
+
+    class Imdb:
+        name = "synth_tune"
+        image_index = list(range(len(paths)))
+
+        def image_path_at(self, i):
+            return paths[i]
+    saved_root, saved_per = cfg.ROOT_DIR, cfg.TRAIN.ANCHORS_PER_IMG
+    cfg.ROOT_DIR = str(tmp_path)
+    try:
+        C.cfg_set_mode("Train")
+        hnet = synth.HashNet(seed=11, zoom_rate=0.5)
+        th = U.tune_thresh({"full": hnet, "fc": hnet}, Imdb())
+        assert float(th) == float(g["thresh_per20"])
+        assert float(C.cfg_load_thresh(os.path.join(C.get_output_dir(Imdb(), hnet), "thresh.pkl"))) == float(th)
+        cfg.TRAIN.ANCHORS_PER_IMG = 1000000
+        assert U.tune_thresh({"full": hnet, "fc": hnet}, Imdb()) == -np.inf
+        cfg.TRAIN.ANCHORS_PER_IMG = 5
+        az, _, _, _ = _small_nets(dev)
+        th_fast = U.tune_thresh(az, Imdb())
+
+        class Foreign(dict):
+            pass
+        wrap = lambda n: type("W", (), {"forward": n.forward, "blobs": n.blobs, "name": n.name})()
+        th_host = U.tune_thresh(Foreign(full=wrap(az["full"]), fc=wrap(az["fc"])), Imdb())
+        assert np.isfinite(th_fast) and abs(float(th_fast) - float(th_host)) < 2e-3
+        out = capsys.readouterr().out
+        assert "the threshold is set to" in out and "im_tune: 6/6" in out
+    finally:
+        cfg.ROOT_DIR, cfg.TRAIN.ANCHORS_PER_IMG = saved_root, saved_per
+
+
 def _small_nets(dev, num_classes=6):
     from aznet_b200 import backbone, net
     bw = backbone.make_vgg16_weights(seed=5, width_div=8)                 # conv5_3 has 64 channels

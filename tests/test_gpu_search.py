@@ -92,6 +92,48 @@ def test_search_matches_reference_golden(dev, golden, name, merge_root):
             np.testing.assert_allclose(boxes[i], ref, rtol=1e-5, atol=1e-5)
 
 
+TUNE_CASES = ["train_375x500", "train_voc_600x1000", "tz05_480x640", "stop_early_333x500"]
+
+
+@pytest.mark.parametrize("name", TUNE_CASES)
+def test_tune_search_matches_reference_golden(dev, golden, name):
+    """SearchEngine(tune=True) = the reference's diagnostic im_propose (lib/detect/tune.py:256-316): K levels, Tz = 0
+    at the first, anchor history bit for bit (regions f64, zoom scores f32-exact)."""
+    from aznet_b200 import engine
+    g = golden["tune"]
+    H, W, max_size, bs, tz, rate, nprop = g[name + "_cfg"]
+    n_img = 2
+    eng = engine.SearchEngine(_FakeHead(dev), n_img, int(H), int(W), max_size=int(max_size), batch_size=int(bs), tz=float(tz),
+                              fixed_num=True, num_proposals=int(nprop), tune=True)
+    assert eng.n_levels == eng.K and not eng.merge_root
+    boxes, scores, n_eval, depth = _drive_with_hashnet(eng, synth.HashNet(seed=11, zoom_rate=float(rate)), n_img)
+    hist = eng.history()
+    ref_h, ref_y = g[name + "_Bhis"], g[name + "_Y5"]
+    for i in range(n_img):
+        assert "{0} proposals, evaluate {1} regions, reaches depth {2}.".format(len(boxes[i]), n_eval[i], depth[i] - 1) == str(g[name + "_log"])
+        assert np.array_equal(hist[i].view(np.uint64), ref_h.view(np.uint64)), "anchor history differs"
+        y5 = np.hstack((boxes[i], scores[i][:, None].astype(np.float64)))
+        if not np.allclose(y5, ref_y, rtol=1e-5, atol=1e-5):
+            np.testing.assert_allclose(y5[np.lexsort(y5.T[::-1])], ref_y[np.lexsort(ref_y.T[::-1])], rtol=1e-5, atol=1e-5)
+
+
+def test_tune_threshold_kernel(dev, golden):
+    """azn_tune_threshold = the reference's heap: k-th highest zoom score, -inf when fewer anchors, ragged counts."""
+    from aznet_b200 import ops
+    rng = np.random.default_rng(5)
+    n, cap = 37, 3000
+    counts = rng.integers(0, cap + 1, n).astype(np.int32)
+    counts[3] = 0
+    z = rng.random((n, cap), dtype=np.float32)
+    z[5, :10] = z[6, :10]                                                # ties across images
+    flat = np.sort(np.concatenate([z[i, :counts[i]] for i in range(n)]))[::-1]
+    zt, ct = torch.from_numpy(z).to(dev), torch.from_numpy(counts).to(dev)
+    for k in (1, 20 * n, len(flat) - 1):
+        assert float(ops.tune_threshold(zt, ct, k).item()) == float(flat[k - 1])
+    assert float(ops.tune_threshold(zt, ct, len(flat)).item()) == -np.inf
+    assert float(ops.tune_threshold(zt, ct, len(flat) + 5).item()) == -np.inf
+
+
 def test_search_levels_match_oracle_trace(dev, O):
     """Regions of every level (order included) are bit-identical to the oracle's B."""
     from aznet_b200 import engine

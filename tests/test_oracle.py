@@ -94,6 +94,45 @@ def test_im_propose_golden(golden, name):
         assert sorted(map(tuple, Y)) == sorted(map(tuple, ref))
 
 
+TUNE_CASES = ["train_375x500", "train_voc_600x1000", "tz05_480x640", "stop_early_333x500"]
+
+
+def _run_tune_case(name, g):
+    H, W, max_size, bs, tz, rate, nprop = g[name + "_cfg"]
+    cfg = O.OracleCfg(TEST_MAX_SIZE=int(max_size), BATCH_SIZE=int(bs), Tz=float(tz), NUM_PROPOSALS=int(nprop))
+    net = synth.HashNet(seed=11, zoom_rate=float(rate))
+    conv = {"conv5_3": np.zeros((1, 1, 2, 2), np.float32)}
+    return O.im_propose_tune({"full": net, "fc": net}, (int(H), int(W), 3), cfg, conv=conv)
+
+
+@pytest.mark.parametrize("name", TUNE_CASES)
+def test_im_propose_tune_golden(golden, name):
+    """The restated diagnostic search equals the reference's own lib/detect/tune.py run (history bit for bit)."""
+    g = golden["tune"]
+    Y5, Bhis, info = _run_tune_case(name, g)
+    assert "{0} proposals, evaluate {1} regions, reaches depth {2}.".format(
+        Y5.shape[0], info["num_eval"], info["depth"]) == str(g[name + "_log"])
+    assert np.array_equal(Bhis.view(np.uint64), g[name + "_Bhis"].view(np.uint64))
+    ref = g[name + "_Y5"]
+    if not np.array_equal(Y5, ref):
+        assert sorted(map(tuple, Y5)) == sorted(map(tuple, ref))
+
+
+def test_tune_thresh_golden(golden):
+    """tune_thresh's heap over six images (three sizes) = the reference's thresh.pkl."""
+    g = golden["tune"]
+    cfg = O.OracleCfg(Tz=0.0, NUM_PROPOSALS=2000)
+    net = synth.HashNet(seed=11, zoom_rate=0.5)
+    conv = {"conv5_3": np.zeros((1, 1, 2, 2), np.float32)}
+    hist = [O.im_propose_tune({"full": net, "fc": net}, (int(h), int(w), 3), cfg, conv=conv)[1] for h, w in g["thresh_shapes"]]
+    assert O.tune_thresh(hist, 20) == float(g["thresh_per20"])
+    assert O.tune_thresh(hist, 1000000) == -np.inf
+    # order-independence, which is what lets the product compute it in one batched device pass
+    assert O.tune_thresh(hist[::-1], 20) == float(g["thresh_per20"])
+    allz = np.sort(np.concatenate([h[:, 4] for h in hist]))[::-1]
+    assert allz[20 * len(hist) - 1] == float(g["thresh_per20"])
+
+
 def test_decode_clip_unwrap_golden(golden):
     g = golden["search"]
     pred = O.bbox_pred(g["bbox_boxes"], g["bbox_deltas"])
