@@ -48,7 +48,7 @@ class VGG16Native:
     def __init__(self, weights: dict, device, pixel_means=PIXEL_MEANS):
         self.dev = torch.device(device)
         self.pixel_means = tuple(float(m) for m in pixel_means)
-        self.layers, self.dims = [], []
+        self.layers, self.dims, self.names = [], [], []
         c_in = None
         for s, (_, n) in enumerate(VGG16_CFG, 1):
             for i in range(1, n + 1):
@@ -56,6 +56,7 @@ class VGG16Native:
                 W = torch.from_numpy(np.ascontiguousarray(W)).to(self.dev)
                 co, ci = W.shape[0], W.shape[1]
                 self.dims.append((ci, co, i == n and s < 5))
+                self.names.append("conv%d_%d" % (s, i))
                 if c_in is None:
                     self.in_channels = ci
                 cop, cip = _pad64(co), _pad64(ci)
@@ -79,16 +80,37 @@ class VGG16Native:
         return total
 
     @torch.no_grad()
-    def run_padded(self, x: torch.Tensor) -> torch.Tensor:
-        """x bf16 [n, Hs+2, Ws+2, cpad_in] zero-bordered -> conv5_3 bf16 NHWC [n, fh, fw, C] (post-ReLU)."""
+    def run_padded(self, x: torch.Tensor, taps=None):
+        """x bf16 [n, Hs+2, Ws+2, cpad_in] zero-bordered -> conv5_3 bf16 NHWC [n, fh, fw, C] (post-ReLU).
+        With `taps` (layer names, e.g. ('conv3_3', 'conv4_3', 'conv5_3') for the skip-layer detector,
+        experiments/cfgs/voc_skip.yml:20) -> dict name -> that layer's post-ReLU map, bf16 NHWC without border."""
         last = len(self.layers) - 1
+        out = {}
         for k, (wt, b, pool) in enumerate(self.layers):
             x = ops.conv3x3(x, wt, b, relu=True, unpadded=(k == last))
+            name = self.names[k]
+            if taps and name in taps:
+                m = x if k == last else ops.nhwc_border(x, to_padded=False)
+                co = self.dims[k][1]
+                out[name] = m if m.shape[3] == co else m[..., :co].contiguous()
             if pool:
                 x = ops.maxpool2x2(x)
+        if taps:
+            missing = [t for t in taps if t not in out]
+            if missing:
+                raise KeyError("unknown backbone layers %s" % missing)
+            return out
         if x.shape[3] != self.out_channels:
             x = x[..., :self.out_channels].contiguous()
         return x
+
+    @torch.no_grad()
+    def taps_from_data(self, data: torch.Tensor, taps):
+        """Caffe's 'data' blob f32 NCHW (device) -> dict layer name -> bf16 NHWC map."""
+        n, c, h, w = data.shape
+        x = torch.zeros((n, h + 2, w + 2, self.cpad_in), dtype=torch.bfloat16, device=data.device)
+        x[:, 1:h + 1, 1:w + 1, :c] = data.permute(0, 2, 3, 1)
+        return self.run_padded(x, taps=tuple(taps))
 
     @torch.no_grad()
     def from_images(self, images: torch.Tensor, im_scale: float) -> torch.Tensor:

@@ -287,6 +287,15 @@ __device__ __forceinline__ float sigmoid_caffe(float x) { return __fdiv_rn(1.f, 
 // thrashed the instruction cache (measured 12 us per 128 x 128 tile instead of ~1).
 // AZN_ACT_AZ_HEAD: columns are [adj_score (nsub) | adj_bbox (4*nsub) | zoom_score (1)]; the two score
 // groups go through the Sigmoid layers adj_prob / zoom_prob (test_fc.prototxt:221-232).
+// Caffe's ReLU is std::max(x, 0) (relu_layer.cpp:16-19), which hands a NaN through (the comparison is false); one
+// FMNMX.NAN instead of the NaN-dropping `v > 0 ? v : 0` -- the skip-layer head's GRN produces NaNs by design for
+// all-zero pooled positions (grn_layer.cpp has no epsilon).
+__device__ __forceinline__ float relu_caffe(float v) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 __device__ __forceinline__ void bias_act32(float (&v)[32], const float *__restrict__ bias, int col0, int N, int act, int nsub) {
     if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
 #pragma unroll
@@ -300,7 +309,7 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float *__restri
     }
     if (act == AZN_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = relu_caffe(v[j]);
     } else if (act == AZN_ACT_AZ_HEAD) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -310,7 +319,7 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float *__restri
     }
 }
 __device__ __forceinline__ float apply_act(float v, int act, int col, int nsub) {
-    if (act == AZN_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == AZN_ACT_RELU) return relu_caffe(v);
     if (act == AZN_ACT_AZ_HEAD) return (col < nsub || col == 5 * nsub) ? sigmoid_caffe(v) : v;
     return v;
 }

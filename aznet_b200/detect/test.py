@@ -231,12 +231,27 @@ def im_propose(net, im, return_conv=False, num_proposals=None):
         full = net['full']
         eng = _engine_for(full, im.shape, num_proposals)
         data, _ = _get_image_blob(im)
-        conv_dev, nhwc = full.conv_from_data(data)
+        names = tuple(cfg.SEAR.FRCNN_CONV)
+        taps = None
+        if return_conv and names != ('conv5_3',):
+            # skip-layer detector (experiments/cfgs/voc_skip.yml:20): hand out conv3_3 / conv4_3 / conv5_3 of the same pass
+            taps = full.backbone.taps_from_data(torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(full.dev),
+                                                tuple(set(names) | {'conv5_3'}))
+            nhwc = taps['conv5_3']
+        else:
+            conv_dev, nhwc = full.conv_from_data(data)
         eng.propose(nhwc)
         boxes, _, n_eval, depth = eng.results()
         Y, num_eval, k = boxes[0], int(n_eval[0]), int(depth[0])
         conv = None
-        if return_conv:
+        if return_conv and taps is not None:
+            conv = {}
+            for name in names:
+                dev = taps[name].permute(0, 3, 1, 2).float().contiguous()
+                host = dev.cpu().numpy()
+                full._maps[name] = ((id(host), host.__array_interface__["data"][0], host.shape), dev, taps[name], host)
+                conv[name] = host
+        elif return_conv:
             host = conv_dev.cpu().numpy()
             full._last_conv = (host, conv_dev, nhwc)
             conv = {name: host for name in cfg.SEAR.FRCNN_CONV}

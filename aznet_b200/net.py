@@ -37,6 +37,29 @@ class FRCNNHeadWeights:
         self.bo = torch.cat([bc, bb], 0).to(device).float().contiguous()
 
 
+class FRCNNSkipHeadWeights(FRCNNHeadWeights):
+    """The skip-layer detector head of models/COCO/VGG16_skip/frcnn/test_fc.prototxt:28-232: ROI pools
+    over conv3_3 / conv4_3 / conv5_3 at 1/4, 1/8, 1/16, GRN each, concat, x1000, conv_pool5 (1x1, + ReLU), then the
+    plain Fast R-CNN fc layers over the c_out-channel pool5.  conv_pool5 is a GEMM over pooled positions; its K is
+    zero-padded to the tensor-core kernel's K granularity (64)."""
+    conv_names = ("conv3_3", "conv4_3", "conv5_3")
+    scales = (0.25, 0.125, 0.0625)
+    grn_scale = 1000.0
+
+    def __init__(self, weights: dict, device, pooled=7):
+        FRCNNHeadWeights.__init__(self, weights, device, pooled)
+        wc, bc = weights["conv_pool5"]
+        wc = torch.from_numpy(np.ascontiguousarray(wc)).reshape(wc.shape[0], -1)
+        ctot = wc.shape[1]
+        self.src_channels = tuple(int(c) for c in weights.get("skip_channels", (ctot // 5, 2 * ctot // 5, 2 * ctot // 5)))
+        assert sum(self.src_channels) == ctot and wc.shape[0] == self.C, "conv_pool5 shape does not match the pools / fc6"
+        self.k_cat = (ctot + 63) // 64 * 64
+        wp = torch.zeros((wc.shape[0], self.k_cat), dtype=torch.float32)
+        wp[:, :ctot] = wc
+        self.wc = wp.to(device).to(torch.bfloat16).contiguous()
+        self.bc = torch.from_numpy(np.ascontiguousarray(bc)).to(device).float().contiguous()
+
+
 class _Blob:
     def __init__(self):
         self.shape = ()
@@ -62,11 +85,16 @@ class Net:
         elif kind == "frcnn":
             self.head = weights if isinstance(weights, FRCNNHeadWeights) else FRCNNHeadWeights(weights, self.dev, pooled)
             self.outputs = ["cls_prob", "bbox_pred"]
+        elif kind == "frcnn_skip":
+            self.head = weights if isinstance(weights, FRCNNSkipHeadWeights) else FRCNNSkipHeadWeights(weights, self.dev, pooled)
+            self.outputs = ["cls_prob", "bbox_pred"]
         else:
-            raise ValueError("kind must be 'az' or 'frcnn'")
-        self.inputs = ["data", "rois"] if backbone is not None else ["conv5_3", "rois"]
-        self.blobs = {k: _Blob() for k in ("data", "rois", "conv5_3")}
+            raise ValueError("kind must be 'az', 'frcnn' or 'frcnn_skip'")
+        self.conv_names = tuple(self.head.conv_names) if kind == "frcnn_skip" else ("conv5_3",)
+        self.inputs = ["data", "rois"] if backbone is not None else list(self.conv_names) + ["rois"]
+        self.blobs = {k: _Blob() for k in ("data", "rois", "conv5_3") + self.conv_names}
         self._conv_key, self._conv_nhwc, self._conv_dev = None, None, None
+        self._maps = {}                         # skip head: name -> (key, f32 NCHW device copy, bf16 NHWC)
 
     # conv maps handed in as host arrays are uploaded once per distinct array (the reference re-uploads
     # the 4.9 MB map on every call, pycaffe.py:90)
@@ -82,11 +110,36 @@ class Net:
         conv = self.backbone(torch.from_numpy(np.ascontiguousarray(data_host, dtype=np.float32)).to(self.dev))
         return conv, ops.nchw_to_nhwc_bf16(conv)
 
-    def heads_device(self, nhwc: torch.Tensor, rois: torch.Tensor):
-        """ROI pool + fc layers on device tensors; returns the f32 output matrix [R, ld]."""
+    def _resident_map(self, name, host: np.ndarray):
+        key = (id(host), host.__array_interface__["data"][0], host.shape)
+        ent = self._maps.get(name)
+        if ent is None or ent[0] != key:
+            dev = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32)).to(self.dev)
+            ent = (key, dev, ops.nchw_to_nhwc_bf16(dev), host)
+            self._maps[name] = ent
+        return ent[2]
+
+    def skip_pool5(self, maps: dict, rois: torch.Tensor, n_rois: torch.Tensor | None = None):
+        """The skip head up to pool5: three ROI pools -> GRN + concat + x1000 -> conv_pool5 (+ReLU).
+        maps: name -> bf16 NHWC; returns bf16 [R, 49 * c_out] (the pooled-row matrix of fc6)."""
+        hd, P = self.head, self.pooled
+        R = rois.shape[0]
+        pooled = [ops.roi_pool(maps[n], rois, P, sc, layout="NHWC", n_rois=n_rois).view(R * P * P, -1)
+                  for n, sc in zip(hd.conv_names, hd.scales)]
+        cat = torch.zeros((R * P * P, hd.k_cat), dtype=torch.bfloat16, device=rois.device)
+        ops.grn_concat(pooled, hd.grn_scale, n_units=n_rois, rows_per_unit=P * P, out=cat)
+        m_live = None if n_rois is None else n_rois * (P * P)
+        return ops.fc_forward(cat, hd.wc, hd.bc, L.ACT_RELU, m_live=m_live).view(R, -1)
+
+    def heads_device(self, nhwc, rois: torch.Tensor):
+        """ROI pool + fc layers on device tensors; returns the f32 output matrix [R, ld].
+        nhwc: the bf16 NHWC conv5_3 map, or for the skip head a dict name -> map."""
         hd = self.head
-        pool = ops.roi_pool(nhwc, rois, self.pooled, self.spatial_scale, layout="NHWC")
-        a = pool.view(pool.shape[0], -1)
+        if self.kind == "frcnn_skip":
+            a = self.skip_pool5(nhwc, rois)
+        else:
+            pool = ops.roi_pool(nhwc, rois, self.pooled, self.spatial_scale, layout="NHWC")
+            a = pool.view(pool.shape[0], -1)
         if self.kind == "az":
             h6 = ops.fc_forward(a, hd.w6, hd.b6, L.ACT_RELU)
             h7 = ops.fc_forward(h6, hd.w7, hd.b7, L.ACT_RELU)
@@ -108,7 +161,16 @@ class Net:
                 raise Exception("Input is not batch sized")                          # pycaffe.py:88-89
         rois_h = np.ascontiguousarray(kwargs["rois"], dtype=np.float32)
         out, conv_host = {}, None
-        if self.backbone is not None:
+        skip_hosts = None
+        if self.kind == "frcnn_skip":
+            if self.backbone is not None:
+                data = torch.from_numpy(np.ascontiguousarray(kwargs["data"], dtype=np.float32)).to(self.dev)
+                nhwc = self.backbone.taps_from_data(data, self.conv_names)
+            else:
+                nhwc = {n: self._resident_map(n, kwargs[n]) for n in self.conv_names}
+                skip_hosts = {n: kwargs[n] for n in self.conv_names}
+            conv_dev = None
+        elif self.backbone is not None:
             conv_dev, nhwc = self.conv_from_data(kwargs["data"])
         else:
             conv_host = kwargs["conv5_3"]
@@ -129,7 +191,16 @@ class Net:
             out["cls_prob"] = np.ascontiguousarray(res[:, :c])
             out["bbox_pred"] = np.ascontiguousarray(res[:, c:5 * c])
         for b in (blobs or []):
-            if b == "conv5_3":
+            if self.kind == "frcnn_skip" and b in self.conv_names:
+                if skip_hosts is None:                     # maps computed by the backbone: hand them out as Caffe blobs
+                    skip_hosts = {}
+                if b not in skip_hosts:
+                    dev = nhwc[b].permute(0, 3, 1, 2).float().contiguous()
+                    skip_hosts[b] = dev.cpu().numpy()
+                    self._maps[b] = ((id(skip_hosts[b]), skip_hosts[b].__array_interface__["data"][0], skip_hosts[b].shape),
+                                     dev, nhwc[b], skip_hosts[b])
+                out[b] = skip_hosts[b]
+            elif b == "conv5_3":
                 if conv_host is None:
                     conv_host = conv_dev.cpu().numpy()
                     # remember the upload so that handing this array back to the 'fc' net costs nothing
@@ -141,6 +212,9 @@ class Net:
 
     def adopt_conv(self, other: "Net"):
         """Share the device copy of a conv map produced by another net's forward (full -> fc hand-over)."""
+        for name, ent in getattr(other, "_maps", {}).items():
+            if name in self.conv_names and self.kind == "frcnn_skip":
+                self._maps[name] = ent
         last = getattr(other, "_last_conv", None)
         if last is not None:
             host, dev, nhwc = last

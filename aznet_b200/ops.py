@@ -161,6 +161,26 @@ def detect_thresholds(top_scores: torch.Tensor, det_count: torch.Tensor, max_per
     return out
 
 
+def grn_concat(pooled: list, scale: float = 1000.0, n_units: torch.Tensor | None = None, rows_per_unit: int = 49,
+               out: torch.Tensor | None = None):
+    """GRN of every source + channel concat + Power scale (VGG16_skip test_fc.prototxt:39-110, grn_layer.cpp:27-56).
+    pooled: list of bf16 [rows, C_l] (pooled positions x channels).  Returns bf16 [rows, sum C_l]."""
+    import ctypes as C
+    _need_cuda(*pooled, n_units)
+    rows = pooled[0].shape[0]
+    for t in pooled:
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.dim() == 2 and t.shape[0] == rows
+    ctot = sum(int(t.shape[1]) for t in pooled)
+    if out is None:
+        out = torch.empty((rows, ctot), dtype=torch.bfloat16, device=pooled[0].device)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[0] == rows and out.shape[1] >= ctot
+    ptrs = (C.c_void_p * len(pooled))(*[t.data_ptr() for t in pooled])
+    chans = (C.c_int32 * len(pooled))(*[int(t.shape[1]) for t in pooled])
+    L.check(L.lib().azn_grn_concat_forward(ptrs, chans, len(pooled), _ptr(n_units), rows, int(rows_per_unit), float(scale),
+                                           _ptr(out), int(out.shape[1]), _stream()), "azn_grn_concat_forward")
+    return out
+
+
 def tune_threshold(zoom: torch.Tensor, counts: torch.Tensor, max_per_set: int):
     """tune_thresh's zoom threshold (lib/detect/tune.py:318-366): the max_per_set-th highest anchor zoom score of the
     image set, -inf when fewer anchors were seen.  zoom f32 [n, cap], counts int32 [n].  Returns f32 [1]."""

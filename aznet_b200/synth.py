@@ -51,6 +51,18 @@ def make_frcnn_weights(seed=4, num_classes=21, C=512, pooled=7, h6=4096, h7=4096
     return w
 
 
+def make_frcnn_skip_weights(seed=4, num_classes=21, channels=(256, 512, 512), c_out=512, pooled=7, h6=4096, h7=4096):
+    """The skip-layer detector head (models/COCO/VGG16_skip/frcnn/test_fc.prototxt): the Fast R-CNN fc weights over a
+    c_out-channel pool5 plus conv_pool5, the 1x1 convolution over the GRN-normalised, x1000-scaled concat of the three
+    ROI pools -- gaussian std 0.001 like its weight_filler (test_fc.prototxt:124-131), which gives O(1) activations."""
+    w = make_frcnn_weights(seed, num_classes, C=c_out, pooled=pooled, h6=h6, h7=h7)
+    rng = np.random.default_rng(seed + 1000)
+    ctot = int(sum(channels))
+    w["conv_pool5"] = (_normal(rng, (c_out, ctot, 1, 1), 0.001), np.zeros((c_out,), np.float32))
+    w["skip_channels"] = tuple(int(c) for c in channels)
+    return w
+
+
 def conv_shape(im_h, im_w, im_scale=1.0):
     """conv5_3 spatial size of VGG16 for a scaled image: four ceil-mode 2x2/2 max-pools
     (caffe-fast-rcnn/src/caffe/layers/pooling_layer.cpp:93-95), 3x3 pad-1 convs keep size."""

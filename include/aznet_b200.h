@@ -323,6 +323,20 @@ int azn_maxpool2x2_forward(const void *in_padded, int n_img, int H, int W, int C
                            azn_stream_t stream);
 int azn_nhwc_border(const void *in, int n_img, int H, int W, int C, void *out, int to_padded, azn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The skip-layer detector head: models/COCO/VGG16_skip/frcnn/test_fc.prototxt:28-135.
+ * azn_grn_concat_forward  replaces: GRNLayer::Forward (caffe-fast-rcnn/src/caffe/layers/grn_layer.cpp:27-56) of
+ *   roi_norm3/4/5 + ConcatLayer (axis 1) + PowerLayer (scale 1000, power 1, shift 0).
+ *   pooled[l] bf16 [rows, channels[l]]: the NHWC output of azn_roi_pool_fwd over map l seen as rows of pooled
+ *   positions (rows = R * PH * PW); out bf16 [rows, ld_out], ld_out >= sum channels (columns past the sum are
+ *   left untouched: zero them once when K must be padded for the GEMM):  out[r, off_l + c] = scale * (x / sqrt(sum_c x^2)),
+ *   each source normalised on its own.  n_units (device, may be NULL) = live ROI count, rows_per_unit = PH * PW:
+ *   only n_units * rows_per_unit rows are processed.  `pooled` and `channels` are HOST arrays of n_src <= 4 entries.
+ *   The 1x1 convolution conv_pool5 (+ReLU) that follows is azn_fc_forward over the same rows (K = sum channels,
+ *   N = 512): its output [rows, 512] is the [R, PH*PW*512] pooled-row matrix of fc6. */
+int azn_grn_concat_forward(const void *const *pooled, const int32_t *channels, int n_src, const int32_t *n_units,
+                           long long rows_cap, int rows_per_unit, float scale, void *out, int ld_out, azn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,6 +140,34 @@ def relu(x):
     return np.maximum(x, np.float32(0))
 
 
+def grn(x):
+    """GRNLayer::Forward_cpu, caffe-fast-rcnn/src/caffe/layers/grn_layer.cpp:27-56, on a blob [N, C, H, W]:
+    square (caffe_sqr), sum across channels (caffe_cpu_gemv with a ones vector; fp32, BLAS summation order),
+    root (caffe_powx 0.5), divide every channel by the per-position norm (caffe_div).  No epsilon: an all-zero
+    position yields 0/0 = NaN, as in the reference."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    sq = x * x
+    norm = np.power(sq.sum(axis=1, dtype=np.float32, keepdims=True), np.float32(0.5)).astype(np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (x / norm).astype(np.float32)
+
+
+def skip_pool5(w, maps, rois, pooled=7, scales=(0.25, 0.125, 0.0625), names=("conv3_3", "conv4_3", "conv5_3"), act_round=None,
+               threads=None):
+    """models/COCO/VGG16_skip/frcnn/test_fc.prototxt:28-142: roi_pool{3,4,5} -> GRN -> concat (axis 1) -> Power
+    (scale 1000) -> conv_pool5 (1x1 convolution = per-position inner product over channels) -> ReLU.
+    Returns pool5 [R, c_out, 7, 7] float32.  act_round (e.g. round_bf16) emulates the product's bf16 storage of the
+    concat operand."""
+    rnd = act_round or (lambda v: v)
+    cat = np.concatenate([grn(roi_pool_fwd(maps[n], rois, pooled, sc)) for n, sc in zip(names, scales)], axis=1)
+    cat = rnd((cat * np.float32(1000.0)).astype(np.float32))                     # power_layer.cpp: y = scale * x (power 1)
+    R, ctot = cat.shape[0], cat.shape[1]
+    wc, bc = w["conv_pool5"]
+    x = cat.transpose(0, 2, 3, 1).reshape(R * pooled * pooled, ctot)            # one row per pooled position
+    y = relu(inner_product(x, wc.reshape(wc.shape[0], ctot), bc, threads))
+    return np.ascontiguousarray(y.reshape(R, pooled, pooled, -1).transpose(0, 3, 1, 2))
+
+
 def round_bf16(x):
     """float32 -> nearest-even bfloat16 -> float32 (the storage format of the product's activations)."""
     u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
@@ -180,9 +208,10 @@ class OracleNet:
         self.name = name
         self.cfg = cfg or OracleCfg()
         self.threads = threads
-        self.inputs = ["data", "rois"] if backbone is not None else ["conv5_3", "rois"]
+        self.conv_names = ["conv3_3", "conv4_3", "conv5_3"] if kind == "frcnn_skip" else ["conv5_3"]
+        self.inputs = ["data", "rois"] if backbone is not None else self.conv_names + ["rois"]
         self.outputs = ["zoom_prob", "adj_prob", "adj_bbox"] if kind == "az" else ["cls_prob", "bbox_pred"]
-        self.blobs = {k: _Blob() for k in self.inputs + ["conv5_3"]}
+        self.blobs = {k: _Blob() for k in self.inputs + self.conv_names}
         self.stats = {"pool_s": 0.0, "fc_s": 0.0}
 
     def forward(self, blobs=None, **kwargs):
@@ -193,9 +222,14 @@ class OracleNet:
             if v.shape[0] != self.blobs[k].num:
                 raise Exception("Input is not batch sized")
         rois = kwargs["rois"]
-        conv = self.backbone(kwargs["data"]) if self.backbone is not None else kwargs["conv5_3"]
         t0 = time.perf_counter()
-        pool5 = roi_pool_fwd(conv, rois, self.cfg.POOLED, self.cfg.SPATIAL_SCALE)
+        if self.kind == "frcnn_skip":
+            # the skip-layer detector: `backbone` returns a dict of the three maps (test.prototxt of VGG16_skip)
+            conv = self.backbone(kwargs["data"]) if self.backbone is not None else {n: kwargs[n] for n in self.conv_names}
+            pool5 = skip_pool5(self.w, conv, rois, self.cfg.POOLED, act_round=self.act_round, threads=self.threads)
+        else:
+            conv = self.backbone(kwargs["data"]) if self.backbone is not None else kwargs["conv5_3"]
+            pool5 = roi_pool_fwd(conv, rois, self.cfg.POOLED, self.cfg.SPATIAL_SCALE)
         t1 = time.perf_counter()
         x = pool5.reshape(pool5.shape[0], -1)            # K index = c*49 + ph*7 + pw (Q12)
         ip = lambda name, v: inner_product(v, self.w[name][0], self.w[name][1], self.threads)
@@ -216,7 +250,9 @@ class OracleNet:
         self.stats["pool_s"] += t1 - t0
         self.stats["fc_s"] += time.perf_counter() - t1
         for b in (blobs or []):
-            if b == "conv5_3":
+            if self.kind == "frcnn_skip" and b in self.conv_names:
+                out[b] = conv[b]
+            elif b == "conv5_3":
                 out[b] = conv
             elif b == "pool5":
                 out[b] = pool5
