@@ -351,7 +351,15 @@ _DET_ENGINES = {}
 
 def _fast_detect_route(net, key='full'):
     n = net.get(key) if hasattr(net, 'get') else None
-    return isinstance(n, Net) and n.kind == "frcnn" and len(cfg.TEST.SCALES) == 1 and (key == 'fc' or n.backbone is not None)
+    return (isinstance(n, Net) and n.kind in ("frcnn", "frcnn_skip") and len(cfg.TEST.SCALES) == 1
+            and (key == 'fc' or n.backbone is not None))
+
+
+def _maps_from_data(full: Net, data, names):
+    """The bf16 NHWC maps a detector needs from one backbone pass: conv5_3 alone, or the skip-layer taps as a dict."""
+    if tuple(names) == ('conv5_3',):
+        return full.conv_from_data(data)[1]
+    return full.backbone.taps_from_data(torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(full.dev), tuple(names))
 
 
 def _det_engine_for(fr_net: Net, im_shape, cap):
@@ -483,7 +491,7 @@ def test_net(net, prop_file, imdb):
         _t['im_detect'].tic()
         if fast:
             data, _ = _get_image_blob(im)
-            _, nhwc = net['full'].conv_from_data(data)
+            nhwc = _maps_from_data(net['full'], data, net['full'].conv_names)
             _detect_on_device(net['full'], nhwc, im.shape, prop_boxes[i], dset, i)
             torch.cuda.current_stream().synchronize()
             num_boxes += prop_boxes[i].shape[0]
@@ -531,9 +539,14 @@ def test_net_shared(sc_net, frcnn_net, imdb):
             full = sc_net['full']
             eng = _engine_for(full, im.shape, None)
             data, _ = _get_image_blob(im)
-            _, nhwc = full.conv_from_data(data)
-            eng.propose(nhwc)
-            _detect_on_device(frcnn_net['fc'], nhwc, im.shape, (eng.out_boxes, eng.out_count), dset, i)
+            fr = frcnn_net['fc']
+            if fr.kind == "frcnn_skip":          # one backbone pass serves the search (conv5_3) and the three ROI pools
+                nhwc = _maps_from_data(full, data, tuple(dict.fromkeys(fr.conv_names + ('conv5_3',))))
+                eng.propose(nhwc['conv5_3'])
+            else:
+                nhwc = _maps_from_data(full, data, ('conv5_3',))
+                eng.propose(nhwc)
+            _detect_on_device(fr, nhwc, im.shape, (eng.out_boxes, eng.out_count), dset, i)
             n_prop, n_eval, depth = int(eng.out_count[0].item()), int(eng.n_eval[0].item()), int(eng.depth[0].item())
             print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(n_prop, n_eval, depth))
             num_boxes += n_prop

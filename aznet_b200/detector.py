@@ -53,6 +53,13 @@ class DetectEngine:
         self.pool5 = torch.empty((m_cap, k6), dtype=torch.bfloat16, device=dev)
         self.h6 = torch.empty((m_cap, head.w6.shape[0]), dtype=torch.bfloat16, device=dev)
         self.h7 = torch.empty((m_cap, head.w7.shape[0]), dtype=torch.bfloat16, device=dev)
+        # skip-layer head: three pooled-position matrices, their normalised concat, the live row count
+        self.skip = hasattr(head, "conv_names")
+        if self.skip:
+            P2 = head.pooled * head.pooled
+            self.pooled_src = [torch.empty((m_cap * P2, c), dtype=torch.bfloat16, device=dev) for c in head.src_channels]
+            self.cat = torch.zeros((m_cap * P2, head.k_cat), dtype=torch.bfloat16, device=dev)
+            self.m_rows = z(1)
         self.n_out = 5 * Cc
         self.ld = (self.n_out + 3) // 4 * 4
         self.out = torch.zeros((m_cap, self.ld), dtype=torch.float32, device=dev)
@@ -81,13 +88,31 @@ class DetectEngine:
         L.check(L.lib().azn_detect_rois(C.byref(st), ops._stream()), "azn_detect_rois")
         self.launches += 2
 
-    def run_head(self, conv_nhwc: torch.Tensor):
-        """ROI pool (staged kernel: ~300 ROIs per image) + fc6 / fc7 / [cls_score | bbox_pred] with softmax."""
+    def _skip_pool5(self, maps: dict):
+        """roi_pool{3,4,5} -> GRN + concat + x1000 -> conv_pool5 (+ReLU) into self.pool5 (VGG16_skip test_fc.prototxt:28-142)."""
         hd = self.head
-        assert conv_nhwc.dtype == torch.bfloat16 and conv_nhwc.shape[0] == self.n_img and conv_nhwc.is_contiguous()
+        mc, P = self.n_img * self.cap, hd.pooled
+        for name, sc, buf in zip(hd.conv_names, hd.scales, self.pooled_src):
+            m = maps[name]
+            assert m.dtype == torch.bfloat16 and m.shape[0] == self.n_img and m.is_contiguous()
+            ops.roi_pool(m, self.rois, P, sc, layout="NHWC", n_rois=self.m_total, out=buf.view(mc, P, P, buf.shape[1]), staged=True)
+        ops.grn_concat(self.pooled_src, hd.grn_scale, n_units=self.m_total, rows_per_unit=P * P, out=self.cat)
+        torch.mul(self.m_total, P * P, out=self.m_rows)
+        ops.fc_forward(self.cat, hd.wc, hd.bc, L.ACT_RELU, m_live=self.m_rows, out=self.pool5.view(mc * P * P, hd.C))
+        self.launches += 3 * 3 + 1 + 1 + 2
+        return self.pool5
+
+    def run_head(self, conv_nhwc):
+        """ROI pool (staged kernel: ~300 ROIs per image) + fc6 / fc7 / [cls_score | bbox_pred] with softmax.
+        conv_nhwc: the bf16 NHWC conv5_3 maps, or for the skip-layer head a dict name -> maps."""
+        hd = self.head
         mc = self.n_img * self.cap
-        pool = ops.roi_pool(conv_nhwc, self.rois, hd.pooled, self.spatial_scale, layout="NHWC", n_rois=self.m_total,
-                            out=self.pool5.view(mc, hd.pooled, hd.pooled, hd.C), staged=True)
+        if self.skip:
+            pool = self._skip_pool5(conv_nhwc)
+        else:
+            assert conv_nhwc.dtype == torch.bfloat16 and conv_nhwc.shape[0] == self.n_img and conv_nhwc.is_contiguous()
+            pool = ops.roi_pool(conv_nhwc, self.rois, hd.pooled, self.spatial_scale, layout="NHWC", n_rois=self.m_total,
+                                out=self.pool5.view(mc, hd.pooled, hd.pooled, hd.C), staged=True)
         ops.fc_forward(pool.view(mc, -1), hd.w6, hd.b6, L.ACT_RELU, m_live=self.m_total, out=self.h6)
         ops.fc_forward(self.h6, hd.w7, hd.b7, L.ACT_RELU, m_live=self.m_total, out=self.h7)
         ops.fc_forward(self.h7, hd.wo, hd.bo, L.ACT_SOFTMAX_BBOX, self.C, m_live=self.m_total, out=self.out[:, :self.n_out])

@@ -173,3 +173,63 @@ def test_skip_shared_detection_dropin(dev, O, capsys):
         cfg.SEAR.FRCNN_CONV, cfg.DEDUP_BOXES = saved
         C.cfg_set_mode("Test", 0.5)
     capsys.readouterr()
+
+
+def test_skip_drivers_device_route_equals_host_route(dev, tmp_path, capsys):
+    """test_net / test_net_shared with the skip-layer detector: DetectEngine's skip head (three staged/direct ROI pools,
+    azn_grn_concat_forward, conv_pool5 GEMM with a device-side live row count) against the reference's host loop over
+    the same Net objects."""
+    import os
+    import pickle
+    import cv2
+    from aznet_b200 import net
+    from aznet_b200.detect import config as C
+    from aznet_b200.detect import test as T
+    nets, w, bb = _skip_setup(dev)
+    azw = synth.make_az_weights(seed=3, C=64, h6=256, h71=96, h72=32, zoom_bias=0.0)
+    az = {"full": net.Net(azw, "az", backbone=bb, name="az_small"), "fc": net.Net(azw, "az", name="az_small")}
+    cfg = C.cfg
+    saved = (list(cfg.SEAR.FRCNN_CONV), cfg.DEDUP_BOXES, cfg.ROOT_DIR)
+    cfg.SEAR.FRCNN_CONV, cfg.DEDUP_BOXES = ["conv3_3", "conv4_3", "conv5_3"], 0.5
+    C.cfg_set_path("pytest_skip")
+    C.cfg_set_mode("Test", 0.5)
+    try:
+        paths = []
+        for i, im in enumerate(synth.make_images(3, 200, 300, seed=70)):
+            p = str(tmp_path / ("im%d.png" % i))
+            cv2.imwrite(p, im)
+            paths.append(p)
+        cfg.ROOT_DIR = str(tmp_path)
+        imdb = synth.SyntheticImdb(paths, num_classes=6)
+        T.test_proposals(az, imdb)
+        prop_file = os.path.join(C.get_output_dir(imdb, az["full"]), "proposals.pkl")
+        det_file = os.path.join(C.get_output_dir(imdb, nets["full"]), "detections.pkl")
+
+        class Foreign(dict):
+            pass
+        wrap = lambda n: type("W", (), {"forward": n.forward, "blobs": n.blobs, "name": n.name})()
+
+        def run(dn, shared):
+            if shared:
+                T.test_net_shared(az, dn, imdb)
+            else:
+                T.test_net(dn, prop_file, imdb)
+            capsys.readouterr()
+            return pickle.load(open(det_file, "rb")), imdb.evaluated[0]
+
+        total = 0
+        for shared in (False, True):
+            pre_d, nms_d = run(nets, shared)
+            pre_h, nms_h = run(Foreign(full=wrap(nets["full"]), fc=wrap(nets["fc"])), shared)
+            for a_set, b_set in ((pre_d, pre_h), (nms_d, nms_h)):
+                for j in range(1, 6):
+                    for i in range(3):
+                        a, b = a_set[j][i], b_set[j][i]
+                        assert len(a) == len(b), (shared, j, i, len(a), len(b))
+                        total += len(a)
+                        if len(a):
+                            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-4)
+        assert total > 50
+    finally:
+        cfg.SEAR.FRCNN_CONV, cfg.DEDUP_BOXES, cfg.ROOT_DIR = saved
+        C.cfg_set_mode("Test", 0.5)
