@@ -92,11 +92,29 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
 // L = vectors per map cell (C * sizeof(T) / 16).
 constexpr int POOL_MAX_PW = 32;
 
-template <typename Ops, int NV>
+// GRN = true (bf16 only, L <= 32 * NV so that one warp holds every channel of its bin): the skip-layer head's
+// roi_norm + concat + Power epilogue (VGG16_skip test_fc.prototxt:39-110, grn_layer.cpp:27-56) fused into the pool --
+// the warp sums the squares of its bin's channels (float32; a bf16 square is exact), and writes
+// grn_scale * (x / sqrt(sum)) at channel-vector offset out_off of a row of out_ld vectors (the concat buffer).
+__device__ __forceinline__ float sq_pair(unsigned u) {
+    const float lo = __uint_as_float(u << 16), hi = __uint_as_float(u & 0xffff0000u);
+    return __fadd_rn(__fmul_rn(lo, lo), __fmul_rn(hi, hi));
+}
+__device__ __forceinline__ unsigned grn_pair(unsigned u, float inv) {
+    // inv = scale / norm, one IEEE division per pooled position.  The reference rounds scale * (x / norm) twice in
+    // float32; x * inv differs from it by at most ~1.5 float32 ulp, far below the bf16 rounding (2^-9) of the operand.
+    const float a = __fmul_rn(__uint_as_float(u << 16), inv);
+    const float b = __fmul_rn(__uint_as_float(u & 0xffff0000u), inv);
+    const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const unsigned *>(&r);
+}
+
+template <typename Ops, int NV, bool GRN = false>
 __global__ void __launch_bounds__(256)
 roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
-                     int PH, int PW, float scale, uint4 *__restrict__ out) {
+                     int PH, int PW, float scale, uint4 *__restrict__ out, int out_ld = 0, int out_off = 0,
+                     float grn_scale = 1.f) {
     pdl_enter();
     __shared__ int s_ws[2][POOL_MAX_PW], s_we[2][POOL_MAX_PW], s_row[2][3];
     const int R = n_rois ? min(*n_rois, R_cap) : R_cap;
@@ -124,11 +142,14 @@ roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         __syncthreads();                          // double-buffered geometry: one barrier per item
         const int hs = s_row[buf][0], he = s_row[buf][1], b = s_row[buf][2];
         const uint4 *base = feat + (size_t)(b < 0 ? 0 : b) * H * row_stride;
-        uint4 *orow = out + (size_t)it * PW * L;
+        const int ld = GRN ? out_ld : L;
+        uint4 *orow = out + (size_t)it * PW * ld + (GRN ? out_off : 0);
         for (int pw = warp; pw < PW; pw += nwarps) {
             const int ws = s_ws[buf][pw], we = s_we[buf][pw];
             const bool empty = b < 0 || he <= hs || we <= ws;
-            for (int v0 = lane; v0 < L; v0 += 32 * NV) {
+            // GRN: every lane runs exactly one pass (the warp-wide sum needs all 32 lanes; loads/stores stay guarded)
+            const int vend = GRN ? 32 : L;
+            for (int v0 = lane; v0 < vend; v0 += 32 * NV) {
                 uint4 acc[NV];
 #pragma unroll
                 for (int j = 0; j < NV; ++j) acc[j] = empty ? make_uint4(0u, 0u, 0u, 0u) : Ops::lowest();
@@ -143,9 +164,25 @@ roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                         }
                     }
                 }
+                if (GRN) {
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        if (v0 + 32 * j < L)
+                            ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(sq_pair(acc[j].x), sq_pair(acc[j].y)),
+                                                         __fadd_rn(sq_pair(acc[j].z), sq_pair(acc[j].w))));
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, d));
+                    const float inv = __fdiv_rn(grn_scale, sqrtf(ss));
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        acc[j].x = grn_pair(acc[j].x, inv); acc[j].y = grn_pair(acc[j].y, inv);
+                        acc[j].z = grn_pair(acc[j].z, inv); acc[j].w = grn_pair(acc[j].w, inv);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < NV; ++j)
-                    if (v0 + 32 * j < L) st_stream(orow + (size_t)pw * L + v0 + 32 * j, acc[j]);
+                    if (v0 + 32 * j < L) st_stream(orow + (size_t)pw * ld + v0 + 32 * j, acc[j]);
             }
         }
     }
@@ -828,7 +865,7 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         const uint4 *f = (const uint4 *)feat;
         uint4 *o = (uint4 *)out;
 #define AZN_POOL_LAUNCH(OPS, NVV) \
-        AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_kernel<OPS, NVV>, dim3((unsigned)blocks), dim3(nwarps * 32), 0, s, f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o))
+        AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_kernel<OPS, NVV>, dim3((unsigned)blocks), dim3(nwarps * 32), 0, s, f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o, 0, 0, 1.f))
         if (dtype == AZN_DTYPE_F32) {
             if (nv == 4) AZN_POOL_LAUNCH(OpsF32, 4); else if (nv == 2) AZN_POOL_LAUNCH(OpsF32, 2); else AZN_POOL_LAUNCH(OpsF32, 1);
         } else {
@@ -892,6 +929,37 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
             (__nv_bfloat16 *)out);
     }
     AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+// ROI max-pool + GRN + concat offset + Power scale in one kernel (the skip-layer head).
+extern "C" int azn_roi_pool_grn_fwd(const void *feat, int n_img, int C, int H, int W, const float *rois, const int32_t *n_rois,
+                                    int R_cap, int PH, int PW, float spatial_scale, float grn_scale, void *out, int ld_out,
+                                    int ch_off, azn_stream_t stream) {
+    if (R_cap == 0) return AZN_OK;
+    AZN_REQUIRE(feat && rois && out, "azn_roi_pool_grn_fwd: null pointer");
+    AZN_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R_cap > 0,
+                "azn_roi_pool_grn_fwd: bad shape n_img=%d C=%d H=%d W=%d PH=%d PW=%d R=%d", n_img, C, H, W, PH, PW, R_cap);
+    AZN_REQUIRE(C % 8 == 0 && C <= 1024, "azn_roi_pool_grn_fwd: C=%d must be a multiple of 8 and <= 1024 (one warp holds a bin's channels)", C);
+    AZN_REQUIRE(ld_out % 8 == 0 && ch_off % 8 == 0 && ch_off >= 0 && ch_off + C <= ld_out,
+                "azn_roi_pool_grn_fwd: ld_out=%d / ch_off=%d must be multiples of 8 with ch_off + C <= ld_out", ld_out, ch_off);
+    AZN_REQUIRE(((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0), "azn_roi_pool_grn_fwd: 16-byte alignment");
+    AZN_REQUIRE((double)R_cap * PH < 2.0e9 && PW <= POOL_MAX_PW, "azn_roi_pool_grn_fwd: too many ROI rows / pooled width > %d", POOL_MAX_PW);
+    const int L = C / 8;
+    const long items = (long)R_cap * PH;
+    const int nwarps = PW < 8 ? PW : 8;
+    long blocks = items;
+    const long max_blocks = (long)azn_num_sms() * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    const int nv = L > 64 ? 4 : (L > 32 ? 2 : 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint4 *f = (const uint4 *)feat;
+    uint4 *o = (uint4 *)out;
+#define AZN_GRN_LAUNCH(NVV) \
+    AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_kernel<OpsBF16, NVV, true>, dim3((unsigned)blocks), dim3(nwarps * 32), 0, s, f, n_img, H, W, L, \
+                            rois, n_rois, R_cap, PH, PW, spatial_scale, o, ld_out / 8, ch_off / 8, grn_scale))
+    if (nv == 4) AZN_GRN_LAUNCH(4); else if (nv == 2) AZN_GRN_LAUNCH(2); else AZN_GRN_LAUNCH(1);
+#undef AZN_GRN_LAUNCH
     return AZN_OK;
 }
 

@@ -13,14 +13,15 @@
 // [R, 49 * 512] pooled-row matrix that fc6 consumes.
 //
 // Arithmetic: the sum of squares runs in float32 (each bf16 square is exact in float32), norm = sqrtf(sum),
-// y = 1000 * (x / norm) with IEEE float division and multiplication in the reference's order, rounded once to
-// bf16 for the tensor-core operand.  A position whose channels are all zero divides 0 by 0 exactly like the
+// y = x * (1000 / norm) -- one IEEE division per position instead of one per element; the reference's
+// 1000 * (x / norm) differs by at most ~1.5 float32 ulp, which the single bf16 rounding of the tensor-core operand
+// (2^-9) hides but for rare ties.  A position whose channels are all zero divides 0 by 0 exactly like the
 // reference (NaN): the layer has no epsilon.
 #include "common.cuh"
 
 namespace {
 
-constexpr int GRN_MAX_SRC = 4;
+constexpr int GRN_MAX_SRC = 8;
 constexpr int GRN_MAX_VPL = 4;          // 16-byte vectors per lane per source: C <= 1024 channels per source
 
 struct GrnArgs {
@@ -34,9 +35,16 @@ struct GrnArgs {
 __device__ __forceinline__ float bf_lo(unsigned u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(unsigned u) { return __uint_as_float(u & 0xffff0000u); }
 
-__device__ __forceinline__ unsigned grn_pair(unsigned u, float norm, float scale) {
-    const float a = __fmul_rn(scale, __fdiv_rn(bf_lo(u), norm));
-    const float b = __fmul_rn(scale, __fdiv_rn(bf_hi(u), norm));
+__device__ __forceinline__ float sq_pair(unsigned u) {
+    const float lo = bf_lo(u), hi = bf_hi(u);
+    return __fadd_rn(__fmul_rn(lo, lo), __fmul_rn(hi, hi));
+}
+
+__device__ __forceinline__ unsigned grn_pair(unsigned u, float inv) {
+    // inv = scale / norm, one IEEE division per pooled position.  The reference rounds scale * (x / norm) twice in
+    // float32; x * inv differs from it by at most ~1.5 float32 ulp, far below the bf16 rounding (2^-9) of the operand.
+    const float a = __fmul_rn(__uint_as_float(u << 16), inv);
+    const float b = __fmul_rn(__uint_as_float(u & 0xffff0000u), inv);
     const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const unsigned *>(&r);
 }
@@ -63,25 +71,20 @@ grn_concat_kernel(GrnArgs a, const int32_t *__restrict__ n_units, long rows_cap,
                 const int i = lane + 32 * q;
                 v[q] = make_uint4(0u, 0u, 0u, 0u);
                 if (i < nv) v[q] = __ldg(p + i);
-                const unsigned w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float lo = bf_lo(w[t]), hi = bf_hi(w[t]);
-                    ss = __fadd_rn(ss, __fmul_rn(lo, lo));
-                    ss = __fadd_rn(ss, __fmul_rn(hi, hi));
-                }
+                // the same summation order as the fused epilogue of azn_roi_pool_grn_fwd (roi_pool.cu): bit-identical results
+                if (i < nv) ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(sq_pair(v[q].x), sq_pair(v[q].y)), __fadd_rn(sq_pair(v[q].z), sq_pair(v[q].w))));
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, d));
-            const float norm = sqrtf(ss);
+            const float inv = __fdiv_rn(scale, sqrtf(ss));
             uint4 *o = out + row * a.out_vec + a.off[l];
 #pragma unroll
             for (int q = 0; q < GRN_MAX_VPL; ++q) {
                 const int i = lane + 32 * q;
                 if (i < nv) {
                     uint4 r;
-                    r.x = grn_pair(v[q].x, norm, scale); r.y = grn_pair(v[q].y, norm, scale);
-                    r.z = grn_pair(v[q].z, norm, scale); r.w = grn_pair(v[q].w, norm, scale);
+                    r.x = grn_pair(v[q].x, inv); r.y = grn_pair(v[q].y, inv);
+                    r.z = grn_pair(v[q].z, inv); r.w = grn_pair(v[q].w, inv);
                     o[i] = r;
                 }
             }

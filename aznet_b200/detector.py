@@ -57,7 +57,6 @@ class DetectEngine:
         self.skip = hasattr(head, "conv_names")
         if self.skip:
             P2 = head.pooled * head.pooled
-            self.pooled_src = [torch.empty((m_cap * P2, c), dtype=torch.bfloat16, device=dev) for c in head.src_channels]
             self.cat = torch.zeros((m_cap * P2, head.k_cat), dtype=torch.bfloat16, device=dev)
             self.m_rows = z(1)
         self.n_out = 5 * Cc
@@ -89,17 +88,19 @@ class DetectEngine:
         self.launches += 2
 
     def _skip_pool5(self, maps: dict):
-        """roi_pool{3,4,5} -> GRN + concat + x1000 -> conv_pool5 (+ReLU) into self.pool5 (VGG16_skip test_fc.prototxt:28-142)."""
+        """roi_pool{3,4,5} with GRN + concat + x1000 fused (azn_roi_pool_grn_fwd) -> conv_pool5 (+ReLU) into self.pool5
+        (VGG16_skip test_fc.prototxt:28-142).  The pooled intermediates never reach HBM."""
         hd = self.head
         mc, P = self.n_img * self.cap, hd.pooled
-        for name, sc, buf in zip(hd.conv_names, hd.scales, self.pooled_src):
+        off = 0
+        for name, sc, c in zip(hd.conv_names, hd.scales, hd.src_channels):
             m = maps[name]
             assert m.dtype == torch.bfloat16 and m.shape[0] == self.n_img and m.is_contiguous()
-            ops.roi_pool(m, self.rois, P, sc, layout="NHWC", n_rois=self.m_total, out=buf.view(mc, P, P, buf.shape[1]), staged=True)
-        ops.grn_concat(self.pooled_src, hd.grn_scale, n_units=self.m_total, rows_per_unit=P * P, out=self.cat)
+            ops.roi_pool_grn(m, self.rois, self.cat, off, P, sc, hd.grn_scale, n_rois=self.m_total)
+            off += c
         torch.mul(self.m_total, P * P, out=self.m_rows)
         ops.fc_forward(self.cat, hd.wc, hd.bc, L.ACT_RELU, m_live=self.m_rows, out=self.pool5.view(mc * P * P, hd.C))
-        self.launches += 3 * 3 + 1 + 1 + 2
+        self.launches += 3 + 1 + 2
         return self.pool5
 
     def run_head(self, conv_nhwc):

@@ -119,15 +119,21 @@ class Net:
             self._maps[name] = ent
         return ent[2]
 
-    def skip_pool5(self, maps: dict, rois: torch.Tensor, n_rois: torch.Tensor | None = None):
+    def skip_pool5(self, maps: dict, rois: torch.Tensor, n_rois: torch.Tensor | None = None, fused: bool = True):
         """The skip head up to pool5: three ROI pools -> GRN + concat + x1000 -> conv_pool5 (+ReLU).
         maps: name -> bf16 NHWC; returns bf16 [R, 49 * c_out] (the pooled-row matrix of fc6)."""
         hd, P = self.head, self.pooled
         R = rois.shape[0]
-        pooled = [ops.roi_pool(maps[n], rois, P, sc, layout="NHWC", n_rois=n_rois).view(R * P * P, -1)
-                  for n, sc in zip(hd.conv_names, hd.scales)]
         cat = torch.zeros((R * P * P, hd.k_cat), dtype=torch.bfloat16, device=rois.device)
-        ops.grn_concat(pooled, hd.grn_scale, n_units=n_rois, rows_per_unit=P * P, out=cat)
+        if fused:                                  # GRN + concat + scale in the pooling kernel's epilogue
+            off = 0
+            for n, sc, c in zip(hd.conv_names, hd.scales, hd.src_channels):
+                ops.roi_pool_grn(maps[n], rois, cat, off, P, sc, hd.grn_scale, n_rois=n_rois)
+                off += c
+        else:
+            pooled = [ops.roi_pool(maps[n], rois, P, sc, layout="NHWC", n_rois=n_rois).view(R * P * P, -1)
+                      for n, sc in zip(hd.conv_names, hd.scales)]
+            ops.grn_concat(pooled, hd.grn_scale, n_units=n_rois, rows_per_unit=P * P, out=cat)
         m_live = None if n_rois is None else n_rois * (P * P)
         return ops.fc_forward(cat, hd.wc, hd.bc, L.ACT_RELU, m_live=m_live).view(R, -1)
 

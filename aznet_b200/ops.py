@@ -161,6 +161,20 @@ def detect_thresholds(top_scores: torch.Tensor, det_count: torch.Tensor, max_per
     return out
 
 
+def roi_pool_grn(feat: torch.Tensor, rois: torch.Tensor, out: torch.Tensor, ch_off: int, pooled: int = 7,
+                 spatial_scale: float = 0.0625, grn_scale: float = 1000.0, n_rois: torch.Tensor | None = None):
+    """ROI max pooling with the skip head's GRN + concat + Power epilogue fused (azn_roi_pool_grn_fwd).
+    feat bf16 [n,H,W,C]; out bf16 [R*P*P, ld]: columns [ch_off, ch_off+C) are written."""
+    _need_cuda(feat, rois, out, n_rois)
+    assert feat.dtype == torch.bfloat16 and feat.is_contiguous() and rois.is_contiguous() and rois.dtype == torch.float32
+    n, H, W, Cc = feat.shape
+    R = rois.shape[0]
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 2 and out.shape[0] >= R * pooled * pooled
+    L.check(L.lib().azn_roi_pool_grn_fwd(_ptr(feat), n, Cc, H, W, _ptr(rois), _ptr(n_rois), R, pooled, pooled, float(spatial_scale),
+                                         float(grn_scale), _ptr(out), int(out.shape[1]), int(ch_off), _stream()), "azn_roi_pool_grn_fwd")
+    return out
+
+
 def grn_concat(pooled: list, scale: float = 1000.0, n_units: torch.Tensor | None = None, rows_per_unit: int = 49,
                out: torch.Tensor | None = None):
     """GRN of every source + channel concat + Power scale (VGG16_skip test_fc.prototxt:39-110, grn_layer.cpp:27-56).

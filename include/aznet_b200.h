@@ -331,9 +331,16 @@ int azn_nhwc_border(const void *in, int n_img, int H, int W, int C, void *out, i
  *   positions (rows = R * PH * PW); out bf16 [rows, ld_out], ld_out >= sum channels (columns past the sum are
  *   left untouched: zero them once when K must be padded for the GEMM):  out[r, off_l + c] = scale * (x / sqrt(sum_c x^2)),
  *   each source normalised on its own.  n_units (device, may be NULL) = live ROI count, rows_per_unit = PH * PW:
- *   only n_units * rows_per_unit rows are processed.  `pooled` and `channels` are HOST arrays of n_src <= 4 entries.
+ *   only n_units * rows_per_unit rows are processed.  `pooled` and `channels` are HOST arrays of n_src <= 8 entries.
  *   The 1x1 convolution conv_pool5 (+ReLU) that follows is azn_fc_forward over the same rows (K = sum channels,
  *   N = 512): its output [rows, 512] is the [R, PH*PW*512] pooled-row matrix of fc6. */
+/* azn_roi_pool_grn_fwd: ROI max-pool (bf16 NHWC map, the semantics of azn_roi_pool_fwd) with the GRN + concat
+ * offset + Power scale fused into its epilogue: out bf16 [R * PH * PW, ld_out], columns [ch_off, ch_off + C) of row
+ * (r, ph, pw) = grn_scale * pooled / sqrt(sum_c pooled^2).  Three calls (conv3_3 / conv4_3 / conv5_3 at 1/4, 1/8,
+ * 1/16) fill the concat operand of conv_pool5 without the pooled intermediates ever reaching HBM.  C <= 1024. */
+int azn_roi_pool_grn_fwd(const void *feat, int n_img, int C, int H, int W, const float *rois, const int32_t *n_rois,
+                         int R_cap, int PH, int PW, float spatial_scale, float grn_scale, void *out, int ld_out,
+                         int ch_off, azn_stream_t stream);
 int azn_grn_concat_forward(const void *const *pooled, const int32_t *channels, int n_src, const int32_t *n_units,
                            long long rows_cap, int rows_per_unit, float scale, void *out, int ld_out, azn_stream_t stream);
 

@@ -233,3 +233,29 @@ def test_skip_drivers_device_route_equals_host_route(dev, tmp_path, capsys):
     finally:
         cfg.SEAR.FRCNN_CONV, cfg.DEDUP_BOXES, cfg.ROOT_DIR = saved
         C.cfg_set_mode("Test", 0.5)
+
+
+def test_roi_pool_grn_fused_equals_pool_then_grn(dev):
+    """azn_roi_pool_grn_fwd = azn_roi_pool_fwd followed by azn_grn_concat_forward, bit for bit (same summation order),
+    for every source geometry of the skip head, with a device-side ROI count, empty bins (NaN) included."""
+    from aznet_b200 import ops
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    n_img, H, W = 3, 240, 320
+    rois = torch.from_numpy(synth.make_rois(500, H, W, seed=4, n_img=n_img)).to(dev)
+    n_live = torch.tensor([437], dtype=torch.int32, device=dev)
+    specs = [(32, 4, 0.25), (64, 8, 0.125), (512, 16, 0.0625), (256, 4, 0.25), (1024, 16, 0.0625)]
+    ctot = sum(c for c, _, _ in specs)
+    fused = torch.full((500 * 49, ctot + 24), 3.0, dtype=torch.bfloat16, device=dev)
+    pooled, off = [], 0
+    for c, stride, sc in specs:
+        m = torch.randn((n_img, H // stride, W // stride, c), generator=g, device=dev).clamp_(min=0).to(torch.bfloat16).contiguous()
+        ops.roi_pool_grn(m, rois, fused, off, 7, sc, 1000.0, n_rois=n_live)
+        pooled.append(ops.roi_pool(m, rois, 7, sc, layout="NHWC", n_rois=n_live).view(500 * 49, c))
+        off += c
+    ref = torch.full((500 * 49, ctot + 24), 3.0, dtype=torch.bfloat16, device=dev)
+    ops.grn_concat(pooled, 1000.0, n_units=n_live, rows_per_unit=49, out=ref)
+    assert torch.equal(fused.view(torch.int16), ref.view(torch.int16))
+    live = fused[:437 * 49, :ctot].float()
+    assert torch.isnan(live).any() and torch.isfinite(live).float().mean() > 0.9      # border ROIs have empty bins
+    assert bool((fused[437 * 49:] == 3.0).all())
