@@ -11,7 +11,9 @@
 // Every f32 operation below is an explicit round-to-nearest intrinsic so nvcc cannot contract
 // a multiply-add into an FMA (x86-64 gcc, which built the reference, has no FMA by default).
 //
-// Large single problem (azn_nms), four launches on one stream:
+// Large single problem (azn_nms).  The mask is produced one super-row (1024 boxes) at a time on the caller's stream
+// while the greedy pass runs on an internal high-priority stream: launch s of the pass waits only for the mask rows
+// of super-tiles <= s, so the serial chain hides behind the mask of the rows that follow.  Kernels:
 //   1. nms_rank_kernel   -- rank sort by (score desc, index desc) on a 2-D grid: every thread counts
 //      nms_scatter_kernel   the detections of one score tile that precede its own (shared memory),
 //                           partial counts are added atomically, then boxes move to sorted position.
@@ -31,6 +33,8 @@
 // Many small problems (azn_nms_batched, one per class per image in apply_nms,
 // lib/detect/test.py:467-484): one warp per problem, boxes in shared memory, the suppression
 // state in per-lane registers exchanged with ballots.
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -67,20 +71,51 @@ __device__ __forceinline__ bool precedes(float sj, int j, float si, int i) {
 constexpr int RANK_THREADS = 256;
 constexpr int RANK_TILE = 2048;
 
+// monotone float -> uint key of the reference's comparison (`>` on float32; -0 == +0; NaN scores are not ordered by
+// numpy either and are out of contract)
+__device__ __forceinline__ unsigned rank_key(float s) {
+    const unsigned b = __float_as_uint(s + 0.f);                // -0 -> +0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 // grid = (ceil(n/256), ceil(n/RANK_TILE)): block (bx, by) counts, for its 256 detections, how many of the
 // by-th tile of detections precede each of them, and adds the partial count to rank[i].
+// j precedes i  <=>  key_j > key_i, or key_j == key_i and j > i: one unsigned compare per pair -- `>=` for the
+// elements behind i, `>` for those before it -- on keys staged once per tile, four per 16-byte shared load.
 __global__ void __launch_bounds__(RANK_THREADS)
 nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank) {
-    __shared__ float s_tile[RANK_TILE];
+    __shared__ __align__(16) unsigned s_key[RANK_TILE];
     const int i = blockIdx.x * RANK_THREADS + threadIdx.x;
     const int t0 = blockIdx.y * RANK_TILE, tn = min(RANK_TILE, n - t0);
-    for (int k = threadIdx.x; k < tn; k += RANK_THREADS) s_tile[k] = dets[(size_t)(t0 + k) * 5 + 4];
+    for (int k = threadIdx.x; k < RANK_TILE; k += RANK_THREADS)
+        s_key[k] = k < tn ? rank_key(dets[(size_t)(t0 + k) * 5 + 4]) : 0u;       // padding: key 0 precedes nothing (see below)
     __syncthreads();
     if (i >= n) return;
-    const float si = dets[(size_t)i * 5 + 4];
+    const unsigned ki = rank_key(dets[(size_t)i * 5 + 4]);
+    // elements with index < split compare with `>`, the others with `>=` (equal keys: the higher index comes first);
+    // `a >= ki` is `a > ki - 1` and ki >= 1 for every real score (key 0 would be the NaN pattern 0xffffffff), and the
+    // zero padding never counts: 0 > x is false for unsigned x.
+    const int split = min(max(i + 1 - t0, 0), RANK_TILE);      // local index of the first element behind i
+    const unsigned kge = ki - 1u;
     int cnt = 0;
-#pragma unroll 8
-    for (int k = 0; k < tn; ++k) cnt += precedes(s_tile[k], t0 + k, si, i) ? 1 : 0;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(s_key);
+    const int q_split = split >> 2;
+#pragma unroll 4
+    for (int q = 0; q < q_split; ++q) {
+        const uint4 v = s4[q];
+        cnt += (v.x > ki) + (v.y > ki) + (v.z > ki) + (v.w > ki);
+    }
+    if (q_split < RANK_TILE / 4) {                              // the group that straddles the split
+        const uint4 v = s4[q_split];
+        const int r = split & 3;
+        cnt += (v.x > (r > 0 ? ki : kge)) + (v.y > (r > 1 ? ki : kge)) + (v.z > (r > 2 ? ki : kge)) + (v.w > kge);
+    }
+#pragma unroll 4
+    for (int q = q_split + 1; q < RANK_TILE / 4; ++q) {
+        const uint4 v = s4[q];
+        cnt += (v.x > kge) + (v.y > kge) + (v.z > kge) + (v.w > kge);
+    }
+    // element i itself (local index split - 1 when it lies in this tile) was compared with `>`: not counted
     if (cnt) atomicAdd(rank + i, cnt);
 }
 
@@ -116,11 +151,16 @@ __device__ __forceinline__ bool intersects(const float4 &a, const float4 &b) {
 // runs the division path for every row, because some lane of 32 random columns always intersects.)
 constexpr int MASK_THREADS = 64;
 
+// id_base: the launch covers the blocks [id_base, id_base + gridDim.x) of the row-major triangle -- azn_nms launches
+// the mask one super-row (16 row tiles = 1024 boxes) at a time so that the greedy pass of super-tile s can start as soon
+// as ITS rows exist and runs concurrently with the mask of the rows behind it (see azn_nms).  A diagonal block also
+// writes its transpose: diag_t[t][j] bit i <=> row i of tile t suppresses row j of tile t (i < j); the greedy pass
+// resolves a tile from these columns (which kept rows suppress me?) in a few ballot rounds.
 __global__ void __launch_bounds__(MASK_THREADS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
-                u64 *__restrict__ mask, int col_tiles) {
+                u64 *__restrict__ mask, int col_tiles, long id_base, u64 *__restrict__ diag_t) {
     // block id -> (rt, ct), ct >= rt: row rt of the triangle starts at id0(rt) = rt * T - rt * (rt - 1) / 2
-    const long id = blockIdx.x;
+    const long id = id_base + blockIdx.x;
     const double Tp = 2.0 * col_tiles + 1.0;
     int rt = (int)((Tp - sqrt(Tp * Tp - 8.0 * (double)id)) * 0.5);
     rt = max(0, min(rt, col_tiles - 1));
@@ -129,6 +169,7 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
     const int ct = rt + (int)(id - ((long)rt * col_tiles - (long)rt * (rt - 1) / 2));
     __shared__ float4 cb[64];
     __shared__ float ca[64];
+    __shared__ u64 s_d[64];
     const int cn = min(64, n - ct * 64);
     if ((int)threadIdx.x < cn) {
         cb[threadIdx.x] = boxes[ct * 64 + threadIdx.x];
@@ -137,47 +178,39 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
     __syncthreads();
     u64 *dst = mask + ((size_t)rt * col_tiles + ct) * 64 + threadIdx.x;      // blocked: [row tile][col tile][64 rows]
     const int row = rt * 64 + threadIdx.x;
-    if (row >= n) {                                                          // rows past the end: no suppression bits
-        *dst = 0ull;
-        return;
-    }
-    const float4 rb = boxes[row];
-    const float ra = areas[row];
-    const int start = (rt == ct) ? threadIdx.x + 1 : 0;
-    unsigned cand_lo = 0, cand_hi = 0;
-    if (thresh > 0.0) {
+    u64 bits = 0;                                                            // rows past the end: no suppression bits
+    if (row < n) {
+        const float4 rb = boxes[row];
+        const float ra = areas[row];
+        const int start = (rt == ct) ? threadIdx.x + 1 : 0;
+        unsigned cand_lo = 0, cand_hi = 0;
+        if (thresh > 0.0) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            if (k >= start && k < cn && intersects(rb, cb[k])) cand_lo |= 1u << k;
-            if (k + 32 >= start && k + 32 < cn && intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+            for (int k = 0; k < 32; ++k) {
+                if (k >= start && k < cn && intersects(rb, cb[k])) cand_lo |= 1u << k;
+                if (k + 32 >= start && k + 32 < cn && intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+            }
+        } else {
+            const u64 all = (cn == 64 ? ~0ull : ((1ull << cn) - 1ull)) & (start >= 64 ? 0ull : (~0ull << start));
+            cand_lo = (unsigned)all;
+            cand_hi = (unsigned)(all >> 32);
         }
-    } else {
-        const u64 all = (cn == 64 ? ~0ull : ((1ull << cn) - 1ull)) & (start >= 64 ? 0ull : (~0ull << start));
-        cand_lo = (unsigned)all;
-        cand_hi = (unsigned)(all >> 32);
-    }
-    u64 cand = (u64)cand_lo | ((u64)cand_hi << 32);
-    u64 bits = 0;
-    while (cand) {
-        const int k = __ffsll((long long)cand) - 1;
-        cand &= cand - 1;
-        if (suppresses(rb, ra, cb[k], ca[k], thresh)) bits |= 1ull << k;
+        u64 cand = (u64)cand_lo | ((u64)cand_hi << 32);
+        while (cand) {
+            const int k = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            if (suppresses(rb, ra, cb[k], ca[k], thresh)) bits |= 1ull << k;
+        }
     }
     *dst = bits;
-}
-
-// Transposed diagonal blocks: diag_t[t][j] bit i <=> row i of tile t suppresses row j of tile t (i < j).  The
-// greedy pass resolves a tile from these columns (which kept rows suppress me?) in a few ballot rounds.
-__global__ void __launch_bounds__(64)
-nms_diag_transpose_kernel(const u64 *__restrict__ mask, int col_tiles, u64 *__restrict__ diag_t) {
-    __shared__ u64 s_d[64];
-    const int t = blockIdx.x;
-    s_d[threadIdx.x] = mask[((size_t)t * col_tiles + t) * 64 + threadIdx.x];
-    __syncthreads();
-    u64 col = 0;
+    if (rt == ct) {                                                          // block-uniform
+        s_d[threadIdx.x] = bits;
+        __syncthreads();
+        u64 col = 0;
 #pragma unroll 8
-    for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> threadIdx.x) & 1ull) << i;
-    diag_t[(size_t)t * 64 + threadIdx.x] = col;
+        for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> threadIdx.x) & 1ull) << i;
+        diag_t[(size_t)rt * 64 + threadIdx.x] = col;
+    }
 }
 
 constexpr int SCAN_THREADS = 1024;
@@ -185,9 +218,10 @@ constexpr int SUPER = 16;                      // column tiles per super-tile
 constexpr int SUPER_UPDATERS = 48;             // CTAs of a launch that push the previous super-tile's kept rows
 
 __device__ __forceinline__ u64 warp_or(u64 v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
+    // redux.sync.or.b32: one instruction per half instead of a 5-step shuffle butterfly (ten dependent SHFLs for
+    // 64 bits) -- this sits on the serial path of the greedy pass once per tile
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((u64)hi << 32) | lo;
 }
 // OR of the words of one 64-row block whose row bit is set in `kb`; lane l holds rows 2l and 2l+1 (one 16-byte load)
 __device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
@@ -425,6 +459,34 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
     return w;
 }
 
+// Internal stream + events of azn_nms, one set per device, created on first use (never destroyed: process lifetime).
+struct NmsStreams {
+    cudaStream_t chain = nullptr;
+    cudaEvent_t done = nullptr;
+    std::vector<cudaEvent_t> ev;
+};
+
+NmsStreams *nms_streams(int n_events) {
+    static std::mutex mu;
+    static NmsStreams per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    NmsStreams &ns = per_dev[dev];
+    if (!ns.chain) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&ns.chain, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ns.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    while ((int)ns.ev.size() < n_events) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ns.ev.push_back(e);
+    }
+    return &ns;
+}
+
 }  // namespace
 
 extern "C" size_t azn_nms_workspace_bytes(int64_t n) {
@@ -456,10 +518,6 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
     AZN_LAUNCH_CHECK();
     nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
     AZN_LAUNCH_CHECK();
-    nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles);
-    AZN_LAUNCH_CHECK();
-    nms_diag_transpose_kernel<<<col_tiles, 64, 0, s>>>(w.mask, col_tiles, w.diag_t);
-    AZN_LAUNCH_CHECK();
     {
         const size_t smem = (size_t)SUPER * SUPER * 64 * sizeof(u64);      // 128 KB diagonal super-block
         static bool attr_set = false;
@@ -468,15 +526,30 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             attr_set = true;
         }
         const int n_super = (col_tiles + SUPER - 1) / SUPER;
+        // Two streams: the caller's stream produces the mask one super-row at a time (most expensive rows first: row
+        // block r has col_tiles - 16 r column tiles); the greedy chain runs on an internal high-priority stream and
+        // launch si waits only for the mask rows of super-tiles <= si (its diagonal block, and super-tile si-1's rows
+        // for the urgent and bulk updates).  The serial chain (~20 us per super-tile) thus hides behind the mask of the
+        // rows that follow instead of starting after the whole triangle; the caller's stream joins at the end.
+        NmsStreams *ns = nms_streams(n_super);
+        AZN_REQUIRE(ns != nullptr, "azn_nms: could not create the internal stream / events");
         for (int si = 0; si < n_super; ++si) {
+            const int rt0 = si * SUPER, rt1 = min(col_tiles, rt0 + SUPER);
+            const long id0 = (long)rt0 * col_tiles - (long)rt0 * (rt0 - 1) / 2, id1 = (long)rt1 * col_tiles - (long)rt1 * (rt1 - 1) / 2;
+            nms_mask_kernel<<<(unsigned)(id1 - id0), MASK_THREADS, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, id0, w.diag_t);
+            AZN_LAUNCH_CHECK();
+            AZN_CUDA(cudaEventRecord(ns->ev[si], s));
+            AZN_CUDA(cudaStreamWaitEvent(ns->chain, ns->ev[si], 0));
             // the updaters of launch si push super-tile si-1 into the columns after super-tile si
             const int upd_cols = col_tiles - (si + 1) * SUPER;
             int updaters = (si == 0 || upd_cols <= 0) ? 0 : (SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
             if (updaters > SUPER_UPDATERS) updaters = SUPER_UPDATERS;
-            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, s, (const u64 *)w.mask, (const u64 *)w.diag_t,
+            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, ns->chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
                                     (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
                                     si == n_super - 1 ? 1 : 0));
         }
+        AZN_CUDA(cudaEventRecord(ns->done, ns->chain));
+        AZN_CUDA(cudaStreamWaitEvent(s, ns->done, 0));
     }
     return AZN_OK;
 }
