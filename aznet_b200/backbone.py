@@ -49,6 +49,7 @@ class VGG16Native:
         self.dev = torch.device(device)
         self.pixel_means = tuple(float(m) for m in pixel_means)
         self.layers, self.dims, self.names = [], [], []
+        self.first_patches = False
         c_in = None
         for s, (_, n) in enumerate(VGG16_CFG, 1):
             for i in range(1, n + 1):
@@ -64,11 +65,18 @@ class VGG16Native:
                 Wp[:co] = W
                 bp = torch.zeros((cop,), dtype=torch.float32, device=self.dev)
                 bp[:co] = torch.from_numpy(np.ascontiguousarray(b)).to(self.dev)
-                self.layers.append((ops.pack_conv_weight(Wp, cip), bp, i == n and s < 5))
+                # the first layer with few input channels (3 -> 27 real K values): gathered patches, one 64-deep tap
+                if not self.layers:
+                    self.first_patches = 9 * ci <= 64
+                if not self.layers and self.first_patches:
+                    self.layers.append((ops.pack_patch_weight(Wp, 64), bp, i == n and s < 5))
+                else:
+                    self.layers.append((ops.pack_conv_weight(Wp, cip), bp, i == n and s < 5))
                 c_in = co
         self.out_channels = c_in
-        self.cpad_in = _pad64(self.in_channels)
-        self.launches_per_call = 1 + len(self.layers) + sum(1 for l in self.layers if l[2])
+        # network-input grid: 8 channels per pixel when the first layer runs on patches, else padded to the GEMM's 64
+        self.cpad_in = 8 if self.first_patches else _pad64(self.in_channels)
+        self.launches_per_call = 1 + len(self.layers) + sum(1 for l in self.layers if l[2]) + int(self.first_patches)
 
     def flops(self, hs: int, ws: int) -> float:
         """Algorithmic FLOPs of conv1_1 .. conv5_3 for one hs x ws network input (real channel counts)."""
@@ -87,7 +95,10 @@ class VGG16Native:
         last = len(self.layers) - 1
         out = {}
         for k, (wt, b, pool) in enumerate(self.layers):
-            x = ops.conv3x3(x, wt, b, relu=True, unpadded=(k == last))
+            if k == 0 and self.first_patches:
+                x = ops.conv_patches(ops.patches3x3(x, self.in_channels, 64), wt, b, relu=True, unpadded=(k == last))
+            else:
+                x = ops.conv3x3(x, wt, b, relu=True, unpadded=(k == last))
             name = self.names[k]
             if taps and name in taps:
                 m = x if k == last else ops.nhwc_border(x, to_padded=False)

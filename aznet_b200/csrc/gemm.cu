@@ -336,7 +336,7 @@ struct EpiParams {
     // CONV kernels only -- 3x3 / pad 1 / stride 1 convolution as an implicit GEMM over a zero-bordered NHWC map
     // (see azn_conv3x3_forward): k-blocks per filter tap (Cin / 64), padded width / height, rows per image,
     // and whether the output map is written without the border (the last layer of the backbone)
-    int cv_kbt, cv_wp, cv_hp, cv_plane, cv_unpad;
+    int cv_kbt, cv_wp, cv_hp, cv_plane, cv_unpad, cv_taps;   // cv_taps: 9, or 1 = the taps are already gathered into K (patches)
 };
 
 // Row of the padded pixel grid -> is it a border pixel, and which output row does it go to.
@@ -473,7 +473,7 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], halves * C::A_HALF_BYTES + C::B_BYTES);
                     int a_col = kb * BLOCK_K, a_row = m_tile * TILE_M;
-                    if (CONV) {
+                    if (CONV && ep.cv_taps != 1) {
                         // k-block -> (filter tap, channel block): the A box of tap (dy, dx) is the same 128 pixels
                         // shifted by dy rows and dx columns of the padded grid; rows outside the tensor read as zero
                         const int tap = kb / ep.cv_kbt, dy = tap / 3;
@@ -815,7 +815,7 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     ep.flags = (int *)((char *)workspace + WS_DATA_BYTES);
     ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
     ep.trace = g_trace;
-    ep.cv_kbt = ep.cv_wp = ep.cv_hp = ep.cv_plane = ep.cv_unpad = 0;
+    ep.cv_kbt = ep.cv_wp = ep.cv_hp = ep.cv_plane = ep.cv_unpad = ep.cv_taps = 0;
     if (bn == 256 && mh == 2) rc = launch_gemm<256, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 256) rc = launch_gemm<256, 1>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 128 && mh == 2) rc = launch_gemm<128, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
@@ -842,9 +842,9 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
 // further; rows before 0 / past P are zero-filled by TMA) into the same tcgen05 pipeline.  Border rows of the
 // output are computed like any other and then stored as zeros (they are the next layer's padding): (H+2)(W+2)/(HW)
 // of the minimum work, 1.03x at 240x400, 1.11x at 30x50.
-extern "C" int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
-                                   int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
-                                   azn_stream_t stream) {
+static int conv_grid_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
+                             int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
+                             azn_stream_t stream, int taps) {
     AZN_REQUIRE(X && Wt && bias && Y, "azn_conv3x3_forward: null pointer");
     AZN_REQUIRE(n_img > 0 && H > 0 && W > 0, "azn_conv3x3_forward: bad shape n=%d H=%d W=%d", n_img, H, W);
     AZN_REQUIRE(Cin > 0 && Cin % BLOCK_K == 0, "azn_conv3x3_forward: Cin=%d must be a multiple of %d (pad the channels)", Cin, BLOCK_K);
@@ -857,7 +857,7 @@ extern "C" int azn_conv3x3_forward(const void *X, const void *Wt, const float *b
         azn_set_error("azn_conv3x3_forward: workspace %zu < %zu bytes", workspace_bytes, need);
         return AZN_ERR_CAPACITY;
     }
-    const int K = 9 * Cin;
+    const int K = taps * Cin;
     const int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
     CUtensorMap ta, tw;
     int rc = make_tmap(X, (int)P, Cin, HALF_M, &ta);
@@ -874,11 +874,25 @@ extern "C" int azn_conv3x3_forward(const void *X, const void *Wt, const float *b
     ep.flags = (int *)((char *)workspace + WS_DATA_BYTES);
     ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
     ep.trace = nullptr;
-    ep.cv_kbt = Cin / BLOCK_K; ep.cv_wp = W + 2; ep.cv_hp = H + 2; ep.cv_plane = (H + 2) * (W + 2); ep.cv_unpad = out_unpadded ? 1 : 0;
+    ep.cv_kbt = Cin / BLOCK_K; ep.cv_wp = W + 2; ep.cv_hp = H + 2; ep.cv_plane = (H + 2) * (W + 2); ep.cv_unpad = out_unpadded ? 1 : 0; ep.cv_taps = taps;
     const int grid = azn_num_sms();
     cudaStream_t s = (cudaStream_t)stream;
     if (bn == 256) rc = launch_gemm<256, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
     else if (bn == 128) rc = launch_gemm<128, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
     else rc = launch_gemm<64, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
     return rc;
+}
+
+extern "C" int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
+                                   int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
+                                   azn_stream_t stream) {
+    return conv_grid_forward(X, Wt, bias, Y, n_img, H, W, Cin, Cout, relu, out_unpadded, workspace, workspace_bytes, stream, 9);
+}
+
+// The same convolution over rows whose 3x3 neighbourhood is already gathered into K (azn_patches3x3): one tap, no
+// row shifts -- a pointwise GEMM over the padded grid with the border-zeroing epilogue.
+extern "C" int azn_conv_patches_forward(const void *Xp, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
+                                        int Kp, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
+                                        azn_stream_t stream) {
+    return conv_grid_forward(Xp, Wt, bias, Y, n_img, H, W, Kp, Cout, relu, out_unpadded, workspace, workspace_bytes, stream, 1);
 }

@@ -304,6 +304,47 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, relu: bool = 
     return out
 
 
+def patches3x3(x: torch.Tensor, cin: int, kp: int = 64, out: torch.Tensor | None = None):
+    """Zero-bordered [n, H+2, W+2, Cs] bf16 (Cs >= cin) -> [n, H+2, W+2, kp]: every pixel's 3x3 x cin neighbourhood as one
+    K row, entry (ky*3+kx)*cin + c (azn_patches3x3) -- the operand of conv_patches."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    n, hp, wp, cs = x.shape
+    if out is None:
+        out = torch.empty((n, hp, wp, kp), dtype=torch.bfloat16, device=x.device)
+    assert tuple(out.shape) == (n, hp, wp, kp) and out.is_contiguous() and out.dtype == torch.bfloat16
+    L.check(L.lib().azn_patches3x3(_ptr(x), n, hp - 2, wp - 2, cs, int(cin), _ptr(out), kp, _stream()), "azn_patches3x3")
+    return out
+
+
+def pack_patch_weight(w: torch.Tensor, kp: int = 64):
+    """Caffe conv weight [Cout, Cin, 3, 3] with 9*Cin <= kp -> bf16 [Cout, kp], column (ky*3+kx)*Cin + c, zero-padded."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3 and 9 * ci <= kp
+    t = torch.zeros((co, kp), dtype=torch.float32, device=w.device)
+    t[:, :9 * ci] = w.permute(0, 2, 3, 1).reshape(co, 9 * ci)
+    return t.to(torch.bfloat16).contiguous()
+
+
+def conv_patches(xp: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, relu: bool = True, out: torch.Tensor | None = None,
+                 unpadded: bool = False):
+    """The 3x3 convolution over gathered patches (azn_conv_patches_forward): xp bf16 [n, H+2, W+2, Kp] from patches3x3,
+    wt = pack_patch_weight(W) -> zero-bordered [n, H+2, W+2, Cout] (or [n, H, W, Cout])."""
+    _need_cuda(xp, wt, bias)
+    assert xp.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert xp.is_contiguous() and wt.is_contiguous() and xp.dim() == 4 and wt.shape[1] == xp.shape[3]
+    n, hp, wp, kp = xp.shape
+    cout = wt.shape[0]
+    shape = (n, hp - 2, wp - 2, cout) if unpadded else (n, hp, wp, cout)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=xp.device)
+    assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.bfloat16
+    ws = fc_workspace(xp.device, cout)
+    L.check(L.lib().azn_conv_patches_forward(_ptr(xp), _ptr(wt), _ptr(bias), _ptr(out), n, hp - 2, wp - 2, kp, cout, int(relu),
+                                             int(unpadded), _ptr(ws), ws.numel(), _stream()), "azn_conv_patches_forward")
+    return out
+
+
 def maxpool2x2(x: torch.Tensor, out: torch.Tensor | None = None):
     """MAX 2x2 / stride 2 pooling, ceil mode (pooling_layer.cpp:81-95), zero-bordered NHWC bf16 in and out."""
     _need_cuda(x)

@@ -319,6 +319,15 @@ int azn_image_blob(const uint8_t *images, int n_img, int H0, int W0, double im_s
 int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
                         int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
                         azn_stream_t stream);
+/* conv1_1 (Cin = 3) without the 61 padding channels per tap: azn_patches3x3 gathers every pixel's 3x3 neighbourhood into
+ * one K = Kp row -- entry (ky*3+kx)*Cin + c, the K order of the packed weights -- over the same zero-bordered grid
+ * (in [n, H+2, W+2, Cs] bf16 with Cs >= Cin channels per pixel, e.g. azn_image_blob with Cpad = 8; out [n, H+2, W+2, Kp],
+ * Kp % 64 == 0 for the GEMM), and azn_conv_patches_forward runs the convolution as ONE tap: Wt bf16 [Cout, Kp]. */
+int azn_patches3x3(const void *in_padded, int n_img, int H, int W, int Cs, int Cin, void *out_padded, int Kp,
+                   azn_stream_t stream);
+int azn_conv_patches_forward(const void *Xp, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
+                             int Kp, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
+                             azn_stream_t stream);
 int azn_maxpool2x2_forward(const void *in_padded, int n_img, int H, int W, int C, void *out_padded,
                            azn_stream_t stream);
 int azn_nhwc_border(const void *in, int n_img, int H, int W, int C, void *out, int to_padded, azn_stream_t stream);

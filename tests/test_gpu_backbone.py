@@ -109,6 +109,43 @@ def test_conv3x3_matches_fp32_convolution(dev, n, H, W, Cin, Cout, unpadded):
     assert bool((err <= tol).all()), (float(err.max()), float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("n,H,W,Cin,Cs,Cout,unpadded", [(2, 13, 17, 3, 8, 64, False), (1, 30, 50, 3, 8, 64, True), (2, 9, 11, 7, 8, 16, False),
+                                                        (1, 24, 40, 1, 16, 128, False)])
+def test_conv_patches_matches_fp32_convolution(dev, n, H, W, Cin, Cs, Cout, unpadded):
+    """The first-layer route (azn_patches3x3 + azn_conv_patches_forward: the 3x3 neighbourhood gathered into one K = 64
+    tap) against torch's fp32 convolution of the same bf16 operands, and bit-identical patch gathering."""
+    from aznet_b200 import ops
+    g = torch.Generator().manual_seed(n * 1000 + H * 10 + Cin)
+    x = torch.randn((n, H, W, Cin), generator=g).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(torch.bfloat16)
+    b = torch.randn((Cout,), generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)).permute(0, 2, 3, 1)
+    xs = torch.zeros((n, H + 2, W + 2, Cs), dtype=torch.bfloat16)
+    xs[:, 1:H + 1, 1:W + 1, :Cin] = x
+    patches = ops.patches3x3(xs.to(dev).contiguous(), Cin, 64)
+    # the gather itself is a pure copy: compare with unfold on the host
+    pad = torch.zeros((n, H + 4, W + 4, Cin), dtype=torch.bfloat16)
+    pad[:, 2:H + 2, 2:W + 2] = x
+    exp = torch.zeros((n, H + 2, W + 2, 64), dtype=torch.bfloat16)
+    for ky in range(3):
+        for kx in range(3):
+            exp[:, 1:H + 1, 1:W + 1, (ky * 3 + kx) * Cin:(ky * 3 + kx + 1) * Cin] = pad[:, 1 + ky:1 + ky + H, 1 + kx:1 + kx + W]
+    assert torch.equal(patches.cpu().view(torch.int16), exp.view(torch.int16))
+    wt = ops.pack_patch_weight(w.float().to(dev), 64)
+    shape = (n, H, W, Cout) if unpadded else (n, H + 2, W + 2, Cout)
+    out = torch.full(shape, 5.0, dtype=torch.bfloat16, device=dev)
+    y = ops.conv_patches(patches, wt, b.to(dev), relu=True, out=out, unpadded=unpadded)
+    torch.cuda.synchronize()
+    if not unpadded:
+        yb = y.float().cpu()
+        assert not yb[:, 0].any() and not yb[:, -1].any() and not yb[:, :, 0].any() and not yb[:, :, -1].any()
+        y = ops.nhwc_border(y, False)
+    got = y.float().cpu()
+    err = (got - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2e-3
+    assert bool((err <= tol).all()), (float(err.max()), float(ref.abs().max()))
+
+
 def test_conv3x3_argument_errors(dev):
     from aznet_b200 import ops
     x = torch.zeros((1, 6, 6, 32), dtype=torch.bfloat16, device=dev)

@@ -225,7 +225,7 @@ def test_im_detect_vs_oracle(dev, O, cfg):
     # (1) the oracle with the product's bf16 activation storage emulated: only the fp32 summation order differs
     onet = O.OracleNet(wq, "frcnn", cfg=ocfg, act_round=O.round_bf16)
     s_ref, p_ref, _ = O.frcnn_forward({"full": onet, "fc": onet}, im.shape, boxes, 6, {"conv5_3": bf(conv)}, ocfg)
-    np.testing.assert_allclose(scores, s_ref, atol=5e-3)
+    np.testing.assert_allclose(scores, s_ref, atol=2e-2)           # a flipped bf16 rounding of one activation moves a probability by ~1e-2
     np.testing.assert_allclose(pred, p_ref, rtol=5e-3, atol=0.5)
     # (2) the reference's fp32 blobs: stated tolerance for bf16 activations.  The logits here are O(10) (the conv
     # map of a random-init backbone is not normalised), so a 2^-9 relative activation error moves a probability

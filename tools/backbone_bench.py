@@ -47,7 +47,7 @@ def main():
     net = backbone.VGG16Native(w, dev)
     # two distinct batches so that no step finds its input in L2 (the maps themselves are far larger than L2)
     ims = [torch.from_numpy(np.stack(synth.make_images(args.batch, IM_H, IM_W, seed=1000 + 100 * s))).to(dev) for s in range(2)]
-    names = ["blob"]
+    names = ["blob"] + (["patches"] if net.first_patches else [])
     for s, (_, n) in enumerate(backbone.VGG16_CFG, 1):
         for i in range(1, n + 1):
             names.append("conv%d_%d" % (s, i))
@@ -62,7 +62,13 @@ def main():
         ev[1].record()
         k, last = 1, len(net.layers) - 1
         for li, (wt, b, pool) in enumerate(net.layers):
-            x = ops.conv3x3(x, wt, b, relu=True, unpadded=(li == last))
+            if li == 0 and net.first_patches:
+                x = ops.patches3x3(x, net.in_channels, 64)
+                k += 1
+                ev[k].record()
+                x = ops.conv_patches(x, wt, b, relu=True, unpadded=(li == last))
+            else:
+                x = ops.conv3x3(x, wt, b, relu=True, unpadded=(li == last))
             k += 1
             ev[k].record()
             if pool:
@@ -103,6 +109,9 @@ def main():
             byts = args.batch * h * wd * net.dims[li - 1][1] * 2 * 1.25     # read once + quarter-size write
             layers.append({"layer": nm, "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1)})
             h, wd = (h + 1) // 2, (wd + 1) // 2
+        elif nm == "patches":
+            byts = args.batch * (hs + 2) * (ws + 2) * (net.cpad_in + 64) * 2
+            layers.append({"layer": nm, "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1)})
         else:
             byts = args.batch * (IM_H * IM_W * 3 + (hs + 2) * (ws + 2) * net.cpad_in * 2)
             layers.append({"layer": nm, "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1)})
