@@ -345,6 +345,8 @@ template <> struct KeyOps<true> {
         return m & 0x7fff7fffu;
     }
     static __device__ __forceinline__ bool neg_zero(unsigned x) { return __vcmpeq2(x, 0x80008000u) != 0u; }
+    // a half with the sign bit set or a NaN pattern: anything that is not an ordinary value >= +0
+    static __device__ __forceinline__ bool not_plain(unsigned x) { return ((x & 0x80008000u) | __vcmpgtu2(x & 0x7fff7fffu, 0x7f807f80u)) != 0u; }
     static __device__ __forceinline__ unsigned to_key(unsigned x) {
         const unsigned k = x ^ flipmask(x);
         const unsigned nan = __vcmpgtu2(x & 0x7fff7fffu, 0x7f807f80u);    // 0xffff in every NaN half
@@ -357,6 +359,7 @@ template <> struct KeyOps<true> {
 template <> struct KeyOps<false> {
     typedef OpsF32 Exact;
     static __device__ __forceinline__ bool neg_zero(unsigned x) { return x == 0x80000000u; }
+    static __device__ __forceinline__ bool not_plain(unsigned x) { return x > 0x7f800000u; }        // sign bit set, or NaN
     static __device__ __forceinline__ unsigned to_key(unsigned x) {
         if ((x & 0x7fffffffu) > 0x7f800000u) return 0x80800000u;         // NaN -> key(-FLT_MAX)
         return x ^ (((unsigned)((int)x >> 31)) & 0x7fffffffu);
@@ -419,7 +422,19 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
 #ifdef AZN_POOL_TRACE
         const long long t2 = clock64();
 #endif
-        if (real) {                                          // raw bits -> keys in place, looking for a -0 on the way
+        // A slice of ordinary values >= +0 (every post-ReLU map: the conv5_3 of this path) needs no keys at all: the
+        // bit patterns of non-negative floats already order like signed integers, so the slice is pooled as staged,
+        // from an accumulator of +0, with no transform before and none after.
+        bool plain = false;
+        if (real) {
+            bool np = false;
+            for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
+                const uint4 v = s_map[i];
+                np |= K::not_plain(v.x) | K::not_plain(v.y) | K::not_plain(v.z) | K::not_plain(v.w);
+            }
+            plain = __syncthreads_or(np ? 1 : 0) == 0;
+        }
+        if (real && !plain) {                                // raw bits -> keys in place, looking for a -0 on the way
             bool nz = false;
             for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
                 uint4 v = s_map[i];
@@ -475,7 +490,8 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                     if (nh > 0 && nw > 0) {
                         const uint4 *p = rowbase + ws * SV;
                         if (!exact) {
-                            uint4 acc = make_uint4(K::lowest(), K::lowest(), K::lowest(), K::lowest());
+                            const unsigned a0 = plain ? 0u : K::lowest();
+                            uint4 acc = make_uint4(a0, a0, a0, a0);
 #define AZN_MAX3(A, B)                                                                           \
     acc.x = K::max3(acc.x, (A).x, (B).x); acc.y = K::max3(acc.y, (A).y, (B).y);                  \
     acc.z = K::max3(acc.z, (A).z, (B).z); acc.w = K::max3(acc.w, (A).w, (B).w)
@@ -514,7 +530,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                                 }
                             }
 #undef AZN_MAX3
-                            res = make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
+                            res = plain ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
                         } else {
                             res = Exact::lowest();
 #pragma unroll 1
