@@ -531,25 +531,35 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         // launch si waits only for the mask rows of super-tiles <= si (its diagonal block, and super-tile si-1's rows
         // for the urgent and bulk updates).  The serial chain (~20 us per super-tile) thus hides behind the mask of the
         // rows that follow instead of starting after the whole triangle; the caller's stream joins at the end.
-        NmsStreams *ns = nms_streams(n_super);
-        AZN_REQUIRE(ns != nullptr, "azn_nms: could not create the internal stream / events");
+        // Inside a stream capture (a caller building a CUDA graph) everything stays on the caller's stream: the graph
+        // would serialise the fork anyway and the lazily created stream / events must not be born inside a capture.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        AZN_CUDA(cudaStreamIsCapturing(s, &cap));
+        const bool two_streams = cap == cudaStreamCaptureStatusNone && n_super > 1;
+        NmsStreams *ns = two_streams ? nms_streams(n_super) : nullptr;
+        AZN_REQUIRE(!two_streams || ns != nullptr, "azn_nms: could not create the internal stream / events");
+        cudaStream_t chain = two_streams ? ns->chain : s;
         for (int si = 0; si < n_super; ++si) {
             const int rt0 = si * SUPER, rt1 = min(col_tiles, rt0 + SUPER);
             const long id0 = (long)rt0 * col_tiles - (long)rt0 * (rt0 - 1) / 2, id1 = (long)rt1 * col_tiles - (long)rt1 * (rt1 - 1) / 2;
             nms_mask_kernel<<<(unsigned)(id1 - id0), MASK_THREADS, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, id0, w.diag_t);
             AZN_LAUNCH_CHECK();
-            AZN_CUDA(cudaEventRecord(ns->ev[si], s));
-            AZN_CUDA(cudaStreamWaitEvent(ns->chain, ns->ev[si], 0));
+            if (two_streams) {
+                AZN_CUDA(cudaEventRecord(ns->ev[si], s));
+                AZN_CUDA(cudaStreamWaitEvent(chain, ns->ev[si], 0));
+            }
             // the updaters of launch si push super-tile si-1 into the columns after super-tile si
             const int upd_cols = col_tiles - (si + 1) * SUPER;
             int updaters = (si == 0 || upd_cols <= 0) ? 0 : (SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
             if (updaters > SUPER_UPDATERS) updaters = SUPER_UPDATERS;
-            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, ns->chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
+            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
                                     (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
                                     si == n_super - 1 ? 1 : 0));
         }
-        AZN_CUDA(cudaEventRecord(ns->done, ns->chain));
-        AZN_CUDA(cudaStreamWaitEvent(s, ns->done, 0));
+        if (two_streams) {
+            AZN_CUDA(cudaEventRecord(ns->done, chain));
+            AZN_CUDA(cudaStreamWaitEvent(s, ns->done, 0));
+        }
     }
     return AZN_OK;
 }

@@ -187,6 +187,29 @@ def test_nms_ties_and_idempotence(dev, O):
     assert int(cnt2.item()) == len(k1)
 
 
+def test_nms_inside_cuda_graph_and_on_side_stream(dev, O):
+    """azn_nms forks its greedy chain onto an internal stream; inside a stream capture it stays on the caller's stream.
+    Both give the oracle's keep list, also when replayed from a graph and when the caller's stream is not the default."""
+    from aznet_b200 import ops
+    d = synth.make_dets(5000, seed=9)
+    ref = O.nms(d, 0.5)
+    dt = torch.from_numpy(d).to(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        keep, cnt = ops.nms(dt, 0.5)                               # warm-up on the side stream (two-stream path)
+        side.synchronize()
+        assert keep[:int(cnt.item())].cpu().tolist() == ref
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            keep_g, cnt_g = ops.nms(dt, 0.5)
+    for _ in range(2):
+        keep_g.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert keep_g[:int(cnt_g.item())].cpu().tolist() == ref
+
+
 def test_nms_batched_matches_per_segment(dev, O):
     from aznet_b200 import ops
     rng = np.random.default_rng(0)
