@@ -30,7 +30,7 @@ EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
-    "azn_nms", "azn_nms_batched", "azn_nms_segments",
+    "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter", "azn_tune_threshold",
     "azn_image_blob", "azn_conv3x3_forward", "azn_maxpool2x2_forward", "azn_nhwc_border", "azn_grn_concat_forward", "azn_roi_pool_grn_fwd", "azn_patches3x3", "azn_conv_patches_forward",
 ]
@@ -157,6 +157,8 @@ def _bind(L):
     L.azn_detect_select.argtypes = [C.POINTER(DetectState), vp]
     L.azn_detect_thresholds.restype = i32
     L.azn_detect_thresholds.argtypes = [vp, vp, i32, i32, i32, C.c_longlong, vp, vp]
+    L.azn_nms_tune.restype = None
+    L.azn_nms_tune.argtypes = [i32]
     L.azn_roi_pool_grn_fwd.restype = i32
     L.azn_roi_pool_grn_fwd.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, f32, f32, vp, i32, i32, vp]
     L.azn_grn_concat_forward.restype = i32

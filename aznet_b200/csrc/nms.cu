@@ -33,6 +33,8 @@
 // Many small problems (azn_nms_batched, one per class per image in apply_nms,
 // lib/detect/test.py:467-484): one warp per problem, boxes in shared memory, the suppression
 // state in per-lane registers exchanged with ballots.
+#include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -158,7 +160,7 @@ constexpr int MASK_THREADS = 64;
 // resolves a tile from these columns (which kept rows suppress me?) in a few ballot rounds.
 __global__ void __launch_bounds__(MASK_THREADS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
-                u64 *__restrict__ mask, int col_tiles, long id_base, u64 *__restrict__ diag_t) {
+                u64 *__restrict__ mask, int col_tiles, long id_base, u64 *__restrict__ diag_t, int *__restrict__ row_done) {
     // block id -> (rt, ct), ct >= rt: row rt of the triangle starts at id0(rt) = rt * T - rt * (rt - 1) / 2
     const long id = id_base + blockIdx.x;
     const double Tp = 2.0 * col_tiles + 1.0;
@@ -211,6 +213,12 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
         for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> threadIdx.x) & 1ull) << i;
         diag_t[(size_t)rt * 64 + threadIdx.x] = col;
     }
+    // publish: one more tile of super-row rt / 16 is in memory (the greedy pass polls these counters)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(row_done + rt / 16, 1);
+    }
 }
 
 constexpr int SCAN_THREADS = 1024;
@@ -234,7 +242,7 @@ __device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, const int *__restrict__ order, int n, int col_tiles, int s_idx,
                  u64 *__restrict__ removed, u64 *__restrict__ kept_bits, int *__restrict__ nkept_ptr,
-                 int64_t *__restrict__ keep, int32_t *__restrict__ keep_count, int last) {
+                 int64_t *__restrict__ keep, int32_t *__restrict__ keep_count, int last, const int *__restrict__ row_done) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T0 = s_idx * SUPER;
     if (blockIdx.x > 0) {
@@ -280,9 +288,18 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     __shared__ u64 s_col[SUPER], s_kept[SUPER], s_prev[SUPER];
     __shared__ int s_order[SUPER * 64];
     const int nt = min(SUPER, col_tiles - T0);
-    // The mask, its transposed diagonal blocks and the sort order were written before the FIRST launch of the
-    // greedy pass: this launch may stage them while the previous one is still resolving (PDL), and only then
-    // waits for the previous super-tile's results.
+    // The mask kernel runs concurrently (other stream / SM partition) and publishes, per super-row, how many of its
+    // tiles are in memory; this launch needs super-row s (its diagonal blocks -- super-row s-1, read by the urgent and
+    // bulk updates, was awaited by the previous launch).  The sort order was written before the first launch.  So the
+    // launch may stage while the previous one is still resolving (PDL), and only then waits for that one's results.
+    if (tid == 0) {
+        int need = 0;
+        for (int rt = T0; rt < T0 + nt; ++rt) need += col_tiles - rt;
+        const volatile int *flag = row_done + s_idx;
+        while (*flag < need) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
     if (T0 * 64 + tid < n) s_order[tid] = order[T0 * 64 + tid];
     // A: stage the upper triangle of the diagonal super-block (16-byte cp.async chunks, 32 per 64-row block)
     for (int ch = tid; ch < SUPER * SUPER * 32; ch += SCAN_THREADS) {
@@ -437,7 +454,7 @@ nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ s
 struct NmsWorkspace {
     float4 *boxes;
     float *areas;
-    int *order, *rank, *nkept;
+    int *order, *rank, *nkept, *row_done;
     u64 *removed, *kept_bits, *diag_t, *mask;
 };
 
@@ -450,21 +467,71 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
     w.areas = (float *)p;   p += align_up(sizeof(float) * n, 256);
     w.order = (int *)p;     p += align_up(sizeof(int) * n, 256);
     w.rank = (int *)p;      p += align_up(sizeof(int) * n, 256);
-    // zeroed per call in one memset: rank | removed | kept_bits | nkept
+    // zeroed per call in one memset: rank | removed | kept_bits | nkept | row_done
     w.removed = (u64 *)p;   p += align_up(sizeof(u64) * col_tiles, 256);
     w.kept_bits = (u64 *)p; p += align_up(sizeof(u64) * col_tiles, 256);
     w.nkept = (int *)p;     p += 256;
+    w.row_done = (int *)p;  p += align_up(sizeof(int) * ((col_tiles + SUPER - 1) / SUPER), 256);
     w.diag_t = (u64 *)p;    p += align_up(sizeof(u64) * col_tiles * 64, 256);
     w.mask = (u64 *)p;
     return w;
 }
 
-// Internal stream + events of azn_nms, one set per device, created on first use (never destroyed: process lifetime).
+// Internal streams + events of azn_nms, one set per device, created on first use (never destroyed: process lifetime).
+// The greedy chain is a latency-bound single CTA; sharing its SM with the mask kernel's CTAs stretches it from ~17 to
+// ~27 us per super-tile (issue-slot contention), and that serial term bounds the whole call.  So the two run on
+// DISJOINT SM partitions when the driver offers green contexts (CUDA 12.4+): 8 SMs for the chain (CTA 0 + its bulk
+// updaters), the rest for the mask.  Without them: one extra high-priority stream on the whole device.
 struct NmsStreams {
-    cudaStream_t chain = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaStream_t chain = nullptr;       // greedy pass
+    cudaStream_t mask = nullptr;        // mask launches (green-context stream), or null: the caller's stream
+    cudaEvent_t done = nullptr, fork = nullptr, mask_done = nullptr;
     std::vector<cudaEvent_t> ev;
+    bool tried = false;
 };
+
+template <typename Fn> Fn driver_fn(const char *name) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (Fn)p;
+}
+
+// 8 SMs for the chain, the remaining SMs for the mask.  Returns false (and leaves ns untouched) when anything is missing.
+bool make_partitions(int dev, NmsStreams &ns) {
+    typedef CUresult (*GetRes)(CUdevice, CUdevResource *, CUdevResourceType);
+    typedef CUresult (*Split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+    typedef CUresult (*GenDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+    typedef CUresult (*CtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*StreamCreate)(CUstream *, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*DevGet)(CUdevice *, int);
+    const GetRes get_res = driver_fn<GetRes>("cuDeviceGetDevResource");
+    const Split split = driver_fn<Split>("cuDevSmResourceSplitByCount");
+    const GenDesc gen = driver_fn<GenDesc>("cuDevResourceGenerateDesc");
+    const CtxCreate ctx_create = driver_fn<CtxCreate>("cuGreenCtxCreate");
+    const StreamCreate stream_create = driver_fn<StreamCreate>("cuGreenCtxStreamCreate");
+    const DevGet dev_get = driver_fn<DevGet>("cuDeviceGet");
+    if (!get_res || !split || !gen || !ctx_create || !stream_create || !dev_get) return false;
+    if (getenv("AZN_NMS_NO_PARTITION")) return false;
+    CUdevice cu_dev;
+    if (dev_get(&cu_dev, dev) != CUDA_SUCCESS) return false;
+    CUdevResource all, part, rest;
+    if (get_res(cu_dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned int groups = 1;
+    if (split(&part, &groups, &all, &rest, 0, 8) != CUDA_SUCCESS || groups != 1) return false;
+    if (part.sm.smCount < 8 || rest.sm.smCount < 32) return false;
+    CUdevResourceDesc d_chain, d_mask;
+    if (gen(&d_chain, &part, 1) != CUDA_SUCCESS || gen(&d_mask, &rest, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx g_chain, g_mask;
+    if (ctx_create(&g_chain, d_chain, cu_dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (ctx_create(&g_mask, d_mask, cu_dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream s_chain, s_mask;
+    if (stream_create(&s_chain, g_chain, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+    if (stream_create(&s_mask, g_mask, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+    ns.chain = (cudaStream_t)s_chain;
+    ns.mask = (cudaStream_t)s_mask;
+    return true;
+}
 
 NmsStreams *nms_streams(int n_events) {
     static std::mutex mu;
@@ -473,12 +540,19 @@ NmsStreams *nms_streams(int n_events) {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
     NmsStreams &ns = per_dev[dev];
-    if (!ns.chain) {
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        if (cudaStreamCreateWithPriority(&ns.chain, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&ns.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (!ns.tried) {
+        ns.tried = true;
+        if (!make_partitions(dev, ns)) {
+            ns.mask = nullptr;
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            if (cudaStreamCreateWithPriority(&ns.chain, cudaStreamNonBlocking, greatest) != cudaSuccess) ns.chain = nullptr;
+        }
+        if (cudaEventCreateWithFlags(&ns.done, cudaEventDisableTiming) != cudaSuccess) ns.chain = nullptr;
+        if (cudaEventCreateWithFlags(&ns.fork, cudaEventDisableTiming) != cudaSuccess) ns.chain = nullptr;
+        if (cudaEventCreateWithFlags(&ns.mask_done, cudaEventDisableTiming) != cudaSuccess) ns.chain = nullptr;
     }
+    if (!ns.chain) return nullptr;
     while ((int)ns.ev.size() < n_events) {
         cudaEvent_t e;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -489,11 +563,17 @@ NmsStreams *nms_streams(int n_events) {
 
 }  // namespace
 
+// Diagnostic hook (like azn_fc_tune): 0 = default schedule; 1 = everything on the caller's stream, mask then chain;
+// 2 = stop after the mask; 3 = stop after the sort (rank + scatter).  Modes 2 / 3 leave keep_count untouched.
+static int g_nms_mode = 0;
+extern "C" void azn_nms_tune(int mode) { g_nms_mode = mode; }
+
 extern "C" size_t azn_nms_workspace_bytes(int64_t n) {
     if (n <= 0) return 256;
     const size_t ct = (size_t)((n + 63) / 64);
     return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + 2 * align_up(sizeof(int) * n, 256) +
-           2 * align_up(sizeof(u64) * ct, 256) + 256 + align_up(sizeof(u64) * ct * 64, 256) + align_up(sizeof(u64) * ct * ct * 64, 256);
+           2 * align_up(sizeof(u64) * ct, 256) + 256 + align_up(sizeof(int) * ((ct + 15) / 16), 256) + align_up(sizeof(u64) * ct * 64, 256) +
+           align_up(sizeof(u64) * ct * ct * 64, 256);
 }
 
 extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *keep, int32_t *keep_count,
@@ -526,39 +606,46 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             attr_set = true;
         }
         const int n_super = (col_tiles + SUPER - 1) / SUPER;
-        // Two streams: the caller's stream produces the mask one super-row at a time (most expensive rows first: row
-        // block r has col_tiles - 16 r column tiles); the greedy chain runs on an internal high-priority stream and
-        // launch si waits only for the mask rows of super-tiles <= si (its diagonal block, and super-tile si-1's rows
-        // for the urgent and bulk updates).  The serial chain (~20 us per super-tile) thus hides behind the mask of the
-        // rows that follow instead of starting after the whole triangle; the caller's stream joins at the end.
+        // Two streams: the mask is ONE launch (row-major over the triangle, so super-rows complete roughly in order) that
+        // publishes per-super-row tile counters; the greedy chain runs concurrently -- on its own SM partition when the
+        // driver offers green contexts, else on a high-priority stream -- and launch si polls the counter of super-row
+        // si before it stages its diagonal block.  The serial chain thus trails the mask by one super-row instead of
+        // starting after the whole triangle; the caller's stream joins at the end.
         // Inside a stream capture (a caller building a CUDA graph) everything stays on the caller's stream: the graph
         // would serialise the fork anyway and the lazily created stream / events must not be born inside a capture.
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         AZN_CUDA(cudaStreamIsCapturing(s, &cap));
-        const bool two_streams = cap == cudaStreamCaptureStatusNone && n_super > 1;
-        NmsStreams *ns = two_streams ? nms_streams(n_super) : nullptr;
+        if (g_nms_mode == 3) return AZN_OK;
+        const bool two_streams = cap == cudaStreamCaptureStatusNone && n_super > 1 && g_nms_mode == 0;
+        NmsStreams *ns = two_streams ? nms_streams(0) : nullptr;
         AZN_REQUIRE(!two_streams || ns != nullptr, "azn_nms: could not create the internal stream / events");
         cudaStream_t chain = two_streams ? ns->chain : s;
-        for (int si = 0; si < n_super; ++si) {
-            const int rt0 = si * SUPER, rt1 = min(col_tiles, rt0 + SUPER);
-            const long id0 = (long)rt0 * col_tiles - (long)rt0 * (rt0 - 1) / 2, id1 = (long)rt1 * col_tiles - (long)rt1 * (rt1 - 1) / 2;
-            nms_mask_kernel<<<(unsigned)(id1 - id0), MASK_THREADS, 0, s>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, id0, w.diag_t);
-            AZN_LAUNCH_CHECK();
-            if (two_streams) {
-                AZN_CUDA(cudaEventRecord(ns->ev[si], s));
-                AZN_CUDA(cudaStreamWaitEvent(chain, ns->ev[si], 0));
-            }
+        cudaStream_t ms = (two_streams && ns->mask) ? ns->mask : s;      // partitioned: the mask has its own SMs and stream
+        if (two_streams) {
+            AZN_CUDA(cudaEventRecord(ns->fork, s));                       // sorted boxes / zeroed state are ready
+            if (ms != s) AZN_CUDA(cudaStreamWaitEvent(ms, ns->fork, 0));
+            AZN_CUDA(cudaStreamWaitEvent(chain, ns->fork, 0));
+        }
+        nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
+                                                                                                 w.diag_t, w.row_done);
+        AZN_LAUNCH_CHECK();
+        for (int si = 0; si < n_super && g_nms_mode != 2; ++si) {
             // the updaters of launch si push super-tile si-1 into the columns after super-tile si
             const int upd_cols = col_tiles - (si + 1) * SUPER;
             int updaters = (si == 0 || upd_cols <= 0) ? 0 : (SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
-            if (updaters > SUPER_UPDATERS) updaters = SUPER_UPDATERS;
+            const int upd_cap = ms != s ? 15 : SUPER_UPDATERS;        // partitioned: the chain owns 8 SMs (2 such CTAs each)
+            if (updaters > upd_cap) updaters = upd_cap;
             AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
                                     (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
-                                    si == n_super - 1 ? 1 : 0));
+                                    si == n_super - 1 ? 1 : 0, (const int *)w.row_done));
         }
         if (two_streams) {
             AZN_CUDA(cudaEventRecord(ns->done, chain));
             AZN_CUDA(cudaStreamWaitEvent(s, ns->done, 0));
+            if (ms != s) {                                                // (implied by `done`, kept explicit for the join)
+                AZN_CUDA(cudaEventRecord(ns->mask_done, ms));
+                AZN_CUDA(cudaStreamWaitEvent(s, ns->mask_done, 0));
+            }
         }
     }
     return AZN_OK;

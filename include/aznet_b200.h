@@ -233,6 +233,9 @@ int azn_nms_batched(const float *dets, const int32_t *seg_off, int n_seg, double
 /* The same kernel over padded storage: segment s = rows [seg_off[s], seg_off[s] + seg_len[s]) of dets, both int32
  * [n_seg] on the device, every length <= max_len <= AZN_NMS_SEG_MAX (a longer segment reports keep_count -1).
  * This is how the batched detection step runs apply_nms over its [image, class, 100, 5] detections. */
+/* Diagnostic / tuning hook: 0 = default (mask and greedy chain pipelined on two streams / SM partitions), 1 = one
+ * stream, mask then chain, 2 = stop after the mask, 3 = stop after the sort.  Used by tools/microbench.py --nms-phases. */
+void azn_nms_tune(int mode);
 int azn_nms_segments(const float *dets, const int32_t *seg_off, const int32_t *seg_len, int n_seg, int max_len,
                      double thresh, int64_t *keep, int32_t *keep_count, azn_stream_t stream);
 

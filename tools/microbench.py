@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--sizes", default="2000,8000,20000")
     ap.add_argument("--hw", default="38,63", help="conv5_3 map size: 38,63 (default cfg, scale 1.0) or 30,50 (voc.yml, scale 0.8)")
     ap.add_argument("--only", default="", help="roi_pool | nms")
+    ap.add_argument("--nms-phases", action="store_true", help="also time the NMS phases (azn_nms_tune): sort, sort+mask, sequential")
     ap.add_argument("--pool-mode", type=int, default=0, help="azn_roi_pool_tune: 0 auto, 1 direct, 2 staged")
     args = ap.parse_args()
     _lib.build()
@@ -79,6 +80,13 @@ def main():
             best, mean = timeit(run, flush)
             line = {"bench": "nms", "N": N, "thresh": th, "ms_best": best, "ms_mean": mean, "kept": int(res["c"].item()),
                     "boxes_per_s": N / (best * 1e-3), "mask_bytes": 16 * N * ((N + 63) // 64) + 28 * N}
+            if args.nms_phases:
+                ph = {}
+                for mode, name in ((3, "sort_ms"), (2, "sort_mask_ms"), (1, "sequential_ms")):
+                    _lib.lib().azn_nms_tune(mode)
+                    ph[name] = round(timeit(run, flush)[0], 4)
+                _lib.lib().azn_nms_tune(0)
+                line["phases"] = ph
             if args.cpu and N <= 8000:
                 t0 = time.perf_counter()
                 k = O.nms(d_host, th)
