@@ -11,9 +11,10 @@
 // Every f32 operation below is an explicit round-to-nearest intrinsic so nvcc cannot contract
 // a multiply-add into an FMA (x86-64 gcc, which built the reference, has no FMA by default).
 //
-// Large single problem (azn_nms).  The mask is produced one super-row (1024 boxes) at a time on the caller's stream
-// while the greedy pass runs on an internal high-priority stream: launch s of the pass waits only for the mask rows
-// of super-tiles <= s, so the serial chain hides behind the mask of the rows that follow.  Kernels:
+// Large single problem (azn_nms).  The mask is ONE launch, column-major over the triangle (cheapest columns first),
+// publishing per-super-column tile counters; the greedy pass runs concurrently on an internal stream (its own 8-SM
+// green-context partition when the driver has them) and launch s polls the counters of super-columns s and s+1, so
+// the serial chain runs alongside the mask and ends ~40 us after it.  Kernels:
 //   1. nms_rank_kernel   -- rank sort by (score desc, index desc) on a 2-D grid: every thread counts
 //      nms_scatter_kernel   the detections of one score tile that precede its own (shared memory),
 //                           partial counts are added atomically, then boxes move to sorted position.
@@ -27,8 +28,9 @@
 //                           resolves the 64 x 64 diagonal block of tile b with register-resident words while
 //                           the other 31 warps OR together column b+1's words of the rows kept so far; kept
 //                           original indices are appended to `keep` (on-device compaction; the count never
-//                           visits the host).  The other CTAs of the same launch push the PREVIOUS super-tile's
-//                           kept rows into the `removed` words of all later columns (bulk update, atomicOr).
+//                           visits the host).  The other CTAs of the same launch push the kept rows of ALL EARLIER
+//                           super-tiles into the `removed` words of the NEXT super-tile's columns (left-looking
+//                           bulk update, atomicOr).
 //                           No CTA ever waits for another inside a launch.
 // Many small problems (azn_nms_batched, one per class per image in apply_nms,
 // lib/detect/test.py:467-484): one warp per problem, boxes in shared memory, the suppression
@@ -161,14 +163,15 @@ constexpr int MASK_THREADS = 64;
 __global__ void __launch_bounds__(MASK_THREADS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
                 u64 *__restrict__ mask, int col_tiles, long id_base, u64 *__restrict__ diag_t, int *__restrict__ row_done) {
-    // block id -> (rt, ct), ct >= rt: row rt of the triangle starts at id0(rt) = rt * T - rt * (rt - 1) / 2
+    // block id -> (rt, ct), rt <= ct, COLUMN-major over the triangle (column ct starts at id0(ct) = ct (ct + 1) / 2): the
+    // cheap columns come first, so the greedy pass -- which consumes the mask column by column -- starts at once and
+    // is nearly done when the last, most expensive column super-block lands
     const long id = id_base + blockIdx.x;
-    const double Tp = 2.0 * col_tiles + 1.0;
-    int rt = (int)((Tp - sqrt(Tp * Tp - 8.0 * (double)id)) * 0.5);
-    rt = max(0, min(rt, col_tiles - 1));
-    while (rt > 0 && (long)rt * col_tiles - (long)rt * (rt - 1) / 2 > id) --rt;
-    while ((long)(rt + 1) * col_tiles - (long)(rt + 1) * rt / 2 <= id) ++rt;
-    const int ct = rt + (int)(id - ((long)rt * col_tiles - (long)rt * (rt - 1) / 2));
+    int ct = (int)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
+    ct = max(0, min(ct, col_tiles - 1));
+    while (ct > 0 && (long)ct * (ct + 1) / 2 > id) --ct;
+    while ((long)(ct + 1) * (ct + 2) / 2 <= id) ++ct;
+    const int rt = (int)(id - (long)ct * (ct + 1) / 2);
     __shared__ float4 cb[64];
     __shared__ float ca[64];
     __shared__ u64 s_d[64];
@@ -213,11 +216,11 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
         for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> threadIdx.x) & 1ull) << i;
         diag_t[(size_t)rt * 64 + threadIdx.x] = col;
     }
-    // publish: one more tile of super-row rt / 16 is in memory (the greedy pass polls these counters)
+    // publish: one more tile of super-column ct / 16 is in memory (the greedy pass polls these counters)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(row_done + rt / 16, 1);
+        atomicAdd(row_done + ct / 16, 1);
     }
 }
 
@@ -237,7 +240,8 @@ __device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
 }
 
 // Launch s of the greedy pass (see the header).  mask is blocked [row tile][col tile][64]; `removed[c]` collects
-// the suppression bits of column tile c from all kept rows of super-tiles that are at least two behind c's;
+// the suppression bits of column tile c from all kept rows of super-tiles that are at least two behind c's (written
+// by the bulk updaters of the launch just before c's predecessor -- left-looking: complete exactly when c's turn comes);
 // `kept_bits[t]` is the kept mask of row tile t; `nkept` the running number of kept boxes.
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, const int *__restrict__ order, int n, int col_tiles, int s_idx,
@@ -246,13 +250,22 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T0 = s_idx * SUPER;
     if (blockIdx.x > 0) {
-        // ---------------- bulk update: kept rows of super-tile s-1 -> removed[] of the columns after super-tile s
+        // ---------------- bulk update (left-looking): kept rows of ALL super-tiles before s -> removed[] of the columns
+        // of super-tile s+1 (the rows of super-tile s itself reach them through the urgent update of launch s+1)
         pdl_enter();
         if (s_idx == 0) return;
-        const int pt0 = T0 - SUPER, c0 = T0 + SUPER;
-        const int ncols = col_tiles - c0;
+        const int pt0 = 0, c0 = T0 + SUPER;
+        const int ncols = min(SUPER, col_tiles - c0);
         if (ncols <= 0) return;
-        const long nblk = (long)SUPER * ncols;
+        if (tid == 0) {                                          // the mask of super-column s+1 must have landed
+            int need = 0;
+            for (int c = c0; c < c0 + ncols; ++c) need += c + 1;
+            const volatile int *flag = row_done + s_idx + 1;
+            while (*flag < need) __nanosleep(64);
+            __threadfence();
+        }
+        __syncthreads();
+        const long nblk = (long)T0 * ncols;
         const long wid = (long)(blockIdx.x - 1) * (SCAN_THREADS / 32) + warp, nw = (long)(gridDim.x - 1) * (SCAN_THREADS / 32);
         for (long k0 = wid; k0 < nblk; k0 += 4 * nw) {
             ulonglong2 w[4];
@@ -288,13 +301,13 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     __shared__ u64 s_col[SUPER], s_kept[SUPER], s_prev[SUPER];
     __shared__ int s_order[SUPER * 64];
     const int nt = min(SUPER, col_tiles - T0);
-    // The mask kernel runs concurrently (other stream / SM partition) and publishes, per super-row, how many of its
-    // tiles are in memory; this launch needs super-row s (its diagonal blocks -- super-row s-1, read by the urgent and
-    // bulk updates, was awaited by the previous launch).  The sort order was written before the first launch.  So the
+    // The mask kernel runs concurrently (other stream / SM partition) and publishes, per super-COLUMN, how many of its
+    // tiles are in memory; CTA 0 needs super-column s (its diagonal blocks and the urgent update), the bulk updaters
+    // super-column s+1.  The sort order was written before the first launch.  So the
     // launch may stage while the previous one is still resolving (PDL), and only then waits for that one's results.
     if (tid == 0) {
         int need = 0;
-        for (int rt = T0; rt < T0 + nt; ++rt) need += col_tiles - rt;
+        for (int c = T0; c < T0 + nt; ++c) need += c + 1;
         const volatile int *flag = row_done + s_idx;
         while (*flag < need) __nanosleep(64);
         __threadfence();
@@ -606,11 +619,11 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             attr_set = true;
         }
         const int n_super = (col_tiles + SUPER - 1) / SUPER;
-        // Two streams: the mask is ONE launch (row-major over the triangle, so super-rows complete roughly in order) that
-        // publishes per-super-row tile counters; the greedy chain runs concurrently -- on its own SM partition when the
-        // driver offers green contexts, else on a high-priority stream -- and launch si polls the counter of super-row
-        // si before it stages its diagonal block.  The serial chain thus trails the mask by one super-row instead of
-        // starting after the whole triangle; the caller's stream joins at the end.
+        // Two streams: the mask is ONE launch (column-major over the triangle, cheapest columns first, so super-columns
+        // complete roughly in order) that publishes per-super-column tile counters; the greedy chain runs concurrently
+        // -- on its own SM partition when the driver offers green contexts, else on a high-priority stream -- and launch
+        // si polls the counters of super-columns si (CTA 0) and si + 1 (bulk updaters).  The serial chain thus runs
+        // alongside the mask instead of after it; the caller's stream joins at the end.
         // Inside a stream capture (a caller building a CUDA graph) everything stays on the caller's stream: the graph
         // would serialise the fork anyway and the lazily created stream / events must not be born inside a capture.
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -630,12 +643,12 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
                                                                                                  w.diag_t, w.row_done);
         AZN_LAUNCH_CHECK();
         for (int si = 0; si < n_super && g_nms_mode != 2; ++si) {
-            // the updaters of launch si push super-tile si-1 into the columns after super-tile si
-            const int upd_cols = col_tiles - (si + 1) * SUPER;
-            int updaters = (si == 0 || upd_cols <= 0) ? 0 : (SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
+            // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1
+            const int upd_cols = min(SUPER, col_tiles - (si + 1) * SUPER);
+            long updaters = (si == 0 || upd_cols <= 0) ? 0 : ((long)si * SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
             const int upd_cap = ms != s ? 15 : SUPER_UPDATERS;        // partitioned: the chain owns 8 SMs (2 such CTAs each)
             if (updaters > upd_cap) updaters = upd_cap;
-            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
+            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + (unsigned)updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
                                     (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
                                     si == n_super - 1 ? 1 : 0, (const int *)w.row_done));
         }
