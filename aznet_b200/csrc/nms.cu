@@ -52,7 +52,15 @@ __device__ __forceinline__ float box_area(float x1, float y1, float x2, float y2
 }
 
 // true iff box j must be suppressed by kept box i
-__device__ __forceinline__ bool suppresses(const float4 &a, float area_a, const float4 &b, float area_b, double thresh) {
+// (double)ovr >= thresh for a float ovr  <=>  ovr >= F, F = the smallest float whose double value is >= thresh: the
+// reference's double compare (nms.pyx:65-66) without a conversion and a 64-bit compare per pair.
+__device__ __forceinline__ float thresh_as_float(double t) {
+    float f = (float)t;                                   // round to nearest
+    if ((double)f < t) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+__device__ __forceinline__ bool suppresses(const float4 &a, float area_a, const float4 &b, float area_b, float thresh_f) {
     float xx1 = a.x >= b.x ? a.x : b.x;
     float yy1 = a.y >= b.y ? a.y : b.y;
     float xx2 = a.z <= b.z ? a.z : b.z;
@@ -64,7 +72,7 @@ __device__ __forceinline__ bool suppresses(const float4 &a, float area_a, const 
     float inter = __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     float ovr = __fdiv_rn(inter, uni);
-    return (double)ovr >= thresh;
+    return ovr >= thresh_f;
 }
 
 // (score desc, index desc): does detection j come before detection i ?
@@ -136,15 +144,19 @@ nms_scatter_kernel(const float *__restrict__ dets, int n, const int *__restrict_
     order[r] = i;
 }
 
-// true iff the clamped intersection of a and b is non-empty (w > 0 and h > 0 with the reference's f32 ops)
-__device__ __forceinline__ bool intersects(const float4 &a, const float4 &b) {
-    float xx1 = a.x >= b.x ? a.x : b.x;
-    float yy1 = a.y >= b.y ? a.y : b.y;
-    float xx2 = a.z <= b.z ? a.z : b.z;
-    float yy2 = a.w <= b.w ? a.w : b.w;
-    float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.f);
-    float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
-    return w > 0.f && h > 0.f;
+// Is the clamped intersection of a and b non-empty, i.e. w > 0 and h > 0 with the reference's float32 operations
+// w = (min(a.x2, b.x2) - max(a.x1, b.x1)) + 1 ?  Two exact simplifications:
+//   (1) fl(fl(d) + 1) > 0  <=>  fl(d) > -1: floats just above -1 are spaced 2^-24, so fl(d) + 1 is then an exactly
+//       representable positive number, and fl(d) <= -1 gives a sum <= 0;
+//   (2) rounding is monotone, so fl(min(a2, b2) - max(a1, b1)) is the minimum of the four fl(x2 - x1) combinations:
+//       the test is  fl(a2 - b1) > -1 && fl(b2 - a1) > -1  for the pair, and  fl(a2 - a1) > -1, fl(b2 - b1) > -1  per box
+//       (box_valid: checked once per box, an invalid column box is poisoned with x1 = +inf).
+// Four subtractions and four compares per pair instead of four min/max, four add/sub and two compares plus guards.
+__device__ __forceinline__ bool box_valid(const float4 &b) {
+    return __fsub_rn(b.z, b.x) > -1.f && __fsub_rn(b.w, b.y) > -1.f;
+}
+__device__ __forceinline__ bool pair_intersects(const float4 &a, const float4 &b) {
+    return __fsub_rn(a.z, b.x) > -1.f && __fsub_rn(b.z, a.x) > -1.f && __fsub_rn(a.w, b.y) > -1.f && __fsub_rn(b.w, a.y) > -1.f;
 }
 
 // One 64-thread CTA per 64 x 64 tile of the upper triangle (linear block id -> (row tile, col tile)); thread =
@@ -177,10 +189,15 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
     __shared__ u64 s_d[64];
     const int cn = min(64, n - ct * 64);
     if ((int)threadIdx.x < cn) {
-        cb[threadIdx.x] = boxes[ct * 64 + threadIdx.x];
+        float4 b = boxes[ct * 64 + threadIdx.x];
+        // a box whose own extent is empty under the reference's arithmetic ((x2 - x1) + 1 <= 0) intersects nothing:
+        // poison it so that the pair test below fails without a per-pair check (only when the test is used at all)
+        if (thresh > 0.0 && !box_valid(b)) b.x = INFINITY;
+        cb[threadIdx.x] = b;
         ca[threadIdx.x] = areas[ct * 64 + threadIdx.x];
     }
     __syncthreads();
+    const float thresh_f = thresh_as_float(thresh);
     u64 *dst = mask + ((size_t)rt * col_tiles + ct) * 64 + threadIdx.x;      // blocked: [row tile][col tile][64 rows]
     const int row = rt * 64 + threadIdx.x;
     u64 bits = 0;                                                            // rows past the end: no suppression bits
@@ -190,10 +207,20 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
         const int start = (rt == ct) ? threadIdx.x + 1 : 0;
         unsigned cand_lo = 0, cand_hi = 0;
         if (thresh > 0.0) {
+            if (!box_valid(rb)) {
+                // nothing intersects an empty row box
+            } else if (rt != ct && cn == 64) {               // the bulk of the triangle: full off-diagonal tiles, no guards
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k >= start && k < cn && intersects(rb, cb[k])) cand_lo |= 1u << k;
-                if (k + 32 >= start && k + 32 < cn && intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+                for (int k = 0; k < 32; ++k) {
+                    if (pair_intersects(rb, cb[k])) cand_lo |= 1u << k;
+                    if (pair_intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    if (k >= start && k < cn && pair_intersects(rb, cb[k])) cand_lo |= 1u << k;
+                    if (k + 32 >= start && k + 32 < cn && pair_intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+                }
             }
         } else {
             const u64 all = (cn == 64 ? ~0ull : ((1ull << cn) - 1ull)) & (start >= 64 ? 0ull : (~0ull << start));
@@ -204,7 +231,7 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
         while (cand) {
             const int k = __ffsll((long long)cand) - 1;
             cand &= cand - 1;
-            if (suppresses(rb, ra, cb[k], ca[k], thresh)) bits |= 1ull << k;
+            if (suppresses(rb, ra, cb[k], ca[k], thresh_f)) bits |= 1ull << k;
         }
     }
     *dst = bits;
@@ -423,6 +450,7 @@ nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ s
                    int n_seg, double thresh, int max_seg, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float thresh_f = thresh_as_float(thresh);
     float *sx1 = smem + (size_t)warp * 6 * max_seg;
     float *sy1 = sx1 + max_seg, *sx2 = sy1 + max_seg, *sy2 = sx2 + max_seg, *sar = sy2 + max_seg;
     int *sid = (int *)(sar + max_seg);
@@ -456,7 +484,7 @@ nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ s
             const float ai = sar[i];
             for (int j = lane + ((i + 1 - lane + 31) & ~31); j < n; j += 32) {   // first j > i owned by lane
                 const float4 bj = make_float4(sx1[j], sy1[j], sx2[j], sy2[j]);
-                if (suppresses(bi, ai, bj, sar[j], thresh)) dead |= 1u << (j >> 5);
+                if (suppresses(bi, ai, bj, sar[j], thresh_f)) dead |= 1u << (j >> 5);
             }
         }
         if (lane == 0) keep_count[seg] = nkept;
