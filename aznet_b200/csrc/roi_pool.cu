@@ -482,56 +482,59 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 const int hs = hb & 0xffff, nh = phv ? (int)(hb >> 16) - hs : 0;
                 uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
                 const uint4 *rowbase = s_map + (size_t)hs * row_step + j;
+                // Column re-use.  Consecutive bins of a row overlap by at most one map column -- bin p+1 starts at
+                // floor((p+1) b) >= ceil((p+1) b) - 1, the last column of bin p, and clamping keeps that order; for ROIs
+                // narrower than 7 cells several bins even share all their columns -- so the maximum over the lane's bin rows
+                // of the LAST column visited is kept in registers and re-used by the next bin: every (bin row, map column) pair
+                // of the ROI is read from shared memory exactly once (roi_w + 1 columns instead of roi_w + 7: 40 % fewer reads
+                // for the average ROI, 3x fewer for small ones).  New columns are reduced two at a time: four independent
+                // shared-memory loads in flight per lane.
+                const unsigned a0 = plain ? 0u : K::lowest();
+                int w_cached = -1;                           // warp-uniform
+                uint4 cache = make_uint4(a0, a0, a0, a0);
 #pragma unroll 1
                 for (int pw = 0; pw < ST_P; ++pw, optr += L) {
                     const unsigned wb = __shfl_sync(0xffffffffu, gb, ST_P + pw);
-                    const int ws = wb & 0xffff, nw = (int)(wb >> 16) - ws;          // warp-uniform
+                    const int ws = wb & 0xffff, we = (int)(wb >> 16);                // warp-uniform
                     uint4 res = make_uint4(0u, 0u, 0u, 0u);
-                    if (nh > 0 && nw > 0) {
-                        const uint4 *p = rowbase + ws * SV;
+                    if (we > ws) {
                         if (!exact) {
-                            const unsigned a0 = plain ? 0u : K::lowest();
                             uint4 acc = make_uint4(a0, a0, a0, a0);
-#define AZN_MAX3(A, B)                                                                           \
-    acc.x = K::max3(acc.x, (A).x, (B).x); acc.y = K::max3(acc.y, (A).y, (B).y);                  \
-    acc.z = K::max3(acc.z, (A).z, (B).z); acc.w = K::max3(acc.w, (A).w, (B).w)
-                            if (nw == 1) {                   // two rows per VIMNMX3
+#define AZN_MAX3(D, A, B)                                                                        \
+    (D).x = K::max3((D).x, (A).x, (B).x); (D).y = K::max3((D).y, (A).y, (B).y);                  \
+    (D).z = K::max3((D).z, (A).z, (B).z); (D).w = K::max3((D).w, (A).w, (B).w)
+                            int w = ws;
+                            if (w == w_cached) { acc = cache; ++w; }         // the previous bin's last column, already reduced
+#pragma unroll 1
+                            for (; w + 1 < we; w += 2) {
+                                uint4 c0 = make_uint4(a0, a0, a0, a0), c1 = c0;
+                                const uint4 *q = rowbase + w * SV;
                                 int t = 0;
 #pragma unroll 1
-                                for (; t + 1 < nh; t += 2, p += 2 * row_step) { const uint4 a = p[0], b = p[row_step]; AZN_MAX3(a, b); }
-                                if (t < nh) { const uint4 a = p[0]; AZN_MAX3(a, a); }
-                            } else if (nw == 2) {            // all loads of two rows in flight before the first max
-                                int t = 0;
-#pragma unroll 1
-                                for (; t + 1 < nh; t += 2, p += 2 * row_step) {
-                                    const uint4 a = p[0], b = p[SV], c = p[row_step], d = p[row_step + SV];
-                                    AZN_MAX3(a, b); AZN_MAX3(c, d);
+                                for (; t + 1 < nh; t += 2, q += 2 * row_step) {
+                                    const uint4 a = q[0], b = q[SV], c = q[row_step], d = q[row_step + SV];
+                                    AZN_MAX3(c0, a, c); AZN_MAX3(c1, b, d);
                                 }
-                                if (t < nh) { const uint4 a = p[0], b = p[SV]; AZN_MAX3(a, b); }
-                            } else if (nw == 3) {
-#pragma unroll 1
-                                for (int t = 0; t < nh; ++t, p += row_step) {
-                                    const uint4 a = p[0], b = p[SV], c = p[2 * SV];
-                                    AZN_MAX3(a, b); AZN_MAX3(c, c);
-                                }
-                            } else if (nw == 4) {
-#pragma unroll 1
-                                for (int t = 0; t < nh; ++t, p += row_step) {
-                                    const uint4 a = p[0], b = p[SV], c = p[2 * SV], d = p[3 * SV];
-                                    AZN_MAX3(a, b); AZN_MAX3(c, d);
-                                }
-                            } else {
-#pragma unroll 1
-                                for (int t = 0; t < nh; ++t, p += row_step) {
-                                    int w = 0;
-#pragma unroll 1
-                                    for (; w + 1 < nw; w += 2) { const uint4 a = p[w * SV], b = p[(w + 1) * SV]; AZN_MAX3(a, b); }
-                                    if (w < nw) { const uint4 a = p[w * SV]; AZN_MAX3(a, a); }
-                                }
+                                if (t < nh) { const uint4 a = q[0], b = q[SV]; AZN_MAX3(c0, a, a); AZN_MAX3(c1, b, b); }
+                                AZN_MAX3(acc, c0, c1);
+                                cache = c1;
                             }
+                            if (w < we) {
+                                uint4 c0 = make_uint4(a0, a0, a0, a0);
+                                const uint4 *q = rowbase + w * SV;
+                                int t = 0;
+#pragma unroll 1
+                                for (; t + 1 < nh; t += 2, q += 2 * row_step) { const uint4 a = q[0], b = q[row_step]; AZN_MAX3(c0, a, b); }
+                                if (t < nh) { const uint4 a = q[0]; AZN_MAX3(c0, a, a); }
+                                AZN_MAX3(acc, c0, c0);
+                                cache = c0;
+                            }
+                            w_cached = we - 1;
 #undef AZN_MAX3
-                            res = plain ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
-                        } else {
+                            if (nh > 0) res = plain ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
+                        } else if (nh > 0) {
+                            const int nw = we - ws;
+                            const uint4 *p = rowbase + ws * SV;
                             res = Exact::lowest();
 #pragma unroll 1
                             for (int t = 0; t < nh; ++t, p += row_step)
