@@ -8,7 +8,7 @@ echo "== gpu tests"; timeout -k 10 900 python -m pytest tests -m gpu -q 2>&1 > g
 echo "== smoke"; timeout -k 10 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/smoke.log
 echo "== bench"; timeout -k 10 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench.log | cut -c1-400
 echo "== bench reference arm"; timeout -k 10 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref.log | cut -c1-400
-echo "== microbench"; (timeout -k 10 600 python tools/microbench.py; timeout -k 10 300 python tools/microbench.py --only roi_pool --hw 30,50) 2>&1 | tee gpurun_out/microbench.jsonl | cut -c1-160
+echo "== microbench"; (timeout -k 10 600 python tools/microbench.py --nms-phases; timeout -k 10 300 python tools/microbench.py --only roi_pool --hw 30,50) 2>&1 | tee gpurun_out/microbench.jsonl | cut -c1-160
 echo "== detbench"; timeout -k 10 600 python tools/detbench.py 2>&1 | tail -1 | tee gpurun_out/detbench.json | cut -c1-400
 echo "== backbone"; timeout -k 10 600 python tools/backbone_bench.py 2>&1 | tail -1 | tee gpurun_out/backbone.json | cut -c1-300
 echo "== skipbench"; timeout -k 10 600 python tools/skipbench.py 2>&1 | tail -1 | tee gpurun_out/skipbench.json | cut -c1-300
