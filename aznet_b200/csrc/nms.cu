@@ -94,8 +94,11 @@ __device__ __forceinline__ unsigned rank_key(float s) {
 // by-th tile of detections precede each of them, and adds the partial count to rank[i].
 // j precedes i  <=>  key_j > key_i, or key_j == key_i and j > i: one unsigned compare per pair -- `>=` for the
 // elements behind i, `>` for those before it -- on keys staged once per tile, four per 16-byte shared load.
+// With a single score tile (n <= RANK_TILE) the count is already the final rank: the thread moves its box to sorted
+// position itself and the scatter launch is skipped (small problems are launch-latency bound).
 __global__ void __launch_bounds__(RANK_THREADS)
-nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank) {
+nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank, float4 *__restrict__ boxes,
+                float *__restrict__ areas, int *__restrict__ order) {
     __shared__ __align__(16) unsigned s_key[RANK_TILE];
     const int i = blockIdx.x * RANK_THREADS + threadIdx.x;
     const int t0 = blockIdx.y * RANK_TILE, tn = min(RANK_TILE, n - t0);
@@ -128,7 +131,15 @@ nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank) {
         cnt += (v.x > kge) + (v.y > kge) + (v.z > kge) + (v.w > kge);
     }
     // element i itself (local index split - 1 when it lies in this tile) was compared with `>`: not counted
-    if (cnt) atomicAdd(rank + i, cnt);
+    if (gridDim.y == 1) {
+        const float *d = dets + (size_t)i * 5;
+        const float4 b = make_float4(d[0], d[1], d[2], d[3]);
+        boxes[cnt] = b;
+        areas[cnt] = box_area(b.x, b.y, b.z, b.w);
+        order[cnt] = i;
+    } else if (cnt) {
+        atomicAdd(rank + i, cnt);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -635,10 +646,12 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
     NmsWorkspace w = carve(workspace, n, col_tiles);
     AZN_CUDA(cudaMemsetAsync(w.rank, 0, (size_t)((char *)w.diag_t - (char *)w.rank), s));   // rank, removed, kept_bits, nkept
     nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
-                      RANK_THREADS, 0, s>>>(dets, (int)n, w.rank);
+                      RANK_THREADS, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
     AZN_LAUNCH_CHECK();
-    nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
-    AZN_LAUNCH_CHECK();
+    if (n > RANK_TILE) {
+        nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
+        AZN_LAUNCH_CHECK();
+    }
     {
         const size_t smem = (size_t)SUPER * SUPER * 64 * sizeof(u64);      // 128 KB diagonal super-block
         static bool attr_set = false;
