@@ -310,6 +310,9 @@ def main():
     for i in range(max(args.warmup, 2)):
         step_e2e(i)
     drain()
+    if collector is not None:
+        collector.gather()                            # warm-up of the job's one exchange (buffers, NCCL channels)
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
