@@ -238,6 +238,26 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
             cand_lo = (unsigned)all;
             cand_hi = (unsigned)(all >> 32);
         }
+        // Area-ratio filter between the two phases: the clamped intersection is never larger than either box
+        // (w <= w_a, h <= h_a and every operation is monotone), so inter <= m = min(area_a, area_b) exactly, the union
+        // fl(fl(a + b) - inter) >= max(area_a, area_b) (1 - 2^-22), and ovr <= (m / M)(1 + 2^-21).  A pair with
+        // m < thresh_f * M * (1 - 2^-19) therefore cannot reach the threshold: it is dropped here for two multiplies,
+        // and the division loop below runs over a mask that is several times sparser (boxes of unlike size rarely
+        // suppress each other) -- which matters because that loop runs at the pace of the slowest lane of the warp.
+        if (thresh > 0.0) {
+            const float tq = __fmul_rn(thresh_f, 0.999998f);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                unsigned c = half ? cand_hi : cand_lo, keep = c;
+                while (c) {
+                    const int k = __ffs((int)c) - 1;
+                    c &= c - 1;
+                    const float ak = ca[half * 32 + k];
+                    if (fminf(ra, ak) < __fmul_rn(tq, fmaxf(ra, ak))) keep &= ~(1u << k);
+                }
+                if (half) cand_hi = keep; else cand_lo = keep;
+            }
+        }
         u64 cand = (u64)cand_lo | ((u64)cand_hi << 32);
         while (cand) {
             const int k = __ffsll((long long)cand) - 1;
