@@ -356,18 +356,25 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     const long long tt0 = clock64();
 #endif
     extern __shared__ u64 s_blk[];                               // [SUPER][SUPER][64] diagonal super-block
-    __shared__ u64 s_col[SUPER], s_kept[SUPER], s_prev[SUPER];
+    __shared__ u64 s_col[SUPER], s_kept[SUPER];
     __shared__ int s_order[SUPER * 64];
     const int nt = min(SUPER, col_tiles - T0);
     // The mask kernel runs concurrently (other stream / SM partition) and publishes, per super-COLUMN, how many of its
-    // tiles are in memory; CTA 0 needs super-column s (its diagonal blocks and the urgent update), the bulk updaters
+    // tiles are in memory; CTA 0 needs super-column s (its diagonal blocks) and s+1 (push-ahead), the bulk updaters
     // super-column s+1.  The sort order was written before the first launch.  So the
     // launch may stage while the previous one is still resolving (PDL), and only then waits for that one's results.
+    const int c0n = T0 + SUPER, ncols_next = max(0, min(SUPER, col_tiles - c0n));       // the next super-tile's columns
     if (tid == 0) {
         int need = 0;
         for (int c = T0; c < T0 + nt; ++c) need += c + 1;
         const volatile int *flag = row_done + s_idx;
         while (*flag < need) __nanosleep(64);
+        if (ncols_next > 0) {                                // push-ahead (below) reads this super-tile's rows of super-column s+1
+            need = 0;
+            for (int c = c0n; c < c0n + ncols_next; ++c) need += c + 1;
+            flag = row_done + s_idx + 1;
+            while (*flag < need) __nanosleep(64);
+        }
         __threadfence();
     }
     __syncthreads();
@@ -383,46 +390,22 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     asm volatile("cp.async.commit_group;" ::: "memory");
     pdl_enter();
     if (tid < SUPER) {
+        // complete: the bulk updaters of the previous launch pushed the kept rows of super-tiles < s-1, its CTA 0 those of
+        // super-tile s-1 (push-ahead, below) -- there is no update left to do before the first tile can be resolved
         s_col[tid] = tid < nt ? removed[T0 + tid] : 0ull;
         s_kept[tid] = 0ull;
-        s_prev[tid] = s_idx > 0 ? kept_bits[T0 - SUPER + tid] : 0ull;
-    }
-    __syncthreads();
-    // B: urgent update -- kept rows of super-tile s-1 against this super-tile's columns (SUPER x nt blocks)
-    if (s_idx > 0) {
-        const int pt0 = T0 - SUPER;
-        const int nblk = SUPER * nt;                                       // <= 256 blocks: 8 per warp, all in flight
-        ulonglong2 w[8];
-        u64 kb[8];
-        int bcol[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = warp + u * (SCAN_THREADS / 32);
-            bcol[u] = -1;
-            kb[u] = 0ull;
-            w[u] = make_ulonglong2(0ull, 0ull);
-            if (k < nblk) {
-                const int tp = k / nt, b = k - tp * nt;
-                kb[u] = s_prev[tp];
-                bcol[u] = b;
-                if (kb[u]) w[u] = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(pt0 + tp) * col_tiles + (T0 + b)) * 64) + lane);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (bcol[u] < 0 || kb[u] == 0ull) continue;                   // warp-uniform
-            const u64 v = warp_or(select2(w[u], kb[u], lane));
-            if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(&s_col[bcol[u]]), (unsigned long long)v);
-        }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #ifdef AZN_NMS_TRACE
     const long long tt1 = clock64();
 #endif
-    // C: the 16 tiles in order.  Iteration b: warp 0 resolves tile b; warps 1..31 gather, for column b+1, the words of
+    // The 16 tiles in order.  Iteration b: warp 0 resolves tile b; warps 1..31 gather, for column b+1, the words of
     // the rows kept in tiles 0..b-1 of this super-tile; warp 0 adds tile b's own rows once it knows them.
     int nkept = *nkept_ptr;
+    const int push_col = (warp >= 16 && warp - 16 < ncols_next) ? c0n + (warp - 16) : -1;       // warp-uniform
+    ulonglong2 pend_w = make_ulonglong2(0ull, 0ull);
+    u64 pend_kb = 0ull;
     for (int b = 0; b < nt; ++b) {
         if (warp == 0) {
             const int row0 = (T0 + b) * 64;
@@ -453,22 +436,54 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
             if ((kept >> (lane + 32)) & 1ull) keep[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = s_order[b * 64 + 32 + lane];
             if (lane == 0) { s_kept[b] = kept; kept_bits[T0 + b] = kept; }
             nkept += __popcll(kept);
-        } else if (b + 1 < nt && b >= 1) {
-            u64 acc = 0;
-            for (int p = tid - 32; p < b * 64; p += SCAN_THREADS - 32) {
-                const int tp = p >> 6, i = p & 63;
-                if ((s_kept[tp] >> i) & 1ull) acc |= s_blk[(size_t)(tp * SUPER + b + 1) * 64 + i];
+        } else {
+            // Push-ahead: the kept rows of tile b-1 go into the `removed` words of the NEXT super-tile's columns while
+            // warp 0 resolves tile b (warps 16..31, one column each; the 512-byte block is loaded in one iteration and
+            // folded in the next, so its L2 latency never sits on the per-tile barrier).  The next launch then finds its
+            // columns complete and starts resolving at once: no "urgent" update on the serial path.
+            if (push_col >= 0) {
+                if (pend_kb) {
+                    const u64 v = warp_or(select2(pend_w, pend_kb, lane));
+                    if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + push_col), (unsigned long long)v);
+                    pend_kb = 0ull;
+                }
+                if (b >= 1) {
+                    const u64 kb = s_kept[b - 1];
+                    if (kb) {
+                        pend_w = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(T0 + b - 1) * col_tiles + push_col) * 64) + lane);
+                        pend_kb = kb;
+                    }
+                }
             }
-            acc = warp_or(acc);
-            if (lane == 0 && acc) atomicOr(reinterpret_cast<unsigned long long *>(&s_col[b + 1]), (unsigned long long)acc);
+            if (b + 1 < nt && b >= 1) {
+                u64 acc = 0;
+                for (int p = tid - 32; p < b * 64; p += SCAN_THREADS - 32) {
+                    const int tp = p >> 6, i = p & 63;
+                    if ((s_kept[tp] >> i) & 1ull) acc |= s_blk[(size_t)(tp * SUPER + b + 1) * 64 + i];
+                }
+                acc = warp_or(acc);
+                if (lane == 0 && acc) atomicOr(reinterpret_cast<unsigned long long *>(&s_col[b + 1]), (unsigned long long)acc);
+            }
         }
         __syncthreads();
+    }
+    if (push_col >= 0) {                                     // the block still in flight, then the last tile's rows
+        if (pend_kb) {
+            const u64 v = warp_or(select2(pend_w, pend_kb, lane));
+            if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + push_col), (unsigned long long)v);
+        }
+        const u64 kb = s_kept[nt - 1];
+        if (kb) {
+            const ulonglong2 w = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(T0 + nt - 1) * col_tiles + push_col) * 64) + lane);
+            const u64 v = warp_or(select2(w, kb, lane));
+            if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + push_col), (unsigned long long)v);
+        }
     }
     if (tid == 0) {
         *nkept_ptr = nkept;
         if (last) *keep_count = nkept;
 #ifdef AZN_NMS_TRACE
-        printf("nms super %d: stage+urgent %lld cycles, 16 tiles %lld cycles\n", s_idx, tt1 - tt0, clock64() - tt1);
+        printf("nms super %d: stage %lld cycles, 16 tiles %lld cycles\n", s_idx, tt1 - tt0, clock64() - tt1);
 #endif
     }
 }
