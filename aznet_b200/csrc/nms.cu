@@ -167,7 +167,10 @@ __device__ __forceinline__ bool box_valid(const float4 &b) {
     return __fsub_rn(b.z, b.x) > -1.f && __fsub_rn(b.w, b.y) > -1.f;
 }
 __device__ __forceinline__ bool pair_intersects(const float4 &a, const float4 &b) {
-    return __fsub_rn(a.z, b.x) > -1.f && __fsub_rn(b.z, a.x) > -1.f && __fsub_rn(a.w, b.y) > -1.f && __fsub_rn(b.w, a.y) > -1.f;
+    // branch-free: the minimum of the four differences against -1 (`&&` made the compiler emit a divergent branch
+    // region per pair: 135 BSSY/BSYNC pairs in the unrolled tile loop)
+    const float dx = fminf(__fsub_rn(a.z, b.x), __fsub_rn(b.z, a.x)), dy = fminf(__fsub_rn(a.w, b.y), __fsub_rn(b.w, a.y));
+    return fminf(dx, dy) > -1.f;
 }
 
 // One 64-thread CTA per 64 x 64 tile of the upper triangle (linear block id -> (row tile, col tile)); thread =
@@ -223,14 +226,14 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
             } else if (rt != ct && cn == 64) {               // the bulk of the triangle: full off-diagonal tiles, no guards
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    if (pair_intersects(rb, cb[k])) cand_lo |= 1u << k;
-                    if (pair_intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+                    cand_lo |= pair_intersects(rb, cb[k]) ? (1u << k) : 0u;
+                    cand_hi |= pair_intersects(rb, cb[k + 32]) ? (1u << k) : 0u;
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    if (k >= start && k < cn && pair_intersects(rb, cb[k])) cand_lo |= 1u << k;
-                    if (k + 32 >= start && k + 32 < cn && pair_intersects(rb, cb[k + 32])) cand_hi |= 1u << k;
+                    cand_lo |= ((k >= start) & (k < cn) & pair_intersects(rb, cb[min(k, 63)])) ? (1u << k) : 0u;
+                    cand_hi |= ((k + 32 >= start) & (k + 32 < cn) & pair_intersects(rb, cb[k + 32])) ? (1u << k) : 0u;
                 }
             }
         } else {
@@ -722,7 +725,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1
             const int upd_cols = min(SUPER, col_tiles - (si + 1) * SUPER);
             long updaters = (si == 0 || upd_cols <= 0) ? 0 : ((long)si * SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
-            const int upd_cap = ms != s ? 15 : SUPER_UPDATERS;        // partitioned: the chain owns 8 SMs (2 such CTAs each)
+            const int upd_cap = ms != s ? 7 : SUPER_UPDATERS;         // partitioned: the chain owns 8 SMs -- CTA 0 keeps one to itself
             if (updaters > upd_cap) updaters = upd_cap;
             AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + (unsigned)updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
                                     (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
