@@ -102,6 +102,21 @@ def make_boxes(n, im_h=600, im_w=1000, seed=3, lo=16.0, hi=400.0):
     return b
 
 
+def make_detect_proposals(counts, im_h, im_w, seed=21, cap=None):
+    """Proposal lists for the detection step: f64 [n_img, cap, 4] (zero padded) with, per image, pairs that share a
+    feature-space cell but not their image-space box and exact duplicates (the dedup / un-dedup of _frcnn_forward,
+    lib/detect/test.py:280-288, 311-313).  Shared by oracle/gen_golden.py --only detect and the tests."""
+    cap = max(counts) if cap is None else cap
+    boxes = np.zeros((len(counts), max(cap, 1), 4))
+    for i, c in enumerate(counts):
+        b = make_boxes(c, im_h, im_w, seed=seed + i, lo=12, hi=500)
+        if c > 40:
+            b[30:40] = b[5:15] + 0.25
+            b[c - 3:] = b[:3]
+        boxes[i, :c] = b
+    return boxes
+
+
 def make_rois(n, im_h=600, im_w=1000, seed=3, n_img=1):
     """f32 [n,5] ROI blob (batch_index, x1,y1,x2,y2); batch indices round-robin over n_img."""
     b = make_boxes(n, im_h, im_w, seed)

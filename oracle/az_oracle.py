@@ -17,10 +17,17 @@ the pin is the reference's own code executed in the authoring container:
   * _bbox_pred/_clip_boxes/_unwrap_adj_pred/_az_forward/im_propose/test_net
     selection are checked against lib/detect/test.py (mechanically converted
     py2->py3 into oracle/_ref/, never committed) through tests/golden/search_*.npz;
-  * the Caffe layers (ROIPooling, InnerProduct) cannot be built here (no
-    glog/gflags/boost/BLAS headers): PARITY UNPINNED for those two, the restatement
-    of Forward_cpu is the oracle (cross-checked bitwise with torchvision's CPU
-    roi_pool, which implements the same algorithm).
+  * frcnn_forward / test_net_select / apply_nms are checked against the reference's own
+    im_detect, test_net (detections.pkl) and apply_nms run by oracle/gen_golden.py --only
+    detect with HashDetNet (tests/golden/detect.npz; bit for bit);
+  * the Caffe layers: Caffe as a whole cannot be built here (no glog/gflags/boost/BLAS/protoc),
+    but the layer SOURCES on the path compile unmodified against the stand-in framework
+    headers of oracle/caffe_shim (oracle/build_ref.py -> oracle/_ref/libcaffe_layers_ref.so):
+    ROIPooling (+argmax), GRN, Sigmoid, ReLU, Softmax, MAX Pooling are pinned BIT FOR BIT to
+    Forward_cpu of those sources (tests/golden/caffe_layers.npz + fresh random inputs);
+    InnerProduct's layer code is pinned the same way, its fp32 summation order is not (the
+    reference's BLAS is un-vendored: ATLAS | MKL | OpenBLAS, no pinned version), so the fc
+    layers stay tolerance-based, as north_star states.
 """
 from __future__ import annotations
 
@@ -138,6 +145,23 @@ def inner_product(x, w, b, threads=None):
 def relu(x):
     """caffe-fast-rcnn/src/caffe/layers/relu_layer.cpp:16-19."""
     return np.maximum(x, np.float32(0))
+
+
+def max_pool_ceil(x, kernel=2, stride=2):
+    """PoolingLayer (MAX, pad 0), caffe-fast-rcnn/src/caffe/layers/pooling_layer.cpp: output size
+    ceil((H - kernel) / stride) + 1 (:93-96), windows clipped to the map (:152-155), strict > from -FLT_MAX (:157-166;
+    a NaN never wins).  x f32 [n,C,H,W]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, C, H, W = x.shape
+    ph = int(np.ceil(np.float32(H - kernel) / stride)) + 1
+    pw = int(np.ceil(np.float32(W - kernel) / stride)) + 1
+    out = np.full((n, C, ph, pw), -np.finfo(np.float32).max, np.float32)
+    for dy in range(kernel):
+        for dx in range(kernel):
+            v = x[:, :, dy::stride, dx::stride][:, :, :ph, :pw]
+            o = out[:, :, :v.shape[2], :v.shape[3]]
+            np.copyto(o, v, where=v > o)
+    return out
 
 
 def grn(x):

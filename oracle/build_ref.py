@@ -11,7 +11,11 @@ GPU box with the snapshot like any other built artefact):
   * lib/utils/bbox.pyx -> oracle/_ref/cython_bbox*.so   unmodified (recall parity only)
   * lib/detect/{test,tune,config}.py, lib/utils/{blob,timer}.py -> oracle/_ref/pyref/  mechanical
     py2 -> py3 text conversion (print statement, xrange, iteritems, has_key, cPickle, tabs),
-    used ONLY by oracle/gen_golden.py in this container.
+    used ONLY by oracle/gen_golden.py in this container (and, when present, by bench.py's reference arm).
+  * caffe-fast-rcnn/src/caffe/layers/{roi_pooling,grn,sigmoid,softmax,relu,inner_product,pooling}_layer.cpp
+    -> oracle/_ref/libcaffe_layers_ref.so   UNMODIFIED sources, #included by oracle/ref_caffe_wrap.cpp and
+    compiled against the stand-in framework headers of oracle/caffe_shim (Caffe itself cannot be built here);
+    bindings in oracle/ref_caffe.py.
 
 Nothing is copied into tracked files.  No-op (returns False) when /root/reference is absent,
 e.g. on the GPU box, which uses the prebuilt .so files.
@@ -93,12 +97,25 @@ def _convert_python():
         open(os.path.join(dst, rel), "w").write(_py2to3(src))
 
 
+def _build_caffe_layers():
+    layers = os.path.join(REF, "caffe-fast-rcnn", "src", "caffe", "layers")
+    so = os.path.join(OUT, "libcaffe_layers_ref.so")
+    deps = [os.path.join(HERE, "ref_caffe_wrap.cpp"), os.path.join(HERE, "caffe_shim", "caffe", "shim.hpp")]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return
+    # -ffp-contract=off: one rounding per float operation, like the reference's own (pre-FMA-default) builds
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                           "-I", os.path.join(HERE, "caffe_shim"), "-I", layers, deps[0], "-o", so])
+
+
 def build() -> bool:
     if not os.path.isdir(os.path.join(REF, "lib", "utils")):
         return False
     os.makedirs(OUT, exist_ok=True)
-    _build_cython()
+    if not have_ref_cython():
+        _build_cython()
     _convert_python()
+    _build_caffe_layers()
     return True
 
 

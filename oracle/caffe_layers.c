@@ -8,13 +8,17 @@
  * (aznet_b200/) never does.
  *
  * Parity status:
- *   - azo_roi_pool_fwd      PARITY UNPINNED by the reference (its only ROI-pool
- *                           test is a GPU gradient check,
+ *   - azo_roi_pool_fwd      pinned BIT FOR BIT (values and argmax) to Forward_cpu of the
+ *                           reference's own unmodified roi_pooling_layer.cpp, compiled against
+ *                           oracle/caffe_shim into oracle/_ref/libcaffe_layers_ref.so
+ *                           (tests/test_oracle.py, tests/golden/caffe_layers.npz).  The reference
+ *                           itself holds no forward test (only a GPU gradient check,
  *                           caffe-fast-rcnn/src/caffe/test/test_roi_pooling_layer.cpp:90-101).
- *                           Cross-checked bitwise against torchvision.ops.roi_pool (CPU)
- *                           in tests/test_oracle.py.
- *   - azo_sigmoid           formula pinned by test_neuron_layer.cpp:202-217.
- *   - azo_softmax           formula pinned (1e-4) by test_softmax_layer.cpp:40-72.
+ *                           Secondary cross-check: torchvision.ops.roi_pool (CPU).
+ *   - azo_sigmoid           pinned bit for bit to the compiled sigmoid_layer.cpp (and by
+ *                           test_neuron_layer.cpp:202-217 to 4 ulp).
+ *   - azo_softmax           pinned bit for bit to the compiled softmax_layer.cpp (and by
+ *                           test_softmax_layer.cpp:40-72 to 1e-4).
  *   - azo_nms               pinned against the reference's own lib/utils/nms.pyx
  *                           compiled here (oracle/_ref) and by tests/golden/nms_*.npz.
  *

@@ -1,0 +1,2 @@
+// oracle/caffe_shim -- TEST INFRASTRUCTURE: forwards to the stand-in declarations in shim.hpp
+#include "caffe/shim.hpp"

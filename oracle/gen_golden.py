@@ -8,7 +8,7 @@ The fixtures store inputs' seeds + the reference's outputs; tests/ compare the o
 restatement (CPU suite) and the CUDA path (gpu suite) against them.
 
     python oracle/gen_golden.py                 # rewrites tests/golden/
-    python oracle/gen_golden.py --only blob     # one fixture file (div | nms | search | blob | tune)
+    python oracle/gen_golden.py --only blob     # one fixture file (div | nms | search | blob | tune | detect | layers)
 """
 from __future__ import annotations
 
@@ -258,6 +258,143 @@ def gen_tune(rconfig):
     np.savez_compressed(os.path.join(GOLD, "tune.npz"), **out)
 
 
+# name, num_classes, [(H, W)] per image, MAX_SIZE, BATCH_SIZE, proposals per image, NMS threshold
+DETECT_CASES = [
+    ("voc_3sizes", 21, [(600, 1000), (375, 500), (480, 640), (600, 1000), (375, 500), (480, 640)], 1000, 10000,
+     [300, 257, 300, 150, 300, 64], 0.3),          # six PNGs of three sizes; max_per_set = 40 * 6 < pushed -> thresholds
+    ("coco_480x640", 81, [(480, 640)] * 4, 800, 10000, [300, 300, 12, 0], 0.5),   # 81 classes; an image w/o proposals
+    ("voc_chunked_375x500", 21, [(375, 500)] * 2, 1000, 100, [300, 150], 0.3),    # dedup per BATCH_SIZE = 100 boxes
+]
+
+
+def detect_case_proposals(shapes, counts, seed=21):
+    """Per-image proposal arrays of a DETECT_CASES row (same generator for the goldens and the tests): image i uses
+    synth.make_detect_proposals with seed + i on its own shape."""
+    return [synth.make_detect_proposals([c], h, w, seed=seed + i)[0, :c] for i, ((h, w), c) in enumerate(zip(shapes, counts))]
+
+
+def gen_detect(rtest, rconfig):
+    """The reference's own detection path with HashDetNet: im_detect -> _frcnn_forward (lib/detect/test.py:259-318,
+    416-430), test_net's per-class selection + heap + final filter (:541-668, detections.pkl) and apply_nms
+    (:467-484, what imdb.evaluate_detections receives)."""
+    import pickle
+    import tempfile
+    import cv2
+    cfg = rconfig.cfg
+    out = {}
+    keep = (cfg.TEST.MAX_SIZE, cfg.SEAR.BATCH_SIZE, cfg.TEST.NMS)
+    for name, ncls, shapes, max_size, bs, counts, nms_t in DETECT_CASES:
+        cfg.TEST.MAX_SIZE, cfg.SEAR.BATCH_SIZE, cfg.TEST.NMS = max_size, bs, nms_t
+        props = detect_case_proposals(shapes, counts)
+        net = synth.HashDetNet(seed=13, num_classes=ncls)
+        with tempfile.TemporaryDirectory() as tmp:
+            paths = []
+            for i, sh in enumerate(shapes):
+                paths.append(os.path.join(tmp, "%d.png" % i))
+                cv2.imwrite(paths[-1], np.zeros(sh + (3,), np.uint8))
+            seen = {}
+
+            class Imdb:
+                name = "synth"
+                image_index = list(range(len(shapes)))
+                num_classes = ncls
+                classes = ["c%d" % j for j in range(ncls)]
+
+                def image_path_at(self, i):
+                    return paths[i]
+
+                def evaluate_detections(self, all_boxes, output_dir):
+                    seen["nms"] = all_boxes
+
+            cfg.ROOT_DIR = tmp
+            rconfig.cfg_set_path("golden")
+            prop_file = os.path.join(tmp, "proposals.pkl")
+            with open(prop_file, "wb") as f:
+                pickle.dump({"boxes": props, "time": 0.0, "recall": 0}, f)
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                rtest.test_net({"full": net}, prop_file, Imdb())
+            with open(os.path.join(rconfig.get_output_dir(Imdb(), net), "detections.pkl"), "rb") as f:
+                dets = pickle.load(f)
+            # im_detect of the smallest non-empty image (bounded fixture size)
+            i0 = min((c, i) for i, c in enumerate(counts) if c > 0)[1]
+            sc, pb = rtest.im_detect({"full": net}, cv2.imread(paths[i0]), props[i0], ncls)
+        out[name + "_imdet_index"] = np.array(i0)
+        out[name + "_imdet_scores"] = sc.astype(np.float32)        # f32 values promoted to f64 by vstack (:266, 315)
+        assert np.array_equal(out[name + "_imdet_scores"].astype(np.float64), sc)
+        out[name + "_imdet_boxes"] = pb
+        for tag, ab in (("det", dets), ("nms", seen["nms"])):
+            rows, cnt = [], np.zeros((ncls, len(shapes)), np.int32)
+            for j in range(ncls):
+                for i in range(len(shapes)):
+                    d = ab[j][i]
+                    if isinstance(d, list):
+                        continue
+                    cnt[j, i] = d.shape[0]
+                    assert d.dtype == np.float32
+                    rows.append(d)
+            out["%s_%s_rows" % (name, tag)] = np.vstack(rows) if rows else np.zeros((0, 5), np.float32)
+            out["%s_%s_count" % (name, tag)] = cnt
+        out[name + "_last_line"] = np.array(buf.getvalue().strip().split("\n")[-1])
+        print("detect:", name, "rows", out[name + "_det_rows"].shape[0], "after nms", out[name + "_nms_rows"].shape[0],
+              "|", buf.getvalue().strip().split("\n")[-1])
+    cfg.TEST.MAX_SIZE, cfg.SEAR.BATCH_SIZE, cfg.TEST.NMS = keep
+    np.savez_compressed(os.path.join(GOLD, "detect.npz"), **out)
+
+
+def layer_roi_cases():
+    """ROI sets of the Caffe-layer goldens: edge cases (coordinates landing on .5 after the 1/16 scale, out-of-image,
+    malformed, whole image) and the 739 'natural' regions of the full-zoom cascade of a 600x1000 image."""
+    from oracle import az_oracle as O
+    edge = synth.make_rois(200, 600, 1000, seed=5, n_img=2)
+    edge[:10, 1:] = np.round(edge[:10, 1:] / 8) * 8
+    edge[10:14, 1:] += 900
+    edge[14] = [0, 50, 50, 40, 40]
+    edge[15] = [1, -300, -200, -20, -30]
+    edge[16] = [0, 0, 0, 999, 599]
+    edge[17] = [1, 0, 0, 1000, 600]
+    lv, regs = np.array([[0, 0, 999, 599.]]), []
+    for _ in range(5):
+        regs.append(lv)
+        lv = O.divide_region(lv, 10.0)
+    nat = np.vstack(regs)
+    nat = np.hstack([np.zeros((nat.shape[0], 1)), nat]).astype(np.float32)
+    return edge, nat
+
+
+def gen_layers():
+    """Forward_cpu of the reference's own layer sources (oracle/_ref/libcaffe_layers_ref.so, oracle/ref_caffe.py)."""
+    from oracle import ref_caffe as RC
+    out = {}
+    feat = synth.make_conv_maps(2, 6, 38, 63, seed=7)
+    feat[1] -= 0.5                                          # negative values as well (pre-ReLU style maps)
+    feat[1, 0, 3, 4] = np.nan
+    feat[1, 1, 10:20, 10:30] = -0.0
+    edge, nat = layer_roi_cases()
+    for tag, rois in (("edge", edge), ("natural", nat)):
+        o, am = RC.roi_pool_fwd(feat, rois, want_argmax=True)
+        out["roi_%s_rois" % tag], out["roi_%s_out" % tag], out["roi_%s_argmax" % tag] = rois, o, am.astype(np.int16 if am.max() < 32768 else np.int32)
+    out["roi_feat_seed"] = np.array(7)
+    x = np.random.default_rng(1).standard_normal((3, 40, 7, 7)).astype(np.float32)
+    x[0, :, 0, 0] = 0
+    out["grn_in"] = x
+    with np.errstate(all="ignore"):
+        out["grn_out"] = RC.grn(x)
+    z = np.linspace(-30, 30, 2001).astype(np.float32)
+    out["sigmoid_in"], out["sigmoid_out"] = z, RC.sigmoid(z)
+    out["relu_out"] = RC.relu(z)
+    s = (np.random.default_rng(2).standard_normal((60, 81)) * 5).astype(np.float32)
+    out["softmax_in"], out["softmax_out"] = s, RC.softmax(s)
+    xx = np.random.default_rng(3).standard_normal((9, 4, 7, 7)).astype(np.float32)
+    w = np.random.default_rng(4).standard_normal((13, 196)).astype(np.float32)
+    b = np.random.default_rng(5).standard_normal(13).astype(np.float32)
+    out["ip_x"], out["ip_w"], out["ip_b"], out["ip_out"] = xx, w, b, RC.inner_product(xx, w, b)
+    pm = np.random.default_rng(6).standard_normal((1, 3, 75, 125)).astype(np.float32)
+    out["maxpool_in"], out["maxpool_out"] = pm, RC.max_pool(pm)
+    np.savez_compressed(os.path.join(GOLD, "caffe_layers.npz"), **out)
+    print("layers: roi edge", out["roi_edge_out"].shape, "natural", out["roi_natural_out"].shape, "maxpool", out["maxpool_out"].shape)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     rtest, rconfig, div, nms = load_reference()
@@ -272,6 +409,10 @@ def main():
         gen_blob(rtest, rconfig)
     if only in (None, "tune"):
         gen_tune(rconfig)
+    if only in (None, "detect"):
+        gen_detect(rtest, rconfig)
+    if only in (None, "layers"):
+        gen_layers()
 
 
 if __name__ == "__main__":

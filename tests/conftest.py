@@ -16,7 +16,7 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(d, n + ".npz"), allow_pickle=False) for n in ("div", "nms", "search", "tune")}
+    return {n: np.load(os.path.join(d, n + ".npz"), allow_pickle=False) for n in ("div", "nms", "search", "tune", "detect", "caffe_layers")}
 
 
 @pytest.fixture(scope="session")

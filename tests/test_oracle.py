@@ -158,6 +158,113 @@ def test_roi_pool_matches_torchvision_cpu():
     assert np.array_equal(out, ref)
 
 
+def _layer_feat():
+    feat = synth.make_conv_maps(2, 6, 38, 63, seed=7)          # as oracle/gen_golden.py::gen_layers
+    feat[1] -= 0.5
+    feat[1, 0, 3, 4] = np.nan
+    feat[1, 1, 10:20, 10:30] = -0.0
+    return feat
+
+
+def test_caffe_layers_golden(golden):
+    """The restated layers equal, BIT FOR BIT, what Forward_cpu of the reference's own unmodified layer sources
+    produced (oracle/_ref/libcaffe_layers_ref.so via oracle/gen_golden.py --only layers): ROI max-pool incl. argmax on
+    the edge-ROI set and the 739 natural regions (negative values, NaN, -0 in the map), GRN incl. the 0/0 position,
+    sigmoid, ReLU, softmax, MAX pooling in ceil mode; InnerProduct within fp32 summation-order noise."""
+    g = golden["caffe_layers"]
+    feat = _layer_feat()
+    for tag in ("edge", "natural"):
+        out, am = O.roi_pool_fwd(feat, g["roi_%s_rois" % tag], want_argmax=True)
+        assert np.array_equal(out.view(np.uint32), g["roi_%s_out" % tag].view(np.uint32)), tag
+        assert np.array_equal(am, g["roi_%s_argmax" % tag].astype(np.int32)), tag
+    assert g["roi_natural_rois"].shape[0] == 739
+    with np.errstate(all="ignore"):
+        assert np.array_equal(O.grn(g["grn_in"]).view(np.uint32), g["grn_out"].view(np.uint32))
+    assert np.isnan(g["grn_out"][0, :, 0, 0]).all()
+    assert np.array_equal(O.sigmoid(g["sigmoid_in"]), g["sigmoid_out"])
+    assert np.array_equal(O.relu(g["sigmoid_in"]), g["relu_out"])
+    assert np.array_equal(O.softmax(g["softmax_in"]), g["softmax_out"])
+    x = g["ip_x"].reshape(g["ip_x"].shape[0], -1)               # axis-1 flattening = c*49 + ph*7 + pw (SURVEY Q12)
+    np.testing.assert_allclose(O.inner_product(x, g["ip_w"], g["ip_b"]), g["ip_out"], rtol=0, atol=2e-5)
+    assert np.array_equal(O.max_pool_ceil(g["maxpool_in"]), g["maxpool_out"])
+
+
+def test_against_compiled_reference_layers():
+    """Fresh random inputs through the compiled reference layer sources (authoring container and GPU box: the .so
+    travels prebuilt)."""
+    from oracle import ref_caffe as RC
+    if not RC.available():
+        pytest.skip("oracle/_ref/libcaffe_layers_ref.so not built")
+    rng = np.random.default_rng(123)
+    for t in range(3):
+        C, H, W = int(rng.integers(1, 9)), int(rng.integers(5, 40)), int(rng.integers(5, 64))
+        feat = rng.standard_normal((2, C, H, W)).astype(np.float32)
+        rois = synth.make_rois(400, H * 16, W * 16, seed=50 + t, n_img=2)
+        rois[:40, 1:] = np.round(rois[:40, 1:] / 8) * 8
+        rois[40:60, 1:] -= 100
+        for pooled, sc in ((7, 0.0625), (6, 0.125), (3, 0.25)):
+            a, am = O.roi_pool_fwd(feat, rois, pooled, sc, want_argmax=True)
+            b, bm = RC.roi_pool_fwd(feat, rois, pooled, sc, want_argmax=True)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(am, bm)
+        x = rng.standard_normal((5, 16, 7, 7)).astype(np.float32)
+        assert np.array_equal(O.grn(x), RC.grn(x))
+        z = (rng.standard_normal((33, 21)) * 6).astype(np.float32)
+        assert np.array_equal(O.softmax(z), RC.softmax(z)) and np.array_equal(O.sigmoid(z), RC.sigmoid(z))
+        pm = rng.standard_normal((1, 2, int(rng.integers(3, 50)), int(rng.integers(3, 50)))).astype(np.float32)
+        assert np.array_equal(O.max_pool_ceil(pm), RC.max_pool(pm))
+    with pytest.raises(RuntimeError):
+        RC.roi_pool_fwd(np.zeros((1, 1, 4, 4), np.float32), np.array([[2, 0, 0, 10, 10]], np.float32))
+
+
+def _detect_case(g, name, ncls, shapes, max_size, bs, counts):
+    from oracle.gen_golden import detect_case_proposals
+    cfg = O.OracleCfg(TEST_MAX_SIZE=max_size, BATCH_SIZE=bs)
+    net = synth.HashDetNet(seed=13, num_classes=ncls)
+    props = detect_case_proposals(shapes, counts)
+    per_image = []
+    for (h, w), p in zip(shapes, props):
+        if p.shape[0] == 0:
+            per_image.append(None)
+            continue
+        s_ref, p_ref, _ = O.frcnn_forward({"full": net, "fc": net}, (h, w, 3), p, ncls,
+                                          {"conv5_3": np.zeros((1, 1, 2, 2), np.float32)}, cfg)
+        per_image.append((s_ref, p_ref))
+    return per_image
+
+
+def _flatten(all_boxes, ncls, n_img):
+    rows, cnt = [], np.zeros((ncls, n_img), np.int32)
+    for j in range(ncls):
+        for i in range(n_img):
+            d = all_boxes[j][i]
+            if isinstance(d, list):
+                continue
+            cnt[j, i] = d.shape[0]
+            rows.append(d)
+    return (np.vstack(rows) if rows else np.zeros((0, 5), np.float32)), cnt
+
+
+def test_detection_path_golden(golden):
+    """frcnn_forward / test_net_select / apply_nms of the oracle equal the reference's OWN im_detect, test_net
+    (detections.pkl) and apply_nms (what evaluate_detections received) bit for bit (oracle/gen_golden.py --only
+    detect; HashDetNet scores are tie-free 24-bit draws per (roi, class))."""
+    from oracle.gen_golden import DETECT_CASES
+    g = golden["detect"]
+    for name, ncls, shapes, max_size, bs, counts, nms_t in DETECT_CASES:
+        per_image = _detect_case(g, name, ncls, shapes, max_size, bs, counts)
+        i0 = int(g[name + "_imdet_index"])
+        assert np.array_equal(per_image[i0][0], g[name + "_imdet_scores"].astype(np.float64)), name
+        assert np.array_equal(per_image[i0][1].view(np.uint64), g[name + "_imdet_boxes"].view(np.uint64)), name
+        all_boxes, thresh = O.test_net_select(per_image, ncls)
+        rows, cnt = _flatten(all_boxes, ncls, len(shapes))
+        assert np.array_equal(cnt, g[name + "_det_count"]), name
+        assert np.array_equal(rows.view(np.uint32), g[name + "_det_rows"].view(np.uint32)), name
+        rows, cnt = _flatten(O.apply_nms(all_boxes, nms_t), ncls, len(shapes))
+        assert np.array_equal(cnt, g[name + "_nms_count"]), name
+        assert np.array_equal(rows.view(np.uint32), g[name + "_nms_rows"].view(np.uint32)), name
+        assert np.isfinite(thresh[1:]).any(), "the case must exercise the max_per_set threshold"
+
+
 def test_roi_pool_argmax_and_errors():
     feat = synth.make_conv_maps(1, 4, 10, 12, seed=1)
     rois = np.array([[0, 0, 0, 191, 159], [0, 16, 16, 47, 47]], np.float32)
