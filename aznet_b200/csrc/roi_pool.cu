@@ -369,12 +369,62 @@ template <> struct KeyOps<false> {
     static __device__ __forceinline__ unsigned max3(unsigned a, unsigned b, unsigned c) { return (unsigned)__vimax3_s32((int)a, (int)b, (int)c); }
 };
 
+// Pooling of one ROI's bin rows with a FIXED number of map rows per column (variant 2 of the keys kernel).
+// The generic loop nest of roi_pool_keys_kernel spends ~8 instructions of control flow per shared-memory load (the
+// per-lane row count nh makes the row loop a real loop with a tail).  Here MH = the warp-wide maximum bin height
+// is a template parameter and a lane whose bin is shorter re-reads its last row (max is idempotent), so that a
+// column reduce is straight-line code: MH loads at precomputed row offsets and (MH+1)/2 packed max instructions.
+// Column re-use between neighbouring bins is kept (see the generic path).
+template <typename K, int MH, bool PLAIN>
+__device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbase, int nh, int row_step, int sv, unsigned gb,
+                                                bool phv, uint4 *__restrict__ optr, int L) {
+#define AZN_MX2(D, A) \
+    (D).x = K::max3((D).x, (A).x, (A).x); (D).y = K::max3((D).y, (A).y, (A).y); (D).z = K::max3((D).z, (A).z, (A).z); (D).w = K::max3((D).w, (A).w, (A).w)
+#define AZN_MX3(D, A, B) \
+    (D).x = K::max3((D).x, (A).x, (B).x); (D).y = K::max3((D).y, (A).y, (B).y); (D).z = K::max3((D).z, (A).z, (B).z); (D).w = K::max3((D).w, (A).w, (B).w)
+    int roff[MH];
+    const int last = max(nh, 1) - 1;
+#pragma unroll
+    for (int t = 0; t < MH; ++t) roff[t] = min(t, last) * row_step;
+    const unsigned a0 = PLAIN ? 0u : K::lowest();
+    int w_cached = -1;                                       // warp-uniform
+    uint4 cache = make_uint4(a0, a0, a0, a0);
+#pragma unroll
+    for (int pw = 0; pw < ST_P; ++pw) {
+        const unsigned wb = __shfl_sync(0xffffffffu, gb, ST_P + pw);
+        const int ws = wb & 0xffff, we = (int)(wb >> 16);    // warp-uniform
+        uint4 acc = make_uint4(a0, a0, a0, a0);
+        if (we > ws) {
+            int w = ws;
+            if (w == w_cached) { acc = cache; ++w; }         // the previous bin's last column, already reduced
+#pragma unroll 1
+            for (; w < we; ++w) {
+                const uint4 *q = rowbase + w * sv;
+                uint4 c = q[roff[0]];
+                if (MH == 2) { const uint4 b = q[roff[1]]; AZN_MX2(c, b); }
+                if (MH >= 3) { const uint4 b = q[roff[1]], d = q[roff[2]]; AZN_MX3(c, b, d); }
+                if (MH == 4) { const uint4 b = q[roff[3]]; AZN_MX2(c, b); }
+                if (MH >= 5) { const uint4 b = q[roff[3]], d = q[roff[4]]; AZN_MX3(c, b, d); }
+                if (MH == 6) { const uint4 b = q[roff[5]]; AZN_MX2(c, b); }
+                AZN_MX2(acc, c);
+                cache = c;
+            }
+            w_cached = we - 1;
+        }
+        uint4 res = make_uint4(0u, 0u, 0u, 0u);
+        if (we > ws && nh > 0) res = PLAIN ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
+        if (phv) st_stream(optr + (size_t)pw * L, res);
+    }
+#undef AZN_MX2
+#undef AZN_MX3
+}
+
 template <bool BF16, int SV>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
                      const int32_t *__restrict__ bucket_off, const int32_t *__restrict__ perm,
-                     float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices) {
+                     float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices, int variant) {
     typedef KeyOps<BF16> K;
     typedef typename K::Exact Exact;
     extern __shared__ uint4 s_dyn[];
@@ -472,6 +522,8 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 else bin_bounds(lane - ST_P, q.bin_w, q.start_w, W, a, b);
                 gb = (unsigned)a | ((unsigned)b << 16);
             }
+            // the tallest bin of the ROI (warp-uniform): selects the fixed-height variant
+            const int mh = __reduce_max_sync(0xffffffffu, lane < ST_P ? (int)(gb >> 16) - (int)(gb & 0xffff) : 0);
             // A pass pools one COLUMN of bins (fixed pw): every lane of the warp then has the same [ws, we), so the
             // inner loops are warp-uniform; lanes differ only in their bin row (ph = lane / SV) and channel vector.
 #pragma unroll 1
@@ -481,6 +533,24 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 const unsigned hb = __shfl_sync(0xffffffffu, gb, min(ph, ST_P - 1));
                 const int hs = hb & 0xffff, nh = phv ? (int)(hb >> 16) - hs : 0;
                 uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
+                if (variant == 2 && !exact && mh <= 6) {     // warp-uniform: fixed-height straight-line column reduces
+                    const uint4 *rb = s_map + (size_t)min(hs, H - 1) * row_step + j;
+#define AZN_FIX(MHH)                                                                                   \
+    do {                                                                                               \
+        if (plain) pool_bins_fixed<K, MHH, true>(rb, nh, row_step, SV, gb, phv, optr, L);              \
+        else pool_bins_fixed<K, MHH, false>(rb, nh, row_step, SV, gb, phv, optr, L);                   \
+    } while (0)
+                    switch (mh) {
+                    case 0: case 1: AZN_FIX(1); break;
+                    case 2: AZN_FIX(2); break;
+                    case 3: AZN_FIX(3); break;
+                    case 4: AZN_FIX(4); break;
+                    case 5: AZN_FIX(5); break;
+                    default: AZN_FIX(6); break;
+                    }
+#undef AZN_FIX
+                    continue;
+                }
                 const uint4 *rowbase = s_map + (size_t)hs * row_step + j;
                 // Column re-use.  Consecutive bins of a row overlap by at most one map column -- bin p+1 starts at
                 // floor((p+1) b) >= ceil((p+1) b) - 1, the last column of bin p, and clamping keeps that order; for ROIs
@@ -748,6 +818,7 @@ extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, i
 
 namespace {
 int g_pool_mode = 0;           // azn_roi_pool_tune: 0 automatic, 1 direct kernels only, 2 staged whenever possible
+int g_pool_variant = 2;        // keys kernel: 1 generic loop nest, 2 fixed-height column reduces (azn_roi_pool_tune(mode + 10 * variant))
 
 constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the staged kernel may ask for
 
@@ -822,7 +893,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         }                                                                                                                \
         roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                                 \
             (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,         \
-            (int)nchunk, nslices);                                                                                       \
+            (int)nchunk, nslices, g_pool_variant);                                                                                   \
     } while (0)
     if (MODE == 0) {
         if (sv == 8) AZN_KEY_LAUNCH(8); else if (sv == 4) AZN_KEY_LAUNCH(4); else AZN_KEY_LAUNCH(2);
@@ -847,7 +918,10 @@ bool want_staged(int n_img, int H, int W, int PH, int PW, const int32_t *n_rois,
 }
 }  // namespace
 
-extern "C" void azn_roi_pool_tune(int mode) { g_pool_mode = mode; }
+extern "C" void azn_roi_pool_tune(int mode) {
+    g_pool_mode = mode % 10;
+    if (mode >= 10) g_pool_variant = mode / 10;          // 12 / 22: staged with the generic / fixed-height pooling loop
+}
 
 extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                                 const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,

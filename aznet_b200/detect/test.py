@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from .config import cfg, get_output_dir
+from . import batched
 from .. import ops
 from ..detector import DetectEngine, DetectionSet
 from ..engine import SearchEngine, im_scale_for, search_depth
@@ -160,7 +161,10 @@ def _az_forward(net, im, all_boxes, conv=None):
             index, inv = _dedup(blobs['rois'])
             blobs['rois'] = blobs['rois'][index, :]
             boxes = boxes[index, :]
-        out, conv = _net_forward(net, blobs, conv, cfg.SEAR.AZ_CONV)
+        # the 'full' net is asked for (and `conv` caches) SEAR.FRCNN_CONV, like the reference (test.py:222-226), so that
+        # the shared maps can be handed to a skip-layer detector; the 'fc' net is fed SEAR.AZ_CONV (:231-236)
+        full_pass = conv is None or 'fc' not in net.keys()
+        out, conv = _net_forward(net, blobs, conv, cfg.SEAR.FRCNN_CONV if full_pass else cfg.SEAR.AZ_CONV)
         z = out['zoom_prob']
         scores = out['adj_prob']
         pred = _bbox_pred_clip(boxes, out['adj_bbox'], im.shape)
@@ -196,30 +200,22 @@ def _frcnn_forward(net, im, all_boxes, num_classes, conv=None):
 
 
 # --------------------------------------------------------------------------- the adaptive search
-_ENGINES = {}
-
-
-def _engine_for(az_net: Net, im_shape, num_proposals):
-    key = (id(az_net.head), int(im_shape[0]), int(im_shape[1]), tuple(cfg.TEST.SCALES), cfg.TEST.MAX_SIZE, cfg.SEAR.MIN_SIDE,
-           float(cfg.SEAR.Tz), float(cfg.SEAR.Tc), bool(cfg.SEAR.FIXED_PROPOSAL_NUM), num_proposals, cfg.SEAR.BATCH_SIZE,
-           float(cfg.DEDUP_BOXES), float(cfg.EPS))
-    eng = _ENGINES.get(key)
-    if eng is None:
-        if len(_ENGINES) > 16:
-            _ENGINES.clear()
-        fixed = bool(cfg.SEAR.FIXED_PROPOSAL_NUM) or num_proposals is not None
-        eng = SearchEngine(az_net.head, 1, im_shape[0], im_shape[1], scales=tuple(cfg.TEST.SCALES), max_size=cfg.TEST.MAX_SIZE,
-                           min_side=cfg.SEAR.MIN_SIDE, tz=float(cfg.SEAR.Tz), tc=float(cfg.SEAR.Tc), fixed_num=fixed,
-                           num_proposals=num_proposals if num_proposals is not None else cfg.SEAR.NUM_PROPOSALS,
-                           batch_size=cfg.SEAR.BATCH_SIZE, dedup=float(cfg.DEDUP_BOXES), eps=float(cfg.EPS),
-                           spatial_scale=az_net.spatial_scale)
-        _ENGINES[key] = eng
-    return eng
+def _engine_for(az_net: Net, im_shape, num_proposals, n_img=1):
+    return batched.search_engine(az_net, im_shape, n_img, num_proposals)
 
 
 def _fast_route(net):
     full = net.get('full') if hasattr(net, 'get') else None
     return isinstance(full, Net) and full.kind == "az" and full.backbone is not None and len(cfg.TEST.SCALES) == 1
+
+
+def _device_maps(full: Net, im, names):
+    """One image -> the bf16 NHWC maps `names` of one backbone pass, network input built on the device
+    (azn_image_blob: the mean-subtract + cv2.resize of _get_image_blob, test.py:27-59, without the host)."""
+    pix = torch.from_numpy(np.ascontiguousarray(im, dtype=np.uint8)[None]).to(full.dev)
+    scale = im_scale_for(im.shape[0], im.shape[1], tuple(cfg.TEST.SCALES), cfg.TEST.MAX_SIZE)
+    bb = full.backbone
+    return bb.run_padded(ops.image_blob(pix, scale, bb.pixel_means, bb.cpad_in), taps=tuple(names))
 
 
 def im_propose(net, im, return_conv=False, num_proposals=None):
@@ -230,16 +226,14 @@ def im_propose(net, im, return_conv=False, num_proposals=None):
     if _fast_route(net):
         full = net['full']
         eng = _engine_for(full, im.shape, num_proposals)
-        data, _ = _get_image_blob(im)
         names = tuple(cfg.SEAR.FRCNN_CONV)
         taps = None
         if return_conv and names != ('conv5_3',):
             # skip-layer detector (experiments/cfgs/voc_skip.yml:20): hand out conv3_3 / conv4_3 / conv5_3 of the same pass
-            taps = full.backbone.taps_from_data(torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(full.dev),
-                                                tuple(set(names) | {'conv5_3'}))
+            taps = _device_maps(full, im, tuple(dict.fromkeys(names + ('conv5_3',))))
             nhwc = taps['conv5_3']
         else:
-            conv_dev, nhwc = full.conv_from_data(data)
+            nhwc = _device_maps(full, im, ('conv5_3',))['conv5_3']
         eng.propose(nhwc)
         boxes, _, n_eval, depth = eng.results()
         Y, num_eval, k = boxes[0], int(n_eval[0]), int(depth[0])
@@ -249,9 +243,10 @@ def im_propose(net, im, return_conv=False, num_proposals=None):
             for name in names:
                 dev = taps[name].permute(0, 3, 1, 2).float().contiguous()
                 host = dev.cpu().numpy()
-                full._maps[name] = ((id(host), host.__array_interface__["data"][0], host.shape), dev, taps[name], host)
+                full._maps[name] = (full._map_key(host), dev, taps[name], host)
                 conv[name] = host
         elif return_conv:
+            conv_dev = nhwc.permute(0, 3, 1, 2).float().contiguous()
             host = conv_dev.cpu().numpy()
             full._last_conv = (host, conv_dev, nhwc)
             conv = {name: host for name in cfg.SEAR.FRCNN_CONV}
@@ -346,48 +341,31 @@ def apply_nms(all_boxes, thresh):
 
 
 # --------------------------------------------------------------------------- device-resident detection
-_DET_ENGINES = {}
-
-
 def _fast_detect_route(net, key='full'):
     n = net.get(key) if hasattr(net, 'get') else None
     return (isinstance(n, Net) and n.kind in ("frcnn", "frcnn_skip") and len(cfg.TEST.SCALES) == 1
             and (key == 'fc' or n.backbone is not None))
 
 
-def _maps_from_data(full: Net, data, names):
-    """The bf16 NHWC maps a detector needs from one backbone pass: conv5_3 alone, or the skip-layer taps as a dict."""
-    if tuple(names) == ('conv5_3',):
-        return full.conv_from_data(data)[1]
-    return full.backbone.taps_from_data(torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(full.dev), tuple(names))
+def _boxes_to_device(prop_list, cap, dev):
+    """Per-image proposal arrays (f64 [R_i, >=4]) -> zero-padded device tensor [n, cap, 4] + int32 counts."""
+    n = len(prop_list)
+    host = np.zeros((n, cap, 4))
+    counts = np.zeros((n,), np.int32)
+    for k, b in enumerate(prop_list):
+        if b is None or len(b) == 0:
+            continue
+        counts[k] = b.shape[0]
+        host[k, :b.shape[0]] = b[:, :4]
+    return torch.from_numpy(host).to(dev), torch.from_numpy(counts).to(dev)
 
 
-def _det_engine_for(fr_net: Net, im_shape, cap):
-    key = (id(fr_net.head), int(im_shape[0]), int(im_shape[1]), int(cap), tuple(cfg.TEST.SCALES), cfg.TEST.MAX_SIZE,
-           cfg.SEAR.BATCH_SIZE, float(cfg.DEDUP_BOXES), float(cfg.EPS))
-    eng = _DET_ENGINES.get(key)
-    if eng is None:
-        if len(_DET_ENGINES) > 8:
-            _DET_ENGINES.clear()
-        eng = DetectEngine(fr_net.head, 1, im_shape[0], im_shape[1], cap, scales=tuple(cfg.TEST.SCALES),
-                           max_size=cfg.TEST.MAX_SIZE, batch_size=cfg.SEAR.BATCH_SIZE, dedup=float(cfg.DEDUP_BOXES),
-                           eps=float(cfg.EPS), spatial_scale=fr_net.spatial_scale)
-        _DET_ENGINES[key] = eng
-    return eng
-
-
-def _detect_on_device(fr_net: Net, nhwc, im_shape, boxes, dset: DetectionSet, i):
-    """One image's detection step into slot i of the set.  boxes: f64 ndarray [R,4] or (device [1,cap,4], count [1])."""
-    if isinstance(boxes, tuple):
-        boxes_d, count_d = boxes
-    else:
-        R = boxes.shape[0]
-        cap = max(int(cfg.SEAR.NUM_PROPOSALS), (R + 127) // 128 * 128)
-        boxes_d = torch.zeros((1, cap, 4), dtype=torch.float64, device=fr_net.dev)
-        boxes_d[0, :R] = torch.from_numpy(np.ascontiguousarray(boxes[:, :4], dtype=np.float64)).to(fr_net.dev)
-        count_d = torch.tensor([R], dtype=torch.int32, device=fr_net.dev)
-    eng = _det_engine_for(fr_net, im_shape, boxes_d.shape[1])
-    eng.detect(nhwc, boxes_d, count_d, **dset.slot(i, i + 1))
+def _proposal_cap(max_rows):
+    """Row capacity of the detector's proposal buffer: the configured proposal count (SEAR.NUM_PROPOSALS exists only
+    after cfg_set_mode -- tools/test_det_net.py never calls it -- so fall back to TEST.NUM_PROPOSALS), or more when a
+    proposals.pkl holds longer lists."""
+    want = int(getattr(cfg.SEAR, 'NUM_PROPOSALS', cfg.TEST.NUM_PROPOSALS))
+    return max(want, (int(max_rows) + 127) // 128 * 128)
 
 
 def _finish_on_device(dset: DetectionSet, skip, imdb, output_dir):
@@ -405,7 +383,70 @@ def _finish_on_device(dset: DetectionSet, skip, imdb, output_dir):
     imdb.evaluate_detections(nms_dets, output_dir)
 
 
+class _BatchClock:
+    """The reference's per-image Timer (utils/timer.py) for batched execution: average_time = wall time since the
+    first batch was submitted / images finished."""
+
+    def __init__(self):
+        self.timer, self.t0 = Timer(), None
+
+    def start(self):
+        import time
+        if self.t0 is None:
+            self.t0 = time.time()
+
+    def done(self, n_images):
+        import time
+        t = self.timer
+        t.calls += n_images
+        t.total_time = time.time() - self.t0
+        t.average_time = t.total_time / max(t.calls, 1)
+        return t.average_time
+
+
 # --------------------------------------------------------------------------- dataset drivers
+def _test_proposals_batched(net, imdb, prop_boxes, stats):
+    """The fast route of test_proposals: read-ahead, same-shape batches, device image blob, batched backbone + search
+    (detect/batched.py).  Prints the reference's per-image lines as each batch finishes."""
+    full = net['full']
+    num_images = len(imdb.image_index)
+    copy_stream = torch.cuda.Stream(device=full.dev)
+    clock = _BatchClock()
+    done = [0]
+
+    def finish(item):
+        db, fetch = item
+        r = fetch.get()
+        if int(r['status'][0]) != 0:
+            raise RuntimeError("search capacity overflow on device (status %d)" % int(r['status'][0]))
+        avg = clock.done(db.n)
+        for k, i in enumerate(db.idx):
+            c = int(r['count'][k])
+            prop_boxes[i] = r['boxes'][k, :c].copy()
+            stats['num_eval'] += int(r['n_eval'][k])
+            print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(c, int(r['n_eval'][k]), int(r['depth'][k])))
+            done[0] += 1
+            print('im_prop: {:d}/{:d} {:.3f}s'.format(done[0], num_images, avg))
+
+    pending = None
+    for batch in batched.ImageFeeder(imdb, range(num_images)):
+        clock.start()
+        db = batched.DeviceBatch(full, batch, copy_stream)
+        eng = _engine_for(full, db.shape + (3,), None, db.n_pad)
+        eng.propose(db.maps)
+        fetch = batched.Fetch(boxes=eng.out_boxes[:db.n], count=eng.out_count[:db.n], n_eval=eng.n_eval[:db.n],
+                              depth=eng.depth[:db.n], status=eng.status)
+        stats['h2d_bytes'] += db.h2d_bytes
+        stats['d2h_bytes'] += fetch.bytes
+        stats['batches'] += 1
+        if pending is not None:
+            finish(pending)
+        pending = (db, fetch)
+    if pending is not None:
+        finish(pending)
+    return clock.timer
+
+
 def test_proposals(net, imdb):
     """Generate proposals on an image database and pickle them (test.py:486-539)."""
     import cv2
@@ -414,14 +455,21 @@ def test_proposals(net, imdb):
     output_dir = get_output_dir(imdb, net['full'])
     if not os.path.exists(output_dir):
         os.makedirs(output_dir)
-    t = Timer()
     num_boxes = 0.0
-    for i in range(num_images):
-        im = cv2.imread(imdb.image_path_at(i))
-        t.tic()
-        prop_boxes[i] = im_propose(net, im)
-        t.toc()
-        print('im_prop: {:d}/{:d} {:.3f}s'.format(i + 1, num_images, t.average_time))
+    stats = test_proposals.last_stats = {'route': 'host', 'num_eval': 0, 'h2d_bytes': 0, 'd2h_bytes': 0, 'batches': 0}
+    if cfg.SEAR.APPEND_BOXES:
+        raise NotImplementedError("SEAR.APPEND_BOXES (off by default, config.py:170) is outside the hot path")
+    if _fast_route(net):
+        stats['route'] = 'batched'
+        t = _test_proposals_batched(net, imdb, prop_boxes, stats)
+    else:
+        t = Timer()
+        for i in range(num_images):
+            im = cv2.imread(imdb.image_path_at(i))
+            t.tic()
+            prop_boxes[i] = im_propose(net, im)
+            t.toc()
+            print('im_prop: {:d}/{:d} {:.3f}s'.format(i + 1, num_images, t.average_time))
     recall = 0
     prop = {'boxes': prop_boxes, 'time': t.average_time, 'recall': recall}
     with open(os.path.join(output_dir, 'proposals.pkl'), 'wb') as f:
@@ -463,6 +511,58 @@ def _finish_detections(all_boxes, thresh, skip, imdb, output_dir):
     imdb.evaluate_detections(nms_dets, output_dir)
 
 
+def _detect_batch(fr_net, db, boxes_d, count_d, dset, copy_back=True):
+    """One batch's Fast R-CNN step (DetectEngine over all images of the batch) into the set-wide buffers at the
+    batch's image indices."""
+    eng = batched.detect_engine(fr_net, db.shape, db.n_pad, boxes_d.shape[1])
+    dets, tops, cnt = eng.detect(db.maps, boxes_d, count_d)
+    idx = torch.tensor(db.idx, dtype=torch.long, device=fr_net.dev)
+    dset.dets.index_copy_(0, idx, dets[:db.n])
+    dset.top_scores.index_copy_(0, idx, tops[:db.n])
+    dset.det_count.index_copy_(0, idx, cnt[:db.n])
+    return eng
+
+
+def _test_net_batched(net, prop_boxes, imdb, dset, todo, stats):
+    """Fast route of test_net: batches of same-shape images, backbone + DetectEngine per batch, nothing but the
+    uint8 pixels and the proposal lists crosses PCIe before the set-wide finish."""
+    full = net['full']
+    num_images = len(imdb.image_index)
+    copy_stream = torch.cuda.Stream(device=full.dev)
+    clock = _BatchClock()
+    done, num_boxes = 0, 0.0
+    cap = _proposal_cap(max([prop_boxes[i].shape[0] for i in todo] + [1]))
+    pending = None
+    for batch in batched.ImageFeeder(imdb, todo):
+        clock.start()
+        db = batched.DeviceBatch(full, batch, copy_stream, taps=full.conv_names)
+        plist = [prop_boxes[i] for i in db.idx] + [None] * (db.n_pad - db.n)
+        boxes_d, count_d = _boxes_to_device(plist, cap, full.dev)
+        _detect_batch(full, db, boxes_d, count_d, dset)
+        ev = torch.cuda.Event()
+        ev.record()
+        stats['h2d_bytes'] += db.h2d_bytes + boxes_d.numel() * 8
+        stats['batches'] += 1
+        if pending is not None:
+            pdb, pev = pending
+            pev.synchronize()
+            avg = clock.done(pdb.n)
+            for i in pdb.idx:
+                done += 1
+                num_boxes += prop_boxes[i].shape[0]
+                print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(done, num_images, avg, 0.0))
+        pending = (db, ev)
+    if pending is not None:
+        pdb, pev = pending
+        pev.synchronize()
+        avg = clock.done(pdb.n)
+        for i in pdb.idx:
+            done += 1
+            num_boxes += prop_boxes[i].shape[0]
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(done, num_images, avg, 0.0))
+    return clock.timer, num_boxes
+
+
 def test_net(net, prop_file, imdb):
     """Fast R-CNN over pre-computed proposals (test.py:541-668)."""
     import cv2
@@ -480,39 +580,77 @@ def test_net(net, prop_file, imdb):
     if not os.path.exists(output_dir):
         os.makedirs(output_dir)
     _t = {'im_detect': Timer(), 'misc': Timer()}
-    skip = set()
-    fast = _fast_detect_route(net)
-    dset = DetectionSet(num_images, imdb.num_classes, max_per_image, net['full'].dev) if fast else None
-    for i in range(num_images):
-        if prop_boxes[i].shape[0] == 0:
-            skip.add(i)
-            continue
-        im = cv2.imread(imdb.image_path_at(i))
-        _t['im_detect'].tic()
-        if fast:
-            data, _ = _get_image_blob(im)
-            nhwc = _maps_from_data(net['full'], data, net['full'].conv_names)
-            _detect_on_device(net['full'], nhwc, im.shape, prop_boxes[i], dset, i)
-            torch.cuda.current_stream().synchronize()
-            num_boxes += prop_boxes[i].shape[0]
-            _t['im_detect'].toc()
-            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
-                                                                _t['misc'].average_time))
-            continue
-        scores, boxes = im_detect(net, im, prop_boxes[i], imdb.num_classes)
-        num_boxes += scores.shape[0]
-        _t['im_detect'].toc()
-        _t['misc'].tic()
-        _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, imdb.num_classes)
-        _t['misc'].toc()
-        print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
-                                                            _t['misc'].average_time))
-    if fast:
+    skip = set(i for i in range(num_images) if prop_boxes[i].shape[0] == 0)
+    stats = test_net.last_stats = {'route': 'host', 'h2d_bytes': 0, 'batches': 0}
+    if _fast_detect_route(net):
+        stats['route'] = 'batched'
+        dset = DetectionSet(num_images, imdb.num_classes, max_per_image, net['full'].dev)
+        _t['im_detect'], num_boxes = _test_net_batched(net, prop_boxes, imdb, dset, [i for i in range(num_images) if i not in skip], stats)
         _finish_on_device(dset, skip, imdb, output_dir)
     else:
+        for i in range(num_images):
+            if i in skip:
+                continue
+            im = cv2.imread(imdb.image_path_at(i))
+            _t['im_detect'].tic()
+            scores, boxes = im_detect(net, im, prop_boxes[i], imdb.num_classes)
+            num_boxes += scores.shape[0]
+            _t['im_detect'].toc()
+            _t['misc'].tic()
+            _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, imdb.num_classes)
+            _t['misc'].toc()
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
+                                                                _t['misc'].average_time))
         _finish_detections(all_boxes, thresh, skip, imdb, output_dir)
     print('The average time is proposal {:.3f}s, detection {:.3f}s'.format(prop['time'], _t['im_detect'].average_time))
     print('On average, {0} boxes per image are generated'.format(num_boxes / num_images))
+
+
+def _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats):
+    """Fast route of test_net_shared: one backbone pass per batch serves the search and the detector; the proposals
+    never leave the device (the search engine's output buffers are the detector's input)."""
+    full, fr = sc_net['full'], frcnn_net['fc']
+    num_images = len(imdb.image_index)
+    copy_stream = torch.cuda.Stream(device=full.dev)
+    clock = _BatchClock()
+    state = {'done': 0, 'boxes': 0.0}
+    taps = tuple(dict.fromkeys(tuple(fr.conv_names) + ('conv5_3',)))
+
+    def finish(item):
+        db, fetch = item
+        r = fetch.get()
+        if int(r['status'][0]) != 0:
+            raise RuntimeError("search capacity overflow on device (status %d)" % int(r['status'][0]))
+        avg = clock.done(db.n)
+        for k in range(db.n):
+            print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(int(r['count'][k]), int(r['n_eval'][k]),
+                                                                                   int(r['depth'][k])))
+            state['boxes'] += int(r['count'][k])
+            state['done'] += 1
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(state['done'], num_images, avg, 0.0))
+
+    pending = None
+    for batch in batched.ImageFeeder(imdb, range(num_images)):
+        clock.start()
+        db = batched.DeviceBatch(full, batch, copy_stream, taps=taps)
+        maps = db.maps
+        conv5 = maps['conv5_3'] if isinstance(maps, dict) else maps
+        eng = _engine_for(full, db.shape + (3,), None, db.n_pad)
+        eng.propose(conv5)
+        if db.n_pad > db.n:
+            eng.out_count[db.n:].zero_()                      # padding images propose nothing
+        if fr.kind != "frcnn_skip":
+            db.maps = conv5
+        _detect_batch(fr, db, eng.out_boxes, eng.out_count, dset)
+        fetch = batched.Fetch(count=eng.out_count[:db.n], n_eval=eng.n_eval[:db.n], depth=eng.depth[:db.n], status=eng.status)
+        stats['h2d_bytes'] += db.h2d_bytes
+        stats['batches'] += 1
+        if pending is not None:
+            finish(pending)
+        pending = (db, fetch)
+    if pending is not None:
+        finish(pending)
+    return clock.timer, state['boxes']
 
 
 def test_net_shared(sc_net, frcnn_net, imdb):
@@ -529,42 +667,24 @@ def test_net_shared(sc_net, frcnn_net, imdb):
     if not os.path.exists(output_dir):
         os.makedirs(output_dir)
     _t = {'im_detect': Timer(), 'misc': Timer()}
-    fast = _fast_route(sc_net) and _fast_detect_route(frcnn_net, 'fc')
-    dset = DetectionSet(num_images, imdb.num_classes, max_per_image, sc_net['full'].dev) if fast else None
-    for i in range(num_images):
-        im = cv2.imread(imdb.image_path_at(i))
-        _t['im_detect'].tic()
-        if fast:
-            # proposals never leave the device: the search engine's output buffers are the detector's input
-            full = sc_net['full']
-            eng = _engine_for(full, im.shape, None)
-            data, _ = _get_image_blob(im)
-            fr = frcnn_net['fc']
-            if fr.kind == "frcnn_skip":          # one backbone pass serves the search (conv5_3) and the three ROI pools
-                nhwc = _maps_from_data(full, data, tuple(dict.fromkeys(fr.conv_names + ('conv5_3',))))
-                eng.propose(nhwc['conv5_3'])
-            else:
-                nhwc = _maps_from_data(full, data, ('conv5_3',))
-                eng.propose(nhwc)
-            _detect_on_device(fr, nhwc, im.shape, (eng.out_boxes, eng.out_count), dset, i)
-            n_prop, n_eval, depth = int(eng.out_count[0].item()), int(eng.n_eval[0].item()), int(eng.depth[0].item())
-            print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(n_prop, n_eval, depth))
-            num_boxes += n_prop
-            _t['im_detect'].toc()
-            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
-                                                                _t['misc'].average_time))
-            continue
-        scores, boxes = im_detect_shared(sc_net, frcnn_net, im, imdb.num_classes)
-        num_boxes += scores.shape[0]
-        _t['im_detect'].toc()
-        _t['misc'].tic()
-        _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, imdb.num_classes)
-        _t['misc'].toc()
-        print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
-                                                            _t['misc'].average_time))
-    if fast:
+    stats = test_net_shared.last_stats = {'route': 'host', 'h2d_bytes': 0, 'batches': 0}
+    if _fast_route(sc_net) and _fast_detect_route(frcnn_net, 'fc') and not cfg.SEAR.APPEND_BOXES:
+        stats['route'] = 'batched'
+        dset = DetectionSet(num_images, imdb.num_classes, max_per_image, sc_net['full'].dev)
+        _t['im_detect'], num_boxes = _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats)
         _finish_on_device(dset, set(), imdb, output_dir)
     else:
+        for i in range(num_images):
+            im = cv2.imread(imdb.image_path_at(i))
+            _t['im_detect'].tic()
+            scores, boxes = im_detect_shared(sc_net, frcnn_net, im, imdb.num_classes)
+            num_boxes += scores.shape[0]
+            _t['im_detect'].toc()
+            _t['misc'].tic()
+            _select_detections(scores, boxes, thresh, top_scores, max_per_image, max_per_set, all_boxes, i, imdb.num_classes)
+            _t['misc'].toc()
+            print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(i + 1, num_images, _t['im_detect'].average_time,
+                                                                _t['misc'].average_time))
         _finish_detections(all_boxes, thresh, set(), imdb, output_dir)
     print('The average detection time is {:.3f}s'.format(_t['im_detect'].average_time))
     print('On average, {0} boxes per image are proposed'.format(num_boxes / num_images))

@@ -239,3 +239,16 @@ class SyntheticImdb:
 
     def competition_mode(self, on):
         pass
+
+
+class InMemoryImdb(SyntheticImdb):
+    """An image database whose images are arrays in host memory.  `image_at(i)` is the optional hook the batched
+    drivers use instead of cv2.imread(image_path_at(i)) (aznet_b200/detect/batched.py); everything else is the
+    reference's imdb protocol."""
+
+    def __init__(self, images, num_classes=21, name="synthetic_mem"):
+        SyntheticImdb.__init__(self, ["<memory:%d>" % i for i in range(len(images))], num_classes, name)
+        self._images = list(images)
+
+    def image_at(self, i):
+        return self._images[i]

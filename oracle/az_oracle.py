@@ -212,6 +212,21 @@ class _Blob:
         return self.shape[0] if self.shape else 0
 
 
+class _PortLayers:
+    roi_pool_fwd = staticmethod(lambda *a, **k: roi_pool_fwd(*a, **k))
+    relu = staticmethod(lambda x: relu(x))
+    sigmoid = staticmethod(lambda x: sigmoid(x))
+    softmax = staticmethod(lambda x: softmax(x))
+
+
+class _RefLayers:
+    def __init__(self):
+        from . import ref_caffe
+        if not ref_caffe.available():
+            raise RuntimeError("oracle/_ref/libcaffe_layers_ref.so is not built (oracle/build_ref.py)")
+        self.roi_pool_fwd, self.relu, self.sigmoid, self.softmax = ref_caffe.roi_pool_fwd, ref_caffe.relu, ref_caffe.sigmoid, ref_caffe.softmax
+
+
 class OracleNet:
     """Duck-typed caffe.Net (caffe-fast-rcnn/python/caffe/pycaffe.py:52-95) running the
     fc part of AZ-Net (models/Pascal/VGG16/az-net/test_fc.prototxt:14-232) or of the
@@ -222,7 +237,11 @@ class OracleNet:
              'full' net; without one it is the 'fc' net whose inputs are (conv5_3, rois).
     """
 
-    def __init__(self, weights, kind="az", backbone=None, name="oracle", cfg=None, threads=None, act_round=None):
+    def __init__(self, weights, kind="az", backbone=None, name="oracle", cfg=None, threads=None, act_round=None, layers="port"):
+        # layers="ref": ROIPooling / ReLU / Sigmoid / Softmax run the reference's OWN layer sources compiled into
+        # oracle/_ref/libcaffe_layers_ref.so (oracle/ref_caffe.py); InnerProduct stays the threaded sgemm below (the
+        # reference's BLAS is un-vendored).  Used by bench.py's reference arm.
+        self.L = _RefLayers() if layers == "ref" else _PortLayers()
         self.w = weights
         # optional storage rounding of the hidden activations (e.g. round_bf16): lets a test separate the
         # product's bf16 activation storage from everything else.  None = the reference's fp32 blobs.
@@ -253,12 +272,13 @@ class OracleNet:
             pool5 = skip_pool5(self.w, conv, rois, self.cfg.POOLED, act_round=self.act_round, threads=self.threads)
         else:
             conv = self.backbone(kwargs["data"]) if self.backbone is not None else kwargs["conv5_3"]
-            pool5 = roi_pool_fwd(conv, rois, self.cfg.POOLED, self.cfg.SPATIAL_SCALE)
+            pool5 = self.L.roi_pool_fwd(conv, rois, self.cfg.POOLED, self.cfg.SPATIAL_SCALE)
         t1 = time.perf_counter()
         x = pool5.reshape(pool5.shape[0], -1)            # K index = c*49 + ph*7 + pw (Q12)
         ip = lambda name, v: inner_product(v, self.w[name][0], self.w[name][1], self.threads)
         out = {}
         rnd = self.act_round
+        relu, sigmoid, softmax = self.L.relu, self.L.sigmoid, self.L.softmax
         if self.kind == "az":
             h6 = rnd(relu(ip("int6", x)))                 # dropout in TEST phase = identity
             h71 = rnd(relu(ip("int7_1", h6)))

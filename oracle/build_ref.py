@@ -93,8 +93,13 @@ def _convert_python():
         os.makedirs(os.path.join(dst, sub), exist_ok=True)
         open(os.path.join(dst, sub, "__init__.py"), "w").close()
     for rel in ("detect/test.py", "detect/tune.py", "detect/config.py", "utils/blob.py", "utils/timer.py"):
-        src = open(os.path.join(REF, "lib", rel)).read()
-        open(os.path.join(dst, rel), "w").write(_py2to3(src))
+        src = _py2to3(open(os.path.join(REF, "lib", rel)).read())
+        if rel == "detect/test.py":
+            # two more edits that keep the Python-2 / NumPy-1 meaning: integer division and the
+            # list-vs-array comparison `dets == []` (elementwise under NumPy 2)
+            src = src.replace("max_per_set = 800 / (imdb.num_classes - 1)", "max_per_set = 800 // (imdb.num_classes - 1)")
+            src = src.replace("if dets == []:", "if isinstance(dets, list) and dets == []:")
+        open(os.path.join(dst, rel), "w").write(src)
 
 
 def _build_caffe_layers():
@@ -131,6 +136,52 @@ def import_ref_cython():
         sys.path.insert(0, OUT)
     return (importlib.import_module("cython_div"), importlib.import_module("cython_nms"),
             importlib.import_module("cython_bbox"))
+
+
+def load_pyref():
+    """Import the converted reference modules of oracle/_ref/pyref (detect.test, detect.config) with the compiled
+    reference Cython modules behind them and stand-ins for the absent `easydict` / `caffe` packages.  Nothing is
+    built here: returns None when oracle/_ref is not populated.  The pyref tree shadows top-level `detect` and
+    `utils`; callers that also use aznet_b200.detect import that through its package name, so the two do not clash."""
+    import types
+    pyref = os.path.join(OUT, "pyref")
+    if not (have_ref_cython() and os.path.exists(os.path.join(pyref, "detect", "test.py"))):
+        return None
+    div, nms, bbox = import_ref_cython()
+
+    class EasyDict(dict):                      # 20-line stand-in for the absent `easydict`
+        def __init__(self, d=None, **kw):
+            super().__init__()
+            for k, v in dict(d or {}, **kw).items():
+                self[k] = v
+
+        def __setitem__(self, k, v):
+            if isinstance(v, dict) and not isinstance(v, EasyDict):
+                v = EasyDict(v)
+            super().__setitem__(k, v)
+
+        __setattr__ = __setitem__
+
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    ed = types.ModuleType("easydict")
+    ed.EasyDict = EasyDict
+    sys.modules["easydict"] = ed
+    sys.modules.setdefault("caffe", types.ModuleType("caffe"))
+    if pyref not in sys.path:
+        sys.path.insert(0, pyref)
+    import utils  # noqa  (pyref/utils)
+    sys.modules["utils.cython_nms"] = nms
+    sys.modules["utils.cython_bbox"] = bbox
+    sys.modules["utils.cython_div"] = div
+    utils.cython_nms, utils.cython_bbox, utils.cython_div = nms, bbox, div
+    import detect.test as rtest
+    import detect.config as rconfig
+    return rtest, rconfig, div, nms
 
 
 def have_ref_cython() -> bool:

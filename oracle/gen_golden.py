@@ -15,7 +15,6 @@ from __future__ import annotations
 import io
 import os
 import sys
-import types
 import contextlib
 
 import numpy as np
@@ -29,49 +28,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 def load_reference():
-    """Import the converted lib/detect/test.py with the compiled Cython modules behind it."""
+    """Build oracle/_ref from /root/reference and import the converted lib/detect/test.py with the compiled Cython
+    modules behind it (oracle/build_ref.py::load_pyref)."""
     assert build_ref.build(), "/root/reference is required to generate goldens"
-    div, nms, bbox = build_ref.import_ref_cython()
-    pyref = os.path.join(build_ref.OUT, "pyref")
-    # py3/NumPy-2 compatibility edits that keep Python-2 semantics (SURVEY appendix Q13):
-    p = os.path.join(pyref, "detect", "test.py")
-    s = open(p).read()
-    s = s.replace("max_per_set = 800 / (imdb.num_classes - 1)", "max_per_set = 800 // (imdb.num_classes - 1)")
-    s = s.replace("if dets == []:", "if isinstance(dets, list) and dets == []:")
-    open(p, "w").write(s)
-
-    class EasyDict(dict):                      # 20-line stand-in for the absent `easydict`
-        def __init__(self, d=None, **kw):
-            super().__init__()
-            for k, v in dict(d or {}, **kw).items():
-                self[k] = v
-
-        def __setitem__(self, k, v):
-            if isinstance(v, dict) and not isinstance(v, EasyDict):
-                v = EasyDict(v)
-            super().__setitem__(k, v)
-
-        __setattr__ = __setitem__
-
-        def __getattr__(self, k):
-            try:
-                return self[k]
-            except KeyError:
-                raise AttributeError(k)
-
-    ed = types.ModuleType("easydict")
-    ed.EasyDict = EasyDict
-    sys.modules["easydict"] = ed
-    sys.modules["caffe"] = types.ModuleType("caffe")
-    sys.path.insert(0, pyref)
-    import utils  # noqa  (pyref/utils)
-    sys.modules["utils.cython_nms"] = nms
-    sys.modules["utils.cython_bbox"] = bbox
-    sys.modules["utils.cython_div"] = div
-    utils.cython_nms, utils.cython_bbox, utils.cython_div = nms, bbox, div
-    import detect.test as rtest
-    import detect.config as rconfig
-    return rtest, rconfig, div, nms
+    return build_ref.load_pyref()
 
 
 def gen_div(div):
@@ -366,7 +326,7 @@ def gen_layers():
     """Forward_cpu of the reference's own layer sources (oracle/_ref/libcaffe_layers_ref.so, oracle/ref_caffe.py)."""
     from oracle import ref_caffe as RC
     out = {}
-    feat = synth.make_conv_maps(2, 6, 38, 63, seed=7)
+    feat = synth.make_conv_maps(2, 8, 38, 63, seed=7)
     feat[1] -= 0.5                                          # negative values as well (pre-ReLU style maps)
     feat[1, 0, 3, 4] = np.nan
     feat[1, 1, 10:20, 10:30] = -0.0

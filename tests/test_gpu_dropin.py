@@ -10,6 +10,7 @@ import pytest
 torch = pytest.importorskip("torch")
 
 from aznet_b200 import synth  # noqa: E402
+from helpers import RowMatcher, _same_blob_for_both_routes  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -168,9 +169,10 @@ def _small_nets(dev, num_classes=6):
     return az, fr, azw, frw
 
 
-def test_im_propose_fast_route_equals_host_route(dev, cfg, capsys):
+def test_im_propose_fast_route_equals_host_route(dev, cfg, capsys, monkeypatch):
     """Device-resident engine vs one-forward-per-level host loop over the same Net objects."""
     from aznet_b200.detect import test as T
+    _same_blob_for_both_routes(monkeypatch, dev)
     az, _, _, _ = _small_nets(dev)
     im = synth.make_images(1, 240, 320, seed=3)[0]
     Y_fast, conv = T.im_propose(az, im, return_conv=True)
@@ -274,12 +276,13 @@ def test_drivers_and_pickle_formats(dev, O, cfg, tmp_path, capsys):
     assert "The average detection time is" in capsys.readouterr().out
 
 
-def test_test_net_device_route_equals_host_route(dev, cfg, tmp_path, capsys):
+def test_test_net_device_route_equals_host_route(dev, cfg, tmp_path, capsys, monkeypatch):
     """test_net / test_net_shared with Net detectors (DetectEngine + set-wide finish on the device) against the
     reference's host loop over the same Net objects (numpy selection, heap thresholds, per-class NMS calls)."""
     import cv2
     from aznet_b200.detect import config as C
     from aznet_b200.detect import test as T
+    _same_blob_for_both_routes(monkeypatch, dev)
     az, fr, _, _ = _small_nets(dev)
     paths = []
     for i, im in enumerate(synth.make_images(4, 200, 300, seed=60)):
@@ -304,6 +307,7 @@ def test_test_net_device_route_equals_host_route(dev, cfg, tmp_path, capsys):
         capsys.readouterr()
         return pickle.load(open(det_file, "rb")), imdb.evaluated[0]
 
+    match = RowMatcher(atol=0.5)
     for shared in (False, True):
         pre_d, nms_d = run(fr, shared)
         pre_h, nms_h = run(Foreign(full=wrap(fr["full"]), fc=wrap(fr["fc"])), shared)
@@ -311,6 +315,93 @@ def test_test_net_device_route_equals_host_route(dev, cfg, tmp_path, capsys):
             for j in range(1, 6):
                 for i in range(4):
                     a, b = a_set[j][i], b_set[j][i]
-                    assert len(a) == len(b), (shared, j, i, len(a), len(b))
-                    if len(a):
-                        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-4)
+                    match.add(a, b)          # the batched route runs 4 images per GEMM, the host loop one
+    match.check(0.95, min_total=100)
+
+
+def test_batched_drivers_mixed_shapes_and_in_memory_imdb(dev, cfg, tmp_path, capsys, monkeypatch):
+    """test_proposals / test_net / test_net_shared on a database of TWO image shapes (7 images -> two same-shape
+    batches, padded to 8 and 2): results land at their image indices, equal the per-image im_propose / im_detect of the
+    same nets up to bf16 rounding flips, the reference's lines are printed once per image, and an imdb that offers
+    image_at(i) (in-memory arrays) gives the same proposals as the PNG files."""
+    import cv2
+    from aznet_b200.detect import config as C
+    from aznet_b200.detect import test as T
+    _same_blob_for_both_routes(monkeypatch, dev)
+    az, fr, _, _ = _small_nets(dev)
+    ims = synth.make_images(5, 200, 300, seed=80) + synth.make_images(2, 240, 200, seed=90)
+    order = [0, 5, 1, 2, 6, 3, 4]                              # shapes interleaved in database order
+    ims = [ims[k] for k in order]
+    paths = []
+    for i, im in enumerate(ims):
+        p = str(tmp_path / ("m%d.png" % i))
+        cv2.imwrite(p, im)
+        paths.append(p)
+    C.cfg.ROOT_DIR = str(tmp_path)
+    imdb = synth.SyntheticImdb(paths, num_classes=6, name="mixed")
+    T.test_proposals(az, imdb)
+    out = capsys.readouterr().out
+    assert T.test_proposals.last_stats["route"] == "batched" and T.test_proposals.last_stats["batches"] == 2
+    assert out.count("proposals, evaluate") == 7 and "im_prop: 7/7" in out and "im_prop: 1/7" in out
+    prop_file = os.path.join(C.get_output_dir(imdb, az["full"]), "proposals.pkl")
+    prop = pickle.load(open(prop_file, "rb"))
+    match = RowMatcher(atol=0.05)
+    for i, im in enumerate(ims):
+        assert prop["boxes"][i].dtype == np.float64 and 0 < prop["boxes"][i].shape[0] <= 300
+        match.add(prop["boxes"][i], T.im_propose(az, im))     # single-image engine on the same image
+    match.check(0.97, min_total=200)
+    capsys.readouterr()
+    mem = synth.InMemoryImdb(ims, num_classes=6, name="mixed_mem")
+    T.test_proposals(az, mem)
+    capsys.readouterr()
+    prop_mem = pickle.load(open(os.path.join(C.get_output_dir(mem, az["full"]), "proposals.pkl"), "rb"))
+    for i in range(7):
+        assert np.array_equal(prop_mem["boxes"][i], prop["boxes"][i])        # same batches, same kernels: bit-identical
+    # detection over the saved proposals; one image without proposals is skipped like the reference does
+    prop["boxes"][3] = np.zeros((0, 4))
+    pickle.dump(prop, open(prop_file, "wb"))
+    T.test_net(fr, prop_file, imdb)
+    out = capsys.readouterr().out
+    assert T.test_net.last_stats["route"] == "batched" and "im_detect: 6/7" in out and "im_detect: 7/7" not in out
+    dets = pickle.load(open(os.path.join(C.get_output_dir(imdb, fr["full"]), "detections.pkl"), "rb"))
+    assert all(isinstance(dets[j][3], list) and dets[j][3] == [] for j in range(6))
+    match = RowMatcher(atol=0.5)
+    for i in (0, 1, 4):
+        s_one, p_one = T.im_detect(fr, ims[i], prop["boxes"][i], 6)
+        for j in range(1, 6):
+            top = np.argsort(-s_one[:, j], kind="stable")[:100]
+            one = np.hstack((p_one[top, 4 * j:4 * j + 4], s_one[top, j:j + 1]))
+            thr = dets[j][i][:, 4].min() if len(dets[j][i]) else np.inf
+            match.add(dets[j][i], one[one[:, 4] >= thr - 1e-3])
+    match.check(0.95, min_total=200)
+    T.test_net_shared(az, fr, imdb)
+    out = capsys.readouterr().out
+    assert T.test_net_shared.last_stats["route"] == "batched" and "im_detect: 7/7" in out
+    assert out.count("proposals, evaluate") == 7
+
+
+def test_test_net_without_cfg_set_mode(dev, tmp_path, capsys):
+    """tools/test_det_net.py calls test_net(nets, prop_file, imdb) WITHOUT cfg_set_mode, so SEAR.NUM_PROPOSALS and
+    SEAR.Tz do not exist (lib/detect/config.py:272-280); the reference's test_net never reads them."""
+    import cv2
+    from aznet_b200.detect import config as C
+    from aznet_b200.detect import test as T
+    _, fr, _, _ = _small_nets(dev)
+    saved = {k: C.cfg.SEAR.pop(k) for k in ("NUM_PROPOSALS", "Tz") if k in C.cfg.SEAR}
+    try:
+        assert not hasattr(C.cfg.SEAR, "NUM_PROPOSALS")
+        paths = []
+        for i, im in enumerate(synth.make_images(2, 200, 300, seed=95)):
+            paths.append(str(tmp_path / ("n%d.png" % i)))
+            cv2.imwrite(paths[-1], im)
+        C.cfg.ROOT_DIR = str(tmp_path)
+        C.cfg_set_path("pytest_nomode")
+        imdb = synth.SyntheticImdb(paths, num_classes=6, name="nomode")
+        prop_file = str(tmp_path / "proposals.pkl")
+        boxes = [synth.make_boxes(350, 200, 300, seed=96 + i, lo=12, hi=150) for i in range(2)]   # longer than 300 rows
+        pickle.dump({"boxes": boxes, "time": 0.0, "recall": 0}, open(prop_file, "wb"))
+        T.test_net(fr, prop_file, imdb)
+        assert "Evaluating detections" in capsys.readouterr().out and imdb.evaluated is not None
+    finally:
+        for k, v in saved.items():
+            C.cfg.SEAR[k] = v

@@ -159,7 +159,7 @@ def test_roi_pool_matches_torchvision_cpu():
 
 
 def _layer_feat():
-    feat = synth.make_conv_maps(2, 6, 38, 63, seed=7)          # as oracle/gen_golden.py::gen_layers
+    feat = synth.make_conv_maps(2, 8, 38, 63, seed=7)          # as oracle/gen_golden.py::gen_layers
     feat[1] -= 0.5
     feat[1, 0, 3, 4] = np.nan
     feat[1, 1, 10:20, 10:30] = -0.0
@@ -214,6 +214,39 @@ def test_against_compiled_reference_layers():
         assert np.array_equal(O.max_pool_ceil(pm), RC.max_pool(pm))
     with pytest.raises(RuntimeError):
         RC.roi_pool_fwd(np.zeros((1, 1, 4, 4), np.float32), np.array([[2, 0, 0, 10, 10]], np.float32))
+
+
+def test_reference_im_propose_with_a_real_net_equals_the_port():
+    """The reference's OWN lib/detect/test.py::im_propose (oracle/_ref/pyref) + its own compiled div.pyx, driving its own
+    layer sources (oracle/_ref/libcaffe_layers_ref.so: ROIPooling / ReLU / Sigmoid) with float32 sgemm heads -- a REAL
+    network, not the integer-hash one -- gives bit for bit the proposals of the oracle port (which is what the CUDA
+    path is compared with at full width).  This is also the stack bench.py's reference arm times."""
+    from oracle import ref_caffe as RC
+    ref = build_ref.load_pyref()
+    if ref is None or not RC.available():
+        pytest.skip("oracle/_ref not built")
+    rtest, rconfig = ref[0], ref[1]
+    w = synth.make_az_weights(seed=3, C=64, h6=256, h71=96, h72=32, zoom_bias=0.0)
+    conv = synth.make_conv_maps(1, 64, 30, 50, seed=7)
+    cfg = O.OracleCfg(TEST_MAX_SIZE=800, BATCH_SIZE=1000)
+    port = O.OracleNet(w, "az", cfg=cfg)
+    Y_port, _, info = O.im_propose({"full": port, "fc": port}, (600, 1000, 3), cfg, conv={"conv5_3": conv}, return_scores=True)
+    rc = rconfig.cfg
+    keep = (rc.TEST.MAX_SIZE, rc.SEAR.BATCH_SIZE)
+    rc.TEST.MAX_SIZE, rc.SEAR.BATCH_SIZE = 800, 1000
+    rconfig.cfg_set_mode("Test", 0.5)
+    try:
+        full = O.OracleNet(w, "az", cfg=cfg, layers="ref", backbone=lambda data: conv)      # the backbone is out of scope: cached map
+        fc = O.OracleNet(w, "az", cfg=cfg, layers="ref")
+        import contextlib
+        import io
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            Y_ref = rtest.im_propose({"full": full, "fc": fc}, np.zeros((600, 1000, 3), np.uint8))
+    finally:
+        rc.TEST.MAX_SIZE, rc.SEAR.BATCH_SIZE = keep
+    assert "evaluate {0} regions".format(info["num_eval"]) in buf.getvalue() and info["num_eval"] > 100
+    assert np.array_equal(Y_ref.view(np.uint64), Y_port.view(np.uint64))
 
 
 def _detect_case(g, name, ncls, shapes, max_size, bs, counts):
