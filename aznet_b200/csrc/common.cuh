@@ -60,6 +60,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_enter() { pdl_grid_wait(); pdl_launch_dependents(); }
 
 extern int g_azn_pdl;
+extern int g_azn_coop;
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t azn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
@@ -74,5 +75,31 @@ static inline cudaError_t azn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_azn_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- cooperative launch ---------------------------------------------------------------------------
+// The persistent GEMM spins on device-side flags and on a grid-wide barrier: every CTA of its grid (one per SM) must be
+// resident at the same time.  A plain launch gives no such guarantee -- if another kernel holds some SMs (a second
+// persistent GEMM on another stream, the NMS chain's SM partition, an NCCL kernel) part of the grid waits for SMs that
+// the running part never frees: deadlock.  Launched with cudaLaunchAttributeCooperative the driver either places the
+// whole grid together (waiting for the SMs it needs) or fails the launch with cudaErrorCooperativeLaunchTooLarge,
+// which surfaces as AZN_ERR_CUDA instead of a hang.  Cooperative and programmatic-dependent launch are not combined:
+// griddepcontrol.* in the kernel are no-ops without the PDL attribute (measured neutral under CUDA-graph replay,
+// DESIGN.md).  azn_set_coop(0) restores the plain / PDL launch (A/B).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t azn_launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                          Args &&...args) {
+    if (!g_azn_coop) return azn_launch_pdl(kernel, grid, block, smem, s, static_cast<Args &&>(args)...);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }

@@ -756,7 +756,18 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_l
         AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N, MH, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
-    AZN_CUDA(azn_launch_pdl(fc_gemm_kernel<BLOCK_N, MH, CONV>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep));
+    // every CTA of the persistent grid must be co-resident (flag spin-waits, grid barrier): cooperative launch
+    static int max_grid = 0;
+    if (!max_grid) {
+        int per_sm = 0;
+        AZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fc_gemm_kernel<BLOCK_N, MH, CONV>, C::THREADS, C::SMEM_BYTES));
+        max_grid = per_sm * azn_num_sms();
+    }
+    if (grid > max_grid) {
+        azn_set_error("azn_fc_forward: a grid of %d persistent CTAs cannot be co-resident on this device (max %d)", grid, max_grid);
+        return AZN_ERR_CUDA;
+    }
+    AZN_CUDA(azn_launch_coop(fc_gemm_kernel<BLOCK_N, MH, CONV>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep));
     return AZN_OK;
 }
 

@@ -15,16 +15,37 @@ def shard_images(num_images: int, rank: int, world: int):
     return lo, min(lo + per, num_images)
 
 
+def _pad_rows(t: torch.Tensor, rows: int, fill):
+    """Pad the leading dimension to `rows` (shard_images hands out uneven or empty shards whenever
+    num_images % world != 0; all_gather_into_tensor needs identical shapes on every rank)."""
+    if t.shape[0] == rows:
+        return t.contiguous()
+    out = torch.full((rows,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
+
+
+def _max_rows(n: int, device) -> int:
+    """Largest shard size over the ranks (one tiny all_reduce; end-of-job paths only)."""
+    t = torch.tensor([int(n)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def gather_proposals(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
     """all_gather of [imgs_per_rank, P, 4] f64 boxes, [imgs_per_rank, P] f32 scores and [imgs_per_rank] i32
-    counts; returns rank-ordered (= image-ordered for shard_images) concatenations on every rank."""
+    counts; returns rank-ordered (= image-ordered for shard_images) concatenations on every rank.  Shards may be
+    uneven: every rank's block is padded to the largest shard with count-0 rows, so rank r's images start at row
+    r * ceil(num_images / world) -- exactly shard_images' `lo`."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return boxes, scores, counts
     world = dist.get_world_size()
+    rows = _max_rows(boxes.shape[0], boxes.device)
     outs = []
     for t in (boxes, scores, counts):
-        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(buf, t.contiguous())
+        t = _pad_rows(t, rows, 0)
+        buf = torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t)
         outs.append(buf)
     return tuple(outs)
 
@@ -69,10 +90,15 @@ class ProposalCollector:
         self.scores[j].copy_(scores, non_blocking=True)
         self.counts[j].copy_(counts, non_blocking=True)
 
-    def gather(self):
-        """-> (boxes [world*n_batches*imgs, P, 4], scores [.., P], counts [..]) on every rank."""
+    def gather(self, views: bool = False):
+        """-> (boxes [world*n_batches*imgs, P, 4], scores [.., P], counts [..]) on every rank.  Every rank must have
+        been built with the same n_batches and buffer shapes (the collective needs identical sizes; a rank with fewer
+        batches leaves count-0 slots).  views=True skips the three re-packing copies and returns strided views
+        [world, n_batches*imgs, ...] into the receive buffer (valid until the next gather)."""
         flat = lambda t: t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            if views:
+                return tuple(flat(t).unsqueeze(0) for t in (self.boxes, self.scores, self.counts))
             return flat(self.boxes), flat(self.scores), flat(self.counts)
         world = dist.get_world_size()
         if self._gathered is None:
@@ -80,8 +106,11 @@ class ProposalCollector:
         dist.all_gather_into_tensor(self._gathered.view(-1), self._buf)
         outs, off = [], 0
         for t, sz in zip((self.boxes, self.scores, self.counts), self._sizes):
-            g = self._gathered[:, off:off + sz].contiguous().view(t.dtype)
-            outs.append(g.view((world * t.shape[0] * t.shape[1],) + tuple(t.shape[2:])))
+            g = self._gathered[:, off:off + sz]
+            if views:
+                outs.append(g.view(t.dtype).view((world, t.shape[0] * t.shape[1]) + tuple(t.shape[2:])))
+            else:
+                outs.append(g.contiguous().view(t.dtype).view((world * t.shape[0] * t.shape[1],) + tuple(t.shape[2:])))
             off += sz
         return tuple(outs)
 
@@ -89,13 +118,15 @@ class ProposalCollector:
 def gather_detection_scores(top_scores: torch.Tensor, det_count: torch.Tensor):
     """The exchange step of the detection path: test_net's thresh[j] is global over the image set
     (lib/detect/test.py:624-631) but order-independent, so every rank all-gathers the [imgs, C, 100] f32 score
-    tensor and the [imgs, C] counts of its shard (equal shard sizes) and computes identical thresholds."""
+    tensor and the [imgs, C] counts of its shard and computes identical thresholds."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return top_scores, det_count
     world = dist.get_world_size()
-    outs = []
-    for t in (top_scores, det_count):
-        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(buf, t.contiguous())
+    rows = _max_rows(top_scores.shape[0], top_scores.device)        # uneven shards: pad with empty images (count 0, -inf),
+    outs = []                                                       # which never enter the thresholds
+    for t, fill in ((top_scores, float("-inf")), (det_count, 0)):
+        t = _pad_rows(t, rows, fill)
+        buf = torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t)
         outs.append(buf)
     return tuple(outs)

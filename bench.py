@@ -10,10 +10,15 @@ runs once per image before the search and is out of scope).
   value   whole-job images/sec with the maps resident in HBM (NHWC bf16)
   e2e     the same through the host-facing call: f32 NCHW maps in pinned host memory -> H2D -> layout
           conversion -> search -> D2H of the proposal lists, every step
-  roofline  the int6 GEMM (25088 -> 4096) launch of the deepest level vs the measured bf16 peak
-  cpu_baseline / --impl reference  the oracle port of the reference's CPU path on the host cores
+  roofline  the int6 GEMM (25088 -> 4096), time-weighted over its launches of a step, vs the measured bf16 peak
+  parity    oracle vs CUDA path on the first images of the timed batch (outside the timed region)
+  extra     the other metrics of BASELINE.json in the same record: ROI-pool GB/s, NMS boxes/s (config #4), config #3,
+            config #2 on the default-cfg 38x63 map
+  e2e_entry images/s THROUGH detect.test.test_proposals (the call tools/prop_az.py makes), backbone included
+  cpu_baseline / --impl reference  the reference's CPU path on the host cores: its own lib/detect/test.py control
+            flow + compiled div.pyx + its own layer sources (oracle/_ref) when present, else the oracle port
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--job IMAGES] [--no-extra]
 """
 from __future__ import annotations
 
@@ -120,36 +125,113 @@ class ClockSampler:
 
 
 class OracleRunner:
-    """The reference's CPU path (oracle port: lib/detect/test.py control flow, Caffe ROIPooling loop on one
-    core, fp32 sgemm heads on `threads` cores) on images of the bench workload."""
+    """The reference's CPU path on images of the bench workload.
+
+    kind "reference": the reference's OWN code wherever it can run here -- lib/detect/test.py::im_propose (converted
+    py2->py3, oracle/_ref/pyref), lib/utils/div.pyx compiled unmodified, and Forward_cpu of its own roi_pooling /
+    relu / sigmoid layer sources (oracle/_ref/libcaffe_layers_ref.so); the InnerProduct layers' sgemm goes to
+    torch-CPU (MKL) on `threads` cores because the reference's BLAS is un-vendored.  Like the reference it redoes the
+    host image blob (mean-subtract + cv2.resize) at every level (test.py:208) and runs ROI pooling and the control
+    flow on one core.  The backbone is out of scope on both arms: the 'full' net hands back the cached conv5_3 map.
+    kind "port": the oracle restatement (oracle/az_oracle.py), when oracle/_ref is not populated."""
 
     def __init__(self, weights, threads, n_maps=8, seed=7):
         from aznet_b200 import synth
         from oracle import az_oracle as O
+        from oracle import build_ref, ref_caffe
         self.O = O
         self.cfg = O.OracleCfg(TEST_MAX_SIZE=CFG["max_size"], Tz=CFG["tz"], NUM_PROPOSALS=CFG["num_proposals"],
                                BATCH_SIZE=CFG["batch_size"])
         s = O.im_scale_for((IM_H, IM_W), self.cfg)[0]
         fh, fw = synth.conv_shape(IM_H, IM_W, s)
         self.conv = synth.make_conv_maps(n_maps, 512, fh, fw, seed=seed)
-        self.net = O.OracleNet(weights, "az", cfg=self.cfg, threads=threads)
         self.regions = 0
         self.images = 0
+        self.threads = threads
+        ref = build_ref.load_pyref() if ref_caffe.available() else None
+        if ref is not None:
+            self.kind = "reference"
+            self.rtest, rconfig = ref[0], ref[1]
+            rc = rconfig.cfg
+            rc.TEST.MAX_SIZE, rc.SEAR.BATCH_SIZE = CFG["max_size"], CFG["batch_size"]
+            rconfig.cfg_set_mode("Test", CFG["tz"])
+            rc.SEAR.NUM_PROPOSALS = CFG["num_proposals"]
+            self.cur = None
+            self.full = O.OracleNet(weights, "az", cfg=self.cfg, threads=threads, layers="ref", backbone=lambda data: self.cur)
+            self.fc = O.OracleNet(weights, "az", cfg=self.cfg, threads=threads, layers="ref")
+            self.im = np.zeros((IM_H, IM_W, 3), np.uint8)
+            self.what = ("the reference's own lib/detect/test.py::im_propose + compiled div.pyx + its own ROIPooling/ReLU/Sigmoid "
+                         "layer sources (oracle/_ref); sgemm heads through torch-CPU on %d threads; ROI-pool, host image blob "
+                         "per level and control flow on 1 core like the reference" % threads)
+        else:
+            self.kind = "port"
+            self.net = O.OracleNet(weights, "az", cfg=self.cfg, threads=threads)
+            self.what = ("oracle port of lib/detect/test.py + Caffe layers (oracle/_ref not populated); ROI-pool and control "
+                         "flow single-threaded like the reference, sgemm heads on %d threads" % threads)
 
     def run(self, n_images, start=0):
-        nets = {"full": self.net, "fc": self.net}
+        import contextlib
+        import io
+        import re
         for i in range(n_images):
             j = (start + i) % self.conv.shape[0]
-            _, _, info = self.O.im_propose(nets, (IM_H, IM_W, 3), self.cfg, conv={"conv5_3": self.conv[j:j + 1]},
-                                           return_scores=True)
-            self.regions += info["num_eval"]
+            if self.kind == "reference":
+                self.cur = self.conv[j:j + 1]
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    self.rtest.im_propose({"full": self.full, "fc": self.fc}, self.im)
+                self.regions += int(re.search(r"evaluate (\d+) regions", buf.getvalue()).group(1))
+            else:
+                nets = {"full": self.net, "fc": self.net}
+                _, _, info = self.O.im_propose(nets, (IM_H, IM_W, 3), self.cfg, conv={"conv5_3": self.conv[j:j + 1]},
+                                               return_scores=True)
+                self.regions += info["num_eval"]
             self.images += 1
 
 
+def reference_entry_point(weights, threads, n_images=2):
+    """The reference-arm twin of `e2e_entry`: the reference's own test_proposals(net, imdb) (oracle/_ref/pyref) over PNG
+    files, its 'full' net = VGG16 conv1_1..conv5_3 in fp32 on the host cores (torch-CPU conv2d: the class of library
+    Caffe's im2col + sgemm is) + the AZ head through the reference's layer sources.  None when oracle/_ref is absent."""
+    import contextlib
+    import io
+    import tempfile
+    import cv2
+    from aznet_b200 import backbone, synth
+    from oracle import az_oracle as O
+    from oracle import build_ref, ref_caffe
+    ref = build_ref.load_pyref() if ref_caffe.available() else None
+    if ref is None:
+        return None
+    rtest, rconfig = ref[0], ref[1]
+    rc = rconfig.cfg
+    ocfg = O.OracleCfg(TEST_MAX_SIZE=CFG["max_size"], Tz=CFG["tz"], NUM_PROPOSALS=CFG["num_proposals"], BATCH_SIZE=CFG["batch_size"])
+    bw = backbone.make_vgg16_weights(seed=5)
+    full = O.OracleNet(weights, "az", cfg=ocfg, threads=threads, layers="ref", name="az_vgg16",
+                       backbone=lambda data: O.vgg16_conv5(bw, data, threads=threads))
+    fc = O.OracleNet(weights, "az", cfg=ocfg, threads=threads, layers="ref", name="az_vgg16")
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for i, im in enumerate(synth.make_images(n_images, IM_H, IM_W, seed=1000)):
+            paths.append(os.path.join(tmp, "%d.png" % i))
+            cv2.imwrite(paths[-1], im)
+        imdb = synth.SyntheticImdb(paths, num_classes=21, name="bench_ref")
+        rc.TEST.MAX_SIZE, rc.SEAR.BATCH_SIZE, rc.ROOT_DIR = CFG["max_size"], CFG["batch_size"], tmp
+        rconfig.cfg_set_path("bench")
+        rconfig.cfg_set_mode("Test", CFG["tz"])
+        rc.SEAR.NUM_PROPOSALS = CFG["num_proposals"]
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            rtest.test_proposals({"full": full, "fc": fc}, imdb)
+        dt = time.perf_counter() - t0
+    return {"value": n_images / dt, "unit": "images/s", "images": n_images, "seconds": dt, "cores": threads,
+            "what": "the reference's own test_proposals over PNG files: cv2.imread, host image blob per level, VGG16 conv stack "
+                    "in fp32 on the host cores, AZ head, proposals.pkl"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; Caffe cannot be
-    built here) on the host cores, same config / metric / unit.  One step = a bounded sample of
-    4 images of the 64-image batch."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same config / metric /
+    unit.  One step = a bounded sample of 4 images of the 64-image batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -173,23 +255,90 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "regions_per_image": runner.regions / max(runner.images, 1),
                    "step": "bounded sample: %d images of the 64-image batch per step" % per_step},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "%d images of the bench workload in %.1f s (oracle port of lib/detect/test.py + Caffe layers; "
-                                   "ROI-pool and control flow single-threaded like the reference, sgemm heads on %d threads)"
-                                   % (n, dt, threads)},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": runner.kind,
+                         "sample": "%d images of the bench workload in %.1f s (%s)" % (n, dt, runner.what)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_extra:
+        try:
+            ent = reference_entry_point(w, threads)
+            if ent is not None:
+                line["e2e_entry"] = ent
+        except Exception as e:                                        # the entry-point twin is a side figure
+            line["e2e_entry"] = {"error": repr(e)}
     print(json.dumps(line))
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    """DRAM bytes per launch of the roofline kernel.  It cannot be measured by the run itself (that needs ncu): the
+    figure is STATIC, read from the committed summary of an `ncu --set full` capture (profiles/traffic.json names the
+    capture and the commit it was taken at).  Returns (bytes or None, provenance string)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return int(next(iter(json.load(f).values()))["dram_bytes_per_launch"])
+            k, v = next(iter(json.load(f).items()))
+        return int(v["dram_bytes_per_launch"]), "static: %s (%s)" % (v.get("source", "profiles/traffic.json"), v.get("commit", "commit not recorded"))
     except Exception:
-        return None
+        return None, "no capture committed"
+
+
+def parity_block(eng, dev_maps, host_maps, weights, n_check=4):
+    """Oracle vs CUDA path on the first images of the timed batch, OUTSIDE the timed region: the fp32 oracle on the
+    bf16-rounded weights and maps (the product's storage precision) with bf16 activation storage emulated."""
+    import torch
+    from oracle import az_oracle as O
+    eng.propose(dev_maps)
+    boxes, scores, n_eval, _ = eng.results()
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+    wq = {k: (bf(v[0]), v[1]) for k, v in weights.items()}
+    cfg = O.OracleCfg(TEST_MAX_SIZE=CFG["max_size"], Tz=CFG["tz"], NUM_PROPOSALS=CFG["num_proposals"], BATCH_SIZE=CFG["batch_size"])
+    net = O.OracleNet(wq, "az", cfg=cfg, threads=os.cpu_count() or 1, act_round=O.round_bf16)
+
+    def iou(a, b):
+        x1, y1 = np.maximum(a[:, None, 0], b[None, :, 0]), np.maximum(a[:, None, 1], b[None, :, 1])
+        x2, y2 = np.minimum(a[:, None, 2], b[None, :, 2]), np.minimum(a[:, None, 3], b[None, :, 3])
+        inter = np.clip(x2 - x1 + 1, 0, None) * np.clip(y2 - y1 + 1, 0, None)
+        aa = (a[:, 2] - a[:, 0] + 1) * (a[:, 3] - a[:, 1] + 1)
+        ab = (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
+        return inter / (aa[:, None] + ab[None, :] - inter)
+    ne_g, ne_o, rec_o, rec_g, dtop = [], [], [], [], []
+    hm = host_maps.numpy()
+    for i in range(n_check):
+        Y, sc, info = O.im_propose({"full": net, "fc": net}, (IM_H, IM_W, 3), cfg, conv={"conv5_3": bf(hm[i:i + 1])}, return_scores=True)
+        m = iou(Y, boxes[i])
+        ne_g.append(int(n_eval[i]))
+        ne_o.append(int(info["num_eval"]))
+        rec_o.append(float((m.max(1) >= 0.9).mean()))             # oracle proposals recovered by the CUDA path
+        rec_g.append(float((m.max(0) >= 0.9).mean()))             # and vice versa
+        top = min(20, len(sc), len(scores[i]))
+        dtop.append(float(np.abs(np.sort(scores[i])[::-1][:top] - np.sort(sc)[::-1][:top]).max()))
+    ok = all(abs(a - b) <= max(2, 0.03 * b) for a, b in zip(ne_g, ne_o)) and min(rec_o + rec_g) >= 0.95 and max(dtop) <= 3e-2
+    return {"images": n_check, "n_eval_gpu": ne_g, "n_eval_oracle": ne_o, "recall_of_oracle_proposals_iou0.9": rec_o,
+            "recall_of_gpu_proposals_iou0.9": rec_g, "top20_score_max_abs_diff": dtop,
+            "tolerance": "regions evaluated within 3 % (+-2), recall >= 0.95 both ways at IoU 0.9, top-20 scores within 3e-2 "
+                         "(bf16 operands and activations; tests/test_gpu_golden.py::test_full_width_search_vs_oracle)",
+            "status": "green" if ok else "RED"}
+
+
+def extra_blocks(dev, head, hbm_peak):
+    """BASELINE.json's other metrics and configs, measured in the same process right after the headline (outside its
+    timed region, bounded to a few seconds each): see tools/benchlib.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import benchlib as BL
+    from oracle import az_oracle as O
+    extra = {}
+    wr = BL.hbm_write_only_gbs(dev)
+    extra["roi_pool"] = {"metric": "ROI max-pool achieved HBM GB/s on the algorithmic bytes (map once + 20 B/ROI + pooled rows once)",
+                         "peak_gbs": hbm_peak, "hbm_write_only_gbs": round(wr, 1),
+                         "note": "frac = achieved / the measured COPY rate (read + write bytes); the kernel is >99 % writes, and a plain "
+                                 "streaming-store kernel reaches hbm_write_only_gbs on this GPU",
+                         "rows": BL.roi_pool_sweep(dev, hbm_peak, iters=5)}
+    extra["nms"] = {"metric": "greedy NMS boxes/s (whole azn_nms call: sort + mask + chain + compaction)",
+                    "rows": BL.nms_sweep(dev, oracle=O, iters=5)}
+    extra["config2_default_cfg_map"] = BL.search_throughput(dev, head, dict(CFG, max_size=1000, batch_size=10000))
+    extra["config3_detection"] = BL.detection_throughput(dev, head, CFG)
+    entry = BL.entry_point_throughput(dev, head, CFG)
+    return extra, entry
 
 
 def main():
@@ -201,6 +350,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (A/B)")
+    ap.add_argument("--no-coop", action="store_true", help="plain (PDL) launch of the persistent GEMM instead of the cooperative launch (A/B)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra / e2e_entry / parity blocks (they run outside the timed regions)")
+    ap.add_argument("--job", type=int, default=0, help="strong-scaling mode (BASELINE config #5): a job of this many images "
+                    "(a multiple of 64) sharded over the ranks in batches of 64; --steps is ignored")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -222,7 +375,11 @@ def main():
     _lib.build()
     _lib.require_device()
     _lib.lib().azn_set_pdl(0 if args.no_pdl else 1)
+    _lib.lib().azn_set_coop(0 if args.no_coop else 1)
 
+    if args.job:
+        assert args.job % (BATCH * world) == 0, "--job must be a multiple of 64 x the number of GPUs"
+        args.steps = args.job // (BATCH * world)
     weights = synth.make_az_weights(seed=3, zoom_bias=ZOOM_BIAS)
     head = engine.AZHeadWeights(weights, dev)
     eng = engine.SearchEngine(head, BATCH, IM_H, IM_W, **CFG)
@@ -277,6 +434,7 @@ def main():
             pipe.result(pending.pop(0))
 
     gathered = [None, None, None]
+    gather_ms = [0.0]
 
     def timed(step_fn, steps, profile=False):
         barrier()
@@ -290,11 +448,14 @@ def main():
         for i in range(steps):
             step_fn(i)
         drain()                                       # e2e: the last proposals are on the host
+        eg = torch.cuda.Event(enable_timing=True)
+        eg.record()
         if world > 1:
-            gathered[:] = collector.gather()          # the job's only exchange: all ranks' proposal lists
+            gathered[:] = collector.gather(views=True)     # the job's only exchange: all ranks' proposal lists
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        gather_ms[0] = eg.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,6 +479,7 @@ def main():
         sampler.start()
     ms_total = timed(step_resident, args.steps)
     launches = eng.launches
+    gather_resident_ms = gather_ms[0]
     # per-kernel CUDA-event timings need host-issued launches: a second pass over the same K steps, not the timed one
     timed(step_resident, args.steps, profile=True)
     prof = eng.prof_summary()
@@ -333,9 +495,17 @@ def main():
         value = world * BATCH * args.steps / (ms_total / 1e3)
         e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
         top = prof["int6_deepest"]
+        # int6 over ALL its launches of a step: algorithmic FLOPs of every level / the time of every level
+        int6 = [r for r in prof["levels"] if r["stage"] == "int6"]
+        k6, n6 = head.w6.shape[1], head.w6.shape[0]
+        int6_ms = sum(r["ms"] for r in int6)
+        int6_tf = sum(2.0 * r["m"] * n6 * k6 for r in int6) / (int6_ms * 1e-3) / 1e12 if int6_ms > 0 else 0.0
+        step_flops = sum(r["m"] for r in int6) * 216119808.0          # FLOPs per ROI of the whole AZ head
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": "AZ proposal images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.job else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "regions_per_image": regions,
                        "l2": "working set per step (216 MB bf16 weights + pooled rows) exceeds the 126 MB L2; inputs rotate over 2 distinct batches",
@@ -344,15 +514,26 @@ def main():
                        "parallelism": "image-sharded x%d, no collective on the hot path; one NCCL all_gather of all K steps' proposal lists at the end, inside the timed region" % world},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
             "gpu_launches": launches,
-            "roofline": {"kernel": "fc_gemm_kernel<256,2> int6 25088->4096, deepest level", "bound": "tensor",
-                         "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
-                         "traffic": ncu_traffic(), "peak_source": which + " (sustained bf16)", "m_rows": top["m"], "ms": top["ms"],
+            "roofline": {"kernel": "fc_gemm_kernel<256,2> int6 25088->4096, all %d launches of a step (time-weighted)" % len(int6), "bound": "tensor",
+                         "achieved": int6_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": int6_tf / tf_peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": which + " (sustained bf16)",
+                         "ms_per_step_in_kernel": int6_ms, "share_of_step": int6_ms / (ms_total / args.steps),
+                         "deepest_launch": {"m_rows": top["m"], "ms": top["ms"], "achieved": top["tflops"], "frac": top["tflops"] / tf_peak},
+                         "whole_step": {"flops": step_flops, "achieved": step_flops / (ms_total / args.steps * 1e-3) / 1e12,
+                                        "frac": step_flops / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
                          "per_level": prof["levels"], "hbm_peak_gbs": hbm_peak},
         }
+        if args.job:
+            line["config"]["job"] = "BASELINE config #5: %d images = %d batches of 64, %d per rank; one NCCL all_gather of the lists at the end" % (
+                args.job, args.job // BATCH, args.steps)
+        if world > 1:
+            line["gather_ms"] = {"resident": gather_resident_ms, "e2e": gather_ms[0],
+                                 "bytes_per_rank": int(sum(t.numel() * t.element_size() for t in (collector.boxes, collector.scores, collector.counts)))}
+        threads = os.cpu_count() or 1
+        runner = None
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
             runner = OracleRunner(weights, threads)
             runner.run(1)
             runner.regions = runner.images = 0
@@ -362,9 +543,18 @@ def main():
                 runner.run(16)
                 n_cpu += 16
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "images/s", "cores": threads, "kind": "port",
-                                    "sample": "%d images of the same workload in %.1f s (oracle port; ROI-pool/control flow 1 core, "
-                                              "sgemm heads %d threads); %.0f regions/image" % (n_cpu, dt, threads, runner.regions / n_cpu)}
+            line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "images/s", "cores": threads, "kind": runner.kind,
+                                    "sample": "%d images of the same workload in %.1f s (%s); %.0f regions/image" % (
+                                        n_cpu, dt, runner.what, runner.regions / n_cpu)}
+        if not args.no_extra and world == 1:
+            try:
+                line["parity"] = parity_block(eng, dev_sets[0], host_sets[0], weights)
+            except Exception as e:
+                line["parity"] = {"error": repr(e)}
+            try:
+                line["extra"], line["e2e_entry"] = extra_blocks(dev, head, hbm_peak)
+            except Exception as e:
+                line["extra"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -49,6 +49,16 @@ int azn_check_device(void);
 /* Programmatic dependent launch of the level-loop kernels (default on): kernel K+1 is scheduled while kernel K
  * drains and waits (griddepcontrol.wait) before it touches global memory.  0 = plain stream order (benchmarks). */
 void azn_set_pdl(int on);
+/* Cooperative launch of the persistent GEMM kernels (default on): azn_fc_forward / azn_conv3x3_forward spin on device-side
+ * flags and a grid-wide barrier, so all of their CTAs (one per SM) must be co-resident.  With the cooperative launch
+ * attribute the driver places the whole grid together -- waiting for SMs held by other kernels instead of
+ * deadlocking -- or fails the launch (AZN_ERR_CUDA).  0 = plain / PDL launch, which requires the caller to keep the
+ * GPU free of concurrent kernels (benchmarks, A/B). */
+void azn_set_coop(int on);
+/* Measurement utility (no reference counterpart): fills `bytes` of device memory with 16-byte streaming stores from a
+ * grid of one CTA per SM x 8 -- the write-only HBM rate that a store-dominated kernel such as the ROI max-pool can be
+ * compared with (the copy rate of MEASURED_PEAKS.json counts read + write bytes). */
+int azn_hbm_write_probe(void *dst, size_t bytes, azn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * ROI max pooling, forward.
