@@ -54,6 +54,11 @@ class Batch:
         self._ring[self._slot][1] = event
 
 
+# Pinned staging buffers are page-locked allocations (cudaHostAlloc: tens of milliseconds for a 115 MB batch), so they
+# are kept for the life of the process: a ring of 3 per (batch, image shape), a few shapes at a time.
+_PINNED_RINGS = OrderedDict()
+
+
 class ImageFeeder:
     """Iterates over same-shape batches of the images `indices` of an imdb, reading ahead `window` images."""
 
@@ -61,7 +66,6 @@ class ImageFeeder:
         self.imdb, self.indices, self.batch = imdb, list(indices), int(batch)
         self.workers = workers or min(32, os.cpu_count() or 4)
         self.window = window or 3 * self.batch
-        self._rings = {}
         self._loader = imdb.image_at if hasattr(imdb, "image_at") else self._imread
 
     def _imread(self, i):
@@ -73,11 +77,14 @@ class ImageFeeder:
 
     def _stage(self, pool, shape, items):
         """Copy a group's images into a pinned [batch, H, W, 3] buffer (ring of 3 per shape) with the reader threads."""
-        ring = self._rings.get(shape)
+        key = (self.batch, shape)
+        ring = _PINNED_RINGS.get(key)
         if ring is None:
-            ring = self._rings[shape] = {"next": 0}
-            if len(self._rings) > 6:                                  # bound pinned memory across many distinct shapes
-                self._rings.pop(next(iter(self._rings)))
+            ring = _PINNED_RINGS[key] = {"next": 0}
+            if len(_PINNED_RINGS) > 6:                                # bound pinned memory across many distinct shapes
+                _PINNED_RINGS.popitem(last=False)
+        else:
+            _PINNED_RINGS.move_to_end(key)
         slot = ring["next"] % 3
         ring["next"] += 1
         if slot not in ring:
@@ -186,13 +193,19 @@ class DeviceBatch:
         self.maps = outs["conv5_3"] if taps == ("conv5_3",) else outs
 
 
+_PINNED_POOL = {}
+
+
 class Fetch:
-    """Device tensors -> pinned host copies on the current stream; `get()` waits for them."""
+    """Device tensors -> pinned host copies on the current stream; `get()` waits for them and hands out arrays that
+    stay valid (copies): the pinned buffers go back to a small pool."""
 
     def __init__(self, **tensors):
         self.host = {}
         for k, t in tensors.items():
-            h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            key = (tuple(t.shape), t.dtype)
+            free = _PINNED_POOL.setdefault(key, [])
+            h = free.pop() if free else torch.empty(t.shape, dtype=t.dtype).pin_memory()
             h.copy_(t, non_blocking=True)
             self.host[k] = h
         self.bytes = sum(h.numel() * h.element_size() for h in self.host.values())
@@ -201,4 +214,10 @@ class Fetch:
 
     def get(self):
         self.done.synchronize()
-        return {k: v.numpy() for k, v in self.host.items()}
+        out = {k: v.numpy().copy() for k, v in self.host.items()}
+        for v in self.host.values():
+            free = _PINNED_POOL[(tuple(v.shape), v.dtype)]
+            if len(free) < 4:
+                free.append(v)
+        self.host = {}
+        return out

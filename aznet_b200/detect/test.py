@@ -428,8 +428,12 @@ def _test_proposals_batched(net, imdb, prop_boxes, stats):
             done[0] += 1
             print('im_prop: {:d}/{:d} {:.3f}s'.format(done[0], num_images, avg))
 
+    import time
     pending = None
+    t_mark = time.perf_counter()
     for batch in batched.ImageFeeder(imdb, range(num_images)):
+        t0 = time.perf_counter()
+        stats['host_feed_s'] = stats.get('host_feed_s', 0.0) + (t0 - t_mark)          # read-ahead + pinned staging
         clock.start()
         db = batched.DeviceBatch(full, batch, copy_stream)
         eng = _engine_for(full, db.shape + (3,), None, db.n_pad)
@@ -439,11 +443,17 @@ def _test_proposals_batched(net, imdb, prop_boxes, stats):
         stats['h2d_bytes'] += db.h2d_bytes
         stats['d2h_bytes'] += fetch.bytes
         stats['batches'] += 1
+        t1 = time.perf_counter()
+        stats['host_submit_s'] = stats.get('host_submit_s', 0.0) + (t1 - t0)           # launches of one batch
         if pending is not None:
             finish(pending)
         pending = (db, fetch)
+        t_mark = time.perf_counter()
+        stats['host_finish_s'] = stats.get('host_finish_s', 0.0) + (t_mark - t1)       # waiting for the previous batch + unpack
     if pending is not None:
+        t1 = time.perf_counter()
         finish(pending)
+        stats['host_finish_s'] = stats.get('host_finish_s', 0.0) + (time.perf_counter() - t1)
     return clock.timer
 
 

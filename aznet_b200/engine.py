@@ -26,6 +26,11 @@ from . import _lib as L
 from . import ops
 
 
+# The head's three output layers: "mma" = azn_az_heads_forward (small mma.sync kernel), "gemm" = the persistent tcgen05
+# kernel with the AZ-head epilogue (azn_fc_forward); same arithmetic, A/B switch for benchmarks.
+HEADS_KERNEL = "mma"
+
+
 def im_scale_for(im_h, im_w, scales=(600,), max_size=1000):
     """Image -> network-input scale, _get_image_blob (lib/detect/test.py:40-52), first TEST.SCALES entry."""
     size_min, size_max = min(im_h, im_w), max(im_h, im_w)
@@ -217,7 +222,10 @@ class SearchEngine:
         t = ev(level, "int6", t, midx)
         ops.fc_forward(self.h6[:mc], hd.w7, hd.b7, L.ACT_RELU, m_live=self.m_total, out=self.h7[:mc])
         t = ev(level, "int7", t, midx)
-        ops.fc_forward(self.h7[:mc], hd.wh, hd.bh, L.ACT_AZ_HEAD, hd.nsub, m_live=self.m_total, out=self.heads[:mc])
+        if HEADS_KERNEL == "mma":
+            ops.az_heads(self.h7[:mc], hd.wh, hd.bh, hd.nsub, m_live=self.m_total, out=self.heads[:mc])
+        else:
+            ops.fc_forward(self.h7[:mc], hd.wh, hd.bh, L.ACT_AZ_HEAD, hd.nsub, m_live=self.m_total, out=self.heads[:mc])
         ev(level, "heads", t, midx)
         self.launches += 1 + 3 * 2
 

@@ -161,7 +161,7 @@ class Net:
             h6 = ops.fc_forward(a, hd.w6, hd.b6, L.ACT_RELU)
             h7 = ops.fc_forward(h6, hd.w7, hd.b7, L.ACT_RELU)
             out = torch.empty((a.shape[0], hd.ld_head), dtype=torch.float32, device=a.device)
-            return ops.fc_forward(h7, hd.wh, hd.bh, L.ACT_AZ_HEAD, hd.nsub, out=out)
+            return ops.az_heads(h7, hd.wh, hd.bh, hd.nsub, out=out)
         h6 = ops.fc_forward(a, hd.w6, hd.b6, L.ACT_RELU)
         h7 = ops.fc_forward(h6, hd.w7, hd.b7, L.ACT_RELU)
         n = hd.wo.shape[0]

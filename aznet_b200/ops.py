@@ -106,6 +106,24 @@ def fc_forward(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, act: int = 
     return out
 
 
+def az_heads(h7: torch.Tensor, wh: torch.Tensor, bias: torch.Tensor, nsub: int, m_live: torch.Tensor | None = None,
+             out: torch.Tensor | None = None):
+    """[adj_prob | adj_bbox | zoom_prob] = the AZ head's three output layers + sigmoids (test_fc.prototxt:146-232) in
+    one small mma.sync kernel (azn_az_heads_forward).  h7 bf16 [M, K], wh bf16 [N = 5*nsub+1, K], bias f32 [N];
+    out f32 [M, ld >= N]."""
+    _need_cuda(h7, wh, bias, m_live)
+    assert h7.dtype == torch.bfloat16 and wh.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert h7.is_contiguous() and wh.is_contiguous() and h7.shape[1] == wh.shape[1]
+    M, K = h7.shape
+    N = wh.shape[0]
+    if out is None:
+        out = torch.empty((M, (N + 7) // 8 * 8), dtype=torch.float32, device=h7.device)
+    assert out.dtype == torch.float32 and out.shape[0] >= M and out.stride(1) == 1
+    L.check(L.lib().azn_az_heads_forward(_ptr(h7), _ptr(wh), _ptr(bias), _ptr(out), out.stride(0), M, _ptr(m_live), N, K, int(nsub),
+                                         _stream()), "azn_az_heads_forward")
+    return out
+
+
 def nms(dets: torch.Tensor, thresh: float):
     """Greedy NMS (lib/utils/nms.pyx:17-68) on a CUDA f32 [n,5] tensor.  Returns (keep int64 [n],
     count int32 [1]) on the device; keep[:count] are the kept indices in descending score order."""

@@ -15,8 +15,8 @@ from .engine import SearchEngine
 
 
 class _Slot:
-    def __init__(self, eng: SearchEngine, shape, dev):
-        self.stage = torch.empty(shape, dtype=torch.float32, device=dev)
+    def __init__(self, eng: SearchEngine, shape, dev, dtype=torch.float32):
+        self.stage = torch.empty(shape, dtype=dtype, device=dev)
         self.boxes = torch.empty(eng.out_boxes.shape, dtype=torch.float64).pin_memory()
         self.scores = torch.empty(eng.out_scores.shape, dtype=torch.float32).pin_memory()
         self.count = torch.empty(eng.out_count.shape, dtype=torch.int32).pin_memory()
@@ -30,24 +30,35 @@ class _Slot:
 
 
 class ProposalPipeline:
-    def __init__(self, eng: SearchEngine, map_shape, depth: int = 2, after_search=None, use_graph: bool = True):
-        """map_shape = (n_img, C, H, W) of the f32 NCHW batches; after_search: optional callable run on the
-        compute stream right after the search (e.g. the NCCL gather of a multi-GPU run); use_graph: replay the
-        layout conversion + level loop of every slot from a CUDA graph."""
-        self.eng, self.dev = eng, eng.dev
+    def __init__(self, eng: SearchEngine, map_shape, depth: int = 2, after_search=None, use_graph: bool = True,
+                 layout: str = "nchw_f32"):
+        """map_shape = (n_img, C, H, W) of the batches; after_search: optional callable run on the compute stream right
+        after the search (e.g. the NCCL gather of a multi-GPU run); use_graph: replay the layout conversion + level
+        loop of every slot from a CUDA graph.
+        layout "nchw_f32": host batches are f32 NCHW, what the reference's 'fc' net is handed (pycaffe blobs);
+        layout "nhwc_bf16": host batches are already in the engine's own storage format, bf16 [n, H, W, C] -- half the
+        PCIe bytes and no conversion kernel, for callers that keep their maps that way (e.g. downloaded from
+        aznet_b200.backbone)."""
+        assert layout in ("nchw_f32", "nhwc_bf16")
+        self.eng, self.dev, self.layout = eng, eng.dev, layout
         self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.slots = [_Slot(eng, map_shape, self.dev) for _ in range(depth)]
-        self.nhwc = torch.empty((map_shape[0], map_shape[2], map_shape[3], map_shape[1]), dtype=torch.bfloat16, device=self.dev)
+        n, c, h, w = map_shape
+        if layout == "nchw_f32":
+            self.slots = [_Slot(eng, map_shape, self.dev) for _ in range(depth)]
+            self.nhwc = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=self.dev)
+        else:
+            self.slots = [_Slot(eng, (n, h, w, c), self.dev, torch.bfloat16) for _ in range(depth)]
+            self.nhwc = None
         self.after_search = after_search
         self.use_graph = use_graph
         self.launches_per_submit = 0
         self._i = 0
-        self.h2d_bytes = int(map_shape[0] * map_shape[1] * map_shape[2] * map_shape[3] * 4)
+        self.h2d_bytes = int(n * c * h * w * (4 if layout == "nchw_f32" else 2))
         s = self.slots[0]
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (s.boxes, s.scores, s.count, s.n_eval, s.status))
 
     def submit(self, host_maps: torch.Tensor) -> _Slot:
-        """host_maps: f32 NCHW CPU tensor (pinned for an asynchronous copy)."""
+        """host_maps: CPU tensor in the pipeline's layout (pinned for an asynchronous copy)."""
         slot = self.slots[self._i % len(self.slots)]
         self._i += 1
         if slot.busy:
@@ -59,14 +70,17 @@ class ProposalPipeline:
             slot.stage.copy_(host_maps, non_blocking=True)
             slot.h2d_done.record(self.copy_stream)
         compute.wait_event(slot.h2d_done)
+        direct = self.layout == "nhwc_bf16"
         if self.use_graph:
             if slot.graph is None:
                 def pre(stage=slot.stage):
                     ops.nchw_to_nhwc_bf16(stage, out=self.nhwc)
                     self.eng.launches += 1
-                slot.graph, self.launches_per_submit = self.eng.capture(self.nhwc, pre=pre)
+                slot.graph, self.launches_per_submit = self.eng.capture(slot.stage if direct else self.nhwc, pre=None if direct else pre)
             slot.graph.replay()
             self.eng.launches += self.launches_per_submit
+        elif direct:
+            self.eng.propose(slot.stage)
         else:
             ops.nchw_to_nhwc_bf16(slot.stage, out=self.nhwc)
             self.eng.launches += 1

@@ -207,6 +207,7 @@ def reference_entry_point(weights, threads, n_images=2):
     rc = rconfig.cfg
     ocfg = O.OracleCfg(TEST_MAX_SIZE=CFG["max_size"], Tz=CFG["tz"], NUM_PROPOSALS=CFG["num_proposals"], BATCH_SIZE=CFG["batch_size"])
     bw = backbone.make_vgg16_weights(seed=5)
+    bw["conv1_1"] = (bw["conv1_1"][0] / np.float32(128.0), bw["conv1_1"][1])     # as tools/benchlib.py::entry_point_throughput
     full = O.OracleNet(weights, "az", cfg=ocfg, threads=threads, layers="ref", name="az_vgg16",
                        backbone=lambda data: O.vgg16_conv5(bw, data, threads=threads))
     fc = O.OracleNet(weights, "az", cfg=ocfg, threads=threads, layers="ref", name="az_vgg16")
@@ -351,6 +352,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (A/B)")
     ap.add_argument("--no-coop", action="store_true", help="plain (PDL) launch of the persistent GEMM instead of the cooperative launch (A/B)")
+    ap.add_argument("--streams", type=int, default=2, choices=(1, 2, 3, 4),
+                    help="batches in flight for the device-resident figure: 2 = two engines on two CUDA streams, so that the latency-bound "
+                         "kernels of one batch (ROI pool, decode / subdivide, selection) run next to the other batch's tensor-core GEMMs")
+    ap.add_argument("--heads", default="mma", choices=("mma", "gemm"), help="output layers of the head: small mma.sync kernel or the persistent GEMM (A/B)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra / e2e_entry / parity blocks (they run outside the timed regions)")
     ap.add_argument("--job", type=int, default=0, help="strong-scaling mode (BASELINE config #5): a job of this many images "
                     "(a multiple of 64) sharded over the ranks in batches of 64; --steps is ignored")
@@ -376,6 +381,7 @@ def main():
     _lib.require_device()
     _lib.lib().azn_set_pdl(0 if args.no_pdl else 1)
     _lib.lib().azn_set_coop(0 if args.no_coop else 1)
+    engine.HEADS_KERNEL = args.heads
 
     if args.job:
         assert args.job % (BATCH * world) == 0, "--job must be a multiple of 64 x the number of GPUs"
@@ -384,8 +390,8 @@ def main():
     head = engine.AZHeadWeights(weights, dev)
     eng = engine.SearchEngine(head, BATCH, IM_H, IM_W, **CFG)
     fh, fw = synth.conv_shape(IM_H, IM_W, eng.scale)
-    # two distinct synthetic batches per rank (rotated, so consecutive steps never see the same maps)
-    n_sets = 2
+    # distinct synthetic batches per rank (rotated, so consecutive steps never see the same maps): one per stream, >= 2
+    n_sets = max(2, 1 if args.no_graph else args.streams)
     host_sets, dev_sets = [], []
     for sidx in range(n_sets):
         maps = synth.make_conv_maps(BATCH, 512, fh, fw, seed=7 + 1000 * rank + 100 * sidx)
@@ -396,13 +402,26 @@ def main():
     # N > 1: every rank collects its batches' proposal lists on the device and the job does ONE NCCL all_gather
     # at the end of the K steps (inside the timed region) -- no collective per step, like test_proposals, which
     # appends per image and writes proposals.pkl once (lib/detect/test.py:508-539)
-    collector = ProposalCollector(max(args.steps, args.warmup, 2), eng.out_boxes, eng.out_scores, eng.out_count) if world > 1 else None
+    # Two batches in flight (--streams 2): a second engine with its own buffers on a second stream.  Images are
+    # independent, so consecutive batches have no dependency; the persistent GEMMs of the two streams take turns (they
+    # are launched cooperatively: each needs every SM), while the small kernels of one batch fill the other batch's GEMM
+    # time -- they use no tensor pipe and little shared memory, so they are co-resident with the GEMM's one CTA per SM.
+    n_streams = 1 if args.no_graph else args.streams
+    engines = [eng] + [engine.SearchEngine(head, BATCH, IM_H, IM_W, **CFG) for _ in range(n_streams - 1)]
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else []
+    slots = (max(args.steps, args.warmup, 2) + n_streams - 1) // n_streams
+    collectors = [ProposalCollector(slots, e.out_boxes, e.out_scores, e.out_count) for e in engines] if world > 1 else []
+    collector = collectors[0] if collectors else None
     # the copy into the collection is the last kernel of the search (azn_collect_proposals, slot from a device-side
     # counter), so it is part of the replayed CUDA graph
-    eng.collector = collector
+    for e, c in zip(engines, collectors):
+        e.collector = c
     after = None
     pipe = ProposalPipeline(eng, tuple(host_sets[0].shape), depth=2, after_search=after, use_graph=not args.no_graph)
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+    # the same call with the host maps already in the engine's storage format (bf16 NHWC): half the PCIe bytes
+    host_sets_bf16 = [d.cpu().pin_memory() for d in dev_sets]
+    pipe_bf16 = ProposalPipeline(eng, tuple(host_sets[0].shape), depth=2, use_graph=not args.no_graph, layout="nhwc_bf16")
 
     def barrier():
         torch.cuda.synchronize()
@@ -414,44 +433,71 @@ def main():
 
     def step_resident(i):
         if graphs and not eng.profile:
-            g, n = graphs[i % n_sets]
-            g.replay()
+            g, n = graphs[i % n_sets]                 # set k is captured on engine k % n_streams
+            if side:
+                with torch.cuda.stream(side[i % n_streams]):
+                    g.replay()
+            else:
+                g.replay()
             eng.launches += n
         else:
             eng.propose(dev_sets[i % n_sets])
+
+    def fork():
+        cur = torch.cuda.current_stream(dev)
+        for st in side:
+            st.wait_stream(cur)
+
+    def join():
+        cur = torch.cuda.current_stream(dev)
+        for st in side:
+            cur.wait_stream(st)
 
     pending = []
 
     def step_e2e(i):
         # host maps -> H2D (copy stream) -> layout conversion -> search -> D2H of the proposal lists; the upload
         # of step i overlaps the search of step i-1, every step moves its own h2d_bytes + d2h_bytes
-        pending.append(pipe.submit(host_sets[i % n_sets]))
+        pending.append((pipe, pipe.submit(host_sets[i % n_sets])))
         if len(pending) == 2:
-            pipe.result(pending.pop(0))
+            p, t = pending.pop(0)
+            p.result(t)
 
     def drain():
         while pending:
-            pipe.result(pending.pop(0))
+            p, t = pending.pop(0)
+            p.result(t)
+
+    def step_e2e_bf16(i):
+        pending.append((pipe_bf16, pipe_bf16.submit(host_sets_bf16[i % n_sets])))
+        if len(pending) == 2:
+            p, t = pending.pop(0)
+            p.result(t)
 
     gathered = [None, None, None]
     gather_ms = [0.0]
 
     def timed(step_fn, steps, profile=False):
         barrier()
-        if collector is not None:
-            collector.reset()
+        for c in collectors:
+            c.reset()
         eng.launches = 0
         eng.profile = profile
         eng.prof_events = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        fork()
         for i in range(steps):
             step_fn(i)
+        join()
         drain()                                       # e2e: the last proposals are on the host
         eg = torch.cuda.Event(enable_timing=True)
         eg.record()
         if world > 1:
-            gathered[:] = collector.gather(views=True)     # the job's only exchange: all ranks' proposal lists
+            if step_fn is step_resident and not profile:
+                gathered[:] = [c.gather(views=True) for c in collectors]     # the job's only exchange: all ranks' proposal lists
+            else:
+                gathered[:] = [collector.gather(views=True)]
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -465,14 +511,21 @@ def main():
     for i in range(args.warmup):
         step_resident(i)
     if not args.no_graph:
-        graphs.extend(eng.capture(d) for d in dev_sets)
+        for k, e in enumerate(engines[1:], 1):
+            e.propose(dev_sets[k])                    # warm-up of the other engines' buffers
+        graphs.extend(engines[k % n_streams].capture(d) for k, d in enumerate(dev_sets))
+        fork()
         for i in range(args.warmup):
             step_resident(i)
+        join()
     for i in range(max(args.warmup, 2)):
         step_e2e(i)
     drain()
-    if collector is not None:
-        collector.gather()                            # warm-up of the job's one exchange (buffers, NCCL channels)
+    for i in range(max(args.warmup, 2)):
+        step_e2e_bf16(i)
+    drain()
+    for c in collectors:
+        c.gather()                                    # warm-up of the job's one exchange (buffers, NCCL channels)
         torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -485,9 +538,10 @@ def main():
     prof = eng.prof_summary()
     eng.profile = False
     regions = float(eng.n_eval.float().mean().item())
-    if int(eng.status.item()) != 0:
+    if any(int(e.status.item()) != 0 for e in engines):
         raise RuntimeError("search capacity overflow during the bench")
     ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_bf16 = timed(step_e2e_bf16, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -509,12 +563,16 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "regions_per_image": regions,
                        "l2": "working set per step (216 MB bf16 weights + pooled rows) exceeds the 126 MB L2; inputs rotate over 2 distinct batches",
-                       "launch": "eager" if args.no_graph else "CUDA graph replay of the whole level loop (static launch sequence, device-side counts); "
-                                 "roofline events from a second, host-launched pass over the same steps",
+                       "launch": "eager" if args.no_graph else "CUDA graph replay of the whole level loop (static launch sequence, device-side counts), "
+                                 "%d batch(es) in flight on %d stream(s); roofline events from a second, host-launched, single-stream pass over the same steps" % (n_streams, n_streams),
                        "parallelism": "image-sharded x%d, no collective on the hot path; one NCCL all_gather of all K steps' proposal lists at the end, inside the timed region" % world},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
+                    "input": "f32 NCHW conv5_3 maps in pinned host memory (the blobs the reference's 'fc' net is handed)",
+                    "bf16_nhwc_input": {"value": world * BATCH * args.steps / (ms_e2e_bf16 / 1e3), "unit": "images/s",
+                                        "h2d_bytes_per_step": pipe_bf16.h2d_bytes, "ms_per_step": ms_e2e_bf16 / args.steps,
+                                        "note": "same call, host maps already bf16 NHWC (the engine's storage format): half the PCIe bytes, no conversion kernel"}},
             "gpu_launches": launches,
             "roofline": {"kernel": "fc_gemm_kernel<256,2> int6 25088->4096, all %d launches of a step (time-weighted)" % len(int6), "bound": "tensor",
                          "achieved": int6_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": int6_tf / tf_peak,
@@ -530,7 +588,7 @@ def main():
                 args.job, args.job // BATCH, args.steps)
         if world > 1:
             line["gather_ms"] = {"resident": gather_resident_ms, "e2e": gather_ms[0],
-                                 "bytes_per_rank": int(sum(t.numel() * t.element_size() for t in (collector.boxes, collector.scores, collector.counts)))}
+                                 "bytes_per_rank": int(sum(t.numel() * t.element_size() for c in collectors for t in (c.boxes, c.scores, c.counts)))}
         threads = os.cpu_count() or 1
         runner = None
         if not args.no_cpu_baseline:

@@ -116,6 +116,19 @@ int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, i
                    int ldo, int M_cap, const int32_t *m_live, int N, int K, int act, int act_aux,
                    void *workspace, size_t workspace_bytes, azn_stream_t stream);
 
+/* The three output layers of the AZ-Net head in one small kernel (csrc/heads.cu):
+ *   out[M, N] f32 = [sigmoid | identity | sigmoid](h7[M, K] . wh[N, K]^T + bias),  N = 5*nsub + 1 <= 64, K % 64 == 0
+ * replaces: InnerProduct adj_score / adj_bbox / zoom_score + Sigmoid adj_prob / zoom_prob
+ *           models/Pascal/VGG16/az-net/test_fc.prototxt:146-232 (inner_product_layer.cpp:80-93, sigmoid_layer.cpp:11-24)
+ *   h7   bf16 [M_cap, K] = [int7_1 | int7_2] activations, wh bf16 [N, K] the block-diagonal fusion of the three
+ *   weight blobs (rows: nsub adj_score, 4*nsub adj_bbox, 1 zoom_score), bias f32 [N], out f32 [M_cap, ldo];
+ *   columns [0, nsub) and 5*nsub go through the sigmoid.  m_live: int32 device scalar with the live row count or NULL.
+ * Same arithmetic as azn_fc_forward(..., AZN_ACT_AZ_HEAD, nsub) (bf16 operands, fp32 accumulation; the summation order
+ * differs), as an ordinary -- not persistent, not cooperative -- grid of warp-level mma.sync tiles: a few
+ * microseconds instead of the persistent kernel's fixed 13-18, and co-resident with another stream's GEMM. */
+int azn_az_heads_forward(const void *h7, const void *wh, const float *bias, float *out, int ldo, int M_cap,
+                         const int32_t *m_live, int N, int K, int nsub, azn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * One level of the adaptive search for a batch of images, after the heads have run.
  * replaces: _bbox_pred, _clip_boxes, un-dedup, _unwrap_adj_pred (lib/detect/test.py:106-151,

@@ -295,6 +295,34 @@ def test_fc_forward_live_count_and_f32_heads(dev):
     assert torch.all(got[333:] == -7.0)                                # rows past the live count untouched
 
 
+@pytest.mark.parametrize("M,m_live", [(900, 333), (64, None), (1, None), (1536, 1494), (130, 65)])
+def test_az_heads_kernel_vs_fp32_and_the_gemm_epilogue(dev, M, m_live):
+    """azn_az_heads_forward (mma.sync kernel) = fp32 product of the same bf16 operands + bias + sigmoids on columns
+    [0, nsub) and 5*nsub, to 2e-3 (fp32 accumulation of bf16 products; only the summation order differs), rows past the
+    live count untouched; and it agrees with azn_fc_forward's AZN_ACT_AZ_HEAD epilogue to 1e-4."""
+    from aznet_b200 import _lib as L
+    from aznet_b200 import ops
+    nsub, K = 11, 1280
+    N = 5 * nsub + 1
+    gen = torch.Generator(device="cpu").manual_seed(7 + M)
+    A = torch.relu(torch.randn((M, K), generator=gen)).to(torch.bfloat16).to(dev)
+    W = (torch.randn((N, K), generator=gen) * 0.05).to(torch.bfloat16).to(dev)
+    b = (torch.randn((N,), generator=gen) * 0.1).to(dev)
+    ml = None if m_live is None else torch.tensor([m_live], dtype=torch.int32, device=dev)
+    live = M if m_live is None else m_live
+    out = torch.full((M, 56), -7.0, dtype=torch.float32, device=dev)
+    ops.az_heads(A, W, b, nsub, m_live=ml, out=out)
+    ref = A.float() @ W.float().t() + b
+    want = ref.clone()
+    want[:, :nsub] = torch.sigmoid(ref[:, :nsub])
+    want[:, 5 * nsub] = torch.sigmoid(ref[:, 5 * nsub])
+    assert (out[:live] - want[:live]).abs().max().item() < 2e-3
+    assert torch.all(out[live:] == -7.0)
+    out2 = torch.full((M, 56), -7.0, dtype=torch.float32, device=dev)
+    ops.fc_forward(A, W, b, L.ACT_AZ_HEAD, nsub, m_live=ml, out=out2)
+    assert (out[:live] - out2[:live]).abs().max().item() < 1e-4
+
+
 def test_fc_forward_splitk_small_m(dev):
     from aznet_b200 import _lib as L
     for M in (1, 8, 64, 200):

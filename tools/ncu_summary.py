@@ -15,7 +15,12 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max"]
+        "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max",
+        # shared-memory / LSU data pipe (what bounds the staged ROI pool) and issue utilisation
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__m_l1tex2xbar_write_bytes.sum"]
 
 
 def main(rep, out):
