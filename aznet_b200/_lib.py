@@ -28,7 +28,7 @@ LEVEL_LAST, LEVEL_ROOT_PROPS, LEVEL_TUNE = 1, 2, 4
 
 EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_set_coop", "azn_hbm_write_probe", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
-    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_az_heads_forward", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
+    "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_az_heads_forward", "azn_az_heads_tune", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter", "azn_tune_threshold",
@@ -131,6 +131,8 @@ def _bind(L):
     L.azn_fc_trace.argtypes = [vp]
     L.azn_fc_forward.restype = i32
     L.azn_fc_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, sz, vp]
+    L.azn_az_heads_tune.restype = None
+    L.azn_az_heads_tune.argtypes = [i32]
     L.azn_az_heads_forward.restype = i32
     L.azn_az_heads_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, vp]
     L.azn_search_init.restype = i32

@@ -742,6 +742,8 @@ long long *g_trace = nullptr;
 void pick_tile(int N, int &bn, int &mh) {
     bn = N >= 2048 ? 256 : (N > 64 ? 128 : 64);
     mh = N >= 2048 ? 2 : 1;
+    // (measured, round 2: for the mid-width int7 layer, N = 1280, the 128 x 128 tile beats 256 x 128, 128 x 256 and
+    // 256 x 256 in CUDA-graph replay -- 0.789 vs 0.814 / 0.809 / 0.830 ms per step with four batches in flight)
     if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) bn = g_force_bn;
     if (g_force_mh == 1 || g_force_mh == 2) mh = g_force_mh;
     if (bn == 64) mh = 1;

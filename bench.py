@@ -352,7 +352,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (A/B)")
     ap.add_argument("--no-coop", action="store_true", help="plain (PDL) launch of the persistent GEMM instead of the cooperative launch (A/B)")
-    ap.add_argument("--streams", type=int, default=2, choices=(1, 2, 3, 4),
+    ap.add_argument("--streams", type=int, default=4, choices=(1, 2, 3, 4, 6, 8),
                     help="batches in flight for the device-resident figure: 2 = two engines on two CUDA streams, so that the latency-bound "
                          "kernels of one batch (ROI pool, decode / subdivide, selection) run next to the other batch's tensor-core GEMMs")
     ap.add_argument("--heads", default="mma", choices=("mma", "gemm"), help="output layers of the head: small mma.sync kernel or the persistent GEMM (A/B)")
@@ -382,6 +382,7 @@ def main():
     _lib.lib().azn_set_pdl(0 if args.no_pdl else 1)
     _lib.lib().azn_set_coop(0 if args.no_coop else 1)
     engine.HEADS_KERNEL = args.heads
+    _lib.lib().azn_az_heads_tune(1 if (args.no_graph or args.streams == 1) else 0)
 
     if args.job:
         assert args.job % (BATCH * world) == 0, "--job must be a multiple of 64 x the number of GPUs"

@@ -126,6 +126,9 @@ int azn_fc_forward(const void *A, const void *W, const float *bias, void *out, i
  * Same arithmetic as azn_fc_forward(..., AZN_ACT_AZ_HEAD, nsub) (bf16 operands, fp32 accumulation; the summation order
  * differs), as an ordinary -- not persistent, not cooperative -- grid of warp-level mma.sync tiles: a few
  * microseconds instead of the persistent kernel's fixed 13-18, and co-resident with another stream's GEMM. */
+/* Benchmark hook: 1 = plain stream-ordered launch of azn_az_heads_forward instead of programmatic dependent launch (the
+ * better choice with a single batch in flight, see csrc/heads.cu). */
+void azn_az_heads_tune(int plain_launch);
 int azn_az_heads_forward(const void *h7, const void *wh, const float *bias, float *out, int ldo, int M_cap,
                          const int32_t *m_live, int N, int K, int nsub, azn_stream_t stream);
 
