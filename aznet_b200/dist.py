@@ -57,11 +57,13 @@ class ProposalCollector:
     `gather()` is the job's only exchange: one all_gather per tensor, image order = (rank, batch, image) for a
     contiguous block partition of the batches."""
 
-    def __init__(self, n_batches: int, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
+    def __init__(self, n_batches: int, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor, storage: torch.Tensor | None = None):
         self.n_batches = nb = int(n_batches)
         # one byte buffer [all boxes slots | all scores slots | all counts slots]: the gather is ONE collective
+        # (`storage`: a slice of a CollectorGroup's joint buffer, so that several engines still gather in one call)
         sizes = [nb * t.numel() * t.element_size() for t in (boxes, scores, counts)]
-        self._buf = torch.zeros(sum(sizes), dtype=torch.uint8, device=boxes.device)
+        self._buf = torch.zeros(sum(sizes), dtype=torch.uint8, device=boxes.device) if storage is None else storage
+        assert self._buf.numel() == sum(sizes) and self._buf.dtype == torch.uint8
         views, off = [], 0
         for t, sz in zip((boxes, scores, counts), sizes):
             views.append(self._buf[off:off + sz].view(t.dtype).view((nb,) + tuple(t.shape)))
@@ -113,6 +115,47 @@ class ProposalCollector:
                 outs.append(g.contiguous().view(t.dtype).view((world * t.shape[0] * t.shape[1],) + tuple(t.shape[2:])))
             off += sz
         return tuple(outs)
+
+
+class CollectorGroup:
+    """One ProposalCollector per engine of a multi-stream run (several batches in flight, each engine with its own
+    device-side slot counter) over ONE joint byte buffer, so that the end-of-job exchange stays a single all_gather.
+    `gather()` -> per collector the strided views [world, n_batches*imgs, ...] of `ProposalCollector.gather(views=True)`."""
+
+    @staticmethod
+    def nbytes(n_batches, boxes, scores, counts):
+        return sum(int(n_batches) * t.numel() * t.element_size() for t in (boxes, scores, counts))
+
+    def __init__(self, n_batches: int, outputs):
+        """outputs: per engine its (out_boxes, out_scores, out_count) tensors (identical shapes)."""
+        outputs = list(outputs)
+        per = self.nbytes(n_batches, *outputs[0])
+        per_al = (per + 255) // 256 * 256
+        self._per, self._per_al = per, per_al
+        self._buf = torch.zeros(per_al * len(outputs), dtype=torch.uint8, device=outputs[0][0].device)
+        self.collectors = [ProposalCollector(n_batches, *o, storage=self._buf[k * per_al:k * per_al + per]) for k, o in enumerate(outputs)]
+        self._gathered = None
+
+    def reset(self):
+        for c in self.collectors:
+            c.reset()
+
+    def gather(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return [c.gather(views=True) for c in self.collectors]
+        world = dist.get_world_size()
+        if self._gathered is None:
+            self._gathered = torch.empty((world, self._buf.numel()), dtype=torch.uint8, device=self._buf.device)
+        dist.all_gather_into_tensor(self._gathered.view(-1), self._buf)
+        out = []
+        for k, c in enumerate(self.collectors):
+            base, off, views = k * self._per_al, 0, []
+            for t, sz in zip((c.boxes, c.scores, c.counts), c._sizes):
+                g = self._gathered[:, base + off:base + off + sz]
+                views.append(g.view(t.dtype).view((world, t.shape[0] * t.shape[1]) + tuple(t.shape[2:])))
+                off += sz
+            out.append(tuple(views))
+        return out
 
 
 def gather_detection_scores(top_scores: torch.Tensor, det_count: torch.Tensor):

@@ -368,7 +368,7 @@ def main():
     import torch
     import torch.distributed as dist
     from aznet_b200 import _lib, engine, ops, synth
-    from aznet_b200.dist import ProposalCollector
+    from aznet_b200.dist import CollectorGroup
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -411,7 +411,8 @@ def main():
     engines = [eng] + [engine.SearchEngine(head, BATCH, IM_H, IM_W, **CFG) for _ in range(n_streams - 1)]
     side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else []
     slots = (max(args.steps, args.warmup, 2) + n_streams - 1) // n_streams
-    collectors = [ProposalCollector(slots, e.out_boxes, e.out_scores, e.out_count) for e in engines] if world > 1 else []
+    group = CollectorGroup(slots, [(e.out_boxes, e.out_scores, e.out_count) for e in engines]) if world > 1 else None
+    collectors = group.collectors if group else []
     collector = collectors[0] if collectors else None
     # the copy into the collection is the last kernel of the search (azn_collect_proposals, slot from a device-side
     # counter), so it is part of the replayed CUDA graph
@@ -496,7 +497,7 @@ def main():
         eg.record()
         if world > 1:
             if step_fn is step_resident and not profile:
-                gathered[:] = [c.gather(views=True) for c in collectors]     # the job's only exchange: all ranks' proposal lists
+                gathered[:] = group.gather()          # the job's only exchange: ONE all_gather of all ranks' proposal lists
             else:
                 gathered[:] = [collector.gather(views=True)]
         e1.record()
@@ -525,8 +526,9 @@ def main():
     for i in range(max(args.warmup, 2)):
         step_e2e_bf16(i)
     drain()
-    for c in collectors:
-        c.gather()                                    # warm-up of the job's one exchange (buffers, NCCL channels)
+    if group is not None:
+        group.gather()                                # warm-up of the job's one exchange (buffers, NCCL channels)
+        collector.gather(views=True)
         torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -112,6 +112,26 @@ def _gloo_worker(rank, world, port, q):
         first = azdist.shard_images(n_img, r, world)[0]
         ok = ok and float(gb[(r * 2 + 0) * per, 0, 0]) == first and float(gb[(r * 2 + 1) * per, 0, 0]) == first + 1000.0
         ok = ok and int(gc[(r * 2 + 1) * per]) == 1 + first % P
+    # several engines (batches in flight), one joint buffer, ONE collective (bench.py --streams)
+    grp = azdist.CollectorGroup(2, [(boxes, scores, counts), (boxes, scores, counts)])
+    grp.collectors[0].add(0, boxes, scores, counts)
+    grp.collectors[1].add(0, boxes + 500.0, scores, counts)
+    grp.collectors[1].add(1, boxes + 700.0, scores, counts)
+    res = grp.gather()
+    ok = ok and len(res) == 2 and res[0][0].shape == (world, 2 * per, P, 4) and res[1][2].shape == (world, 2 * per)
+    for r in range(world):
+        first = azdist.shard_images(n_img, r, world)[0]
+        ok = ok and float(res[0][0][r, 0, 0, 0]) == first and float(res[1][0][r, 0, 0, 0]) == first + 500.0
+        ok = ok and float(res[1][0][r, per, 0, 0]) == first + 700.0 and int(res[1][2][r, per]) == 1 + first % P
+    # uneven shards: gather_proposals pads every rank's block to the largest shard with count-0 rows
+    lo2, hi2 = azdist.shard_images(5, rank, world)
+    ub = torch.full((hi2 - lo2, P, 4), float(rank), dtype=torch.float64)
+    uc = torch.full((hi2 - lo2,), 2, dtype=torch.int32)
+    gb2, _, gc2 = azdist.gather_proposals(ub, torch.zeros((hi2 - lo2, P)), uc)
+    per_max = (5 + world - 1) // world
+    ok = ok and gb2.shape[0] == world * per_max and int(gc2.sum()) == 2 * 5
+    ok = ok and all(int(gc2[r * per_max + k]) == (2 if azdist.shard_images(5, r, world)[0] + k < azdist.shard_images(5, r, world)[1] else 0)
+                    for r in range(world) for k in range(per_max))
     # the detection path's exchange step: every rank ends up with the whole set's [imgs, C, mpi] scores / counts
     Cc, mpi = 4, 3
     top = torch.full((hi - lo, Cc, mpi), float("-inf"))
