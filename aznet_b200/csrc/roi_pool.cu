@@ -376,16 +376,24 @@ template <> struct KeyOps<false> {
 // column reduce is straight-line code: MH loads at precomputed row offsets and (MH+1)/2 packed max instructions.
 // Column re-use between neighbouring bins is kept (see the generic path).
 template <typename K, int MH, bool PLAIN>
-__device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbase, int nh, int row_step, int sv, unsigned gb,
-                                                bool phv, uint4 *__restrict__ optr, int L) {
+__device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbase, int nh, int rot, int row_step, int sv, unsigned gb,
+                                                bool phv, bool valid, uint4 *__restrict__ optr, int L) {
 #define AZN_MX2(D, A) \
     (D).x = K::max3((D).x, (A).x, (A).x); (D).y = K::max3((D).y, (A).y, (A).y); (D).z = K::max3((D).z, (A).z, (A).z); (D).w = K::max3((D).w, (A).w, (A).w)
 #define AZN_MX3(D, A, B) \
     (D).x = K::max3((D).x, (A).x, (B).x); (D).y = K::max3((D).y, (A).y, (B).y); (D).z = K::max3((D).z, (A).z, (B).z); (D).w = K::max3((D).w, (A).w, (B).w)
+    // Row order of this lane: row (t + rot) mod nh at step t (any order will do: max is commutative, and a lane whose
+    // bin is shorter than MH simply cycles).  `rot` = 1 for the second bin row of a quarter-warp when its first map row
+    // lies an even distance from its partner's: the two 64-byte pieces of every LDS.128 then land in opposite bank halves
+    // instead of the same one (17.8 M of 47.8 M shared-load wavefronts were such conflicts at R = 20 000).
     int roff[MH];
-    const int last = max(nh, 1) - 1;
+    const int nhe = max(nh, 1);
+    int idx = rot < nhe ? rot : 0;
 #pragma unroll
-    for (int t = 0; t < MH; ++t) roff[t] = min(t, last) * row_step;
+    for (int t = 0; t < MH; ++t) {
+        roff[t] = idx * row_step;
+        idx = idx + 1 < nhe ? idx + 1 : 0;
+    }
     const unsigned a0 = PLAIN ? 0u : K::lowest();
     int w_cached = -1;                                       // warp-uniform
     uint4 cache = make_uint4(a0, a0, a0, a0);
@@ -412,7 +420,7 @@ __device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbas
             w_cached = we - 1;
         }
         uint4 res = make_uint4(0u, 0u, 0u, 0u);
-        if (we > ws && nh > 0) res = PLAIN ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
+        if (we > ws && valid) res = PLAIN ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
         if (phv) st_stream(optr + (size_t)pw * L, res);
     }
 #undef AZN_MX2
@@ -438,7 +446,13 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
     const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
     const int cells = H * W;
     const long n_items = (long)n_buckets * nchunk * nslices;
-    const int row_step = W * SV;
+    // Shared-memory row pitch in cells: ODD.  A quarter-warp of an LDS.128 serves two bin rows (2 x 4 vectors of 64
+    // bytes); the two 64-byte pieces share their banks exactly when their cell indices have the same parity, and with an
+    // even width the parity of cell (h, w) does not depend on h at all: every pair of distinct rows conflicts (the
+    // 30x50 map).  With an odd pitch rows alternate, and the row rotation of pool_bins_fixed takes care of the rest.
+    const int Wp = W | 1;
+    const int cells_p = H * Wp;
+    const int row_step = Wp * SV;
     for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slice = (int)(item % nslices);
         const int chunk = (int)((item / nslices) % nchunk);
@@ -458,13 +472,14 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
             // every CTA starts its sweep over the map at a different cell: CTAs that all walk the same cells in
             // the same order queue up on the same few L2 slices (measured: ~35 us per staging instead of ~3)
             const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
-            const int n_vec = cells * SV;
-            const int rot = (int)(((long)blockIdx.x * cells) / gridDim.x) * SV;
+            const int n_vec = cells_p * SV;
+            const int rot = (int)(((long)blockIdx.x * cells_p) / gridDim.x) * SV;
             for (int i0 = threadIdx.x; i0 < n_vec; i0 += ST_THREADS) {
                 const int i = i0 + rot < n_vec ? i0 + rot : i0 + rot - n_vec;
                 const int cell = i / SV, jj = i - cell * SV;
-                if (c0v + jj < L) cp_async16(s_map + i, src + (size_t)cell * L + jj);
-                else s_map[i] = make_uint4(0u, 0u, 0u, 0u);
+                const int h = cell / Wp, w = cell - h * Wp;
+                if (w < W && c0v + jj < L) cp_async16(s_map + i, src + (size_t)(h * W + w) * L + jj);
+                else s_map[i] = make_uint4(0u, 0u, 0u, 0u);          // channel padding of the last slice / the pitch column
             }
         }
         cp_async_wait_all();
@@ -478,7 +493,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         bool plain = false;
         if (real) {
             bool np = false;
-            for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
+            for (int i = threadIdx.x; i < cells_p * SV; i += ST_THREADS) {
                 const uint4 v = s_map[i];
                 np |= K::not_plain(v.x) | K::not_plain(v.y) | K::not_plain(v.z) | K::not_plain(v.w);
             }
@@ -486,7 +501,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         }
         if (real && !plain) {                                // raw bits -> keys in place, looking for a -0 on the way
             bool nz = false;
-            for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
+            for (int i = threadIdx.x; i < cells_p * SV; i += ST_THREADS) {
                 uint4 v = s_map[i];
                 nz |= K::neg_zero(v.x) | K::neg_zero(v.y) | K::neg_zero(v.z) | K::neg_zero(v.w);
                 v.x = K::to_key(v.x); v.y = K::to_key(v.y); v.z = K::to_key(v.z); v.w = K::to_key(v.w);
@@ -498,9 +513,11 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         const bool exact = s_negzero != 0;
         if (exact) {                                         // rare: bring the raw slice back for the exact path
             const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
-            for (int i = threadIdx.x; i < cells * SV; i += ST_THREADS) {
+            for (int i = threadIdx.x; i < cells_p * SV; i += ST_THREADS) {
                 const int cell = i / SV, jj = i - cell * SV;
-                if (c0v + jj < L) cp_async16(s_map + i, src + (size_t)cell * L + jj);
+                const int h = cell / Wp, w = cell - h * Wp;
+                if (w < W && c0v + jj < L) cp_async16(s_map + i, src + (size_t)(h * W + w) * L + jj);
+                else s_map[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             cp_async_wait_all();
             __syncthreads();
@@ -535,10 +552,20 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
                 if (variant == 2 && !exact && mh <= 6) {     // warp-uniform: fixed-height straight-line column reduces
                     const uint4 *rb = s_map + (size_t)min(hs, H - 1) * row_step + j;
+                    // partner = the other bin row of this lane's quarter-warp (lanes 4k..4k+7 hold bin rows 2k', 2k'+1
+                    // when SV == 4; with SV == 8 a quarter-warp is one bin row and there is nothing to rotate)
+                    // The idle lane group of the last pass (bin row 7 of 8) mirrors bin row 6 -- same rows, same
+                    // order: a broadcast, not a second set of wavefronts.
+                    const int nh_rows = (int)(hb >> 16) - hs;
+                    int rot = 0;
+                    if (SV <= 4) {
+                        const int hs_partner = __shfl_xor_sync(0xffffffffu, hs, SV);
+                        rot = (SV == 4 && (bsub & 1) && ph < ST_P && nh_rows >= 2 && hs_partner != hs && ((hs_partner - hs) & 1) == 0) ? 1 : 0;
+                    }
 #define AZN_FIX(MHH)                                                                                   \
     do {                                                                                               \
-        if (plain) pool_bins_fixed<K, MHH, true>(rb, nh, row_step, SV, gb, phv, optr, L);              \
-        else pool_bins_fixed<K, MHH, false>(rb, nh, row_step, SV, gb, phv, optr, L);                   \
+        if (plain) pool_bins_fixed<K, MHH, true>(rb, nh_rows, rot, row_step, SV, gb, phv, nh > 0, optr, L);     \
+        else pool_bins_fixed<K, MHH, false>(rb, nh_rows, rot, row_step, SV, gb, phv, nh > 0, optr, L);          \
     } while (0)
                     switch (mh) {
                     case 0: case 1: AZN_FIX(1); break;
@@ -827,7 +854,7 @@ constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the 
 template <typename Ops, int MODE>
 int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float *rois, const int32_t *n_rois, int R_cap,
                   float scale, void *out, int32_t *argmax, int32_t *bucket_ws, cudaStream_t s) {
-    const size_t cells = (size_t)H * W;
+    const size_t cells = (size_t)H * (MODE == 0 ? (W | 1) : W);     // the keys kernel pads its row pitch to an odd cell count
     int sv = 0, rb = ST_RB_MAX;
     for (int cand = (MODE == 0 ? 8 : 4); cand >= 2; cand >>= 1) {
         const size_t map_bytes = cells * cand * 16;
