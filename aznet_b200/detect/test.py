@@ -124,6 +124,21 @@ def _unwrap_adj_pred(boxes, scores):
     return b[keep, :], scores[keep]
 
 
+def _append_boxes(boxes):
+    """SEAR.APPEND_BOXES (lib/detect/test.py:320-344): every proposal spawns the boxes of SEAR.APPEND_TEMP (itself, four
+    boxes grown by a quarter on one side, one grown / one shrunk by an eighth all round), duplicates sifted on a grid of
+    1 / DEDUP_BOXES pixels (`div._sift_dup`, CUDA).  Off by default (config.py:176)."""
+    temp = cfg.SEAR.APPEND_TEMP                                   # [1, 4, n_templates]
+    n, ns = boxes.shape[0], temp.shape[2]
+    if n == 0:
+        return np.zeros((0, 4))
+    w, h = boxes[:, [2]] - boxes[:, [0]], boxes[:, [3]] - boxes[:, [1]]
+    Lm = np.hstack((w, h, w, h))[:, :, np.newaxis]
+    delta = np.hstack((boxes[:, [0]], boxes[:, [1]], boxes[:, [0]], boxes[:, [1]]))[:, :, np.newaxis]
+    subs = np.transpose(Lm * temp + delta, [2, 0, 1]).reshape((n * ns, 4))
+    return div._sift_dup(np.ascontiguousarray(subs, dtype=np.float64), 1 / cfg.DEDUP_BOXES)
+
+
 def _dedup(rois_blob):
     v = np.array([1, 1e3, 1e6, 1e9, 1e12])
     hashes = np.round(rois_blob * cfg.DEDUP_BOXES).dot(v)
@@ -221,8 +236,6 @@ def _device_maps(full: Net, im, names):
 def im_propose(net, im, return_conv=False, num_proposals=None):
     """Generate object proposals with AZ-Net (lib/detect/test.py:346-414).
     net: {'full': Net[, 'fc': Net]}; im: HxWx3 uint8 BGR.  Returns Y [n,4] float64 (and conv dict)."""
-    if cfg.SEAR.APPEND_BOXES:
-        raise NotImplementedError("SEAR.APPEND_BOXES (off by default, config.py:170) is outside the hot path")
     if _fast_route(net):
         full = net['full']
         eng = _engine_for(full, im.shape, num_proposals)
@@ -270,6 +283,8 @@ def im_propose(net, im, return_conv=False, num_proposals=None):
         else:
             n = cfg.SEAR.NUM_PROPOSALS if num_proposals is None else num_proposals
             Y = Y[np.argsort(-a_scores, kind='stable')[:min(n, Y.shape[0])], :]
+    if cfg.SEAR.APPEND_BOXES:                                     # test.py:403-406
+        Y = _clip_boxes(_append_boxes(Y), im.shape)
     print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(Y.shape[0], num_eval, k))
     return (Y, conv) if return_conv else Y
 
@@ -423,6 +438,9 @@ def _test_proposals_batched(net, imdb, prop_boxes, stats):
         for k, i in enumerate(db.idx):
             c = int(r['count'][k])
             prop_boxes[i] = r['boxes'][k, :c].copy()
+            if cfg.SEAR.APPEND_BOXES:                             # test.py:403-406, per image on the fetched list
+                prop_boxes[i] = _clip_boxes(_append_boxes(prop_boxes[i]), db.shape)
+                c = prop_boxes[i].shape[0]
             stats['num_eval'] += int(r['n_eval'][k])
             print('{0} proposals, evaluate {1} regions, reaches depth {2}.'.format(c, int(r['n_eval'][k]), int(r['depth'][k])))
             done[0] += 1
@@ -467,8 +485,6 @@ def test_proposals(net, imdb):
         os.makedirs(output_dir)
     num_boxes = 0.0
     stats = test_proposals.last_stats = {'route': 'host', 'num_eval': 0, 'h2d_bytes': 0, 'd2h_bytes': 0, 'batches': 0}
-    if cfg.SEAR.APPEND_BOXES:
-        raise NotImplementedError("SEAR.APPEND_BOXES (off by default, config.py:170) is outside the hot path")
     if _fast_route(net):
         stats['route'] = 'batched'
         t = _test_proposals_batched(net, imdb, prop_boxes, stats)

@@ -84,6 +84,7 @@ class OracleCfg:
     Tz: float = 0.5                      # injected by cfg_set_mode; no default in the reference
     Tc: float = 0.05                     # config.py:166
     FIXED_PROPOSAL_NUM: bool = True      # config.py:167
+    APPEND_BOXES: bool = False           # config.py:176
     MIN_SIDE: object = 10                # config.py:183 (an int: Python-2 `/` is floor division)
     BATCH_SIZE: int = 10000              # config.py:186 (voc.yml: 1000)
     DEDUP_BOXES: float = 1. / 16.        # config.py:203
@@ -523,11 +524,26 @@ def search_depth(im_shape, cfg):
     return int(np.log2(q) + 1.0)
 
 
+APPEND_TEMP = np.transpose(np.array([[[0, 0, 1, 1], [-0.25, 0, 1, 1], [0, 0, 1.25, 1], [0, -0.25, 1, 1], [0, 0, 1, 1.25],
+                                      [-0.125, -0.125, 1.125, 1.125], [0.125, 0.125, 0.875, 0.875]]]), axes=[0, 2, 1])   # config.py:177-183
+
+
+def append_boxes(boxes, cfg):
+    """_append_boxes, lib/detect/test.py:320-344: template boxes around every proposal, template-major, then
+    `_sift_dup` on a grid of 1 / DEDUP_BOXES pixels."""
+    n, ns = boxes.shape[0], APPEND_TEMP.shape[2]
+    w, h = boxes[:, [2]] - boxes[:, [0]], boxes[:, [3]] - boxes[:, [1]]
+    Lm = np.hstack((w, h, w, h))[:, :, np.newaxis]
+    delta = np.hstack((boxes[:, [0]], boxes[:, [1]], boxes[:, [0]], boxes[:, [1]]))[:, :, np.newaxis]
+    subs = np.transpose(Lm * APPEND_TEMP + delta, [2, 0, 1]).reshape((n * ns, 4)).astype(np.float64, copy=False)
+    return sift_dup(subs, 1 / cfg.DEDUP_BOXES)
+
+
 def im_propose(net, im_shape, cfg, conv=None, data_blob=None, num_proposals=None, return_scores=False,
                trace=None):
-    """im_propose, lib/detect/test.py:346-414 (APPEND_BOXES branch :404-406 omitted: off by
-    default, config.py:170).  Returns Y [n,4] float64 (and the matching scores / a per-level
-    trace for the parity tests)."""
+    """im_propose, lib/detect/test.py:346-414 (with cfg.APPEND_BOXES the appended, clipped boxes of :403-406; the
+    returned scores then still belong to the un-appended selection).  Returns Y [n,4] float64 (and the matching
+    scores / a per-level trace for the parity tests)."""
     B = np.array([[0, 0, im_shape[1] - 1.0, im_shape[0] - 1.0]])
     Y = np.zeros((0, 4))
     a_scores = np.zeros((0,))
@@ -556,6 +572,8 @@ def im_propose(net, im_shape, cfg, conv=None, data_blob=None, num_proposals=None
         ind_a = np.argsort(-a_scores, kind="stable")[:min(num_proposals, Y.shape[0])]
     info = {"num_eval": num_eval, "depth": k, "Y_all": Y, "scores_all": a_scores}
     Y = Y[ind_a, :]
+    if cfg.APPEND_BOXES:
+        Y = clip_boxes(append_boxes(Y, cfg), im_shape)
     if return_scores:
         return Y, a_scores[ind_a], info
     return Y

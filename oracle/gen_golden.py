@@ -92,8 +92,10 @@ def gen_search(rtest, rconfig):
         ("chunked_480x640", (480, 640), 800, 50, 0.0, 0.5, 300, True),
         ("tc_thresh_333x500", (333, 500), 1000, 10000, 0.5, 0.5, None, False),
         ("nozoom_600x1000", (600, 1000), 1000, 10000, 0.999, 0.0, 300, True),
+        ("append_375x500", (375, 500), 1000, 10000, 0.5, 0.5, 300, True),       # SEAR.APPEND_BOXES (test.py:320-344, 403-406)
     ]
     for name, shape, max_size, bs, tz, rate, nprop, fixed in cases:
+        cfg.SEAR.APPEND_BOXES = name.startswith("append")
         cfg.TEST.MAX_SIZE = max_size
         cfg.SEAR.BATCH_SIZE = bs
         cfg.SEAR.FIXED_PROPOSAL_NUM = fixed
@@ -114,6 +116,7 @@ def gen_search(rtest, rconfig):
         out[name + "_cfg"] = np.array([shape[0], shape[1], max_size, bs, tz, rate, -1 if nprop is None else nprop,
                                        int(fixed)], dtype=np.float64)
         print("search:", name, line)
+    cfg.SEAR.APPEND_BOXES = False
     # component vectors
     rng = np.random.default_rng(9)
     boxes = synth.make_boxes(64, 600, 1000, seed=8)

@@ -33,11 +33,11 @@ def O():
 @pytest.fixture()
 def cfg():
     from aznet_b200.detect import config as C
-    saved = (C.cfg.TEST.MAX_SIZE, C.cfg.SEAR.BATCH_SIZE, C.cfg.SEAR.FIXED_PROPOSAL_NUM)
+    saved = (C.cfg.TEST.MAX_SIZE, C.cfg.SEAR.BATCH_SIZE, C.cfg.SEAR.FIXED_PROPOSAL_NUM, C.cfg.SEAR.APPEND_BOXES)
     C.cfg_set_path("pytest")
     C.cfg_set_mode("Test", 0.5)
     yield C.cfg
-    C.cfg.TEST.MAX_SIZE, C.cfg.SEAR.BATCH_SIZE, C.cfg.SEAR.FIXED_PROPOSAL_NUM = saved
+    C.cfg.TEST.MAX_SIZE, C.cfg.SEAR.BATCH_SIZE, C.cfg.SEAR.FIXED_PROPOSAL_NUM, C.cfg.SEAR.APPEND_BOXES = saved
     C.cfg_set_mode("Test", 0.5)
 
 
@@ -77,7 +77,7 @@ def test_bbox_pred_clip_dropin(dev, golden, cfg):
     assert T._bbox_pred(np.zeros((0, 4)), np.zeros((0, 44), np.float32)).shape == (0, 44)
 
 
-@pytest.mark.parametrize("name", ["d0_600x1000", "chunked_480x640", "tc_thresh_333x500"])
+@pytest.mark.parametrize("name", ["d0_600x1000", "chunked_480x640", "tc_thresh_333x500", "append_375x500"])
 def test_im_propose_host_route_matches_reference_golden(dev, golden, cfg, name, capsys):
     """Duck-typed foreign net (HashNet) -> host level loop with CUDA decode/divide; equals the reference's run."""
     from aznet_b200.detect import config as C
@@ -85,6 +85,7 @@ def test_im_propose_host_route_matches_reference_golden(dev, golden, cfg, name, 
     g = golden["search"]
     H, W, max_size, bs, tz, rate, nprop, fixed = g[name + "_cfg"]
     cfg.TEST.MAX_SIZE, cfg.SEAR.BATCH_SIZE, cfg.SEAR.FIXED_PROPOSAL_NUM = int(max_size), int(bs), bool(fixed)
+    cfg.SEAR.APPEND_BOXES = name.startswith("append")               # test.py:320-344, 403-406 (off by default)
     C.cfg_set_mode("Test", float(tz))
     if nprop > 0:
         cfg.SEAR.NUM_PROPOSALS = int(nprop)

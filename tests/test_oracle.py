@@ -72,7 +72,8 @@ def test_against_compiled_reference_cython():
 def _run_search_case(name, g):
     H, W, max_size, bs, tz, rate, nprop, fixed = g[name + "_cfg"]
     cfg = O.OracleCfg(TEST_MAX_SIZE=int(max_size), BATCH_SIZE=int(bs), Tz=float(tz),
-                      FIXED_PROPOSAL_NUM=bool(fixed), NUM_PROPOSALS=300 if nprop < 0 else int(nprop))
+                      FIXED_PROPOSAL_NUM=bool(fixed), NUM_PROPOSALS=300 if nprop < 0 else int(nprop),
+                      APPEND_BOXES=name.startswith("append"))
     net = synth.HashNet(seed=11, zoom_rate=float(rate))
     conv = {"conv5_3": np.zeros((1, 1, 2, 2), np.float32)}
     Y, s, info = O.im_propose({"full": net, "fc": net}, (int(H), int(W), 3), cfg, conv=conv, return_scores=True)
@@ -80,7 +81,7 @@ def _run_search_case(name, g):
 
 
 @pytest.mark.parametrize("name", ["d0_600x1000", "voc_600x1000", "fullzoom_600x1000", "small_375x500",
-                                  "chunked_480x640", "tc_thresh_333x500", "nozoom_600x1000"])
+                                  "chunked_480x640", "tc_thresh_333x500", "nozoom_600x1000", "append_375x500"])
 def test_im_propose_golden(golden, name):
     g = golden["search"]
     Y, info = _run_search_case(name, g)
