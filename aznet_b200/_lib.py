@@ -27,7 +27,7 @@ NMS_SEG_MAX = 1024
 LEVEL_LAST, LEVEL_ROOT_PROPS, LEVEL_TUNE = 1, 2, 4
 
 EXPORTS = [
-    "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_set_coop", "azn_hbm_write_probe", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_nchw_f32_to_nhwc_bf16",
+    "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_set_coop", "azn_hbm_write_probe", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_roi_pool_fwd_ex", "azn_nchw_f32_to_nhwc_bf16",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_az_heads_forward", "azn_az_heads_tune", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
@@ -111,6 +111,8 @@ def _bind(L):
     L.azn_check_device.restype = i32
     L.azn_roi_pool_fwd.restype = i32
     L.azn_roi_pool_fwd.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp, vp, sz, vp]
+    L.azn_roi_pool_fwd_ex.restype = i32
+    L.azn_roi_pool_fwd_ex.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp, vp, sz, i32, vp]
     L.azn_roi_pool_workspace_bytes.restype = sz
     L.azn_roi_pool_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, i32]
     L.azn_roi_pool_tune.restype = None

@@ -713,8 +713,25 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         AZN_REQUIRE(!two_streams || ns != nullptr, "azn_nms: could not create the internal stream / events");
         cudaStream_t chain = two_streams ? ns->chain : s;
         cudaStream_t ms = (two_streams && ns->mask) ? ns->mask : s;      // partitioned: the mask has its own SMs and stream
+        // The internal streams and their events are shared by every azn_nms call on this device.  The enqueue of one
+        // call -- fork, launches, join -- is therefore one critical section: another host thread must not re-record
+        // `fork` / `done` between this call's record and its wait (an already enqueued wait keeps the record it saw).
+        // And whatever happens after the fork, the caller's stream is joined with the internal ones before returning,
+        // error or not: the caller may free the workspace as soon as its own stream is idle.
+        static std::mutex enqueue_mu;
+        std::unique_lock<std::mutex> enqueue_lock(enqueue_mu, std::defer_lock);
+        if (two_streams) enqueue_lock.lock();
+        struct Join {
+            NmsStreams *ns; cudaStream_t s, chain, ms; bool armed;
+            ~Join() {
+                if (!armed) return;
+                if (cudaEventRecord(ns->done, chain) == cudaSuccess) cudaStreamWaitEvent(s, ns->done, 0);
+                if (ms != s && cudaEventRecord(ns->mask_done, ms) == cudaSuccess) cudaStreamWaitEvent(s, ns->mask_done, 0);
+            }
+        } join{ns, s, chain, ms, false};
         if (two_streams) {
             AZN_CUDA(cudaEventRecord(ns->fork, s));                       // sorted boxes / zeroed state are ready
+            join.armed = true;
             if (ms != s) AZN_CUDA(cudaStreamWaitEvent(ms, ns->fork, 0));
             AZN_CUDA(cudaStreamWaitEvent(chain, ns->fork, 0));
         }
@@ -731,14 +748,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
                                     (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
                                     si == n_super - 1 ? 1 : 0, (const int *)w.row_done));
         }
-        if (two_streams) {
-            AZN_CUDA(cudaEventRecord(ns->done, chain));
-            AZN_CUDA(cudaStreamWaitEvent(s, ns->done, 0));
-            if (ms != s) {                                                // (implied by `done`, kept explicit for the join)
-                AZN_CUDA(cudaEventRecord(ns->mask_done, ms));
-                AZN_CUDA(cudaStreamWaitEvent(s, ns->mask_done, 0));
-            }
-        }
+        // `join` (above) makes the caller's stream wait for the chain and the mask on every path out of this scope
     }
     return AZN_OK;
 }

@@ -936,11 +936,11 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
 }
 
 // The staged kernel pays one slice load per (image, chunk): worth it when an image has many ROIs.
-bool want_staged(int n_img, int H, int W, int PH, int PW, const int32_t *n_rois, int R_cap, bool have_bucket_ws) {
-    if (g_pool_mode == 1) return false;
+bool want_staged(int mode, int n_img, int H, int W, int PH, int PW, const int32_t *n_rois, int R_cap, bool have_bucket_ws) {
+    if (mode == 1) return false;
     if (PH != ST_P || PW != ST_P || H > 65535 || W > 65535) return false;
     if (n_img > 1 && !have_bucket_ws) return false;
-    if (g_pool_mode == 2) return true;
+    if (mode == 2) return true;
     return n_rois == nullptr && (long)R_cap >= 64L * n_img;
 }
 }  // namespace
@@ -954,7 +954,16 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
                                 const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
                                 float spatial_scale, void *out, int32_t *argmax, void *workspace,
                                 size_t workspace_bytes, azn_stream_t stream) {
+    return azn_roi_pool_fwd_ex(feat, n_img, C, H, W, layout, dtype, rois, n_rois, R_cap, PH, PW, spatial_scale, out, argmax,
+                               workspace, workspace_bytes, g_pool_mode, stream);
+}
+
+extern "C" int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
+                                   const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
+                                   float spatial_scale, void *out, int32_t *argmax, void *workspace,
+                                   size_t workspace_bytes, int kernel_choice, azn_stream_t stream) {
     if (R_cap == 0) return AZN_OK;
+    AZN_REQUIRE(kernel_choice >= 0 && kernel_choice <= 2, "azn_roi_pool_fwd_ex: kernel_choice must be 0 (auto), 1 (direct) or 2 (staged)");
     AZN_REQUIRE(feat && rois && out, "azn_roi_pool_fwd: null pointer");
     AZN_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R_cap >= 0,
                 "azn_roi_pool_fwd: bad shape n_img=%d C=%d H=%d W=%d PH=%d PW=%d R=%d", n_img, C, H, W, PH, PW, R_cap);
@@ -968,7 +977,7 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         AZN_REQUIRE(((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0), "azn_roi_pool_fwd: 16-byte alignment");
         const int L = C * esize / 16;
         const bool bucket_ok = n_img <= 1 || (workspace && bucket_ws_bytes(n_img, R_cap) > 0 && workspace_bytes >= bucket_ws_bytes(n_img, R_cap));
-        if (want_staged(n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
+        if (want_staged(kernel_choice, n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
             const int rc = dtype == AZN_DTYPE_F32
                 ? launch_staged<OpsF32, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s)
                 : launch_staged<OpsBF16, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s);
@@ -1009,7 +1018,7 @@ extern "C" int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W
         {
             int32_t *bws = (int32_t *)((char *)workspace + need);
             const bool bucket_ok = n_img <= 1 || (bucket_ws_bytes(n_img, R_cap) > 0 && workspace_bytes >= need + bucket_ws_bytes(n_img, R_cap));
-            if (C % 4 == 0 && want_staged(n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
+            if (C % 4 == 0 && want_staged(kernel_choice, n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
                 const int rc = argmax
                     ? launch_staged<OpsF32, 2>(nhwc, n_img, H, W, C / 4, rois, n_rois, R_cap, spatial_scale, out, argmax, bws, s)
                     : launch_staged<OpsF32, 1>(nhwc, n_img, H, W, C / 4, rois, n_rois, R_cap, spatial_scale, out, nullptr, bws, s);

@@ -45,13 +45,12 @@ def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_sc
     nbytes = L.lib().azn_roi_pool_workspace_bytes(n, Cc, H, W, lay, dt, R)
     ws = _scratch(feat.device, nbytes) if nbytes else None
     if staged is not None:                     # many ROIs per image with a device-side count: ask for the staged kernel
-        L.lib().azn_roi_pool_tune(2 if staged else 1)
-    try:
+        L.check(L.lib().azn_roi_pool_fwd_ex(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
+                                            spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, 2 if staged else 1, _stream()),
+                "azn_roi_pool_fwd_ex")
+    else:
         L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
                                          spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, _stream()), "azn_roi_pool_fwd")
-    finally:
-        if staged is not None:
-            L.lib().azn_roi_pool_tune(0)
     return (out, amax) if want_argmax else out
 
 

@@ -85,6 +85,12 @@ int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layou
                      const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
                      float spatial_scale, void *out, int32_t *argmax, void *workspace,
                      size_t workspace_bytes, azn_stream_t stream);
+/* The same with the kernel choice as an ARGUMENT (0 automatic, 1 direct kernels only, 2 staged kernel whenever it
+ * applies) instead of the process-wide azn_roi_pool_tune setting: what callers that run several host threads use. */
+int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
+                        const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
+                        float spatial_scale, void *out, int32_t *argmax, void *workspace,
+                        size_t workspace_bytes, int kernel_choice, azn_stream_t stream);
 
 /* f32 NCHW -> bf16 NHWC feature-map conversion (layout the search engine keeps resident). */
 int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, void *dst,
