@@ -254,10 +254,13 @@ def run_reference(args):
         "impl": "reference", "metric": "AZ proposal images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "regions_per_image": runner.regions / max(runner.images, 1),
-                   "step": "bounded sample: %d images of the 64-image batch per step" % per_step},
+        # the same workload description as the GPU arm's `config` (a subset of its keys, equal values); what this arm
+        # actually timed -- a bounded sample of that workload -- is stated in cpu_baseline.sample
+        "config": {"workload": WORKLOAD, "global_batch": args.gpus * BATCH},
+        "regions_per_image": runner.regions / max(runner.images, 1),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": runner.kind,
-                         "sample": "%d images of the bench workload in %.1f s (%s)" % (n, dt, runner.what)},
+                         "sample": "a step = a bounded sample of %d images of the 64-image batch; %d images in %.1f s (%s)" % (
+                             per_step, n, dt, runner.what)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if not args.no_extra:
