@@ -83,6 +83,7 @@ class DetectEngine:
         st = self._st
         assert boxes.dtype == torch.float64 and boxes.is_contiguous() and tuple(boxes.shape) == (self.n_img, self.cap, 4)
         assert counts.dtype == torch.int32 and counts.numel() == self.n_img and counts.is_contiguous()
+        self._boxes, self._counts = boxes, counts           # azn_detect_select reads them again: keep the storage alive
         st.boxes, st.n_boxes = boxes.data_ptr(), counts.data_ptr()
         L.check(L.lib().azn_detect_rois(C.byref(st), ops._stream()), "azn_detect_rois")
         self.launches += 2
