@@ -427,19 +427,188 @@ __device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbas
 #undef AZN_MX3
 }
 
+// ---- (1d) grouped pooling: one warp = 32/SV ROIs of the SAME width in map cells -----------------------------------
+// The per-ROI loop nest above spends ~630 warp instructions per ROI-slice of which ~140 are loads, maxima and stores:
+// every lane recomputes the ROI geometry (16 times per ROI, once per slice), a warp walks ONE ROI with its lanes on the
+// seven bin rows -- so every map row on a bin boundary is read by two lane groups -- and the column loop is a real
+// loop per bin.  Here a pre-pass (roi_group_kernel) sorts the ROIs of an image by their width in cells and packs them
+// into groups of G = 32/SV; a warp pools one group, lane group g = ROI g, and walks the seven bin rows one after the
+// other.  What that buys:
+//   * the bins' column ranges depend on the ROI width alone (floor(p*w/7), ceil((p+1)*w/7): a 64 x 7 table built once
+//     per CTA with the reference's float formulas), so the column sweep of a group is ONE warp-uniform program:
+//     load column, fold, and where a bin ends store it and restart the accumulator from nothing or from that column
+//     (consecutive bins overlap by at most one column) -- every column is reduced once, no per-bin loop, no geometry;
+//   * the bins' row ranges come from the same table indexed by the ROI height (per lane); the tallest bin of the
+//     group fixes the template parameter MH as before, shorter bins cycle through their rows;
+//   * the pre-pass orders a class by height and alternates the parity of (start_h + start_w): the two ROIs that share a
+//     quarter-warp of an LDS.128 then read cells of opposite parity, i.e. opposite bank halves (odd row pitch).
+// ROIs the tables do not cover (clipped by the map border, wider or taller than 64 cells, bad batch index) stay on the
+// per-ROI path through the old bucket list.
+constexpr int GP_MAXDIM = 64;            // ROI sides, in cells, of the grouped path
+constexpr int GP_MAX_IMG = 6;            // images per call (the pre-pass keeps a 33 KB histogram per image in shared memory)
+constexpr int GP_CLS = GP_MAXDIM;        // width classes per image
+constexpr int GP_PITCH = 2 * GP_MAXDIM + 1;   // histogram cells per class: 2 parities x 64 heights (+1: bank spread)
+
+// floor(p * bin) | ceil((p + 1) * bin) << 8 of a ROI side of rs cells, before the start offset and the clamp
+__device__ __forceinline__ unsigned gp_bin_rel(int rs, int p) {
+    const float bin = __fdiv_rn((float)rs, (float)ST_P);
+    const int lo = (int)floorf(__fmul_rn((float)p, bin));
+    const int hi = (int)ceilf(__fmul_rn((float)(p + 1), bin));
+    return (unsigned)lo | ((unsigned)hi << 8);
+}
+__device__ __forceinline__ int gp_extent(int rs) { return (int)(gp_bin_rel(rs, ST_P - 1) >> 8); }   // cells a side of rs really spans
+
+struct GpTables {
+    unsigned short rel[GP_MAXDIM][8];                       // [rs - 1][p]: lo | hi << 8
+    // [rs - 1]: the column program of a side of rs cells, 4 bits per column: bins that end at this column (0..7) |
+    // 8 if the bin after them starts at this very column (consecutive bins overlap by at most one column; bins that
+    // end together with a later one necessarily start at it)
+    unsigned long long code[GP_MAXDIM][4];
+};
+
+__device__ __forceinline__ void gp_build_tables(GpTables &t) {
+    for (int i = threadIdx.x; i < GP_MAXDIM * 8; i += blockDim.x)
+        t.rel[i / 8][i % 8] = (unsigned short)(i % 8 < ST_P ? gp_bin_rel(i / 8 + 1, i % 8) : 0u);
+    __syncthreads();
+    if (threadIdx.x < GP_MAXDIM) {
+        const int rs = threadIdx.x + 1;
+        const unsigned short *r = t.rel[rs - 1];
+        const int ncol = r[ST_P - 1] >> 8;
+        unsigned long long word[4] = {0ull, 0ull, 0ull, 0ull};
+        int p = 0;
+        for (int w = 0; w < ncol && w < 64; ++w) {
+            unsigned n = 0, carry = 0;
+            while (p < ST_P && (r[p] >> 8) - 1 == w) {
+                carry = (p + 1 < ST_P && (r[p + 1] & 0xff) == w) ? 8u : 0u;
+                ++n;
+                ++p;
+            }
+            word[w >> 4] |= (unsigned long long)(n | carry) << (4 * (w & 15));
+        }
+        for (int k = 0; k < 4; ++k) t.code[rs - 1][k] = word[k];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned mov_fence(unsigned x) {   // a copy the compiler cannot fold away
+    unsigned y;
+    asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+// One bin row of a group: `arow` = shared byte address of (first map row of the lane's bin, first column of its ROI,
+// its channel vector), nh rows of row_bytes, MH = the group's tallest bin in this bin row (0: any height, row loop).
+// The loop is latency-bound unless loads run ahead (32 warps per SM, a handful of instructions per load): the next
+// column's rows are requested as soon as the current column is reduced, before it is folded into the bins, and a
+// stored accumulator is copied first, so that the restart of the accumulator does not wait for the store to drain.
+template <typename K, int SV, int MH, bool PLAIN>
+__device__ __forceinline__ void pool_group_row(const GpTables &t, unsigned arow, int nh, int mh, unsigned row_bytes, int rw,
+                                               uint4 *__restrict__ optr, int L, bool store) {
+#define AZN_MX2(D, A) \
+    (D).x = K::max3((D).x, (A).x, (A).x); (D).y = K::max3((D).y, (A).y, (A).y); (D).z = K::max3((D).z, (A).z, (A).z); (D).w = K::max3((D).w, (A).w, (A).w)
+#define AZN_MX3(D, A, B) \
+    (D).x = K::max3((D).x, (A).x, (B).x); (D).y = K::max3((D).y, (A).y, (B).y); (D).z = K::max3((D).z, (A).z, (B).z); (D).w = K::max3((D).w, (A).w, (B).w)
+    constexpr unsigned COL = SV * 16;
+    // row r of the lane at step k: k mod nh (max is idempotent: a lane whose bin is shorter cycles through its rows)
+    unsigned ra0 = arow, ra1 = arow, ra2 = arow, ra3 = arow, ra4 = arow, ra5 = arow;
+    if (MH >= 2) {
+        int idx = 1 < nh ? 1 : 0;
+        ra1 = arow + (unsigned)idx * row_bytes; idx = idx + 1 < nh ? idx + 1 : 0;
+        if (MH >= 3) { ra2 = arow + (unsigned)idx * row_bytes; idx = idx + 1 < nh ? idx + 1 : 0; }
+        if (MH >= 4) { ra3 = arow + (unsigned)idx * row_bytes; idx = idx + 1 < nh ? idx + 1 : 0; }
+        if (MH >= 5) { ra4 = arow + (unsigned)idx * row_bytes; idx = idx + 1 < nh ? idx + 1 : 0; }
+        if (MH >= 6) { ra5 = arow + (unsigned)idx * row_bytes; }
+    }
+    const unsigned a0 = PLAIN ? 0u : K::lowest();
+    uint4 v0, v1, v2, v3, v4, v5;
+    v1 = v2 = v3 = v4 = v5 = make_uint4(a0, a0, a0, a0);
+#define AZN_LOAD_COL()                                                                            \
+    do {                                                                                          \
+        if (MH == 0) {       /* tall bins: a row loop, rows past the lane's own bin re-read its last */ \
+            unsigned a = ra0;                                                                     \
+            v0 = lds128(a);                                                                       \
+            for (int k = 1; k < mh; ++k) {                                                        \
+                if (k < nh) a += row_bytes;                                                       \
+                const uint4 b = lds128(a);                                                        \
+                AZN_MX2(v0, b);                                                                   \
+            }                                                                                     \
+            ra0 += COL;                                                                           \
+        } else {                                                                                  \
+            v0 = lds128(ra0); ra0 += COL;                                                         \
+            if (MH >= 2) { v1 = lds128(ra1); ra1 += COL; }                                        \
+            if (MH >= 3) { v2 = lds128(ra2); ra2 += COL; }                                        \
+            if (MH >= 4) { v3 = lds128(ra3); ra3 += COL; }                                        \
+            if (MH >= 5) { v4 = lds128(ra4); ra4 += COL; }                                        \
+            if (MH >= 6) { v5 = lds128(ra5); ra5 += COL; }                                        \
+        }                                                                                         \
+    } while (0)
+    uint4 acc = make_uint4(a0, a0, a0, a0);
+#define AZN_EMIT()                                                                                \
+    do {                                                                                          \
+        uint4 r;                                                                                  \
+        if (PLAIN) r = make_uint4(mov_fence(acc.x), mov_fence(acc.y), mov_fence(acc.z), mov_fence(acc.w)); \
+        else r = make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w)); \
+        if (store) st_stream(optr, r);                                                            \
+        optr += L;                                                                                \
+    } while (0)
+    const unsigned long long *cw = t.code[rw - 1];
+    const int ncol = t.rel[rw - 1][ST_P - 1] >> 8;
+    unsigned long long word = cw[0];
+    int w = 0;
+    AZN_LOAD_COL();
+#pragma unroll 1
+    for (;;) {
+        uint4 c = v0;                                        // the column's maximum over the lane's rows
+        if (MH == 2) { AZN_MX2(c, v1); }
+        if (MH >= 3) { AZN_MX3(c, v1, v2); }
+        if (MH == 4) { AZN_MX2(c, v3); }
+        if (MH >= 5) { AZN_MX3(c, v3, v4); }
+        if (MH == 6) { AZN_MX2(c, v5); }
+        ++w;
+        if (w < ncol) AZN_LOAD_COL();                        // in flight while this column is folded and stored
+        AZN_MX2(acc, c);
+        const unsigned code = (unsigned)word & 15u;
+        word >>= 4;
+        unsigned n = code & 7u;                              // bins that end at this column
+        if (n) {
+#pragma unroll 1
+            for (; n > 1u; --n) { AZN_EMIT(); acc = c; }
+            AZN_EMIT();
+            acc = (code & 8u) ? c : make_uint4(a0, a0, a0, a0);
+        }
+        if (w >= ncol) break;
+        if ((w & 15) == 0) word = cw[w >> 4];
+    }
+#undef AZN_EMIT
+#undef AZN_LOAD_COL
+#undef AZN_MX2
+#undef AZN_MX3
+}
+
 template <bool BF16, int SV>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
                      const int32_t *__restrict__ bucket_off, const int32_t *__restrict__ perm,
-                     float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices, int variant) {
+                     float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices, int variant,
+                     const int32_t *__restrict__ goff, const uint2 *__restrict__ gdesc) {
+    // gdesc != nullptr: the grouped path (1d).  goff[b] .. goff[b + 1] = image b's groups in gdesc (G slots of
+    // (ROI index or -1, start_w | start_h << 8 | roi_h << 16 | roi_w << 24) each); bucket_off / perm then list only
+    // the ROIs the grouped path does not cover.  The kernel is launched as a programmatic dependent of the pre-pass.
     typedef KeyOps<BF16> K;
     typedef typename K::Exact Exact;
     extern __shared__ uint4 s_dyn[];
     uint4 *s_map = s_dyn;                                   // [H*W][SV]
     __shared__ int s_negzero;
-    __shared__ int s_next;
+    __shared__ int s_next, s_gnext;
+    __shared__ GpTables s_gp;
     constexpr int PHG = 32 / SV;                            // bin rows a warp covers at once
+    constexpr int G = 32 / SV;                              // ROIs per group (1d)
     constexpr int NG = (ST_P + PHG - 1) / PHG;              // groups of bin rows per ROI
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = lane % SV, bsub = lane / SV;
@@ -453,6 +622,29 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
     const int Wp = W | 1;
     const int cells_p = H * Wp;
     const int row_step = Wp * SV;
+    // every CTA starts its sweep over the map at a different cell: CTAs that all walk the same cells in
+    // the same order queue up on the same few L2 slices (measured: ~35 us per staging instead of ~3)
+    auto stage_slice = [&](int bucket, int c0v) {
+        const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
+        const int n_vec = cells_p * SV;
+        const int rot = (int)(((long)blockIdx.x * cells_p) / gridDim.x) * SV;
+        for (int i0 = threadIdx.x; i0 < n_vec; i0 += ST_THREADS) {
+            const int i = i0 + rot < n_vec ? i0 + rot : i0 + rot - n_vec;
+            const int cell = i / SV, jj = i - cell * SV;
+            const int h = cell / Wp, w = cell - h * Wp;
+            if (w < W && c0v + jj < L) cp_async16(s_map + i, src + (size_t)(h * W + w) * L + jj);
+            else s_map[i] = make_uint4(0u, 0u, 0u, 0u);              // channel padding of the last slice / the pitch column
+        }
+    };
+    long prestaged = -1;
+    if (gdesc) {
+        // The map does not depend on the pre-pass: build the tables and stage the first item's slice while it runs.
+        gp_build_tables(s_gp);
+        const long item = blockIdx.x;
+        const int bucket = (int)(item / ((long)nslices * nchunk));
+        if (item < n_items && bucket < n_img) { stage_slice(bucket, (int)(item % nslices) * SV); prestaged = item; }
+        pdl_grid_wait();
+    }
     for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slice = (int)(item % nslices);
         const int chunk = (int)((item / nslices) % nchunk);
@@ -460,28 +652,21 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         const int base = bucket_off ? bucket_off[bucket] : 0;
         const int cnt = bucket_off ? bucket_off[bucket + 1] - base : R;
         const int lo = base + (int)((long)cnt * chunk / nchunk), hi = base + (int)((long)cnt * (chunk + 1) / nchunk);
-        if (hi <= lo) continue;
         const bool real = bucket < n_img;
+        // this chunk's share of the image's groups: every nchunk-th one, so that all chunks get the same mix of sizes
+        const int g_lo = gdesc && real ? goff[bucket] : 0, g_hi = gdesc && real ? goff[bucket + 1] : 0;
+        const int n_grp = g_hi - g_lo > chunk ? (g_hi - g_lo - chunk + nchunk - 1) / nchunk : 0;
+        if (hi <= lo && n_grp == 0) {
+            if (prestaged == item) { cp_async_wait_all(); __syncthreads(); }     // nobody may still be writing the slice
+            continue;
+        }
         const int c0v = slice * SV;
-        if (threadIdx.x == 0) { s_negzero = 0; s_next = lo + ST_THREADS / 32; }
+        if (threadIdx.x == 0) { s_negzero = 0; s_next = lo + ST_THREADS / 32; s_gnext = ST_THREADS / 32; }
         const bool jv = c0v + j < L;
 #ifdef AZN_POOL_TRACE
         const long long t0 = clock64();
 #endif
-        if (real) {
-            // every CTA starts its sweep over the map at a different cell: CTAs that all walk the same cells in
-            // the same order queue up on the same few L2 slices (measured: ~35 us per staging instead of ~3)
-            const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
-            const int n_vec = cells_p * SV;
-            const int rot = (int)(((long)blockIdx.x * cells_p) / gridDim.x) * SV;
-            for (int i0 = threadIdx.x; i0 < n_vec; i0 += ST_THREADS) {
-                const int i = i0 + rot < n_vec ? i0 + rot : i0 + rot - n_vec;
-                const int cell = i / SV, jj = i - cell * SV;
-                const int h = cell / Wp, w = cell - h * Wp;
-                if (w < W && c0v + jj < L) cp_async16(s_map + i, src + (size_t)(h * W + w) * L + jj);
-                else s_map[i] = make_uint4(0u, 0u, 0u, 0u);          // channel padding of the last slice / the pitch column
-            }
-        }
+        if (real && prestaged != item) stage_slice(bucket, c0v);
         cp_async_wait_all();
         __syncthreads();
 #ifdef AZN_POOL_TRACE
@@ -525,11 +710,8 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
 #ifdef AZN_POOL_TRACE
         const long long t3 = clock64();
 #endif
-        // ROIs are handed out dynamically (shared cursor): their cost varies by an order of magnitude with
-        // their size, and a static deal leaves a tail of one big ROI per item.
-        int ri = lo + warp;
-        while (ri < hi) {
-            const int r = perm ? perm[ri] : ri;
+        // the per-ROI path: one warp, one ROI, lanes on the bin rows
+        auto pool_one = [&](const int r) {
             const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
             const bool ok = real && q.b == bucket;
             unsigned gb = 0;                                 // lanes 0..6: packed h bounds of bin row `lane`; 7..13: w bounds
@@ -550,7 +732,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 const unsigned hb = __shfl_sync(0xffffffffu, gb, min(ph, ST_P - 1));
                 const int hs = hb & 0xffff, nh = phv ? (int)(hb >> 16) - hs : 0;
                 uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
-                if (variant == 2 && !exact && mh <= 6) {     // warp-uniform: fixed-height straight-line column reduces
+                if ((variant & 255) == 2 && !exact && mh <= 6) {     // warp-uniform: fixed-height straight-line column reduces
                     const uint4 *rb = s_map + (size_t)min(hs, H - 1) * row_step + j;
                     // partner = the other bin row of this lane's quarter-warp (lanes 4k..4k+7 hold bin rows 2k', 2k'+1
                     // when SV == 4; with SV == 8 a quarter-warp is one bin row and there is nothing to rotate)
@@ -642,6 +824,72 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                     if (phv) st_stream(optr, res);
                 }
             }
+        };
+        // (1d) the image's groups, largest ROIs first (the pre-pass sorts by ascending width; a big group handed out last
+        // would be the item's tail)
+        if (n_grp > 0) {
+            // Work unit = one bin row of one group, handed out in order: the seven bin rows of a group are pooled by seven
+            // warps at about the same time, and -- more important -- the CTAs of the other slices reach the same unit within
+            // a few microseconds.  A pooled row of C channels is assembled in L2 from the 64-byte pieces of nslices CTAs; with
+            // whole groups as units (7 x longer) the CTAs drifted apart by more than the L2 residency of a line, the halves
+            // of a 128-byte line went to DRAM separately, and the kernel ran at the rate of scattered 64-byte writes
+            // (2.6 TB/s, tools/probes/tlb_probe.cu) instead of the streaming rate.
+            const int g = lane / SV;
+            const unsigned smap_a = (unsigned)__cvta_generic_to_shared(s_map);
+            const unsigned row_bytes = (unsigned)row_step * 16u;
+            const int n_units = n_grp * ST_P;
+            // the next unit's index and descriptor are fetched while the current one is pooled
+            int u = warp;
+            uint2 e = make_uint2(0u, 0u);
+            if (u < n_units) e = gdesc[(size_t)(g_hi - 1 - (chunk + (u / ST_P) * nchunk)) * G + g];
+            while (u < n_units) {
+                int u2 = 0;
+                if (lane == 0) u2 = atomicAdd(&s_gnext, 1);
+                u2 = __shfl_sync(0xffffffffu, u2, 0);
+                uint2 e2 = make_uint2(0u, 0u);
+                if (u2 < n_units) e2 = gdesc[(size_t)(g_hi - 1 - (chunk + (u2 / ST_P) * nchunk)) * G + g];
+                const int ph = u % ST_P;
+                if (!exact) {
+                    const int dbg = variant >> 8;
+                    const int idx = (int)e.x;
+                    const int sw = e.y & 0xff, sh = (e.y >> 8) & 0xff, rh = (e.y >> 16) & 0xff;
+                    const int rw = __shfl_sync(0xffffffffu, (int)(e.y >> 24), 0);        // the same for the whole group
+                    const bool store = idx >= 0 && jv && dbg != 1;
+                    const unsigned hb = s_gp.rel[rh - 1][ph];
+                    const int hl = hb & 0xff, nh = (int)(hb >> 8) - hl;
+                    const int mh = __reduce_max_sync(0xffffffffu, nh);
+                    const unsigned arow = smap_a + (unsigned)(((sh + hl) * Wp + sw) * SV + j) * 16u;
+                    uint4 *optr = out + ((size_t)max(idx, 0) * ST_BINS + (size_t)ph * ST_P) * L + c0v + j;
+#define AZN_GRP(MHH)                                                                                      \
+    do {                                                                                                  \
+        if (plain) pool_group_row<K, SV, MHH, true>(s_gp, arow, nh, mh, row_bytes, rw, optr, L, store);    \
+        else pool_group_row<K, SV, MHH, false>(s_gp, arow, nh, mh, row_bytes, rw, optr, L, store);         \
+    } while (0)
+                    switch (mh) {
+                    case 1: AZN_GRP(1); break;
+                    case 2: AZN_GRP(2); break;
+                    case 3: AZN_GRP(3); break;
+                    case 4: AZN_GRP(4); break;
+                    case 5: AZN_GRP(5); break;
+                    case 6: AZN_GRP(6); break;
+                    default: AZN_GRP(0); break;
+                    }
+#undef AZN_GRP
+                } else if (ph == 0) {                        // a slice with a -0: the exact per-ROI path, ROI by ROI
+                    for (int gg = 0; gg < G; ++gg) {
+                        const int idx = __shfl_sync(0xffffffffu, (int)e.x, gg * SV);
+                        if (idx >= 0) pool_one(idx);
+                    }
+                }
+                u = u2;
+                e = e2;
+            }
+        }
+        // ROIs are handed out dynamically (shared cursor): their cost varies by an order of magnitude with
+        // their size, and a static deal leaves a tail of one big ROI per item.
+        int ri = lo + warp;
+        while (ri < hi) {
+            pool_one(perm ? perm[ri] : ri);
             int nxt = 0;
             if (lane == 0) nxt = atomicAdd(&s_next, 1);
             ri = __shfl_sync(0xffffffffu, nxt, 0);
@@ -698,6 +946,98 @@ roi_bucket_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         const int b = (int)rois[(size_t)r * 5];
         perm[atomicAdd(&s_cnt[(b < 0 || b >= n_img) ? n_img : b], 1)] = r;
+    }
+}
+
+// Pre-pass of the grouped path (1d).  One CTA: every ROI is classified -- regular (the tables cover it: sides of at
+// most 64 cells, not clipped by the map border) or not -- and the regular ones are counting-sorted by (image, width,
+// parity of start_h + start_w, height) into gdesc, each (image, width) class padded to a multiple of G slots; inside a
+// class the two parity sequences (each ascending in height) are zipped, so that neighbouring slots -- the two ROIs of a
+// quarter-warp -- have opposite parity and similar heights.  The rest goes to the per-ROI lists ioff / iperm (bucket
+// n_img = bad batch index), in the format of roi_bucket_kernel.
+__device__ __forceinline__ int gp_classify(const float *__restrict__ roi, float scale, int n_img, int H, int W, int &bucket,
+                                           int &cell, unsigned &geom) {
+    const int b = (int)roi[0];
+    const int sw = (int)roundf(__fmul_rn(roi[1], scale)), sh = (int)roundf(__fmul_rn(roi[2], scale));
+    const int ew = (int)roundf(__fmul_rn(roi[3], scale)), eh = (int)roundf(__fmul_rn(roi[4], scale));
+    if (b < 0 || b >= n_img) { bucket = n_img; return 2; }
+    bucket = b;
+    const long rw = max((long)ew - sw + 1, 1L), rh = max((long)eh - sh + 1, 1L);
+    if (rw > GP_MAXDIM || rh > GP_MAXDIM || sw < 0 || sh < 0) return 1;
+    const int xw = gp_extent((int)rw), xh = gp_extent((int)rh);
+    if (xw > GP_MAXDIM || xh > GP_MAXDIM || sw + xw > W || sh + xh > H) return 1;
+    cell = (b * GP_CLS + (int)rw - 1) * GP_PITCH + ((sw + sh) & 1) * GP_MAXDIM + (int)rh - 1;
+    geom = (unsigned)sw | ((unsigned)sh << 8) | ((unsigned)rh << 16) | ((unsigned)rw << 24);
+    return 0;
+}
+
+__global__ void __launch_bounds__(1024)
+roi_group_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap, int n_img, int H, int W,
+                 float scale, int G, int32_t *__restrict__ goff, int32_t *__restrict__ ioff, int32_t *__restrict__ iperm,
+                 uint2 *__restrict__ gdesc) {
+    pdl_launch_dependents();                                 // the pooling kernel may start staging its first slice
+    extern __shared__ int s_gh[];
+    __shared__ int s_wtot[33];
+    const int ncls = n_img * GP_CLS;
+    int *hist = s_gh, *n0 = hist + ncls * GP_PITCH, *n1 = n0 + ncls, *cbase = n1 + ncls, *icnt = cbase + ncls;   // icnt[n_img + 2]
+    const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < ncls * GP_PITCH + 3 * ncls + n_img + 2; i += blockDim.x) s_gh[i] = 0;
+    __syncthreads();
+    for (int r = tid; r < R; r += blockDim.x) {
+        int bucket, cell = 0;
+        unsigned geom;
+        if (gp_classify(rois + (size_t)r * 5, scale, n_img, H, W, bucket, cell, geom) == 0) atomicAdd(&hist[cell], 1);
+        else atomicAdd(&icnt[bucket], 1);
+    }
+    __syncthreads();
+    // per class: totals of the two parity sequences, counts -> exclusive offsets inside each sequence
+    int slots = 0;
+    if (tid < ncls) {
+        int *h = hist + tid * GP_PITCH;
+        int a = 0, b = 0;
+        for (int k = 0; k < GP_MAXDIM; ++k) { const int t = h[k]; h[k] = a; a += t; }
+        for (int k = 0; k < GP_MAXDIM; ++k) { const int t = h[GP_MAXDIM + k]; h[GP_MAXDIM + k] = b; b += t; }
+        n0[tid] = a;
+        n1[tid] = b;
+        slots = (a + b + G - 1) / G * G;
+    }
+    // exclusive scan of the padded class sizes (ncls <= 1024: one class per thread)
+    int incl = warp_incl_scan(slots, lane);
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int t = s_wtot[lane];
+        const int ti = warp_incl_scan(t, lane);
+        s_wtot[lane] = ti - t;
+        if (lane == 31) s_wtot[32] = ti;
+    }
+    __syncthreads();
+    const int my_base = s_wtot[warp] + incl - slots;
+    if (tid < ncls) {
+        cbase[tid] = my_base;
+        if (tid % GP_CLS == 0) goff[tid / GP_CLS] = my_base / G;
+        const unsigned pad = ((unsigned)(tid % GP_CLS + 1) << 24) | (1u << 16);      // a 1-row ROI of this width at cell (0, 0)
+        for (int k = n0[tid] + n1[tid]; k < slots; ++k) gdesc[my_base + k] = make_uint2(0xffffffffu, pad);
+    }
+    if (tid == 0) {
+        goff[n_img] = s_wtot[32] / G;
+        int run = 0;
+        for (int b = 0; b <= n_img; ++b) { const int t = icnt[b]; ioff[b] = run; icnt[b] = run; run += t; }
+        ioff[n_img + 1] = run;
+    }
+    __syncthreads();
+    for (int r = tid; r < R; r += blockDim.x) {
+        int bucket, cell = 0;
+        unsigned geom;
+        if (gp_classify(rois + (size_t)r * 5, scale, n_img, H, W, bucket, cell, geom) == 0) {
+            const int cls = cell / GP_PITCH, par = (cell - cls * GP_PITCH) / GP_MAXDIM;
+            const int i = atomicAdd(&hist[cell], 1);         // rank inside the class's parity sequence
+            const int m = min(n0[cls], n1[cls]);
+            gdesc[cbase[cls] + (i < m ? 2 * i + par : m + i)] = make_uint2((unsigned)r, geom);
+        } else {
+            iperm[atomicAdd(&icnt[bucket], 1)] = r;
+        }
     }
 }
 
@@ -838,14 +1178,27 @@ static size_t bucket_ws_bytes(int n_img, int R_cap) {
     return ((size_t)(n_img + 2) + (size_t)(R_cap > 0 ? R_cap : 0)) * sizeof(int32_t);
 }
 
+// grouped path (NHWC): [goff n_img + 1] [ioff n_img + 2] [iperm R_cap] | [gdesc (R_cap + 7 pads per width class) x 8 bytes]
+static size_t group_ints(int n_img, int R_cap) { return ((size_t)(2 * n_img + 3) + (size_t)(R_cap > 0 ? R_cap : 0) + 1) / 2 * 2; }
+static size_t group_ws_bytes(int n_img, int R_cap) {
+    if (n_img < 1 || n_img > GP_MAX_IMG) return 0;
+    return group_ints(n_img, R_cap) * sizeof(int32_t) + ((size_t)(R_cap > 0 ? R_cap : 0) + (size_t)n_img * GP_CLS * 7) * sizeof(uint2);
+}
+static size_t bucket_ws_aligned(int n_img, int R_cap) { return (bucket_ws_bytes(n_img, R_cap) + 15) / 16 * 16; }
+
 extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype, int R_cap) {
     if (layout == AZN_LAYOUT_NCHW && dtype != AZN_DTYPE_F32) return 0;
+    if (layout == AZN_LAYOUT_NHWC) return bucket_ws_aligned(n_img, R_cap) + group_ws_bytes(n_img, R_cap);
     return map_ws_bytes(n_img, C, H, W, layout, dtype) + bucket_ws_bytes(n_img, R_cap);
 }
 
 namespace {
 int g_pool_mode = 0;           // azn_roi_pool_tune: 0 automatic, 1 direct kernels only, 2 staged whenever possible
-int g_pool_variant = 2;        // keys kernel: 1 generic loop nest, 2 fixed-height column reduces (azn_roi_pool_tune(mode + 10 * variant))
+int g_pool_debug = 0;
+int g_pool_variant = 2;        // keys kernel: 1 generic loop nest, 2 fixed-height column reduces (default), 3 grouped by ROI width (1d)
+                               // when an image has enough ROIs, 4 grouped whenever the path applies (azn_roi_pool_tune(mode + 10 *
+                               // variant)).  The grouped path is kept for A/B only: measured SLOWER than variant 2 at every size
+                               // (profiles/README.md, negative results of round 2)
 
 constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the staged kernel may ask for
 
@@ -853,7 +1206,8 @@ constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the 
 // launch, or 1 when the configuration is outside the staged kernel's domain (caller takes the direct kernel).
 template <typename Ops, int MODE>
 int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float *rois, const int32_t *n_rois, int R_cap,
-                  float scale, void *out, int32_t *argmax, int32_t *bucket_ws, cudaStream_t s) {
+                  float scale, void *out, int32_t *argmax, int32_t *bucket_ws, cudaStream_t s, void *group_ws = nullptr,
+                  size_t group_bytes = 0) {
     const size_t cells = (size_t)H * (MODE == 0 ? (W | 1) : W);     // the keys kernel pads its row pitch to an odd cell count
     int sv = 0, rb = ST_RB_MAX;
     for (int cand = (MODE == 0 ? 8 : 4); cand >= 2; cand >>= 1) {
@@ -871,9 +1225,29 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     if (sv == 0) return 1;
     const int sms = azn_num_sms();
     const int nslices = (L + sv - 1) / sv;
-    const int n_buckets = n_img > 1 ? n_img + 1 : 1;
+    int n_buckets = n_img > 1 ? n_img + 1 : 1;
     int32_t *off = nullptr, *perm = nullptr;
-    if (n_img > 1) {
+    // (1d) grouped by ROI width: needs the pre-pass workspace, few images, and enough ROIs per image to fill the classes
+    int32_t *goff = nullptr;
+    uint2 *gdesc = nullptr;
+    const bool grouped = MODE == 0 && (sv == 4 || sv == 8) && g_pool_variant >= 3 && n_img <= GP_MAX_IMG && H <= 255 && W <= 255 &&
+                         group_ws && group_bytes >= group_ws_bytes(n_img, R_cap) && ((uintptr_t)group_ws % 8 == 0) &&
+                         (g_pool_variant == 4 || (long)R_cap >= 1024L * n_img);
+    if (grouped) {
+        goff = (int32_t *)group_ws;
+        off = goff + n_img + 1;
+        perm = off + n_img + 2;
+        gdesc = (uint2 *)(goff + group_ints(n_img, R_cap));
+        n_buckets = n_img + 1;
+        const size_t sm = ((size_t)n_img * GP_CLS * (GP_PITCH + 3) + n_img + 2) * sizeof(int);
+        static size_t attr_sm = 0;
+        if (sm > attr_sm) {
+            AZN_CUDA(cudaFuncSetAttribute(roi_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            attr_sm = sm;
+        }
+        roi_group_kernel<<<1, 1024, sm, s>>>(rois, n_rois, R_cap, n_img, H, W, scale, 32 / sv, goff, off, perm, gdesc);
+        AZN_LAUNCH_CHECK();
+    } else if (n_img > 1) {
         off = bucket_ws;
         perm = bucket_ws + n_img + 2;
         roi_bucket_kernel<<<1, 1024, (size_t)(n_img + 2) * sizeof(int), s>>>(rois, n_rois, R_cap, n_img, off, perm);
@@ -882,7 +1256,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     // (bucket, chunk, slice) items are dealt round-robin to one CTA per SM.  Cost model in units of one ROI-slice
     // of pooling (measured ~300 cycles): an item costs its staging (~27 units: load + key transform of the slice)
     // plus its ROIs; the launch costs rounds(items) x the item.  Pick the chunk count that minimises it.
-    const long pairs = (long)n_buckets * nslices;
+    const long pairs = (long)(grouped ? n_img : n_buckets) * nslices;   // (the grouped path's extra bucket holds bad indices only)
     const double rois_per_bucket = (double)R_cap / (double)n_img;
     long nchunk = 1;
     double best_cost = 0.0;
@@ -918,9 +1292,14 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
                                           (int)ST_SMEM_BUDGET));                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
-        roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                                 \
-            (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,         \
-            (int)nchunk, nslices, g_pool_variant);                                                                                   \
+        if (grouped)                                                                                                     \
+            AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV>, dim3(grid), dim3(ST_THREADS), smem, s,             \
+                                    (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale,          \
+                                    (uint4 *)out, n_buckets, (int)nchunk, nslices, 2 + (g_pool_debug << 8), goff, gdesc)); \
+        else                                                                                                             \
+            roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                             \
+                (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,     \
+                (int)nchunk, nslices, g_pool_variant >= 2 ? 2 : 1, nullptr, nullptr);                                    \
     } while (0)
     if (MODE == 0) {
         if (sv == 8) AZN_KEY_LAUNCH(8); else if (sv == 4) AZN_KEY_LAUNCH(4); else AZN_KEY_LAUNCH(2);
@@ -946,6 +1325,8 @@ bool want_staged(int mode, int n_img, int H, int W, int PH, int PW, const int32_
 }  // namespace
 
 extern "C" void azn_roi_pool_tune(int mode) {
+    g_pool_debug = mode / 100;
+    mode %= 100;
     g_pool_mode = mode % 10;
     if (mode >= 10) g_pool_variant = mode / 10;          // 12 / 22: staged with the generic / fixed-height pooling loop
 }
@@ -978,9 +1359,12 @@ extern "C" int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, in
         const int L = C * esize / 16;
         const bool bucket_ok = n_img <= 1 || (workspace && bucket_ws_bytes(n_img, R_cap) > 0 && workspace_bytes >= bucket_ws_bytes(n_img, R_cap));
         if (want_staged(kernel_choice, n_img, H, W, PH, PW, n_rois, R_cap, bucket_ok)) {
+            const size_t g_at = bucket_ws_aligned(n_img, R_cap);
+            void *gws = workspace && workspace_bytes > g_at ? (void *)((char *)workspace + g_at) : nullptr;
+            const size_t gbytes = gws ? workspace_bytes - g_at : 0;
             const int rc = dtype == AZN_DTYPE_F32
-                ? launch_staged<OpsF32, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s)
-                : launch_staged<OpsBF16, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s);
+                ? launch_staged<OpsF32, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s, gws, gbytes)
+                : launch_staged<OpsBF16, 0>(feat, n_img, H, W, L, rois, n_rois, R_cap, spatial_scale, out, nullptr, (int32_t *)workspace, s, gws, gbytes);
             if (rc != 1) return rc;
         }
         AZN_REQUIRE((double)R_cap * PH < 2.0e9, "azn_roi_pool_fwd: too many ROI rows for one launch");

@@ -69,11 +69,12 @@ _SCRATCH = {}
 
 
 def _scratch(device, nbytes):
-    """Grow-only per-device scratch buffer (stream-ordered reuse on torch's current stream)."""
-    t = _SCRATCH.get(device)
+    """Grow-only scratch buffer per (device, stream): reuse is ordered by the stream it belongs to."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    t = _SCRATCH.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _SCRATCH[device] = t
+        _SCRATCH[key] = t
     return t
 
 

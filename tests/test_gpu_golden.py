@@ -35,7 +35,7 @@ def _layer_feat():
     return feat
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["auto", "direct", "staged"])
+@pytest.mark.parametrize("mode", [0, 1, 22, 42], ids=["auto", "direct", "staged", "staged_grouped"])
 def test_roi_pool_equals_reference_layer_golden(dev, golden, mode):
     """azn_roi_pool_fwd == ROIPoolingLayer<float>::Forward_cpu of the reference's own source, bit for bit: values
     and argmax (NCHW f32, the layer's blob layout), NHWC f32, and bf16 (max commutes with the monotone rounding)."""
@@ -60,7 +60,7 @@ def test_roi_pool_equals_reference_layer_golden(dev, golden, mode):
             want_b = torch.from_numpy(ref).to(torch.bfloat16).float().numpy()
             assert np.array_equal(got_b.view(np.uint32), want_b.view(np.uint32)), tag
     finally:
-        _lib.lib().azn_roi_pool_tune(0)
+        _lib.lib().azn_roi_pool_tune(20)
 
 
 def test_detection_step_equals_reference_golden(dev, golden):

@@ -47,13 +47,14 @@ def _edge_rois(n_img):
 
 
 # ------------------------------------------------------------------------------- ROI pooling
-@pytest.fixture(params=[0, 1, 2], ids=["auto", "direct", "staged"])
+@pytest.fixture(params=[0, 1, 22, 42], ids=["auto", "direct", "staged", "staged_grouped"])
 def pool_mode(request):
-    """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, shared-memory-staged kernel."""
+    """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, shared-memory-staged kernel with the
+    per-ROI loop, staged kernel with the ROIs grouped by width whenever that path applies."""
     from aznet_b200 import _lib
     _lib.lib().azn_roi_pool_tune(request.param)
     yield request.param
-    _lib.lib().azn_roi_pool_tune(0)
+    _lib.lib().azn_roi_pool_tune(20)
 
 
 @pytest.mark.parametrize("hw", [(38, 63), (30, 50)])
