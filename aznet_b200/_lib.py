@@ -27,7 +27,7 @@ NMS_SEG_MAX = 1024
 LEVEL_LAST, LEVEL_ROOT_PROPS, LEVEL_TUNE = 1, 2, 4
 
 EXPORTS = [
-    "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_set_coop", "azn_hbm_write_probe", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_roi_pool_fwd_ex", "azn_nchw_f32_to_nhwc_bf16",
+    "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_set_coop", "azn_hbm_write_probe", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_roi_pool_fwd_ex", "azn_nchw_f32_to_nhwc_bf16", "azn_nchw_bf16_to_nhwc_bf16", "azn_host_f32_to_bf16", "azn_host_threads",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_az_heads_forward", "azn_az_heads_tune", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
@@ -37,7 +37,8 @@ EXPORTS = [
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")))
+    """CUDA sources (nvcc) and the host-only C++ sources (g++: no device code, x86 intrinsics)."""
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(_CSRC, "*.cpp")))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -53,11 +54,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for s in srcs:
-        o = os.path.join(build_dir, os.path.basename(s)[:-3] + ".o")
+        o = os.path.join(build_dir, os.path.splitext(os.path.basename(s))[0] + ".o")
         objs.append(o)
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("AZN_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
+        if s.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", s, "-o", o]
+        else:
+            cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("AZN_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s, p in procs:
         out, _ = p.communicate()
@@ -65,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed on %s:\n%s" % (s, out))
         if verbose and out:
             print(out)
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread", "-o", SO_PATH] + objs)
     return SO_PATH
 
 
@@ -119,6 +123,12 @@ def _bind(L):
     L.azn_roi_pool_tune.argtypes = [i32]
     L.azn_nchw_f32_to_nhwc_bf16.restype = i32
     L.azn_nchw_f32_to_nhwc_bf16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.azn_nchw_bf16_to_nhwc_bf16.restype = i32
+    L.azn_nchw_bf16_to_nhwc_bf16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.azn_host_f32_to_bf16.restype = i32
+    L.azn_host_f32_to_bf16.argtypes = [vp, vp, sz, i32]
+    L.azn_host_threads.restype = i32
+    L.azn_host_threads.argtypes = []
     L.azn_fc_workspace_bytes.restype = sz
     L.azn_fc_workspace_bytes.argtypes = [i32, i32, i32]
     L.azn_fc_tune.restype = None

@@ -1147,17 +1147,20 @@ roi_pool_nchw_bf16_kernel(const __nv_bfloat16 *__restrict__ feat, int n_img, int
 __device__ __forceinline__ void cvt_store(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 __device__ __forceinline__ void cvt_store(float *p, float v) { *p = v; }
 
-template <typename TOut>
+__device__ __forceinline__ float cvt_load(const float *p) { return *p; }
+__device__ __forceinline__ float cvt_load(const __nv_bfloat16 *p) { return __bfloat162float(*p); }   // exact; the store rounds it back
+
+template <typename TOut, typename TIn = float>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float *__restrict__ src, int C, int HW, TOut *__restrict__ dst) {
+nchw_to_nhwc_kernel(const TIn *__restrict__ src, int C, int HW, TOut *__restrict__ dst) {
     __shared__ float tile[32][33];
     const int img = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const float *s = src + (size_t)img * C * HW;
+    const TIn *s = src + (size_t)img * C * HW;
     TOut *d = dst + (size_t)img * C * HW;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         int c = c0 + j, p = p0 + threadIdx.x;
-        tile[j][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
+        tile[j][threadIdx.x] = (c < C && p < HW) ? cvt_load(s + (size_t)c * HW + p) : 0.f;
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -1482,6 +1485,15 @@ extern "C" int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int
     const int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img), block(32, 8);
     nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, HW, (__nv_bfloat16 *)dst);
+    AZN_LAUNCH_CHECK();
+    return AZN_OK;
+}
+
+extern "C" int azn_nchw_bf16_to_nhwc_bf16(const void *src, int n_img, int C, int H, int W, void *dst, azn_stream_t stream) {
+    AZN_REQUIRE(src && dst && n_img > 0 && C > 0 && H > 0 && W > 0, "azn_nchw_bf16_to_nhwc_bf16: bad argument");
+    const int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img), block(32, 8);
+    nchw_to_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, C, HW, (__nv_bfloat16 *)dst);
     AZN_LAUNCH_CHECK();
     return AZN_OK;
 }

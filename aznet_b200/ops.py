@@ -64,6 +64,27 @@ def nchw_to_nhwc_bf16(src: torch.Tensor, out: torch.Tensor | None = None):
     return out
 
 
+def nchw_bf16_to_nhwc_bf16(src: torch.Tensor, out: torch.Tensor | None = None):
+    """bf16 NCHW (a batch narrowed on the host, `host_f32_to_bf16`) -> the engine's bf16 NHWC."""
+    _need_cuda(src)
+    assert src.dtype == torch.bfloat16 and src.is_contiguous()
+    n, Cc, H, W = src.shape
+    if out is None:
+        out = torch.empty((n, H, W, Cc), dtype=torch.bfloat16, device=src.device)
+    L.check(L.lib().azn_nchw_bf16_to_nhwc_bf16(_ptr(src), n, Cc, H, W, _ptr(out), _stream()), "azn_nchw_bf16_to_nhwc_bf16")
+    return out
+
+
+def host_f32_to_bf16(src: torch.Tensor, out: torch.Tensor, threads: int = 0):
+    """HOST tensors: out (bf16, same element count, may be pinned) = round-to-nearest-even of src (f32), on `threads`
+    worker threads of the library (0: all hardware threads).  The call releases the GIL (ctypes)."""
+    assert src.device.type == "cpu" and out.device.type == "cpu", "host_f32_to_bf16 converts host arrays"
+    assert src.dtype == torch.float32 and out.dtype == torch.bfloat16 and src.is_contiguous() and out.is_contiguous()
+    assert src.numel() == out.numel()
+    L.check(L.lib().azn_host_f32_to_bf16(src.data_ptr(), out.data_ptr(), src.numel(), int(threads)), "azn_host_f32_to_bf16")
+    return out
+
+
 _WS = {}
 _SCRATCH = {}
 

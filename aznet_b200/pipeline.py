@@ -5,8 +5,17 @@ The reference uploads the map and downloads the head outputs once per level per 
 (pycaffe.py:90,95).  Here a batch crosses PCIe once in each direction, and the upload of batch i+1
 (copy stream) overlaps the search of batch i (compute stream): `submit()` returns a ticket immediately,
 `result(ticket)` blocks until that batch's proposals are on the host.
+
+PCIe bounds this call (196.6 MB of f32 maps per 64-image batch against a 0.8 ms search), and the engine stores maps
+as bf16 anyway, so the batch can be NARROWED ON THE HOST before it crosses the link (`host_narrow`): the library's
+worker threads round image chunk k to bf16 into pinned memory (`azn_host_f32_to_bf16`, the same rounding as the device
+conversion: identical bits in HBM) while the copy engine uploads chunk k-1.  Whether that wins depends on the host
+(cores per rank, memory bandwidth), so "auto" times both routes on the first batch and keeps the faster one.
 """
 from __future__ import annotations
+
+import os
+import time
 
 import torch
 
@@ -14,9 +23,22 @@ from . import ops
 from .engine import SearchEngine
 
 
+def default_host_threads():
+    """Worker threads for the host-side narrowing: this rank's share of the cores it may run on, at most 16."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(16, n // local))
+
+
 class _Slot:
-    def __init__(self, eng: SearchEngine, shape, dev, dtype=torch.float32):
+    def __init__(self, eng: SearchEngine, shape, dev, dtype=torch.float32, narrow=False):
         self.stage = torch.empty(shape, dtype=dtype, device=dev)
+        # host-narrowed route: pinned bf16 staging (the DMA source) + its device twin, both NCHW like the input
+        self.pin16 = torch.empty(shape, dtype=torch.bfloat16).pin_memory() if narrow else None
+        self.stage16 = torch.empty(shape, dtype=torch.bfloat16, device=dev) if narrow else None
         self.boxes = torch.empty(eng.out_boxes.shape, dtype=torch.float64).pin_memory()
         self.scores = torch.empty(eng.out_scores.shape, dtype=torch.float32).pin_memory()
         self.count = torch.empty(eng.out_count.shape, dtype=torch.int32).pin_memory()
@@ -31,20 +53,30 @@ class _Slot:
 
 class ProposalPipeline:
     def __init__(self, eng: SearchEngine, map_shape, depth: int = 2, after_search=None, use_graph: bool = True,
-                 layout: str = "nchw_f32"):
+                 layout: str = "nchw_f32", host_narrow: str = "off", host_threads: int = 0, narrow_chunks: int = 8):
         """map_shape = (n_img, C, H, W) of the batches; after_search: optional callable run on the compute stream right
         after the search (e.g. the NCCL gather of a multi-GPU run); use_graph: replay the layout conversion + level
         loop of every slot from a CUDA graph.
         layout "nchw_f32": host batches are f32 NCHW, what the reference's 'fc' net is handed (pycaffe blobs);
         layout "nhwc_bf16": host batches are already in the engine's own storage format, bf16 [n, H, W, C] -- half the
         PCIe bytes and no conversion kernel, for callers that keep their maps that way (e.g. downloaded from
-        aznet_b200.backbone)."""
+        aznet_b200.backbone).
+        host_narrow (layout "nchw_f32" only): "off" uploads the f32 batch as it is; "on" rounds it to bf16 on the host
+        first, `narrow_chunks` image chunks pipelined against their uploads, on `host_threads` worker threads (0: this
+        rank's share of the cores); "auto" times both on the first submitted batch and keeps the faster route
+        (`self.narrow`, `self.narrow_timing`)."""
         assert layout in ("nchw_f32", "nhwc_bf16")
+        assert host_narrow in ("off", "on", "auto")
         self.eng, self.dev, self.layout = eng, eng.dev, layout
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         n, c, h, w = map_shape
+        want_narrow = layout == "nchw_f32" and host_narrow != "off"
+        self.narrow = True if (want_narrow and host_narrow == "on") else (None if want_narrow else False)   # None: undecided
+        self.host_threads = host_threads if host_threads > 0 else default_host_threads()
+        self.narrow_chunks = max(1, min(narrow_chunks, n))
+        self.narrow_timing = None
         if layout == "nchw_f32":
-            self.slots = [_Slot(eng, map_shape, self.dev) for _ in range(depth)]
+            self.slots = [_Slot(eng, map_shape, self.dev, narrow=want_narrow) for _ in range(depth)]
             self.nhwc = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=self.dev)
         else:
             self.slots = [_Slot(eng, (n, h, w, c), self.dev, torch.bfloat16) for _ in range(depth)]
@@ -53,9 +85,50 @@ class ProposalPipeline:
         self.use_graph = use_graph
         self.launches_per_submit = 0
         self._i = 0
-        self.h2d_bytes = int(n * c * h * w * (4 if layout == "nchw_f32" else 2))
+        self._map_elems = int(n * c * h * w)
         s = self.slots[0]
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (s.boxes, s.scores, s.count, s.n_eval, s.status))
+
+    @property
+    def h2d_bytes(self):
+        """Bytes that cross PCIe per submitted batch on the route in use."""
+        return self._map_elems * (2 if (self.layout == "nhwc_bf16" or self.narrow) else 4)
+
+    def _upload_narrowed(self, slot: _Slot, host_maps: torch.Tensor):
+        """Round image chunk k to bf16 on the host while the copy engine uploads chunk k-1."""
+        n = host_maps.shape[0]
+        k = self.narrow_chunks
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.consumed)
+            for i in range(k):
+                a, b = n * i // k, n * (i + 1) // k
+                if b > a:
+                    ops.host_f32_to_bf16(host_maps[a:b], slot.pin16[a:b], self.host_threads)
+                    slot.stage16[a:b].copy_(slot.pin16[a:b], non_blocking=True)
+            slot.h2d_done.record(self.copy_stream)
+
+    def _upload_plain(self, slot: _Slot, host_maps: torch.Tensor):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.consumed)          # the previous user of this staging buffer
+            slot.stage.copy_(host_maps, non_blocking=True)
+            slot.h2d_done.record(self.copy_stream)
+
+    def _decide(self, slot: _Slot, host_maps: torch.Tensor):
+        """host_narrow="auto": host time from call to upload complete, best of three, of both routes on this batch."""
+        best = {}
+        for name, fn in (("f32_upload", self._upload_plain), ("host_bf16_then_upload", self._upload_narrowed)):
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize(self.dev)
+                t0 = time.perf_counter()
+                fn(slot, host_maps)
+                slot.h2d_done.synchronize()
+                ts.append(time.perf_counter() - t0)
+            best[name] = min(ts)
+        self.narrow = best["host_bf16_then_upload"] < best["f32_upload"]
+        self.narrow_timing = {k: round(v * 1e3, 3) for k, v in best.items()}
+        self.narrow_timing.update(unit="ms per batch", host_threads=self.host_threads, chunks=self.narrow_chunks,
+                                  chosen="host_bf16_then_upload" if self.narrow else "f32_upload")
 
     def submit(self, host_maps: torch.Tensor) -> _Slot:
         """host_maps: CPU tensor in the pipeline's layout (pinned for an asynchronous copy)."""
@@ -65,16 +138,18 @@ class ProposalPipeline:
             raise RuntimeError("pipeline slot still in flight: call result() on the oldest ticket first")
         slot.busy = True
         compute = torch.cuda.current_stream(self.dev)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(slot.consumed)          # the previous user of this staging buffer
-            slot.stage.copy_(host_maps, non_blocking=True)
-            slot.h2d_done.record(self.copy_stream)
+        if self.narrow is None:
+            self._decide(slot, host_maps)
+        if self.narrow:
+            self._upload_narrowed(slot, host_maps)
+        else:
+            self._upload_plain(slot, host_maps)
         compute.wait_event(slot.h2d_done)
         direct = self.layout == "nhwc_bf16"
         if self.use_graph:
             if slot.graph is None:
-                def pre(stage=slot.stage):
-                    ops.nchw_to_nhwc_bf16(stage, out=self.nhwc)
+                def pre(stage=slot.stage16 if self.narrow else slot.stage):
+                    (ops.nchw_bf16_to_nhwc_bf16 if self.narrow else ops.nchw_to_nhwc_bf16)(stage, out=self.nhwc)
                     self.eng.launches += 1
                 slot.graph, self.launches_per_submit = self.eng.capture(slot.stage if direct else self.nhwc, pre=None if direct else pre)
             slot.graph.replay()
@@ -82,7 +157,10 @@ class ProposalPipeline:
         elif direct:
             self.eng.propose(slot.stage)
         else:
-            ops.nchw_to_nhwc_bf16(slot.stage, out=self.nhwc)
+            if self.narrow:
+                ops.nchw_bf16_to_nhwc_bf16(slot.stage16, out=self.nhwc)
+            else:
+                ops.nchw_to_nhwc_bf16(slot.stage, out=self.nhwc)
             self.eng.launches += 1
             self.eng.propose(self.nhwc)
         slot.consumed.record(compute)

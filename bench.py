@@ -359,6 +359,8 @@ def main():
                     help="batches in flight for the device-resident figure: 2 = two engines on two CUDA streams, so that the latency-bound "
                          "kernels of one batch (ROI pool, decode / subdivide, selection) run next to the other batch's tensor-core GEMMs")
     ap.add_argument("--heads", default="mma", choices=("mma", "gemm"), help="output layers of the head: small mma.sync kernel or the persistent GEMM (A/B)")
+    ap.add_argument("--host-narrow", default="auto", choices=("auto", "on", "off"),
+                    help="e2e call: round the f32 host maps to bf16 on the host cores before the upload (auto: time both routes on the first batch)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra / e2e_entry / parity blocks (they run outside the timed regions)")
     ap.add_argument("--job", type=int, default=0, help="strong-scaling mode (BASELINE config #5): a job of this many images "
                     "(a multiple of 64) sharded over the ranks in batches of 64; --steps is ignored")
@@ -422,8 +424,12 @@ def main():
     for e, c in zip(engines, collectors):
         e.collector = c
     after = None
-    pipe = ProposalPipeline(eng, tuple(host_sets[0].shape), depth=2, after_search=after, use_graph=not args.no_graph)
-    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+    # --host-narrow auto: the pipeline times "upload the f32 batch" against "round it to bf16 on the host cores, chunk by
+    # chunk, and upload half the bytes" on the first warm-up batch and keeps the faster route (aznet_b200/pipeline.py)
+    pipe = ProposalPipeline(eng, tuple(host_sets[0].shape), depth=2, after_search=after, use_graph=not args.no_graph,
+                            host_narrow=args.host_narrow)
+    pipe_f32 = ProposalPipeline(eng, tuple(host_sets[0].shape), depth=2, use_graph=not args.no_graph) if args.host_narrow != "off" else None
+    d2h_bytes = pipe.d2h_bytes
     # the same call with the host maps already in the engine's storage format (bf16 NHWC): half the PCIe bytes
     host_sets_bf16 = [d.cpu().pin_memory() for d in dev_sets]
     pipe_bf16 = ProposalPipeline(eng, tuple(host_sets[0].shape), depth=2, use_graph=not args.no_graph, layout="nhwc_bf16")
@@ -479,6 +485,12 @@ def main():
             p, t = pending.pop(0)
             p.result(t)
 
+    def step_e2e_f32(i):
+        pending.append((pipe_f32, pipe_f32.submit(host_sets[i % n_sets])))
+        if len(pending) == 2:
+            p, t = pending.pop(0)
+            p.result(t)
+
     gathered = [None, None, None]
     gather_ms = [0.0]
 
@@ -529,6 +541,10 @@ def main():
     for i in range(max(args.warmup, 2)):
         step_e2e_bf16(i)
     drain()
+    if pipe_f32 is not None:
+        for i in range(max(args.warmup, 2)):
+            step_e2e_f32(i)
+        drain()
     if group is not None:
         group.gather()                                # warm-up of the job's one exchange (buffers, NCCL channels)
         collector.gather(views=True)
@@ -548,6 +564,13 @@ def main():
         raise RuntimeError("search capacity overflow during the bench")
     ms_e2e = timed(step_e2e, args.steps)
     ms_e2e_bf16 = timed(step_e2e_bf16, args.steps)
+    narrowed = bool(pipe.narrow)
+    if world > 1:                                     # the ranks decide for themselves; the extra timed pass must be collective
+        t = torch.tensor([1.0 if narrowed else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        narrowed = bool(t.item() > 0)
+    ms_e2e_f32 = timed(step_e2e_f32, args.steps) if (pipe_f32 is not None and narrowed) else None
+    h2d_bytes = pipe.h2d_bytes
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -576,6 +599,12 @@ def main():
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
                     "input": "f32 NCHW conv5_3 maps in pinned host memory (the blobs the reference's 'fc' net is handed)",
+                    "route": ("host cores round each image chunk to bf16 (azn_host_f32_to_bf16, %d threads) while the previous chunk uploads; "
+                              "bf16 NCHW -> NHWC on the device" % pipe.host_threads) if pipe.narrow else "f32 batch uploaded as it is; f32 NCHW -> bf16 NHWC on the device",
+                    "route_timing": pipe.narrow_timing,
+                    "f32_upload": None if ms_e2e_f32 is None else {
+                        "value": world * BATCH * args.steps / (ms_e2e_f32 / 1e3), "unit": "images/s", "h2d_bytes_per_step": pipe_f32.h2d_bytes,
+                        "ms_per_step": ms_e2e_f32 / args.steps, "note": "same call with host_narrow off: the whole f32 batch crosses PCIe"},
                     "bf16_nhwc_input": {"value": world * BATCH * args.steps / (ms_e2e_bf16 / 1e3), "unit": "images/s",
                                         "h2d_bytes_per_step": pipe_bf16.h2d_bytes, "ms_per_step": ms_e2e_bf16 / args.steps,
                                         "note": "same call, host maps already bf16 NHWC (the engine's storage format): half the PCIe bytes, no conversion kernel"}},

@@ -97,6 +97,16 @@ int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, int W, int la
 /* f32 NCHW -> bf16 NHWC feature-map conversion (layout the search engine keeps resident). */
 int azn_nchw_f32_to_nhwc_bf16(const float *src, int n_img, int C, int H, int W, void *dst,
                               azn_stream_t stream);
+/* The same from a bf16 NCHW map: what arrives when the host narrowed the batch before the upload (below). */
+int azn_nchw_bf16_to_nhwc_bf16(const void *src, int n_img, int C, int H, int W, void *dst, azn_stream_t stream);
+
+/* HOST helper (no device work): f32 -> bf16, round to nearest even, NaN -> 0x7fff -- bit for bit what the device
+ * conversion above stores -- of n elements on `threads` worker threads (<= 0: all hardware threads).  The conv5_3
+ * blobs the reference hands its 'fc' net are f32 (lib/detect/test.py:228-236, pycaffe.py:90); narrowing a batch on
+ * the host halves the bytes that cross PCIe, the link that bounds the batched host-facing call
+ * (aznet_b200/pipeline.py).  dst may be pinned memory; 32-byte aligned outputs are written with streaming stores. */
+int azn_host_f32_to_bf16(const float *src, uint16_t *dst, size_t n, int threads);
+int azn_host_threads(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fully connected layer on the tensor cores: out = act(A . W^T + bias).

@@ -249,3 +249,52 @@ def test_collector_slots_follow_the_device_counter(dev):
         assert torch.equal(col.counts[slot], want[k][2])
     gb, gs, gc = col.gather()                            # single process: the flattened collection itself
     assert gb.shape[0] == 3 * n_img and torch.equal(gc[:n_img], want[0][2])
+
+
+@pytest.mark.parametrize("host_narrow", ["off", "on", "auto"])
+def test_proposal_pipeline_routes_agree_bit_for_bit(dev, host_narrow):
+    """The batched host-facing call (f32 NCHW host maps in, proposal lists out): uploading the f32 batch, or rounding it
+    to bf16 on the host first (azn_host_f32_to_bf16 + azn_nchw_bf16_to_nhwc_bf16), puts the same bits in HBM, so every
+    route returns exactly what the engine returns on the resident bf16 map -- with and without CUDA-graph replay,
+    and again when the slots are reused."""
+    from aznet_b200 import engine, ops
+    from aznet_b200.pipeline import ProposalPipeline
+    C, H, W, n_img = 64, 375, 500, 4
+    w = synth.make_az_weights(seed=3, C=C, h6=512, h71=192, h72=64, zoom_bias=-0.3)
+    s = engine.im_scale_for(H, W)
+    fh, fw = synth.conv_shape(H, W, s)
+    head = engine.AZHeadWeights(w, dev)
+    eng = engine.SearchEngine(head, n_img, H, W, num_proposals=300, tz=0.5)
+    batches = [synth.make_conv_maps(n_img, C, fh, fw, seed=7 + k) for k in range(3)]
+    batches[1][0, 0, 0, :4] = [np.nan, -0.0, np.inf, 1e-40]
+    want = []
+    for conv in batches:
+        dev_f32 = torch.from_numpy(conv).to(dev)
+        nhwc = ops.nchw_to_nhwc_bf16(dev_f32)
+        via16 = ops.nchw_bf16_to_nhwc_bf16(dev_f32.to(torch.bfloat16))
+        assert torch.equal(nhwc.view(torch.int16), via16.view(torch.int16))
+        eng.propose(nhwc)
+        torch.cuda.synchronize()
+        want.append([t.clone() for t in (eng.out_boxes, eng.out_scores, eng.out_count, eng.n_eval)])
+    def same(got, ref, tag):
+        boxes, scores, count, n_eval = [t.cpu() for t in ref]
+        assert torch.equal(got[2], count) and torch.equal(got[3], n_eval), tag
+        for i in range(n_img):                                      # rows past an image's count are not part of the result
+            c = int(count[i])
+            assert torch.equal(got[0][i, :c], boxes[i, :c]) and torch.equal(got[1][i, :c], scores[i, :c]), tag
+
+    for use_graph in (False, True):
+        pipe = ProposalPipeline(eng, batches[0].shape, depth=2, use_graph=use_graph, host_narrow=host_narrow, host_threads=3, narrow_chunks=3)
+        hosts = [torch.from_numpy(b).pin_memory() for b in batches]
+        tickets = []
+        for k in (0, 1, 2, 1, 0):
+            tickets.append((k, pipe.submit(hosts[k])))
+            if len(tickets) == 2:
+                kk, t = tickets.pop(0)
+                same(pipe.result(t), want[kk], (host_narrow, use_graph, kk))
+        kk, t = tickets.pop(0)
+        same(pipe.result(t), want[kk], (host_narrow, use_graph, kk))
+        assert pipe.narrow == (host_narrow == "on") or host_narrow == "auto"
+        assert pipe.h2d_bytes == batches[0].size * (2 if pipe.narrow else 4)
+        if host_narrow == "auto":
+            assert pipe.narrow_timing and pipe.narrow_timing["chosen"] in ("f32_upload", "host_bf16_then_upload")

@@ -170,3 +170,33 @@ def test_hashnet_is_deterministic():
     assert np.array_equal(z1, z2) and np.array_equal(p1, p2) and np.array_equal(d1, d2)
     assert z1.shape == (50, 1) and p1.shape == (50, 11) and d1.shape == (50, 44)
     assert 0 <= p1.min() and p1.max() < 1
+
+
+def test_host_f32_to_bf16_equals_the_device_rounding():
+    """azn_host_f32_to_bf16 (the host-side narrowing of the batched proposal call) == round-to-nearest-even of every
+    element, bit for bit, for every thread count and for lengths / alignments that exercise the vector body and both
+    scalar tails; NaN -> 0x7fff like __float2bfloat16_rn.  A host function: no GPU involved."""
+    from aznet_b200 import _lib, ops
+    _lib.build()
+    assert _lib.lib().azn_host_threads() >= 1
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal(300007).astype(np.float32))
+    bits = torch.from_numpy(rng.integers(0, 2 ** 32, 4096, dtype=np.uint64).astype(np.uint32).view(np.float32).copy())   # any bit pattern
+    special = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), 1e-40, -1e-40, 3.4e38, -3.4e38, 1.00390625, 1.01171875,
+                            float("nan")], dtype=torch.float32)
+    x = torch.cat([special, bits, x])
+    want = x.to(torch.bfloat16).view(torch.int16)
+    nan = torch.isnan(x)
+    for threads in (0, 1, 3, 8):
+        for off, n in ((0, x.numel()), (1, 4099), (3, 17), (5, 15), (7, 1), (2, 0), (11, 65536 + 5)):
+            src = x[off:off + n].clone()
+            buf = torch.zeros(n + 16, dtype=torch.bfloat16)
+            dst = buf[off % 16:off % 16 + n]                       # outputs at every alignment
+            ops.host_f32_to_bf16(src, dst, threads)
+            got = dst.view(torch.int16)
+            m = ~nan[off:off + n]
+            assert torch.equal(got[m], want[off:off + n][m]), (threads, off, n)
+            assert bool(((got[~m] & 0x7fff) == 0x7fff).all()), "NaN pattern"
+            assert int(buf[off % 16 + n:].view(torch.int16).abs().sum()) == 0 and int(buf[:off % 16].view(torch.int16).abs().sum()) == 0, "wrote outside"
+    with pytest.raises(AssertionError):
+        ops.host_f32_to_bf16(x, torch.zeros(3, dtype=torch.bfloat16))
