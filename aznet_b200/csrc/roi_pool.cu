@@ -1216,6 +1216,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     for (int cand = (MODE == 0 ? 8 : 4); cand >= 2; cand >>= 1) {
         const size_t map_bytes = cells * cand * 16;
         if (map_bytes > ST_SMEM_BUDGET) continue;
+        if (MODE == 0 && g_pool_debug == 2 && cand == 8) continue;       // A/B: 64-byte slices where 128-byte ones would fit
         if (MODE != 0) {
             const size_t per = (size_t)cand * 4 * ST_BINS * 4 * (MODE == 2 ? 2 : 1);
             const size_t fit = (ST_SMEM_BUDGET - map_bytes) / per;

@@ -266,7 +266,7 @@ def test_proposal_pipeline_routes_agree_bit_for_bit(dev, host_narrow):
     head = engine.AZHeadWeights(w, dev)
     eng = engine.SearchEngine(head, n_img, H, W, num_proposals=300, tz=0.5)
     batches = [synth.make_conv_maps(n_img, C, fh, fw, seed=7 + k) for k in range(3)]
-    batches[1][0, 0, 0, :4] = [np.nan, -0.0, np.inf, 1e-40]
+    batches[1][0, 0, 0, :4] = [np.nan, -0.0, 65504.0, 1e-40]         # NaN never wins a max; no inf (inf - inf in the heads)
     want = []
     for conv in batches:
         dev_f32 = torch.from_numpy(conv).to(dev)
@@ -281,7 +281,8 @@ def test_proposal_pipeline_routes_agree_bit_for_bit(dev, host_narrow):
         assert torch.equal(got[2], count) and torch.equal(got[3], n_eval), tag
         for i in range(n_img):                                      # rows past an image's count are not part of the result
             c = int(count[i])
-            assert torch.equal(got[0][i, :c], boxes[i, :c]) and torch.equal(got[1][i, :c], scores[i, :c]), tag
+            assert torch.equal(got[0][i, :c].view(torch.int64), boxes[i, :c].view(torch.int64)), tag          # bit patterns
+            assert torch.equal(got[1][i, :c].view(torch.int32), scores[i, :c].view(torch.int32)), tag
 
     for use_graph in (False, True):
         pipe = ProposalPipeline(eng, batches[0].shape, depth=2, use_graph=use_graph, host_narrow=host_narrow, host_threads=3, narrow_chunks=3)
