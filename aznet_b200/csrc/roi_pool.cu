@@ -17,6 +17,7 @@
 //      memory with row-coalesced loads, then every thread scans its bin out of shared memory
 //      and the CTA writes its C_GROUP*PH*PW outputs as one contiguous run.
 #include <float.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -590,13 +591,38 @@ __device__ __forceinline__ void pool_group_row(const GpTables &t, unsigned arow,
 #undef AZN_MX3
 }
 
+// ---- (1e) row bands: 128-byte slices for maps whose full height does not fit shared memory at SV = 8 ------------------
+// A slice of SV = 8 vectors (64 bf16 / 32 f32 channels = one 128-byte line per cell) pools 15 % faster than SV = 4 on the
+// same map (30x50: 0.69 vs 0.60 of the HBM peak): every output piece is a full line (no reliance on L2 merging the 64-byte
+// halves written by two CTAs at different times) and the per-ROI geometry is paid half as often.  The default-cfg 38x63 map
+// needs 306 KB at SV = 8, so the map is cut into `nb` overlapping bands of `rows` rows (27 for 63 columns); a pre-pass
+// (roi_band_kernel) sends every ROI to the band that holds all of its rows -- bucket = image * nb + band -- and the ROIs
+// that fit no band (taller than a band minus the band step: ~8 % of the microbench's boxes) to a second launch of the
+// SV = 4 kernel over the whole map.  Buckets differ in size, so the pre-pass also cuts them into chunks of about equal
+// ROI counts (the chunk table) and the CTAs draw (chunk, slice) items from a device-side counter.
+// MEASURED (R = 20 000, 38x63, bf16): 0.351 ms banded vs 0.272 ms for the plain SV = 4 kernel (f32: 0.593 vs 0.519; R = 2000:
+// 0.077 vs 0.045).  The ROIs no band holds are the tall ones -- a tenth of the boxes but about half of the shared-memory
+// reads -- so the launch that keeps the 64-byte slices still carries half of the work, now behind the banded launch
+// instead of beside it, and the pre-pass + second launch cost ~30 us.  Bit-exact, kept behind azn_roi_pool_tune(322).
+constexpr int BAND_MAX = 8;                 // bands per image
+constexpr int BAND_TAB_MAX = 1024;          // chunk table entries
+constexpr int BAND_MAX_BUCKETS = 2048;      // n_img * nb (the pre-pass scans the buckets serially)
+struct BandPlan {
+    const int4 *ctab;                       // [ctrl[1]]: (bucket, first, last + 1 in perm, -); nullptr: no bands
+    int32_t *ctrl;                          // [0] item counter (zeroed by the pre-pass), [1] chunks in the table
+    int nb, rows;
+};
+__host__ __device__ __forceinline__ int band_row0(int k, int nb, int H, int rows) {
+    return nb > 1 ? (int)(((long)k * (H - rows)) / (nb - 1)) : 0;
+}
+
 template <bool BF16, int SV>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
                      const int32_t *__restrict__ bucket_off, const int32_t *__restrict__ perm,
                      float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices, int variant,
-                     const int32_t *__restrict__ goff, const uint2 *__restrict__ gdesc) {
+                     const int32_t *__restrict__ goff, const uint2 *__restrict__ gdesc, BandPlan bp) {
     // gdesc != nullptr: the grouped path (1d).  goff[b] .. goff[b + 1] = image b's groups in gdesc (G slots of
     // (ROI index or -1, start_w | start_h << 8 | roi_h << 16 | roi_w << 24) each); bucket_off / perm then list only
     // the ROIs the grouped path does not cover.  The kernel is launched as a programmatic dependent of the pre-pass.
@@ -614,18 +640,21 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
     const int j = lane % SV, bsub = lane / SV;
     const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
     const int cells = H * W;
-    const long n_items = (long)n_buckets * nchunk * nslices;
+    const bool banded = bp.ctab != nullptr;
+    const int SH = banded ? bp.rows : H;                    // map rows a CTA stages
+    __shared__ long s_item;
+    const long n_items = banded ? (long)bp.ctrl[1] * nslices : (long)n_buckets * nchunk * nslices;
     // Shared-memory row pitch in cells: ODD.  A quarter-warp of an LDS.128 serves two bin rows (2 x 4 vectors of 64
     // bytes); the two 64-byte pieces share their banks exactly when their cell indices have the same parity, and with an
     // even width the parity of cell (h, w) does not depend on h at all: every pair of distinct rows conflicts (the
     // 30x50 map).  With an odd pitch rows alternate, and the row rotation of pool_bins_fixed takes care of the rest.
     const int Wp = W | 1;
-    const int cells_p = H * Wp;
+    const int cells_p = SH * Wp;
     const int row_step = Wp * SV;
     // every CTA starts its sweep over the map at a different cell: CTAs that all walk the same cells in
     // the same order queue up on the same few L2 slices (measured: ~35 us per staging instead of ~3)
-    auto stage_slice = [&](int bucket, int c0v) {
-        const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
+    auto stage_slice = [&](int img, int row0, int c0v) {
+        const uint4 *src = feat + ((size_t)img * cells + (size_t)row0 * W) * L + c0v;
         const int n_vec = cells_p * SV;
         const int rot = (int)(((long)blockIdx.x * cells_p) / gridDim.x) * SV;
         for (int i0 = threadIdx.x; i0 < n_vec; i0 += ST_THREADS) {
@@ -642,17 +671,34 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         gp_build_tables(s_gp);
         const long item = blockIdx.x;
         const int bucket = (int)(item / ((long)nslices * nchunk));
-        if (item < n_items && bucket < n_img) { stage_slice(bucket, (int)(item % nslices) * SV); prestaged = item; }
+        if (item < n_items && bucket < n_img) { stage_slice(bucket, 0, (int)(item % nslices) * SV); prestaged = item; }
         pdl_grid_wait();
     }
-    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // the next item: dealt round-robin, or (banded: items of unequal size) drawn from the device-side counter
+    auto next_item = [&](long item) -> long {
+        if (!banded) return item + gridDim.x;
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (long)gridDim.x + atomicAdd(&bp.ctrl[0], 1);
+        __syncthreads();
+        return s_item;
+    };
+    for (long item = blockIdx.x; item < n_items; item = next_item(item)) {
         const int slice = (int)(item % nslices);
-        const int chunk = (int)((item / nslices) % nchunk);
-        const int bucket = (int)(item / ((long)nslices * nchunk));
-        const int base = bucket_off ? bucket_off[bucket] : 0;
-        const int cnt = bucket_off ? bucket_off[bucket + 1] - base : R;
-        const int lo = base + (int)((long)cnt * chunk / nchunk), hi = base + (int)((long)cnt * (chunk + 1) / nchunk);
-        const bool real = bucket < n_img;
+        int chunk, bucket, lo, hi;
+        if (banded) {
+            const int4 e = bp.ctab[item / nslices];
+            chunk = 0; bucket = e.x; lo = e.y; hi = e.z;
+        } else {
+            chunk = (int)((item / nslices) % nchunk);
+            bucket = (int)(item / ((long)nslices * nchunk));
+            const int base = bucket_off ? bucket_off[bucket] : 0;
+            const int cnt = bucket_off ? bucket_off[bucket + 1] - base : R;
+            lo = base + (int)((long)cnt * chunk / nchunk);
+            hi = base + (int)((long)cnt * (chunk + 1) / nchunk);
+        }
+        const bool real = bucket < (banded ? n_img * bp.nb : n_img);
+        const int img = banded ? bucket / bp.nb : bucket;                       // image of a real bucket
+        const int row0 = banded && real ? band_row0(bucket % bp.nb, bp.nb, H, SH) : 0;   // first map row in shared memory
         // this chunk's share of the image's groups: every nchunk-th one, so that all chunks get the same mix of sizes
         const int g_lo = gdesc && real ? goff[bucket] : 0, g_hi = gdesc && real ? goff[bucket + 1] : 0;
         const int n_grp = g_hi - g_lo > chunk ? (g_hi - g_lo - chunk + nchunk - 1) / nchunk : 0;
@@ -666,7 +712,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
 #ifdef AZN_POOL_TRACE
         const long long t0 = clock64();
 #endif
-        if (real && prestaged != item) stage_slice(bucket, c0v);
+        if (real && prestaged != item) stage_slice(img, row0, c0v);
         cp_async_wait_all();
         __syncthreads();
 #ifdef AZN_POOL_TRACE
@@ -697,7 +743,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         __syncthreads();
         const bool exact = s_negzero != 0;
         if (exact) {                                         // rare: bring the raw slice back for the exact path
-            const uint4 *src = feat + (size_t)bucket * cells * L + c0v;
+            const uint4 *src = feat + ((size_t)img * cells + (size_t)row0 * W) * L + c0v;
             for (int i = threadIdx.x; i < cells_p * SV; i += ST_THREADS) {
                 const int cell = i / SV, jj = i - cell * SV;
                 const int h = cell / Wp, w = cell - h * Wp;
@@ -713,7 +759,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         // the per-ROI path: one warp, one ROI, lanes on the bin rows
         auto pool_one = [&](const int r) {
             const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
-            const bool ok = real && q.b == bucket;
+            const bool ok = real && q.b == img;
             unsigned gb = 0;                                 // lanes 0..6: packed h bounds of bin row `lane`; 7..13: w bounds
             if (ok && lane < 2 * ST_P) {
                 int a, b;
@@ -733,7 +779,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 const int hs = hb & 0xffff, nh = phv ? (int)(hb >> 16) - hs : 0;
                 uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
                 if ((variant & 255) == 2 && !exact && mh <= 6) {     // warp-uniform: fixed-height straight-line column reduces
-                    const uint4 *rb = s_map + (size_t)min(hs, H - 1) * row_step + j;
+                    const uint4 *rb = s_map + (size_t)min(max(hs - row0, 0), SH - 1) * row_step + j;
                     // partner = the other bin row of this lane's quarter-warp (lanes 4k..4k+7 hold bin rows 2k', 2k'+1
                     // when SV == 4; with SV == 8 a quarter-warp is one bin row and there is nothing to rotate)
                     // The idle lane group of the last pass (bin row 7 of 8) mirrors bin row 6 -- same rows, same
@@ -760,7 +806,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
 #undef AZN_FIX
                     continue;
                 }
-                const uint4 *rowbase = s_map + (size_t)hs * row_step + j;
+                const uint4 *rowbase = s_map + (size_t)min(max(hs - row0, 0), SH - 1) * row_step + j;   // (a bin with rows lies inside the band)
                 // Column re-use.  Consecutive bins of a row overlap by at most one map column -- bin p+1 starts at
                 // floor((p+1) b) >= ceil((p+1) b) - 1, the last column of bin p, and clamping keeps that order; for ROIs
                 // narrower than 7 cells several bins even share all their columns -- so the maximum over the lane's bin rows
@@ -946,6 +992,79 @@ roi_bucket_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         const int b = (int)rois[(size_t)r * 5];
         perm[atomicAdd(&s_cnt[(b < 0 || b >= n_img) ? n_img : b], 1)] = r;
+    }
+}
+
+// Pre-pass of the banded path (1e).  One CTA.  Every ROI goes to set 1 -- bucket image * nb + band of the band that holds
+// all of its rows (the one whose middle is nearest when several do), bucket n_img * nb for a bad batch index -- or, when no
+// band holds it, to set 2 (bucket = image), the ROIs of the whole-map launch.  Counting sort into perm1 / perm2 (order
+// inside a bucket is irrelevant), offsets off1[n_img * nb + 2] / off2[n_img + 2], and the chunk table of set 1: every
+// non-empty bucket is cut into round(T * share) >= 1 chunks of equal ROI counts.
+__device__ __forceinline__ int band_classify(const float *__restrict__ roi, float scale, int n_img, int H, int nb, int rows, int &bucket) {
+    const RoiGeom q = roi_geom(roi, scale, ST_P, ST_P);
+    if (q.b < 0 || q.b >= n_img) { bucket = n_img * nb; return 1; }
+    int lo, hi, t;
+    bin_bounds(0, q.bin_h, q.start_h, H, lo, t);              // bins are monotone: the ROI's rows are [lo of bin 0, hi of bin 6)
+    bin_bounds(ST_P - 1, q.bin_h, q.start_h, H, t, hi);
+    if (hi <= lo) { bucket = q.b * nb; return 1; }           // no rows at all (outside the map): any band will do
+    int best = -1, best_d = 0;
+    for (int k = 0; k < nb; ++k) {
+        const int r0 = band_row0(k, nb, H, rows);
+        if (lo < r0 || hi > r0 + rows) continue;
+        const int d = abs(2 * r0 + rows - (lo + hi));
+        if (best < 0 || d < best_d) { best = k; best_d = d; }
+    }
+    if (best < 0) { bucket = q.b; return 2; }
+    bucket = q.b * nb + best;
+    return 1;
+}
+
+__global__ void __launch_bounds__(1024)
+roi_band_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap, int n_img, int H, float scale,
+                int nb, int rows, int T, int32_t *__restrict__ ctrl, int4 *__restrict__ ctab, int32_t *__restrict__ off1,
+                int32_t *__restrict__ perm1, int32_t *__restrict__ off2, int32_t *__restrict__ perm2) {
+    extern __shared__ int s_bc[];                            // [n1 + 1] set 1 | [n_img + 2] set 2: counts -> offsets -> cursors
+    const int n1 = n_img * nb + 1;                           // buckets of set 1 (the last one: bad batch index)
+    int *c1 = s_bc, *c2 = s_bc + n1 + 1;
+    const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
+    for (int i = threadIdx.x; i < n1 + 1 + n_img + 2; i += blockDim.x) s_bc[i] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        int b;
+        if (band_classify(rois + (size_t)r * 5, scale, n_img, H, nb, rows, b) == 1) atomicAdd(&c1[b], 1);
+        else atomicAdd(&c2[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int b = 0; b < n1; ++b) total += c1[b];
+        int run = 0, nch = 0;
+        for (int b = 0; b < n1; ++b) {
+            const int cnt = c1[b];
+            off1[b] = run;
+            c1[b] = run;
+            if (cnt > 0) {
+                int t = (int)(((long)T * cnt + total / 2) / total);
+                t = max(1, min(min(t, cnt), BAND_TAB_MAX - nch - (n1 - 1 - b)));      // leave an entry for every later bucket
+                for (int c = 0; c < t; ++c)
+                    ctab[nch++] = make_int4(b, run + (int)((long)cnt * c / t), run + (int)((long)cnt * (c + 1) / t), 0);
+            }
+            run += cnt;
+        }
+        off1[n1] = run;
+        ctrl[0] = 0;
+        ctrl[1] = nch;
+    }
+    if (threadIdx.x == 32) {
+        int run = 0;
+        for (int b = 0; b <= n_img; ++b) { const int cnt = c2[b]; off2[b] = run; c2[b] = run; run += cnt; }
+        off2[n_img + 1] = run;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        int b;
+        if (band_classify(rois + (size_t)r * 5, scale, n_img, H, nb, rows, b) == 1) perm1[atomicAdd(&c1[b], 1)] = r;
+        else perm2[atomicAdd(&c2[b], 1)] = r;
     }
 }
 
@@ -1188,10 +1307,16 @@ static size_t group_ws_bytes(int n_img, int R_cap) {
     return group_ints(n_img, R_cap) * sizeof(int32_t) + ((size_t)(R_cap > 0 ? R_cap : 0) + (size_t)n_img * GP_CLS * 7) * sizeof(uint2);
 }
 static size_t bucket_ws_aligned(int n_img, int R_cap) { return (bucket_ws_bytes(n_img, R_cap) + 15) / 16 * 16; }
+// banded path (NHWC), at the same place as the grouped path's (the two exclude each other):
+// [ctab BAND_TAB_MAX x int4] [ctrl 4] [off1 n_img * BAND_MAX + 2] [off2 n_img + 2] [perm1 R_cap] [perm2 R_cap]
+static size_t band_ws_bytes(int n_img, int R_cap) {
+    if (n_img < 1 || (long)n_img * BAND_MAX > BAND_MAX_BUCKETS) return 0;
+    return (size_t)BAND_TAB_MAX * sizeof(int4) + ((size_t)4 + (size_t)n_img * BAND_MAX + 2 + n_img + 2 + 2 * (size_t)(R_cap > 0 ? R_cap : 0)) * sizeof(int32_t);
+}
 
 extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype, int R_cap) {
     if (layout == AZN_LAYOUT_NCHW && dtype != AZN_DTYPE_F32) return 0;
-    if (layout == AZN_LAYOUT_NHWC) return bucket_ws_aligned(n_img, R_cap) + group_ws_bytes(n_img, R_cap);
+    if (layout == AZN_LAYOUT_NHWC) return bucket_ws_aligned(n_img, R_cap) + std::max(group_ws_bytes(n_img, R_cap), band_ws_bytes(n_img, R_cap));
     return map_ws_bytes(n_img, C, H, W, layout, dtype) + bucket_ws_bytes(n_img, R_cap);
 }
 
@@ -1228,6 +1353,74 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     }
     if (sv == 0) return 1;
     const int sms = azn_num_sms();
+    // (1e) row bands: the map does not fit at SV = 8, a band of >= 12 rows does, and the workspace for the pre-pass is there
+    if (MODE == 0 && sv < 8 && L >= 8 && g_pool_variant == 2 && g_pool_debug == 3 && H <= 65535) {      // opt-in: measured slower (below)
+        const int rows = (int)(ST_SMEM_BUDGET / ((size_t)(W | 1) * 8 * 16));
+        int nb = rows >= 12 && rows < H ? 1 + (H - rows + std::max(1, rows / 4) - 1) / std::max(1, rows / 4) : 0;
+        if (nb > BAND_MAX) nb = 0;                           // a map this tall against a band this short: most ROIs would fit no band
+        const size_t need = band_ws_bytes(n_img, R_cap);
+        if (nb >= 2 && (long)n_img * nb <= BAND_MAX_BUCKETS && (long)n_img * nb + 1 < BAND_TAB_MAX / 2 && group_ws && need > 0 &&
+            group_bytes >= need && ((uintptr_t)group_ws % 16 == 0)) {
+            int4 *ctab = (int4 *)group_ws;
+            int32_t *ctrl = (int32_t *)(ctab + BAND_TAB_MAX);
+            int32_t *off1 = ctrl + 4, *off2 = off1 + (size_t)n_img * BAND_MAX + 2;
+            int32_t *perm1 = off2 + n_img + 2, *perm2 = perm1 + (R_cap > 0 ? R_cap : 0);
+            const int ns8 = (L + 7) / 8;
+            // chunks of the banded launch: the cost model below with all buckets together (the pre-pass shares them out)
+            long T = 1;
+            double best_cost = 0.0;
+            for (int rounds = 1; rounds <= 4; ++rounds) {
+                long c = (long)rounds * sms / ns8;
+                if (c < 1) c = 1;
+                const long it = c * ns8;
+                const double cost = (double)((it + sms - 1) / sms) * (27.0 + (double)R_cap / (double)c);
+                if (rounds == 1 || cost < best_cost * 0.97) { best_cost = cost; T = c; }
+            }
+            T = std::min<long>(T, BAND_TAB_MAX - ((long)n_img * nb + 1));
+            const size_t psm = ((size_t)n_img * nb + 2 + n_img + 2) * sizeof(int);
+            AZN_REQUIRE(psm <= 40 * 1024, "azn_roi_pool_fwd: too many images for the banded pre-pass");
+            roi_band_kernel<<<1, 1024, psm, s>>>(rois, n_rois, R_cap, n_img, H, scale, nb, rows, (int)T, ctrl, ctab, off1, perm1, off2, perm2);
+            AZN_LAUNCH_CHECK();
+            constexpr bool kBf16 = sizeof(typename Ops::tag) == 2;
+            static bool attr8 = false;
+            if (!attr8) {
+                AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BUDGET));
+                attr8 = true;
+            }
+            BandPlan bp;
+            bp.ctab = ctab; bp.ctrl = ctrl; bp.nb = nb; bp.rows = rows;
+            const size_t smem8 = (size_t)rows * (W | 1) * 8 * 16;
+            roi_pool_keys_kernel<kBf16, 8><<<sms, ST_THREADS, smem8, s>>>((const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off1, perm1,
+                                                                          scale, (uint4 *)out, n_img * nb + 1, 1, ns8, 2, nullptr, nullptr, bp);
+            AZN_LAUNCH_CHECK();
+            // the ROIs no band holds: the whole map at the slice width that fits, buckets = images (set 2 of the pre-pass);
+            // their number is only known on the device -- chunks sized for an eighth of the ROIs
+            const int nsl = (L + sv - 1) / sv;
+            const long pairs2 = (long)n_img * nsl;
+            long c2 = std::max<long>(1, std::min<long>(sms / pairs2, (long)(R_cap / 8 / n_img / 64)));
+            const long items2 = (long)(n_img + 1) * c2 * nsl;
+            const unsigned grid2 = (unsigned)std::min<long>(items2, sms);
+            const size_t smem2 = cells * sv * 16;
+            BandPlan none;
+            none.ctab = nullptr; none.ctrl = nullptr; none.nb = 1; none.rows = H;
+#define AZN_REST_LAUNCH(SVV)                                                                                             \
+    do {                                                                                                                 \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)ST_SMEM_BUDGET));                                                         \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        roi_pool_keys_kernel<kBf16, SVV><<<grid2, ST_THREADS, smem2, s>>>(                                               \
+            (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off2, perm2, scale, (uint4 *)out, n_img + 1,       \
+            (int)c2, nsl, 2, nullptr, nullptr, none);                                                                    \
+    } while (0)
+            if (sv == 4) AZN_REST_LAUNCH(4); else AZN_REST_LAUNCH(2);
+#undef AZN_REST_LAUNCH
+            AZN_LAUNCH_CHECK();
+            return AZN_OK;
+        }
+    }
     const int nslices = (L + sv - 1) / sv;
     int n_buckets = n_img > 1 ? n_img + 1 : 1;
     int32_t *off = nullptr, *perm = nullptr;
@@ -1273,6 +1466,8 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     }
     const long items = (long)n_buckets * nchunk * nslices;
     const unsigned grid = (unsigned)(items < sms ? items : sms);
+    BandPlan no_bands;
+    no_bands.ctab = nullptr; no_bands.ctrl = nullptr; no_bands.nb = 1; no_bands.rows = H;
     size_t smem = cells * sv * 16;
     if (MODE != 0) smem += (size_t)rb * sv * 4 * ST_BINS * 4 * (MODE == 2 ? 2 : 1);
 #define AZN_ST_LAUNCH(SVV)                                                                                               \
@@ -1299,11 +1494,12 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         if (grouped)                                                                                                     \
             AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV>, dim3(grid), dim3(ST_THREADS), smem, s,             \
                                     (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale,          \
-                                    (uint4 *)out, n_buckets, (int)nchunk, nslices, 2 + (g_pool_debug << 8), goff, gdesc)); \
+                                    (uint4 *)out, n_buckets, (int)nchunk, nslices, 2 + (g_pool_debug << 8), goff, gdesc, \
+                                    no_bands));                                                                          \
         else                                                                                                             \
             roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                             \
                 (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,     \
-                (int)nchunk, nslices, g_pool_variant >= 2 ? 2 : 1, nullptr, nullptr);                                    \
+                (int)nchunk, nslices, g_pool_variant >= 2 ? 2 : 1, nullptr, nullptr, no_bands);                          \
     } while (0)
     if (MODE == 0) {
         if (sv == 8) AZN_KEY_LAUNCH(8); else if (sv == 4) AZN_KEY_LAUNCH(4); else AZN_KEY_LAUNCH(2);

@@ -81,7 +81,9 @@ int azn_hbm_write_probe(void *dst, size_t bytes, azn_stream_t stream);
 size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype, int R_cap);
 /* Benchmark hook: 0 automatic kernel choice, 1 direct kernels only, 2 staged kernel whenever it applies; + 10 x the
  * staged kernel's pooling loop (1 generic loop nest, 2 fixed-height column reduces = default, 3 / 4 ROIs grouped by width:
- * kept for A/B, measured slower); + 100: the grouped loop with its stores disabled (profiling only). */
+ * kept for A/B, measured slower); + 100: the grouped loop with its stores disabled (profiling only); + 200: 64-byte
+ * slices even where 128-byte ones fit; + 300: row bands of 128-byte slices for maps too tall for shared memory (A/B,
+ * measured slower). */
 void azn_roi_pool_tune(int mode);
 int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                      const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,

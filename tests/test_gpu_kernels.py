@@ -47,10 +47,11 @@ def _edge_rois(n_img):
 
 
 # ------------------------------------------------------------------------------- ROI pooling
-@pytest.fixture(params=[0, 1, 22, 42], ids=["auto", "direct", "staged", "staged_grouped"])
+@pytest.fixture(params=[0, 1, 22, 322, 42], ids=["auto", "direct", "staged", "staged_bands", "staged_grouped"])
 def pool_mode(request):
     """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, shared-memory-staged kernel with the
-    per-ROI loop, staged kernel with the ROIs grouped by width whenever that path applies."""
+    per-ROI loop, the same with row bands of 128-byte slices when the whole map does not fit (the 38x63 maps below: an
+    A/B variant), staged kernel with the ROIs grouped by width whenever that path applies."""
     from aznet_b200 import _lib
     _lib.lib().azn_roi_pool_tune(request.param)
     yield request.param
@@ -117,6 +118,60 @@ def test_roi_pool_device_count_bad_index_and_empty(dev, O, pool_mode):
     assert z.shape[0] == 0
     with pytest.raises(ValueError):
         ops.roi_pool(torch.zeros((1, 4, 4, 3), device=dev), r, layout="NHWC")     # C*4 % 16 != 0
+
+
+@pytest.mark.parametrize("n_img,C,hw", [(1, 512, (38, 63)), (3, 64, (38, 63)), (2, 64, (75, 40)), (64, 64, (38, 63))])
+def test_roi_pool_row_bands_equal_the_direct_kernel(dev, O, n_img, C, hw):
+    """The banded staged path (azn_roi_pool_tune(322); a pre-pass sorts the ROIs by the row band that holds them, 128-byte slices per band, a second
+    launch for the ROIs no band holds) against the direct kernel -- itself pinned to the oracle above -- on thousands of
+    ROIs: every band, ROIs taller than a band, outside the map, bad batch indices, a device-side count, a map with -0 and
+    NaN (the exact compare-select fallback), f32 and bf16; a sample against the oracle as well."""
+    from aznet_b200 import _lib, ops
+    H, W = hw
+    R = 6000 if n_img < 64 else 64 * 80
+    feat = synth.make_conv_maps(n_img, C, H, W, seed=31)
+    rois = synth.make_rois(R, H * 16, W * 16, seed=17, n_img=n_img)
+    rois[::211, 0] = n_img + 2                                    # bad batch index -> zero row
+    rois[7:12, 1:] += 5000                                        # outside the map
+    rois[12] = [0, 0, 0, W * 16 - 1, H * 16 - 1]                  # the whole map: taller than any band
+    rois[13] = [0, 40, 0, 90, H * 16 - 1]                         # a full-height sliver
+    f = torch.from_numpy(feat).to(dev).permute(0, 2, 3, 1).contiguous()
+    r = torch.from_numpy(rois).to(dev)
+    lib = _lib.lib()
+    try:
+        for variant in ("relu", "signed"):
+            if variant == "signed":
+                g = feat.copy()
+                g[g < 0.4] = 0.0
+                rs = np.random.RandomState(5)
+                g[rs.rand(*g.shape) < 0.2] *= -1.0                # -0.0 and negative values
+                g[rs.rand(*g.shape) < 0.01] = np.nan
+                f = torch.from_numpy(g).to(dev).permute(0, 2, 3, 1).contiguous()
+            for dt in (torch.float32, torch.bfloat16):
+                fm = f.to(dt)
+                lib.azn_roi_pool_tune(1)
+                want = ops.roi_pool(fm, r, layout="NHWC")
+                lib.azn_roi_pool_tune(322)
+                got = ops.roi_pool(fm, r, layout="NHWC")
+                iv = torch.int32 if dt == torch.float32 else torch.int16
+                assert torch.equal(got.view(iv), want.view(iv)), (variant, dt)
+                # a device-side count (the staged kernel asked for explicitly): rows past it stay untouched
+                out = torch.full_like(want, -1.0)
+                live = R // 3
+                ops.roi_pool(fm, r, layout="NHWC", n_rois=torch.tensor([live], dtype=torch.int32, device=dev), out=out, staged=True)
+                assert torch.equal(out[:live].view(iv), want[:live].view(iv)) and bool((out[live:] == -1.0).all())
+        # and the oracle on a sample (f32, the ReLU-like map)
+        idx = np.r_[0:40, R - 40:R]
+        ok = rois[idx].copy()
+        bad = (ok[:, 0] < 0) | (ok[:, 0] >= n_img)
+        ok[bad, 0] = 0
+        ref = O.roi_pool_fwd(feat, ok).transpose(0, 2, 3, 1).copy()
+        ref[bad] = 0
+        lib.azn_roi_pool_tune(322)
+        got = ops.roi_pool(torch.from_numpy(feat).to(dev).permute(0, 2, 3, 1).contiguous(), r, layout="NHWC")
+        assert np.array_equal(got[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    finally:
+        lib.azn_roi_pool_tune(20)
 
 
 def test_roi_pool_signed_zero_nan_and_many_images(dev, O, pool_mode):
