@@ -155,6 +155,131 @@ nms_scatter_kernel(const float *__restrict__ dets, int n, const int *__restrict_
     order[r] = i;
 }
 
+// ---- bucket sort for large n ------------------------------------------------------------------------------------
+// The rank kernel above compares every pair: n^2 = 4e8 key compares at n = 20 000, 60-70 us -- a fifth of the whole call.
+// For n >= BKT_MIN_N the order is found in two steps instead.  nms_bucket_kernel (one CTA) spreads the keys over BKT
+// buckets that are linear in the uint key between the smallest and the largest key present, highest keys first
+// (shared-memory histogram, scan, scatter of (key, index) pairs in bucket order); nms_bucket_rank_kernel then ranks every
+// detection inside its own bucket only -- a few dozen compares with the same rule as above (key desc, index desc) -- and
+// moves its box to sorted position.  The result is the exact order of the rank kernel; the cost depends on the score
+// distribution only through the largest bucket (all scores equal: one bucket, the n^2 loop again).
+constexpr int BKT = 2048;
+constexpr int BKT_THREADS = 1024;
+constexpr int BKT_MIN_N = 4096;
+
+// ITEMS > 0: n <= ITEMS * BKT_THREADS and every thread keeps its keys in registers -- the scores are read from global
+// memory once (strided 20-byte records: the one pass costs ~5 us on one SM) instead of once per phase; ITEMS == 0: any n.
+template <int ITEMS>
+__global__ void __launch_bounds__(BKT_THREADS)
+nms_bucket_kernel(const float *__restrict__ dets, int n, uint2 *__restrict__ bpair, int *__restrict__ boff, int staged) {
+    // staged: dynamic shared memory holds n (key, index) pairs -- the scatter into bucket order goes there and leaves the
+    // SM as one coalesced copy (40 000 scattered 4-byte stores from a single SM cost ~20 us, more than everything else)
+    extern __shared__ uint2 s_stage[];
+    __shared__ int s_hist[BKT];                               // counts -> exclusive offsets -> cursors
+    __shared__ unsigned s_min[BKT_THREADS / 32], s_max[BKT_THREADS / 32];
+    __shared__ int s_wsum[BKT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+    unsigned key[ITEMS > 0 ? ITEMS : 1];
+    if (ITEMS > 0) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int i = tid + j * BKT_THREADS;
+            key[j] = i < n ? rank_key(dets[(size_t)i * 5 + 4]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+            if (tid + j * BKT_THREADS < n) { kmin = min(kmin, key[j]); kmax = max(kmax, key[j]); }
+    } else {
+        for (int i = tid; i < n; i += BKT_THREADS) {
+            const unsigned k = rank_key(dets[(size_t)i * 5 + 4]);
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
+        }
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) { s_min[warp] = kmin; s_max[warp] = kmax; }
+    for (int b = tid; b < BKT; b += BKT_THREADS) s_hist[b] = 0;
+    __syncthreads();
+    kmin = s_min[lane];                                       // 32 warps: one partial per lane
+    kmax = s_max[lane];
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    int shift = 0;
+    while (((kmax - kmin) >> shift) >= (unsigned)BKT) ++shift;           // <= 21 steps: (kmax - kmin) >> shift < BKT
+    if (ITEMS > 0) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+            if (tid + j * BKT_THREADS < n) atomicAdd(&s_hist[(kmax - key[j]) >> shift], 1);
+    } else {
+        for (int i = tid; i < n; i += BKT_THREADS) atomicAdd(&s_hist[(kmax - rank_key(dets[(size_t)i * 5 + 4])) >> shift], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the BKT counts: two consecutive buckets per thread
+    const int c0 = s_hist[2 * tid], c1 = s_hist[2 * tid + 1];
+    const int incl = warp_incl_scan(c0 + c1, lane);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int t = s_wsum[lane];
+        const int ti = warp_incl_scan(t, lane);
+        s_wsum[lane] = ti - t;
+    }
+    __syncthreads();
+    const int base = s_wsum[warp] + incl - (c0 + c1);
+    s_hist[2 * tid] = base;
+    s_hist[2 * tid + 1] = base + c0;
+    boff[2 * tid] = base;
+    boff[2 * tid + 1] = base + c0;
+    if (tid == 0) { boff[BKT] = n; boff[BKT + 1] = shift; boff[BKT + 2] = (int)kmax; }
+    __syncthreads();
+    uint2 *dst = staged ? s_stage : bpair;
+    if (ITEMS > 0) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int i = tid + j * BKT_THREADS;
+            if (i < n) dst[atomicAdd(&s_hist[(kmax - key[j]) >> shift], 1)] = make_uint2(key[j], (unsigned)i);
+        }
+    } else {
+        for (int i = tid; i < n; i += BKT_THREADS) {
+            const unsigned k = rank_key(dets[(size_t)i * 5 + 4]);
+            dst[atomicAdd(&s_hist[(kmax - k) >> shift], 1)] = make_uint2(k, (unsigned)i);
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (int e = tid; e < n; e += BKT_THREADS) bpair[e] = s_stage[e];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nms_bucket_rank_kernel(const float *__restrict__ dets, int n, const uint2 *__restrict__ bpair, const int *__restrict__ boff,
+                       float4 *__restrict__ boxes, float *__restrict__ areas, int *__restrict__ order) {
+    pdl_enter();
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    const uint2 me = bpair[e];
+    const unsigned k = me.x;
+    const int i = (int)me.y;
+    const int shift = boff[BKT + 1];
+    const unsigned kmax = (unsigned)boff[BKT + 2];
+    const int b = (int)((kmax - k) >> shift);
+    const int lo = boff[b], hi = boff[b + 1];
+    int cnt = 0;
+#pragma unroll 4
+    for (int q = lo; q < hi; ++q) {                            // neighbouring threads share their bucket: broadcast loads
+        const uint2 p = bpair[q];
+        cnt += (int)(p.x > k) | ((int)(p.x == k) & (int)((int)p.y > i));
+    }
+    const int r = lo + cnt;
+    const float *d = dets + (size_t)i * 5;
+    const float4 bx = make_float4(d[0], d[1], d[2], d[3]);
+    boxes[r] = bx;
+    areas[r] = box_area(bx.x, bx.y, bx.z, bx.w);
+    order[r] = i;
+}
+
 // Is the clamped intersection of a and b non-empty, i.e. w > 0 and h > 0 with the reference's float32 operations
 // w = (min(a.x2, b.x2) - max(a.x1, b.x1)) + 1 ?  Two exact simplifications:
 //   (1) fl(fl(d) + 1) > 0  <=>  fl(d) > -1: floats just above -1 are spaced 2^-24, so fl(d) + 1 is then an exactly
@@ -655,6 +780,7 @@ NmsStreams *nms_streams(int n_events) {
 
 // Diagnostic hook (like azn_fc_tune): 0 = default schedule; 1 = everything on the caller's stream, mask then chain;
 // 2 = stop after the mask; 3 = stop after the sort (rank + scatter).  Modes 2 / 3 leave keep_count untouched.
+// + 8: the all-pairs rank sort for every n (A/B of the bucket sort that large n take by default).
 static int g_nms_mode = 0;
 extern "C" void azn_nms_tune(int mode) { g_nms_mode = mode; }
 
@@ -683,12 +809,38 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
     const int col_tiles = (int)((n + 63) / 64);
     NmsWorkspace w = carve(workspace, n, col_tiles);
     AZN_CUDA(cudaMemsetAsync(w.rank, 0, (size_t)((char *)w.diag_t - (char *)w.rank), s));   // rank, removed, kept_bits, nkept
-    nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
-                      RANK_THREADS, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
-    AZN_LAUNCH_CHECK();
-    if (n > RANK_TILE) {
-        nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
+    if (n >= BKT_MIN_N && !(g_nms_mode & 8)) {
+        // (key, index) pairs in bucket order and the bucket offsets: at the head of the mask
+        // area (64 x 64 tiles x 512 B >= 2 MB at this n; the mask kernel, which runs after the sort, overwrites them)
+        uint2 *bpair = (uint2 *)w.mask;
+        int *boff = (int *)(bpair + n);
+        const size_t stage = (size_t)n * sizeof(uint2);
+        const int staged = stage <= 200 * 1024 ? 1 : 0;
+#define AZN_BKT_LAUNCH(IT)                                                                                                          \
+    do {                                                                                                                            \
+        static bool attr_set = false;                                                                                               \
+        if (!attr_set) {                                                                                                            \
+            AZN_CUDA(cudaFuncSetAttribute(nms_bucket_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));         \
+            attr_set = true;                                                                                                        \
+        }                                                                                                                           \
+        nms_bucket_kernel<IT><<<1, BKT_THREADS, staged ? stage : 0, s>>>(dets, (int)n, bpair, boff, staged);                        \
+    } while (0)
+        if (n <= 8 * BKT_THREADS) AZN_BKT_LAUNCH(8);
+        else if (n <= 20 * BKT_THREADS) AZN_BKT_LAUNCH(20);
+        else if (n <= 32 * BKT_THREADS) AZN_BKT_LAUNCH(32);
+        else AZN_BKT_LAUNCH(0);
+#undef AZN_BKT_LAUNCH
         AZN_LAUNCH_CHECK();
+        AZN_CUDA(azn_launch_pdl(nms_bucket_rank_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dets, (int)n, (const uint2 *)bpair,
+                                (const int *)boff, w.boxes, w.areas, w.order));
+    } else {
+        nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
+                          RANK_THREADS, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
+        AZN_LAUNCH_CHECK();
+        if (n > RANK_TILE) {
+            nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
+            AZN_LAUNCH_CHECK();
+        }
     }
     {
         const size_t smem = (size_t)SUPER * SUPER * 64 * sizeof(u64);      // 128 KB diagonal super-block
@@ -707,8 +859,8 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         // would serialise the fork anyway and the lazily created stream / events must not be born inside a capture.
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         AZN_CUDA(cudaStreamIsCapturing(s, &cap));
-        if (g_nms_mode == 3) return AZN_OK;
-        const bool two_streams = cap == cudaStreamCaptureStatusNone && n_super > 1 && g_nms_mode == 0;
+        if ((g_nms_mode & 7) == 3) return AZN_OK;
+        const bool two_streams = cap == cudaStreamCaptureStatusNone && n_super > 1 && (g_nms_mode & 7) == 0;
         NmsStreams *ns = two_streams ? nms_streams(0) : nullptr;
         AZN_REQUIRE(!two_streams || ns != nullptr, "azn_nms: could not create the internal stream / events");
         cudaStream_t chain = two_streams ? ns->chain : s;
@@ -738,7 +890,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
                                                                                                  w.diag_t, w.row_done);
         AZN_LAUNCH_CHECK();
-        for (int si = 0; si < n_super && g_nms_mode != 2; ++si) {
+        for (int si = 0; si < n_super && (g_nms_mode & 7) != 2; ++si) {
             // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1
             const int upd_cols = min(SUPER, col_tiles - (si + 1) * SUPER);
             long updaters = (si == 0 || upd_cols <= 0) ? 0 : ((long)si * SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp

@@ -223,7 +223,7 @@ def test_nms_golden_and_oracle(dev, O, golden):
     assert int(cnt.item()) == 0
 
 
-@pytest.mark.parametrize("n,th", [(8000, 0.3), (8000, 0.7), (20000, 0.3)])
+@pytest.mark.parametrize("n,th", [(8000, 0.3), (8000, 0.7), (20000, 0.3), (20000, 0.7), (4096, 0.5), (21000, 0.5), (33000, 0.6)])
 def test_nms_large_matches_oracle(dev, O, n, th):
     from aznet_b200 import ops
     d = synth.make_dets(n, seed=3)
@@ -241,6 +241,41 @@ def test_nms_ties_and_idempotence(dev, O):
     kept = np.ascontiguousarray(d[k1])
     keep2, cnt2 = ops.nms(torch.from_numpy(kept).to(dev), 0.5)     # survivors never suppress each other
     assert int(cnt2.item()) == len(k1)
+
+
+@pytest.mark.parametrize("dist", ["ties", "all_equal", "saturated", "negative_and_zero", "wide_range"])
+def test_nms_bucket_sort_orders_like_the_rank_sort(dev, O, dist):
+    """n >= 4096 sorts by score buckets (nms_bucket_kernel + nms_bucket_rank_kernel) instead of the all-pairs rank: the keep
+    list equals the oracle's and the all-pairs sort's (azn_nms_tune(8)) on score distributions that stress the bucketing --
+    thousands of exact ties, one single score, scores saturated at 1.0, negative scores with -0 / +0, twenty decades."""
+    from aznet_b200 import _lib, ops
+    n = 6000
+    d = synth.make_dets(n, seed=13)
+    rng = np.random.default_rng(3)
+    if dist == "ties":
+        d[:, 4] = np.round(d[:, 4] * 40) / 40
+    elif dist == "all_equal":
+        d[:, 4] = 0.5
+    elif dist == "saturated":
+        d[:, 4] = np.where(rng.random(n) < 0.6, 1.0, d[:, 4]).astype(np.float32)
+    elif dist == "negative_and_zero":
+        d[:, 4] = (d[:, 4] - 0.5).astype(np.float32)
+        d[::7, 4] = 0.0
+        d[3::7, 4] = -0.0
+    else:
+        d[:, 4] = np.exp(rng.uniform(-40, 5, n)).astype(np.float32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    dt = torch.from_numpy(d).to(dev)
+    ref = O.nms(d, 0.5)
+    keep, cnt = ops.nms(dt, 0.5)
+    assert keep[:int(cnt.item())].cpu().tolist() == ref, dist
+    lib = _lib.lib()
+    lib.azn_nms_tune(8)
+    try:
+        keep2, cnt2 = ops.nms(dt, 0.5)
+        assert keep2[:int(cnt2.item())].cpu().tolist() == ref, dist
+    finally:
+        lib.azn_nms_tune(0)
 
 
 def test_nms_inside_cuda_graph_and_on_side_stream(dev, O):

@@ -82,7 +82,7 @@ def main():
                     "boxes_per_s": N / (best * 1e-3), "mask_bytes": 16 * N * ((N + 63) // 64) + 28 * N}
             if args.nms_phases:
                 ph = {}
-                for mode, name in ((3, "sort_ms"), (2, "sort_mask_ms"), (1, "sequential_ms")):
+                for mode, name in ((3, "sort_ms"), (8 + 3, "sort_allpairs_ms"), (2, "sort_mask_ms"), (1, "sequential_ms"), (8, "total_allpairs_sort_ms")):
                     _lib.lib().azn_nms_tune(mode)
                     ph[name] = round(timeit(run, flush)[0], 4)
                 _lib.lib().azn_nms_tune(0)
