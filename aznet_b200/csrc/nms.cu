@@ -305,6 +305,9 @@ __device__ __forceinline__ bool pair_intersects(const float4 &a, const float4 &b
 // so those pairs can never be suppressed.  (A lanes-own-columns / ballot variant was measured 1.5x slower: it
 // runs the division path for every row, because some lane of 32 random columns always intersects.)
 constexpr int MASK_THREADS = 64;
+constexpr int SCAN_THREADS = 1024;
+constexpr int SUPER = 16;                      // column tiles per super-tile
+constexpr int SUPER_UPDATERS = 48;             // CTAs of a launch that push the previous super-tile's kept rows
 
 // id_base: the launch covers the blocks [id_base, id_base + gridDim.x) of the row-major triangle -- azn_nms launches
 // the mask one super-row (16 row tiles = 1024 boxes) at a time so that the greedy pass of super-tile s can start as soon
@@ -313,7 +316,8 @@ constexpr int MASK_THREADS = 64;
 // resolves a tile from these columns (which kept rows suppress me?) in a few ballot rounds.
 __global__ void __launch_bounds__(MASK_THREADS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
-                u64 *__restrict__ mask, int col_tiles, long id_base, u64 *__restrict__ diag_t, int *__restrict__ row_done) {
+                u64 *__restrict__ mask, int col_tiles, long id_base, u64 *__restrict__ diag_t, int *__restrict__ row_done,
+                u64 *__restrict__ sup_t) {
     // block id -> (rt, ct), rt <= ct, COLUMN-major over the triangle (column ct starts at id0(ct) = ct (ct + 1) / 2): the
     // cheap columns come first, so the greedy pass -- which consumes the mask column by column -- starts at once and
     // is nearly done when the last, most expensive column super-block lands
@@ -394,13 +398,16 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
         }
     }
     *dst = bits;
-    if (rt == ct) {                                                          // block-uniform
+    if (rt / SUPER == ct / SUPER) {                                          // block-uniform: a tile of a diagonal super-block
+        // its transpose, for the greedy pass: sup_t[ct][rt % 16][j] bit i <=> row i of tile rt suppresses row j of tile ct
+        // (the block-wise pass keeps, per row, the 16 words that say which rows of its super-tile suppress it)
         s_d[threadIdx.x] = bits;
         __syncthreads();
         u64 col = 0;
 #pragma unroll 8
         for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> threadIdx.x) & 1ull) << i;
-        diag_t[(size_t)rt * 64 + threadIdx.x] = col;
+        if (rt == ct) diag_t[(size_t)rt * 64 + threadIdx.x] = col;
+        sup_t[((size_t)ct * SUPER + rt % SUPER) * 64 + threadIdx.x] = col;
     }
     // publish: one more tile of super-column ct / 16 is in memory (the greedy pass polls these counters)
     __syncthreads();
@@ -410,9 +417,6 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
     }
 }
 
-constexpr int SCAN_THREADS = 1024;
-constexpr int SUPER = 16;                      // column tiles per super-tile
-constexpr int SUPER_UPDATERS = 48;             // CTAs of a launch that push the previous super-tile's kept rows
 
 __device__ __forceinline__ u64 warp_or(u64 v) {
     // redux.sync.or.b32: one instruction per half instead of a 5-step shuffle butterfly (ten dependent SHFLs for
@@ -423,6 +427,53 @@ __device__ __forceinline__ u64 warp_or(u64 v) {
 // OR of the words of one 64-row block whose row bit is set in `kb`; lane l holds rows 2l and 2l+1 (one 16-byte load)
 __device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
     return (((kb >> (2 * lane)) & 1ull) ? w.x : 0ull) | (((kb >> (2 * lane + 1)) & 1ull) ? w.y : 0ull);
+}
+
+// Bulk update (left-looking), the CTAs 1 .. gridDim.x - 1 of a greedy launch: kept rows of ALL super-tiles before s ->
+// removed[] of the columns of super-tile s+1 (the rows of super-tile s itself reach them through CTA 0's push-ahead).
+__device__ __forceinline__ void nms_bulk_update(const u64 *__restrict__ mask, int col_tiles, int s_idx, u64 *__restrict__ removed,
+                                                const u64 *__restrict__ kept_bits, const int *__restrict__ row_done) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T0 = s_idx * SUPER;
+    pdl_enter();
+    if (s_idx == 0) return;
+    const int pt0 = 0, c0 = T0 + SUPER;
+    const int ncols = min(SUPER, col_tiles - c0);
+    if (ncols <= 0) return;
+    if (tid == 0) {                                          // the mask of super-column s+1 must have landed
+        int need = 0;
+        for (int c = c0; c < c0 + ncols; ++c) need += c + 1;
+        const volatile int *flag = row_done + s_idx + 1;
+        while (*flag < need) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+    const long nblk = (long)T0 * ncols;
+    const long wid = (long)(blockIdx.x - 1) * (SCAN_THREADS / 32) + warp, nw = (long)(gridDim.x - 1) * (SCAN_THREADS / 32);
+    for (long k0 = wid; k0 < nblk; k0 += 4 * nw) {
+        ulonglong2 w[4];
+        u64 kb[4];
+        int col[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                       // four independent 512-byte blocks in flight per warp
+            const long k = k0 + u * nw;
+            col[u] = -1;
+            kb[u] = 0ull;
+            w[u] = make_ulonglong2(0ull, 0ull);
+            if (k < nblk) {
+                const int tp = (int)(k / ncols), c = c0 + (int)(k - (long)tp * ncols);
+                kb[u] = kept_bits[pt0 + tp];
+                col[u] = c;
+                if (kb[u]) w[u] = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(pt0 + tp) * col_tiles + c) * 64) + lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (col[u] < 0 || kb[u] == 0ull) continue;      // warp-uniform
+            const u64 v = warp_or(select2(w[u], kb[u], lane));
+            if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + col[u]), (unsigned long long)v);
+        }
+    }
 }
 
 // Launch s of the greedy pass (see the header).  mask is blocked [row tile][col tile][64]; `removed[c]` collects
@@ -436,47 +487,7 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T0 = s_idx * SUPER;
     if (blockIdx.x > 0) {
-        // ---------------- bulk update (left-looking): kept rows of ALL super-tiles before s -> removed[] of the columns
-        // of super-tile s+1 (the rows of super-tile s itself reach them through the urgent update of launch s+1)
-        pdl_enter();
-        if (s_idx == 0) return;
-        const int pt0 = 0, c0 = T0 + SUPER;
-        const int ncols = min(SUPER, col_tiles - c0);
-        if (ncols <= 0) return;
-        if (tid == 0) {                                          // the mask of super-column s+1 must have landed
-            int need = 0;
-            for (int c = c0; c < c0 + ncols; ++c) need += c + 1;
-            const volatile int *flag = row_done + s_idx + 1;
-            while (*flag < need) __nanosleep(64);
-            __threadfence();
-        }
-        __syncthreads();
-        const long nblk = (long)T0 * ncols;
-        const long wid = (long)(blockIdx.x - 1) * (SCAN_THREADS / 32) + warp, nw = (long)(gridDim.x - 1) * (SCAN_THREADS / 32);
-        for (long k0 = wid; k0 < nblk; k0 += 4 * nw) {
-            ulonglong2 w[4];
-            u64 kb[4];
-            int col[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                       // four independent 512-byte blocks in flight per warp
-                const long k = k0 + u * nw;
-                col[u] = -1;
-                kb[u] = 0ull;
-                w[u] = make_ulonglong2(0ull, 0ull);
-                if (k < nblk) {
-                    const int tp = (int)(k / ncols), c = c0 + (int)(k - (long)tp * ncols);
-                    kb[u] = kept_bits[pt0 + tp];
-                    col[u] = c;
-                    if (kb[u]) w[u] = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)(pt0 + tp) * col_tiles + c) * 64) + lane);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (col[u] < 0 || kb[u] == 0ull) continue;      // warp-uniform
-                const u64 v = warp_or(select2(w[u], kb[u], lane));
-                if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + col[u]), (unsigned long long)v);
-            }
-        }
+        nms_bulk_update(mask, col_tiles, s_idx, removed, kept_bits, row_done);
         return;
     }
     // ---------------- CTA 0: resolve super-tile s
@@ -616,6 +627,119 @@ nms_super_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ diag_t, c
     }
 }
 
+// Block-wise greedy launch (default): CTA 0 resolves ALL 1024 rows of super-tile s together instead of its 16 tiles one
+// after the other.  Thread j owns row j of the super-tile and keeps, in registers, the (up to) 16 words that say which rows
+// of the super-tile suppress it (sup_t, written transposed by the mask kernel); the kept set K and the undecided set U live
+// in shared memory, 16 words each.  A round: a row with a KEPT suppressor is removed, a row with no undecided suppressor
+// left is kept -- the same rule as the per-tile ballot rounds of nms_super_kernel, applied to the whole super-tile, so
+// rows in different tiles decide in the same round and the per-tile barrier / column hand-over (16 x ~0.7 us) disappears:
+// a super-tile takes as many rounds as its longest chain of "suppressed only by a row that is itself still undecided"
+// (a handful for detection boxes; the worst case, 1024 rows that each depend on their predecessor, is 1024 rounds --
+// correct, merely as slow as the serial scan).  The lowest undecided row always decides, so the loop terminates.  Then the
+// kept rows are compacted into the keep list (score order) and pushed into the `removed` words of the next super-tile's
+// columns; CTAs 1.. are the same bulk updaters as before.
+__global__ void __launch_bounds__(SCAN_THREADS)
+nms_block_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ sup_t, const int *__restrict__ order, int n, int col_tiles, int s_idx,
+                 u64 *__restrict__ removed, u64 *__restrict__ kept_bits, int *__restrict__ nkept_ptr,
+                 int64_t *__restrict__ keep, int32_t *__restrict__ keep_count, int last, const int *__restrict__ row_done) {
+    if (blockIdx.x > 0) {
+        nms_bulk_update(mask, col_tiles, s_idx, removed, kept_bits, row_done);
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T0 = s_idx * SUPER;
+    const int nt = min(SUPER, col_tiles - T0);
+    const int c0n = T0 + SUPER, ncols_next = max(0, min(SUPER, col_tiles - c0n));       // the next super-tile's columns
+    __shared__ u64 s_K[SUPER], s_U[SUPER], s_push[SUPER];
+    __shared__ int s_pre[SUPER + 1];
+    if (tid == 0) {                                          // the mask of super-columns s (this block) and s+1 (push) must have landed
+        int need = 0;
+        for (int c = T0; c < T0 + nt; ++c) need += c + 1;
+        const volatile int *flag = row_done + s_idx;
+        while (*flag < need) __nanosleep(64);
+        if (ncols_next > 0) {
+            need = 0;
+            for (int c = c0n; c < c0n + ncols_next; ++c) need += c + 1;
+            flag = row_done + s_idx + 1;
+            while (*flag < need) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    // the row's suppressor words (rows of tiles 0 .. c of this super-tile; tile c's own word only has bits below the row) and
+    // its words of the next super-tile's columns: all independent loads, one L2 round trip, issued before the previous
+    // launch's results are awaited (they depend on the mask alone)
+    const int c = tid >> 6, jj = tid & 63;
+    const int row = T0 * 64 + tid;
+    const bool live = c < nt && row < n;
+    u64 col[SUPER];
+#pragma unroll
+    for (int r = 0; r < SUPER; ++r) col[r] = (live && r <= c) ? __ldcg(sup_t + ((size_t)(T0 + c) * SUPER + r) * 64 + jj) : 0ull;
+    // the rows' words of the next super-tile's columns go to shared memory ([row tile][column][64 rows], 16-byte cp.async
+    // chunks): 32 more registers per thread would not fit next to col[] at 1024 threads per CTA
+    extern __shared__ u64 s_nxt[];
+    for (int ch = tid; ch < nt * ncols_next * 32; ch += SCAN_THREADS) {
+        const int blk = ch >> 5, tp = blk / ncols_next, k = blk - tp * ncols_next;
+        const u64 *src = mask + ((size_t)(T0 + tp) * col_tiles + c0n + k) * 64 + (ch & 31) * 2;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_nxt + ((size_t)tp * SUPER + k) * 64 + (ch & 31) * 2)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int my_order = live ? order[row] : 0;
+    pdl_enter();                                             // the previous launch: removed[] of our columns, nkept, kept_bits
+    if (tid < SUPER) {
+        const int rows = min(64, n - (T0 + tid) * 64);
+        const u64 valid = tid < nt ? (rows >= 64 ? ~0ull : ((1ull << max(rows, 0)) - 1ull)) : 0ull;
+        s_U[tid] = tid < nt ? (~__ldcg(removed + T0 + tid) & valid) : 0ull;
+        s_K[tid] = 0ull;
+        s_push[tid] = 0ull;
+    }
+    __syncthreads();
+    bool und = live && ((s_U[c] >> jj) & 1ull);
+    bool kept = false;
+    for (;;) {
+        bool rem = false, ok = false;
+        if (und) {
+            u64 hit = 0ull, pend = 0ull;
+#pragma unroll
+            for (int r = 0; r < SUPER; ++r) { hit |= col[r] & s_K[r]; pend |= col[r] & s_U[r]; }
+            rem = hit != 0ull;
+            ok = !rem && pend == 0ull;
+        }
+        const unsigned bk = __ballot_sync(0xffffffffu, ok), br = __ballot_sync(0xffffffffu, rem);
+        __syncthreads();                                     // every thread has read K / U of this round
+        if (lane == 0 && (bk | br)) {                        // a warp owns one 32-bit half of its tile's words
+            unsigned *K32 = reinterpret_cast<unsigned *>(s_K) + (warp >> 1) * 2 + (warp & 1);
+            unsigned *U32 = reinterpret_cast<unsigned *>(s_U) + (warp >> 1) * 2 + (warp & 1);
+            *K32 |= bk;
+            *U32 &= ~(bk | br);
+        }
+        kept |= ok;
+        und = und && !rem && !ok;
+        if (!__syncthreads_or(und ? 1 : 0)) break;
+    }
+    // keep list, score order: kept rows before this one = the kept rows of earlier tiles + the lower bits of its own tile
+    if (tid == 0) {
+        int run = *nkept_ptr;
+        for (int t = 0; t < SUPER; ++t) { s_pre[t] = run; run += __popcll(s_K[t]); }
+        s_pre[SUPER] = run;
+    }
+    if (tid < nt) kept_bits[T0 + tid] = s_K[tid];
+    // push-ahead: kept rows of this super-tile -> removed[] of the next super-tile's columns
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int k = 0; k < ncols_next; ++k) {
+        const u64 v = warp_or(kept ? s_nxt[((size_t)c * SUPER + k) * 64 + jj] : 0ull);
+        if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(&s_push[k]), (unsigned long long)v);
+    }
+    __syncthreads();
+    if (kept) keep[s_pre[c] + __popcll(s_K[c] & ((1ull << jj) - 1ull))] = my_order;
+    if (tid < ncols_next && s_push[tid]) atomicOr(reinterpret_cast<unsigned long long *>(removed + c0n + tid), (unsigned long long)s_push[tid]);
+    if (tid == 0) {
+        *nkept_ptr = s_pre[SUPER];
+        if (last) *keep_count = s_pre[SUPER];
+    }
+}
+
 // One warp per segment.  Shared memory per warp: 6 * max_seg floats/ints.
 constexpr int BATCH_WARPS = 4;
 
@@ -670,7 +794,7 @@ struct NmsWorkspace {
     float4 *boxes;
     float *areas;
     int *order, *rank, *nkept, *row_done;
-    u64 *removed, *kept_bits, *diag_t, *mask;
+    u64 *removed, *kept_bits, *diag_t, *sup_t, *mask;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -688,6 +812,7 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
     w.nkept = (int *)p;     p += 256;
     w.row_done = (int *)p;  p += align_up(sizeof(int) * ((col_tiles + SUPER - 1) / SUPER), 256);
     w.diag_t = (u64 *)p;    p += align_up(sizeof(u64) * col_tiles * 64, 256);
+    w.sup_t = (u64 *)p;     p += align_up(sizeof(u64) * col_tiles * SUPER * 64, 256);     // [col tile][row tile in its super-tile][64]
     w.mask = (u64 *)p;
     return w;
 }
@@ -780,7 +905,8 @@ NmsStreams *nms_streams(int n_events) {
 
 // Diagnostic hook (like azn_fc_tune): 0 = default schedule; 1 = everything on the caller's stream, mask then chain;
 // 2 = stop after the mask; 3 = stop after the sort (rank + scatter).  Modes 2 / 3 leave keep_count untouched.
-// + 8: the all-pairs rank sort for every n (A/B of the bucket sort that large n take by default).
+// + 8: the all-pairs rank sort for every n (A/B of the bucket sort that large n take by default); + 16: the tile-by-tile
+// greedy pass (nms_super_kernel) instead of the block-wise one.
 static int g_nms_mode = 0;
 extern "C" void azn_nms_tune(int mode) { g_nms_mode = mode; }
 
@@ -789,7 +915,7 @@ extern "C" size_t azn_nms_workspace_bytes(int64_t n) {
     const size_t ct = (size_t)((n + 63) / 64);
     return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + 2 * align_up(sizeof(int) * n, 256) +
            2 * align_up(sizeof(u64) * ct, 256) + 256 + align_up(sizeof(int) * ((ct + 15) / 16), 256) + align_up(sizeof(u64) * ct * 64, 256) +
-           align_up(sizeof(u64) * ct * ct * 64, 256);
+           align_up(sizeof(u64) * ct * SUPER * 64, 256) + align_up(sizeof(u64) * ct * ct * 64, 256);
 }
 
 extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *keep, int32_t *keep_count,
@@ -847,6 +973,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         static bool attr_set = false;
         if (!attr_set) {
             AZN_CUDA(cudaFuncSetAttribute(nms_super_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            AZN_CUDA(cudaFuncSetAttribute(nms_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
         const int n_super = (col_tiles + SUPER - 1) / SUPER;
@@ -888,7 +1015,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             AZN_CUDA(cudaStreamWaitEvent(chain, ns->fork, 0));
         }
         nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
-                                                                                                 w.diag_t, w.row_done);
+                                                                                                 w.diag_t, w.row_done, w.sup_t);
         AZN_LAUNCH_CHECK();
         for (int si = 0; si < n_super && (g_nms_mode & 7) != 2; ++si) {
             // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1
@@ -896,9 +1023,14 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             long updaters = (si == 0 || upd_cols <= 0) ? 0 : ((long)si * SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
             const int upd_cap = ms != s ? 7 : SUPER_UPDATERS;         // partitioned: the chain owns 8 SMs -- CTA 0 keeps one to itself
             if (updaters > upd_cap) updaters = upd_cap;
-            AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + (unsigned)updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
-                                    (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
-                                    si == n_super - 1 ? 1 : 0, (const int *)w.row_done));
+            if (g_nms_mode & 16)                               // A/B: the tile-by-tile pass
+                AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + (unsigned)updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
+                                        (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
+                                        si == n_super - 1 ? 1 : 0, (const int *)w.row_done));
+            else
+                AZN_CUDA(azn_launch_pdl(nms_block_kernel, dim3(1 + (unsigned)updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.sup_t,
+                                        (const int *)w.order, (int)n, col_tiles, si, w.removed, w.kept_bits, w.nkept, keep, keep_count,
+                                        si == n_super - 1 ? 1 : 0, (const int *)w.row_done));
         }
         // `join` (above) makes the caller's stream wait for the chain and the mask on every path out of this scope
     }

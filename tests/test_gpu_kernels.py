@@ -270,12 +270,33 @@ def test_nms_bucket_sort_orders_like_the_rank_sort(dev, O, dist):
     keep, cnt = ops.nms(dt, 0.5)
     assert keep[:int(cnt.item())].cpu().tolist() == ref, dist
     lib = _lib.lib()
-    lib.azn_nms_tune(8)
     try:
-        keep2, cnt2 = ops.nms(dt, 0.5)
-        assert keep2[:int(cnt2.item())].cpu().tolist() == ref, dist
+        for mode in (8, 16, 24):                       # all-pairs sort / tile-by-tile greedy pass / both: the A/B variants
+            lib.azn_nms_tune(mode)
+            keep2, cnt2 = ops.nms(dt, 0.5)
+            assert keep2[:int(cnt2.item())].cpu().tolist() == ref, (dist, mode)
     finally:
         lib.azn_nms_tune(0)
+
+
+def test_nms_long_dependency_chain(dev, O):
+    """The block-wise greedy pass decides a super-tile of 1024 rows in rounds; a staircase of boxes in which every box is
+    suppressed by its predecessor alone (kept, removed, kept, ...) is its worst case -- one round per row -- and must
+    still give the serial scan's answer.  Two staircases across super-tile borders plus unrelated boxes in between."""
+    from aznet_b200 import ops
+    n = 3000
+    d = np.zeros((n, 5), np.float32)
+    x = np.arange(n, dtype=np.float32) * 4.0                      # 10-wide boxes shifted by 4: IoU(i, i+1) = 7/15 > 0.4, IoU(i, i+2) < 0.4
+    d[:, 0], d[:, 2] = x, x + 10.0
+    d[:, 1], d[:, 3] = 5.0, 50.0
+    d[:, 4] = np.linspace(1.0, 0.1, n)                            # score order = position
+    d[1000:1400, 1] += 500.0                                      # an unrelated group on another row of the image
+    d[1000:1400, 3] += 500.0
+    d = np.ascontiguousarray(d)
+    ref = O.nms(d, 0.4)
+    assert 1200 < len(ref) < 1800
+    keep, cnt = ops.nms(torch.from_numpy(d).to(dev), 0.4)
+    assert keep[:int(cnt.item())].cpu().tolist() == ref
 
 
 def test_nms_inside_cuda_graph_and_on_side_stream(dev, O):
