@@ -40,6 +40,7 @@
 #include <mutex>
 #include <vector>
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -427,6 +428,151 @@ __device__ __forceinline__ u64 warp_or(u64 v) {
 // OR of the words of one 64-row block whose row bit is set in `kb`; lane l holds rows 2l and 2l+1 (one 16-byte load)
 __device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
     return (((kb >> (2 * lane)) & 1ull) ? w.x : 0ull) | (((kb >> (2 * lane + 1)) & 1ull) ? w.y : 0ull);
+}
+
+// ---- mask kernel, second version (thresh > 0): conservative packed-half screen + warp-balanced exact evaluation ----------
+// ncu of nms_mask_kernel at N = 20 000 (profiles/r2_ncu_nms_mask.csv): 1757 warp instructions per warp and tile, of which 650
+// the float32 intersection screen of the 64 columns (10 per pair), 390 the per-lane area-ratio loops (12 trips at 8.6 live
+// lanes), 420 the per-lane division loop (9 trips at 7.7 live lanes): most of the time goes to loops that run at the pace
+// of the lane with the most candidates.  This version
+//   (1) screens two columns per instruction in packed half precision with DIRECTED rounding, so that the screen can only
+//       err towards "candidate": the exact test fl(a.x2 - b.x1) > -1 implies a.x2 + 1 > b.x1 in the reals, hence
+//       RU(a.x2 + 1) > RD(b.x1) for any rounding up / down to half (+-inf included); likewise the other three
+//       differences.  The area-ratio condition min >= t' max that the exact filter applies becomes |log2 A - log2 B| <= L
+//       with L = -log2 t' plus 0.05 of slack for the half rounding of the logs (their error is below 0.02).  Five packed
+//       compares and three logic operations per TWO pairs; ~3 % of the pairs come out as candidates;
+//   (2) gathers the candidates of the warp's 32 rows into one list (prefix sum of the per-lane counts) and evaluates them
+//       32 at a time, one per lane: the exact intersection test, the exact area filter and the IEEE division of the
+//       first version, in the same order -- so the bits are the same -- but in ~T/32 trips with all lanes busy.
+// Column p and column p + 32 share a half2: accumulator bit p % 16 of the low / high half.
+constexpr int MASK_LIST = 256;                 // candidate list entries per warp and pass
+
+__device__ __forceinline__ float bump_up(float v) { return nextafterf(v, INFINITY); }
+__device__ __forceinline__ unsigned pack_h2(__half lo, __half hi) {
+    return (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
+}
+__device__ __forceinline__ __half2 as_h2(unsigned u) { return *reinterpret_cast<const __half2 *>(&u); }
+
+__global__ void __launch_bounds__(MASK_THREADS)
+nms_mask2_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, int n, double thresh,
+                 u64 *__restrict__ mask, int col_tiles, u64 *__restrict__ diag_t, int *__restrict__ row_done, u64 *__restrict__ sup_t) {
+    const long id = blockIdx.x;                                               // column-major over the triangle, as in version 1
+    int ct = (int)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
+    ct = max(0, min(ct, col_tiles - 1));
+    while (ct > 0 && (long)ct * (ct + 1) / 2 > id) --ct;
+    while ((long)(ct + 1) * (ct + 2) / 2 <= id) ++ct;
+    const int rt = (int)(id - (long)ct * (ct + 1) / 2);
+    __shared__ float4 cb[64], rbx[64];
+    __shared__ float ca[64], rba[64];
+    __shared__ __align__(16) unsigned hb[32][4];                              // pair p: x1 | y1 | RU(x2 + 1) | RU(y2 + 1), halves = columns p, p + 32
+    __shared__ unsigned hl[32];                                               // pair p: log2(area)
+    __shared__ __align__(8) unsigned s_bits[64][2];
+    __shared__ unsigned short s_list[MASK_THREADS / 32][MASK_LIST];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cn = min(64, n - ct * 64);
+    const int row = rt * 64 + tid;
+    const float thresh_f = thresh_as_float(thresh);
+    {
+        // column tid: exact copy + its packed-half screen values (an absent or empty column can match nothing: x1 = +inf)
+        float4 b = make_float4(INFINITY, 0.f, 0.f, 0.f);
+        float ar = 0.f;
+        if (tid < cn) {
+            b = boxes[ct * 64 + tid];
+            ar = areas[ct * 64 + tid];
+            if (!box_valid(b)) b.x = INFINITY;
+        }
+        cb[tid] = b;
+        ca[tid] = ar;
+        unsigned short *h16 = reinterpret_cast<unsigned short *>(&hb[tid & 31][0]) + (tid >> 5);
+        h16[0] = __half_as_ushort(__float2half_rd(b.x));
+        h16[2] = __half_as_ushort(__float2half_rd(b.y));
+        h16[4] = __half_as_ushort(__float2half_ru(bump_up(__fadd_rn(b.z, 1.f))));
+        h16[6] = __half_as_ushort(__float2half_ru(bump_up(__fadd_rn(b.w, 1.f))));
+        reinterpret_cast<unsigned short *>(&hl[tid & 31])[tid >> 5] = __half_as_ushort(__float2half_rn(__log2f(ar)));
+        s_bits[tid][0] = 0u;
+        s_bits[tid][1] = 0u;
+    }
+    float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ra = 0.f;
+    bool row_ok = false;
+    if (row < n) {
+        rb = boxes[row];
+        ra = areas[row];
+        row_ok = box_valid(rb);
+    }
+    rbx[tid] = rb;
+    rba[tid] = ra;
+    __syncthreads();
+    // (1) the screen
+    u64 cand = 0ull;
+    if (row_ok) {
+        const __half a1x = __float2half_rd(rb.x), a1y = __float2half_rd(rb.y);
+        const __half a2x = __float2half_ru(bump_up(__fadd_rn(rb.z, 1.f))), a2y = __float2half_ru(bump_up(__fadd_rn(rb.w, 1.f)));
+        const __half2 A1x = __halves2half2(a1x, a1x), A1y = __halves2half2(a1y, a1y), A2x = __halves2half2(a2x, a2x), A2y = __halves2half2(a2y, a2y);
+        const __half la = __float2half_rn(__log2f(ra));
+        const __half2 LA = __halves2half2(la, la);
+        const float Lf = -__log2f(__fmul_rn(thresh_f, 0.999998f)) + 0.05f;
+        const __half lh = __float2half_ru(fmaxf(Lf, 0.05f));
+        const __half2 LH = __halves2half2(lh, lh);
+        unsigned acc0 = 0u, acc1 = 0u;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const uint4 c = *reinterpret_cast<const uint4 *>(&hb[p][0]);
+            const unsigned m1 = __hgt2_mask(A2x, as_h2(c.x)), m2 = __hgt2_mask(as_h2(c.z), A1x);
+            const unsigned m3 = __hgt2_mask(A2y, as_h2(c.y)), m4 = __hgt2_mask(as_h2(c.w), A1y);
+            const unsigned m5 = __hle2_mask(__habs2(__hsub2(LA, as_h2(hl[p]))), LH);
+            const unsigned hit = (m1 & m2 & m3) & (m4 & m5) & ((1u << (p & 15)) * 0x00010001u);
+            if (p < 16) acc0 |= hit; else acc1 |= hit;
+        }
+        const unsigned lo = (acc0 & 0xffffu) | (acc1 << 16), hi = (acc0 >> 16) | (acc1 & 0xffff0000u);
+        cand = (u64)lo | ((u64)hi << 32);
+        if (rt == ct) cand &= tid >= 63 ? 0ull : (~0ull << (tid + 1));          // the diagonal tile: columns behind the row only
+    }
+    // (2) the warp's candidates, 32 at a time
+    const int cnt = __popcll(cand);
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const float tq = __fmul_rn(thresh_f, 0.999998f);
+    unsigned short *list = s_list[warp];
+    for (int base = 0; base < total; base += MASK_LIST) {
+        {
+            u64 c = cand;
+            int e = incl - cnt - base;                                       // position of this lane's first candidate in the window
+            while (c) {
+                const int k = __ffsll((long long)c) - 1;
+                c &= c - 1;
+                if (e >= 0 && e < MASK_LIST) list[e] = (unsigned short)((lane << 6) | k);
+                ++e;
+            }
+        }
+        __syncwarp();
+        const int m = min(MASK_LIST, total - base);
+        for (int e = lane; e < m; e += 32) {
+            const int ent = list[e], r = warp * 32 + (ent >> 6), k = ent & 63;
+            const float4 a = rbx[r], b = cb[k];
+            if (!pair_intersects(a, b)) continue;
+            const float aa = rba[r], ab = ca[k];
+            if (fminf(aa, ab) < __fmul_rn(tq, fmaxf(aa, ab))) continue;
+            if (suppresses(a, aa, b, ab, thresh_f)) atomicOr(&s_bits[r][k >> 5], 1u << (k & 31));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const u64 bits = (u64)s_bits[tid][0] | ((u64)s_bits[tid][1] << 32);
+    mask[((size_t)rt * col_tiles + ct) * 64 + tid] = bits;                   // blocked: [row tile][col tile][64 rows]
+    if (rt / SUPER == ct / SUPER) {                                          // block-uniform: see version 1
+        u64 *s_d = reinterpret_cast<u64 *>(&s_bits[0][0]);
+        u64 col = 0;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) col |= ((s_d[i] >> tid) & 1ull) << i;
+        if (rt == ct) diag_t[(size_t)rt * 64 + tid] = col;
+        sup_t[((size_t)ct * SUPER + rt % SUPER) * 64 + tid] = col;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(row_done + ct / 16, 1);
+    }
 }
 
 // Bulk update (left-looking), the CTAs 1 .. gridDim.x - 1 of a greedy launch: kept rows of ALL super-tiles before s ->
@@ -906,7 +1052,7 @@ NmsStreams *nms_streams(int n_events) {
 // Diagnostic hook (like azn_fc_tune): 0 = default schedule; 1 = everything on the caller's stream, mask then chain;
 // 2 = stop after the mask; 3 = stop after the sort (rank + scatter).  Modes 2 / 3 leave keep_count untouched.
 // + 8: the all-pairs rank sort for every n (A/B of the bucket sort that large n take by default); + 16: the tile-by-tile
-// greedy pass (nms_super_kernel) instead of the block-wise one.
+// greedy pass (nms_super_kernel) instead of the block-wise one; + 32: the float32 mask kernel (version 1) for every threshold.
 static int g_nms_mode = 0;
 extern "C" void azn_nms_tune(int mode) { g_nms_mode = mode; }
 
@@ -1014,8 +1160,12 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             if (ms != s) AZN_CUDA(cudaStreamWaitEvent(ms, ns->fork, 0));
             AZN_CUDA(cudaStreamWaitEvent(chain, ns->fork, 0));
         }
-        nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
-                                                                                                 w.diag_t, w.row_done, w.sup_t);
+        if (thresh > 0.0 && !(g_nms_mode & 32))
+            nms_mask2_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles,
+                                                                                                      w.diag_t, w.row_done, w.sup_t);
+        else
+            nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
+                                                                                                     w.diag_t, w.row_done, w.sup_t);
         AZN_LAUNCH_CHECK();
         for (int si = 0; si < n_super && (g_nms_mode & 7) != 2; ++si) {
             // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1

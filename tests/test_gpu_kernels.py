@@ -271,7 +271,7 @@ def test_nms_bucket_sort_orders_like_the_rank_sort(dev, O, dist):
     assert keep[:int(cnt.item())].cpu().tolist() == ref, dist
     lib = _lib.lib()
     try:
-        for mode in (8, 16, 24):                       # all-pairs sort / tile-by-tile greedy pass / both: the A/B variants
+        for mode in (8, 16, 24, 32, 56):               # all-pairs sort / tile-by-tile greedy pass / both / float32 mask kernel / all: the A/B variants
             lib.azn_nms_tune(mode)
             keep2, cnt2 = ops.nms(dt, 0.5)
             assert keep2[:int(cnt2.item())].cpu().tolist() == ref, (dist, mode)
