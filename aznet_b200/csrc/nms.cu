@@ -38,6 +38,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -99,8 +100,12 @@ __device__ __forceinline__ unsigned rank_key(float s) {
 // position itself and the scatter launch is skipped (small problems are launch-latency bound).
 __global__ void __launch_bounds__(RANK_THREADS)
 nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank, float4 *__restrict__ boxes,
-                float *__restrict__ areas, int *__restrict__ order) {
+                float *__restrict__ areas, int *__restrict__ order, uint4 *__restrict__ zero, int n_zero) {
     __shared__ __align__(16) unsigned s_key[RANK_TILE];
+    // the per-call state of the later kernels (removed | kept_bits | nkept | row_done | ctl: a few KB) is zeroed here instead of
+    // by a memset of its own -- small problems are bound by the number of host-side launches
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int k = threadIdx.x; k < n_zero; k += RANK_THREADS) zero[k] = make_uint4(0u, 0u, 0u, 0u);
     const int i = blockIdx.x * RANK_THREADS + threadIdx.x;
     const int t0 = blockIdx.y * RANK_TILE, tn = min(RANK_TILE, n - t0);
     for (int k = threadIdx.x; k < RANK_TILE; k += RANK_THREADS)
@@ -158,7 +163,7 @@ nms_scatter_kernel(const float *__restrict__ dets, int n, const int *__restrict_
 
 // ---- bucket sort for large n ------------------------------------------------------------------------------------
 // The rank kernel above compares every pair: n^2 = 4e8 key compares at n = 20 000, 60-70 us -- a fifth of the whole call.
-// For n >= BKT_MIN_N the order is found in two steps instead.  nms_bucket_kernel (one CTA) spreads the keys over BKT
+// For n > RANK_TILE the order is found in two steps instead.  nms_bucket_kernel (one CTA) spreads the keys over BKT
 // buckets that are linear in the uint key between the smallest and the largest key present, highest keys first
 // (shared-memory histogram, scan, scatter of (key, index) pairs in bucket order); nms_bucket_rank_kernel then ranks every
 // detection inside its own bucket only -- a few dozen compares with the same rule as above (key desc, index desc) -- and
@@ -166,13 +171,15 @@ nms_scatter_kernel(const float *__restrict__ dets, int n, const int *__restrict_
 // distribution only through the largest bucket (all scores equal: one bucket, the n^2 loop again).
 constexpr int BKT = 2048;
 constexpr int BKT_THREADS = 1024;
-constexpr int BKT_MIN_N = 4096;
+constexpr int BKT_MIN_N = RANK_TILE + 1;     // everything the single-tile rank kernel does not take
 
 // ITEMS > 0: n <= ITEMS * BKT_THREADS and every thread keeps its keys in registers -- the scores are read from global
 // memory once (strided 20-byte records: the one pass costs ~5 us on one SM) instead of once per phase; ITEMS == 0: any n.
 template <int ITEMS>
 __global__ void __launch_bounds__(BKT_THREADS)
-nms_bucket_kernel(const float *__restrict__ dets, int n, uint2 *__restrict__ bpair, int *__restrict__ boff, int staged) {
+nms_bucket_kernel(const float *__restrict__ dets, int n, uint2 *__restrict__ bpair, int *__restrict__ boff, int staged,
+                  uint4 *__restrict__ zero, int n_zero) {
+    for (int k = threadIdx.x; k < n_zero; k += BKT_THREADS) zero[k] = make_uint4(0u, 0u, 0u, 0u);      // see nms_rank_kernel
     // staged: dynamic shared memory holds n (key, index) pairs -- the scatter into bucket order goes there and leaves the
     // SM as one coalesced copy (40 000 scattered 4-byte stores from a single SM cost ~20 us, more than everything else)
     extern __shared__ uint2 s_stage[];
@@ -431,7 +438,7 @@ __device__ __forceinline__ u64 select2(const ulonglong2 &w, u64 kb, int lane) {
 }
 
 // ---- mask kernel, second version (thresh > 0): conservative packed-half screen + warp-balanced exact evaluation ----------
-// ncu of nms_mask_kernel at N = 20 000 (profiles/r2_ncu_nms_mask.csv): 1757 warp instructions per warp and tile, of which 650
+// ncu of nms_mask_kernel at N = 20 000 (profiles/r2_ncu_nms_mask_v1.csv): 1757 warp instructions per warp and tile, of which 650
 // the float32 intersection screen of the 64 columns (10 per pair), 390 the per-lane area-ratio loops (12 trips at 8.6 live
 // lanes), 420 the per-lane division loop (9 trips at 7.7 live lanes): most of the time goes to loops that run at the pace
 // of the lane with the most candidates.  This version
@@ -535,7 +542,12 @@ nms_mask2_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
     const float tq = __fmul_rn(thresh_f, 0.999998f);
     unsigned short *list = s_list[warp];
     for (int base = 0; base < total; base += MASK_LIST) {
-        {
+        if (total <= MASK_LIST) {                                            // warp-uniform, the usual case: everything fits, no window checks
+            unsigned short *dst = list + (incl - cnt);
+            const unsigned tag = (unsigned)lane << 6;
+            for (unsigned c = (unsigned)cand; c; c &= c - 1) *dst++ = (unsigned short)(tag | (unsigned)(__ffs((int)c) - 1));
+            for (unsigned c = (unsigned)(cand >> 32); c; c &= c - 1) *dst++ = (unsigned short)(tag | 32u | (unsigned)(__ffs((int)c) - 1));
+        } else {
             u64 c = cand;
             int e = incl - cnt - base;                                       // position of this lane's first candidate in the window
             while (c) {
@@ -886,6 +898,179 @@ nms_block_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ sup_t, co
     }
 }
 
+// Persistent greedy pass (A/B variant, azn_nms_tune(64); NOT the default: at N = 20 000 it measured 0.233-0.244 ms against
+// 0.208-0.219 ms for one PDL launch per super-tile -- ~10 us per super-tile instead of ~6: the flag hand-overs through L2
+// (resolver -> updaters -> resolver, each a poll with a sleep) cost more than the hardware hand-over between programmatic
+// dependent launches, whose successor has its operands fetched before the predecessor exits).
+// ONE launch for the whole chain instead of one per super-tile.  CTA 0 runs the
+// block-wise rounds of nms_block_kernel for the super-tiles in a loop, the bulk updaters loop over their target
+// super-columns.  What the kernel boundaries did is done by flags in global memory (ctl, zeroed per call):
+//   done[s]  = 2           a resolver has published kept_bits / nkept of super-tile s and pushed its kept rows into removed[]
+//                          of super-column s + 1      (the other resolver waits for it; so do the updaters of target s + 2)
+//   upd[s]  += 1 per CTA   an updater has pushed the kept rows of super-tiles <= s - 2 into removed[] of super-column s
+//                                                                                        (the resolver of s waits for all)
+// CTAs 0 and 1 alternate as resolvers (even / odd super-tiles), so that the mask words of super-tile s + 1 are fetched while
+// s is being resolved; CTAs 2.. are the updaters.  The CTAs spin on each other: the grid (<= 8 CTAs of 1024 threads) is always
+// co-resident eventually -- nothing it waits for waits for it -- and every spin has a time-out that raises ctl.abort
+// (keep_count = -1) instead of hanging the GPU.
+struct ChainCtl {
+    int *done, *upd, *abort, *nkept;
+};
+
+__device__ __forceinline__ bool chain_wait(const volatile int *flag, int need, volatile int *abort_flag) {
+    unsigned it = 0;
+    while (*flag < need) {
+        if (*abort_flag || ++it > (1u << 23)) { *abort_flag = 1; return false; }      // ~2 s: a bug, not a wait
+        __nanosleep(it < 32 ? 20 : 200);
+    }
+    __threadfence();
+    return true;
+}
+__device__ __forceinline__ int super_col_tiles(int s, int col_tiles) {      // mask tiles of super-column s (what row_done[s] counts up to)
+    int need = 0;
+    for (int c = s * SUPER; c < min((s + 1) * SUPER, col_tiles); ++c) need += c + 1;
+    return need;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+nms_chain_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ sup_t, const int *__restrict__ order, int n, int col_tiles, int n_super,
+                 u64 *__restrict__ removed, u64 *__restrict__ kept_bits, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count,
+                 const int *__restrict__ row_done, ChainCtl ctl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_ok, s_ok2;                                  // two flags: thread 0 may reach the second wait before a slow warp has read the first
+    if (blockIdx.x > 1) {
+        // ---------------- bulk updaters: target super-column t gets the kept rows of super-tiles 0 .. t - 2
+        const int n_upd = gridDim.x - 2;
+        for (int t = 2; t < n_super; ++t) {
+            const int c0 = t * SUPER, ncols = min(SUPER, col_tiles - c0);
+            if (tid == 0) s_ok = chain_wait(ctl.done + (t - 2), 2, ctl.abort) && chain_wait(row_done + t, super_col_tiles(t, col_tiles), ctl.abort);
+            __syncthreads();
+            if (!s_ok) return;
+            const long nblk = (long)(t - 1) * SUPER * ncols;
+            const long wid = (long)(blockIdx.x - 2) * (SCAN_THREADS / 32) + warp, nw = (long)n_upd * (SCAN_THREADS / 32);
+            for (long k0 = wid; k0 < nblk; k0 += 4 * nw) {
+                ulonglong2 w[4];
+                u64 kb[4];
+                int col[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                   // four independent 512-byte blocks in flight per warp
+                    const long k = k0 + u * nw;
+                    col[u] = -1;
+                    kb[u] = 0ull;
+                    w[u] = make_ulonglong2(0ull, 0ull);
+                    if (k < nblk) {
+                        const int tp = (int)(k / ncols), c = c0 + (int)(k - (long)tp * ncols);
+                        kb[u] = __ldcg(kept_bits + tp);
+                        col[u] = c;
+                        if (kb[u]) w[u] = __ldcg(reinterpret_cast<const ulonglong2 *>(mask + ((size_t)tp * col_tiles + c) * 64) + lane);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (col[u] < 0 || kb[u] == 0ull) continue;  // warp-uniform
+                    const u64 v = warp_or(select2(w[u], kb[u], lane));
+                    if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(removed + col[u]), (unsigned long long)v);
+                }
+            }
+            __syncthreads();                                     // every warp's atomics are issued ...
+            if (tid == 0) {
+                __threadfence();                                 // ... and ordered before the count
+                atomicAdd(ctl.upd + t, 1);
+            }
+        }
+        return;
+    }
+    // ---------------- CTAs 0 and 1: the super-tiles in order, alternating -- while one resolves super-tile s the other has
+    // already fetched what super-tile s + 1 needs from the mask (256 KB per super-tile: on one SM that is ~2.5 us, which a
+    // single resolver would pay between every two super-tiles)
+    extern __shared__ u64 s_nxt[];                               // [row tile][next column][64 rows]
+    __shared__ u64 s_K[SUPER], s_U[SUPER], s_push[SUPER];
+    __shared__ int s_pre[SUPER + 1];
+    const int n_upd = gridDim.x - 2;
+    const int c = tid >> 6, jj = tid & 63;
+    for (int s = blockIdx.x; s < n_super; s += 2) {
+        const int T0 = s * SUPER;
+        const int nt = min(SUPER, col_tiles - T0);
+        const int c0n = T0 + SUPER, ncols_next = max(0, min(SUPER, col_tiles - c0n));
+        if (tid == 0)
+            s_ok = chain_wait(row_done + s, super_col_tiles(s, col_tiles), ctl.abort) &&
+                   (ncols_next == 0 || chain_wait(row_done + s + 1, super_col_tiles(s + 1, col_tiles), ctl.abort));
+        __syncthreads();
+        if (!s_ok) break;
+        const int row = T0 * 64 + tid;
+        const bool live = c < nt && row < n;
+        u64 col[SUPER];
+#pragma unroll
+        for (int r = 0; r < SUPER; ++r) col[r] = (live && r <= c) ? __ldcg(sup_t + ((size_t)(T0 + c) * SUPER + r) * 64 + jj) : 0ull;
+        for (int ch = tid; ch < nt * ncols_next * 32; ch += SCAN_THREADS) {
+            const int blk = ch >> 5, tp = blk / ncols_next, k = blk - tp * ncols_next;
+            const u64 *src = mask + ((size_t)(T0 + tp) * col_tiles + c0n + k) * 64 + (ch & 31) * 2;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s_nxt + ((size_t)tp * SUPER + k) * 64 + (ch & 31) * 2)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int my_order = live ? order[row] : 0;
+        // the previous super-tile (the other resolver: its kept rows are in removed[] of our columns, nkept is current) and
+        // the updaters' share
+        if (tid == 0)
+            s_ok2 = (s == 0 || chain_wait(ctl.done + (s - 1), 2, ctl.abort)) && (s < 2 || n_upd <= 0 || chain_wait(ctl.upd + s, n_upd, ctl.abort));
+        __syncthreads();
+        if (!s_ok2) break;
+        if (tid < SUPER) {
+            const int rows = min(64, n - (T0 + tid) * 64);
+            const u64 valid = tid < nt ? (rows >= 64 ? ~0ull : ((1ull << max(rows, 0)) - 1ull)) : 0ull;
+            s_U[tid] = tid < nt ? (~__ldcg(removed + T0 + tid) & valid) : 0ull;
+            s_K[tid] = 0ull;
+            s_push[tid] = 0ull;
+        }
+        const int nkept0 = tid == 0 ? __ldcg(ctl.nkept) : 0;
+        __syncthreads();
+        bool und = live && ((s_U[c] >> jj) & 1ull);
+        bool kept = false;
+        for (;;) {
+            bool rem = false, ok = false;
+            if (und) {
+                u64 hit = 0ull, pend = 0ull;
+#pragma unroll
+                for (int r = 0; r < SUPER; ++r) { hit |= col[r] & s_K[r]; pend |= col[r] & s_U[r]; }
+                rem = hit != 0ull;
+                ok = !rem && pend == 0ull;
+            }
+            const unsigned bk = __ballot_sync(0xffffffffu, ok), br = __ballot_sync(0xffffffffu, rem);
+            __syncthreads();                                     // every thread has read K / U of this round
+            if (lane == 0 && (bk | br)) {                        // a warp owns one 32-bit half of its tile's words
+                reinterpret_cast<unsigned *>(s_K)[warp] |= bk;
+                reinterpret_cast<unsigned *>(s_U)[warp] &= ~(bk | br);
+            }
+            kept |= ok;
+            und = und && !rem && !ok;
+            if (!__syncthreads_or(und ? 1 : 0)) break;
+        }
+        if (tid == 0) {
+            int run = nkept0;
+            for (int t = 0; t < SUPER; ++t) { s_pre[t] = run; run += __popcll(s_K[t]); }
+            s_pre[SUPER] = run;
+            *ctl.nkept = run;
+        }
+        if (tid < nt) kept_bits[T0 + tid] = s_K[tid];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                         // s_nxt and s_pre are complete
+        for (int k = 0; k < ncols_next; ++k) {
+            const u64 v = warp_or(kept ? s_nxt[((size_t)c * SUPER + k) * 64 + jj] : 0ull);
+            if (lane == 0 && v) atomicOr(reinterpret_cast<unsigned long long *>(&s_push[k]), (unsigned long long)v);
+        }
+        __syncthreads();
+        if (tid < ncols_next && s_push[tid]) atomicOr(reinterpret_cast<unsigned long long *>(removed + c0n + tid), (unsigned long long)s_push[tid]);
+        if (kept) keep[s_pre[c] + __popcll(s_K[c] & ((1ull << jj) - 1ull))] = my_order;
+        __syncthreads();                                         // the pushes, kept_bits and nkept are issued ...
+        if (tid == 0) {
+            __threadfence();                                     // ... and ordered before the flag; done[s] = 2: resolved and pushed
+            *reinterpret_cast<volatile int *>(ctl.done + s) = 2;
+            if (s == n_super - 1) *keep_count = s_pre[SUPER];
+        }
+    }
+    if (tid == 0 && *reinterpret_cast<volatile int *>(ctl.abort)) *keep_count = -1;
+}
+
 // One warp per segment.  Shared memory per warp: 6 * max_seg floats/ints.
 constexpr int BATCH_WARPS = 4;
 
@@ -939,7 +1124,7 @@ nms_batched_kernel(const float *__restrict__ dets, const int32_t *__restrict__ s
 struct NmsWorkspace {
     float4 *boxes;
     float *areas;
-    int *order, *rank, *nkept, *row_done;
+    int *order, *rank, *nkept, *row_done, *ctl;
     u64 *removed, *kept_bits, *diag_t, *sup_t, *mask;
 };
 
@@ -952,11 +1137,12 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
     w.areas = (float *)p;   p += align_up(sizeof(float) * n, 256);
     w.order = (int *)p;     p += align_up(sizeof(int) * n, 256);
     w.rank = (int *)p;      p += align_up(sizeof(int) * n, 256);
-    // zeroed per call in one memset: rank | removed | kept_bits | nkept | row_done
+    // zeroed per call in one memset: rank | removed | kept_bits | nkept | row_done | ctl
     w.removed = (u64 *)p;   p += align_up(sizeof(u64) * col_tiles, 256);
     w.kept_bits = (u64 *)p; p += align_up(sizeof(u64) * col_tiles, 256);
     w.nkept = (int *)p;     p += 256;
     w.row_done = (int *)p;  p += align_up(sizeof(int) * ((col_tiles + SUPER - 1) / SUPER), 256);
+    w.ctl = (int *)p;       p += align_up(sizeof(int) * (2 * ((col_tiles + SUPER - 1) / SUPER) + 4), 256);     // done[n_super] | upd[n_super] | abort
     w.diag_t = (u64 *)p;    p += align_up(sizeof(u64) * col_tiles * 64, 256);
     w.sup_t = (u64 *)p;     p += align_up(sizeof(u64) * col_tiles * SUPER * 64, 256);     // [col tile][row tile in its super-tile][64]
     w.mask = (u64 *)p;
@@ -1052,7 +1238,8 @@ NmsStreams *nms_streams(int n_events) {
 // Diagnostic hook (like azn_fc_tune): 0 = default schedule; 1 = everything on the caller's stream, mask then chain;
 // 2 = stop after the mask; 3 = stop after the sort (rank + scatter).  Modes 2 / 3 leave keep_count untouched.
 // + 8: the all-pairs rank sort for every n (A/B of the bucket sort that large n take by default); + 16: the tile-by-tile
-// greedy pass (nms_super_kernel) instead of the block-wise one; + 32: the float32 mask kernel (version 1) for every threshold.
+// greedy pass (nms_super_kernel) instead of the block-wise one; + 32: the float32 mask kernel (version 1) for every threshold;
+// + 64: the persistent chain (nms_chain_kernel, one launch for all super-tiles) instead of one launch per super-tile.
 static int g_nms_mode = 0;
 extern "C" void azn_nms_tune(int mode) { g_nms_mode = mode; }
 
@@ -1060,7 +1247,8 @@ extern "C" size_t azn_nms_workspace_bytes(int64_t n) {
     if (n <= 0) return 256;
     const size_t ct = (size_t)((n + 63) / 64);
     return align_up(sizeof(float4) * n, 256) + align_up(sizeof(float) * n, 256) + 2 * align_up(sizeof(int) * n, 256) +
-           2 * align_up(sizeof(u64) * ct, 256) + 256 + align_up(sizeof(int) * ((ct + 15) / 16), 256) + align_up(sizeof(u64) * ct * 64, 256) +
+           2 * align_up(sizeof(u64) * ct, 256) + 256 + align_up(sizeof(int) * ((ct + 15) / 16), 256) + align_up(sizeof(int) * (2 * ((ct + 15) / 16) + 4), 256) +
+           align_up(sizeof(u64) * ct * 64, 256) +
            align_up(sizeof(u64) * ct * SUPER * 64, 256) + align_up(sizeof(u64) * ct * ct * 64, 256);
 }
 
@@ -1080,7 +1268,10 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
     }
     const int col_tiles = (int)((n + 63) / 64);
     NmsWorkspace w = carve(workspace, n, col_tiles);
-    AZN_CUDA(cudaMemsetAsync(w.rank, 0, (size_t)((char *)w.diag_t - (char *)w.rank), s));   // rank, removed, kept_bits, nkept
+    // zeroed per call: removed | kept_bits | nkept | row_done | ctl -- by the first sort kernel; plus `rank` (a memset) when the
+    // all-pairs rank sort runs over several score tiles and accumulates its counts there
+    uint4 *zero = (uint4 *)w.removed;
+    const int n_zero = (int)(((char *)w.diag_t - (char *)w.removed) / 16);
     if (n >= BKT_MIN_N && !(g_nms_mode & 8)) {
         // (key, index) pairs in bucket order and the bucket offsets: at the head of the mask
         // area (64 x 64 tiles x 512 B >= 2 MB at this n; the mask kernel, which runs after the sort, overwrites them)
@@ -1095,7 +1286,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             AZN_CUDA(cudaFuncSetAttribute(nms_bucket_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));         \
             attr_set = true;                                                                                                        \
         }                                                                                                                           \
-        nms_bucket_kernel<IT><<<1, BKT_THREADS, staged ? stage : 0, s>>>(dets, (int)n, bpair, boff, staged);                        \
+        nms_bucket_kernel<IT><<<1, BKT_THREADS, staged ? stage : 0, s>>>(dets, (int)n, bpair, boff, staged, zero, n_zero);                        \
     } while (0)
         if (n <= 8 * BKT_THREADS) AZN_BKT_LAUNCH(8);
         else if (n <= 20 * BKT_THREADS) AZN_BKT_LAUNCH(20);
@@ -1106,8 +1297,9 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         AZN_CUDA(azn_launch_pdl(nms_bucket_rank_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dets, (int)n, (const uint2 *)bpair,
                                 (const int *)boff, w.boxes, w.areas, w.order));
     } else {
+        if (n > RANK_TILE) AZN_CUDA(cudaMemsetAsync(w.rank, 0, sizeof(int) * (size_t)n, s));
         nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
-                          RANK_THREADS, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
+                          RANK_THREADS, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order, zero, n_zero);
         AZN_LAUNCH_CHECK();
         if (n > RANK_TILE) {
             nms_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dets, (int)n, w.rank, w.boxes, w.areas, w.order);
@@ -1167,6 +1359,21 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
                                                                                                      w.diag_t, w.row_done, w.sup_t);
         AZN_LAUNCH_CHECK();
+        if ((g_nms_mode & 64) && !(g_nms_mode & 16) && (g_nms_mode & 7) != 2) {       // A/B only: measured slower than one launch per super-tile
+            // the persistent chain: CTA 0 + up to 7 updaters (the chain's SM partition has 8 SMs; fewer when the columns are few)
+            const long blocks = n_super > 2 ? ((long)(n_super - 2) * SUPER * SUPER + 127) / 128 : 0;
+            const int upd = (int)std::min<long>(blocks, 6);
+            ChainCtl ctl;
+            ctl.done = w.ctl; ctl.upd = w.ctl + n_super; ctl.abort = w.ctl + 2 * n_super; ctl.nkept = w.nkept;
+            static bool chain_attr = false;
+            if (!chain_attr) {
+                AZN_CUDA(cudaFuncSetAttribute(nms_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                chain_attr = true;
+            }
+            nms_chain_kernel<<<(n_super > 1 ? 2 : 1) + upd, SCAN_THREADS, smem, chain>>>((const u64 *)w.mask, (const u64 *)w.sup_t, (const int *)w.order, (int)n, col_tiles, n_super,
+                                                                    w.removed, w.kept_bits, keep, keep_count, (const int *)w.row_done, ctl);
+            AZN_LAUNCH_CHECK();
+        } else
         for (int si = 0; si < n_super && (g_nms_mode & 7) != 2; ++si) {
             // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1
             const int upd_cols = min(SUPER, col_tiles - (si + 1) * SUPER);

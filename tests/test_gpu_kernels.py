@@ -223,7 +223,7 @@ def test_nms_golden_and_oracle(dev, O, golden):
     assert int(cnt.item()) == 0
 
 
-@pytest.mark.parametrize("n,th", [(8000, 0.3), (8000, 0.7), (20000, 0.3), (20000, 0.7), (4096, 0.5), (21000, 0.5), (33000, 0.6)])
+@pytest.mark.parametrize("n,th", [(8000, 0.3), (8000, 0.7), (20000, 0.3), (20000, 0.7), (4096, 0.5), (2049, 0.5), (3000, 0.4), (21000, 0.5), (33000, 0.6)])
 def test_nms_large_matches_oracle(dev, O, n, th):
     from aznet_b200 import ops
     d = synth.make_dets(n, seed=3)
@@ -271,7 +271,7 @@ def test_nms_bucket_sort_orders_like_the_rank_sort(dev, O, dist):
     assert keep[:int(cnt.item())].cpu().tolist() == ref, dist
     lib = _lib.lib()
     try:
-        for mode in (8, 16, 24, 32, 56):               # all-pairs sort / tile-by-tile greedy pass / both / float32 mask kernel / all: the A/B variants
+        for mode in (8, 16, 24, 32, 56, 64):           # all-pairs sort / tile-by-tile greedy pass / both / float32 mask kernel / all / persistent greedy chain: the A/B variants
             lib.azn_nms_tune(mode)
             keep2, cnt2 = ops.nms(dt, 0.5)
             assert keep2[:int(cnt2.item())].cpu().tolist() == ref, (dist, mode)
