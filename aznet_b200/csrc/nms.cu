@@ -12,26 +12,28 @@
 // a multiply-add into an FMA (x86-64 gcc, which built the reference, has no FMA by default).
 //
 // Large single problem (azn_nms).  The mask is ONE launch, column-major over the triangle (cheapest columns first),
-// publishing per-super-column tile counters; the greedy pass runs concurrently on an internal stream (its own 8-SM
+// publishing per-super-column tile counters; the greedy pass runs concurrently on an internal stream (its own 16-SM
 // green-context partition when the driver has them) and launch s polls the counters of super-columns s and s+1, so
-// the serial chain runs alongside the mask and ends ~40 us after it.  Kernels:
-//   1. nms_rank_kernel   -- rank sort by (score desc, index desc) on a 2-D grid: every thread counts
-//      nms_scatter_kernel   the detections of one score tile that precede its own (shared memory),
-//                           partial counts are added atomically, then boxes move to sorted position.
-//   2. nms_mask_kernel   -- 64x64 IoU tiles of the upper triangle -> one 64-bit suppression word
-//                           per (row, column tile); exact intersection pre-test, division only
-//                           for intersecting pairs.
-//   3. nms_super_kernel  -- the greedy pass, blocked like a triangular solve: super-tiles of 16 column tiles
-//                           (1024 boxes) are resolved one launch each.  CTA 0 stages the 1024 x 1024-bit
-//                           diagonal block (128 KB) in shared memory, folds in the suppression words of the
-//                           previous super-tile's kept rows ("urgent" update), then walks its 16 tiles: warp 0
-//                           resolves the 64 x 64 diagonal block of tile b with register-resident words while
-//                           the other 31 warps OR together column b+1's words of the rows kept so far; kept
-//                           original indices are appended to `keep` (on-device compaction; the count never
-//                           visits the host).  The other CTAs of the same launch push the kept rows of ALL EARLIER
-//                           super-tiles into the `removed` words of the NEXT super-tile's columns (left-looking
-//                           bulk update, atomicOr).
-//                           No CTA ever waits for another inside a launch.
+// the serial chain runs alongside the mask and ends ~25 us after it.  Kernels (round 2; the round-1 kernels they replace
+// stay selectable through azn_nms_tune for A/B):
+//   1. n <= 2048: nms_rank_kernel -- every thread counts the detections that precede its own (score desc, index desc)
+//      among the keys staged in shared memory and moves its box to sorted position.
+//      n > 2048: nms_bucket_kernel + nms_bucket_rank_kernel -- one CTA spreads the keys over 2048 buckets that are linear
+//      in the uint key (histogram, scan, shared-memory-staged scatter), then every detection is ranked inside its own
+//      bucket only: the same exact order for a few dozen compares per box instead of n.
+//   2. nms_mask2_kernel  -- 64x64 tiles of the upper triangle -> one 64-bit suppression word per (row, column tile).
+//      A packed-half screen with directed rounding (two columns per instruction; intersection + area ratio; can only err
+//      towards "candidate") leaves ~3 % of the pairs, which the warp gathers into one list and evaluates 32 at a time
+//      with the exact float32 tests and the IEEE division of the reference.  Tiles of a diagonal super-block are also
+//      written transposed (sup_t) for the greedy pass.  (thresh <= 0: nms_mask_kernel, the float32 version.)
+//   3. nms_block_kernel  -- the greedy pass, blocked like a triangular solve: one PDL launch per super-tile of 1024 boxes.
+//      CTA 0: thread j owns row j and keeps in registers the 16 words that say which rows of the super-tile suppress it;
+//      the kept set K and the undecided set U live in shared memory and the 1024 rows are decided together in fixed-point
+//      rounds (a row with a kept suppressor is removed, a row with no undecided suppressor left is kept); kept original
+//      indices are appended to `keep` (on-device compaction; the count never visits the host) and the kept rows are pushed
+//      into the `removed` words of the next super-tile's columns.  The other CTAs of the launch push the kept rows of ALL
+//      EARLIER super-tiles into the NEXT super-tile's columns (left-looking bulk update, atomicOr).
+//      No CTA ever waits for another inside a launch.
 // Many small problems (azn_nms_batched, one per class per image in apply_nms,
 // lib/detect/test.py:467-484): one warp per problem, boxes in shared memory, the suppression
 // state in per-lane registers exchanged with ballots.
@@ -1152,7 +1154,7 @@ inline NmsWorkspace carve(void *ws, int64_t n, int col_tiles) {
 // Internal streams + events of azn_nms, one set per device, created on first use (never destroyed: process lifetime).
 // The greedy chain is a latency-bound single CTA; sharing its SM with the mask kernel's CTAs stretches it from ~17 to
 // ~27 us per super-tile (issue-slot contention), and that serial term bounds the whole call.  So the two run on
-// DISJOINT SM partitions when the driver offers green contexts (CUDA 12.4+): 8 SMs for the chain (CTA 0 + its bulk
+// DISJOINT SM partitions when the driver offers green contexts (CUDA 12.4+): 16 SMs for the chain (CTA 0 + its bulk
 // updaters), the rest for the mask.  Without them: one extra high-priority stream on the whole device.
 struct NmsStreams {
     cudaStream_t chain = nullptr;       // greedy pass
@@ -1160,6 +1162,7 @@ struct NmsStreams {
     cudaEvent_t done = nullptr, fork = nullptr, mask_done = nullptr;
     std::vector<cudaEvent_t> ev;
     bool tried = false;
+    int chain_sms = 8;                  // SMs of the chain's partition
 };
 
 template <typename Fn> Fn driver_fn(const char *name) {
@@ -1169,7 +1172,7 @@ template <typename Fn> Fn driver_fn(const char *name) {
     return (Fn)p;
 }
 
-// 8 SMs for the chain, the remaining SMs for the mask.  Returns false (and leaves ns untouched) when anything is missing.
+// 16 SMs for the chain, the remaining SMs for the mask.  Returns false (and leaves ns untouched) when anything is missing.
 bool make_partitions(int dev, NmsStreams &ns) {
     typedef CUresult (*GetRes)(CUdevice, CUdevResource *, CUdevResourceType);
     typedef CUresult (*Split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
@@ -1190,8 +1193,14 @@ bool make_partitions(int dev, NmsStreams &ns) {
     CUdevResource all, part, rest;
     if (get_res(cu_dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
     unsigned int groups = 1;
-    if (split(&part, &groups, &all, &rest, 0, 8) != CUDA_SUCCESS || groups != 1) return false;
+    // 16 SMs: CTA 0 + 15 bulk updaters.  The updaters read the whole upper triangle of the mask once (25 MB at N = 20 000) and
+    // 7 of them could not keep up with the block-wise resolver: measured 0.205-0.215 ms with 8 SMs, 0.170-0.179 with 12-24
+    // (the mask kernel loses the SMs the chain gets: 0.167-0.189 with 32)
+    int want = 16;
+    if (const char *e = getenv("AZN_NMS_CHAIN_SMS")) want = std::max(8, std::min(64, atoi(e)));
+    if (split(&part, &groups, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || groups != 1) return false;
     if (part.sm.smCount < 8 || rest.sm.smCount < 32) return false;
+    ns.chain_sms = (int)part.sm.smCount;
     CUdevResourceDesc d_chain, d_mask;
     if (gen(&d_chain, &part, 1) != CUDA_SUCCESS || gen(&d_mask, &rest, 1) != CUDA_SUCCESS) return false;
     CUgreenCtx g_chain, g_mask;
@@ -1378,7 +1387,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             // the updaters of launch si push the kept rows of super-tiles < si into the columns of super-tile si + 1
             const int upd_cols = min(SUPER, col_tiles - (si + 1) * SUPER);
             long updaters = (si == 0 || upd_cols <= 0) ? 0 : ((long)si * SUPER * upd_cols + 127) / 128;      // ~4 blocks per warp
-            const int upd_cap = ms != s ? 7 : SUPER_UPDATERS;         // partitioned: the chain owns 8 SMs -- CTA 0 keeps one to itself
+            const int upd_cap = ms != s ? ns->chain_sms - 1 : SUPER_UPDATERS;      // partitioned: CTA 0 keeps one SM of the chain's partition to itself
             if (updaters > upd_cap) updaters = upd_cap;
             if (g_nms_mode & 16)                               // A/B: the tile-by-tile pass
                 AZN_CUDA(azn_launch_pdl(nms_super_kernel, dim3(1 + (unsigned)updaters), dim3(SCAN_THREADS), smem, chain, (const u64 *)w.mask, (const u64 *)w.diag_t,
