@@ -616,7 +616,9 @@ __host__ __device__ __forceinline__ int band_row0(int k, int nb, int H, int rows
     return nb > 1 ? (int)(((long)k * (H - rows)) / (nb - 1)) : 0;
 }
 
-template <bool BF16, int SV>
+// EXT selects the experimental paths at compile time -- 0: none (the default kernel carries none of their code: with both
+// compiled in, the 64-register build spilled 80 bytes and ran 3 % slower), 1: width-grouped ROIs (1d), 2: row bands (1e).
+template <bool BF16, int SV, int EXT = 0>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
@@ -640,7 +642,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
     const int j = lane % SV, bsub = lane / SV;
     const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
     const int cells = H * W;
-    const bool banded = bp.ctab != nullptr;
+    const bool banded = EXT == 2 && bp.ctab != nullptr;
     const int SH = banded ? bp.rows : H;                    // map rows a CTA stages
     __shared__ long s_item;
     const long n_items = banded ? (long)bp.ctrl[1] * nslices : (long)n_buckets * nchunk * nslices;
@@ -666,7 +668,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         }
     };
     long prestaged = -1;
-    if (gdesc) {
+    if (EXT == 1 && gdesc) {
         // The map does not depend on the pre-pass: build the tables and stage the first item's slice while it runs.
         gp_build_tables(s_gp);
         const long item = blockIdx.x;
@@ -700,7 +702,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         const int img = banded ? bucket / bp.nb : bucket;                       // image of a real bucket
         const int row0 = banded && real ? band_row0(bucket % bp.nb, bp.nb, H, SH) : 0;   // first map row in shared memory
         // this chunk's share of the image's groups: every nchunk-th one, so that all chunks get the same mix of sizes
-        const int g_lo = gdesc && real ? goff[bucket] : 0, g_hi = gdesc && real ? goff[bucket + 1] : 0;
+        const int g_lo = EXT == 1 && gdesc && real ? goff[bucket] : 0, g_hi = EXT == 1 && gdesc && real ? goff[bucket + 1] : 0;
         const int n_grp = g_hi - g_lo > chunk ? (g_hi - g_lo - chunk + nchunk - 1) / nchunk : 0;
         if (hi <= lo && n_grp == 0) {
             if (prestaged == item) { cp_async_wait_all(); __syncthreads(); }     // nobody may still be writing the slice
@@ -873,7 +875,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         };
         // (1d) the image's groups, largest ROIs first (the pre-pass sorts by ascending width; a big group handed out last
         // would be the item's tail)
-        if (n_grp > 0) {
+        if (EXT == 1 && n_grp > 0) {
             // Work unit = one bin row of one group, handed out in order: the seven bin rows of a group are pooled by seven
             // warps at about the same time, and -- more important -- the CTAs of the other slices reach the same unit within
             // a few microseconds.  A pooled row of C channels is assembled in L2 from the 64-byte pieces of nslices CTAs; with
@@ -1384,13 +1386,13 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
             constexpr bool kBf16 = sizeof(typename Ops::tag) == 2;
             static bool attr8 = false;
             if (!attr8) {
-                AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BUDGET));
+                AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BUDGET));
                 attr8 = true;
             }
             BandPlan bp;
             bp.ctab = ctab; bp.ctrl = ctrl; bp.nb = nb; bp.rows = rows;
             const size_t smem8 = (size_t)rows * (W | 1) * 8 * 16;
-            roi_pool_keys_kernel<kBf16, 8><<<sms, ST_THREADS, smem8, s>>>((const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off1, perm1,
+            roi_pool_keys_kernel<kBf16, 8, 2><<<sms, ST_THREADS, smem8, s>>>((const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off1, perm1,
                                                                           scale, (uint4 *)out, n_img * nb + 1, 1, ns8, 2, nullptr, nullptr, bp);
             AZN_LAUNCH_CHECK();
             // the ROIs no band holds: the whole map at the slice width that fits, buckets = images (set 2 of the pre-pass);
@@ -1489,10 +1491,12 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         if (!attr_set) {                                                                                                 \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)ST_SMEM_BUDGET));                                                         \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)ST_SMEM_BUDGET));                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
         if (grouped)                                                                                                     \
-            AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV>, dim3(grid), dim3(ST_THREADS), smem, s,             \
+            AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV, 1>, dim3(grid), dim3(ST_THREADS), smem, s,          \
                                     (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale,          \
                                     (uint4 *)out, n_buckets, (int)nchunk, nslices, 2 + (g_pool_debug << 8), goff, gdesc, \
                                     no_bands));                                                                          \
