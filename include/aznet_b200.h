@@ -280,7 +280,12 @@ int azn_nms_batched(const float *dets, const int32_t *seg_off, int n_seg, double
  * [n_seg] on the device, every length <= max_len <= AZN_NMS_SEG_MAX (a longer segment reports keep_count -1).
  * This is how the batched detection step runs apply_nms over its [image, class, 100, 5] detections. */
 /* Diagnostic / tuning hook: 0 = default (mask and greedy chain pipelined on two streams / SM partitions), 1 = one
- * stream, mask then chain, 2 = stop after the mask, 3 = stop after the sort.  Used by tools/microbench.py --nms-phases. */
+ * stream, mask then chain, 2 = stop after the mask, 3 = stop after the sort.  Used by tools/microbench.py --nms-phases.
+ * A/B flags added to the mode, each selecting the round-1 kernel of one stage: + 8 all-pairs rank sort for every n (default:
+ * bucket sort above 2048 boxes), + 16 tile-by-tile greedy pass (default: block-wise fixed-point rounds), + 32 float32 mask
+ * kernel for every threshold (default: packed-half screen + exact evaluation for thresh > 0), + 64 one persistent launch for
+ * the whole greedy chain (measured slower than one launch per super-tile).  All variants return identical keep lists.
+ * A time-out of the persistent variant's spin-waits reports keep_count = -1 instead of hanging. */
 void azn_nms_tune(int mode);
 int azn_nms_segments(const float *dets, const int32_t *seg_off, const int32_t *seg_len, int n_seg, int max_len,
                      double thresh, int64_t *keep, int32_t *keep_count, azn_stream_t stream);
