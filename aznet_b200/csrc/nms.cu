@@ -16,8 +16,8 @@
 // green-context partition when the driver has them) and launch s polls the counters of super-columns s and s+1, so
 // the serial chain runs alongside the mask and ends ~25 us after it.  Kernels (round 2; the round-1 kernels they replace
 // stay selectable through azn_nms_tune for A/B):
-//   1. n <= 2048: nms_rank_kernel -- every thread counts the detections that precede its own (score desc, index desc)
-//      among the keys staged in shared memory and moves its box to sorted position.
+//   1. n <= 2048: nms_rank1_kernel -- eight threads count the detections that precede theirs (score desc, index desc)
+//      among the keys staged in shared memory; the box moves to sorted position.
 //      n > 2048: nms_bucket_kernel + nms_bucket_rank_kernel -- one CTA spreads the keys over 2048 buckets that are linear
 //      in the uint key (histogram, scan, shared-memory-staged scatter), then every detection is ranked inside its own
 //      bucket only: the same exact order for a few dozen compares per box instead of n.
@@ -147,6 +147,45 @@ nms_rank_kernel(const float *__restrict__ dets, int n, int *__restrict__ rank, f
         order[cnt] = i;
     } else if (cnt) {
         atomicAdd(rank + i, cnt);
+    }
+}
+
+// Single-tile problems (n <= RANK_TILE), round 2: the kernel above gives one thread all 2048 compares of its detection and
+// runs n / 256 = 8 CTAs -- 20 us at n = 2000, two fifths of the whole call.  Here eight threads share a detection (256 keys
+// each, four per 16-byte shared load, combined by shuffles) and a CTA takes 32 detections: 63 CTAs instead of 8, each thread a
+// few hundred instructions.  Same rule: j precedes i  <=>  key_j > key_i, or key_j == key_i and j > i.
+constexpr int RANK1_SUB = 8;                         // threads per detection
+constexpr int RANK1_DETS = RANK_THREADS / RANK1_SUB; // detections per CTA
+__global__ void __launch_bounds__(RANK_THREADS)
+nms_rank1_kernel(const float *__restrict__ dets, int n, float4 *__restrict__ boxes, float *__restrict__ areas, int *__restrict__ order,
+                 uint4 *__restrict__ zero, int n_zero) {
+    __shared__ __align__(16) unsigned s_key[RANK_TILE];
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < n_zero; k += RANK_THREADS) zero[k] = make_uint4(0u, 0u, 0u, 0u);      // see nms_rank_kernel
+    for (int k = threadIdx.x; k < RANK_TILE; k += RANK_THREADS) s_key[k] = k < n ? rank_key(dets[(size_t)k * 5 + 4]) : 0u;
+    __syncthreads();
+    const int det = blockIdx.x * RANK1_DETS + threadIdx.x / RANK1_SUB, sub = threadIdx.x % RANK1_SUB;
+    const int i = min(det, n - 1);                                // lanes past the end compute along (the shuffles need them)
+    const unsigned ki = s_key[i], kge = ki - 1u;                  // `a >= ki` is `a > ki - 1`; ki >= 1 for every real score
+    constexpr int PER = RANK_TILE / RANK1_SUB / 4;                // 16-byte groups per thread
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(s_key) + sub * PER;
+    const int j0 = sub * PER * 4;
+    int cnt = 0;
+#pragma unroll 8
+    for (int q = 0; q < PER; ++q) {
+        const uint4 v = s4[q];
+        const int j = j0 + 4 * q;                                 // elements j .. j + 3: `>` up to and including i itself, `>=` behind it
+        cnt += (v.x > (j <= i ? ki : kge)) + (v.y > (j + 1 <= i ? ki : kge)) + (v.z > (j + 2 <= i ? ki : kge)) + (v.w > (j + 3 <= i ? ki : kge));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+    if (sub == 0 && det < n) {
+        const float *d = dets + (size_t)det * 5;
+        const float4 b = make_float4(d[0], d[1], d[2], d[3]);
+        boxes[cnt] = b;
+        areas[cnt] = box_area(b.x, b.y, b.z, b.w);
+        order[cnt] = det;
     }
 }
 
@@ -937,19 +976,19 @@ __device__ __forceinline__ int super_col_tiles(int s, int col_tiles) {      // m
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_chain_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ sup_t, const int *__restrict__ order, int n, int col_tiles, int n_super,
                  u64 *__restrict__ removed, u64 *__restrict__ kept_bits, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count,
-                 const int *__restrict__ row_done, ChainCtl ctl) {
+                 const int *__restrict__ row_done, ChainCtl ctl, int n_res) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_ok, s_ok2;                                  // two flags: thread 0 may reach the second wait before a slow warp has read the first
-    if (blockIdx.x > 1) {
+    if ((int)blockIdx.x >= n_res) {
         // ---------------- bulk updaters: target super-column t gets the kept rows of super-tiles 0 .. t - 2
-        const int n_upd = gridDim.x - 2;
+        const int n_upd = gridDim.x - n_res;
         for (int t = 2; t < n_super; ++t) {
             const int c0 = t * SUPER, ncols = min(SUPER, col_tiles - c0);
             if (tid == 0) s_ok = chain_wait(ctl.done + (t - 2), 2, ctl.abort) && chain_wait(row_done + t, super_col_tiles(t, col_tiles), ctl.abort);
             __syncthreads();
             if (!s_ok) return;
             const long nblk = (long)(t - 1) * SUPER * ncols;
-            const long wid = (long)(blockIdx.x - 2) * (SCAN_THREADS / 32) + warp, nw = (long)n_upd * (SCAN_THREADS / 32);
+            const long wid = (long)(blockIdx.x - n_res) * (SCAN_THREADS / 32) + warp, nw = (long)n_upd * (SCAN_THREADS / 32);
             for (long k0 = wid; k0 < nblk; k0 += 4 * nw) {
                 ulonglong2 w[4];
                 u64 kb[4];
@@ -988,9 +1027,9 @@ nms_chain_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ sup_t, co
     extern __shared__ u64 s_nxt[];                               // [row tile][next column][64 rows]
     __shared__ u64 s_K[SUPER], s_U[SUPER], s_push[SUPER];
     __shared__ int s_pre[SUPER + 1];
-    const int n_upd = gridDim.x - 2;
+    const int n_upd = gridDim.x - n_res;
     const int c = tid >> 6, jj = tid & 63;
-    for (int s = blockIdx.x; s < n_super; s += 2) {
+    for (int s = blockIdx.x; s < n_super; s += n_res) {
         const int T0 = s * SUPER;
         const int nt = min(SUPER, col_tiles - T0);
         const int c0n = T0 + SUPER, ncols_next = max(0, min(SUPER, col_tiles - c0n));
@@ -1305,6 +1344,9 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         AZN_LAUNCH_CHECK();
         AZN_CUDA(azn_launch_pdl(nms_bucket_rank_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dets, (int)n, (const uint2 *)bpair,
                                 (const int *)boff, w.boxes, w.areas, w.order));
+    } else if (n <= RANK_TILE && !(g_nms_mode & 8)) {
+        nms_rank1_kernel<<<(unsigned)((n + RANK1_DETS - 1) / RANK1_DETS), RANK_THREADS, 0, s>>>(dets, (int)n, w.boxes, w.areas, w.order, zero, n_zero);
+        AZN_LAUNCH_CHECK();
     } else {
         if (n > RANK_TILE) AZN_CUDA(cudaMemsetAsync(w.rank, 0, sizeof(int) * (size_t)n, s));
         nms_rank_kernel<<<dim3((unsigned)((n + RANK_THREADS - 1) / RANK_THREADS), (unsigned)((n + RANK_TILE - 1) / RANK_TILE)),
@@ -1368,7 +1410,9 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
             nms_mask_kernel<<<(unsigned)((long)col_tiles * (col_tiles + 1) / 2), MASK_THREADS, 0, ms>>>(w.boxes, w.areas, (int)n, thresh, w.mask, col_tiles, 0,
                                                                                                      w.diag_t, w.row_done, w.sup_t);
         AZN_LAUNCH_CHECK();
-        if ((g_nms_mode & 64) && !(g_nms_mode & 16) && (g_nms_mode & 7) != 2) {       // A/B only: measured slower than one launch per super-tile
+        // The persistent chain, A/B only: measured slower than one launch per super-tile for long chains, and no faster for
+        // the one or two super-tiles of n <= 2048 (one resolver CTA, no hand-over at all: 0.045-0.051 vs 0.044-0.048 ms)
+        if ((g_nms_mode & 64) && !(g_nms_mode & 16) && (g_nms_mode & 7) != 2) {
             // the persistent chain: CTA 0 + up to 7 updaters (the chain's SM partition has 8 SMs; fewer when the columns are few)
             const long blocks = n_super > 2 ? ((long)(n_super - 2) * SUPER * SUPER + 127) / 128 : 0;
             const int upd = (int)std::min<long>(blocks, 6);
@@ -1379,8 +1423,9 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
                 AZN_CUDA(cudaFuncSetAttribute(nms_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 chain_attr = true;
             }
-            nms_chain_kernel<<<(n_super > 1 ? 2 : 1) + upd, SCAN_THREADS, smem, chain>>>((const u64 *)w.mask, (const u64 *)w.sup_t, (const int *)w.order, (int)n, col_tiles, n_super,
-                                                                    w.removed, w.kept_bits, keep, keep_count, (const int *)w.row_done, ctl);
+            const int n_res = n_super > 2 ? 2 : 1;
+            nms_chain_kernel<<<n_res + upd, SCAN_THREADS, smem, chain>>>((const u64 *)w.mask, (const u64 *)w.sup_t, (const int *)w.order, (int)n, col_tiles, n_super,
+                                                                    w.removed, w.kept_bits, keep, keep_count, (const int *)w.row_done, ctl, n_res);
             AZN_LAUNCH_CHECK();
         } else
         for (int si = 0; si < n_super && (g_nms_mode & 7) != 2; ++si) {

@@ -152,7 +152,7 @@ def nms(dets: torch.Tensor, thresh: float):
     assert dets.dtype == torch.float32 and dets.dim() == 2 and dets.shape[1] == 5 and dets.is_contiguous()
     n = dets.shape[0]
     keep = torch.empty(max(n, 1), dtype=torch.int64, device=dets.device)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dets.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=dets.device)          # always written by azn_nms (a memset when n == 0)
     nbytes = L.lib().azn_nms_workspace_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dets.device)
     L.check(L.lib().azn_nms(_ptr(dets), n, float(thresh), _ptr(keep), _ptr(cnt), _ptr(ws), nbytes, _stream()), "azn_nms")

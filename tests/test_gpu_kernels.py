@@ -231,6 +231,28 @@ def test_nms_large_matches_oracle(dev, O, n, th):
     assert keep[:int(cnt.item())].cpu().tolist() == O.nms(d, th)
 
 
+@pytest.mark.parametrize("n", [1, 31, 33, 255, 2047, 2048])
+def test_nms_small_sort_with_ties(dev, O, n):
+    """n <= 2048 sorts with eight threads per detection (nms_rank1_kernel): sizes around its group / CTA / tile borders,
+    many exact score ties and +-0, against the oracle and against the round-1 one-thread-per-detection kernel."""
+    from aznet_b200 import _lib, ops
+    d = synth.make_dets(n, seed=23 + n)
+    d[:, 4] = np.round(d[:, 4] * 16) / 16 - 0.25
+    d[::5, 4] = 0.0
+    d[2::5, 4] = -0.0
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    ref = O.nms(d, 0.45)
+    dt = torch.from_numpy(d).to(dev)
+    lib = _lib.lib()
+    try:
+        for mode in (0, 8):
+            lib.azn_nms_tune(mode)
+            keep, cnt = ops.nms(dt, 0.45)
+            assert keep[:int(cnt.item())].cpu().tolist() == ref, (n, mode)
+    finally:
+        lib.azn_nms_tune(0)
+
+
 def test_nms_ties_and_idempotence(dev, O):
     from aznet_b200 import ops
     d = synth.make_dets(600, seed=11)
