@@ -1415,7 +1415,7 @@ extern "C" int azn_nms(const float *dets, int64_t n, double thresh, int64_t *kee
         if ((g_nms_mode & 64) && !(g_nms_mode & 16) && (g_nms_mode & 7) != 2) {
             // the persistent chain: CTA 0 + up to 7 updaters (the chain's SM partition has 8 SMs; fewer when the columns are few)
             const long blocks = n_super > 2 ? ((long)(n_super - 2) * SUPER * SUPER + 127) / 128 : 0;
-            const int upd = (int)std::min<long>(blocks, 6);
+            const int upd = (int)std::min<long>(blocks, ms != s ? ns->chain_sms - 2 : SUPER_UPDATERS - 2);      // partitioned: what the chain's SMs hold
             ChainCtl ctl;
             ctl.done = w.ctl; ctl.upd = w.ctl + n_super; ctl.abort = w.ctl + 2 * n_super; ctl.nkept = w.nkept;
             static bool chain_attr = false;
