@@ -32,7 +32,7 @@ EXPORTS = [
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter", "azn_tune_threshold",
-    "azn_image_blob", "azn_conv3x3_forward", "azn_maxpool2x2_forward", "azn_nhwc_border", "azn_grn_concat_forward", "azn_roi_pool_grn_fwd", "azn_patches3x3", "azn_conv_patches_forward",
+    "azn_image_blob", "azn_conv3x3_forward", "azn_maxpool2x2_forward", "azn_nhwc_border", "azn_grn_concat_forward", "azn_roi_pool_grn_fwd", "azn_patches3x3", "azn_conv_patches_forward", "azn_conv3x3_direct_forward",
 ]
 
 
@@ -195,6 +195,8 @@ def _bind(L):
     L.azn_conv_patches_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]
     L.azn_patches3x3.restype = i32
     L.azn_patches3x3.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp]
+    L.azn_conv3x3_direct_forward.restype = i32
+    L.azn_conv3x3_direct_forward.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]
     L.azn_maxpool2x2_forward.restype = i32
     L.azn_maxpool2x2_forward.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.azn_nhwc_border.restype = i32

@@ -11,6 +11,8 @@ ceil-mode like Caffe (pooling_layer.cpp:93-95): 600x1000 -> 38x63.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -50,6 +52,7 @@ class VGG16Native:
         self.pixel_means = tuple(float(m) for m in pixel_means)
         self.layers, self.dims, self.names = [], [], []
         self.first_patches = False
+        self.first_direct = False
         c_in = None
         for s, (_, n) in enumerate(VGG16_CFG, 1):
             for i in range(1, n + 1):
@@ -68,6 +71,9 @@ class VGG16Native:
                 # the first layer with few input channels (3 -> 27 real K values): gathered patches, one 64-deep tap
                 if not self.layers:
                     self.first_patches = 9 * ci <= 64
+                    # ... and when the real K fits 32 and the layer has 64 filters (VGG16's conv1_1) even the patch matrix is
+                    # skipped: one mma.sync kernel straight from the network input (AZN_CONV1_PATCHES=1: the patches route, A/B)
+                    self.first_direct = 9 * ci <= 32 and cop == 64 and not os.environ.get("AZN_CONV1_PATCHES")     # (the input grid then has 8 channels)
                 if not self.layers and self.first_patches:
                     self.layers.append((ops.pack_patch_weight(Wp, 64), bp, i == n and s < 5))
                 else:
@@ -76,7 +82,7 @@ class VGG16Native:
         self.out_channels = c_in
         # network-input grid: 8 channels per pixel when the first layer runs on patches, else padded to the GEMM's 64
         self.cpad_in = 8 if self.first_patches else _pad64(self.in_channels)
-        self.launches_per_call = 1 + len(self.layers) + sum(1 for l in self.layers if l[2]) + int(self.first_patches)
+        self.launches_per_call = 1 + len(self.layers) + sum(1 for l in self.layers if l[2]) + int(self.first_patches and not self.first_direct)
 
     def flops(self, hs: int, ws: int) -> float:
         """Algorithmic FLOPs of conv1_1 .. conv5_3 for one hs x ws network input (real channel counts)."""
@@ -95,7 +101,9 @@ class VGG16Native:
         last = len(self.layers) - 1
         out = {}
         for k, (wt, b, pool) in enumerate(self.layers):
-            if k == 0 and self.first_patches:
+            if k == 0 and self.first_patches and self.first_direct and k != last:
+                x = ops.conv_direct(x, self.in_channels, wt, b, relu=True)
+            elif k == 0 and self.first_patches:
                 x = ops.conv_patches(ops.patches3x3(x, self.in_channels, 64), wt, b, relu=True, unpadded=(k == last))
             else:
                 x = ops.conv3x3(x, wt, b, relu=True, unpadded=(k == last))

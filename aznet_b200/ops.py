@@ -356,6 +356,22 @@ def patches3x3(x: torch.Tensor, cin: int, kp: int = 64, out: torch.Tensor | None
     return out
 
 
+def conv_direct(x: torch.Tensor, cin: int, wt: torch.Tensor, bias: torch.Tensor, relu: bool = True, out: torch.Tensor | None = None):
+    """The first 3x3 convolution in one kernel (azn_conv3x3_direct_forward): x zero-bordered [n, H+2, W+2, Cs] bf16 with
+    9 * cin <= 32, wt = pack_patch_weight(W) [64, Kp] -> zero-bordered [n, H+2, W+2, 64]."""
+    _need_cuda(x, wt, bias)
+    assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert x.is_contiguous() and wt.is_contiguous() and x.dim() == 4
+    n, hp, wp, cs = x.shape
+    cout, kp = wt.shape
+    if out is None:
+        out = torch.empty((n, hp, wp, cout), dtype=torch.bfloat16, device=x.device)
+    assert tuple(out.shape) == (n, hp, wp, cout) and out.is_contiguous() and out.dtype == torch.bfloat16
+    L.check(L.lib().azn_conv3x3_direct_forward(_ptr(x), n, hp - 2, wp - 2, cs, int(cin), _ptr(wt), kp, _ptr(bias), _ptr(out), cout,
+                                               int(relu), _stream()), "azn_conv3x3_direct_forward")
+    return out
+
+
 def pack_patch_weight(w: torch.Tensor, kp: int = 64):
     """Caffe conv weight [Cout, Cin, 3, 3] with 9*Cin <= kp -> bf16 [Cout, kp], column (ky*3+kx)*Cin + c, zero-padded."""
     co, ci, kh, kw = w.shape

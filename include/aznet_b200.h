@@ -379,6 +379,11 @@ int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *
  * Kp % 64 == 0 for the GEMM), and azn_conv_patches_forward runs the convolution as ONE tap: Wt bf16 [Cout, Kp]. */
 int azn_patches3x3(const void *in_padded, int n_img, int H, int W, int Cs, int Cin, void *out_padded, int Kp,
                    azn_stream_t stream);
+/* The same layer in ONE kernel without the patch matrix (9 * Cin <= 32, Cs == 8, Cout == 64: conv1_1 of VGG16, test.prototxt:16-31):
+ * warp-level mma.sync over 16-pixel tiles with the A fragments built straight from the network input; Wt bf16 [64, Kp] in the
+ * K order above (Kp >= 32), out the zero-bordered [n, H+2, W+2, 64] bf16 grid with bias and (relu != 0) ReLU applied. */
+int azn_conv3x3_direct_forward(const void *in_padded, int n_img, int H, int W, int Cs, int Cin, const void *wt, int Kp,
+                               const float *bias, void *out_padded, int Cout, int relu, azn_stream_t stream);
 int azn_conv_patches_forward(const void *Xp, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
                              int Kp, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
                              azn_stream_t stream);

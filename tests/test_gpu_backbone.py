@@ -146,6 +146,44 @@ def test_conv_patches_matches_fp32_convolution(dev, n, H, W, Cin, Cs, Cout, unpa
     assert bool((err <= tol).all()), (float(err.max()), float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("n,H,W,Cin,Cs,relu", [(2, 13, 17, 3, 8, True), (1, 30, 50, 3, 8, True), (3, 7, 5, 1, 8, False), (1, 480, 800, 3, 8, True),
+                                                (2, 11, 9, 2, 8, True)])
+def test_conv_direct_matches_fp32_convolution_and_the_patches_route(dev, n, H, W, Cin, Cs, relu):
+    """conv1_1 in one kernel (azn_conv3x3_direct_forward: mma.sync over 16-pixel tiles, A fragments straight from the
+    network input) against torch's fp32 convolution of the same bf16 operands -- the tolerance of the other conv tests --
+    with a zero border, tiles that straddle rows / images / the end of the grid, and within
+    one bf16 ulp of the patches route it replaces (same products, another summation order)."""
+    from aznet_b200 import ops
+    g = torch.Generator().manual_seed(n * 1000 + H * 10 + Cin)
+    x = torch.randn((n, H, W, Cin), generator=g).to(torch.bfloat16)
+    w = (torch.randn((64, Cin, 3, 3), generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(torch.bfloat16)
+    b = torch.randn((64,), generator=g) * 0.1
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    if relu:
+        ref = torch.relu(ref)
+    xs = torch.zeros((n, H + 2, W + 2, Cs), dtype=torch.bfloat16)
+    xs[:, 1:H + 1, 1:W + 1, :Cin] = x
+    xd = xs.to(dev).contiguous()
+    wt = ops.pack_patch_weight(w.float().to(dev), 64)
+    out = torch.full((n, H + 2, W + 2, 64), 5.0, dtype=torch.bfloat16, device=dev)
+    y = ops.conv_direct(xd, Cin, wt, b.to(dev), relu=relu, out=out)
+    torch.cuda.synchronize()
+    yb = y.float().cpu()
+    assert not yb[:, 0].any() and not yb[:, -1].any() and not yb[:, :, 0].any() and not yb[:, :, -1].any()
+    got = yb[:, 1:H + 1, 1:W + 1]
+    err = (got - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2e-3
+    assert bool((err <= tol).all()), (float(err.max()), float(ref.abs().max()))
+    if relu:
+        old = ops.conv_patches(ops.patches3x3(xd, Cin, 64), wt, b.to(dev), relu=True).float().cpu()
+        d = (old - yb).abs()
+        assert bool((d <= 2.0 ** -7 * yb.abs() + 1e-3).all()), float(d.max())
+    with pytest.raises(ValueError):
+        ops.conv_direct(torch.zeros((1, 6, 6, 8), dtype=torch.bfloat16, device=dev), 4, wt, b.to(dev))        # 9 * 4 > 32
+    with pytest.raises(ValueError):
+        ops.conv_direct(torch.zeros((1, 6, 6, 16), dtype=torch.bfloat16, device=dev), 3, wt, b.to(dev))       # 16 channels per pixel
+
+
 def test_conv3x3_argument_errors(dev):
     from aznet_b200 import ops
     x = torch.zeros((1, 6, 6, 32), dtype=torch.bfloat16, device=dev)

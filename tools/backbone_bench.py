@@ -47,7 +47,8 @@ def main():
     net = backbone.VGG16Native(w, dev)
     # two distinct batches so that no step finds its input in L2 (the maps themselves are far larger than L2)
     ims = [torch.from_numpy(np.stack(synth.make_images(args.batch, IM_H, IM_W, seed=1000 + 100 * s))).to(dev) for s in range(2)]
-    names = ["blob"] + (["patches"] if net.first_patches else [])
+    direct = net.first_patches and net.first_direct          # conv1_1 in one mma.sync kernel, no patch matrix
+    names = ["blob"] + (["patches"] if net.first_patches and not direct else [])
     for s, (_, n) in enumerate(backbone.VGG16_CFG, 1):
         for i in range(1, n + 1):
             names.append("conv%d_%d" % (s, i))
@@ -62,7 +63,9 @@ def main():
         ev[1].record()
         k, last = 1, len(net.layers) - 1
         for li, (wt, b, pool) in enumerate(net.layers):
-            if li == 0 and net.first_patches:
+            if li == 0 and direct:
+                x = ops.conv_direct(x, net.in_channels, wt, b, relu=True)
+            elif li == 0 and net.first_patches:
                 x = ops.patches3x3(x, net.in_channels, 64)
                 k += 1
                 ev[k].record()
