@@ -232,12 +232,16 @@ conv3x3_direct_kernel(const uint4 *__restrict__ in, int n_img, int H, int W, int
         // rows g and g + 8 of the tile = pixels tile * 16 + g (+ 8)
         bool interior[2];
         uint32_t fa[2][4];
+        // (row, column) of the tile's first pixel by two 32-bit divisions (the grid has < 2^31 pixels: host check); the 16
+        // pixels of the tile then wrap rows by subtraction -- 64-bit div / mod per pixel cost more than the 16 MMAs
+        const unsigned p0 = (unsigned)tile * 16u, wp = (unsigned)(W + 2), hp = (unsigned)(H + 2);
+        const unsigned row0 = p0 / wp, x0 = p0 - row0 * wp, y0 = row0 % hp;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const long px = tile * 16 + g + 8 * r;
-            const int xp = (int)(px % (W + 2));
-            const int yp = (int)((px / (W + 2)) % (H + 2));
-            interior[r] = px < total && xp >= 1 && xp <= W && yp >= 1 && yp <= H;
+            unsigned xp = x0 + (unsigned)(g + 8 * r), yp = y0;
+            while (xp >= wp) { xp -= wp; ++yp; }
+            if (yp >= hp) yp -= hp;                                   // the next image's grid
+            interior[r] = (long)p0 + g + 8 * r < total && xp >= 1u && xp <= (unsigned)W && yp >= 1u && yp <= (unsigned)H;
             const unsigned short *p = s_in[warp] + (g + 8 * r) * 8;
 #pragma unroll
             for (int u = 0; u < 2; ++u)
@@ -324,6 +328,7 @@ extern "C" int azn_conv3x3_direct_forward(const void *in_padded, int n_img, int 
                 "azn_conv3x3_direct_forward: needs 9*Cin <= 32, Kp >= 32, Cout == 64, 8 channels per input pixel (Cin=%d Kp=%d Cout=%d Cs=%d)",
                 Cin, Kp, Cout, Cs);
     AZN_REQUIRE((uintptr_t)out_padded % 16 == 0 && (uintptr_t)in_padded % 16 == 0, "azn_conv3x3_direct_forward: 16-byte alignment");
+    AZN_REQUIRE((double)n_img * (H + 2) * (W + 2) < 2.0e9, "azn_conv3x3_direct_forward: grid of more than 2e9 pixels");
     const long tiles = ((long)n_img * (H + 2) * (W + 2) + 15) / 16;
     const long want = (tiles + C1_WARPS - 1) / C1_WARPS, cap = (long)azn_num_sms() * 8;
     conv3x3_direct_kernel<<<(unsigned)(want < cap ? want : cap), C1_WARPS * 32, 0, (cudaStream_t)stream>>>(
