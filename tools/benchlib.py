@@ -179,7 +179,7 @@ class _Quiet:
         return self.cm.__exit__(*a)
 
 
-def entry_point_throughput(dev, az_head, cfg_dict, n_images=512, distinct=32, im_h=600, im_w=1000, zoom_fraction=0.4):
+def entry_point_throughput(dev, az_head, cfg_dict, n_images=1024, distinct=32, im_h=600, im_w=1000, zoom_fraction=0.4):
     """images/s THROUGH THE REFERENCE'S ENTRY POINT: aznet_b200.detect.test.test_proposals(net, imdb) on an in-memory
     synthetic imdb of uint8 images -- read-ahead, pinned staging, H2D of the pixels, device image blob, the VGG16
     backbone (hand-written conv kernels), the batched search, D2H of the lists, proposals.pkl.  Host wall clock around the
