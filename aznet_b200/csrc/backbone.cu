@@ -74,26 +74,32 @@ __device__ __forceinline__ unsigned pick_bf16x2(unsigned v, unsigned b) {
 }
 __global__ void __launch_bounds__(256)
 maxpool2x2_kernel(const uint4 *__restrict__ in, int n_img, int H, int W, int L, uint4 *__restrict__ out, int Ho, int Wo) {
-    const long total = (long)n_img * (Ho + 2) * (Wo + 2) * L;
-    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(g % L);
-        const long px = g / L;
-        const int xp = (int)(px % (Wo + 2));
-        const int yp = (int)((px / (Wo + 2)) % (Ho + 2));
-        const int n = (int)(px / ((long)(Wo + 2) * (Ho + 2)));
+    // 32-bit indexing (the host checks the sizes) and the four window loads issued together: a window cut by the edge
+    // (ceil mode, odd H or W) re-reads its last row / column -- the reduction is idempotent -- instead of looping over
+    // data-dependent bounds, which kept one load in flight per thread and spent more instructions on 64-bit div / mod than
+    // on the pooling (3.4 TB/s)
+    const unsigned total = (unsigned)n_img * (unsigned)(Ho + 2) * (unsigned)(Wo + 2) * (unsigned)L;
+    const unsigned wpo = (unsigned)(Wo + 2), hpo = (unsigned)(Ho + 2), uL = (unsigned)L;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        const unsigned px = g / uL, v = g - px * uL;
+        const unsigned row = px / wpo, xp = px - row * wpo;
+        const unsigned n = row / hpo, yp = row - n * hpo;
         uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-        if (xp >= 1 && xp <= Wo && yp >= 1 && yp <= Ho) {
-            const int hs = (yp - 1) * 2, ws = (xp - 1) * 2;
-            const int he = min(hs + 2, H), we = min(ws + 2, W);
+        if (xp >= 1u && xp <= (unsigned)Wo && yp >= 1u && yp <= (unsigned)Ho) {
+            const int hs = (int)(yp - 1u) * 2, ws = (int)(xp - 1u) * 2;
+            const int h1 = min(hs + 1, H - 1), w1 = min(ws + 1, W - 1);
+            const uint4 *r0 = in + ((size_t)(n * (unsigned)(H + 2) + (unsigned)hs + 1u) * (unsigned)(W + 2) + 1u) * uL + v;
+            const uint4 *r1 = in + ((size_t)(n * (unsigned)(H + 2) + (unsigned)h1 + 1u) * (unsigned)(W + 2) + 1u) * uL + v;
+            const uint4 q00 = __ldg(r0 + (size_t)ws * uL), q01 = __ldg(r0 + (size_t)w1 * uL);
+            const uint4 q10 = __ldg(r1 + (size_t)ws * uL), q11 = __ldg(r1 + (size_t)w1 * uL);
             acc = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);       // bf16(-FLT_MAX) = -inf
-            for (int h = hs; h < he; ++h)
-                for (int w = ws; w < we; ++w) {
-                    const uint4 q = __ldg(in + (((size_t)n * (H + 2) + h + 1) * (W + 2) + w + 1) * L + v);
-                    acc.x = pick_bf16x2(q.x, acc.x); acc.y = pick_bf16x2(q.y, acc.y);
-                    acc.z = pick_bf16x2(q.z, acc.z); acc.w = pick_bf16x2(q.w, acc.w);
-                }
+            // the reference's scan order: (hs, ws), (hs, ws+1), (hs+1, ws), (hs+1, ws+1), `v > best ? v : best`
+            acc.x = pick_bf16x2(q00.x, acc.x); acc.y = pick_bf16x2(q00.y, acc.y); acc.z = pick_bf16x2(q00.z, acc.z); acc.w = pick_bf16x2(q00.w, acc.w);
+            acc.x = pick_bf16x2(q01.x, acc.x); acc.y = pick_bf16x2(q01.y, acc.y); acc.z = pick_bf16x2(q01.z, acc.z); acc.w = pick_bf16x2(q01.w, acc.w);
+            acc.x = pick_bf16x2(q10.x, acc.x); acc.y = pick_bf16x2(q10.y, acc.y); acc.z = pick_bf16x2(q10.z, acc.z); acc.w = pick_bf16x2(q10.w, acc.w);
+            acc.x = pick_bf16x2(q11.x, acc.x); acc.y = pick_bf16x2(q11.y, acc.y); acc.z = pick_bf16x2(q11.z, acc.z); acc.w = pick_bf16x2(q11.w, acc.w);
         }
-        out[(size_t)px * L + v] = acc;
+        out[(size_t)g] = acc;
     }
 }
 
@@ -343,6 +349,7 @@ extern "C" int azn_maxpool2x2_forward(const void *in_padded, int n_img, int H, i
     AZN_REQUIRE(n_img > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "azn_maxpool2x2_forward: bad shape (C must be a multiple of 8)");
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;         // ceil((H - 2) / 2) + 1
     const long total = (long)n_img * (Ho + 2) * (Wo + 2) * (C / 8);
+    AZN_REQUIRE(total < (1L << 31) && (long)n_img * (H + 2) * (W + 2) < (1L << 31), "azn_maxpool2x2_forward: map too large for 32-bit indexing");
     maxpool2x2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in_padded, n_img, H, W, C / 8,
                                                                         (uint4 *)out_padded, Ho, Wo);
     AZN_LAUNCH_CHECK();
