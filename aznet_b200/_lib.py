@@ -29,6 +29,7 @@ LEVEL_LAST, LEVEL_ROOT_PROPS, LEVEL_TUNE = 1, 2, 4
 EXPORTS = [
     "azn_version", "azn_last_error", "azn_check_device", "azn_set_pdl", "azn_set_coop", "azn_hbm_write_probe", "azn_roi_pool_workspace_bytes", "azn_roi_pool_tune", "azn_roi_pool_fwd", "azn_roi_pool_fwd_ex", "azn_nchw_f32_to_nhwc_bf16", "azn_nchw_bf16_to_nhwc_bf16", "azn_host_f32_to_bf16", "azn_host_threads",
     "azn_fc_workspace_bytes", "azn_fc_tune", "azn_fc_trace", "azn_fc_forward", "azn_az_heads_forward", "azn_az_heads_tune", "azn_search_init", "azn_search_root", "azn_search_level", "azn_select_proposals", "azn_collect_proposals",
+    "azn_peer_alloc", "azn_peer_open", "azn_peer_close", "azn_peer_free",
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter", "azn_tune_threshold",
@@ -157,6 +158,14 @@ def _bind(L):
     L.azn_select_proposals.argtypes = [C.POINTER(SearchState), i32, i32, f64, vp, vp, vp, i32, vp]
     L.azn_collect_proposals.restype = i32
     L.azn_collect_proposals.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]
+    L.azn_peer_alloc.restype = i32
+    L.azn_peer_alloc.argtypes = [sz, C.POINTER(C.c_void_p), C.c_char_p]
+    L.azn_peer_open.restype = i32
+    L.azn_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.azn_peer_close.restype = i32
+    L.azn_peer_close.argtypes = [vp]
+    L.azn_peer_free.restype = i32
+    L.azn_peer_free.argtypes = [vp]
     L.azn_divide_region.restype = i32
     L.azn_divide_region.argtypes = [vp, i32, f64, vp, vp, i32, i32, vp, sz, vp]
     L.azn_divide_region_scratch_bytes.restype = sz

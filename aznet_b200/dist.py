@@ -50,6 +50,81 @@ def gather_proposals(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Te
     return tuple(outs)
 
 
+class _RawCuda:
+    """A device pointer dressed up for torch.as_tensor (CUDA array interface, version 2)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerWindow:
+    """`world` regions of `nbytes` bytes in the device memory of rank `root`, mapped into every other rank's process
+    (libaznet_b200: azn_peer_alloc / azn_peer_open, CUDA IPC with peer access over NVLink).  Rank r appends its
+    proposal lists by storing through `rank_ptr(r)` -- the last kernel of its search step does it, inside the CUDA
+    graph -- so the job's exchange overlaps the search batch by batch and costs no collective kernel; `fence()` at the
+    end is the only synchronisation.  This is the "gather of per-image proposal lists at the end" of test_proposals
+    (one proposals.pkl written by one process, lib/detect/test.py:533-539) with the copy moved off the critical path.
+    Construction is collective and all-or-nothing: if any rank cannot map the window every rank raises RuntimeError
+    (the caller then keeps the all_gather route)."""
+
+    def __init__(self, nbytes: int, device, root: int = 0):
+        import ctypes as C
+        from . import _lib as L
+        self.rank, self.world, self.root = dist.get_rank(), dist.get_world_size(), int(root)
+        self.per = (int(nbytes) + 255) // 256 * 256
+        self.device = torch.device(device)
+        self.base, self._owner, err = 0, self.rank == self.root, ""
+        handle = [None]
+        if self._owner:
+            ptr, hbuf = C.c_void_p(), C.create_string_buffer(64)
+            rc = L.lib().azn_peer_alloc(self.per * self.world, C.byref(ptr), hbuf)
+            if rc == 0:
+                self.base, handle[0] = int(ptr.value), hbuf.raw
+            else:
+                err = L.lib().azn_last_error().decode()
+        dist.broadcast_object_list(handle, src=self.root)
+        if not self._owner and handle[0] is not None:
+            ptr = C.c_void_p()
+            rc = L.lib().azn_peer_open(handle[0], C.byref(ptr))
+            if rc == 0:
+                self.base = int(ptr.value)
+            else:
+                err = L.lib().azn_last_error().decode()
+        oks = [None] * self.world
+        dist.all_gather_object(oks, (self.base != 0, err))
+        if not all(o[0] for o in oks):
+            self.close()
+            raise RuntimeError("peer window unavailable: " + "; ".join("rank %d: %s" % (r, o[1] or "no handle") for r, o in enumerate(oks) if not o[0]))
+        self._nccl = dist.get_backend() == "nccl"
+        self._tok = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._tensor = None
+
+    def rank_ptr(self, r: int | None = None) -> int:
+        return self.base + (self.rank if r is None else int(r)) * self.per
+
+    def tensor(self) -> torch.Tensor:
+        """uint8 [world, per] view of the whole window (every rank can read it; rank `root` reads local memory)."""
+        if self._tensor is None:
+            self._tensor = torch.as_tensor(_RawCuda(self.base, self.per * self.world), device=self.device).view(self.world, self.per)
+        return self._tensor
+
+    def fence(self):
+        """Every rank's stores through the window (stream-ordered before this call) are visible to every rank's work
+        enqueued after it.  NCCL: one 4-byte all_reduce on the current stream (no host synchronisation)."""
+        if self._nccl:
+            dist.all_reduce(self._tok)
+        else:
+            torch.cuda.synchronize(self.device)
+            dist.barrier()
+
+    def close(self):
+        from . import _lib as L
+        if self.base:
+            self._tensor = None
+            (L.lib().azn_peer_free if self._owner else L.lib().azn_peer_close)(self.base)
+            self.base = 0
+
+
 class ProposalCollector:
     """Per-rank accumulation of the proposal lists of a run of batches, gathered ONCE at the end -- the way
     test_proposals appends per image and writes one proposals.pkl after the loop (lib/detect/test.py:508-539).
@@ -71,10 +146,21 @@ class ProposalCollector:
         self.boxes, self.scores, self.counts = views
         self._sizes = sizes
         self._gathered = None
+        self._dst = tuple(v.data_ptr() for v in views)                            # where device_add writes
+        self._remote = False
         self.state = torch.zeros(2, dtype=torch.int32, device=boxes.device)      # device-side batch counter
 
     def reset(self):
         self.state.zero_()
+
+    def redirect(self, base_ptr: int):
+        """device_add writes its slots at `base_ptr` (same packing as the local buffer) instead -- a region of a
+        PeerWindow: the append lands in the collecting rank's memory."""
+        off, dst = 0, []
+        for sz in self._sizes:
+            dst.append(int(base_ptr) + off)
+            off += sz
+        self._dst, self._remote = tuple(dst), True
 
     def device_add(self, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
         """One kernel launch (azn_collect_proposals) whose slot comes from the device-side counter: the launch is
@@ -82,11 +168,13 @@ class ProposalCollector:
         from . import _lib as L
         n_img, cap = int(boxes.shape[0]), int(boxes.shape[1])
         L.check(L.lib().azn_collect_proposals(boxes.data_ptr(), scores.data_ptr(), counts.data_ptr(), n_img, cap,
-                                              self.boxes.data_ptr(), self.scores.data_ptr(), self.counts.data_ptr(),
+                                              self._dst[0], self._dst[1], self._dst[2],
                                               self.n_batches, self.state.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream), "azn_collect_proposals")
 
     def add(self, i: int, boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor):
+        if self._remote:
+            raise RuntimeError("ProposalCollector.add: the collection lives in a peer window; use device_add")
         j = i % self.n_batches
         self.boxes[j].copy_(boxes, non_blocking=True)
         self.scores[j].copy_(scores, non_blocking=True)
@@ -126,8 +214,11 @@ class CollectorGroup:
     def nbytes(n_batches, boxes, scores, counts):
         return sum(int(n_batches) * t.numel() * t.element_size() for t in (boxes, scores, counts))
 
-    def __init__(self, n_batches: int, outputs):
-        """outputs: per engine its (out_boxes, out_scores, out_count) tensors (identical shapes)."""
+    def __init__(self, n_batches: int, outputs, peer: bool = False):
+        """outputs: per engine its (out_boxes, out_scores, out_count) tensors (identical shapes).
+        peer=True (multi-rank, one box): the collection lives in a PeerWindow of rank 0 and every engine's
+        azn_collect_proposals appends through it; `gather()` is then a fence, not a transfer.  Raises RuntimeError
+        on every rank when the window cannot be set up."""
         outputs = list(outputs)
         per = self.nbytes(n_batches, *outputs[0])
         per_al = (per + 255) // 256 * 256
@@ -135,6 +226,11 @@ class CollectorGroup:
         self._buf = torch.zeros(per_al * len(outputs), dtype=torch.uint8, device=outputs[0][0].device)
         self.collectors = [ProposalCollector(n_batches, *o, storage=self._buf[k * per_al:k * per_al + per]) for k, o in enumerate(outputs)]
         self._gathered = None
+        self.window = None
+        if peer and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.window = PeerWindow(self._buf.numel(), self._buf.device)
+            for k, c in enumerate(self.collectors):
+                c.redirect(self.window.rank_ptr() + k * per_al)
 
     def reset(self):
         for c in self.collectors:
@@ -144,9 +240,13 @@ class CollectorGroup:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return [c.gather(views=True) for c in self.collectors]
         world = dist.get_world_size()
-        if self._gathered is None:
-            self._gathered = torch.empty((world, self._buf.numel()), dtype=torch.uint8, device=self._buf.device)
-        dist.all_gather_into_tensor(self._gathered.view(-1), self._buf)
+        if self.window is not None:
+            self.window.fence()                               # the lists are already in rank 0's memory
+            self._gathered = self.window.tensor()
+        else:
+            if self._gathered is None:
+                self._gathered = torch.empty((world, self._buf.numel()), dtype=torch.uint8, device=self._buf.device)
+            dist.all_gather_into_tensor(self._gathered.view(-1), self._buf)
         out = []
         for k, c in enumerate(self.collectors):
             base, off, views = k * self._per_al, 0, []

@@ -362,6 +362,10 @@ def main():
     ap.add_argument("--host-narrow", default="auto", choices=("auto", "on", "off"),
                     help="e2e call: round the f32 host maps to bf16 on the host cores before the upload (auto: time both routes on the first batch)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra / e2e_entry / parity blocks (they run outside the timed regions)")
+    ap.add_argument("--gather", default="peer", choices=("peer", "nccl"),
+                    help="N > 1: how the ranks' proposal lists reach rank 0 -- peer: every step's lists are stored into a window of "
+                         "rank 0's memory over NVLink by the step's last kernel, the job ends with a 4-byte all_reduce; nccl: one "
+                         "all_gather of all lists at the end (round 1; also the fallback when the window cannot be mapped)")
     ap.add_argument("--job", type=int, default=0, help="strong-scaling mode (BASELINE config #5): a job of this many images "
                     "(a multiple of 64) sharded over the ranks in batches of 64; --steps is ignored")
     args = ap.parse_args()
@@ -416,7 +420,17 @@ def main():
     engines = [eng] + [engine.SearchEngine(head, BATCH, IM_H, IM_W, **CFG) for _ in range(n_streams - 1)]
     side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else []
     slots = (max(args.steps, args.warmup, 2) + n_streams - 1) // n_streams
-    group = CollectorGroup(slots, [(e.out_boxes, e.out_scores, e.out_count) for e in engines]) if world > 1 else None
+    group, gather_route = None, None
+    if world > 1:
+        outs = [(e.out_boxes, e.out_scores, e.out_count) for e in engines]
+        if args.gather == "peer":
+            try:
+                group, gather_route = CollectorGroup(slots, outs, peer=True), "peer"
+            except RuntimeError as e:                 # collective decision: every rank raises or none does
+                if rank == 0:
+                    print("bench: %s -- falling back to the NCCL all_gather" % e, file=sys.stderr)
+        if group is None:
+            group, gather_route = CollectorGroup(slots, outs), "nccl"
     collectors = group.collectors if group else []
     collector = collectors[0] if collectors else None
     # the copy into the collection is the last kernel of the search (azn_collect_proposals, slot from a device-side
@@ -511,8 +525,10 @@ def main():
         eg = torch.cuda.Event(enable_timing=True)
         eg.record()
         if world > 1:
-            if step_fn is step_resident and not profile:
-                gathered[:] = group.gather()          # the job's only exchange: ONE all_gather of all ranks' proposal lists
+            if gather_route == "peer" or (step_fn is step_resident and not profile):
+                # the job's only exchange.  peer: the lists already sit in rank 0's window (every step's last kernel stored
+                # them there), this is the closing fence; nccl: ONE all_gather of all ranks' proposal lists
+                gathered[:] = group.gather()
             else:
                 gathered[:] = [collector.gather(views=True)]
         e1.record()
@@ -594,7 +610,11 @@ def main():
                        "l2": "working set per step (216 MB bf16 weights + pooled rows) exceeds the 126 MB L2; inputs rotate over 2 distinct batches",
                        "launch": "eager" if args.no_graph else "CUDA graph replay of the whole level loop (static launch sequence, device-side counts), "
                                  "%d batch(es) in flight on %d stream(s); roofline events from a second, host-launched, single-stream pass over the same steps" % (n_streams, n_streams),
-                       "parallelism": "image-sharded x%d, no collective on the hot path; one NCCL all_gather of all K steps' proposal lists at the end, inside the timed region" % world},
+                       "parallelism": "image-sharded x%d, no collective on the hot path; %s" % (world, {
+                           None: "single rank",
+                           "peer": "every step's proposal lists are appended to rank 0's collection through a peer window (stores over NVLink by the "
+                                   "step's last kernel, azn_collect_proposals); the job ends with one 4-byte NCCL all_reduce as the fence, inside the timed region",
+                           "nccl": "one NCCL all_gather of all K steps' proposal lists at the end, inside the timed region"}[gather_route])},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
@@ -619,10 +639,10 @@ def main():
                          "per_level": prof["levels"], "hbm_peak_gbs": hbm_peak},
         }
         if args.job:
-            line["config"]["job"] = "BASELINE config #5: %d images = %d batches of 64, %d per rank; one NCCL all_gather of the lists at the end" % (
-                args.job, args.job // BATCH, args.steps)
+            line["config"]["job"] = "BASELINE config #5: %d images = %d batches of 64, %d per rank; lists -> rank 0: %s" % (
+                args.job, args.job // BATCH, args.steps, "peer window + closing fence" if gather_route == "peer" else "one NCCL all_gather at the end")
         if world > 1:
-            line["gather_ms"] = {"resident": gather_resident_ms, "e2e": gather_ms[0],
+            line["gather_ms"] = {"route": gather_route, "resident": gather_resident_ms, "e2e": gather_ms[0],
                                  "bytes_per_rank": int(sum(t.numel() * t.element_size() for c in collectors for t in (c.boxes, c.scores, c.counts)))}
         threads = os.cpu_count() or 1
         runner = None

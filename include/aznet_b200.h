@@ -247,6 +247,19 @@ int azn_collect_proposals(const double *out_boxes, const float *out_scores, cons
                           int cap_out, double *dst_boxes, float *dst_scores, int32_t *dst_counts, int n_slots,
                           uint32_t *state, azn_stream_t stream);
 
+/* Peer window: device memory of the collecting rank (rank 0 writes proposals.pkl, lib/detect/test.py:533-539)
+ * mapped into the other ranks' processes on the same box, so that azn_collect_proposals of rank r appends its
+ * lists with ordinary stores over NVLink (dst_* = window pointers) -- replaces the end-of-job NCCL gather of
+ * round 1 (no collective kernel, no SMs taken from the cooperative GEMMs); the job ends with one barrier.
+ *   azn_peer_alloc: cudaMalloc + zero-fill + cudaIpcGetMemHandle -> *ptr, 64 opaque handle bytes (HOST buffer)
+ *                   that the host side passes to the other processes (aznet_b200/dist.py: object broadcast).
+ *   azn_peer_open:  cudaIpcOpenMemHandle (peer access enabled lazily) in ANOTHER process -> *ptr (device pointer
+ *                   valid in the calling process); azn_peer_close unmaps it, azn_peer_free releases the owner's. */
+int azn_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int azn_peer_open(const unsigned char *handle64, void **ptr);
+int azn_peer_close(void *ptr);
+int azn_peer_free(void *ptr);
+
 /* Stand-alone pieces of the level kernel, exposed with the reference's own signatures.
  * azn_divide_region replaces utils.cython_div.divide_region / _sift_dup for ONE region set
  * (lib/utils/div.pyx:15-88): regions f64 [n,4] -> out f64 [cap_out,4], out_count[1]. */
