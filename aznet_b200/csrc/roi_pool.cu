@@ -428,6 +428,66 @@ __device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbas
 #undef AZN_MX3
 }
 
+// Variant 3 of the keys kernel: fixed-height column reduces over a TWO-LEVEL map.  Behind the slice the CTA keeps a
+// second table, pair[p][w] = max(map[2p][w], map[2p+1][w]) (half the slice again: 38x63 cells x 64 bytes + 19x63 x 64
+// = 229 824 of the 232 448 bytes a CTA may have), and a bin's rows [hs, he) are covered by at most one odd single row
+// in front, the aligned pairs inside and one even single row behind: 1 / 2 / 2 / 3 / 3 / 4 shared-memory loads per
+// (bin row, map column) for bins of 1 .. 6 rows instead of 1 .. 6 -- max is associative and idempotent, so the result
+// is the same bit pattern.  The big ROIs are where the loads are (a tenth of the microbench's boxes, half of the
+// reads), and they are the ones with 4-6 rows per bin.  ME = the warp-wide maximum entry count; a lane with fewer
+// entries cycles through its own (as in pool_bins_fixed).  `base` = the slice at this lane's channel vector,
+// `pair_off` = offset of the pair table in uint4 units (a multiple of 2 cells: bank parity = row + column there too).
+template <typename K, int ME, bool PLAIN>
+__device__ __forceinline__ void pool_bins_pairs(const uint4 *__restrict__ base, int hs, int nh, int rot, int row_step, int pair_off, int sv,
+                                                unsigned gb, bool phv, bool valid, uint4 *__restrict__ optr, int L) {
+#define AZN_MX2(D, A) \
+    (D).x = K::max3((D).x, (A).x, (A).x); (D).y = K::max3((D).y, (A).y, (A).y); (D).z = K::max3((D).z, (A).z, (A).z); (D).w = K::max3((D).w, (A).w, (A).w)
+#define AZN_MX3(D, A, B) \
+    (D).x = K::max3((D).x, (A).x, (B).x); (D).y = K::max3((D).y, (A).y, (B).y); (D).z = K::max3((D).z, (A).z, (B).z); (D).w = K::max3((D).w, (A).w, (B).w)
+    const int he = hs + max(nh, 1);
+    const int odd_s = hs & 1, odd_e = he & 1;
+    const int np = (he - odd_e - hs - odd_s) >> 1;           // aligned pairs inside (>= 0 for nh >= 1)
+    const int ne = odd_s + np + odd_e;                       // entries of this lane: 1 .. ME
+    const int off_s = hs * row_step, off_e = (he - 1) * row_step;
+    const int off_p = pair_off + (((hs + odd_s) >> 1) - odd_s) * row_step;     // + idx * row_step for entry idx in [odd_s, odd_s + np)
+    int eoff[ME];
+    int idx = rot < ne ? rot : 0;
+#pragma unroll
+    for (int t = 0; t < ME; ++t) {
+        eoff[t] = idx < odd_s ? off_s : (idx < odd_s + np ? off_p + idx * row_step : off_e);
+        idx = idx + 1 < ne ? idx + 1 : 0;
+    }
+    const unsigned a0 = PLAIN ? 0u : K::lowest();
+    int w_cached = -1;                                       // warp-uniform
+    uint4 cache = make_uint4(a0, a0, a0, a0);
+#pragma unroll
+    for (int pw = 0; pw < ST_P; ++pw) {
+        const unsigned wb = __shfl_sync(0xffffffffu, gb, ST_P + pw);
+        const int ws = wb & 0xffff, we = (int)(wb >> 16);    // warp-uniform
+        uint4 acc = make_uint4(a0, a0, a0, a0);
+        if (we > ws) {
+            int w = ws;
+            if (w == w_cached) { acc = cache; ++w; }         // the previous bin's last column, already reduced
+#pragma unroll 1
+            for (; w < we; ++w) {
+                const uint4 *q = base + w * sv;
+                uint4 c = q[eoff[0]];
+                if (ME == 2) { const uint4 b = q[eoff[1]]; AZN_MX2(c, b); }
+                if (ME >= 3) { const uint4 b = q[eoff[1]], d = q[eoff[2]]; AZN_MX3(c, b, d); }
+                if (ME == 4) { const uint4 b = q[eoff[3]]; AZN_MX2(c, b); }
+                AZN_MX2(acc, c);
+                cache = c;
+            }
+            w_cached = we - 1;
+        }
+        uint4 res = make_uint4(0u, 0u, 0u, 0u);
+        if (we > ws && valid) res = PLAIN ? acc : make_uint4(K::from_key(acc.x), K::from_key(acc.y), K::from_key(acc.z), K::from_key(acc.w));
+        if (phv) st_stream(optr + (size_t)pw * L, res);
+    }
+#undef AZN_MX2
+#undef AZN_MX3
+}
+
 // ---- (1d) grouped pooling: one warp = 32/SV ROIs of the SAME width in map cells -----------------------------------
 // The per-ROI loop nest above spends ~630 warp instructions per ROI-slice of which ~140 are loads, maxima and stores:
 // every lane recomputes the ROI geometry (16 times per ROI, once per slice), a warp walks ONE ROI with its lanes on the
@@ -755,6 +815,19 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
             cp_async_wait_all();
             __syncthreads();
         }
+        // variant 3: the pair table behind the slice (see pool_bins_pairs); rows 2p, 2p+1 of the staged (key) slice
+        const bool pairs = EXT == 0 && (variant & 0x10000) != 0 && !exact && real;
+        const int pair_off = ((cells_p + 1) & ~1) * SV;       // uint4 units
+        if (pairs) {
+            const int n_pv = (SH >> 1) * row_step;
+            uint4 *s_pair = s_map + pair_off;
+            for (int i = threadIdx.x; i < n_pv; i += ST_THREADS) {
+                const int pr = i / row_step, rem = i - pr * row_step;
+                const uint4 a = s_map[2 * pr * row_step + rem], b = s_map[(2 * pr + 1) * row_step + rem];
+                s_pair[i] = make_uint4(K::max3(a.x, b.x, b.x), K::max3(a.y, b.y, b.y), K::max3(a.z, b.z, b.z), K::max3(a.w, b.w, b.w));
+            }
+            __syncthreads();
+        }
 #ifdef AZN_POOL_TRACE
         const long long t3 = clock64();
 #endif
@@ -780,6 +853,27 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 const unsigned hb = __shfl_sync(0xffffffffu, gb, min(ph, ST_P - 1));
                 const int hs = hb & 0xffff, nh = phv ? (int)(hb >> 16) - hs : 0;
                 uint4 *optr = out + ((size_t)r * ST_BINS + (size_t)min(ph, ST_P - 1) * ST_P) * L + c0v + j;
+                if (pairs && mh <= 6) {                              // warp-uniform: two-level map, <= 4 loads per (bin row, column)
+                    const int nh_rows = (int)(hb >> 16) - hs;
+                    const int hs_c = min(max(hs - row0, 0), SH - 1), nh_c = max(min(nh_rows, SH - hs_c), 1);
+                    const int he_c = hs_c + nh_c;
+                    const int ne_l = (hs_c & 1) + (he_c & 1) + ((he_c - (he_c & 1) - hs_c - (hs_c & 1)) >> 1);
+                    const int me = __reduce_max_sync(0xffffffffu, ph < ST_P ? ne_l : 1);
+                    const int rot = 0;
+#define AZN_PAIR(MEE)                                                                                                     \
+    do {                                                                                                                  \
+        if (plain) pool_bins_pairs<K, MEE, true>(s_map + j, hs_c, nh_c, rot, row_step, pair_off, SV, gb, phv, nh > 0, optr, L);   \
+        else pool_bins_pairs<K, MEE, false>(s_map + j, hs_c, nh_c, rot, row_step, pair_off, SV, gb, phv, nh > 0, optr, L);        \
+    } while (0)
+                    switch (me) {
+                    case 0: case 1: AZN_PAIR(1); break;
+                    case 2: AZN_PAIR(2); break;
+                    case 3: AZN_PAIR(3); break;
+                    default: AZN_PAIR(4); break;
+                    }
+#undef AZN_PAIR
+                    continue;
+                }
                 if ((variant & 255) == 2 && !exact && mh <= 6) {     // warp-uniform: fixed-height straight-line column reduces
                     const uint4 *rb = s_map + (size_t)min(max(hs - row0, 0), SH - 1) * row_step + j;
                     // partner = the other bin row of this lane's quarter-warp (lanes 4k..4k+7 hold bin rows 2k', 2k'+1
@@ -1331,6 +1425,7 @@ int g_pool_variant = 2;        // keys kernel: 1 generic loop nest, 2 fixed-heig
                                // (profiles/README.md, negative results of round 2)
 
 constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the staged kernel may ask for
+constexpr size_t ST_SMEM_MAX = 227 * 1024 - 256;   // ... the default keys kernel with its pair table (its static shared memory is < 64 bytes)
 
 // Staged-kernel launch (see roi_pool_staged_kernel).  `nhwc` is the channels-last map; returns AZN_OK after a
 // launch, or 1 when the configuration is outside the staged kernel's domain (caller takes the direct kernel).
@@ -1343,7 +1438,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     for (int cand = (MODE == 0 ? 8 : 4); cand >= 2; cand >>= 1) {
         const size_t map_bytes = cells * cand * 16;
         if (map_bytes > ST_SMEM_BUDGET) continue;
-        if (MODE == 0 && g_pool_debug == 2 && cand == 8) continue;       // A/B: 64-byte slices where 128-byte ones would fit
+        if (MODE == 0 && (g_pool_debug == 2 || g_pool_debug == 6) && cand == 8) continue;   // A/B: 64-byte slices where 128-byte ones would fit
         if (MODE != 0) {
             const size_t per = (size_t)cand * 4 * ST_BINS * 4 * (MODE == 2 ? 2 : 1);
             const size_t fit = (ST_SMEM_BUDGET - map_bytes) / per;
@@ -1410,7 +1505,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         static bool attr_set = false;                                                                                    \
         if (!attr_set) {                                                                                                 \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)ST_SMEM_BUDGET));                                                         \
+                                          (int)ST_SMEM_MAX));                                                            \
             attr_set = true;                                                                                             \
         }                                                                                                                \
         roi_pool_keys_kernel<kBf16, SVV><<<grid2, ST_THREADS, smem2, s>>>(                                               \
@@ -1472,6 +1567,17 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     no_bands.ctab = nullptr; no_bands.ctrl = nullptr; no_bands.nb = 1; no_bands.rows = H;
     size_t smem = cells * sv * 16;
     if (MODE != 0) smem += (size_t)rb * sv * 4 * ST_BINS * 4 * (MODE == 2 ? 2 : 1);
+    // variant 3 (pool_bins_pairs): the pair table behind the slice, when slice + table fit a CTA's shared memory.
+    // OPT-IN, azn_roi_pool_tune(422) (and (622): with 64-byte slices where 128-byte ones would fit).  MEASURED (R = 20 000,
+    // bf16): 38x63 0.2805 ms vs 0.2751 without the table; 30x50 at SV = 4 0.234 vs 0.262 (and 0.244 for the default SV = 8
+    // there; f32 0.459 vs 0.451).  The table does cut the ideal shared-load wavefronts by a quarter (30.1 M -> 22.5 M,
+    // profiles/r2_ncu_pool_pairs.csv), but the two bin rows of a quarter-warp no longer walk rows of alternating bank
+    // parity -- a single odd row, aligned pairs, a single even row -- so the row rotation that keeps the plain kernel
+    // at 7.8 M conflict wavefronts has nothing to hold on to: 25.7 M with the table, data pipe 88 % instead of 78 %.
+    const size_t smem_pairs = (((cells + 1) & ~(size_t)1) + (size_t)(H / 2) * (W | 1)) * sv * 16;
+    const bool use_pairs = MODE == 0 && !grouped && g_pool_variant == 2 && (g_pool_debug == 4 || g_pool_debug == 6) && H >= 2 &&
+                       smem_pairs <= ST_SMEM_MAX;
+    if (use_pairs) smem = smem_pairs;
 #define AZN_ST_LAUNCH(SVV)                                                                                               \
     do {                                                                                                                 \
         static bool attr_set = false;            /* once per instantiation: the call costs tens of microseconds */     \
@@ -1490,7 +1596,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         static bool attr_set = false;                                                                                    \
         if (!attr_set) {                                                                                                 \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)ST_SMEM_BUDGET));                                                         \
+                                          (int)ST_SMEM_MAX));                                                            \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)ST_SMEM_BUDGET));                                                         \
             attr_set = true;                                                                                             \
@@ -1503,7 +1609,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         else                                                                                                             \
             roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                             \
                 (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,     \
-                (int)nchunk, nslices, g_pool_variant >= 2 ? 2 : 1, nullptr, nullptr, no_bands);                          \
+                (int)nchunk, nslices, (g_pool_variant >= 2 ? 2 : 1) | (use_pairs ? 0x10000 : 0), nullptr, nullptr, no_bands); \
     } while (0)
     if (MODE == 0) {
         if (sv == 8) AZN_KEY_LAUNCH(8); else if (sv == 4) AZN_KEY_LAUNCH(4); else AZN_KEY_LAUNCH(2);

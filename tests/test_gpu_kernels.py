@@ -47,10 +47,10 @@ def _edge_rois(n_img):
 
 
 # ------------------------------------------------------------------------------- ROI pooling
-@pytest.fixture(params=[0, 1, 22, 322, 42], ids=["auto", "direct", "staged", "staged_bands", "staged_grouped"])
+@pytest.fixture(params=[0, 1, 22, 422, 322, 42], ids=["auto", "direct", "staged", "staged_pairs", "staged_bands", "staged_grouped"])
 def pool_mode(request):
     """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, shared-memory-staged kernel with the
-    per-ROI loop, the same with row bands of 128-byte slices when the whole map does not fit (the 38x63 maps below: an
+    per-ROI loop, the same over a two-level map (slice + row-pair table where both fit: an A/B variant), the same with row bands of 128-byte slices when the whole map does not fit (the 38x63 maps below: an
     A/B variant), staged kernel with the ROIs grouped by width whenever that path applies."""
     from aznet_b200 import _lib
     _lib.lib().azn_roi_pool_tune(request.param)
