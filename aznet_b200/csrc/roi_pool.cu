@@ -684,7 +684,10 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                      const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
                      const int32_t *__restrict__ bucket_off, const int32_t *__restrict__ perm,
                      float scale, uint4 *__restrict__ out, int n_buckets, int nchunk, int nslices, int variant,
-                     const int32_t *__restrict__ goff, const uint2 *__restrict__ gdesc, BandPlan bp) {
+                     const int32_t *__restrict__ goff, const uint2 *__restrict__ gdesc, BandPlan bp,
+                     const uint4 *__restrict__ geom = nullptr) {
+    // geom != nullptr: the ROIs' bin bounds come from the records of roi_geom_kernel (the launch before this one; this
+    // kernel is then its programmatic dependent: the slice is staged while the pre-pass runs).
     // gdesc != nullptr: the grouped path (1d).  goff[b] .. goff[b + 1] = image b's groups in gdesc (G slots of
     // (ROI index or -1, start_w | start_h << 8 | roi_h << 16 | roi_w << 24) each); bucket_off / perm then list only
     // the ROIs the grouped path does not cover.  The kernel is launched as a programmatic dependent of the pre-pass.
@@ -775,6 +778,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         const long long t0 = clock64();
 #endif
         if (real && prestaged != item) stage_slice(img, row0, c0v);
+        if (EXT == 0 && geom != nullptr) pdl_grid_wait();    // the records are complete from here on (a no-op after the first time)
         cp_async_wait_all();
         __syncthreads();
 #ifdef AZN_POOL_TRACE
@@ -832,18 +836,24 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         const long long t3 = clock64();
 #endif
         // the per-ROI path: one warp, one ROI, lanes on the bin rows
-        auto pool_one = [&](const int r) {
-            const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
-            const bool ok = real && q.b == img;
+        auto pool_one = [&](const int r, const unsigned gw) {
             unsigned gb = 0;                                 // lanes 0..6: packed h bounds of bin row `lane`; 7..13: w bounds
-            if (ok && lane < 2 * ST_P) {
-                int a, b;
-                if (lane < ST_P) bin_bounds(lane, q.bin_h, q.start_h, H, a, b);
-                else bin_bounds(lane - ST_P, q.bin_w, q.start_w, W, a, b);
-                gb = (unsigned)a | ((unsigned)b << 16);
+            int mh;                                          // the tallest bin of the ROI (warp-uniform): selects the fixed-height variant
+            if (EXT == 0 && geom != nullptr) {               // lane k < 16 holds word k of the ROI's record
+                const bool ok = real && (int)__shfl_sync(0xffffffffu, gw, 14) == img;
+                if (ok && lane < 2 * ST_P) gb = gw;
+                mh = ok ? (int)__shfl_sync(0xffffffffu, gw, 15) : 0;
+            } else {
+                const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
+                const bool ok = real && q.b == img;
+                if (ok && lane < 2 * ST_P) {
+                    int a, b;
+                    if (lane < ST_P) bin_bounds(lane, q.bin_h, q.start_h, H, a, b);
+                    else bin_bounds(lane - ST_P, q.bin_w, q.start_w, W, a, b);
+                    gb = (unsigned)a | ((unsigned)b << 16);
+                }
+                mh = __reduce_max_sync(0xffffffffu, lane < ST_P ? (int)(gb >> 16) - (int)(gb & 0xffff) : 0);
             }
-            // the tallest bin of the ROI (warp-uniform): selects the fixed-height variant
-            const int mh = __reduce_max_sync(0xffffffffu, lane < ST_P ? (int)(gb >> 16) - (int)(gb & 0xffff) : 0);
             // A pass pools one COLUMN of bins (fixed pw): every lane of the warp then has the same [ws, we), so the
             // inner loops are warp-uniform; lanes differ only in their bin row (ph = lane / SV) and channel vector.
 #pragma unroll 1
@@ -1020,7 +1030,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
                 } else if (ph == 0) {                        // a slice with a -0: the exact per-ROI path, ROI by ROI
                     for (int gg = 0; gg < G; ++gg) {
                         const int idx = __shfl_sync(0xffffffffu, (int)e.x, gg * SV);
-                        if (idx >= 0) pool_one(idx);
+                        if (idx >= 0) pool_one(idx, 0u);
                     }
                 }
                 u = u2;
@@ -1029,12 +1039,21 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         }
         // ROIs are handed out dynamically (shared cursor): their cost varies by an order of magnitude with
         // their size, and a static deal leaves a tail of one big ROI per item.
+        // (with the geometry pre-pass: the NEXT ROI's record is fetched while the current one is pooled)
+        auto fetch = [&](const int at) -> unsigned {
+            if (EXT != 0 || geom == nullptr || at >= hi || lane >= 16) return 0u;
+            return reinterpret_cast<const unsigned *>(geom)[(size_t)(perm ? perm[at] : at) * 16 + lane];
+        };
         int ri = lo + warp;
+        unsigned gw = fetch(ri);
         while (ri < hi) {
-            pool_one(perm ? perm[ri] : ri);
             int nxt = 0;
             if (lane == 0) nxt = atomicAdd(&s_next, 1);
-            ri = __shfl_sync(0xffffffffu, nxt, 0);
+            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            const unsigned gw_next = fetch(nxt);
+            pool_one(perm ? perm[ri] : ri, gw);
+            ri = nxt;
+            gw = gw_next;
         }
 #ifdef AZN_POOL_TRACE
         const long long t4 = clock64();
@@ -1089,6 +1108,39 @@ roi_bucket_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_
         const int b = (int)rois[(size_t)r * 5];
         perm[atomicAdd(&s_cnt[(b < 0 || b >= n_img) ? n_img : b], 1)] = r;
     }
+}
+
+// Geometry pre-pass of the default keys kernel.  The pooling kernel meets every ROI once per channel slice (16 x for
+// C = 512 bf16), and deriving the ROI's bin bounds -- four roundf, two IEEE divisions, 14 x floorf / ceilf / clamp --
+// was a quarter of its warp instructions (135 of ~630 per ROI-slice, F2I alone 8 % of the stall samples).  Here they are
+// computed ONCE per ROI, by the very same device functions (roi_geom, bin_bounds), into a 64-byte record:
+//   words 0..6 packed row bounds of the bin rows (lo | hi << 16), 7..13 packed column bounds, 14 batch index
+//   (0x7fffffff when it is not an integer in [0, n_img)), 15 the tallest bin of the ROI in rows.
+// A warp of the pooling kernel fetches a record with one coalesced 64-byte load -- the NEXT ROI's while it pools the
+// current one.
+__global__ void __launch_bounds__(256)
+roi_geom_kernel(const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap, int n_img, int H, int W, float scale,
+                uint4 *__restrict__ geom) {
+    const int R = n_rois ? min(max(*n_rois, 0), R_cap) : R_cap;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();                                 // the pooling kernel may start staging its slice
+    if (r >= R) return;
+    const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, ST_P, ST_P);
+    unsigned wd[16];
+    int mh = 0;
+#pragma unroll
+    for (int p = 0; p < ST_P; ++p) {
+        int a, b;
+        bin_bounds(p, q.bin_h, q.start_h, H, a, b);
+        wd[p] = (unsigned)a | ((unsigned)b << 16);
+        mh = max(mh, b - a);
+        bin_bounds(p, q.bin_w, q.start_w, W, a, b);
+        wd[ST_P + p] = (unsigned)a | ((unsigned)b << 16);
+    }
+    wd[14] = (q.b >= 0 && q.b < n_img) ? (unsigned)q.b : 0x7fffffffu;
+    wd[15] = (unsigned)mh;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) geom[(size_t)r * 4 + k] = make_uint4(wd[4 * k], wd[4 * k + 1], wd[4 * k + 2], wd[4 * k + 3]);
 }
 
 // Pre-pass of the banded path (1e).  One CTA.  Every ROI goes to set 1 -- bucket image * nb + band of the band that holds
@@ -1402,6 +1454,8 @@ static size_t group_ws_bytes(int n_img, int R_cap) {
     if (n_img < 1 || n_img > GP_MAX_IMG) return 0;
     return group_ints(n_img, R_cap) * sizeof(int32_t) + ((size_t)(R_cap > 0 ? R_cap : 0) + (size_t)n_img * GP_CLS * 7) * sizeof(uint2);
 }
+// geometry records of the default staged path (roi_geom_kernel), at the same place as the grouped / banded workspaces
+static size_t geom_ws_bytes(int R_cap) { return (size_t)(R_cap > 0 ? R_cap : 0) * 64; }
 static size_t bucket_ws_aligned(int n_img, int R_cap) { return (bucket_ws_bytes(n_img, R_cap) + 15) / 16 * 16; }
 // banded path (NHWC), at the same place as the grouped path's (the two exclude each other):
 // [ctab BAND_TAB_MAX x int4] [ctrl 4] [off1 n_img * BAND_MAX + 2] [off2 n_img + 2] [perm1 R_cap] [perm2 R_cap]
@@ -1412,7 +1466,8 @@ static size_t band_ws_bytes(int n_img, int R_cap) {
 
 extern "C" size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, int dtype, int R_cap) {
     if (layout == AZN_LAYOUT_NCHW && dtype != AZN_DTYPE_F32) return 0;
-    if (layout == AZN_LAYOUT_NHWC) return bucket_ws_aligned(n_img, R_cap) + std::max(group_ws_bytes(n_img, R_cap), band_ws_bytes(n_img, R_cap));
+    if (layout == AZN_LAYOUT_NHWC)
+        return bucket_ws_aligned(n_img, R_cap) + std::max(std::max(group_ws_bytes(n_img, R_cap), band_ws_bytes(n_img, R_cap)), geom_ws_bytes(R_cap));
     return map_ws_bytes(n_img, C, H, W, layout, dtype) + bucket_ws_bytes(n_img, R_cap);
 }
 
@@ -1578,6 +1633,16 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     const bool use_pairs = MODE == 0 && !grouped && g_pool_variant == 2 && (g_pool_debug == 4 || g_pool_debug == 6) && H >= 2 &&
                        smem_pairs <= ST_SMEM_MAX;
     if (use_pairs) smem = smem_pairs;
+    // geometry pre-pass (roi_geom_kernel): needs the 64 bytes per ROI of workspace; azn_roi_pool_tune(8xx) goes without (A/B).
+    // MEASURED (same box, bf16, 38x63): R = 20 000 0.2875 vs 0.2948 ms, R = 8000 0.127 vs 0.131, R = 2000 0.047 vs 0.046 (the
+    // extra launch) -- a quarter fewer warp instructions buys 2.5 %: the kernel is not issue-bound.  Used from 4096 ROIs.
+    uint4 *geom = nullptr;
+    if (MODE == 0 && !grouped && g_pool_debug != 8 && group_ws && group_bytes >= geom_ws_bytes(R_cap) && R_cap >= 4096 &&
+        ((uintptr_t)group_ws % 16 == 0)) {
+        geom = (uint4 *)group_ws;
+        roi_geom_kernel<<<(unsigned)((R_cap + 255) / 256), 256, 0, s>>>(rois, n_rois, R_cap, n_img, H, W, scale, geom);
+        AZN_LAUNCH_CHECK();
+    }
 #define AZN_ST_LAUNCH(SVV)                                                                                               \
     do {                                                                                                                 \
         static bool attr_set = false;            /* once per instantiation: the call costs tens of microseconds */     \
@@ -1605,7 +1670,13 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
             AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV, 1>, dim3(grid), dim3(ST_THREADS), smem, s,          \
                                     (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale,          \
                                     (uint4 *)out, n_buckets, (int)nchunk, nslices, 2 + (g_pool_debug << 8), goff, gdesc, \
-                                    no_bands));                                                                          \
+                                    no_bands, (const uint4 *)nullptr));                                                  \
+        else if (geom)                                                                                                   \
+            AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV>, dim3(grid), dim3(ST_THREADS), smem, s,             \
+                                    (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale,          \
+                                    (uint4 *)out, n_buckets, (int)nchunk, nslices,                                       \
+                                    (g_pool_variant >= 2 ? 2 : 1) | (use_pairs ? 0x10000 : 0), nullptr, nullptr, no_bands, \
+                                    (const uint4 *)geom));                                                               \
         else                                                                                                             \
             roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                             \
                 (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,     \

@@ -120,6 +120,37 @@ def test_roi_pool_device_count_bad_index_and_empty(dev, O, pool_mode):
         ops.roi_pool(torch.zeros((1, 4, 4, 3), device=dev), r, layout="NHWC")     # C*4 % 16 != 0
 
 
+@pytest.mark.parametrize("n_img", [1, 3])
+def test_roi_pool_geometry_prepass_large_R(dev, O, n_img):
+    """From 4096 ROIs on the staged NHWC kernel takes the ROIs' bin bounds from the records of a pre-pass (roi_geom_kernel)
+    instead of deriving them once per channel slice: same device functions, so the same bits -- against the oracle, and
+    against the same kernel without the pre-pass (azn_roi_pool_tune(822)); edge ROIs and bad batch indices included."""
+    from aznet_b200 import _lib, ops
+    C = 64
+    feat = synth.make_conv_maps(n_img, C, 38, 63, seed=21)
+    feat[0] -= 0.25
+    rois = np.vstack([synth.make_rois(5000, 600, 1000, seed=5, n_img=n_img), _edge_rois(n_img)]).astype(np.float32)
+    rois[17, 0] = n_img + 3                           # bad batch index -> zero row
+    ok = rois.copy()
+    ok[17, 0] = 0
+    ref = O.roi_pool_fwd(feat, ok).transpose(0, 2, 3, 1).copy()
+    ref[17] = 0
+    f = torch.from_numpy(feat).to(dev).permute(0, 2, 3, 1).contiguous()
+    r = torch.from_numpy(rois).to(dev)
+    lib = _lib.lib()
+    try:
+        outs = {}
+        for mode in (22, 822):
+            lib.azn_roi_pool_tune(mode)
+            outs[mode] = ops.roi_pool(f, r, layout="NHWC").cpu().numpy()
+            outs[(mode, "bf16")] = ops.roi_pool(f.to(torch.bfloat16), r, layout="NHWC").float().cpu().numpy()
+    finally:
+        lib.azn_roi_pool_tune(20)
+    assert np.array_equal(outs[22].view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+    assert np.array_equal(outs[22].view(np.uint32), outs[822].view(np.uint32))
+    assert np.array_equal(outs[(22, "bf16")].view(np.uint32), outs[(822, "bf16")].view(np.uint32))
+
+
 @pytest.mark.parametrize("n_img,C,hw", [(1, 512, (38, 63)), (3, 64, (38, 63)), (2, 64, (75, 40)), (64, 64, (38, 63))])
 def test_roi_pool_row_bands_equal_the_direct_kernel(dev, O, n_img, C, hw):
     """The banded staged path (azn_roi_pool_tune(322); a pre-pass sorts the ROIs by the row band that holds them, 128-byte slices per band, a second
