@@ -359,8 +359,9 @@ def main():
                     help="batches in flight for the device-resident figure: 2 = two engines on two CUDA streams, so that the latency-bound "
                          "kernels of one batch (ROI pool, decode / subdivide, selection) run next to the other batch's tensor-core GEMMs")
     ap.add_argument("--heads", default="mma", choices=("mma", "gemm"), help="output layers of the head: small mma.sync kernel or the persistent GEMM (A/B)")
-    ap.add_argument("--host-narrow", default="auto", choices=("auto", "on", "off"),
-                    help="e2e call: round the f32 host maps to bf16 on the host cores before the upload (auto: time both routes on the first batch)")
+    ap.add_argument("--host-narrow", default="auto", choices=("auto", "on", "off", "split"),
+                    help="e2e call: round the f32 host maps to bf16 on the host cores before the upload; split: a third of the images cross "
+                         "the link as f32 while the cores narrow the others (auto: time the routes on the first batch, keep the fastest)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra / e2e_entry / parity blocks (they run outside the timed regions)")
     ap.add_argument("--gather", default="peer", choices=("peer", "nccl"),
                     help="N > 1: how the ranks' proposal lists reach rank 0 -- peer: every step's lists are stored into a window of "
@@ -619,8 +620,12 @@ def main():
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
                     "input": "f32 NCHW conv5_3 maps in pinned host memory (the blobs the reference's 'fc' net is handed)",
-                    "route": ("host cores round each image chunk to bf16 (azn_host_f32_to_bf16, %d threads) while the previous chunk uploads; "
-                              "bf16 NCHW -> NHWC on the device" % pipe.host_threads) if pipe.narrow else "f32 batch uploaded as it is; f32 NCHW -> bf16 NHWC on the device",
+                    "route": (("%d of the %d images cross the link as f32 while the host cores round the others to bf16, chunk by chunk "
+                               "(azn_host_f32_to_bf16, %d threads), each narrowed chunk following the raw piece that was uploading meanwhile; "
+                               "f32 / bf16 NCHW -> bf16 NHWC on the device" % (pipe.raw_images, BATCH, pipe.host_threads)) if pipe.raw_images > 0 else
+                              ("host cores round each image chunk to bf16 (azn_host_f32_to_bf16, %d threads) while the previous chunk uploads; "
+                               "bf16 NCHW -> NHWC on the device" % pipe.host_threads)) if pipe.narrow else "f32 batch uploaded as it is; f32 NCHW -> bf16 NHWC on the device",
+                    "raw_f32_images_per_batch": pipe.raw_images if pipe.narrow else BATCH,
                     "route_timing": pipe.narrow_timing,
                     "f32_upload": None if ms_e2e_f32 is None else {
                         "value": world * BATCH * args.steps / (ms_e2e_f32 / 1e3), "unit": "images/s", "h2d_bytes_per_step": pipe_f32.h2d_bytes,

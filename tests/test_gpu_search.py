@@ -251,10 +251,11 @@ def test_collector_slots_follow_the_device_counter(dev):
     assert gb.shape[0] == 3 * n_img and torch.equal(gc[:n_img], want[0][2])
 
 
-@pytest.mark.parametrize("host_narrow", ["off", "on", "auto"])
+@pytest.mark.parametrize("host_narrow", ["off", "on", "auto", "split"])
 def test_proposal_pipeline_routes_agree_bit_for_bit(dev, host_narrow):
     """The batched host-facing call (f32 NCHW host maps in, proposal lists out): uploading the f32 batch, or rounding it
-    to bf16 on the host first (azn_host_f32_to_bf16 + azn_nchw_bf16_to_nhwc_bf16), puts the same bits in HBM, so every
+    to bf16 on the host first (azn_host_f32_to_bf16 + azn_nchw_bf16_to_nhwc_bf16), or splitting the batch between the two
+    (some images raw, the others narrowed meanwhile), puts the same bits in HBM, so every
     route returns exactly what the engine returns on the resident bf16 map -- with and without CUDA-graph replay,
     and again when the slots are reused."""
     from aznet_b200 import engine, ops
@@ -295,7 +296,12 @@ def test_proposal_pipeline_routes_agree_bit_for_bit(dev, host_narrow):
                 same(pipe.result(t), want[kk], (host_narrow, use_graph, kk))
         kk, t = tickets.pop(0)
         same(pipe.result(t), want[kk], (host_narrow, use_graph, kk))
-        assert pipe.narrow == (host_narrow == "on") or host_narrow == "auto"
-        assert pipe.h2d_bytes == batches[0].size * (2 if pipe.narrow else 4)
+        assert pipe.narrow == (host_narrow in ("on", "split")) or host_narrow == "auto"
+        per_img = batches[0].size // n_img
+        raw = pipe.raw_images if pipe.narrow else n_img               # images that cross the link as f32
+        assert pipe.h2d_bytes == per_img * (4 * raw + 2 * (n_img - raw))
+        if host_narrow == "split":
+            assert 0 < pipe.raw_images < n_img
         if host_narrow == "auto":
-            assert pipe.narrow_timing and pipe.narrow_timing["chosen"] in ("f32_upload", "host_bf16_then_upload")
+            assert pipe.narrow_timing and (pipe.narrow_timing["chosen"] in ("f32_upload", "host_bf16_then_upload")
+                                           or pipe.narrow_timing["chosen"].startswith("split_"))
