@@ -34,6 +34,7 @@
 // M = 64 .. 2048) this is an even split of the K loop across the whole chip: every SM streams its
 // share of the 205 MB int6 weight matrix.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -48,13 +49,20 @@ constexpr size_t WS_DATA_BYTES = (size_t)128 << 20;    // partial-accumulator ar
 constexpr int WS_MAX_SLOTS = 1024;                     // flag words (one per slot)
 
 
-template <int BLOCK_N, int MH> struct Cfg {
+// RU = 1 (3x3 convolution, "row re-use"): a stage holds ONE A box of TILE_M + 8 rows -- the tile's pixels of filter row dy
+// from one pixel to the left to one to the right (+ 5 rows of slack for the box granularity) -- and the W boxes of the
+// three taps (dy, -1), (dy, 0), (dy, +1): the three taps multiply the same shared-memory rows, shifted by one row (128 B)
+// each, instead of three separately loaded boxes.
+template <int BLOCK_N, int MH, int RU = 0> struct Cfg {
     static constexpr int TILE_M = HALF_M * MH;
     static constexpr int A_HALF_BYTES = HALF_M * BLOCK_K * 2;
-    static constexpr int A_BYTES = MH * A_HALF_BYTES;
+    static constexpr int A_TAIL_BYTES = RU ? 8 * BLOCK_K * 2 : 0;
+    static constexpr int A_BYTES = MH * A_HALF_BYTES + A_TAIL_BYTES;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = SMEM_RING_BYTES / STAGE_BYTES < 8 ? SMEM_RING_BYTES / STAGE_BYTES : 8;
+    static constexpr int B_STAGE_BYTES = (RU ? 3 : 1) * B_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+    static constexpr int RING_BYTES = RU ? 216 * 1024 : SMEM_RING_BYTES;
+    static constexpr int STAGES = RING_BYTES / STAGE_BYTES < 8 ? RING_BYTES / STAGE_BYTES : 8;
     static constexpr int ACC_COLS = MH * BLOCK_N;                       // TMEM columns of one accumulator set
     static constexpr int NUM_ACC = 2 * ACC_COLS <= 512 ? 2 : 1;        // double-buffered when it fits
     static constexpr int TMEM_COLS = NUM_ACC * ACC_COLS < 32 ? 32 : NUM_ACC * ACC_COLS;
@@ -64,7 +72,7 @@ template <int BLOCK_N, int MH> struct Cfg {
     static constexpr size_t SLOT_BYTES = (size_t)TILE_M * BLOCK_N * sizeof(float);
     static constexpr int WS_SLOTS = (int)(WS_DATA_BYTES / SLOT_BYTES) < WS_MAX_SLOTS ? (int)(WS_DATA_BYTES / SLOT_BYTES) : WS_MAX_SLOTS;
     static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
-    static_assert(STAGES >= 3, "pipeline too shallow");
+    static_assert(STAGES >= (RU ? 2 : 3), "pipeline too shallow");
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -157,6 +165,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 bytes, 8-row groups
 // 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+// The start address need not be 1024-byte aligned: the tensor core applies the 128-byte swizzle to the ABSOLUTE shared
+// address (bits [4,7) ^= bits [7,10)), exactly like the TMA write that filled the box, so a descriptor that starts r rows
+// (r * 128 B) into a box addresses the same data rows r .. r + 127 -- with the "matrix base offset" field [49,52) left 0.
+// MEASURED (round 2, the RU convolution kernels): base offset 0 is bit-correct against the fp32 convolution on every test
+// shape; setting it to (start >> 7) & 7 -- what the field's description suggests -- gives wrong sums.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -337,6 +350,7 @@ struct EpiParams {
     // (see azn_conv3x3_forward): k-blocks per filter tap (Cin / 64), padded width / height, rows per image,
     // and whether the output map is written without the border (the last layer of the backbone)
     int cv_kbt, cv_wp, cv_hp, cv_plane, cv_unpad, cv_taps;   // cv_taps: 9, or 1 = the taps are already gathered into K (patches)
+    int cv_reuse;        // 1: launched as an RU kernel (one A box per filter row, three taps per stage)
 };
 
 // Row of the padded pixel grid -> is it a border pixel, and which output row does it go to.
@@ -422,11 +436,13 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter) {
     __syncthreads();
 }
 
-template <int BLOCK_N, int MH, bool CONV>
-__global__ void __launch_bounds__(Cfg<BLOCK_N, MH>::THREADS, 1)
+template <int BLOCK_N, int MH, bool CONV, int RU = 0>
+__global__ void __launch_bounds__(Cfg<BLOCK_N, MH, RU>::THREADS, 1)
 fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-               const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, EpiParams ep) {
-    using C = Cfg<BLOCK_N, MH>;
+               const int32_t *__restrict__ m_live_ptr, int M_cap, int N, int K, EpiParams ep,
+               const __grid_constant__ CUtensorMap tmap_a8) {
+    // (tmap_a8: RU only -- the same tensor as tmap_a with boxes of 8 rows, for the tail of the A box)
+    using C = Cfg<BLOCK_N, MH, RU>;
     constexpr int TILE_M = C::TILE_M;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -471,6 +487,20 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
+                    if (RU) {
+                        // k-block -> (filter row dy, channel block): ONE A box of the tile's pixels of that row, from
+                        // one pixel to the left of the tile (row -1) on, and the W boxes of the row's three taps
+                        const int dy = kb / ep.cv_kbt, cb = kb - dy * ep.cv_kbt;
+                        const int a_col = cb * BLOCK_K, a_row = m_tile * TILE_M + (dy - 1) * ep.cv_wp - 1;
+                        mbar_expect_tx(&full[s], halves * C::A_HALF_BYTES + C::A_TAIL_BYTES + C::B_STAGE_BYTES);
+                        for (int h = 0; h < halves; ++h)
+                            tma_load_2d(smem_a + s * C::A_BYTES + h * C::A_HALF_BYTES, &tmap_a, &full[s], a_col, a_row + h * HALF_M);
+                        tma_load_2d(smem_a + s * C::A_BYTES + halves * C::A_HALF_BYTES, &tmap_a8, &full[s], a_col, a_row + halves * HALF_M);
+                        for (int dxi = 0; dxi < 3; ++dxi)
+                            tma_load_2d(smem_b + s * C::B_STAGE_BYTES + dxi * C::B_BYTES, &tmap_w, &full[s],
+                                        ((dy * 3 + dxi) * ep.cv_kbt + cb) * BLOCK_K, n_tile * BLOCK_N);
+                        continue;
+                    }
                     mbar_expect_tx(&full[s], halves * C::A_HALF_BYTES + C::B_BYTES);
                     int a_col = kb * BLOCK_K, a_row = m_tile * TILE_M;
                     if (CONV && ep.cv_taps != 1) {
@@ -507,6 +537,26 @@ fc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     if (tr && it == 0) tr[TR_FIRST_FULL] = global_ns();
+                    if (RU) {
+                        // tap (dy, dx): the same rows, dx + 1 rows (128 B each) further (see umma_smem_desc: the swizzle
+                        // follows the absolute address, so the shifted descriptor reads the shifted rows)
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            const uint32_t a_addr = smem_u32(smem_a + s * C::A_BYTES) + (uint32_t)dxi * 128u;
+                            const uint64_t adesc = umma_smem_desc(a_addr);
+                            const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + s * C::B_STAGE_BYTES + dxi * C::B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint32_t acc = (kb > w.kb0 || k > 0 || dxi > 0) ? 1u : 0u;
+                                umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                                if (MH == 2 && halves == 2)
+                                    umma_f16(tmem_d + BLOCK_N, adesc + (uint64_t)(C::A_HALF_BYTES >> 4) + (uint64_t)(2 * k),
+                                             bdesc + (uint64_t)(2 * k), idesc, acc);
+                            }
+                        }
+                        umma_commit(&empty[s]);
+                        continue;
+                    }
                     const uint64_t adesc = umma_smem_desc(smem_u32(smem_a + s * C::A_BYTES));
                     const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + s * C::B_BYTES));
 #pragma unroll
@@ -749,27 +799,28 @@ void pick_tile(int N, int &bn, int &mh) {
     if (bn == 64) mh = 1;
 }
 
-template <int BLOCK_N, int MH, bool CONV = false>
+template <int BLOCK_N, int MH, bool CONV = false, int RU = 0>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tw, const int32_t *m_live, int M_cap, int N, int K,
-                const EpiParams &ep, int grid, cudaStream_t s) {
-    using C = Cfg<BLOCK_N, MH>;
+                const EpiParams &ep, int grid, cudaStream_t s, const CUtensorMap *ta8 = nullptr) {
+    using C = Cfg<BLOCK_N, MH, RU>;
     static bool attr = false;
     if (!attr) {
-        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N, MH, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        AZN_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BLOCK_N, MH, CONV, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
     // every CTA of the persistent grid must be co-resident (flag spin-waits, grid barrier): cooperative launch
     static int max_grid = 0;
     if (!max_grid) {
         int per_sm = 0;
-        AZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fc_gemm_kernel<BLOCK_N, MH, CONV>, C::THREADS, C::SMEM_BYTES));
+        AZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fc_gemm_kernel<BLOCK_N, MH, CONV, RU>, C::THREADS, C::SMEM_BYTES));
         max_grid = per_sm * azn_num_sms();
     }
     if (grid > max_grid) {
         azn_set_error("azn_fc_forward: a grid of %d persistent CTAs cannot be co-resident on this device (max %d)", grid, max_grid);
         return AZN_ERR_CUDA;
     }
-    AZN_CUDA(azn_launch_coop(fc_gemm_kernel<BLOCK_N, MH, CONV>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep));
+    AZN_CUDA(azn_launch_coop(fc_gemm_kernel<BLOCK_N, MH, CONV, RU>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, ta, tw, m_live, M_cap, N, K, ep,
+                             ta8 ? *ta8 : ta));
     return AZN_OK;
 }
 
@@ -828,7 +879,7 @@ extern "C" int azn_fc_forward(const void *A, const void *W, const float *bias, v
     ep.flags = (int *)((char *)workspace + WS_DATA_BYTES);
     ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
     ep.trace = g_trace;
-    ep.cv_kbt = ep.cv_wp = ep.cv_hp = ep.cv_plane = ep.cv_unpad = ep.cv_taps = 0;
+    ep.cv_kbt = ep.cv_wp = ep.cv_hp = ep.cv_plane = ep.cv_unpad = ep.cv_taps = ep.cv_reuse = 0;
     if (bn == 256 && mh == 2) rc = launch_gemm<256, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 256) rc = launch_gemm<256, 1>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
     else if (bn == 128 && mh == 2) rc = launch_gemm<128, 2>(ta, tw, m_live, M_cap, N, K, ep, grid, s);
@@ -888,8 +939,22 @@ static int conv_grid_forward(const void *X, const void *Wt, const float *bias, v
     ep.sync = (unsigned long long *)((char *)workspace + WS_DATA_BYTES + WS_MAX_SLOTS * sizeof(int));
     ep.trace = nullptr;
     ep.cv_kbt = Cin / BLOCK_K; ep.cv_wp = W + 2; ep.cv_hp = H + 2; ep.cv_plane = (H + 2) * (W + 2); ep.cv_unpad = out_unpadded ? 1 : 0; ep.cv_taps = taps;
+    ep.cv_reuse = 0;
     const int grid = azn_num_sms();
     cudaStream_t s = (cudaStream_t)stream;
+    // Row re-use (RU kernels) for the layers whose tiles are bound by operand delivery, not by the tensor pipe: Cout <= 128
+    // (conv1_2, conv2_x: 52 / 85 FLOP per delivered byte with one A box per tap; 110 / 150 with one per filter row).
+    // MEASURED per 16 images of 480x800: conv1_2 0.893 -> 0.676 ms, conv2_1 0.315 -> 0.252, conv2_2 0.496 -> 0.373; backbone
+    // 3483 -> 3973 images/s on the same box.  AZN_CONV_REUSE=0 goes without (A/B).
+    static const int reuse_env = getenv("AZN_CONV_REUSE") ? atoi(getenv("AZN_CONV_REUSE")) : 1;
+    if (taps == 9 && bn <= 128 && reuse_env != 0) {
+        CUtensorMap ta8;
+        rc = make_tmap(X, (int)P, Cin, 8, &ta8);
+        if (rc) return rc;
+        ep.cv_reuse = 1;
+        if (bn == 128) return launch_gemm<128, 2, true, 1>(ta, tw, nullptr, (int)P, Cout, 3 * Cin, ep, grid, s, &ta8);
+        return launch_gemm<64, 2, true, 1>(ta, tw, nullptr, (int)P, Cout, 3 * Cin, ep, grid, s, &ta8);
+    }
     if (bn == 256) rc = launch_gemm<256, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
     else if (bn == 128) rc = launch_gemm<128, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
     else rc = launch_gemm<64, 2, true>(ta, tw, nullptr, (int)P, Cout, K, ep, grid, s);
