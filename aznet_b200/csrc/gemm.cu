@@ -922,7 +922,12 @@ static int conv_grid_forward(const void *X, const void *Wt, const float *bias, v
         return AZN_ERR_CAPACITY;
     }
     const int K = taps * Cin;
-    const int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+    // Wide layers (Cout >= 256) of a 3x3 convolution also run the RU kernel, on 256 x 128 tiles: 155 FLOP per delivered byte
+    // against 131 for 256 x 256 tiles with one A box per tap.  MEASURED per 16 images: conv3_1 0.249 -> 0.201 ms, conv3_2 / 3_3
+    // 0.387 -> 0.34-0.355, conv4_1 0.213 -> 0.182-0.193, conv4_2 / 4_3 0.349 -> 0.345, conv5_x 0.114 -> 0.103; backbone 3985 ->
+    // 4130-4220 images/s.  AZN_CONV_BN128_CIN=c keeps 256 x 256 tiles for the layers with more than c input channels (A/B).
+    static const int bn128_cin = getenv("AZN_CONV_BN128_CIN") ? atoi(getenv("AZN_CONV_BN128_CIN")) : (1 << 30);
+    const int bn = (Cout >= 256 && !(taps == 9 && Cin <= bn128_cin)) ? 256 : (Cout > 64 ? 128 : 64);
     CUtensorMap ta, tw;
     int rc = make_tmap(X, (int)P, Cin, HALF_M, &ta);
     if (rc) return rc;

@@ -30,7 +30,7 @@ from ..detector import DetectEngine
 from ..engine import SearchEngine, im_scale_for
 
 BATCH = 64            # images per search / detection batch (BASELINE config #2's batch)
-BACKBONE_CHUNK = 32   # images per backbone pass (activations of conv1_x: ~100 MB per image at 480x800; measured 3572 / 3699 / 3528 images/s at 16 / 32 / 64: conv5_x fills its second wave of tiles at 32, conv1_2 slows down at 64)
+BACKBONE_CHUNK = int(os.environ.get("AZN_BACKBONE_CHUNK", "32"))   # images per backbone pass (activations of conv1_x: ~100 MB per image at 480x800; measured 3572 / 3699 / 3528 images/s at 16 / 32 / 64: conv5_x fills its second wave of tiles at 32, conv1_2 slows down at 64)
 _SIZES = (1, 2, 4, 8, 16, 32, 64)
 
 
