@@ -33,7 +33,7 @@ EXPORTS = [
     "azn_divide_region", "azn_divide_region_scratch_bytes", "azn_decode_boxes", "azn_nms_workspace_bytes",
     "azn_nms", "azn_nms_batched", "azn_nms_segments", "azn_nms_tune",
     "azn_detect_rois", "azn_detect_select", "azn_detect_thresholds", "azn_detect_filter", "azn_tune_threshold",
-    "azn_image_blob", "azn_conv3x3_forward", "azn_maxpool2x2_forward", "azn_nhwc_border", "azn_grn_concat_forward", "azn_roi_pool_grn_fwd", "azn_patches3x3", "azn_conv_patches_forward", "azn_conv3x3_direct_forward",
+    "azn_image_blob", "azn_conv3x3_forward", "azn_conv_tune", "azn_maxpool2x2_forward", "azn_nhwc_border", "azn_grn_concat_forward", "azn_roi_pool_grn_fwd", "azn_patches3x3", "azn_conv_patches_forward", "azn_conv3x3_direct_forward",
 ]
 
 
@@ -158,6 +158,8 @@ def _bind(L):
     L.azn_select_proposals.argtypes = [C.POINTER(SearchState), i32, i32, f64, vp, vp, vp, i32, vp]
     L.azn_collect_proposals.restype = i32
     L.azn_collect_proposals.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp]
+    L.azn_conv_tune.restype = None
+    L.azn_conv_tune.argtypes = [i32, i32]
     L.azn_peer_alloc.restype = i32
     L.azn_peer_alloc.argtypes = [sz, C.POINTER(C.c_void_p), C.c_char_p]
     L.azn_peer_open.restype = i32

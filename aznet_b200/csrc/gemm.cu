@@ -34,7 +34,6 @@
 // M = 64 .. 2048) this is an even split of the K loop across the whole chip: every SM streams its
 // share of the 205 MB int6 weight matrix.
 #include <cuda.h>
-#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -788,6 +787,7 @@ int make_tmap(const void *ptr, int rows, int cols, int box_rows, CUtensorMap *ou
 // (int6 / fc6 / fc7); narrower single-accumulator tiles for the small layers, where more tiles beat splitting
 // the K loop.
 int g_force_parts = 0, g_force_finish = -1, g_force_bn = 0, g_force_mh = 0;
+int g_conv_reuse = 1, g_conv_bn128_cin = 1 << 30;          // azn_conv_tune; AZN_CONV_REUSE=0 in the environment starts without
 long long *g_trace = nullptr;
 void pick_tile(int N, int &bn, int &mh) {
     bn = N >= 2048 ? 256 : (N > 64 ? 128 : 64);
@@ -834,6 +834,14 @@ extern "C" void azn_fc_tune(int parts, int finish_mode, int block_n) {
 }
 
 extern "C" void azn_fc_trace(long long *device_buffer) { g_trace = device_buffer; }
+
+// Tuning hook of azn_conv3x3_forward: reuse 1 (default) = the RU kernels (one A box per filter row), 0 = one A box per tap
+// (round 1); bn128_max_cin: wide layers (Cout >= 256) with at most this many input channels run RU on 256 x 128 tiles
+// (default: all of them), the others keep 256 x 256 tiles with one A box per tap.
+extern "C" void azn_conv_tune(int reuse, int bn128_max_cin) {
+    g_conv_reuse = reuse ? 1 : 0;
+    g_conv_bn128_cin = bn128_max_cin < 0 ? (1 << 30) : bn128_max_cin;
+}
 
 extern "C" size_t azn_fc_workspace_bytes(int M_cap, int N, int K) {
     (void)M_cap; (void)K; (void)N;
@@ -925,9 +933,9 @@ static int conv_grid_forward(const void *X, const void *Wt, const float *bias, v
     // Wide layers (Cout >= 256) of a 3x3 convolution also run the RU kernel, on 256 x 128 tiles: 155 FLOP per delivered byte
     // against 131 for 256 x 256 tiles with one A box per tap.  MEASURED per 16 images: conv3_1 0.249 -> 0.201 ms, conv3_2 / 3_3
     // 0.387 -> 0.34-0.355, conv4_1 0.213 -> 0.182-0.193, conv4_2 / 4_3 0.349 -> 0.345, conv5_x 0.114 -> 0.103; backbone 3985 ->
-    // 4130-4220 images/s.  AZN_CONV_BN128_CIN=c keeps 256 x 256 tiles for the layers with more than c input channels (A/B).
-    static const int bn128_cin = getenv("AZN_CONV_BN128_CIN") ? atoi(getenv("AZN_CONV_BN128_CIN")) : (1 << 30);
-    const int bn = (Cout >= 256 && !(taps == 9 && Cin <= bn128_cin)) ? 256 : (Cout > 64 ? 128 : 64);
+    // 4130-4220 images/s.  azn_conv_tune(1, c) keeps 256 x 256 tiles for the layers with more than c input channels (A/B).
+    const int reuse_env = g_conv_reuse, bn128_cin = g_conv_bn128_cin;
+    const int bn = (Cout >= 256 && !(taps == 9 && reuse_env != 0 && Cin <= bn128_cin)) ? 256 : (Cout > 64 ? 128 : 64);
     CUtensorMap ta, tw;
     int rc = make_tmap(X, (int)P, Cin, HALF_M, &ta);
     if (rc) return rc;
@@ -950,8 +958,7 @@ static int conv_grid_forward(const void *X, const void *Wt, const float *bias, v
     // Row re-use (RU kernels) for the layers whose tiles are bound by operand delivery, not by the tensor pipe: Cout <= 128
     // (conv1_2, conv2_x: 52 / 85 FLOP per delivered byte with one A box per tap; 110 / 150 with one per filter row).
     // MEASURED per 16 images of 480x800: conv1_2 0.893 -> 0.676 ms, conv2_1 0.315 -> 0.252, conv2_2 0.496 -> 0.373; backbone
-    // 3483 -> 3973 images/s on the same box.  AZN_CONV_REUSE=0 goes without (A/B).
-    static const int reuse_env = getenv("AZN_CONV_REUSE") ? atoi(getenv("AZN_CONV_REUSE")) : 1;
+    // 3483 -> 3973 images/s on the same box.  azn_conv_tune(0, 0) goes without (A/B).
     if (taps == 9 && bn <= 128 && reuse_env != 0) {
         CUtensorMap ta8;
         rc = make_tmap(X, (int)P, Cin, 8, &ta8);

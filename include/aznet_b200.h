@@ -386,6 +386,10 @@ int azn_image_blob(const uint8_t *images, int n_img, int H0, int W0, double im_s
 int azn_conv3x3_forward(const void *X, const void *Wt, const float *bias, void *Y, int n_img, int H, int W,
                         int Cin, int Cout, int relu, int out_unpadded, void *workspace, size_t workspace_bytes,
                         azn_stream_t stream);
+/* Tuning hook (A/B measurements, tests): reuse = 1 (default) loads ONE activation box per filter row and lets its three
+ * taps read it through row-shifted shared-memory descriptors, 0 loads one box per tap (round 1); wide layers
+ * (Cout >= 256) with Cin <= bn128_max_cin then run 256 x 128 tiles (default -1: all of them). */
+void azn_conv_tune(int reuse, int bn128_max_cin);
 /* conv1_1 (Cin = 3) without the 61 padding channels per tap: azn_patches3x3 gathers every pixel's 3x3 neighbourhood into
  * one K = Kp row -- entry (ky*3+kx)*Cin + c, the K order of the packed weights -- over the same zero-bordered grid
  * (in [n, H+2, W+2, Cs] bf16 with Cs >= Cin channels per pixel, e.g. azn_image_blob with Cpad = 8; out [n, H+2, W+2, Kp],

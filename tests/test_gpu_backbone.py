@@ -81,10 +81,45 @@ def test_maxpool2x2_bit_exact(dev, n, H, W, C):
     assert not yb[:, 0].any() and not yb[:, -1].any() and not yb[:, :, 0].any() and not yb[:, :, -1].any()
 
 
+@pytest.fixture(params=[(1, -1), (1, 128), (0, 0)], ids=["row_reuse", "row_reuse_wide256", "box_per_tap"])
+def conv_variant(request):
+    """azn_conv_tune: the RU kernels (one activation box per filter row, its three taps through row-shifted descriptors;
+    wide layers on 256 x 128 tiles), the same with 256 x 256 tiles for wide layers of more than 128 input channels, and
+    round 1's kernel (one box per tap)."""
+    from aznet_b200 import _lib
+    _lib.lib().azn_conv_tune(*request.param)
+    yield request.param
+    _lib.lib().azn_conv_tune(1, -1)
+
+
+def test_conv3x3_row_reuse_same_bits_at_cin64(dev):
+    """With one channel block per tap the RU kernel accumulates in the same order as the kernel with one box per tap
+    (filter row, tap, 16-wide k step): identical output bits -- the row-shifted descriptors read exactly the rows a
+    shifted box would hold (and a map wider than a tile, so that tiles start in the middle of image rows)."""
+    from aznet_b200 import _lib, ops
+    g = torch.Generator().manual_seed(77)
+    outs = []
+    for n, H, W, Cout in ((2, 37, 301, 64), (1, 50, 90, 128)):
+        x = torch.randn((n, H, W, 64), generator=g).to(torch.bfloat16)
+        w = (torch.randn((Cout, 64, 3, 3), generator=g) * (2.0 / (9 * 64)) ** 0.5).to(torch.bfloat16)
+        b = torch.randn((Cout,), generator=g) * 0.1
+        xp = ops.nhwc_border(x.to(dev).contiguous(), True)
+        wt = ops.pack_conv_weight(w.float().to(dev))
+        got = []
+        try:
+            for variant in ((1, -1), (0, 0)):
+                _lib.lib().azn_conv_tune(*variant)
+                got.append(ops.conv3x3(xp, wt, b.to(dev), relu=True).clone())
+        finally:
+            _lib.lib().azn_conv_tune(1, -1)
+        torch.cuda.synchronize()
+        assert torch.equal(got[0].view(torch.int16), got[1].view(torch.int16))
+
+
 @pytest.mark.parametrize("n,H,W,Cin,Cout,unpadded", [
     (2, 13, 17, 64, 64, False), (1, 30, 50, 512, 512, False), (2, 9, 11, 128, 256, False), (1, 5, 7, 64, 128, True),
     (3, 38, 63, 256, 512, True), (1, 24, 40, 64, 128, False)])
-def test_conv3x3_matches_fp32_convolution(dev, n, H, W, Cin, Cout, unpadded):
+def test_conv3x3_matches_fp32_convolution(dev, conv_variant, n, H, W, Cin, Cout, unpadded):
     """bf16 operands, fp32 accumulation: against torch's fp32 convolution of the SAME bf16-rounded operands the
     only differences are summation order and the bf16 rounding of the output (2^-9 relative)."""
     from aznet_b200 import ops
