@@ -162,13 +162,20 @@ class ProposalPipeline:
             measure(name, m)
         chosen = min(best, key=best.get)
         m = dict(routes)[chosen]
-        if m:                                                # a split won: look one sixteenth of the batch to either side
-            for mm in (m - max(1, n // 16), m + max(1, n // 16)):
+        step = max(1, n // 16)
+        for _ in range(6):                                   # a split won: walk a sixteenth of the batch at a time while it improves
+            if not m:
+                break
+            tried = False
+            for mm in (m - step, m + step):
                 name = "split_%d_of_%d_raw" % (mm, n)
                 if 0 < mm < n and name not in best:
                     routes.append((name, mm))
                     measure(name, mm)
+                    tried = True
             chosen = min(best, key=best.get)
+            if dict(routes)[chosen] == m or not tried:
+                break
             m = dict(routes)[chosen]
         self.narrow = m is not None
         self.raw_images = n if m is None else m
