@@ -420,11 +420,38 @@ class _BatchClock:
 
 
 # --------------------------------------------------------------------------- dataset drivers
-def _test_proposals_batched(net, imdb, prop_boxes, stats):
+def _image_shard(num_images):
+    """Under torch.distributed (one process per GPU, e.g. `torchrun tools/prop_az.py`) the image database is cut into
+    contiguous blocks, one per rank (aznet_b200.dist.shard_images): images are independent (test.py:508-513).
+    -> (rank, world, range of this rank's image indices)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        from ..dist import shard_images
+        rank, world = dist.get_rank(), dist.get_world_size()
+        lo, hi = shard_images(num_images, rank, world)
+        return rank, world, range(lo, hi)
+    return 0, 1, range(num_images)
+
+
+def _merge_image_lists(prop_boxes, indices, world):
+    """Every rank's per-image lists -> the whole database's list on every rank (one object all_gather at the end of the
+    job: the lists are host arrays by now, 300 x 4 f64 per image)."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, {i: prop_boxes[i] for i in indices})
+    for part in parts:
+        for i, b in part.items():
+            prop_boxes[i] = b
+
+
+def _test_proposals_batched(net, imdb, prop_boxes, stats, indices=None):
     """The fast route of test_proposals: read-ahead, same-shape batches, device image blob, batched backbone + search
     (detect/batched.py).  Prints the reference's per-image lines as each batch finishes."""
     full = net['full']
-    num_images = len(imdb.image_index)
+    indices = range(len(imdb.image_index)) if indices is None else indices
+    num_images = len(indices)
     copy_stream = torch.cuda.Stream(device=full.dev)
     clock = _BatchClock()
     done = [0]
@@ -449,7 +476,7 @@ def _test_proposals_batched(net, imdb, prop_boxes, stats):
     import time
     pending = None
     t_mark = time.perf_counter()
-    for batch in batched.ImageFeeder(imdb, range(num_images)):
+    for batch in batched.ImageFeeder(imdb, indices):
         t0 = time.perf_counter()
         stats['host_feed_s'] = stats.get('host_feed_s', 0.0) + (t0 - t_mark)          # read-ahead + pinned staging
         clock.start()
@@ -481,25 +508,29 @@ def test_proposals(net, imdb):
     num_images = len(imdb.image_index)
     prop_boxes = [[] for _ in range(num_images)]
     output_dir = get_output_dir(imdb, net['full'])
-    if not os.path.exists(output_dir):
-        os.makedirs(output_dir)
+    os.makedirs(output_dir, exist_ok=True)
     num_boxes = 0.0
     stats = test_proposals.last_stats = {'route': 'host', 'num_eval': 0, 'h2d_bytes': 0, 'd2h_bytes': 0, 'batches': 0}
+    # one process per GPU: this rank's block of the images; the lists are merged at the end and rank 0 writes the file
+    rank, world, mine = _image_shard(num_images)
+    stats['rank'], stats['world'], stats['images'] = rank, world, len(mine)
     if _fast_route(net):
         stats['route'] = 'batched'
-        t = _test_proposals_batched(net, imdb, prop_boxes, stats)
+        t = _test_proposals_batched(net, imdb, prop_boxes, stats, mine)
     else:
         t = Timer()
-        for i in range(num_images):
+        for k, i in enumerate(mine):
             im = cv2.imread(imdb.image_path_at(i))
             t.tic()
             prop_boxes[i] = im_propose(net, im)
             t.toc()
-            print('im_prop: {:d}/{:d} {:.3f}s'.format(i + 1, num_images, t.average_time))
+            print('im_prop: {:d}/{:d} {:.3f}s'.format(k + 1, len(mine), t.average_time))
+    _merge_image_lists(prop_boxes, mine, world)
     recall = 0
     prop = {'boxes': prop_boxes, 'time': t.average_time, 'recall': recall}
-    with open(os.path.join(output_dir, 'proposals.pkl'), 'wb') as f:
-        pickle.dump(prop, f, pickle.HIGHEST_PROTOCOL)
+    if rank == 0:
+        with open(os.path.join(output_dir, 'proposals.pkl'), 'wb') as f:
+            pickle.dump(prop, f, pickle.HIGHEST_PROTOCOL)
     print('The recall is {:.3f}'.format(recall))
     print('On average, {0} boxes per image are generated'.format(num_boxes / num_images))
     print('The average proposal generation time is {:.3f}s'.format(t.average_time))
@@ -603,8 +634,7 @@ def test_net(net, prop_file, imdb):
     all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
     num_boxes = 0.0
     output_dir = get_output_dir(imdb, net['full'])
-    if not os.path.exists(output_dir):
-        os.makedirs(output_dir)
+    os.makedirs(output_dir, exist_ok=True)
     _t = {'im_detect': Timer(), 'misc': Timer()}
     skip = set(i for i in range(num_images) if prop_boxes[i].shape[0] == 0)
     stats = test_net.last_stats = {'route': 'host', 'h2d_bytes': 0, 'batches': 0}
@@ -690,8 +720,7 @@ def test_net_shared(sc_net, frcnn_net, imdb):
     all_boxes = [[[] for _ in range(num_images)] for _ in range(imdb.num_classes)]
     num_boxes = 0.0
     output_dir = get_output_dir(imdb, sc_net['full'])
-    if not os.path.exists(output_dir):
-        os.makedirs(output_dir)
+    os.makedirs(output_dir, exist_ok=True)
     _t = {'im_detect': Timer(), 'misc': Timer()}
     stats = test_net_shared.last_stats = {'route': 'host', 'h2d_bytes': 0, 'batches': 0}
     if _fast_route(sc_net) and _fast_detect_route(frcnn_net, 'fc') and not cfg.SEAR.APPEND_BOXES:

@@ -11,6 +11,33 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _run_workers(procs, q, timeout_s):
+    """Start the workers and collect one result each; the first failure (or a time-out) ends the others at once -- a
+    rank that died must not leave its peer waiting in a collective for the rest of the GPU lease."""
+    import queue
+    import time
+    [p.start() for p in procs]
+    res, deadline = [], time.monotonic() + timeout_s
+    try:
+        while len(res) < len(procs) and time.monotonic() < deadline:
+            try:
+                r = q.get(timeout=2.0)
+            except queue.Empty:
+                if all(not p.is_alive() for p in procs) and q.empty():
+                    break
+                continue
+            res.append(r)
+            if not r[1]:
+                break
+    finally:
+        for p in procs:
+            p.join(5 if len(res) == len(procs) and all(r[1] for r in res) else 0.1)
+            if p.is_alive():
+                p.terminate()
+                p.join(5)
+    return sorted(res)
+
+
 def _peer_worker(rank, world, port, q):
     try:
         import torch.distributed as dist
@@ -65,7 +92,86 @@ def test_peer_window_append_two_processes_one_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    res = sorted(q.get(timeout=240) for _ in range(2))
-    [p.join(60) for p in procs]
+    res = _run_workers(procs, q, 120)
+    assert res == [(0, True, ""), (1, True, "")], res
+
+
+def _small_az_nets(dev):
+    import numpy as np
+    from aznet_b200 import backbone, net, synth
+    bw = backbone.make_vgg16_weights(seed=5, width_div=8)                 # conv5_3 has 64 channels
+    bb = backbone.VGG16Backbone(bw, dev)
+    azw = synth.make_az_weights(seed=3, C=64, h6=256, h71=96, h72=32, zoom_bias=0.0)
+    return {"full": net.Net(azw, "az", backbone=bb, name="az_small"), "fc": net.Net(azw, "az", name="az_small")}
+
+
+def _shard_worker(rank, world, port, root_dir, q):
+    """test_proposals under torch.distributed: every rank runs the driver on the same imdb; the images are sharded,
+    the lists merged, rank 0 writes proposals.pkl (the reference's one file)."""
+    try:
+        import contextlib
+        import io
+        import pickle
+        import numpy as np
+        import torch.distributed as dist
+        from aznet_b200 import _lib, synth
+        from aznet_b200.detect import config as C
+        from aznet_b200.detect import test as T
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
+        _lib.require_device()
+        C.cfg_set_path("pytest_shard")
+        C.cfg_set_mode("Test", 0.5)
+        C.cfg.ROOT_DIR = root_dir
+        az = _small_az_nets(dev)
+        ims = synth.make_images(5, 200, 300, seed=80) + synth.make_images(2, 240, 200, seed=90)
+        ims = [ims[k] for k in (0, 5, 1, 2, 6, 3, 4)]
+        buf = io.StringIO()
+        single, diag = None, ""
+        if rank == 0:                                            # the single-process result first (no process group yet)
+            mem = synth.InMemoryImdb(ims, num_classes=6, name="shard_single")
+            with contextlib.redirect_stdout(buf):
+                T.test_proposals(az, mem)
+            single = pickle.load(open(os.path.join(C.get_output_dir(mem, az["full"]), "proposals.pkl"), "rb"))["boxes"]
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        import datetime
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=90))
+        imdb = synth.InMemoryImdb(ims, num_classes=6, name="shard_multi")
+        with contextlib.redirect_stdout(buf):
+            T.test_proposals(az, imdb)
+        st = T.test_proposals.last_stats
+        ok = st["world"] == world and st["rank"] == rank and st["images"] == (4 if rank == 0 else 3) and st["route"] == "batched"
+        dist.barrier()
+        path = os.path.join(C.get_output_dir(imdb, az["full"]), "proposals.pkl")
+        if rank == 0:
+            multi = pickle.load(open(path, "rb"))["boxes"]
+            ok = ok and len(multi) == 7
+            hit = tot = 0
+            for i in range(7):
+                a, b = np.asarray(multi[i]), np.asarray(single[i])
+                ok = ok and a.dtype == np.float64 and 0 < a.shape[0] <= 300
+                # different batch compositions (4 + 3 images instead of 5 + 2): bf16 flips may move a few boxes
+                tot += len(b)
+                hit += sum(1 for row in b if len(a) and np.abs(a - row).max(axis=1).min() <= 0.05)
+            diag = "" if (ok and tot >= 150 and hit >= 0.97 * tot) else "stats %r ok %r rows %d matched %d counts %r" % (
+                dict(st), ok, tot, hit, [(len(multi[i]), len(single[i])) for i in range(7)])
+            ok = ok and tot >= 150 and hit >= 0.97 * tot
+        dist.barrier()
+        q.put((rank, bool(ok), diag if rank == 0 else ""))
+        dist.destroy_process_group()
+    except Exception as e:
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-600:]))
+
+
+def test_test_proposals_shards_images_over_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    res = _run_workers(procs, q, 150)
     assert res == [(0, True, ""), (1, True, "")], res
