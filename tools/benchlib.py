@@ -216,7 +216,10 @@ def entry_point_throughput(dev, az_head, cfg_dict, n_images=1024, distinct=32, i
             C.cfg_set_mode("Test", tz)
             C.cfg.SEAR.NUM_PROPOSALS = cfg_dict["num_proposals"]
             with _Quiet():
-                T.test_proposals(nets, synth.InMemoryImdb(images[:64], num_classes=21, name="bench_warm"))    # engines, pinned rings
+                import torch.distributed as dist
+                world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+                # (under torch.distributed test_proposals shards the images: every rank warms up on a full batch of its own)
+                T.test_proposals(nets, synth.InMemoryImdb(images[:64 * world], num_classes=21, name="bench_warm"))    # engines, pinned rings
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 T.test_proposals(nets, imdb)
