@@ -63,6 +63,37 @@ def test_roi_pool_equals_reference_layer_golden(dev, golden, mode):
         _lib.lib().azn_roi_pool_tune(20)
 
 
+def test_roi_pool_microbench_size_vs_oracle_rows(dev, O):
+    """BASELINE config #4 at full size -- 20 000 ROIs of the microbench's size mix over a 512 x 38 x 63 map, the staged
+    kernel with its geometry pre-pass, 1 GB of output -- against the oracle on 600 of the rows (a ROI's pooled row depends
+    on that ROI alone, so a sample of rows is compared bit for bit: bf16 and f32), and two size-independent properties
+    over ALL rows: every pooled value is one of the map's values of its channel or +0 (an empty bin), and pooling the
+    ROIs in reversed order gives the reversed output."""
+    from aznet_b200 import ops
+    C, H, W, R = 512, 38, 63, 20000
+    feat = synth.make_conv_maps(1, C, H, W, seed=7)
+    rois = synth.make_rois(R, 600, 1000, seed=3)
+    rng = np.random.RandomState(11)
+    pick = np.sort(rng.choice(R, 600, replace=False))
+    f = torch.from_numpy(feat).to(dev).permute(0, 2, 3, 1).contiguous()
+    r = torch.from_numpy(rois).to(dev)
+    ref = O.roi_pool_fwd(feat, rois[pick]).transpose(0, 2, 3, 1)
+    got = ops.roi_pool(f, r, layout="NHWC")
+    assert np.array_equal(got[torch.from_numpy(pick).to(dev)].cpu().numpy().view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+    fb = f.to(torch.bfloat16)
+    got_b = ops.roi_pool(fb, r, layout="NHWC")
+    ref_b = O.roi_pool_fwd(fb.float().permute(0, 3, 1, 2).contiguous().cpu().numpy(), rois[pick]).transpose(0, 2, 3, 1)
+    assert np.array_equal(got_b[torch.from_numpy(pick).to(dev)].float().cpu().numpy(), ref_b)
+    # properties over all 20 000 rows, on the device
+    rev = ops.roi_pool(fb, torch.flip(r, dims=[0]).contiguous(), layout="NHWC")
+    assert torch.equal(torch.flip(rev, dims=[0]).view(torch.int16), got_b.view(torch.int16))
+    ch_max = fb.view(-1, C).float().amax(dim=0)
+    ch_min = fb.view(-1, C).float().amin(dim=0)
+    v = got_b.view(-1, C).float()
+    assert bool(((v <= ch_max) & ((v >= ch_min) | (v == 0))).all())
+    del got, got_b, rev, v
+
+
 def test_detection_step_equals_reference_golden(dev, golden):
     """The device detection step (azn_detect_rois / azn_detect_select / azn_detect_thresholds / azn_detect_filter /
     azn_nms_segments) == the reference's own test_net (detections.pkl) and apply_nms, driven by the same HashDetNet:

@@ -142,6 +142,16 @@ def _gloo_worker(rank, world, port, q):
     t, c2 = azdist.gather_detection_scores(top, cnt)
     ok = ok and t.shape == (n_img, Cc, mpi) and all(float(t[i, 1, 0]) == i + 0.5 and int(c2[i, 2]) == 1 + i % mpi
                                                     for i in range(n_img))
+    # the dataset drivers' own sharding (detect/test.py::test_proposals under torch.distributed): contiguous blocks of the
+    # imdb's images, per-image lists merged on every rank at the end
+    from aznet_b200.detect import test as T
+    r, w, mine = T._image_shard(7)
+    ok = ok and (r, w) == (rank, world) and list(mine) == (list(range(0, 4)) if rank == 0 else list(range(4, 7)))
+    lists = [[] for _ in range(7)]
+    for i in mine:
+        lists[i] = np.full((1 + i, 4), float(i))
+    T._merge_image_lists(lists, mine, w)
+    ok = ok and all(isinstance(lists[i], np.ndarray) and lists[i].shape == (1 + i, 4) and float(lists[i][0, 0]) == i for i in range(7))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
