@@ -383,19 +383,39 @@ def _proposal_cap(max_rows):
     return max(want, (int(max_rows) + 127) // 128 * 128)
 
 
-def _finish_on_device(dset: DetectionSet, skip, imdb, output_dir):
-    """thresholds + final filter + NMS for the whole set on the device; same files and calls as _finish_detections."""
+def _finish_on_device(dset: DetectionSet, skip, imdb, output_dir, shard=None):
+    """thresholds + final filter + NMS for the whole set on the device; same files and calls as _finish_detections.
+    shard = (rank, world, range of this rank's images): `dset` then holds this rank's images only; its finish() exchanges
+    the scores so that every rank computes the set-wide thresholds (dist.gather_detection_scores), the per-image results
+    are merged into the database's nesting on every rank and rank 0 writes the file and evaluates."""
+    rank, world, mine = shard if shard is not None else (0, 1, range(len(imdb.image_index)))
     dset.finish(cfg.TEST.NMS)
-    all_boxes = dset.to_host()
+
+    def whole(local):
+        if world == 1:
+            return local
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine.start, [[local[j][k] for k in range(len(mine))] for j in range(imdb.num_classes)]))
+        out = [[[] for _ in range(len(imdb.image_index))] for _ in range(imdb.num_classes)]
+        for lo, part in parts:
+            for j in range(imdb.num_classes):
+                for k, d in enumerate(part[j]):
+                    out[j][lo + k] = d
+        return out
+
+    all_boxes = whole(dset.to_host())
     for j in range(imdb.num_classes):
         for i in skip:
             all_boxes[j][i] = []
-    with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
-        pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
+    if rank == 0:
+        with open(os.path.join(output_dir, 'detections.pkl'), 'wb') as f:
+            pickle.dump(all_boxes, f, pickle.HIGHEST_PROTOCOL)
     print('Applying NMS to all detections')
-    nms_dets = dset.to_host(nms=True)
+    nms_dets = whole(dset.to_host(nms=True))
     print('Evaluating detections')
-    imdb.evaluate_detections(nms_dets, output_dir)
+    if rank == 0:
+        imdb.evaluate_detections(nms_dets, output_dir)
 
 
 class _BatchClock:
@@ -568,23 +588,23 @@ def _finish_detections(all_boxes, thresh, skip, imdb, output_dir):
     imdb.evaluate_detections(nms_dets, output_dir)
 
 
-def _detect_batch(fr_net, db, boxes_d, count_d, dset, copy_back=True):
+def _detect_batch(fr_net, db, boxes_d, count_d, dset, copy_back=True, base=0):
     """One batch's Fast R-CNN step (DetectEngine over all images of the batch) into the set-wide buffers at the
-    batch's image indices."""
+    batch's image indices (minus `base`: the first image of this rank's shard)."""
     eng = batched.detect_engine(fr_net, db.shape, db.n_pad, boxes_d.shape[1])
     dets, tops, cnt = eng.detect(db.maps, boxes_d, count_d)
-    idx = torch.tensor(db.idx, dtype=torch.long, device=fr_net.dev)
+    idx = torch.tensor([i - base for i in db.idx], dtype=torch.long, device=fr_net.dev)
     dset.dets.index_copy_(0, idx, dets[:db.n])
     dset.top_scores.index_copy_(0, idx, tops[:db.n])
     dset.det_count.index_copy_(0, idx, cnt[:db.n])
     return eng
 
 
-def _test_net_batched(net, prop_boxes, imdb, dset, todo, stats):
+def _test_net_batched(net, prop_boxes, imdb, dset, todo, stats, base=0, num_images=None):
     """Fast route of test_net: batches of same-shape images, backbone + DetectEngine per batch, nothing but the
     uint8 pixels and the proposal lists crosses PCIe before the set-wide finish."""
     full = net['full']
-    num_images = len(imdb.image_index)
+    num_images = len(imdb.image_index) if num_images is None else num_images
     copy_stream = torch.cuda.Stream(device=full.dev)
     clock = _BatchClock()
     done, num_boxes = 0, 0.0
@@ -595,7 +615,7 @@ def _test_net_batched(net, prop_boxes, imdb, dset, todo, stats):
         db = batched.DeviceBatch(full, batch, copy_stream, taps=full.conv_names)
         plist = [prop_boxes[i] for i in db.idx] + [None] * (db.n_pad - db.n)
         boxes_d, count_d = _boxes_to_device(plist, cap, full.dev)
-        _detect_batch(full, db, boxes_d, count_d, dset)
+        _detect_batch(full, db, boxes_d, count_d, dset, base=base)
         ev = torch.cuda.Event()
         ev.record()
         stats['h2d_bytes'] += db.h2d_bytes + boxes_d.numel() * 8
@@ -640,9 +660,14 @@ def test_net(net, prop_file, imdb):
     stats = test_net.last_stats = {'route': 'host', 'h2d_bytes': 0, 'batches': 0}
     if _fast_detect_route(net):
         stats['route'] = 'batched'
-        dset = DetectionSet(num_images, imdb.num_classes, max_per_image, net['full'].dev)
-        _t['im_detect'], num_boxes = _test_net_batched(net, prop_boxes, imdb, dset, [i for i in range(num_images) if i not in skip], stats)
-        _finish_on_device(dset, skip, imdb, output_dir)
+        # one process per GPU: this rank's block of the images; the thresholds are set-wide (one exchange of the scores)
+        shard = _image_shard(num_images)
+        rank, world, mine = shard
+        stats['rank'], stats['world'], stats['images'] = rank, world, len(mine)
+        dset = DetectionSet(len(mine), imdb.num_classes, max_per_image, net['full'].dev, total_images=num_images)
+        _t['im_detect'], num_boxes = _test_net_batched(net, prop_boxes, imdb, dset, [i for i in mine if i not in skip], stats,
+                                                       base=mine.start, num_images=len(mine))
+        _finish_on_device(dset, skip, imdb, output_dir, shard)
     else:
         for i in range(num_images):
             if i in skip:
@@ -662,11 +687,12 @@ def test_net(net, prop_file, imdb):
     print('On average, {0} boxes per image are generated'.format(num_boxes / num_images))
 
 
-def _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats):
+def _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats, indices=None):
     """Fast route of test_net_shared: one backbone pass per batch serves the search and the detector; the proposals
     never leave the device (the search engine's output buffers are the detector's input)."""
     full, fr = sc_net['full'], frcnn_net['fc']
-    num_images = len(imdb.image_index)
+    indices = range(len(imdb.image_index)) if indices is None else indices
+    num_images = len(indices)
     copy_stream = torch.cuda.Stream(device=full.dev)
     clock = _BatchClock()
     state = {'done': 0, 'boxes': 0.0}
@@ -686,7 +712,7 @@ def _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats):
             print('im_detect: {:d}/{:d} {:.3f}s {:.3f}s'.format(state['done'], num_images, avg, 0.0))
 
     pending = None
-    for batch in batched.ImageFeeder(imdb, range(num_images)):
+    for batch in batched.ImageFeeder(imdb, indices):
         clock.start()
         db = batched.DeviceBatch(full, batch, copy_stream, taps=taps)
         maps = db.maps
@@ -697,7 +723,7 @@ def _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats):
             eng.out_count[db.n:].zero_()                      # padding images propose nothing
         if fr.kind != "frcnn_skip":
             db.maps = conv5
-        _detect_batch(fr, db, eng.out_boxes, eng.out_count, dset)
+        _detect_batch(fr, db, eng.out_boxes, eng.out_count, dset, base=indices[0] if len(indices) else 0)
         fetch = batched.Fetch(count=eng.out_count[:db.n], n_eval=eng.n_eval[:db.n], depth=eng.depth[:db.n], status=eng.status)
         stats['h2d_bytes'] += db.h2d_bytes
         stats['batches'] += 1
@@ -725,9 +751,12 @@ def test_net_shared(sc_net, frcnn_net, imdb):
     stats = test_net_shared.last_stats = {'route': 'host', 'h2d_bytes': 0, 'batches': 0}
     if _fast_route(sc_net) and _fast_detect_route(frcnn_net, 'fc') and not cfg.SEAR.APPEND_BOXES:
         stats['route'] = 'batched'
-        dset = DetectionSet(num_images, imdb.num_classes, max_per_image, sc_net['full'].dev)
-        _t['im_detect'], num_boxes = _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats)
-        _finish_on_device(dset, set(), imdb, output_dir)
+        shard = _image_shard(num_images)
+        rank, world, mine = shard
+        stats['rank'], stats['world'], stats['images'] = rank, world, len(mine)
+        dset = DetectionSet(len(mine), imdb.num_classes, max_per_image, sc_net['full'].dev, total_images=num_images)
+        _t['im_detect'], num_boxes = _test_net_shared_batched(sc_net, frcnn_net, imdb, dset, stats, mine)
+        _finish_on_device(dset, set(), imdb, output_dir, shard)
     else:
         for i in range(num_images):
             im = cv2.imread(imdb.image_path_at(i))

@@ -25,9 +25,15 @@ def _pad_rows(t: torch.Tensor, rows: int, fill):
     return out
 
 
+def _coll_device(device):
+    """Where an end-of-job collective runs: gloo moves host tensors (the CPU tests, and GPU tests with several processes
+    on one device), NCCL device tensors."""
+    return torch.device("cpu") if dist.get_backend() == "gloo" else device
+
+
 def _max_rows(n: int, device) -> int:
     """Largest shard size over the ranks (one tiny all_reduce; end-of-job paths only)."""
-    t = torch.tensor([int(n)], dtype=torch.int64, device=device)
+    t = torch.tensor([int(n)], dtype=torch.int64, device=_coll_device(device))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return int(t.item())
 
@@ -43,10 +49,11 @@ def gather_proposals(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Te
     rows = _max_rows(boxes.shape[0], boxes.device)
     outs = []
     for t in (boxes, scores, counts):
-        t = _pad_rows(t, rows, 0)
+        home = t.device
+        t = _pad_rows(t, rows, 0).to(_coll_device(home))
         buf = torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(buf, t)
-        outs.append(buf)
+        outs.append(buf.to(home))
     return tuple(outs)
 
 
@@ -268,8 +275,9 @@ def gather_detection_scores(top_scores: torch.Tensor, det_count: torch.Tensor):
     rows = _max_rows(top_scores.shape[0], top_scores.device)        # uneven shards: pad with empty images (count 0, -inf),
     outs = []                                                       # which never enter the thresholds
     for t, fill in ((top_scores, float("-inf")), (det_count, 0)):
-        t = _pad_rows(t, rows, fill)
+        home = t.device
+        t = _pad_rows(t, rows, fill).to(_coll_device(home))
         buf = torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(buf, t)
-        outs.append(buf)
+        outs.append(buf.to(home))
     return tuple(outs)

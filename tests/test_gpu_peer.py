@@ -96,13 +96,18 @@ def test_peer_window_append_two_processes_one_gpu():
     assert res == [(0, True, ""), (1, True, "")], res
 
 
-def _small_az_nets(dev):
+def _small_az_nets(dev, num_classes=6):
     import numpy as np
     from aznet_b200 import backbone, net, synth
     bw = backbone.make_vgg16_weights(seed=5, width_div=8)                 # conv5_3 has 64 channels
     bb = backbone.VGG16Backbone(bw, dev)
     azw = synth.make_az_weights(seed=3, C=64, h6=256, h71=96, h72=32, zoom_bias=0.0)
-    return {"full": net.Net(azw, "az", backbone=bb, name="az_small"), "fc": net.Net(azw, "az", name="az_small")}
+    frw = synth.make_frcnn_weights(seed=4, num_classes=num_classes, C=64, h6=256, h7=128)
+    frw["cls_score"] = (frw["cls_score"][0] * np.float32(0.02), frw["cls_score"][1])      # O(1) logits: unsaturated softmax
+    frw["bbox_pred"] = (frw["bbox_pred"][0] * np.float32(0.05), frw["bbox_pred"][1])
+    az = {"full": net.Net(azw, "az", backbone=bb, name="az_small"), "fc": net.Net(azw, "az", name="az_small")}
+    fr = {"full": net.Net(frw, "frcnn", backbone=bb, name="frcnn_small"), "fc": net.Net(frw, "frcnn", name="frcnn_small")}
+    return az, fr
 
 
 def _shard_worker(rank, world, port, root_dir, q):
@@ -123,16 +128,33 @@ def _shard_worker(rank, world, port, root_dir, q):
         C.cfg_set_path("pytest_shard")
         C.cfg_set_mode("Test", 0.5)
         C.cfg.ROOT_DIR = root_dir
-        az = _small_az_nets(dev)
+        az, fr = _small_az_nets(dev)
         ims = synth.make_images(5, 200, 300, seed=80) + synth.make_images(2, 240, 200, seed=90)
         ims = [ims[k] for k in (0, 5, 1, 2, 6, 3, 4)]
         buf = io.StringIO()
         single, diag = None, ""
-        if rank == 0:                                            # the single-process result first (no process group yet)
+
+        def close(multi_d, single_d):
+            """all_boxes[cls][img] of two runs: nearly every detection of one has a partner in the other (different batch
+            compositions flip a few bf16 roundings: boxes to 0.5 px, scores to 0.02)."""
+            hit = tot = 0
+            for j in range(1, 6):
+                for i in range(7):
+                    a, b = np.asarray(multi_d[j][i]).reshape(-1, 5), np.asarray(single_d[j][i]).reshape(-1, 5)
+                    tot += len(b)
+                    hit += sum(1 for row in b if len(a) and (np.abs(a[:, :4] - row[:4]).max(axis=1) + 25.0 * np.abs(a[:, 4] - row[4])).min() <= 0.5)
+            return tot, hit
+
+        if rank == 0:                                            # the single-process results first (no process group yet)
             mem = synth.InMemoryImdb(ims, num_classes=6, name="shard_single")
             with contextlib.redirect_stdout(buf):
                 T.test_proposals(az, mem)
-            single = pickle.load(open(os.path.join(C.get_output_dir(mem, az["full"]), "proposals.pkl"), "rb"))["boxes"]
+                single_file = os.path.join(C.get_output_dir(mem, az["full"]), "proposals.pkl")
+                T.test_net(fr, single_file, mem)
+                single_det = pickle.load(open(os.path.join(C.get_output_dir(mem, fr["full"]), "detections.pkl"), "rb"))
+                T.test_net_shared(az, fr, mem)
+                single_shared = pickle.load(open(os.path.join(C.get_output_dir(mem, az["full"]), "detections.pkl"), "rb"))
+            single = pickle.load(open(single_file, "rb"))["boxes"]
         os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
         import datetime
         dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=90))
@@ -157,6 +179,32 @@ def _shard_worker(rank, world, port, root_dir, q):
                 dict(st), ok, tot, hit, [(len(multi[i]), len(single[i])) for i in range(7)])
             ok = ok and tot >= 150 and hit >= 0.97 * tot
         dist.barrier()
+        # detection over the saved proposals, then the shared-conv route: sharded images, set-wide thresholds (one exchange
+        # of the scores), merged nesting, one detections.pkl written by rank 0
+        with contextlib.redirect_stdout(buf):
+            T.test_net(fr, path, imdb)
+        st2 = dict(T.test_net.last_stats)
+        dist.barrier()
+        if rank == 0:
+            multi_det = pickle.load(open(os.path.join(C.get_output_dir(imdb, fr["full"]), "detections.pkl"), "rb"))
+            tot, hit = close(multi_det, single_det)
+            good = st2.get("world") == world and st2["route"] == "batched" and len(multi_det) == 6 and len(multi_det[1]) == 7 and tot >= 100 and hit >= 0.93 * tot
+            if not good:
+                diag += " | test_net: stats %r rows %d matched %d" % (st2, tot, hit)
+            ok = ok and good
+        dist.barrier()
+        with contextlib.redirect_stdout(buf):
+            T.test_net_shared(az, fr, imdb)
+        st3 = dict(T.test_net_shared.last_stats)
+        dist.barrier()
+        if rank == 0:
+            multi_shared = pickle.load(open(os.path.join(C.get_output_dir(imdb, az["full"]), "detections.pkl"), "rb"))
+            tot, hit = close(multi_shared, single_shared)
+            good = st3.get("world") == world and st3["route"] == "batched" and tot >= 100 and hit >= 0.93 * tot
+            if not good:
+                diag += " | test_net_shared: stats %r rows %d matched %d" % (st3, tot, hit)
+            ok = ok and good
+        dist.barrier()
         q.put((rank, bool(ok), diag if rank == 0 else ""))
         dist.destroy_process_group()
     except Exception as e:
@@ -164,7 +212,7 @@ def _shard_worker(rank, world, port, root_dir, q):
         q.put((rank, False, traceback.format_exc()[-600:]))
 
 
-def test_test_proposals_shards_images_over_ranks(tmp_path):
+def test_dataset_drivers_shard_images_over_ranks(tmp_path):
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -173,5 +221,5 @@ def test_test_proposals_shards_images_over_ranks(tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
-    res = _run_workers(procs, q, 150)
+    res = _run_workers(procs, q, 200)
     assert res == [(0, True, ""), (1, True, "")], res
