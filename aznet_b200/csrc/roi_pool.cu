@@ -676,8 +676,12 @@ __host__ __device__ __forceinline__ int band_row0(int k, int nb, int H, int rows
     return nb > 1 ? (int)(((long)k * (H - rows)) / (nb - 1)) : 0;
 }
 
-// EXT selects the experimental paths at compile time -- 0: none (the default kernel carries none of their code: with both
-// compiled in, the 64-register build spilled 80 bytes and ran 3 % slower), 1: width-grouped ROIs (1d), 2: row bands (1e).
+// EXT selects the experimental paths at compile time -- 0: none (the default kernel carries none of their code: with the
+// first two compiled in, the 64-register build spilled 80 bytes and ran 3 % slower), 1: width-grouped ROIs (1d), 2: row bands
+// (1e), 3: the two-level map (pool_bins_pairs), 4: bin bounds from the records of the geometry pre-pass.  3 and 4 lived in
+// the default instantiation for a while: no spills to speak of (8 bytes at SV = 8), but the same-box A/B of three builds
+// (tools/runs/gpu_r2bo.sh, profiles/r2_pool_regression_ab.txt) showed the default path 5 % (38x63) to 22 % (30x50, SV = 8)
+// slower at R = 20 000 with their code present -- the 64-register schedule of the hot loops is that fragile.
 template <bool BF16, int SV, int EXT = 0>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
@@ -778,7 +782,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         const long long t0 = clock64();
 #endif
         if (real && prestaged != item) stage_slice(img, row0, c0v);
-        if (EXT == 0 && geom != nullptr) pdl_grid_wait();    // the records are complete from here on (a no-op after the first time)
+        if (EXT == 4 && geom != nullptr) pdl_grid_wait();    // the records are complete from here on (a no-op after the first time)
         cp_async_wait_all();
         __syncthreads();
 #ifdef AZN_POOL_TRACE
@@ -820,7 +824,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
             __syncthreads();
         }
         // variant 3: the pair table behind the slice (see pool_bins_pairs); rows 2p, 2p+1 of the staged (key) slice
-        const bool pairs = EXT == 0 && (variant & 0x10000) != 0 && !exact && real;
+        const bool pairs = EXT == 3 && (variant & 0x10000) != 0 && !exact && real;
         const int pair_off = ((cells_p + 1) & ~1) * SV;       // uint4 units
         if (pairs) {
             const int n_pv = (SH >> 1) * row_step;
@@ -839,7 +843,7 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         auto pool_one = [&](const int r, const unsigned gw) {
             unsigned gb = 0;                                 // lanes 0..6: packed h bounds of bin row `lane`; 7..13: w bounds
             int mh;                                          // the tallest bin of the ROI (warp-uniform): selects the fixed-height variant
-            if (EXT == 0 && geom != nullptr) {               // lane k < 16 holds word k of the ROI's record
+            if (EXT == 4 && geom != nullptr) {               // lane k < 16 holds word k of the ROI's record
                 const bool ok = real && (int)__shfl_sync(0xffffffffu, gw, 14) == img;
                 if (ok && lane < 2 * ST_P) gb = gw;
                 mh = ok ? (int)__shfl_sync(0xffffffffu, gw, 15) : 0;
@@ -1040,20 +1044,29 @@ roi_pool_keys_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
         // ROIs are handed out dynamically (shared cursor): their cost varies by an order of magnitude with
         // their size, and a static deal leaves a tail of one big ROI per item.
         // (with the geometry pre-pass: the NEXT ROI's record is fetched while the current one is pooled)
-        auto fetch = [&](const int at) -> unsigned {
-            if (EXT != 0 || geom == nullptr || at >= hi || lane >= 16) return 0u;
-            return reinterpret_cast<const unsigned *>(geom)[(size_t)(perm ? perm[at] : at) * 16 + lane];
-        };
         int ri = lo + warp;
-        unsigned gw = fetch(ri);
-        while (ri < hi) {
-            int nxt = 0;
-            if (lane == 0) nxt = atomicAdd(&s_next, 1);
-            nxt = __shfl_sync(0xffffffffu, nxt, 0);
-            const unsigned gw_next = fetch(nxt);
-            pool_one(perm ? perm[ri] : ri, gw);
-            ri = nxt;
-            gw = gw_next;
+        if (EXT == 4 && geom != nullptr) {
+            auto fetch = [&](const int at) -> unsigned {
+                if (at >= hi || lane >= 16) return 0u;
+                return reinterpret_cast<const unsigned *>(geom)[(size_t)(perm ? perm[at] : at) * 16 + lane];
+            };
+            unsigned gw = fetch(ri);
+            while (ri < hi) {
+                int nxt = 0;
+                if (lane == 0) nxt = atomicAdd(&s_next, 1);
+                nxt = __shfl_sync(0xffffffffu, nxt, 0);
+                const unsigned gw_next = fetch(nxt);
+                pool_one(perm ? perm[ri] : ri, gw);
+                ri = nxt;
+                gw = gw_next;
+            }
+        } else {
+            while (ri < hi) {
+                pool_one(perm ? perm[ri] : ri, 0u);
+                int nxt = 0;
+                if (lane == 0) nxt = atomicAdd(&s_next, 1);
+                ri = __shfl_sync(0xffffffffu, nxt, 0);
+            }
         }
 #ifdef AZN_POOL_TRACE
         const long long t4 = clock64();
@@ -1480,7 +1493,8 @@ int g_pool_variant = 2;        // keys kernel: 1 generic loop nest, 2 fixed-heig
                                // (profiles/README.md, negative results of round 2)
 
 constexpr size_t ST_SMEM_BUDGET = 216 * 1024;      // dynamic shared memory the staged kernel may ask for
-constexpr size_t ST_SMEM_MAX = 227 * 1024 - 256;   // ... the default keys kernel with its pair table (its static shared memory is < 64 bytes)
+constexpr size_t ST_SMEM_MAX = 227 * 1024 - 256;   // ... the keys kernel with its pair table (EXT = 3; its static shared memory is < 64 bytes)
+constexpr bool POOL_GEOM_AUTO = false;             // default route from 4096 ROIs: with (true) or without the geometry pre-pass
 
 // Staged-kernel launch (see roi_pool_staged_kernel).  `nhwc` is the channels-last map; returns AZN_OK after a
 // launch, or 1 when the configuration is outside the staged kernel's domain (caller takes the direct kernel).
@@ -1560,7 +1574,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         static bool attr_set = false;                                                                                    \
         if (!attr_set) {                                                                                                 \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)ST_SMEM_MAX));                                                            \
+                                          (int)ST_SMEM_BUDGET));                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
         roi_pool_keys_kernel<kBf16, SVV><<<grid2, ST_THREADS, smem2, s>>>(                                               \
@@ -1633,11 +1647,14 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
     const bool use_pairs = MODE == 0 && !grouped && g_pool_variant == 2 && (g_pool_debug == 4 || g_pool_debug == 6) && H >= 2 &&
                        smem_pairs <= ST_SMEM_MAX;
     if (use_pairs) smem = smem_pairs;
-    // geometry pre-pass (roi_geom_kernel): needs the 64 bytes per ROI of workspace; azn_roi_pool_tune(8xx) goes without (A/B).
-    // MEASURED (same box, bf16, 38x63): R = 20 000 0.2875 vs 0.2948 ms, R = 8000 0.127 vs 0.131, R = 2000 0.047 vs 0.046 (the
-    // extra launch) -- a quarter fewer warp instructions buys 2.5 %: the kernel is not issue-bound.  Used from 4096 ROIs.
+    // geometry pre-pass (roi_geom_kernel + the EXT = 4 instantiation): needs the 64 bytes per ROI of workspace.
+    // azn_roi_pool_tune(9xx) switches it on, (8xx) off; POOL_GEOM_AUTO says what the default does from 4096 ROIs.
+    // MEASURED while its code sat in the default instantiation (same box, bf16, 38x63): R = 20 000 0.2875 vs 0.2948 ms,
+    // R = 8000 0.127 vs 0.131, R = 2000 0.047 vs 0.046 (the extra launch) -- a quarter fewer warp instructions bought 2.5 %
+    // there, but that build as a whole was 5-22 % behind the one without the code (see the note on EXT above).
     uint4 *geom = nullptr;
-    if (MODE == 0 && !grouped && g_pool_debug != 8 && group_ws && group_bytes >= geom_ws_bytes(R_cap) && R_cap >= 4096 &&
+    const bool want_geom = g_pool_debug == 9 || (POOL_GEOM_AUTO && g_pool_debug != 8);
+    if (MODE == 0 && !grouped && !use_pairs && want_geom && group_ws && group_bytes >= geom_ws_bytes(R_cap) && R_cap >= 4096 &&
         ((uintptr_t)group_ws % 16 == 0)) {
         geom = (uint4 *)group_ws;
         roi_geom_kernel<<<(unsigned)((R_cap + 255) / 256), 256, 0, s>>>(rois, n_rois, R_cap, n_img, H, W, scale, geom);
@@ -1661,8 +1678,12 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
         static bool attr_set = false;                                                                                    \
         if (!attr_set) {                                                                                                 \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)ST_SMEM_MAX));                                                            \
+                                          (int)ST_SMEM_BUDGET));                                                         \
             AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)ST_SMEM_BUDGET));                                                         \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)ST_SMEM_MAX));                                                            \
+            AZN_CUDA(cudaFuncSetAttribute(roi_pool_keys_kernel<kBf16, SVV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)ST_SMEM_BUDGET));                                                         \
             attr_set = true;                                                                                             \
         }                                                                                                                \
@@ -1672,15 +1693,18 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
                                     (uint4 *)out, n_buckets, (int)nchunk, nslices, 2 + (g_pool_debug << 8), goff, gdesc, \
                                     no_bands, (const uint4 *)nullptr));                                                  \
         else if (geom)                                                                                                   \
-            AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV>, dim3(grid), dim3(ST_THREADS), smem, s,             \
+            AZN_CUDA(azn_launch_pdl(roi_pool_keys_kernel<kBf16, SVV, 4>, dim3(grid), dim3(ST_THREADS), smem, s,          \
                                     (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale,          \
                                     (uint4 *)out, n_buckets, (int)nchunk, nslices,                                       \
-                                    (g_pool_variant >= 2 ? 2 : 1) | (use_pairs ? 0x10000 : 0), nullptr, nullptr, no_bands, \
-                                    (const uint4 *)geom));                                                               \
+                                    (g_pool_variant >= 2 ? 2 : 1), nullptr, nullptr, no_bands, (const uint4 *)geom));    \
+        else if (use_pairs)                                                                                              \
+            roi_pool_keys_kernel<kBf16, SVV, 3><<<grid, ST_THREADS, smem, s>>>(                                          \
+                (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,     \
+                (int)nchunk, nslices, (g_pool_variant >= 2 ? 2 : 1) | 0x10000, nullptr, nullptr, no_bands);              \
         else                                                                                                             \
             roi_pool_keys_kernel<kBf16, SVV><<<grid, ST_THREADS, smem, s>>>(                                             \
                 (const uint4 *)nhwc, n_img, H, W, L, rois, n_rois, R_cap, off, perm, scale, (uint4 *)out, n_buckets,     \
-                (int)nchunk, nslices, (g_pool_variant >= 2 ? 2 : 1) | (use_pairs ? 0x10000 : 0), nullptr, nullptr, no_bands); \
+                (int)nchunk, nslices, (g_pool_variant >= 2 ? 2 : 1), nullptr, nullptr, no_bands);                        \
     } while (0)
     if (MODE == 0) {
         if (sv == 8) AZN_KEY_LAUNCH(8); else if (sv == 4) AZN_KEY_LAUNCH(4); else AZN_KEY_LAUNCH(2);

@@ -83,7 +83,9 @@ size_t azn_roi_pool_workspace_bytes(int n_img, int C, int H, int W, int layout, 
  * staged kernel's pooling loop (1 generic loop nest, 2 fixed-height column reduces = default, 3 / 4 ROIs grouped by width:
  * kept for A/B, measured slower); + 100: the grouped loop with its stores disabled (profiling only); + 200: 64-byte
  * slices even where 128-byte ones fit; + 300: row bands of 128-byte slices for maps too tall for shared memory (A/B,
- * measured slower). */
+ * measured slower); + 400 / + 600: two-level map (slice + row-pair table; 600: with 64-byte slices); + 900: bin bounds from
+ * a geometry pre-pass from 4096 ROIs (+ 800: never) -- both A/B variants with kernel instantiations of their own, measured
+ * no faster. */
 void azn_roi_pool_tune(int mode);
 int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                      const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,

@@ -122,9 +122,10 @@ def test_roi_pool_device_count_bad_index_and_empty(dev, O, pool_mode):
 
 @pytest.mark.parametrize("n_img", [1, 3])
 def test_roi_pool_geometry_prepass_large_R(dev, O, n_img):
-    """From 4096 ROIs on the staged NHWC kernel takes the ROIs' bin bounds from the records of a pre-pass (roi_geom_kernel)
-    instead of deriving them once per channel slice: same device functions, so the same bits -- against the oracle, and
-    against the same kernel without the pre-pass (azn_roi_pool_tune(822)); edge ROIs and bad batch indices included."""
+    """The geometry pre-pass variant of the staged NHWC kernel (azn_roi_pool_tune(922), from 4096 ROIs: the ROIs' bin bounds come
+    from the records of roi_geom_kernel instead of being derived once per channel slice; an A/B variant with an instantiation of
+    its own): same device functions, so the same bits -- against the oracle, and against the default kernel without the
+    pre-pass; edge ROIs and bad batch indices included."""
     from aznet_b200 import _lib, ops
     C = 64
     feat = synth.make_conv_maps(n_img, C, 38, 63, seed=21)
@@ -140,15 +141,16 @@ def test_roi_pool_geometry_prepass_large_R(dev, O, n_img):
     lib = _lib.lib()
     try:
         outs = {}
-        for mode in (22, 822):
+        for mode in (22, 922):
             lib.azn_roi_pool_tune(mode)
             outs[mode] = ops.roi_pool(f, r, layout="NHWC").cpu().numpy()
             outs[(mode, "bf16")] = ops.roi_pool(f.to(torch.bfloat16), r, layout="NHWC").float().cpu().numpy()
     finally:
         lib.azn_roi_pool_tune(20)
     assert np.array_equal(outs[22].view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
-    assert np.array_equal(outs[22].view(np.uint32), outs[822].view(np.uint32))
-    assert np.array_equal(outs[(22, "bf16")].view(np.uint32), outs[(822, "bf16")].view(np.uint32))
+    assert np.array_equal(outs[22].view(np.uint32), outs[922].view(np.uint32))
+    assert np.array_equal(outs[922].view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+    assert np.array_equal(outs[(22, "bf16")].view(np.uint32), outs[(922, "bf16")].view(np.uint32))
 
 
 @pytest.mark.parametrize("n_img,C,hw", [(1, 512, (38, 63)), (3, 64, (38, 63)), (2, 64, (75, 40)), (64, 64, (38, 63))])
