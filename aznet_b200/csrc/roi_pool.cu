@@ -376,6 +376,10 @@ template <> struct KeyOps<false> {
 // is a template parameter and a lane whose bin is shorter re-reads its last row (max is idempotent), so that a
 // column reduce is straight-line code: MH loads at precomputed row offsets and (MH+1)/2 packed max instructions.
 // Column re-use between neighbouring bins is kept (see the generic path).
+#ifndef AZN_POOL_PW_UNROLL
+#define AZN_POOL_PW_UNROLL 7          // bins of a bin row per loop body of pool_bins_fixed (A/B: 1 = not unrolled)
+#endif
+constexpr int POOL_PW_UNROLL = AZN_POOL_PW_UNROLL;
 template <typename K, int MH, bool PLAIN>
 __device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbase, int nh, int rot, int row_step, int sv, unsigned gb,
                                                 bool phv, bool valid, uint4 *__restrict__ optr, int L) {
@@ -398,7 +402,7 @@ __device__ __forceinline__ void pool_bins_fixed(const uint4 *__restrict__ rowbas
     const unsigned a0 = PLAIN ? 0u : K::lowest();
     int w_cached = -1;                                       // warp-uniform
     uint4 cache = make_uint4(a0, a0, a0, a0);
-#pragma unroll
+#pragma unroll POOL_PW_UNROLL
     for (int pw = 0; pw < ST_P; ++pw) {
         const unsigned wb = __shfl_sync(0xffffffffu, gb, ST_P + pw);
         const int ws = wb & 0xffff, we = (int)(wb >> 16);    // warp-uniform
