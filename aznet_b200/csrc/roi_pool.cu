@@ -189,6 +189,75 @@ roi_pool_nhwc_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, in
     }
 }
 
+// ---- (1') direct kernel, one CTA per ROI ---------------------------------------------------------------------------
+// Same arithmetic as roi_pool_nhwc_kernel (the same roi_geom / bin_bounds / Ops::take in the same h-major, w-minor order
+// per bin: the same bits), different mapping: a CTA owns a whole ROI, warp k pools bin row k -- its PW bins one after the
+// other.  In kernel (1) the bin rows of a ROI are items of their own and land on different SMs; neighbouring bin rows
+// overlap by a map row (a bin spans floor .. ceil of its bounds: 1.4 - 1.75 x the ROI's rows in total for the small ROIs
+// of the deep search levels) and every one of those rows comes through L2 again.  Here the seven bin rows run side by
+// side on ONE SM: a row shared by two of them is an L1 hit (or merges with the miss in flight) for the second, as the
+// column shared by two neighbouring bins of a row already is in kernel (1).  One geometry pass and one barrier per ROI
+// instead of per bin row.
+template <typename Ops, int NV>
+__global__ void __launch_bounds__(256)
+roi_pool_nhwc_roi_kernel(const uint4 *__restrict__ feat, int n_img, int H, int W, int L,
+                         const float *__restrict__ rois, const int32_t *__restrict__ n_rois, int R_cap,
+                         int PH, int PW, float scale, uint4 *__restrict__ out) {
+    pdl_enter();
+    __shared__ int s_ws[2][POOL_MAX_PW], s_we[2][POOL_MAX_PW], s_hs[2][POOL_MAX_PW], s_he[2][POOL_MAX_PW], s_b[2];
+    const int R = n_rois ? min(*n_rois, R_cap) : R_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const size_t row_stride = (size_t)W * L;      // vectors per map row
+    int buf = 0;
+    for (int r = blockIdx.x; r < R; r += gridDim.x, buf ^= 1) {
+        if ((int)threadIdx.x < PW + PH) {
+            const RoiGeom q = roi_geom(rois + (size_t)r * 5, scale, PH, PW);
+            int lo, hi;
+            if ((int)threadIdx.x < PW) {
+                bin_bounds(threadIdx.x, q.bin_w, q.start_w, W, lo, hi);
+                s_ws[buf][threadIdx.x] = lo;
+                s_we[buf][threadIdx.x] = hi;
+                if (threadIdx.x == 0) s_b[buf] = (q.b < 0 || q.b >= n_img) ? -1 : q.b;
+            } else {
+                const int p = (int)threadIdx.x - PW;
+                bin_bounds(p, q.bin_h, q.start_h, H, lo, hi);
+                s_hs[buf][p] = lo;
+                s_he[buf][p] = hi;
+            }
+        }
+        __syncthreads();                          // double-buffered geometry: one barrier per ROI
+        const int b = s_b[buf];
+        const uint4 *base = feat + (size_t)(b < 0 ? 0 : b) * H * row_stride;
+        for (int ph = warp; ph < PH; ph += nwarps) {
+            const int hs = s_hs[buf][ph], he = s_he[buf][ph];
+            uint4 *orow = out + ((size_t)r * PH + ph) * PW * L;
+            for (int pw = 0; pw < PW; ++pw) {
+                const int ws = s_ws[buf][pw], we = s_we[buf][pw];
+                const bool empty = b < 0 || he <= hs || we <= ws;
+                for (int v0 = lane; v0 < L; v0 += 32 * NV) {
+                    uint4 acc[NV];
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) acc[j] = empty ? make_uint4(0u, 0u, 0u, 0u) : Ops::lowest();
+                    if (!empty) {
+                        for (int h = hs; h < he; ++h) {
+                            const uint4 *p = base + (size_t)h * row_stride + (size_t)ws * L + v0;
+#pragma unroll 4
+                            for (int w = ws; w < we; ++w, p += L) {
+#pragma unroll
+                                for (int j = 0; j < NV; ++j)
+                                    if (v0 + 32 * j < L) Ops::take(acc[j], ld_map(p + 32 * j));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        if (v0 + 32 * j < L) st_stream(orow + (size_t)pw * L + v0 + 32 * j, acc[j]);
+                }
+            }
+        }
+    }
+}
+
 // ---- (1b) staged kernel: the map slice lives in shared memory ---------------------------------
 // With many ROIs per image the L2 -> SM traffic of kernel (1) (every bin re-reads its window, ~4 map
 // cells per output vector) is what bounds it, not HBM.  Here one CTA stages a channel slice of ONE
@@ -1725,7 +1794,7 @@ int launch_staged(const void *nhwc, int n_img, int H, int W, int L, const float 
 
 // The staged kernel pays one slice load per (image, chunk): worth it when an image has many ROIs.
 bool want_staged(int mode, int n_img, int H, int W, int PH, int PW, const int32_t *n_rois, int R_cap, bool have_bucket_ws) {
-    if (mode == 1) return false;
+    if (mode == 1 || mode == 3) return false;
     if (PH != ST_P || PW != ST_P || H > 65535 || W > 65535) return false;
     if (n_img > 1 && !have_bucket_ws) return false;
     if (mode == 2) return true;
@@ -1753,7 +1822,7 @@ extern "C" int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, in
                                    float spatial_scale, void *out, int32_t *argmax, void *workspace,
                                    size_t workspace_bytes, int kernel_choice, azn_stream_t stream) {
     if (R_cap == 0) return AZN_OK;
-    AZN_REQUIRE(kernel_choice >= 0 && kernel_choice <= 2, "azn_roi_pool_fwd_ex: kernel_choice must be 0 (auto), 1 (direct) or 2 (staged)");
+    AZN_REQUIRE(kernel_choice >= 0 && kernel_choice <= 3, "azn_roi_pool_fwd_ex: kernel_choice must be 0 (auto), 1 (direct), 2 (staged) or 3 (direct, one CTA per ROI)");
     AZN_REQUIRE(feat && rois && out, "azn_roi_pool_fwd: null pointer");
     AZN_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R_cap >= 0,
                 "azn_roi_pool_fwd: bad shape n_img=%d C=%d H=%d W=%d PH=%d PW=%d R=%d", n_img, C, H, W, PH, PW, R_cap);
@@ -1786,8 +1855,20 @@ extern "C" int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, in
         const int nv = L >= 128 ? 4 : (L >= 64 ? 2 : 1);
         const uint4 *f = (const uint4 *)feat;
         uint4 *o = (uint4 *)out;
+        // kernel_choice 3 (or azn_roi_pool_tune(5xx)): one CTA per ROI, one warp per bin row (roi_pool_nhwc_roi_kernel) -- for
+        // MANY SMALL ROIs (the deep levels of the search: level 5 0.0325 -> 0.0254 ms, level 4 0.0242 -> 0.0227 per 64 images);
+        // with few large ROIs the seven long serial bin rows of a CTA lose to the bin-row items of kernel (1) (level 2:
+        // 0.051 -> 0.135 ms), and the library cannot see the ROI sizes from the host: the caller says which it has.
+        const bool per_roi = (kernel_choice == 3 || g_pool_debug == 5) && PH <= POOL_MAX_PW && PW + PH <= 32;
+        const int nwarps_r = PH < 8 ? PH : 8;
+        const long blocks_r = std::min<long>((long)R_cap, (long)sms * 16);
 #define AZN_POOL_LAUNCH(OPS, NVV) \
-        AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_kernel<OPS, NVV>, dim3((unsigned)blocks), dim3(nwarps * 32), 0, s, f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o, 0, 0, 1.f))
+        do { \
+            if (per_roi) \
+                AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_roi_kernel<OPS, NVV>, dim3((unsigned)blocks_r), dim3(nwarps_r * 32), 0, s, f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o)); \
+            else \
+                AZN_CUDA(azn_launch_pdl(roi_pool_nhwc_kernel<OPS, NVV>, dim3((unsigned)blocks), dim3(nwarps * 32), 0, s, f, n_img, H, W, L, rois, n_rois, R_cap, PH, PW, spatial_scale, o, 0, 0, 1.f)); \
+        } while (0)
         if (dtype == AZN_DTYPE_F32) {
             if (nv == 4) AZN_POOL_LAUNCH(OpsF32, 4); else if (nv == 2) AZN_POOL_LAUNCH(OpsF32, 2); else AZN_POOL_LAUNCH(OpsF32, 1);
         } else {

@@ -29,6 +29,13 @@ from . import ops
 # The head's three output layers: "mma" = azn_az_heads_forward (small mma.sync kernel), "gemm" = the persistent tcgen05
 # kernel with the AZ-head epilogue (azn_fc_forward); same arithmetic, A/B switch for benchmarks.
 HEADS_KERNEL = "mma"
+# Levels of the search whose ROI pool asks for the shared-memory-staged kernel (per-image buckets, azn_roi_pool_fwd_ex) instead
+# of the direct L2-fed one: an A/B switch for benchmarks (bench.py --pool-staged-levels); same bits either way.
+POOL_STAGED_LEVELS = ()
+# From this level on the ROI pool runs with one CTA per ROI (azn_roi_pool_fwd_ex kernel_choice 3): the deep levels hold many
+# small ROIs, whose seven bin rows share map rows through L1 when they run on one SM (level 5: 0.0325 -> 0.0254 ms, level 4:
+# 0.0242 -> 0.0227 per 64 images; level 3 is 9 % slower that way and level 2, nine large ROIs per image, 2.6 x).  0: never.
+POOL_PER_ROI_FROM_LEVEL = 4
 
 
 def im_scale_for(im_h, im_w, scales=(600,), max_size=1000):
@@ -215,7 +222,9 @@ class SearchEngine:
         ev = self._ev
         t = ev()
         pool = ops.roi_pool(conv_nhwc, self.rois[:mc], hd.pooled, self.spatial_scale, layout="NHWC",
-                            n_rois=self.m_total, out=self.pool5[:mc].view(mc, hd.pooled, hd.pooled, hd.C))
+                            n_rois=self.m_total, out=self.pool5[:mc].view(mc, hd.pooled, hd.pooled, hd.C),
+                            staged=True if level in POOL_STAGED_LEVELS else None,
+                            per_roi=bool(POOL_PER_ROI_FROM_LEVEL) and level >= POOL_PER_ROI_FROM_LEVEL and level not in POOL_STAGED_LEVELS)
         a = pool.view(mc, -1)
         t = ev(level, "roi_pool", t, midx)
         ops.fc_forward(a, hd.w6, hd.b6, L.ACT_RELU, m_live=self.m_total, out=self.h6[:mc])

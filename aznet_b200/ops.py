@@ -26,7 +26,7 @@ def _need_cuda(*ts):
 
 def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_scale: float = 0.0625,
              layout: str = "NCHW", n_rois: torch.Tensor | None = None, want_argmax: bool = False,
-             out: torch.Tensor | None = None, staged: bool | None = None):
+             out: torch.Tensor | None = None, staged: bool | None = None, per_roi: bool = False):
     """ROI max pooling (roi_pooling_layer.cpp:46-125).  feat [n,C,H,W] (NCHW) or [n,H,W,C] (NHWC),
     f32 or bf16; rois f32 [R,5].  Returns pooled [R,C,P,P] (NCHW) or [R,P,P,C] (NHWC)."""
     _need_cuda(feat, rois, n_rois)
@@ -44,9 +44,11 @@ def roi_pool(feat: torch.Tensor, rois: torch.Tensor, pooled: int = 7, spatial_sc
     lay = L.LAYOUT_NCHW if layout == "NCHW" else L.LAYOUT_NHWC
     nbytes = L.lib().azn_roi_pool_workspace_bytes(n, Cc, H, W, lay, dt, R)
     ws = _scratch(feat.device, nbytes) if nbytes else None
-    if staged is not None:                     # many ROIs per image with a device-side count: ask for the staged kernel
+    if staged is not None or per_roi:          # many ROIs per image with a device-side count: ask for the staged kernel;
+        # per_roi: many SMALL ROIs (deep search levels): the direct kernel with one CTA per ROI (NHWC)
+        choice = 3 if (per_roi and layout == "NHWC") else (2 if staged else 1)
         L.check(L.lib().azn_roi_pool_fwd_ex(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,
-                                            spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, 2 if staged else 1, _stream()),
+                                            spatial_scale, _ptr(out), _ptr(amax), _ptr(ws), nbytes, choice, _stream()),
                 "azn_roi_pool_fwd_ex")
     else:
         L.check(L.lib().azn_roi_pool_fwd(_ptr(feat), n, Cc, H, W, lay, dt, _ptr(rois), _ptr(n_rois), R, pooled, pooled,

@@ -358,6 +358,9 @@ def main():
     ap.add_argument("--streams", type=int, default=4, choices=(1, 2, 3, 4, 6, 8),
                     help="batches in flight for the device-resident figure: 2 = two engines on two CUDA streams, so that the latency-bound "
                          "kernels of one batch (ROI pool, decode / subdivide, selection) run next to the other batch's tensor-core GEMMs")
+    ap.add_argument("--pool-tune", type=int, default=-1, help="A/B: azn_roi_pool_tune code for the whole run (500: direct kernel with one CTA per ROI)")
+    ap.add_argument("--pool-per-roi-from", type=int, default=-1, help="A/B: first search level whose ROI pool runs one CTA per ROI (0: never; default: engine.POOL_PER_ROI_FROM_LEVEL)")
+    ap.add_argument("--pool-staged-levels", default="", help="A/B: search levels (comma list, 1-based) whose ROI pool takes the staged kernel")
     ap.add_argument("--heads", default="mma", choices=("mma", "gemm"), help="output layers of the head: small mma.sync kernel or the persistent GEMM (A/B)")
     ap.add_argument("--host-narrow", default="auto", choices=("auto", "on", "off", "split"),
                     help="e2e call: round the f32 host maps to bf16 on the host cores before the upload; split: a third of the images cross "
@@ -392,6 +395,11 @@ def main():
     _lib.lib().azn_set_pdl(0 if args.no_pdl else 1)
     _lib.lib().azn_set_coop(0 if args.no_coop else 1)
     engine.HEADS_KERNEL = args.heads
+    engine.POOL_STAGED_LEVELS = tuple(int(x) for x in args.pool_staged_levels.split(",") if x)
+    if args.pool_per_roi_from >= 0:
+        engine.POOL_PER_ROI_FROM_LEVEL = args.pool_per_roi_from
+    if args.pool_tune >= 0:
+        _lib.lib().azn_roi_pool_tune(args.pool_tune)
     _lib.lib().azn_az_heads_tune(1 if (args.no_graph or args.streams == 1) else 0)
 
     if args.job:

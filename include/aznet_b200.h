@@ -92,7 +92,9 @@ int azn_roi_pool_fwd(const void *feat, int n_img, int C, int H, int W, int layou
                      float spatial_scale, void *out, int32_t *argmax, void *workspace,
                      size_t workspace_bytes, azn_stream_t stream);
 /* The same with the kernel choice as an ARGUMENT (0 automatic, 1 direct kernels only, 2 staged kernel whenever it
- * applies) instead of the process-wide azn_roi_pool_tune setting: what callers that run several host threads use. */
+ * applies, 3 direct kernel with one CTA per ROI: for many SMALL ROIs with a device-side count, the deep levels of the
+ * search -- NHWC only, same bits) instead of the process-wide azn_roi_pool_tune setting: what callers that run several
+ * host threads use. */
 int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, int W, int layout, int dtype,
                         const float *rois, const int32_t *n_rois, int R_cap, int PH, int PW,
                         float spatial_scale, void *out, int32_t *argmax, void *workspace,

@@ -35,7 +35,7 @@ def _layer_feat():
     return feat
 
 
-@pytest.mark.parametrize("mode", [0, 1, 22, 322, 42], ids=["auto", "direct", "staged", "staged_bands", "staged_grouped"])
+@pytest.mark.parametrize("mode", [0, 1, 501, 22, 322, 42], ids=["auto", "direct", "direct_per_roi", "staged", "staged_bands", "staged_grouped"])
 def test_roi_pool_equals_reference_layer_golden(dev, golden, mode):
     """azn_roi_pool_fwd == ROIPoolingLayer<float>::Forward_cpu of the reference's own source, bit for bit: values
     and argmax (NCHW f32, the layer's blob layout), NHWC f32, and bf16 (max commutes with the monotone rounding)."""

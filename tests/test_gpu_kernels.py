@@ -47,9 +47,9 @@ def _edge_rois(n_img):
 
 
 # ------------------------------------------------------------------------------- ROI pooling
-@pytest.fixture(params=[0, 1, 22, 422, 322, 42], ids=["auto", "direct", "staged", "staged_pairs", "staged_bands", "staged_grouped"])
+@pytest.fixture(params=[0, 1, 501, 22, 422, 322, 42], ids=["auto", "direct", "direct_per_roi", "staged", "staged_pairs", "staged_bands", "staged_grouped"])
 def pool_mode(request):
-    """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, shared-memory-staged kernel with the
+    """Kernel choice of azn_roi_pool_fwd: automatic, direct (L2-fed) kernels only, the direct kernel with one CTA per ROI (501), shared-memory-staged kernel with the
     per-ROI loop, the same over a two-level map (slice + row-pair table where both fit: an A/B variant), the same with row bands of 128-byte slices when the whole map does not fit (the 38x63 maps below: an
     A/B variant), staged kernel with the ROIs grouped by width whenever that path applies."""
     from aznet_b200 import _lib
@@ -118,6 +118,37 @@ def test_roi_pool_device_count_bad_index_and_empty(dev, O, pool_mode):
     assert z.shape[0] == 0
     with pytest.raises(ValueError):
         ops.roi_pool(torch.zeros((1, 4, 4, 3), device=dev), r, layout="NHWC")     # C*4 % 16 != 0
+
+
+def test_roi_pool_per_roi_kernel_choice_same_bits(dev, O):
+    """azn_roi_pool_fwd_ex(kernel_choice = 3): the direct kernel with one CTA per ROI (what the search engine asks for on its
+    deep levels: many small ROIs, device-side count) -- same bits as the default direct kernel and as the oracle, f32 and bf16,
+    rows past the live count untouched, edge ROIs and a bad batch index included."""
+    from aznet_b200 import ops
+    n_img, C = 3, 64
+    feat = synth.make_conv_maps(n_img, C, 30, 50, seed=11)
+    feat[1] -= 0.25
+    rois = np.vstack([synth.make_rois(700, 600, 1000, seed=9, n_img=n_img), _edge_rois(n_img)]).astype(np.float32)
+    rois[:, 1:] *= 0.8                                 # the voc.yml scale: 30 x 50 maps
+    rois[5, 0] = n_img + 1                             # bad batch index -> zero row
+    ok = rois.copy()
+    ok[5, 0] = 0
+    live = rois.shape[0] - 13
+    ref = O.roi_pool_fwd(feat, ok).transpose(0, 2, 3, 1).copy()
+    ref[5] = 0
+    f = torch.from_numpy(feat).to(dev).permute(0, 2, 3, 1).contiguous()
+    r = torch.from_numpy(rois).to(dev)
+    n = torch.tensor([live], dtype=torch.int32, device=dev)
+    for fm in (f, f.to(torch.bfloat16)):
+        outs = []
+        for per_roi in (False, True):
+            out = torch.full((rois.shape[0], 7, 7, C), 7.0, dtype=fm.dtype, device=dev)
+            ops.roi_pool(fm, r, layout="NHWC", n_rois=n, out=out, staged=None if not per_roi else None, per_roi=per_roi)
+            outs.append(out.float().cpu().numpy())
+        assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+        assert np.all(outs[1][live:] == 7.0)
+        if fm.dtype == torch.float32:
+            assert np.array_equal(outs[1][:live].view(np.uint32), np.ascontiguousarray(ref[:live]).view(np.uint32))
 
 
 @pytest.mark.parametrize("n_img", [1, 3])
