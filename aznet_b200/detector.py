@@ -25,6 +25,16 @@ from . import ops
 from .engine import im_scale_for
 
 
+
+# ROI-pool kernel of the detection step: "staged" (shared-memory-staged kernel over per-image buckets: ~300 proposals per
+# image), "direct" (the L2-fed kernel, one CTA per bin row) or "per_roi" (the L2-fed kernel, one CTA per ROI): same bits,
+# an A/B switch for benchmarks (tools/detbench.py --pool).
+POOL_KERNEL = "staged"
+
+
+def pool_kwargs():
+    return {"staged": dict(staged=True), "direct": dict(staged=False), "per_roi": dict(per_roi=True)}[POOL_KERNEL]
+
 class DetectEngine:
     """Buffers + launch sequence of the batched detection step.  One instance per (n_img, image shape, cap_boxes)."""
 
@@ -114,7 +124,7 @@ class DetectEngine:
         else:
             assert conv_nhwc.dtype == torch.bfloat16 and conv_nhwc.shape[0] == self.n_img and conv_nhwc.is_contiguous()
             pool = ops.roi_pool(conv_nhwc, self.rois, hd.pooled, self.spatial_scale, layout="NHWC", n_rois=self.m_total,
-                                out=self.pool5.view(mc, hd.pooled, hd.pooled, hd.C), staged=True)
+                                out=self.pool5.view(mc, hd.pooled, hd.pooled, hd.C), **pool_kwargs())
         ops.fc_forward(pool.view(mc, -1), hd.w6, hd.b6, L.ACT_RELU, m_live=self.m_total, out=self.h6)
         ops.fc_forward(self.h6, hd.w7, hd.b7, L.ACT_RELU, m_live=self.m_total, out=self.h7)
         ops.fc_forward(self.h7, hd.wo, hd.bo, L.ACT_SOFTMAX_BBOX, self.C, m_live=self.m_total, out=self.out[:, :self.n_out])

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--classes", type=int, default=81)
+    ap.add_argument("--pool", default="staged", choices=("staged", "direct", "per_roi"), help="ROI-pool kernel of the detection step (A/B)")
     ap.add_argument("--cpu-images", type=int, default=2)
     args = ap.parse_args()
     import torch
@@ -39,6 +40,7 @@ def main():
     _lib.build()
     _lib.require_device()
     dev = torch.device("cuda:0")
+    detector.POOL_KERNEL = args.pool
     torch.cuda.set_device(dev)
     cfg = dict(B.CFG, batch_size=10000)                       # coco.yml: default SEAR.BATCH_SIZE
     azw = synth.make_az_weights(seed=3, zoom_bias=B.ZOOM_BIAS)
@@ -65,7 +67,7 @@ def main():
         det.prepare(eng.out_boxes, eng.out_count)
         ev[2].record()
         pool = ops.roi_pool(conv, det.rois, hd.pooled, det.spatial_scale, layout="NHWC", n_rois=det.m_total,
-                            out=det.pool5.view(mc, hd.pooled, hd.pooled, hd.C), staged=True)
+                            out=det.pool5.view(mc, hd.pooled, hd.pooled, hd.C), **detector.pool_kwargs())
         ev[3].record()
         ops.fc_forward(pool.view(mc, -1), hd.w6, hd.b6, _lib.ACT_RELU, m_live=det.m_total, out=det.h6)
         ev[4].record()
