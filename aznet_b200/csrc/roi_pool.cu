@@ -1850,7 +1850,7 @@ extern "C" int azn_roi_pool_fwd_ex(const void *feat, int n_img, int C, int H, in
         const long items = (long)R_cap * PH;
         const int nwarps = PW < 8 ? PW : 8;
         long blocks = items;
-        const long max_blocks = (long)sms * 16;
+        const long max_blocks = (long)sms * 16;     // (32 per SM measured the same: level 2's 4032 unequal items 0.0505 vs 0.0509 ms)
         if (blocks > max_blocks) blocks = max_blocks;
         const int nv = L >= 128 ? 4 : (L >= 64 ? 2 : 1);
         const uint4 *f = (const uint4 *)feat;
