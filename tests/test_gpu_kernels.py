@@ -143,7 +143,7 @@ def test_roi_pool_per_roi_kernel_choice_same_bits(dev, O):
         outs = []
         for per_roi in (False, True):
             out = torch.full((rois.shape[0], 7, 7, C), 7.0, dtype=fm.dtype, device=dev)
-            ops.roi_pool(fm, r, layout="NHWC", n_rois=n, out=out, staged=None if not per_roi else None, per_roi=per_roi)
+            ops.roi_pool(fm, r, layout="NHWC", n_rois=n, out=out, per_roi=per_roi)
             outs.append(out.float().cpu().numpy())
         assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
         assert np.all(outs[1][live:] == 7.0)
