@@ -230,6 +230,17 @@ def reference_entry_point(weights, threads, n_images=2):
                     "in fp32 on the host cores, AZ head, proposals.pkl"}
 
 
+def workload_config(world, job=0):
+    """The `config` object of BOTH arms (equal for equal --gpus / --job): what is computed, not how a given arm ran it --
+    an arm's own run details live beside it (`run` on the GPU arm, `cpu_baseline.sample` on the reference arm)."""
+    cfg = {"workload": WORKLOAD, "global_batch": world * BATCH,
+           "l2": "working set per step (216 MB bf16 weights + pooled rows) exceeds the 126 MB L2; inputs rotate over 2 distinct batches",
+           "parallelism": "image-sharded x%d, no collective on the hot path" % world}
+    if job:
+        cfg["job"] = "BASELINE config #5: %d images = %d batches of 64 sharded over %d rank(s)" % (job, job // BATCH, world)
+    return cfg
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores, same config / metric /
     unit.  One step = a bounded sample of 4 images of the 64-image batch."""
@@ -254,9 +265,9 @@ def run_reference(args):
         "impl": "reference", "metric": "AZ proposal images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the same workload description as the GPU arm's `config` (a subset of its keys, equal values); what this arm
-        # actually timed -- a bounded sample of that workload -- is stated in cpu_baseline.sample
-        "config": {"workload": WORKLOAD, "global_batch": args.gpus * BATCH},
+        # the GPU arm's `config`, key for key; what this arm actually timed -- a bounded sample of that workload -- is stated
+        # in cpu_baseline.sample
+        "config": workload_config(args.gpus, args.job),
         "regions_per_image": runner.regions / max(runner.images, 1),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": runner.kind,
                          "sample": "a step = a bounded sample of %d images of the 64-image batch; %d images in %.1f s (%s)" % (
@@ -615,15 +626,15 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.job else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "regions_per_image": regions,
-                       "l2": "working set per step (216 MB bf16 weights + pooled rows) exceeds the 126 MB L2; inputs rotate over 2 distinct batches",
-                       "launch": "eager" if args.no_graph else "CUDA graph replay of the whole level loop (static launch sequence, device-side counts), "
-                                 "%d batch(es) in flight on %d stream(s); roofline events from a second, host-launched, single-stream pass over the same steps" % (n_streams, n_streams),
-                       "parallelism": "image-sharded x%d, no collective on the hot path; %s" % (world, {
-                           None: "single rank",
-                           "peer": "every step's proposal lists are appended to rank 0's collection through a peer window (stores over NVLink by the "
-                                   "step's last kernel, azn_collect_proposals); the job ends with one 4-byte NCCL all_reduce as the fence, inside the timed region",
-                           "nccl": "one NCCL all_gather of all K steps' proposal lists at the end, inside the timed region"}[gather_route])},
+            "config": workload_config(world, args.job),
+            "run": {"regions_per_image": regions,
+                    "launch": "eager" if args.no_graph else "CUDA graph replay of the whole level loop (static launch sequence, device-side counts), "
+                              "%d batch(es) in flight on %d stream(s); roofline events from a second, host-launched, single-stream pass over the same steps" % (n_streams, n_streams),
+                    "lists_to_rank0": {
+                        None: "single rank",
+                        "peer": "every step's proposal lists are appended to rank 0's collection through a peer window (stores over NVLink by the "
+                                "step's last kernel, azn_collect_proposals); the job ends with one 4-byte NCCL all_reduce as the fence, inside the timed region",
+                        "nccl": "one NCCL all_gather of all K steps' proposal lists at the end, inside the timed region"}[gather_route]},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_rank": h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
@@ -652,8 +663,8 @@ def main():
                          "per_level": prof["levels"], "hbm_peak_gbs": hbm_peak},
         }
         if args.job:
-            line["config"]["job"] = "BASELINE config #5: %d images = %d batches of 64, %d per rank; lists -> rank 0: %s" % (
-                args.job, args.job // BATCH, args.steps, "peer window + closing fence" if gather_route == "peer" else "one NCCL all_gather at the end")
+            line["run"]["job"] = "%d batches of 64 per rank; lists -> rank 0: %s" % (
+                args.steps, "peer window + closing fence" if gather_route == "peer" else "one NCCL all_gather at the end")
         if world > 1:
             line["gather_ms"] = {"route": gather_route, "resident": gather_resident_ms, "e2e": gather_ms[0],
                                  "bytes_per_rank": int(sum(t.numel() * t.element_size() for c in collectors for t in (c.boxes, c.scores, c.counts)))}
