@@ -210,3 +210,27 @@ def test_host_f32_to_bf16_equals_the_device_rounding():
             assert int(buf[off % 16 + n:].view(torch.int16).abs().sum()) == 0 and int(buf[:off % 16].view(torch.int16).abs().sum()) == 0, "wrote outside"
     with pytest.raises(AssertionError):
         ops.host_f32_to_bf16(x, torch.zeros(3, dtype=torch.bfloat16))
+
+
+def test_reference_arm_line_contract():
+    """`bench.py --impl reference` (the arm the driver runs beside the GPU arm) needs no GPU: one JSON line with the GPU arm's
+    metric / unit / config object (bench.workload_config, key for key), `impl`, its own cpu_baseline and an e2e object
+    without copies."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--no-extra"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-800:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    sys.path.insert(0, root)
+    import bench
+    assert line["impl"] == "reference" and line["metric"] == "AZ proposal images/sec" and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["config"] == bench.workload_config(1)
+    assert set(bench.workload_config(2, 1024)) == set(bench.workload_config(1)) | {"job"}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
